@@ -1,0 +1,666 @@
+// tcgen05 / TMEM / TMA GEMM family for sm_100a (see gemm_tc.cuh).
+//
+// Kernel anatomy (one persistent CTA per SM, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D tiles (128B swizzle) into a STAGES-deep ring
+//   warp 1      MMA issuer:   one elected thread issues tcgen05.mma.cta_group::1.kind::f16
+//               (M=128, N=BN, K=16) x4 per 64-wide k-block; tcgen05.commit frees ring slots and
+//               publishes finished accumulators; also owns tcgen05.alloc / dealloc
+//   warps 2..5  epilogue: tcgen05.ld 32x32b (lane = output row) from one of two TMEM accumulator
+//               buffers, so the epilogue of tile i overlaps the main loop of tile i+1
+// Operands are K-major bf16: A tile 128 x 64, B tile BN x 64, both landing in the canonical
+// SWIZZLE_128B layout the UMMA shared-memory descriptors describe (8-row groups 1024 B apart).
+#include <cuda.h>
+
+#include "gemm_tc.cuh"
+#include "gemm_f32.cuh"
+
+namespace mocha {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle atom row
+constexpr int UMMA_K = 16;
+constexpr int TC_THREADS = 192;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int SMEM_BUDGET = 196 * 1024;
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a protocol bug becomes a trap (reported as a CUDA error) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (it == 64) t0 = clock64();
+    if (it > 64 && (it & 1023) == 0 && clock64() - t0 > 6000000000LL) {
+      printf("mocha tc kernel: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, K-major operand in SWIZZLE_128B canonical layout:
+//   start address >> 4 | LBO (ignored for swizzled K-major, 1) | SBO = 1024 B (8 rows x 128 B)
+//   | version 1 (sm_100) | layout type 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// work decomposition shared by both epilogues
+// ------------------------------------------------------------------------------------------------
+struct TcShape {
+  int nb;                  // independent row groups ("images"); 1 for a plain GEMM
+  int rows_out_per_b;      // output rows per image
+  int tiles_m_per_b;       // ceil(rows_out_per_b / 128)
+  long long src_rows_per_b;  // A rows per image in the (padded) source tensor
+  int taps;                // temporal taps (1 for a plain GEMM)
+  int kb_per_tap;          // k-blocks per tap
+  int tap_row_stride;      // A row shift per tap
+  int tiles_n;             // ceil(N / BN)
+  int tiles_per_unit;      // consecutive n-tiles handled by one unit
+  int units;               // tiles_m_total * splits
+  int tiles_m_total;
+};
+
+struct LinearEpi {
+  float* C;
+  int ldc;
+  int N;
+  const float* bias;
+  int bias_period;
+  const float* res;
+  int act;
+  struct State {};
+  __device__ __forceinline__ void unit_begin(State&) const {}
+  __device__ __forceinline__ void chunk(State&, long long row, bool row_ok, int col0, const uint32_t (&v)[32]) const {
+    if (!row_ok) return;
+    const float* brow = nullptr;
+    if (bias) brow = bias_period > 0 ? bias + (row % bias_period) * (long long)N : bias;
+    float* crow = C + row * (long long)ldc;
+    const float* rrow = res ? res + row * (long long)ldc : nullptr;
+    float o[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int c = col0 + j;
+      float x = __uint_as_float(v[j]);
+      if (c < N) {
+        if (brow) x += brow[c];
+        if (act == ACT_RELU) x = fmaxf(x, 0.f);
+        else if (act == ACT_GELU) x = gelu_erf(x);
+        else if (act == ACT_LRELU) x = lrelu02(x);
+        if (rrow) x += rrow[c];
+      }
+      o[j] = x;
+    }
+    if (col0 + 32 <= N && (ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(crow + col0) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(crow + col0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < N) crow[col0 + j] = o[j];
+    }
+  }
+  __device__ __forceinline__ void unit_end(State&, long long, bool, int) const {}
+};
+
+template <int KC>
+struct MatchEpi {
+  const float* dbnorm;
+  long long N;
+  float* cand_score;
+  int32_t* cand_idx;
+  int splits;
+  struct State {
+    float s[KC];
+    int32_t i[KC];
+  };
+  __device__ __forceinline__ void unit_begin(State& st) const {
+#pragma unroll
+    for (int t = 0; t < KC; ++t) { st.s[t] = INFINITY; st.i[t] = -1; }
+  }
+  __device__ __forceinline__ void chunk(State& st, long long, bool row_ok, int col0, const uint32_t (&v)[32]) const {
+    if (!row_ok) return;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const long long c = (long long)col0 + j;
+      if (c < N) {
+        // coarse squared distance up to the per-query constant ||q||^2
+        float sc = fmaf(-2.f, __uint_as_float(v[j]), __ldg(dbnorm + c));
+        if (sc < st.s[KC - 1]) {
+          int32_t ci = (int32_t)c;
+#pragma unroll
+          for (int t = 0; t < KC; ++t) {
+            if (sc < st.s[t]) {
+              const float ts = st.s[t]; st.s[t] = sc; sc = ts;
+              const int32_t ti = st.i[t]; st.i[t] = ci; ci = ti;
+            }
+          }
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void unit_end(State& st, long long row, bool row_ok, int split) const {
+    if (!row_ok) return;
+    const long long o = (row * splits + split) * KC;
+#pragma unroll
+    for (int t = 0; t < KC; ++t) { cand_score[o + t] = st.s[t]; cand_idx[o + t] = st.i[t]; }
+  }
+};
+
+template <int BN>
+struct TcSmem {
+  static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, class Epi>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const TcShape sh, const int num_kb, const Epi epi) {
+  using SM = TcSmem<BN>;
+  constexpr int STAGES = SM::STAGES;
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * SM::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int u = blockIdx.x; u < sh.units; u += gridDim.x) {
+        const int mt = u % sh.tiles_m_total, split = u / sh.tiles_m_total;
+        const int b = mt / sh.tiles_m_per_b, mtb = mt - b * sh.tiles_m_per_b;
+        const long long a_row0 = (long long)b * sh.src_rows_per_b + (long long)mtb * BLOCK_M;
+        const int nt_end = min(sh.tiles_n, (split + 1) * sh.tiles_per_unit);
+        for (int nt = split * sh.tiles_per_unit; nt < nt_end; ++nt) {
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * SM::STAGE_BYTES;
+            uint8_t* sb = sa + A_STAGE_BYTES;
+            mbar_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
+            const int tap = kb / sh.kb_per_tap, kc = kb - tap * sh.kb_per_tap;
+            tma_load_2d(sa, &tmA, &full_bar[stage], kc * BLOCK_K, (int)(a_row0 + (long long)tap * sh.tap_row_stride));
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, nt * BN);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_M, BN);
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      for (int u = blockIdx.x; u < sh.units; u += gridDim.x) {
+        const int split = u / sh.tiles_m_total;
+        const int nt_end = min(sh.tiles_n, (split + 1) * sh.tiles_per_unit);
+        for (int nt = split * sh.tiles_per_unit; nt < nt_end; ++nt) {
+          mbar_wait(&tempty_bar[as], aphase ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * SM::STAGE_BYTES);
+            const uint64_t adesc = make_smem_desc(sa);
+            const uint64_t bdesc = make_smem_desc(sa + A_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              // advance 32 B (16 bf16) inside the 128 B swizzle atom: +2 in 16 B units
+              umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&tfull_bar[as]);
+          if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    int as = 0; uint32_t aphase = 0;
+    typename Epi::State st;
+    for (int u = blockIdx.x; u < sh.units; u += gridDim.x) {
+      const int mt = u % sh.tiles_m_total, split = u / sh.tiles_m_total;
+      const int b = mt / sh.tiles_m_per_b, mtb = mt - b * sh.tiles_m_per_b;
+      const int r_in_b = mtb * BLOCK_M + q * 32 + lane;
+      const bool row_ok = r_in_b < sh.rows_out_per_b;
+      const long long row = (long long)b * sh.rows_out_per_b + r_in_b;
+      epi.unit_begin(st);
+      const int nt_end = min(sh.tiles_n, (split + 1) * sh.tiles_per_unit);
+      for (int nt = split * sh.tiles_per_unit; nt < nt_end; ++nt) {
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + (uint32_t)c0, v);
+          epi.chunk(st, row, row_ok, nt * BN + c0, v);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+      epi.unit_end(st, row, row_ok, split);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 [rows, K] row-major, box = box_rows x 64 elements, 128B swizzle, OOB reads return zero
+int make_tmap(CUtensorMap* tm, const void* ptr, unsigned long long rows, unsigned long long K, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(MOCHA_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  MOCHA_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "tensor map: base not 16B aligned");
+  MOCHA_CHECK_ARG((K * 2) % 16 == 0, "tensor map: row pitch %llu B not a multiple of 16", K * 2);
+  cuuint64_t gdim[2] = {K, rows};
+  cuuint64_t gstride[1] = {K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(MOCHA_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return MOCHA_OK;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, class Epi>
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcShape& sh, int num_kb, const Epi& epi,
+              cudaStream_t s) {
+  using SM = TcSmem<BN>;
+  static bool configured = false;
+  if (!configured) {
+    MOCHA_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    configured = true;
+  }
+  const int grid = sh.units < num_sms() ? sh.units : num_sms();
+  tc_gemm_kernel<BN, Epi><<<grid, TC_THREADS, SM::TOTAL, s>>>(tmA, tmB, sh, num_kb, epi);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("tc_gemm_kernel");
+  return MOCHA_OK;
+}
+
+__global__ void cast_act_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n,
+                                     int lrelu) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    float4 v = *reinterpret_cast<const float4*>(x + i);
+    if (lrelu) { v.x = lrelu02(v.x); v.y = lrelu02(v.y); v.z = lrelu02(v.z); v.w = lrelu02(v.w); }
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(y + i) = pk;
+  } else {
+    for (long long j = i; j < n; ++j) {
+      float v = x[j];
+      y[j] = __float2bfloat16_rn(lrelu ? lrelu02(v) : v);
+    }
+  }
+}
+
+// X fp32 [B,T,V,C] -> bf16 [B, T+2*pad, V, C] with reflect padding along T
+__global__ void reflect_pad_cast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int T, int V,
+                                        int C, int pad, long long total4) {
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= total4) return;
+  const long long i = i4 * 4;
+  const int c = (int)(i % C);
+  const long long r = i / C;
+  const int v = (int)(r % V);
+  const long long bt = r / V;
+  const int Tp = T + 2 * pad;
+  const int tp = (int)(bt % Tp);
+  const long long b = bt / Tp;
+  int t = tp - pad;
+  if (t < 0) t = -t;
+  if (t >= T) t = 2 * (T - 1) - t;
+  const float4 val = *reinterpret_cast<const float4*>(x + (((b * T + t) * V + v) * (long long)C + c));
+  __nv_bfloat162 lo = __floats2bfloat162_rn(val.x, val.y), hi = __floats2bfloat162_rn(val.z, val.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&lo);
+  pk.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(y + i) = pk;
+}
+
+struct Blob {
+  const float* b32;
+  const __nv_bfloat16* b16;
+  size_t elems;
+};
+constexpr int MAX_BLOBS = 16;
+Blob g_blobs[MAX_BLOBS];
+int g_nblobs = 0;
+
+int pick_bn(long long tiles_m, int N) {
+  // largest BN that still gives about one wave of CTAs; tiles that would be mostly padding are skipped
+  const int cands[4] = {256, 128, 64, 32};
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    if (bn > 32 && bn / 2 >= N) continue;
+    if (tiles_m * ((N + bn - 1) / bn) >= num_sms()) return bn;
+  }
+  return N >= 128 ? 64 : 32;  // latency-bound problem: more, narrower CTAs
+}
+
+template <class Epi>
+int dispatch_bn(int bn, const CUtensorMap& tmA, const void* Wptr, unsigned long long wrows, unsigned long long K,
+                TcShape sh, int N, int num_kb, const Epi& epi, cudaStream_t s) {
+  CUtensorMap tmB;
+  MOCHA_TRY(make_tmap(&tmB, Wptr, wrows, K, bn));
+  sh.tiles_n = ceil_div(N, bn);
+  sh.tiles_per_unit = 1;
+  sh.units = sh.tiles_m_total * sh.tiles_n;
+  switch (bn) {
+    case 256: return launch_tc<256, Epi>(tmA, tmB, sh, num_kb, epi, s);
+    case 128: return launch_tc<128, Epi>(tmA, tmB, sh, num_kb, epi, s);
+    case 64: return launch_tc<64, Epi>(tmA, tmB, sh, num_kb, epi, s);
+    default: return launch_tc<32, Epi>(tmA, tmB, sh, num_kb, epi, s);
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// public (library-internal) API
+// ------------------------------------------------------------------------------------------------
+bool tc_linear_supported(int M, int N, int K) { return M >= 1 && N >= 16 && K >= 64 && (K % 8) == 0; }
+
+size_t tc_scratch_bytes(size_t rows, size_t K) { return align_up(rows * K * 2, 256) + 256; }
+
+void tc_register_blob(const float* blob32, const void* blob16, size_t elems) {
+  for (int i = 0; i < g_nblobs; ++i)
+    if (g_blobs[i].b32 == blob32) {
+      g_blobs[i].b16 = (const __nv_bfloat16*)blob16;
+      g_blobs[i].elems = elems;
+      return;
+    }
+  if (g_nblobs < MAX_BLOBS) g_blobs[g_nblobs++] = Blob{blob32, (const __nv_bfloat16*)blob16, elems};
+  else g_blobs[MAX_BLOBS - 1] = Blob{blob32, (const __nv_bfloat16*)blob16, elems};
+}
+
+const __nv_bfloat16* tc_lookup_bf16(const float* W) {
+  for (int i = 0; i < g_nblobs; ++i) {
+    const Blob& b = g_blobs[i];
+    if (b.b16 && W >= b.b32 && W < b.b32 + b.elems) return b.b16 + (W - b.b32);
+  }
+  return nullptr;
+}
+
+int tc_linear_bf16(const __nv_bfloat16* A16, const __nv_bfloat16* W16, const float* bias, int bias_period,
+                   const float* res, float* C, int M, int N, int K, int act, cudaStream_t s) {
+  MOCHA_CHECK_ARG(A16 && W16 && C, "tc_linear: null operand");
+  MOCHA_CHECK_ARG(tc_linear_supported(M, N, K), "tc_linear: unsupported shape M=%d N=%d K=%d", M, N, K);
+  CUtensorMap tmA;
+  MOCHA_TRY(make_tmap(&tmA, A16, (unsigned long long)M, (unsigned long long)K, BLOCK_M));
+  TcShape sh{};
+  sh.nb = 1;
+  sh.rows_out_per_b = M;
+  sh.tiles_m_per_b = ceil_div(M, BLOCK_M);
+  sh.tiles_m_total = sh.tiles_m_per_b;
+  sh.src_rows_per_b = M;
+  sh.taps = 1;
+  sh.kb_per_tap = ceil_div(K, BLOCK_K);
+  sh.tap_row_stride = 0;
+  LinearEpi epi{C, N, N, bias, bias_period, res, act};
+  return dispatch_bn(pick_bn(sh.tiles_m_total, N), tmA, W16, (unsigned long long)N, (unsigned long long)K, sh, N,
+                     ceil_div(K, BLOCK_K), epi, s);
+}
+
+int tc_linear(const float* A, const float* W, const float* bias, int bias_period, const float* res, float* C, int M,
+              int N, int K, int act, int a_lrelu, Workspace& ws, cudaStream_t s) {
+  const __nv_bfloat16* W16 = tc_lookup_bf16(W);
+  if (!W16) return set_error(MOCHA_ERR_ARG, "tc_linear: weight %p has no registered bf16 mirror", (const void*)W);
+  const size_t mark = ws.off;
+  __nv_bfloat16* A16 = ws.take<__nv_bfloat16>((size_t)M * K);
+  if (!A16) return set_error(MOCHA_ERR_WORKSPACE, "tc_linear: workspace too small for the bf16 A operand");
+  const long long n = (long long)M * K;
+  MOCHA_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0, "tc_linear: A not 16B aligned");
+  cast_act_bf16_kernel<<<(unsigned)((n / 4 + 255) / 256 + 1), 256, 0, s>>>(A, A16, n, a_lrelu);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("cast_act_bf16");
+  int rc = tc_linear_bf16(A16, W16, bias, bias_period, res, C, M, N, K, act, s);
+  ws.off = mark;  // stream order makes the scratch reusable by the next layer
+  return rc;
+}
+
+bool tc_tconv_supported(int B, int T, int V, int Cin, int Cout, int taps) {
+  return B >= 1 && (Cin % BLOCK_K) == 0 && Cout >= 16 && (taps & 1) && taps / 2 < T && (long long)T * V >= 1;
+}
+size_t tc_tconv_scratch_bytes(int B, int T, int V, int Cin, int taps) {
+  return align_up((size_t)B * (T + 2 * (taps / 2)) * V * Cin * 2, 256) + 256;
+}
+
+int tc_tconv(const float* X, const float* W, const float* bias, int bias_period, float* C, int B, int T, int V,
+             int Cin, int Cout, int taps, Workspace& ws, cudaStream_t s) {
+  MOCHA_CHECK_ARG(tc_tconv_supported(B, T, V, Cin, Cout, taps), "tc_tconv: unsupported geometry");
+  const __nv_bfloat16* W16 = tc_lookup_bf16(W);
+  if (!W16) return set_error(MOCHA_ERR_ARG, "tc_tconv: weight %p has no registered bf16 mirror", (const void*)W);
+  const int pad = taps / 2, Tp = T + 2 * pad;
+  const size_t mark = ws.off;
+  const size_t elems = (size_t)B * Tp * V * Cin;
+  __nv_bfloat16* X16 = ws.take<__nv_bfloat16>(elems);
+  if (!X16) return set_error(MOCHA_ERR_WORKSPACE, "tc_tconv: workspace too small for the padded bf16 operand");
+  reflect_pad_cast_kernel<<<(unsigned)((elems / 4 + 255) / 256), 256, 0, s>>>(X, X16, T, V, Cin, pad,
+                                                                             (long long)(elems / 4));
+  count_launch();
+  MOCHA_LAUNCH_CHECK("reflect_pad_cast");
+  CUtensorMap tmA;
+  MOCHA_TRY(make_tmap(&tmA, X16, (unsigned long long)B * Tp * V, (unsigned long long)Cin, BLOCK_M));
+  TcShape sh{};
+  sh.nb = B;
+  sh.rows_out_per_b = T * V;
+  sh.tiles_m_per_b = ceil_div(T * V, BLOCK_M);
+  sh.tiles_m_total = sh.tiles_m_per_b * B;
+  sh.src_rows_per_b = (long long)Tp * V;
+  sh.taps = taps;
+  sh.kb_per_tap = Cin / BLOCK_K;
+  sh.tap_row_stride = V;
+  LinearEpi epi{C, Cout, Cout, bias, bias_period, nullptr, ACT_NONE};
+  int rc = dispatch_bn(pick_bn(sh.tiles_m_total, Cout), tmA, W16, (unsigned long long)Cout,
+                       (unsigned long long)taps * Cin, sh, Cout, taps * sh.kb_per_tap, epi, s);
+  ws.off = mark;
+  return rc;
+}
+
+int tc_match_splits(int nq, long long N) {
+  const int tiles_m = ceil_div(nq, BLOCK_M);
+  const long long tiles_n = (N + 255) / 256;
+  // ~8 units per SM for balance, but never more splits than n-tiles
+  long long splits = (8LL * num_sms() + tiles_m - 1) / tiles_m;
+  if (splits > tiles_n) splits = tiles_n;
+  if (splits < 1) splits = 1;
+  // recompute so that every split is non-empty
+  const long long tpu = (tiles_n + splits - 1) / splits;
+  splits = (tiles_n + tpu - 1) / tpu;
+  return (int)splits;
+}
+
+int tc_match_coarse(const __nv_bfloat16* Q16, int nq, const __nv_bfloat16* DB16, const float* dbnorm, long long N,
+                    int D, int kc, float* cand_score, int32_t* cand_idx, cudaStream_t s) {
+  MOCHA_CHECK_ARG(Q16 && DB16 && dbnorm && cand_score && cand_idx, "tc_match_coarse: null operand");
+  MOCHA_CHECK_ARG(nq > 0 && N > 0 && N < 2147483647LL, "tc_match_coarse: bad sizes nq=%d N=%lld", nq, N);
+  MOCHA_CHECK_ARG(D >= BLOCK_K && D % 8 == 0, "tc_match_coarse: D=%d must be >= 64 and a multiple of 8", D);
+  MOCHA_CHECK_ARG(kc == 4 || kc == 8 || kc == 16, "tc_match_coarse: kc must be 4, 8 or 16");
+  constexpr int BN = 256;
+  CUtensorMap tmA, tmB;
+  MOCHA_TRY(make_tmap(&tmA, Q16, (unsigned long long)nq, (unsigned long long)D, BLOCK_M));
+  MOCHA_TRY(make_tmap(&tmB, DB16, (unsigned long long)N, (unsigned long long)D, BN));
+  TcShape sh{};
+  sh.nb = 1;
+  sh.rows_out_per_b = nq;
+  sh.tiles_m_per_b = ceil_div(nq, BLOCK_M);
+  sh.tiles_m_total = sh.tiles_m_per_b;
+  sh.src_rows_per_b = nq;
+  sh.taps = 1;
+  sh.kb_per_tap = ceil_div(D, BLOCK_K);
+  sh.tap_row_stride = 0;
+  sh.tiles_n = (int)((N + BN - 1) / BN);
+  const int splits = tc_match_splits(nq, N);
+  sh.tiles_per_unit = ceil_div(sh.tiles_n, splits);
+  sh.units = sh.tiles_m_total * splits;
+  const int num_kb = ceil_div(D, BLOCK_K);
+  if (kc == 4) return launch_tc<BN, MatchEpi<4>>(tmA, tmB, sh, num_kb, MatchEpi<4>{dbnorm, N, cand_score, cand_idx, splits}, s);
+  if (kc == 8) return launch_tc<BN, MatchEpi<8>>(tmA, tmB, sh, num_kb, MatchEpi<8>{dbnorm, N, cand_score, cand_idx, splits}, s);
+  return launch_tc<BN, MatchEpi<16>>(tmA, tmB, sh, num_kb, MatchEpi<16>{dbnorm, N, cand_score, cand_idx, splits}, s);
+}
+
+}  // namespace mocha

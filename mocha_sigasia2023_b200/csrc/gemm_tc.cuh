@@ -1,0 +1,45 @@
+// tcgen05 (5th-gen tensor core) GEMM family for sm_100a:
+//   TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory ring -> tcgen05.mma (bf16 x bf16,
+//   fp32 accumulators in TMEM, double-buffered) -> tcgen05.ld epilogue.
+// Two epilogues share the main loop:
+//   * linear:  C = act(A W^T + bias) (+ residual), optionally as an implicit temporal convolution
+//              (taps shifted TMA row windows over a reflect-padded channel-last activation)
+//   * matcher: coarse squared distances ||x||^2 - 2 q.x with a fused per-row running top-kc
+#pragma once
+#include "common.cuh"
+
+namespace mocha {
+
+// ---- linear ------------------------------------------------------------------------------------
+bool tc_linear_supported(int M, int N, int K);
+// bytes of bf16 scratch needed to stage an [rows, K] A operand
+size_t tc_scratch_bytes(size_t rows, size_t K);
+
+// Registered bf16 mirror of an fp32 weight blob: W16 = blob16 + (W - blob32).
+void tc_register_blob(const float* blob32, const void* blob16, size_t elems);
+const __nv_bfloat16* tc_lookup_bf16(const float* W);
+
+// C[M,N] fp32 = act(prologue(A)[M,K] W[N,K]^T + bias) (+res). A fp32 is cast to bf16 into ws first.
+int tc_linear(const float* A, const float* W, const float* bias, int bias_period, const float* res, float* C,
+              int M, int N, int K, int act, int a_lrelu, Workspace& ws, cudaStream_t s);
+
+// Same with operands already in bf16 (A16 [M,K], W16 [N,K], both K-major, 16B-aligned rows).
+int tc_linear_bf16(const __nv_bfloat16* A16, const __nv_bfloat16* W16, const float* bias, int bias_period,
+                   const float* res, float* C, int M, int N, int K, int act, cudaStream_t s);
+
+// Reflect-padded temporal convolution on tensor cores: X fp32 [B,T,V,Cin] -> C [B*T*V, Cout].
+// W [Cout, taps*Cin] (tap-major K). Stages a bf16 reflect-padded copy of X in ws.
+bool tc_tconv_supported(int B, int T, int V, int Cin, int Cout, int taps);
+size_t tc_tconv_scratch_bytes(int B, int T, int V, int Cin, int taps);
+int tc_tconv(const float* X, const float* W, const float* bias, int bias_period, float* C, int B, int T, int V,
+             int Cin, int Cout, int taps, Workspace& ws, cudaStream_t s);
+
+// ---- matcher coarse pass ---------------------------------------------------------------------------
+constexpr int MATCH_KC_MAX = 16;
+// Number of N-splits the coarse pass will use for (nq, N); candidates are [nq, splits, kc].
+int tc_match_splits(int nq, long long N);
+// cand_score [nq, splits, kc] fp32 (ascending), cand_idx [nq, splits, kc] int32 (-1 = empty)
+int tc_match_coarse(const __nv_bfloat16* Q16, int nq, const __nv_bfloat16* DB16, const float* dbnorm,
+                    long long N, int D, int kc, float* cand_score, int32_t* cand_idx, cudaStream_t s);
+
+}  // namespace mocha

@@ -1,0 +1,775 @@
+// Quaternion forward kinematics, two-bone IK, inertialization and the per-frame post-process
+// (SURVEY §8 rows a10-a18). Quaternion layout is [w,x,y,z] as in the reference's motion/quat.py.
+// Bandwidth/latency-bound: batch kernels stage one skeleton per warp in shared memory (coalesced
+// loads, joint hierarchy walked level by level with one lane per joint); the stateful per-clip
+// post-process runs one thread per clip in fp64 like the reference's NumPy state.
+#include "../../include/mocha_b200.h"
+#include "common.cuh"
+
+using namespace mocha;
+
+namespace {
+
+template <typename T>
+struct V3 { T x, y, z; };
+template <typename T>
+struct Q4 { T w, x, y, z; };
+
+template <typename T> __device__ __forceinline__ V3<T> v3(T x, T y, T z) { V3<T> r; r.x = x; r.y = y; r.z = z; return r; }
+template <typename T> __device__ __forceinline__ V3<T> operator+(V3<T> a, V3<T> b) { return v3<T>(a.x + b.x, a.y + b.y, a.z + b.z); }
+template <typename T> __device__ __forceinline__ V3<T> operator-(V3<T> a, V3<T> b) { return v3<T>(a.x - b.x, a.y - b.y, a.z - b.z); }
+template <typename T> __device__ __forceinline__ V3<T> operator*(T s, V3<T> a) { return v3<T>(s * a.x, s * a.y, s * a.z); }
+template <typename T> __device__ __forceinline__ T dot(V3<T> a, V3<T> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template <typename T> __device__ __forceinline__ V3<T> cross(V3<T> a, V3<T> b) {
+  return v3<T>(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+template <typename T> __device__ __forceinline__ T vlen(V3<T> a) { return sqrt(dot(a, a)); }
+// quat.normalize for 3-vectors: x / (|x| + eps)  (motion/quat.py:15)
+template <typename T> __device__ __forceinline__ V3<T> vnormalize(V3<T> a) {
+  const T d = vlen(a) + (T)1e-8;
+  return v3<T>(a.x / d, a.y / d, a.z / d);
+}
+template <typename T> __device__ __forceinline__ Q4<T> q4(T w, T x, T y, T z) { Q4<T> r; r.w = w; r.x = x; r.y = y; r.z = z; return r; }
+template <typename T> __device__ __forceinline__ V3<T> qvec(Q4<T> q) { return v3<T>(q.x, q.y, q.z); }
+
+// quat.mul (motion/quat.py:112-120)
+template <typename T> __device__ __forceinline__ Q4<T> qmul(Q4<T> a, Q4<T> b) {
+  return q4<T>(b.w * a.w - b.x * a.x - b.y * a.y - b.z * a.z,
+               b.w * a.x + b.x * a.w - b.y * a.z + b.z * a.y,
+               b.w * a.y + b.x * a.z + b.y * a.w - b.z * a.x,
+               b.w * a.z - b.x * a.y + b.y * a.x + b.z * a.w);
+}
+template <typename T> __device__ __forceinline__ Q4<T> qinv(Q4<T> q) { return q4<T>(q.w, -q.x, -q.y, -q.z); }
+// quat.mul_vec (motion/quat.py:128-130)
+template <typename T> __device__ __forceinline__ V3<T> qrot(Q4<T> q, V3<T> x) {
+  const V3<T> t = (T)2 * cross(qvec(q), x);
+  return x + q.w * t + cross(qvec(q), t);
+}
+template <typename T> __device__ __forceinline__ Q4<T> qnormalize(Q4<T> q) {
+  const T d = sqrt(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z) + (T)1e-8;
+  return q4<T>(q.w / d, q.x / d, q.y / d, q.z / d);
+}
+template <typename T> __device__ __forceinline__ Q4<T> qabs(Q4<T> q) {
+  return q.w > (T)0 ? q : q4<T>(-q.w, -q.x, -q.y, -q.z);
+}
+// quat.from_angle_axis (motion/quat.py:21-25)
+template <typename T> __device__ __forceinline__ Q4<T> q_angle_axis(T angle, V3<T> axis) {
+  const T c = cos(angle / (T)2), s = sin(angle / (T)2);
+  return q4<T>(c, s * axis.x, s * axis.y, s * axis.z);
+}
+// quat.exp (motion/quat.py:154-158); np.sinc(h/pi) = sin(h)/h
+template <typename T> __device__ __forceinline__ Q4<T> qexp(V3<T> x) {
+  const T h = vlen(x);
+  const T c = h < (T)1e-5 ? (T)1 : cos(h);
+  const T s = h < (T)1e-5 ? (T)1 : sin(h) / h;
+  return q4<T>(c, s * x.x, s * x.y, s * x.z);
+}
+// quat.log (motion/quat.py:149-152)
+template <typename T> __device__ __forceinline__ V3<T> qlog(Q4<T> q) {
+  const T len = vlen(qvec(q));
+  const T ha = len < (T)1e-5 ? (T)1 : atan2(len, q.w) / len;
+  return ha * qvec(q);
+}
+template <typename T> __device__ __forceinline__ Q4<T> q_from_scaled_angle_axis(V3<T> x) { return qexp((T)0.5 * x); }
+template <typename T> __device__ __forceinline__ V3<T> q_to_scaled_angle_axis(Q4<T> q) { return (T)2 * qlog(q); }
+
+// quat.from_xform (motion/quat.py:69-94): 4-branch matrix -> quaternion, then normalize
+template <typename T> __device__ __forceinline__ Q4<T> q_from_xform(const T (&m)[3][3]) {
+  Q4<T> q;
+  if (m[2][2] < (T)0) {
+    if (m[0][0] > m[1][1])
+      q = q4<T>(m[2][1] - m[1][2], (T)1 + m[0][0] - m[1][1] - m[2][2], m[1][0] + m[0][1], m[0][2] + m[2][0]);
+    else
+      q = q4<T>(m[0][2] - m[2][0], m[1][0] + m[0][1], (T)1 - m[0][0] + m[1][1] - m[2][2], m[2][1] + m[1][2]);
+  } else {
+    if (m[0][0] < -m[1][1])
+      q = q4<T>(m[1][0] - m[0][1], m[0][2] + m[2][0], m[2][1] + m[1][2], (T)1 - m[0][0] - m[1][1] + m[2][2]);
+    else
+      q = q4<T>((T)1 + m[0][0] + m[1][1] + m[2][2], m[2][1] - m[1][2], m[0][2] - m[2][0], m[1][0] - m[0][1]);
+  }
+  return qnormalize(q);
+}
+// quat.from_xform_xy (motion/quat.py:96-107): Gram-Schmidt through two cross products
+template <typename T> __device__ __forceinline__ Q4<T> q_from_xy(V3<T> c0, V3<T> c1in) {
+  V3<T> c2 = cross(c0, c1in);
+  T n = sqrt(dot(c2, c2));
+  c2 = v3<T>(c2.x / n, c2.y / n, c2.z / n);
+  V3<T> c1 = cross(c2, c0);
+  n = sqrt(dot(c1, c1));
+  c1 = v3<T>(c1.x / n, c1.y / n, c1.z / n);
+  const T m[3][3] = {{c0.x, c1.x, c2.x}, {c0.y, c1.y, c2.y}, {c0.z, c1.z, c2.z}};
+  return q_from_xform(m);
+}
+
+// ------------------------------------------------------------------------------------------------
+// element-wise rotation format conversions
+// ------------------------------------------------------------------------------------------------
+__global__ void xy_to_quat_kernel(const float* __restrict__ xy, long long n, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = xy + i * 6;  // [3][2]
+  const Q4<float> q = q_from_xy(v3<float>(p[0], p[2], p[4]), v3<float>(p[1], p[3], p[5]));
+  reinterpret_cast<float4*>(out)[i] = make_float4(q.w, q.x, q.y, q.z);
+}
+
+// quat.to_xform_xy (motion/quat.py:42-55)
+__global__ void quat_to_xy_kernel(const float* __restrict__ quat, long long n, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 q = reinterpret_cast<const float4*>(quat)[i];
+  const float qw = q.x, qx = q.y, qy = q.z, qz = q.w;
+  const float x2 = qx + qx, y2 = qy + qy, z2 = qz + qz;
+  const float xx = qx * x2, yy = qy * y2, wx = qw * x2;
+  const float xy = qx * y2, yz = qy * z2, wy = qw * y2;
+  const float xz = qx * z2, zz = qz * z2, wz = qw * z2;
+  float* o = out + i * 6;
+  o[0] = 1.0f - (yy + zz); o[1] = xy - wz;
+  o[2] = xy + wz;          o[3] = 1.0f - (xx + zz);
+  o[4] = xz - wy;          o[5] = yz + wx;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batch FK / FK with velocities / inverse (global -> local): one warp per skeleton
+// ------------------------------------------------------------------------------------------------
+constexpr int MAXJ = 32;
+constexpr int FK_WARPS = 4;
+
+struct SkelSmem {
+  float rot[MAXJ][4], pos[MAXJ][3], vel[MAXJ][3], ang[MAXJ][3];
+  float grot[MAXJ][4], gpos[MAXJ][3], gvel[MAXJ][3], gang[MAXJ][3];
+};
+
+__device__ __forceinline__ void warp_copy_in(float* dst, const float* __restrict__ src, int n, int lane) {
+  for (int i = lane; i < n; i += 32) dst[i] = src[i];
+}
+__device__ __forceinline__ void warp_copy_out(float* __restrict__ dst, const float* src, int n, int lane) {
+  for (int i = lane; i < n; i += 32) dst[i] = src[i];
+}
+
+// depth of joint `lane` in the hierarchy (parents[i] < i)
+__device__ __forceinline__ int joint_depth(const int32_t* par, int j, int J) {
+  int d = 0;
+  if (j < J) { int p = par[j]; while (p >= 0) { ++d; p = par[p]; } }
+  return d;
+}
+
+template <bool WITH_VEL>
+__global__ void __launch_bounds__(FK_WARPS * 32)
+fk_kernel(const float* __restrict__ lrot, const float* __restrict__ lpos, const float* __restrict__ lvel,
+          const float* __restrict__ lang, const int32_t* __restrict__ parents, long long F, int J,
+          float* __restrict__ grot, float* __restrict__ gpos, float* __restrict__ gvel, float* __restrict__ gang) {
+  __shared__ SkelSmem sm[FK_WARPS];
+  __shared__ int32_t par[MAXJ];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < J) par[threadIdx.x] = parents[threadIdx.x];
+  __syncthreads();
+  const int depth = joint_depth(par, lane, J);
+  int maxd = depth;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) maxd = max(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
+  SkelSmem& s = sm[warp];
+  for (long long f = (long long)blockIdx.x * FK_WARPS + warp; f < F; f += (long long)gridDim.x * FK_WARPS) {
+    warp_copy_in(&s.rot[0][0], lrot + f * J * 4, J * 4, lane);
+    warp_copy_in(&s.pos[0][0], lpos + f * J * 3, J * 3, lane);
+    if (WITH_VEL) {
+      warp_copy_in(&s.vel[0][0], lvel + f * J * 3, J * 3, lane);
+      warp_copy_in(&s.ang[0][0], lang + f * J * 3, J * 3, lane);
+    }
+    __syncwarp();
+    // quat.fk / quat.fk_vel (motion/quat.py:166-204): level-synchronous walk, one lane per joint
+    for (int lvl = 0; lvl <= maxd; ++lvl) {
+      if (lane < J && depth == lvl) {
+        const int j = lane;
+        const Q4<float> lr = q4<float>(s.rot[j][0], s.rot[j][1], s.rot[j][2], s.rot[j][3]);
+        const V3<float> lp = v3<float>(s.pos[j][0], s.pos[j][1], s.pos[j][2]);
+        if (lvl == 0) {
+          s.grot[j][0] = lr.w; s.grot[j][1] = lr.x; s.grot[j][2] = lr.y; s.grot[j][3] = lr.z;
+          s.gpos[j][0] = lp.x; s.gpos[j][1] = lp.y; s.gpos[j][2] = lp.z;
+          if (WITH_VEL) {
+            for (int c = 0; c < 3; ++c) { s.gvel[j][c] = s.vel[j][c]; s.gang[j][c] = s.ang[j][c]; }
+          }
+        } else {
+          const int p = par[j];
+          const Q4<float> pr = q4<float>(s.grot[p][0], s.grot[p][1], s.grot[p][2], s.grot[p][3]);
+          const V3<float> pp = v3<float>(s.gpos[p][0], s.gpos[p][1], s.gpos[p][2]);
+          const V3<float> rp = qrot(pr, lp);
+          const V3<float> gp = rp + pp;
+          const Q4<float> gr = qmul(pr, lr);
+          s.gpos[j][0] = gp.x; s.gpos[j][1] = gp.y; s.gpos[j][2] = gp.z;
+          s.grot[j][0] = gr.w; s.grot[j][1] = gr.x; s.grot[j][2] = gr.y; s.grot[j][3] = gr.z;
+          if (WITH_VEL) {
+            const V3<float> lv = v3<float>(s.vel[j][0], s.vel[j][1], s.vel[j][2]);
+            const V3<float> la = v3<float>(s.ang[j][0], s.ang[j][1], s.ang[j][2]);
+            const V3<float> pv = v3<float>(s.gvel[p][0], s.gvel[p][1], s.gvel[p][2]);
+            const V3<float> pa = v3<float>(s.gang[p][0], s.gang[p][1], s.gang[p][2]);
+            const V3<float> gv = qrot(pr, lv) + cross(pa, rp) + pv;
+            const V3<float> ga = qrot(pr, la) + pa;
+            s.gvel[j][0] = gv.x; s.gvel[j][1] = gv.y; s.gvel[j][2] = gv.z;
+            s.gang[j][0] = ga.x; s.gang[j][1] = ga.y; s.gang[j][2] = ga.z;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    warp_copy_out(grot + f * J * 4, &s.grot[0][0], J * 4, lane);
+    warp_copy_out(gpos + f * J * 3, &s.gpos[0][0], J * 3, lane);
+    if (WITH_VEL) {
+      warp_copy_out(gvel + f * J * 3, &s.gvel[0][0], J * 3, lane);
+      warp_copy_out(gang + f * J * 3, &s.gang[0][0], J * 3, lane);
+    }
+    __syncwarp();
+  }
+}
+
+// quat.ik (motion/quat.py:175-187)
+__global__ void __launch_bounds__(FK_WARPS * 32)
+ik_kernel(const float* __restrict__ grot, const float* __restrict__ gpos, const int32_t* __restrict__ parents,
+          long long F, int J, float* __restrict__ lrot, float* __restrict__ lpos) {
+  __shared__ SkelSmem sm[FK_WARPS];
+  __shared__ int32_t par[MAXJ];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < J) par[threadIdx.x] = parents[threadIdx.x];
+  __syncthreads();
+  SkelSmem& s = sm[warp];
+  for (long long f = (long long)blockIdx.x * FK_WARPS + warp; f < F; f += (long long)gridDim.x * FK_WARPS) {
+    warp_copy_in(&s.grot[0][0], grot + f * J * 4, J * 4, lane);
+    warp_copy_in(&s.gpos[0][0], gpos + f * J * 3, J * 3, lane);
+    __syncwarp();
+    if (lane < J) {
+      const int j = lane;
+      const Q4<float> gr = q4<float>(s.grot[j][0], s.grot[j][1], s.grot[j][2], s.grot[j][3]);
+      const V3<float> gp = v3<float>(s.gpos[j][0], s.gpos[j][1], s.gpos[j][2]);
+      if (par[j] < 0) {
+        s.rot[j][0] = gr.w; s.rot[j][1] = gr.x; s.rot[j][2] = gr.y; s.rot[j][3] = gr.z;
+        s.pos[j][0] = gp.x; s.pos[j][1] = gp.y; s.pos[j][2] = gp.z;
+      } else {
+        const int p = par[j];
+        const Q4<float> pinv = qinv(q4<float>(s.grot[p][0], s.grot[p][1], s.grot[p][2], s.grot[p][3]));
+        const V3<float> pp = v3<float>(s.gpos[p][0], s.gpos[p][1], s.gpos[p][2]);
+        const Q4<float> lr = qmul(pinv, gr);
+        const V3<float> lp = qrot(pinv, gp - pp);
+        s.rot[j][0] = lr.w; s.rot[j][1] = lr.x; s.rot[j][2] = lr.y; s.rot[j][3] = lr.z;
+        s.pos[j][0] = lp.x; s.pos[j][1] = lp.y; s.pos[j][2] = lp.z;
+      }
+    }
+    __syncwarp();
+    warp_copy_out(lrot + f * J * 4, &s.rot[0][0], J * 4, lane);
+    warp_copy_out(lpos + f * J * 3, &s.pos[0][0], J * 3, lane);
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp64 scalar pieces of the post-process
+// ------------------------------------------------------------------------------------------------
+typedef V3<double> D3;
+typedef Q4<double> DQ;
+
+__device__ __forceinline__ D3 ld3(const double* p) { return v3<double>(p[0], p[1], p[2]); }
+__device__ __forceinline__ void st3(double* p, D3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+__device__ __forceinline__ DQ ld4(const double* p) { return q4<double>(p[0], p[1], p[2], p[3]); }
+__device__ __forceinline__ void st4(double* p, DQ q) { p[0] = q.w; p[1] = q.x; p[2] = q.y; p[3] = q.z; }
+
+// Inertialization.fast_negexpf / halflife_to_damping (Inertialization.py:10-14)
+__device__ __forceinline__ double fast_negexp(double x) { return 1.0 / (1.0 + x + 0.48 * x * x + 0.235 * x * x * x); }
+__device__ __forceinline__ double halflife_to_damping(double halflife) { return (4.0 * 0.693147180559945309417) / (halflife + 1e-5); }
+
+// decay_spring_damper_exact, vec3 branch (Inertialization.py:39-54)
+__device__ __forceinline__ void decay_spring_pos(D3& x, D3& v, double halflife, double dt) {
+  const double y = halflife_to_damping(halflife) / 2.0;
+  const double eydt = fast_negexp(y * dt);
+  const D3 j1 = v + y * x;
+  const D3 nx = eydt * (x + dt * j1);
+  const D3 nv = eydt * (v - (y * dt) * j1);
+  x = nx; v = nv;
+}
+// decay_spring_damper_exact_rot (Inertialization.py:28-37)
+__device__ __forceinline__ void decay_spring_rot(DQ& x, D3& v, double halflife, double dt) {
+  const double y = halflife_to_damping(halflife) / 2.0;
+  const D3 j0 = q_to_scaled_angle_axis(x);
+  const D3 j1 = v + y * j0;
+  const double eydt = fast_negexp(y * dt);
+  x = q_from_scaled_angle_axis(eydt * (j0 + dt * j1));
+  v = eydt * (v - (y * dt) * j1);
+}
+
+struct ContactState {
+  bool state, lock;
+  D3 position, velocity, point, target, off_pos, off_vel;
+};
+
+// Inertialization.contact_update (Inertialization.py:300-377)
+__device__ void contact_update_dev(ContactState& c, D3 input_position, bool input_state, double unlock_radius,
+                                   double foot_height, double halflife, double dt) {
+  const double eps = 1e-8;
+  // finite-difference input velocity; the reference divides by (dt + eps)
+  D3 iv = input_position - c.target;
+  iv = v3<double>(iv.x / (dt + eps), iv.y / (dt + eps), iv.z / (dt + eps));
+  c.target = input_position;
+  // inertialize_update (:110-127): decay the offsets, then add them to the fed input
+  decay_spring_pos(c.off_pos, c.off_vel, halflife, dt);
+  const D3 in_x = c.lock ? c.point : input_position;
+  const D3 in_v = c.lock ? v3<double>(0.0, 0.0, 0.0) : iv;
+  c.position = in_x + c.off_pos;
+  c.velocity = in_v + c.off_vel;
+  const bool unlock = c.lock && (vlen(c.point - input_position) > unlock_radius);
+  if (!c.state && input_state) {
+    c.lock = true;
+    c.point = c.position;
+    c.point.y = foot_height;
+    // inertialize_transition (:93-108), src = input, dst = contact point at rest
+    c.off_pos = (input_position + c.off_pos) - c.point;
+    c.off_vel = (iv + c.off_vel) - v3<double>(0.0, 0.0, 0.0);
+  } else if ((c.lock && c.state && !input_state) || unlock) {
+    c.lock = false;
+    c.off_pos = (c.point + c.off_pos) - input_position;
+    c.off_vel = (v3<double>(0.0, 0.0, 0.0) + c.off_vel) - iv;
+  }
+  c.state = input_state;
+}
+
+__device__ __forceinline__ double clip1(double x) { return fmin(1.0, fmax(-1.0, x)); }
+
+// quat.ik_two_bone (motion/quat.py:295-343)
+__device__ void ik_two_bone_dev(D3 bone_root, D3 bone_mid, D3 bone_end, D3 target, D3 fwd, DQ root_gr, DQ mid_gr,
+                                DQ par_gr, double max_length_buffer, DQ& out_root_lr, DQ& out_mid_lr) {
+  const double max_extension = vlen(bone_root - bone_mid) + vlen(bone_mid - bone_end) - max_length_buffer;
+  D3 t = target;
+  if (vlen(target - bone_root) > max_extension) t = bone_root + max_extension * vnormalize(target - bone_root);
+  const D3 axis_dwn = vnormalize(bone_end - bone_root);
+  const D3 axis_rot = vnormalize(cross(axis_dwn, fwd));
+  const D3 a = bone_root, b = bone_mid, c = bone_end;
+  const double lab = vlen(b - a), lcb = vlen(b - c), lat = vlen(t - a);
+  const double ac_ab_0 = acos(clip1(dot(vnormalize(c - a), vnormalize(b - a))));
+  const double ba_bc_0 = acos(clip1(dot(vnormalize(a - b), vnormalize(c - b))));
+  const double ac_ab_1 = acos(clip1((lab * lab + lat * lat - lcb * lcb) / (2.0 * lab * lat)));
+  const double ba_bc_1 = acos(clip1((lab * lab + lcb * lcb - lat * lat) / (2.0 * lab * lcb)));
+  const DQ r0 = q_angle_axis(ac_ab_1 - ac_ab_0, axis_rot);
+  const DQ r1 = q_angle_axis(ba_bc_1 - ba_bc_0, axis_rot);
+  const D3 c_a = vnormalize(bone_end - bone_root);
+  const D3 t_a = vnormalize(t - bone_root);
+  const DQ r2 = q_angle_axis(acos(clip1(dot(c_a, t_a))), vnormalize(cross(c_a, t_a)));
+  out_root_lr = qmul(qinv(par_gr), qmul(r2, qmul(r0, root_gr)));
+  out_mid_lr = qmul(qinv(root_gr), qmul(r1, mid_gr));
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-frame post-process, one thread per clip
+// ------------------------------------------------------------------------------------------------
+__global__ void post_frame_kernel(const mocha_post_params P, const float* __restrict__ Y,
+                                  const float* __restrict__ src_hips_vel, const float* __restrict__ src_rvel,
+                                  const float* __restrict__ src_rang, const uint8_t* __restrict__ contacts, int B,
+                                  int T, int V, int Cin, int init, mocha_clip_state* __restrict__ states,
+                                  mocha_frame_out* __restrict__ outs) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  mocha_clip_state& S = states[b];
+  mocha_frame_out& O = outs[b];
+  const int J = P.J;
+  const double dt = P.dt;
+  const float* Yb = Y + (long long)b * T * V * Cin;
+  const float* last = Yb + (long long)(T - 1) * V * Cin;
+
+  // speed ratio (test_fullframework.py:492-496): mean |hips vel| over the window, fp32 like NumPy
+  float num = 0.f, den = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float* yv = Yb + ((long long)t * V + 0) * Cin + 9;
+    num += sqrtf(yv[0] * yv[0] + yv[1] * yv[1] + yv[2] * yv[2]);
+    const float* sv = src_hips_vel + ((long long)b * T + t) * 3;
+    den += sqrtf(sv[0] * sv[0] + sv[1] * sv[1] + sv[2] * sv[2]);
+  }
+  float ratio = (num / (float)T) / (den / (float)T);
+  if (ratio > 3.0f || ratio < 0.33f) ratio = 1.0f;
+  const D3 yrvel = v3<double>((double)(src_rvel[b * 3 + 0] * ratio), (double)(src_rvel[b * 3 + 1] * ratio),
+                              (double)(src_rvel[b * 3 + 2] * ratio));
+  const D3 yrang = v3<double>((double)src_rang[b * 3 + 0], (double)src_rang[b * 3 + 1], (double)src_rang[b * 3 + 2]);
+
+  // root integration (:500-503 / :345-348)
+  const DQ prev_rot = init ? q4<double>(1.0, 0.0, 0.0, 0.0) : ld4(S.root_rot);
+  const D3 prev_pos = init ? v3<double>(0.0, 0.0, 0.0) : ld3(S.root_pos);
+  const D3 rootvel = qrot(prev_rot, yrvel);
+  const D3 rootang = qrot(prev_rot, yrang);
+  const D3 rootpos = prev_pos + dt * rootvel;
+  const DQ rootrot = qmul(prev_rot, q_from_scaled_angle_axis(dt * rootang));
+
+  // source root (:476-483): the reference keeps it in float32 arrays, so it integrates in fp32
+  {
+    const V3<float> rv = v3<float>(src_rvel[b * 3 + 0], src_rvel[b * 3 + 1], src_rvel[b * 3 + 2]);
+    const V3<float> ra = v3<float>(src_rang[b * 3 + 0], src_rang[b * 3 + 1], src_rang[b * 3 + 2]);
+    if (init) {
+      const D3 p0 = dt * v3<double>((double)rv.x, (double)rv.y, (double)rv.z);
+      const DQ r0 = q_from_scaled_angle_axis(dt * v3<double>((double)ra.x, (double)ra.y, (double)ra.z));
+      st3(O.src_root_vel, v3<double>((double)rv.x, (double)rv.y, (double)rv.z));
+      st3(O.src_root_ang, v3<double>((double)ra.x, (double)ra.y, (double)ra.z));
+      st3(O.src_root_pos, v3<double>((double)(float)p0.x, (double)(float)p0.y, (double)(float)p0.z));
+      st4(O.src_root_rot, q4<double>((double)(float)r0.w, (double)(float)r0.x, (double)(float)r0.y, (double)(float)r0.z));
+    } else {
+      const Q4<float> pr = q4<float>((float)S.src_root_rot[0], (float)S.src_root_rot[1], (float)S.src_root_rot[2],
+                                     (float)S.src_root_rot[3]);
+      const V3<float> pp = v3<float>((float)S.src_root_pos[0], (float)S.src_root_pos[1], (float)S.src_root_pos[2]);
+      const float dtf = (float)dt;
+      const V3<float> wv = qrot(pr, rv), wa = qrot(pr, ra);
+      const V3<float> np_ = pp + dtf * wv;
+      const Q4<float> nr = qmul(pr, q_from_scaled_angle_axis(dtf * wa));
+      st3(O.src_root_vel, v3<double>((double)wv.x, (double)wv.y, (double)wv.z));
+      st3(O.src_root_ang, v3<double>((double)wa.x, (double)wa.y, (double)wa.z));
+      st3(O.src_root_pos, v3<double>((double)np_.x, (double)np_.y, (double)np_.z));
+      st4(O.src_root_rot, q4<double>((double)nr.w, (double)nr.x, (double)nr.y, (double)nr.z));
+    }
+    for (int c = 0; c < 3; ++c) S.src_root_pos[c] = O.src_root_pos[c];
+    for (int c = 0; c < 4; ++c) S.src_root_rot[c] = O.src_root_rot[c];
+  }
+
+  // assemble the 25-bone pose (:505-508): joint values are fp32 results promoted to fp64
+  st3(O.pos[0], rootpos); st3(O.vel[0], rootvel); st4(O.rot[0], rootrot); st3(O.ang[0], rootang);
+  for (int j = 0; j < V; ++j) {
+    const float* y = last + (long long)j * Cin;
+    O.pos[j + 1][0] = (double)y[0]; O.pos[j + 1][1] = (double)y[1]; O.pos[j + 1][2] = (double)y[2];
+    const Q4<float> q = q_from_xy(v3<float>(y[3], y[5], y[7]), v3<float>(y[4], y[6], y[8]));
+    O.rot[j + 1][0] = (double)q.w; O.rot[j + 1][1] = (double)q.x; O.rot[j + 1][2] = (double)q.y; O.rot[j + 1][3] = (double)q.z;
+    O.vel[j + 1][0] = (double)y[9]; O.vel[j + 1][1] = (double)y[10]; O.vel[j + 1][2] = (double)y[11];
+    O.ang[j + 1][0] = (double)y[12]; O.ang[j + 1][1] = (double)y[13]; O.ang[j + 1][2] = (double)y[14];
+  }
+
+  if (init) {
+    // frame 0 (:375-434): lists start from the raw pose; contacts reset from the toe's FK state
+    for (int j = 0; j < J; ++j)
+      for (int c = 0; c < 3; ++c) {
+        O.blend_pos[j][c] = O.pos[j][c]; O.ik_pos[j][c] = O.pos[j][c];
+        S.prev_pos[j][c] = O.pos[j][c]; S.prev_ik_pos[j][c] = O.pos[j][c];
+      }
+    for (int j = 0; j < J; ++j)
+      for (int c = 0; c < 4; ++c) O.ik_rot[j][c] = O.rot[j][c];
+    for (int f = 0; f < 2; ++f) {
+      // quat.fk_vel_bone (motion/quat.py:207-237) along the ancestor chain of the toe
+      int chain[MAXJ]; int n = 0;
+      for (int j = P.contact_bones[f]; j >= 0; j = P.parents[j]) chain[n++] = j;
+      D3 gp = ld3(O.pos[chain[n - 1]]), gv = ld3(O.vel[chain[n - 1]]), ga = ld3(O.ang[chain[n - 1]]);
+      DQ gr = ld4(O.rot[chain[n - 1]]);
+      for (int k = n - 2; k >= 0; --k) {
+        const int j = chain[k];
+        const D3 rp = qrot(gr, ld3(O.pos[j]));
+        const D3 nv = gv + qrot(gr, ld3(O.vel[j])) + cross(ga, rp);
+        const D3 na = qrot(gr, ld3(O.ang[j])) + ga;
+        gp = rp + gp; gv = nv; ga = na;
+        gr = qmul(gr, ld4(O.rot[j]));
+      }
+      S.contact_state[f] = 0; S.contact_lock[f] = 0;
+      st3(S.contact_position[f], gp); st3(S.contact_velocity[f], gv);
+      st3(S.contact_point[f], gp); st3(S.contact_target[f], gp);
+      st3(S.contact_offset_position[f], v3<double>(0, 0, 0)); st3(S.contact_offset_velocity[f], v3<double>(0, 0, 0));
+    }
+    st3(S.root_pos, rootpos); st4(S.root_rot, rootrot);
+    return;
+  }
+
+  // position blending (:532-536, :626)
+  for (int j = 0; j < J; ++j)
+    for (int c = 0; c < 3; ++c) {
+      O.ik_pos[j][c] = (S.prev_ik_pos[j][c] + O.vel[j][c] * dt) * 0.5 + O.pos[j][c] * 0.5;
+      O.blend_pos[j][c] = (S.prev_pos[j][c] + O.vel[j][c] * dt) * 0.5 + O.pos[j][c] * 0.5;
+    }
+  for (int j = 0; j < J; ++j)
+    for (int c = 0; c < 4; ++c) O.ik_rot[j][c] = O.rot[j][c];
+
+  if (P.ik_enabled) {
+    for (int f = 0; f < 2; ++f) {
+      const int toe = P.contact_bones[f], heel = P.parents[toe], knee = P.parents[heel], hip = P.parents[knee],
+                rootb = P.parents[hip];
+      // quat.fk_partial (motion/quat.py:241-272) along the toe's ancestor chain, on the blended pose
+      int chain[MAXJ]; int n = 0;
+      for (int j = toe; j >= 0; j = P.parents[j]) chain[n++] = j;
+      D3 gpos[MAXJ]; DQ grot[MAXJ];
+      {
+        const int r = chain[n - 1];
+        gpos[r] = ld3(O.ik_pos[r]); grot[r] = ld4(O.rot[r]);
+        for (int k = n - 2; k >= 0; --k) {
+          const int j = chain[k], p = chain[k + 1];
+          gpos[j] = qrot(grot[p], ld3(O.ik_pos[j])) + gpos[p];
+          grot[j] = qmul(grot[p], ld4(O.rot[j]));
+        }
+      }
+      ContactState c;
+      c.state = S.contact_state[f] != 0; c.lock = S.contact_lock[f] != 0;
+      c.position = ld3(S.contact_position[f]); c.velocity = ld3(S.contact_velocity[f]);
+      c.point = ld3(S.contact_point[f]); c.target = ld3(S.contact_target[f]);
+      c.off_pos = ld3(S.contact_offset_position[f]); c.off_vel = ld3(S.contact_offset_velocity[f]);
+      contact_update_dev(c, gpos[toe], contacts[b * 2 + f] != 0, P.ik_unlock_radius, P.ik_foot_height,
+                         P.ik_blending_halflife, dt);
+      // the clamp aliases contact_positions[bs] in the reference (:581-582): it persists
+      c.position.y = fmax(c.position.y, P.ik_foot_height);
+      S.contact_state[f] = c.state; S.contact_lock[f] = c.lock;
+      st3(S.contact_position[f], c.position); st3(S.contact_velocity[f], c.velocity);
+      st3(S.contact_point[f], c.point); st3(S.contact_target[f], c.target);
+      st3(S.contact_offset_position[f], c.off_pos); st3(S.contact_offset_velocity[f], c.off_vel);
+
+      const D3 target = c.position + (gpos[heel] - gpos[toe]);
+      const D3 fwd = qrot(grot[knee], v3<double>(0.0, 1.0, 0.0));
+      DQ new_hip, new_knee;
+      ik_two_bone_dev(gpos[hip], gpos[knee], gpos[heel], target, fwd, grot[hip], grot[knee], grot[rootb],
+                      P.ik_max_length_buffer, new_hip, new_knee);
+      st4(O.ik_rot[hip], new_hip);
+      st4(O.ik_rot[knee], new_knee);
+    }
+  }
+
+  // carry state
+  st3(S.root_pos, ld3(O.blend_pos[0])); st4(S.root_rot, rootrot);
+  for (int j = 0; j < J; ++j)
+    for (int c = 0; c < 3; ++c) { S.prev_pos[j][c] = O.blend_pos[j][c]; S.prev_ik_pos[j][c] = O.ik_pos[j][c]; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched stand-alone versions (API completeness + unit parity tests)
+// ------------------------------------------------------------------------------------------------
+__global__ void contact_update_kernel(int32_t* state, int32_t* lock, double* position, double* velocity,
+                                      double* point, double* target, double* off_pos, double* off_vel,
+                                      const double* input_position, const int32_t* input_state, long long n,
+                                      double unlock_radius, double foot_height, double halflife, double dt) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ContactState c;
+  c.state = state[i] != 0; c.lock = lock[i] != 0;
+  c.position = ld3(position + i * 3); c.velocity = ld3(velocity + i * 3); c.point = ld3(point + i * 3);
+  c.target = ld3(target + i * 3); c.off_pos = ld3(off_pos + i * 3); c.off_vel = ld3(off_vel + i * 3);
+  contact_update_dev(c, ld3(input_position + i * 3), input_state[i] != 0, unlock_radius, foot_height, halflife, dt);
+  state[i] = c.state; lock[i] = c.lock;
+  st3(position + i * 3, c.position); st3(velocity + i * 3, c.velocity); st3(point + i * 3, c.point);
+  st3(target + i * 3, c.target); st3(off_pos + i * 3, c.off_pos); st3(off_vel + i * 3, c.off_vel);
+}
+
+__global__ void ik_two_bone_kernel(const double* root, const double* mid, const double* end, const double* target,
+                                   const double* fwd, const double* root_gr, const double* mid_gr,
+                                   const double* par_gr, double max_length_buffer, long long n, double* out_root_lr,
+                                   double* out_mid_lr) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  DQ a, b;
+  ik_two_bone_dev(ld3(root + i * 3), ld3(mid + i * 3), ld3(end + i * 3), ld3(target + i * 3), ld3(fwd + i * 3),
+                  ld4(root_gr + i * 4), ld4(mid_gr + i * 4), ld4(par_gr + i * 4), max_length_buffer, a, b);
+  st4(out_root_lr + i * 4, a);
+  st4(out_mid_lr + i * 4, b);
+}
+
+// Inertialization.pose_transition (Inertialization.py:136-209): thread per (skeleton, bone)
+__global__ void pose_transition_kernel(double* off_pos, double* off_vel, double* off_rot, double* off_ang,
+                                       const double* root_pos, const double* root_vel, const double* root_rot,
+                                       const double* root_ang, const double* src_pos, const double* src_vel,
+                                       const double* src_rot, const double* src_ang, const double* dst_pos,
+                                       const double* dst_vel, const double* dst_rot, const double* dst_ang,
+                                       long long n, int J, double* tr_src_pos, double* tr_src_rot,
+                                       double* tr_dst_pos, double* tr_dst_rot) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * J) return;
+  const long long s = i / J;
+  const int j = (int)(i - s * J);
+  D3 ox = ld3(off_pos + i * 3), ov = ld3(off_vel + i * 3), oa = ld3(off_ang + i * 3);
+  DQ orot = ld4(off_rot + i * 4);
+  if (j == 0) {
+    const DQ t_dst_rot = ld4(root_rot + s * 4);
+    const DQ t_src_rot = ld4(dst_rot + i * 4);
+    const D3 ws_vel = qrot(t_dst_rot, qrot(t_src_rot, ld3(dst_vel + i * 3)));
+    const D3 ws_ang = qrot(t_dst_rot, qrot(t_src_rot, ld3(dst_ang + i * 3)));
+    const D3 rp = ld3(root_pos + s * 3);
+    // inertialize_transition_pos(off, off_v, root_position, root_velocity, root_position, ws_vel)
+    ox = (rp + ox) - rp;
+    ov = (ld3(root_vel + s * 3) + ov) - ws_vel;
+    // inertialize_transition_rot(off, off_v, root_rotation, root_ang, root_rotation, ws_ang)
+    orot = qabs(qmul(qmul(orot, t_dst_rot), qinv(t_dst_rot)));
+    oa = (oa + ld3(root_ang + s * 3)) - ws_ang;
+    st3(tr_dst_pos + s * 3, rp); st4(tr_dst_rot + s * 4, t_dst_rot);
+    st3(tr_src_pos + s * 3, ld3(dst_pos + i * 3)); st4(tr_src_rot + s * 4, t_src_rot);
+  } else {
+    ox = (ld3(src_pos + i * 3) + ox) - ld3(dst_pos + i * 3);
+    ov = (ld3(src_vel + i * 3) + ov) - ld3(dst_vel + i * 3);
+    orot = qabs(qmul(qmul(orot, ld4(src_rot + i * 4)), qinv(ld4(dst_rot + i * 4))));
+    oa = (oa + ld3(src_ang + i * 3)) - ld3(dst_ang + i * 3);
+  }
+  st3(off_pos + i * 3, ox); st3(off_vel + i * 3, ov); st4(off_rot + i * 4, orot); st3(off_ang + i * 3, oa);
+}
+
+// Inertialization.pose_update (Inertialization.py:217-297): thread per (skeleton, bone)
+__global__ void pose_update_kernel(double* pos, double* vel, double* rot, double* ang, double* off_pos,
+                                   double* off_vel, double* off_rot, double* off_ang, const double* in_pos,
+                                   const double* in_vel, const double* in_rot, const double* in_ang,
+                                   const double* tr_src_pos, const double* tr_src_rot, const double* tr_dst_pos,
+                                   const double* tr_dst_rot, double halflife, double dt, long long n, int J) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * J) return;
+  const long long s = i / J;
+  const int j = (int)(i - s * J);
+  D3 ix = ld3(in_pos + i * 3), iv = ld3(in_vel + i * 3), ia = ld3(in_ang + i * 3);
+  DQ ir = ld4(in_rot + i * 4);
+  if (j == 0) {
+    const DQ dr = ld4(tr_dst_rot + s * 4), sr = ld4(tr_src_rot + s * 4);
+    const D3 dp = ld3(tr_dst_pos + s * 3), sp = ld3(tr_src_pos + s * 3);
+    ix = qrot(dr, qrot(qinv(sr), ix - sp)) + dp;
+    iv = qrot(dr, qrot(qinv(sr), iv));
+    ir = qnormalize(qmul(dr, qmul(qinv(sr), ir)));
+    ia = qrot(dr, qrot(qinv(sr), ia));
+  }
+  D3 ox = ld3(off_pos + i * 3), ov = ld3(off_vel + i * 3), oa = ld3(off_ang + i * 3);
+  DQ orot = ld4(off_rot + i * 4);
+  decay_spring_pos(ox, ov, halflife, dt);
+  decay_spring_rot(orot, oa, halflife, dt);
+  st3(pos + i * 3, ix + ox); st3(vel + i * 3, iv + ov);
+  st4(rot + i * 4, qmul(orot, ir)); st3(ang + i * 3, oa + ia);
+  st3(off_pos + i * 3, ox); st3(off_vel + i * 3, ov); st4(off_rot + i * 4, orot); st3(off_ang + i * 3, oa);
+}
+
+int check_parents_arg(const int32_t* d_parents, int J) {
+  MOCHA_CHECK_ARG(d_parents && J >= 1 && J <= MAXJ, "skeleton: need 1 <= J <= %d and a parents table", MAXJ);
+  return MOCHA_OK;
+}
+
+inline unsigned nblk(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+}  // namespace
+
+extern "C" int mocha_xy_to_quat(const float* xy, long long n, float* quat, mocha_stream_t stream) {
+  MOCHA_CHECK_ARG(xy && quat && n > 0, "mocha_xy_to_quat: bad argument");
+  MOCHA_CHECK_ARG((reinterpret_cast<uintptr_t>(quat) & 15) == 0, "mocha_xy_to_quat: output not 16B aligned");
+  xy_to_quat_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(xy, n, quat);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("xy_to_quat_kernel");
+  return MOCHA_OK;
+}
+
+extern "C" int mocha_quat_to_xy(const float* quat, long long n, float* xy, mocha_stream_t stream) {
+  MOCHA_CHECK_ARG(xy && quat && n > 0, "mocha_quat_to_xy: bad argument");
+  MOCHA_CHECK_ARG((reinterpret_cast<uintptr_t>(quat) & 15) == 0, "mocha_quat_to_xy: input not 16B aligned");
+  quat_to_xy_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(quat, n, xy);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("quat_to_xy_kernel");
+  return MOCHA_OK;
+}
+
+static unsigned fk_grid(long long F) {
+  long long g = (F + FK_WARPS - 1) / FK_WARPS;
+  const long long cap = 148LL * 16;
+  return (unsigned)(g < cap ? g : cap);
+}
+
+extern "C" int mocha_fk(const float* lrot, const float* lpos, const int32_t* parents, long long F, int J, float* grot,
+                        float* gpos, mocha_stream_t stream) {
+  MOCHA_CHECK_ARG(lrot && lpos && grot && gpos && F > 0, "mocha_fk: bad argument");
+  MOCHA_TRY(check_parents_arg(parents, J));
+  fk_kernel<false><<<fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream>>>(lrot, lpos, nullptr, nullptr, parents, F, J,
+                                                                          grot, gpos, nullptr, nullptr);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("fk_kernel");
+  return MOCHA_OK;
+}
+
+extern "C" int mocha_fk_vel(const float* lrot, const float* lpos, const float* lvel, const float* lang,
+                            const int32_t* parents, long long F, int J, float* grot, float* gpos, float* gvel,
+                            float* gang, mocha_stream_t stream) {
+  MOCHA_CHECK_ARG(lrot && lpos && lvel && lang && grot && gpos && gvel && gang && F > 0, "mocha_fk_vel: bad argument");
+  MOCHA_TRY(check_parents_arg(parents, J));
+  fk_kernel<true><<<fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream>>>(lrot, lpos, lvel, lang, parents, F, J, grot,
+                                                                         gpos, gvel, gang);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("fk_vel_kernel");
+  return MOCHA_OK;
+}
+
+extern "C" int mocha_ik(const float* grot, const float* gpos, const int32_t* parents, long long F, int J, float* lrot,
+                        float* lpos, mocha_stream_t stream) {
+  MOCHA_CHECK_ARG(lrot && lpos && grot && gpos && F > 0, "mocha_ik: bad argument");
+  MOCHA_TRY(check_parents_arg(parents, J));
+  ik_kernel<<<fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream>>>(grot, gpos, parents, F, J, lrot, lpos);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("ik_kernel");
+  return MOCHA_OK;
+}
+
+extern "C" int mocha_post_frame(const mocha_post_params* params, const float* Y, const float* src_hips_vel,
+                                const float* src_rvel, const float* src_rang, const uint8_t* contacts, int B, int T,
+                                int V, int Cin, int init, mocha_clip_state* state, mocha_frame_out* out,
+                                mocha_stream_t stream) {
+  MOCHA_CHECK_ARG(params && Y && src_hips_vel && src_rvel && src_rang && contacts && state && out && B > 0,
+                  "mocha_post_frame: null/empty argument");
+  MOCHA_CHECK_ARG(params->J == V + 1 && params->J <= 25, "mocha_post_frame: J=%d must equal V+1=%d and be <= 25",
+                  params->J, V + 1);
+  MOCHA_CHECK_ARG(Cin == 15 && T > 0, "mocha_post_frame: pose feature layout needs Cin=15");
+  MOCHA_CHECK_ARG(params->parents[0] == -1, "mocha_post_frame: parents[0] must be -1");
+  for (int j = 1; j < params->J; ++j)
+    MOCHA_CHECK_ARG(params->parents[j] >= 0 && params->parents[j] < j, "mocha_post_frame: parents[%d] out of order", j);
+  for (int f = 0; f < 2; ++f) {
+    int depth = 0;
+    for (int j = params->contact_bones[f]; j > 0 && j < params->J; j = params->parents[j]) ++depth;
+    MOCHA_CHECK_ARG(params->contact_bones[f] > 0 && params->contact_bones[f] < params->J && depth >= 4,
+                    "mocha_post_frame: contact bone %d needs 4 ancestors", params->contact_bones[f]);
+  }
+  post_frame_kernel<<<nblk(B, 64), 64, 0, (cudaStream_t)stream>>>(*params, Y, src_hips_vel, src_rvel, src_rang,
+                                                                 contacts, B, T, V, Cin, init, state, out);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("post_frame_kernel");
+  return MOCHA_OK;
+}
+
+extern "C" int mocha_contact_update(int32_t* state, int32_t* lock, double* position, double* velocity, double* point,
+                                    double* target, double* off_pos, double* off_vel, const double* input_position,
+                                    const int32_t* input_state, long long n, double unlock_radius, double foot_height,
+                                    double halflife, double dt, mocha_stream_t stream) {
+  MOCHA_CHECK_ARG(state && lock && position && velocity && point && target && off_pos && off_vel && input_position &&
+                      input_state && n > 0,
+                  "mocha_contact_update: null/empty argument");
+  contact_update_kernel<<<nblk(n, 128), 128, 0, (cudaStream_t)stream>>>(state, lock, position, velocity, point, target,
+                                                                       off_pos, off_vel, input_position, input_state,
+                                                                       n, unlock_radius, foot_height, halflife, dt);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("contact_update_kernel");
+  return MOCHA_OK;
+}
+
+extern "C" int mocha_ik_two_bone(const double* root_lr, const double* mid_lr, const double* root, const double* mid,
+                                 const double* end, const double* target, const double* fwd, const double* root_gr,
+                                 const double* mid_gr, const double* par_gr, double max_length_buffer, long long n,
+                                 double* out_root_lr, double* out_mid_lr, mocha_stream_t stream) {
+  (void)root_lr; (void)mid_lr;  // inputs the reference accepts but overwrites (motion/quat.py:340-341)
+  MOCHA_CHECK_ARG(root && mid && end && target && fwd && root_gr && mid_gr && par_gr && out_root_lr && out_mid_lr && n > 0,
+                  "mocha_ik_two_bone: null/empty argument");
+  ik_two_bone_kernel<<<nblk(n, 128), 128, 0, (cudaStream_t)stream>>>(root, mid, end, target, fwd, root_gr, mid_gr,
+                                                                    par_gr, max_length_buffer, n, out_root_lr,
+                                                                    out_mid_lr);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("ik_two_bone_kernel");
+  return MOCHA_OK;
+}
+
+extern "C" int mocha_pose_transition(double* off_pos, double* off_vel, double* off_rot, double* off_ang,
+                                     const double* root_pos, const double* root_vel, const double* root_rot,
+                                     const double* root_ang, const double* src_pos, const double* src_vel,
+                                     const double* src_rot, const double* src_ang, const double* dst_pos,
+                                     const double* dst_vel, const double* dst_rot, const double* dst_ang, long long n,
+                                     int J, double* tr_src_pos, double* tr_src_rot, double* tr_dst_pos,
+                                     double* tr_dst_rot, mocha_stream_t stream) {
+  MOCHA_CHECK_ARG(off_pos && off_vel && off_rot && off_ang && root_pos && root_vel && root_rot && root_ang && src_pos &&
+                      src_vel && src_rot && src_ang && dst_pos && dst_vel && dst_rot && dst_ang && tr_src_pos &&
+                      tr_src_rot && tr_dst_pos && tr_dst_rot && n > 0 && J > 0,
+                  "mocha_pose_transition: null/empty argument");
+  pose_transition_kernel<<<nblk(n * J, 128), 128, 0, (cudaStream_t)stream>>>(
+      off_pos, off_vel, off_rot, off_ang, root_pos, root_vel, root_rot, root_ang, src_pos, src_vel, src_rot, src_ang,
+      dst_pos, dst_vel, dst_rot, dst_ang, n, J, tr_src_pos, tr_src_rot, tr_dst_pos, tr_dst_rot);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("pose_transition_kernel");
+  return MOCHA_OK;
+}
+
+extern "C" int mocha_pose_update(double* pos, double* vel, double* rot, double* ang, double* off_pos, double* off_vel,
+                                 double* off_rot, double* off_ang, const double* in_pos, const double* in_vel,
+                                 const double* in_rot, const double* in_ang, const double* tr_src_pos,
+                                 const double* tr_src_rot, const double* tr_dst_pos, const double* tr_dst_rot,
+                                 double halflife, double dt, long long n, int J, mocha_stream_t stream) {
+  MOCHA_CHECK_ARG(pos && vel && rot && ang && off_pos && off_vel && off_rot && off_ang && in_pos && in_vel && in_rot &&
+                      in_ang && tr_src_pos && tr_src_rot && tr_dst_pos && tr_dst_rot && n > 0 && J > 0,
+                  "mocha_pose_update: null/empty argument");
+  pose_update_kernel<<<nblk(n * J, 128), 128, 0, (cudaStream_t)stream>>>(pos, vel, rot, ang, off_pos, off_vel, off_rot,
+                                                                        off_ang, in_pos, in_vel, in_rot, in_ang,
+                                                                        tr_src_pos, tr_src_rot, tr_dst_pos, tr_dst_rot,
+                                                                        halflife, dt, n, J);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("pose_update_kernel");
+  return MOCHA_OK;
+}

@@ -1,0 +1,319 @@
+// Context matching: exact Euclidean k-NN of encoded queries against the character
+// feature DB. Semantics of sklearn.neighbors.BallTree(X).query(q, k) as called at
+// test_fullframework.py:293-296 and :440-443 (float64 arithmetic on float32 inputs).
+//   * mocha_match_exact : brute force in fp64, HBM-bound streaming of the DB (batch-1 / small N)
+//   * mocha_match_tc    : tcgen05 coarse pass with fused top-kc epilogue (gemm_tc.cu) + this file's
+//                         candidate merge and exact fp64 re-rank
+#include "../../include/mocha_b200.h"
+#include "common.cuh"
+#include "gemm_tc.cuh"
+
+using namespace mocha;
+
+namespace {
+
+constexpr int KMAX = 16;
+constexpr int EXQ = 4;  // queries per pass of the exact kernel
+
+// One warp per DB row; the row is streamed once and compared against EXQ queries.
+__global__ void __launch_bounds__(256)
+match_exact_dist_kernel(const float* __restrict__ Q, int nq, int q0, const float* __restrict__ DB, long long N,
+                        int D, double* __restrict__ dist2) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  if (row >= N) return;
+  const float* x = DB + row * (long long)D;
+  double acc[EXQ];
+#pragma unroll
+  for (int j = 0; j < EXQ; ++j) acc[j] = 0.0;
+  const int nqq = min(EXQ, nq - q0);
+  if ((D & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(Q) & 15) == 0)) {
+    for (int d = lane * 4; d < D; d += 128) {
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + d));
+#pragma unroll
+      for (int j = 0; j < EXQ; ++j) {
+        if (j < nqq) {
+          const float4 qv = __ldg(reinterpret_cast<const float4*>(Q + (long long)(q0 + j) * D + d));
+          const double a = (double)qv.x - (double)xv.x, b = (double)qv.y - (double)xv.y;
+          const double c = (double)qv.z - (double)xv.z, e = (double)qv.w - (double)xv.w;
+          acc[j] = fma(a, a, acc[j]);
+          acc[j] = fma(b, b, acc[j]);
+          acc[j] = fma(c, c, acc[j]);
+          acc[j] = fma(e, e, acc[j]);
+        }
+      }
+    }
+  } else {
+    for (int d = lane; d < D; d += 32) {
+      const double xv = (double)x[d];
+#pragma unroll
+      for (int j = 0; j < EXQ; ++j)
+        if (j < nqq) {
+          const double a = (double)Q[(long long)(q0 + j) * D + d] - xv;
+          acc[j] = fma(a, a, acc[j]);
+        }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < EXQ; ++j) {
+    const double s = warp_sum(acc[j]);
+    if (lane == 0 && j < nqq) dist2[(long long)(q0 + j) * N + row] = s;
+  }
+}
+
+__device__ __forceinline__ bool better(double d0, long long i0, double d1, long long i1) {
+  return d0 < d1 || (d0 == d1 && i0 < i1);
+}
+
+// Block-wide top-k of (value, index) pairs by (value asc, index asc). Each thread feeds its own
+// candidates through `local insert`, then k rounds of block arg-min pop the winners.
+template <int NT>
+__device__ void block_topk_pop(double (&ls)[KMAX], long long (&li)[KMAX], int k, double* out_d, long long* out_i,
+                               double* red_d, long long* red_i, int* red_t) {
+  for (int r = 0; r < k; ++r) {
+    // every thread proposes the head of its (ascending) local list
+    double d = ls[0];
+    long long i = li[0];
+    int t = threadIdx.x;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double d2 = __shfl_xor_sync(0xffffffffu, d, o);
+      const long long i2 = __shfl_xor_sync(0xffffffffu, i, o);
+      const int t2 = __shfl_xor_sync(0xffffffffu, t, o);
+      const bool take = (i2 >= 0) && (i < 0 || better(d2, i2, d, i));
+      if (take) { d = d2; i = i2; t = t2; }
+    }
+    if ((threadIdx.x & 31) == 0) { red_d[threadIdx.x >> 5] = d; red_i[threadIdx.x >> 5] = i; red_t[threadIdx.x >> 5] = t; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double bd = red_d[0]; long long bi = red_i[0]; int bt = red_t[0];
+      for (int w = 1; w < NT / 32; ++w) {
+        if (red_i[w] >= 0 && (bi < 0 || better(red_d[w], red_i[w], bd, bi))) { bd = red_d[w]; bi = red_i[w]; bt = red_t[w]; }
+      }
+      out_d[r] = bd; out_i[r] = bi; red_t[0] = bt;
+    }
+    __syncthreads();
+    if (threadIdx.x == red_t[0] && out_i[r] >= 0) {
+      // pop: shift the local list left (static indices keep it in registers)
+#pragma unroll
+      for (int j = 0; j + 1 < KMAX; ++j) { ls[j] = ls[j + 1]; li[j] = li[j + 1]; }
+      ls[KMAX - 1] = INFINITY; li[KMAX - 1] = -1;
+    }
+    __syncthreads();
+  }
+}
+
+// keep the k best (ascending by (value, index)) in ls/li; slots >= k stay empty
+__device__ __forceinline__ void local_insert(double (&ls)[KMAX], long long (&li)[KMAX], int k, double d, long long i) {
+#pragma unroll
+  for (int t = 0; t < KMAX; ++t) {
+    if (t < k && i >= 0 && (li[t] < 0 || better(d, i, ls[t], li[t]))) {
+      const double td = ls[t]; ls[t] = d; d = td;
+      const long long ti = li[t]; li[t] = i; i = ti;
+    }
+  }
+}
+
+// one block per query: top-k over a row of squared distances
+__global__ void __launch_bounds__(256)
+topk_rows_kernel(const double* __restrict__ dist2, long long N, int k, long long index_offset,
+                 int64_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+  __shared__ double red_d[8]; __shared__ long long red_i[8]; __shared__ int red_t[8];
+  __shared__ double od[KMAX]; __shared__ long long oi[KMAX];
+  const int q = blockIdx.x;
+  const double* row = dist2 + (long long)q * N;
+  double ls[KMAX]; long long li[KMAX];
+#pragma unroll
+  for (int t = 0; t < KMAX; ++t) { ls[t] = INFINITY; li[t] = -1; }
+  for (long long n = threadIdx.x; n < N; n += 256) local_insert(ls, li, k, row[n], n);
+  block_topk_pop<256>(ls, li, k, od, oi, red_d, red_i, red_t);
+  if (threadIdx.x < k) {
+    out_idx[(long long)q * k + threadIdx.x] = oi[threadIdx.x] >= 0 ? oi[threadIdx.x] + index_offset : -1;
+    if (out_dist) out_dist[(long long)q * k + threadIdx.x] = sqrt(od[threadIdx.x]);
+  }
+}
+
+// one block per query: merge coarse candidates, exact fp64 re-rank of the best kc, emit top-k
+__global__ void __launch_bounds__(256)
+match_rerank_kernel(const float* __restrict__ Q, const __nv_bfloat16* __restrict__ DB16,
+                    const float* __restrict__ DB32, int D, const float* __restrict__ cand_score,
+                    const int32_t* __restrict__ cand_idx, int ncand, int kc, int k, long long index_offset,
+                    int64_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+  __shared__ double red_d[8]; __shared__ long long red_i[8]; __shared__ int red_t[8];
+  __shared__ double od[KMAX]; __shared__ long long oi[KMAX];
+  __shared__ double exact[KMAX];
+  const int q = blockIdx.x;
+  const float* cs = cand_score + (long long)q * ncand;
+  const int32_t* ci = cand_idx + (long long)q * ncand;
+  double ls[KMAX]; long long li[KMAX];
+#pragma unroll
+  for (int t = 0; t < KMAX; ++t) { ls[t] = INFINITY; li[t] = -1; }
+  for (int n = threadIdx.x; n < ncand; n += 256) {
+    const int32_t id = ci[n];
+    if (id >= 0) local_insert(ls, li, kc, (double)cs[n], (long long)id);
+  }
+  block_topk_pop<256>(ls, li, kc, od, oi, red_d, red_i, red_t);
+  // exact squared distances of the kc survivors, one warp per candidate
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* qv = Q + (long long)q * D;
+  for (int c = warp; c < kc; c += 8) {
+    const long long id = oi[c];
+    double acc = 0.0;
+    if (id >= 0) {
+      if (DB32) {
+        const float* x = DB32 + id * (long long)D;
+        for (int d = lane; d < D; d += 32) { const double a = (double)qv[d] - (double)x[d]; acc = fma(a, a, acc); }
+      } else {
+        const __nv_bfloat16* x = DB16 + id * (long long)D;
+        for (int d = lane; d < D; d += 32) { const double a = (double)qv[d] - (double)__bfloat162float(x[d]); acc = fma(a, a, acc); }
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) exact[c] = id >= 0 ? acc : INFINITY;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // insertion sort of <= 16 entries by (distance, index)
+    double d[KMAX]; long long id[KMAX];
+    int m = 0;
+    for (int c = 0; c < kc; ++c) {
+      if (oi[c] < 0) continue;
+      int p = m++;
+      d[p] = exact[c]; id[p] = oi[c];
+      while (p > 0 && better(d[p], id[p], d[p - 1], id[p - 1])) {
+        const double td = d[p]; d[p] = d[p - 1]; d[p - 1] = td;
+        const long long ti = id[p]; id[p] = id[p - 1]; id[p - 1] = ti;
+        --p;
+      }
+    }
+    for (int r = 0; r < k; ++r) {
+      out_idx[(long long)q * k + r] = r < m ? id[r] + index_offset : -1;
+      if (out_dist) out_dist[(long long)q * k + r] = r < m ? sqrt(d[r]) : INFINITY;
+    }
+  }
+}
+
+// warp per row: fp32 -> bf16 rows + squared norm of the rounded row
+__global__ void __launch_bounds__(256)
+db_pack_kernel(const float* __restrict__ rows, long long N, int D, __nv_bfloat16* __restrict__ rows16,
+               float* __restrict__ norm) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 8 + warp;
+  if (r >= N) return;
+  const float* x = rows + r * (long long)D;
+  __nv_bfloat16* y = rows16 + r * (long long)D;
+  float acc = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const __nv_bfloat16 b = __float2bfloat16_rn(x[d]);
+    y[d] = b;
+    const float f = __bfloat162float(b);
+    acc = fmaf(f, f, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0 && norm) norm[r] = acc;
+}
+
+// thread per query: merge nshard sorted (dist, idx) lists of length k
+__global__ void topk_merge_kernel(const double* __restrict__ dist, const int64_t* __restrict__ idx, int nshard,
+                                  int nq, int k, double* __restrict__ out_dist, int64_t* __restrict__ out_idx) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  int head[64];
+  for (int s = 0; s < nshard; ++s) head[s] = 0;
+  for (int r = 0; r < k; ++r) {
+    int bs = -1; double bd = 0.0; long long bi = -1;
+    for (int s = 0; s < nshard; ++s) {
+      if (head[s] >= k) continue;
+      const long long o = ((long long)s * nq + q) * k + head[s];
+      const long long id = idx[o];
+      if (id < 0) continue;
+      const double d = dist[o];
+      if (bs < 0 || better(d, id, bd, bi)) { bs = s; bd = d; bi = id; }
+    }
+    if (bs >= 0) ++head[bs];
+    out_idx[(long long)q * k + r] = bi;
+    if (out_dist) out_dist[(long long)q * k + r] = bs >= 0 ? bd : INFINITY;
+  }
+}
+
+}  // namespace
+
+extern "C" size_t mocha_match_exact_workspace_bytes(int nq, long long N, int k) {
+  (void)k;
+  if (nq <= 0 || N <= 0) return 0;
+  return align_up((size_t)nq * (size_t)N * sizeof(double), 256) + 256;
+}
+
+extern "C" int mocha_match_exact(const float* Q, int nq, const float* DB, long long N, int D, int k,
+                                 long long index_offset, int64_t* idx, double* dist, void* workspace,
+                                 size_t workspace_bytes, mocha_stream_t stream) {
+  MOCHA_CHECK_ARG(Q && DB && idx, "mocha_match_exact: null argument");
+  MOCHA_CHECK_ARG(nq > 0 && N > 0 && D > 0, "mocha_match_exact: empty problem nq=%d N=%lld D=%d", nq, N, D);
+  MOCHA_CHECK_ARG(k >= 1 && k <= KMAX && k <= N, "mocha_match_exact: k=%d out of range (1..min(%d,N))", k, KMAX);
+  Workspace ws(workspace, workspace_bytes);
+  double* dist2 = ws.take<double>((size_t)nq * (size_t)N);
+  if (ws.overflow)
+    return set_error(MOCHA_ERR_WORKSPACE, "mocha_match_exact: workspace too small (%zu B given, %zu B needed)",
+                     workspace_bytes, ws.off);
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)((N + 7) / 8);
+  for (int q0 = 0; q0 < nq; q0 += EXQ) {
+    match_exact_dist_kernel<<<blocks, 256, 0, s>>>(Q, nq, q0, DB, N, D, dist2);
+    count_launch();
+  }
+  MOCHA_LAUNCH_CHECK("match_exact_dist_kernel");
+  topk_rows_kernel<<<nq, 256, 0, s>>>(dist2, N, k, index_offset, idx, dist);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("topk_rows_kernel");
+  return MOCHA_OK;
+}
+
+extern "C" size_t mocha_match_tc_workspace_bytes(int nq, long long N, int D, int kc) {
+  (void)D;
+  if (nq <= 0 || N <= 0 || kc <= 0) return 0;
+  const size_t ncand = (size_t)tc_match_splits(nq, N) * kc;
+  return 2 * (align_up((size_t)nq * ncand * 4, 256)) + 512;
+}
+
+extern "C" int mocha_match_tc(const float* Q, const void* Q16, int nq, const void* DB16, const float* DB32,
+                              const float* dbnorm, long long N, int D, int k, int kc, long long index_offset,
+                              int64_t* idx, double* dist, void* workspace, size_t workspace_bytes,
+                              mocha_stream_t stream) {
+  MOCHA_CHECK_ARG(Q && Q16 && DB16 && dbnorm && idx, "mocha_match_tc: null argument");
+  MOCHA_CHECK_ARG(k >= 1 && k <= kc && kc <= KMAX, "mocha_match_tc: need 1 <= k <= kc <= %d", KMAX);
+  MOCHA_CHECK_ARG(k <= N, "mocha_match_tc: k=%d > N=%lld", k, N);
+  Workspace ws(workspace, workspace_bytes);
+  const int splits = tc_match_splits(nq, N);
+  const size_t ncand = (size_t)splits * kc;
+  float* cs = ws.take<float>((size_t)nq * ncand);
+  int32_t* ci = ws.take<int32_t>((size_t)nq * ncand);
+  if (ws.overflow)
+    return set_error(MOCHA_ERR_WORKSPACE, "mocha_match_tc: workspace too small (%zu B given, %zu B needed)",
+                     workspace_bytes, ws.off);
+  cudaStream_t s = (cudaStream_t)stream;
+  MOCHA_TRY(tc_match_coarse((const __nv_bfloat16*)Q16, nq, (const __nv_bfloat16*)DB16, dbnorm, N, D, kc, cs, ci, s));
+  match_rerank_kernel<<<nq, 256, 0, s>>>(Q, (const __nv_bfloat16*)DB16, DB32, D, cs, ci, (int)ncand, kc, k,
+                                         index_offset, idx, dist);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("match_rerank_kernel");
+  return MOCHA_OK;
+}
+
+extern "C" int mocha_db_pack_bf16(const float* rows, long long N, int D, void* rows16, float* norm,
+                                  mocha_stream_t stream) {
+  MOCHA_CHECK_ARG(rows && rows16 && N > 0 && D > 0, "mocha_db_pack_bf16: bad argument");
+  db_pack_kernel<<<(unsigned)((N + 7) / 8), 256, 0, (cudaStream_t)stream>>>(rows, N, D, (__nv_bfloat16*)rows16, norm);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("db_pack_kernel");
+  return MOCHA_OK;
+}
+
+extern "C" int mocha_topk_merge(const double* dist, const int64_t* idx, int nshard, int nq, int k, double* out_dist,
+                                int64_t* out_idx, mocha_stream_t stream) {
+  MOCHA_CHECK_ARG(dist && idx && out_idx, "mocha_topk_merge: null argument");
+  MOCHA_CHECK_ARG(nshard >= 1 && nshard <= 64 && nq > 0 && k >= 1 && k <= KMAX, "mocha_topk_merge: bad sizes");
+  topk_merge_kernel<<<(nq + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dist, idx, nshard, nq, k, out_dist, out_idx);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("topk_merge_kernel");
+  return MOCHA_OK;
+}

@@ -1,0 +1,432 @@
+// Bandwidth/latency-bound building blocks (see ops.cuh for the reference citations).
+#include "ops.cuh"
+
+namespace mocha {
+
+namespace {
+
+__global__ void graph_agg_first_kernel(const float* __restrict__ in, const float* __restrict__ A,
+                                       float* __restrict__ out, int V, int C, int Kk, int lrelu) {
+  extern __shared__ float sm[];
+  float* xs = sm;              // [V][C]
+  float* As = sm + V * C;      // [Kk][V][V]
+  const int bt = blockIdx.x;
+  const float* src = in + (long long)bt * V * C;
+  for (int i = threadIdx.x; i < V * C; i += blockDim.x) {
+    float v = src[i];
+    xs[i] = lrelu ? lrelu02(v) : v;
+  }
+  for (int i = threadIdx.x; i < Kk * V * V; i += blockDim.x) As[i] = A[i];
+  __syncthreads();
+  const int KC = Kk * C;
+  float* dst = out + (long long)bt * V * KC;
+  for (int idx = threadIdx.x; idx < V * KC; idx += blockDim.x) {
+    const int w = idx / KC, rem = idx - w * KC;
+    const int k = rem / C, c = rem - k * C;
+    const float* a = As + k * V * V + w;
+    float acc = 0.f;
+    for (int u = 0; u < V; ++u) {
+      const float av = a[u * V];
+      if (av != 0.f) acc = fmaf(xs[u * C + c], av, acc);
+    }
+    dst[idx] = acc;
+  }
+}
+
+__global__ void graph_agg_kv_kernel(const float* __restrict__ in, const float* __restrict__ A2,
+                                    float* __restrict__ out, int U, int Wn, int C, int Kk) {
+  extern __shared__ float sm[];
+  const int KC = Kk * C;
+  float* xs = sm;               // [U][Kk*C]
+  float* As = sm + U * KC;      // [Kk][U][Wn]
+  const int bt = blockIdx.x;
+  const float* src = in + (long long)bt * U * KC;
+  for (int i = threadIdx.x; i < U * KC; i += blockDim.x) xs[i] = src[i];
+  for (int i = threadIdx.x; i < Kk * U * Wn; i += blockDim.x) As[i] = A2[i];
+  __syncthreads();
+  float* dst = out + (long long)bt * Wn * C;
+  for (int idx = threadIdx.x; idx < Wn * C; idx += blockDim.x) {
+    const int w = idx / C, c = idx - w * C;
+    float acc = 0.f;
+    for (int k = 0; k < Kk; ++k)
+      for (int u = 0; u < U; ++u) {
+        const float av = As[(k * U + u) * Wn + w];
+        if (av != 0.f) acc = fmaf(xs[u * KC + k * C + c], av, acc);
+      }
+    dst[idx] = acc;
+  }
+}
+
+constexpr int POOL_MAXP = 8;
+__global__ void pool_joint_body_kernel(const float* __restrict__ in, const float* __restrict__ Wp,
+                                       float* __restrict__ out, int T, int V, int P, int C, int tp) {
+  extern __shared__ float ws[];  // [V][P]
+  for (int i = threadIdx.x; i < V * P; i += blockDim.x) ws[i] = Wp[i];
+  __syncthreads();
+  const int Tp = T / tp;
+  const int b = blockIdx.x / Tp, t2 = blockIdx.x % Tp;
+  const float inv = 1.f / (float)tp;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc[POOL_MAXP];
+#pragma unroll
+    for (int p = 0; p < POOL_MAXP; ++p) acc[p] = 0.f;
+    for (int dt = 0; dt < tp; ++dt) {
+      const float* src = in + ((long long)(b * T + t2 * tp + dt) * V) * C + c;
+      for (int v = 0; v < V; ++v) {
+        const float x = src[(long long)v * C];
+#pragma unroll
+        for (int p = 0; p < POOL_MAXP; ++p)
+          if (p < P) acc[p] = fmaf(x, ws[v * P + p], acc[p]);
+      }
+    }
+    float* dst = out + ((long long)(b * Tp + t2) * P) * C + c;
+#pragma unroll
+    for (int p = 0; p < POOL_MAXP; ++p)
+      if (p < P) dst[(long long)p * C] = acc[p] * inv;
+  }
+}
+
+__global__ void instance_norm_tokens_kernel(const float* __restrict__ x, int n, int C, float eps,
+                                            const float* __restrict__ gb, float* __restrict__ y,
+                                            const float* __restrict__ tab_mean,
+                                            const float* __restrict__ tab_std, float* __restrict__ y2) {
+  const int b = blockIdx.x;
+  const float* xb = x + (long long)b * n * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int i = 0; i < n; ++i) s += xb[(long long)i * C + c];
+    const float mean = s / (float)n;
+    float q = 0.f;
+    for (int i = 0; i < n; ++i) {
+      const float d = xb[(long long)i * C + c] - mean;
+      q = fmaf(d, d, q);
+    }
+    const float sd = sqrtf(q / (float)(n - 1));
+    const float den = sd + eps;
+    float g = 1.f, be = 0.f;
+    if (gb) {
+      g = 1.f + gb[(long long)b * 2 * C + c];
+      be = gb[(long long)b * 2 * C + C + c];
+    }
+    for (int i = 0; i < n; ++i) {
+      const long long o = (long long)i * C + c;
+      // same operation order as the reference: divide, then modulate
+      float v = (xb[o] - mean) / den;
+      if (gb) v = g * v + be;
+      if (y) y[(long long)b * n * C + o] = v;
+      if (y2) y2[(long long)b * n * C + o] = (v - tab_mean[o]) / tab_std[o];
+    }
+  }
+}
+
+__global__ void token_mean_kernel(const float* __restrict__ x, int n, int C, float* __restrict__ out) {
+  const int b = blockIdx.x;
+  const float* xb = x + (long long)b * n * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int i = 0; i < n; ++i) s += xb[(long long)i * C + c];
+    out[(long long)b * C + c] = s / (float)n;
+  }
+}
+
+constexpr int SM_MAXPL = 8;  // up to 256 columns per row
+__global__ void softmax_rows_kernel(float* __restrict__ S, long long rows, int ncols, float scale) {
+  const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * warps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float* r = S + row * ncols;
+  float v[SM_MAXPL];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < SM_MAXPL; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = c < ncols ? r[c] * scale : -INFINITY;
+    m = fmaxf(m, v[i]);
+  }
+  m = warp_max(m);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < SM_MAXPL; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = c < ncols ? expf(v[i] - m) : 0.f;
+    sum += v[i];
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int i = 0; i < SM_MAXPL; ++i) {
+    const int c = lane + 32 * i;
+    if (c < ncols) r[c] = v[i] * inv;
+  }
+}
+
+__global__ void add_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ r,
+                                     const float* __restrict__ g, const float* __restrict__ b,
+                                     float* __restrict__ y, long long rows, int C, float eps,
+                                     const float* __restrict__ tab_mean, const float* __restrict__ tab_std,
+                                     int period, float* __restrict__ y2) {
+  const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * warps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * C;
+  const float* rr = r ? r + row * C : nullptr;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += xr[c] + (rr ? rr[c] : 0.f);
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float d = xr[c] + (rr ? rr[c] : 0.f) - mean;
+    q = fmaf(d, d, q);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  for (int c = lane; c < C; c += 32) {
+    const float v = (xr[c] + (rr ? rr[c] : 0.f) - mean) * rstd * g[c] + b[c];
+    if (y) y[row * C + c] = v;
+    if (y2) {
+      const long long o = (row % period) * C + c;
+      y2[row * C + c] = v * tab_std[o] + tab_mean[o];
+    }
+  }
+}
+
+__global__ void cvae_prior_tokens_kernel(const float* __restrict__ mu_token, const float* __restrict__ lv_token,
+                                         const float* __restrict__ cond, const float* __restrict__ pe,
+                                         float* __restrict__ tok, int ncond, int C, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int n = ncond + 2;
+  const int c = (int)(i % C);
+  const int t = (int)((i / C) % n);
+  const long long b = i / ((long long)C * n);
+  float v;
+  if (t == 0) v = mu_token[c];
+  else if (t == 1) v = lv_token[c];
+  else v = cond[(b * ncond + (t - 2)) * C + c];
+  tok[i] = v + pe[(long long)t * C + c];
+}
+
+__global__ void cvae_memory_kernel(const float* __restrict__ prior_out, int prior_tokens,
+                                   const float* __restrict__ eps, const float* __restrict__ cond,
+                                   float* __restrict__ mem, float* __restrict__ mu_out,
+                                   float* __restrict__ lv_out, int ncond, int C, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int n = ncond + 1;
+  const int c = (int)(i % C);
+  const int t = (int)((i / C) % n);
+  const long long b = i / ((long long)C * n);
+  if (t == 0) {
+    const float mu = prior_out[(b * prior_tokens + 0) * C + c];
+    const float lv = prior_out[(b * prior_tokens + 1) * C + c];
+    float z = mu;
+    if (eps) z = mu + eps[b * C + c] * expf(0.5f * lv);
+    mem[i] = z;
+    if (mu_out) mu_out[b * C + c] = mu;
+    if (lv_out) lv_out[b * C + c] = lv;
+  } else {
+    mem[i] = cond[(b * ncond + (t - 1)) * C + c];
+  }
+}
+
+__global__ void cvae_condition_kernel(const float* __restrict__ src_cnt, const float* __restrict__ prev,
+                                      const float* __restrict__ m0, const float* __restrict__ s0,
+                                      const float* __restrict__ m1, const float* __restrict__ s1,
+                                      float* __restrict__ cond, int n, int C, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long per = (long long)n * C;
+  const long long b = i / (2 * per);
+  const long long r = i - b * 2 * per;
+  if (r < per) cond[i] = (src_cnt[b * per + r] - m0[r]) / s0[r];
+  else cond[i] = (prev[b * per + (r - per)] - m1[r - per]) / s1[r - per];
+}
+
+__global__ void affine_rows_kernel(const float* __restrict__ x, const float* __restrict__ mu,
+                                   const float* __restrict__ sd, float* __restrict__ out, long long total,
+                                   int C, int period) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long o = i % ((long long)period * C);
+  out[i] = x[i] * sd[o] + mu[o];
+}
+
+__global__ void broadcast_rows_kernel(const float* __restrict__ x, float* __restrict__ out, long long n_elems,
+                                      long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  out[i] = x[i % n_elems];
+}
+
+__global__ void add_table_kernel(const float* __restrict__ a, const float* __restrict__ table,
+                                 float* __restrict__ out, long long total, int C, int period) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  out[i] = a[i] + table[i % ((long long)period * C)];
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(x + i);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(y + i) = pk;
+  } else {
+    for (long long j = i; j < n; ++j) y[j] = __float2bfloat16_rn(x[j]);
+  }
+}
+
+inline unsigned blocks_for(long long total, int bs) { return (unsigned)((total + bs - 1) / bs); }
+
+}  // namespace
+
+int graph_agg_first(const float* in, const float* A, float* out, int BT, int V, int C, int Kk, int lrelu,
+                    cudaStream_t s) {
+  MOCHA_CHECK_ARG(in && A && out && BT > 0 && V > 0 && C > 0 && Kk > 0, "graph_agg_first: bad args");
+  size_t smem = (size_t)(V * C + Kk * V * V) * sizeof(float);
+  MOCHA_CHECK_ARG(smem <= 48 * 1024, "graph_agg_first: tile too large (%zu B)", smem);
+  graph_agg_first_kernel<<<BT, 256, smem, s>>>(in, A, out, V, C, Kk, lrelu);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("graph_agg_first");
+  return MOCHA_OK;
+}
+
+int graph_agg_kv(const float* in, const float* A2, float* out, int BT, int U, int Wn, int C, int Kk,
+                 cudaStream_t s) {
+  MOCHA_CHECK_ARG(in && A2 && out && BT > 0 && U > 0 && Wn > 0 && C > 0 && Kk > 0, "graph_agg_kv: bad args");
+  size_t smem = (size_t)(U * Kk * C + Kk * U * Wn) * sizeof(float);
+  MOCHA_CHECK_ARG(smem <= 48 * 1024, "graph_agg_kv: tile too large (%zu B)", smem);
+  graph_agg_kv_kernel<<<BT, 256, smem, s>>>(in, A2, out, U, Wn, C, Kk);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("graph_agg_kv");
+  return MOCHA_OK;
+}
+
+int pool_joint_body(const float* in, const float* Wp, float* out, int B, int T, int V, int P, int C, int tp,
+                    cudaStream_t s) {
+  MOCHA_CHECK_ARG(in && Wp && out && B > 0 && T > 0 && V > 0 && C > 0, "pool_joint_body: bad args");
+  MOCHA_CHECK_ARG(P > 0 && P <= POOL_MAXP, "pool_joint_body: P=%d unsupported (max %d)", P, POOL_MAXP);
+  MOCHA_CHECK_ARG(tp > 0 && T % tp == 0, "pool_joint_body: T=%d not a multiple of tp=%d", T, tp);
+  pool_joint_body_kernel<<<B * (T / tp), 256, (size_t)V * P * sizeof(float), s>>>(in, Wp, out, T, V, P, C, tp);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("pool_joint_body");
+  return MOCHA_OK;
+}
+
+int instance_norm_tokens(const float* x, int B, int n, int C, float eps, const float* gb, float* y,
+                         const float* tab_mean, const float* tab_std, float* y2, cudaStream_t s) {
+  MOCHA_CHECK_ARG(x && B > 0 && n > 1 && C > 0, "instance_norm_tokens: bad args");
+  MOCHA_CHECK_ARG(y || y2, "instance_norm_tokens: no output");
+  MOCHA_CHECK_ARG(!y2 || (tab_mean && tab_std), "instance_norm_tokens: y2 needs its table");
+  instance_norm_tokens_kernel<<<B, 256, 0, s>>>(x, n, C, eps, gb, y, tab_mean, tab_std, y2);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("instance_norm_tokens");
+  return MOCHA_OK;
+}
+
+int token_mean(const float* x, int B, int n, int C, float* out, cudaStream_t s) {
+  MOCHA_CHECK_ARG(x && out && B > 0 && n > 0 && C > 0, "token_mean: bad args");
+  token_mean_kernel<<<B, 256, 0, s>>>(x, n, C, out);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("token_mean");
+  return MOCHA_OK;
+}
+
+int softmax_rows(float* S, long long rows, int ncols, float scale, cudaStream_t s) {
+  MOCHA_CHECK_ARG(S && rows > 0 && ncols > 0, "softmax_rows: bad args");
+  MOCHA_CHECK_ARG(ncols <= 32 * SM_MAXPL, "softmax_rows: ncols=%d > %d", ncols, 32 * SM_MAXPL);
+  softmax_rows_kernel<<<blocks_for(rows, 8), 256, 0, s>>>(S, rows, ncols, scale);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("softmax_rows");
+  return MOCHA_OK;
+}
+
+int add_layernorm(const float* x, const float* r, const float* g, const float* b, float* y, long long rows,
+                  int C, float eps, const float* tab_mean, const float* tab_std, int period, float* y2,
+                  cudaStream_t s) {
+  MOCHA_CHECK_ARG(x && g && b && rows > 0 && C > 0, "add_layernorm: bad args");
+  MOCHA_CHECK_ARG(y || y2, "add_layernorm: no output");
+  MOCHA_CHECK_ARG(!y2 || (tab_mean && tab_std && period > 0), "add_layernorm: y2 needs its table");
+  add_layernorm_kernel<<<blocks_for(rows, 8), 256, 0, s>>>(x, r, g, b, y, rows, C, eps, tab_mean, tab_std,
+                                                          period, y2);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("add_layernorm");
+  return MOCHA_OK;
+}
+
+int cvae_prior_tokens(const float* mu_token, const float* logvar_token, const float* cond, const float* pe,
+                      float* tok, int B, int ncond, int C, cudaStream_t s) {
+  MOCHA_CHECK_ARG(mu_token && logvar_token && cond && pe && tok && B > 0 && ncond > 0 && C > 0,
+                  "cvae_prior_tokens: bad args");
+  const long long total = (long long)B * (ncond + 2) * C;
+  cvae_prior_tokens_kernel<<<blocks_for(total, 256), 256, 0, s>>>(mu_token, logvar_token, cond, pe, tok, ncond,
+                                                                  C, total);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("cvae_prior_tokens");
+  return MOCHA_OK;
+}
+
+int cvae_memory(const float* prior_out, int prior_tokens, const float* eps, const float* cond, float* mem,
+                float* mu_out, float* logvar_out, int B, int ncond, int C, cudaStream_t s) {
+  MOCHA_CHECK_ARG(prior_out && cond && mem && B > 0 && ncond > 0 && C > 0 && prior_tokens >= 2,
+                  "cvae_memory: bad args");
+  const long long total = (long long)B * (ncond + 1) * C;
+  cvae_memory_kernel<<<blocks_for(total, 256), 256, 0, s>>>(prior_out, prior_tokens, eps, cond, mem, mu_out,
+                                                            logvar_out, ncond, C, total);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("cvae_memory");
+  return MOCHA_OK;
+}
+
+int cvae_condition(const float* src_cnt, const float* prev, const float* m0, const float* s0, const float* m1,
+                   const float* s1, float* cond, int B, int n, int C, cudaStream_t s) {
+  MOCHA_CHECK_ARG(src_cnt && prev && m0 && s0 && m1 && s1 && cond && B > 0 && n > 0 && C > 0,
+                  "cvae_condition: bad args");
+  const long long total = (long long)B * 2 * n * C;
+  cvae_condition_kernel<<<blocks_for(total, 256), 256, 0, s>>>(src_cnt, prev, m0, s0, m1, s1, cond, n, C, total);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("cvae_condition");
+  return MOCHA_OK;
+}
+
+int affine_rows(const float* x, const float* mu, const float* sd, float* out, long long rows, int C, int period,
+                cudaStream_t s) {
+  MOCHA_CHECK_ARG(x && mu && sd && out && rows > 0 && C > 0 && period > 0, "affine_rows: bad args");
+  const long long total = rows * C;
+  affine_rows_kernel<<<blocks_for(total, 256), 256, 0, s>>>(x, mu, sd, out, total, C, period);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("affine_rows");
+  return MOCHA_OK;
+}
+
+int broadcast_rows(const float* x, float* out, int B, long long n_elems, cudaStream_t s) {
+  MOCHA_CHECK_ARG(x && out && B > 0 && n_elems > 0, "broadcast_rows: bad args");
+  const long long total = (long long)B * n_elems;
+  broadcast_rows_kernel<<<blocks_for(total, 256), 256, 0, s>>>(x, out, n_elems, total);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("broadcast_rows");
+  return MOCHA_OK;
+}
+
+int add_table(const float* a, const float* table, float* out, long long rows, int C, int period,
+              cudaStream_t s) {
+  MOCHA_CHECK_ARG(a && table && out && rows > 0 && C > 0 && period > 0, "add_table: bad args");
+  const long long total = rows * C;
+  add_table_kernel<<<blocks_for(total, 256), 256, 0, s>>>(a, table, out, total, C, period);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("add_table");
+  return MOCHA_OK;
+}
+
+int cast_f32_bf16(const float* x, __nv_bfloat16* y, long long n, cudaStream_t s) {
+  MOCHA_CHECK_ARG(x && y && n > 0, "cast_f32_bf16: bad args");
+  MOCHA_CHECK_ARG((((uintptr_t)x) & 15) == 0 && (((uintptr_t)y) & 7) == 0, "cast_f32_bf16: misaligned");
+  cast_f32_bf16_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, s>>>(x, y, n);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("cast_f32_bf16");
+  return MOCHA_OK;
+}
+
+}  // namespace mocha

@@ -1,0 +1,64 @@
+// Bandwidth/latency-bound building blocks of the path (graph aggregation, pooling, instance /
+// layer normalisation, softmax, CVAE token assembly). All activations are channel-last:
+// Generator tensors are [B, T, V, C] (row = (b*T + t)*V + v), token tensors are [B, n, C].
+#pragma once
+#include "common.cuh"
+
+namespace mocha {
+
+// out[(bt,w), k*C + c] = sum_u f(in[(bt,u), c]) * A[k,u,w]      (f = LeakyReLU(0.2) if lrelu)
+// Reference: SpatialConv einsum 'nkctv,kvw->nctw' (net/blocks.py:64) commuted in front of the
+// 1x1 convolution, with the pre-activation of STGCN_Block.forward (net/blocks.py:125-129).
+int graph_agg_first(const float* in, const float* A, float* out, int BT, int V, int C, int Kk,
+                    int lrelu, cudaStream_t s);
+
+// out[(bt,w), c] = sum_k sum_u in[(bt,u), k*C + c] * A2[k,u,w]   (U input nodes, Wn output nodes)
+// Same einsum applied after the 1x1 convolution (used by to_mot's JointBlock, where the
+// body-part -> joint un-pooling is folded into A2 on the host).
+int graph_agg_kv(const float* in, const float* A2, float* out, int BT, int U, int Wn, int C, int Kk,
+                 cudaStream_t s);
+
+// out[b,t',p,c] = (1/tp) * sum_{dt<tp} sum_v in[b, tp*t'+dt, v, c] * Wp[v,p]
+// Reference: PoolJointToBodypart.forward (net/graph.py:463-465) + nn.AvgPool2d((tp,1)) (model.py:47).
+int pool_joint_body(const float* in, const float* Wp, float* out, int B, int T, int V, int P, int C,
+                    int tp, cudaStream_t s);
+
+// Instance norm over tokens per (b, channel): unbiased std, eps added to std
+// (mean_variance_norm, net/transformer.py:13-20). Optional AdaIN modulation
+// y = (1+gamma)*IN(x) + beta with gb = [B, 2C] (gamma | beta) (AdaIN.forward, transformer.py:108-113)
+// and optional second output y2 = (y - tab_mean[n,c]) / tab_std[n,c] (test_fullframework.py:293,442).
+int instance_norm_tokens(const float* x, int B, int n, int C, float eps, const float* gb, float* y,
+                         const float* tab_mean, const float* tab_std, float* y2, cudaStream_t s);
+
+// mean over tokens: out[b,c] = mean_n x[b,n,c]  (AdaptiveAvgPool1d(1), transformer.py:102)
+int token_mean(const float* x, int B, int n, int C, float* out, cudaStream_t s);
+
+// in-place softmax over the last dim of S[rows, ncols] after multiplying by scale
+int softmax_rows(float* S, long long rows, int ncols, float scale, cudaStream_t s);
+
+// y = LayerNorm(x + r) * g + b over the last dim C (post-LN TransformerEncoder/DecoderLayer)
+// optional y2 = y * tab_std[row % period, c] + tab_mean[row % period, c]
+int add_layernorm(const float* x, const float* r, const float* g, const float* b, float* y, long long rows,
+                  int C, float eps, const float* tab_mean, const float* tab_std, int period, float* y2,
+                  cudaStream_t s);
+
+// CVAE token assembly (model_CVAE.py:70-76, :159-164)
+int cvae_prior_tokens(const float* mu_token, const float* logvar_token, const float* cond, const float* pe,
+                      float* tok, int B, int ncond, int C, cudaStream_t s);
+// z = mu + eps*exp(0.5*logvar) (eps may be null => z = mu); mem = [z ; cond]
+int cvae_memory(const float* prior_out, int prior_tokens, const float* eps, const float* cond, float* mem,
+                float* mu_out, float* logvar_out, int B, int ncond, int C, cudaStream_t s);
+// cond = [ (src_cnt - m0)/s0 ; (prev - m1)/s1 ]  (test_fullframework.py:446-447)
+int cvae_condition(const float* src_cnt, const float* prev, const float* m0, const float* s0, const float* m1,
+                   const float* s1, float* cond, int B, int n, int C, cudaStream_t s);
+// out[r, c] = x[r, c] * sd[(r % period), c] + mu[(r % period), c]
+int affine_rows(const float* x, const float* mu, const float* sd, float* out, long long rows, int C, int period,
+                cudaStream_t s);
+// out[b, n, c] = x[n, c]  (broadcast a table over the batch)
+int broadcast_rows(const float* x, float* out, int B, long long n_elems, cudaStream_t s);
+// out = a + table[(r % period)]
+int add_table(const float* a, const float* table, float* out, long long rows, int C, int period, cudaStream_t s);
+
+int cast_f32_bf16(const float* x, __nv_bfloat16* y, long long n, cudaStream_t s);
+
+}  // namespace mocha
