@@ -1,0 +1,245 @@
+"""Per-frame characterization session: the reference driver's hot loop (test_fullframework.py:288-641)
+for B independent clips advanced in lock-step, entirely on the GPU.
+
+One `step()` = encode the clips' new pose windows -> context feature -> nearest-neighbour match ->
+CVAE sample (autoregressive on the previous character feature) -> AdaIN decode -> to_mot ->
+de-normalise -> root integration / blending / foot-lock IK. All buffers are pre-allocated, so the
+whole step can be captured once into a CUDA graph (`capture()`) and replayed per frame.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib, kinematics, packing
+from .balltree import BallTree
+
+
+@dataclass
+class NormStats:
+    """Normalisation tables the driver loads from norm.npz / cnt_norm.npz / cvae_norm.npz
+    (test_fullframework.py:64-99), already divided by std_weight where the driver does (:89-92)."""
+    Y_mean: np.ndarray          # [24,15]  (joint rows 1: of the [25,15] table)
+    Y_std: np.ndarray
+    cnt_mean: np.ndarray        # [90,256]
+    cnt_std: np.ndarray
+    src_cnt_mean: np.ndarray
+    src_cnt_std: np.ndarray
+    cha_encoded_mean: np.ndarray
+    cha_encoded_std: np.ndarray
+
+
+class CharacterizationSession:
+    def __init__(self, gen_sd, cvae_sd, cfg, stats: NormStats, cha_encoded, cha_cnt_nm, batch: int,
+                 device="cuda", precision="fp32", with_cm_path=False, match_tensor_cores=None, post_params=None):
+        """gen_sd / cvae_sd: reference-layout state dicts. cha_encoded [N,90,256] and cha_cnt_nm [N,23040]
+        (already (cnt-mean)/std scaled): the target character's feature DB, CUDA or CPU tensors."""
+        self.lib = _lib.load()
+        _lib.check(self.lib.mocha_check_device(), "mocha_check_device")
+        dev = torch.device(device)
+        self.dev, self.B = dev, batch
+        self.prec = _lib.MOCHA_BF16 if precision == "bf16" else _lib.MOCHA_FP32
+        self.gen = packing.PackedGenerator(gen_sd, cfg, dev)
+        self.cvae = packing.PackedCVAE(cvae_sd, 90, 256, 2, 4, 512, dev)
+        d = self.gen.dims
+        self.T, self.V, self.Cin, self.D, self.ntok = d.T, d.V, d.Cin, d.D, self.gen.ntok
+        f32 = dict(dtype=torch.float32, device=dev)
+
+        def tab(a):
+            return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).to(dev).contiguous()
+
+        self.Y_mean, self.Y_std = tab(stats.Y_mean), tab(stats.Y_std)
+        self.cnt_mean, self.cnt_std = tab(stats.cnt_mean), tab(stats.cnt_std)
+        self.m0, self.s0 = tab(stats.src_cnt_mean), tab(stats.src_cnt_std)
+        self.m1, self.s1 = tab(stats.cha_encoded_mean), tab(stats.cha_encoded_std)
+        self.cha_encoded = torch.as_tensor(cha_encoded, dtype=torch.float32).to(dev).contiguous()
+        self.tree = BallTree(torch.as_tensor(cha_cnt_nm, dtype=torch.float32).to(dev), device=dev,
+                             use_tensor_cores=match_tensor_cores)
+        self.with_cm_path = with_cm_path
+        B, n, D = batch, self.ntok, self.D
+        # static I/O buffers (graph-capturable)
+        self.X = torch.zeros((B, d.T, d.V, d.Cin), **f32)
+        self.src_hips_vel = torch.zeros((B, d.T, 3), **f32)
+        self.src_rvel = torch.zeros((B, 3), **f32)
+        self.src_rang = torch.zeros((B, 3), **f32)
+        self.contacts = torch.zeros((B, 2), dtype=torch.uint8, device=dev)
+        self.eps = torch.zeros((B, D), **f32)
+        # intermediates
+        self.tokens = torch.empty((B, n, D), **f32)
+        self.encoded = torch.empty((B, n, D), **f32)
+        self.cnt = torch.empty((B, n, D), **f32)
+        self.cnt_nm = torch.empty((B, n * D), **f32)
+        self.match_idx = torch.zeros((B, 1), dtype=torch.int64, device=dev)
+        self.match_dist = torch.zeros((B, 1), dtype=torch.float64, device=dev)
+        self.cond = torch.empty((B, 2 * n, D), **f32)
+        self.cvae_out = torch.empty((B, n, D), **f32)
+        self.prev_cha = torch.zeros((B, n, D), **f32)      # prev_cha_encoded (de-normalised)
+        self.decoded = torch.empty((B, n, D), **f32)
+        self.Y = torch.empty((B, d.T, d.V, d.Cin), **f32)
+        self.cm_cha = torch.empty((B, n, D), **f32)
+        self.cm_Y = torch.empty((B, d.T, d.V, d.Cin), **f32)
+        self.post = kinematics.PostProcessor(B, dev, post_params)
+        self.cm_post = kinematics.PostProcessor(B, dev, post_params) if with_cm_path else None
+        dims = C.byref(self.gen.struct.dims)
+        nbytes = max(self.lib.mocha_embed_workspace_bytes(dims, B), self.lib.mocha_encoder_workspace_bytes(dims, B),
+                     self.lib.mocha_decoder_workspace_bytes(dims, B), self.lib.mocha_to_mot_workspace_bytes(dims, B),
+                     self.lib.mocha_cvae_workspace_bytes(C.byref(self.cvae.struct), B, 2 * n),
+                     self.lib.mocha_match_exact_workspace_bytes(B, self.tree.N, 1),
+                     self.lib.mocha_match_tc_workspace_bytes(B, self.tree.N, self.tree.D, self.tree.kc))
+        self.ws = torch.empty(nbytes + 4096, dtype=torch.uint8, device=dev)
+        self.frame = 0
+        self.graph = None
+        self.deterministic = False
+        # pinned host staging for the end-to-end path
+        self.h_X = torch.zeros(self.X.shape, dtype=torch.float32).pin_memory()
+        self.h_side = torch.zeros((B, d.T * 3 + 3 + 3), dtype=torch.float32).pin_memory()
+        self.h_contacts = torch.zeros((B, 2), dtype=torch.uint8).pin_memory()
+        self.h_eps = torch.zeros((B, D), dtype=torch.float32).pin_memory()
+        self.h_out = torch.zeros(self.post.out.shape, dtype=torch.uint8).pin_memory()
+        self.side = torch.zeros((B, d.T * 3 + 3 + 3), **f32)
+
+    # ---------------------------------------------------------------------------------------------
+    def _s(self):
+        return _lib.stream_ptr()
+
+    def _ws(self):
+        return _lib.ptr(self.ws), self.ws.numel()
+
+    def encode(self, X, tokens, encoded, cnt, cnt_nm):
+        lib, g = self.lib, C.byref(self.gen.struct)
+        B = X.shape[0]
+        wp, wn = self._ws()
+        _lib.check(lib.mocha_embed_fwd(g, _lib.ptr(X), B, _lib.ptr(tokens), 1, self.prec, wp, wn, self._s()), "embed")
+        _lib.check(lib.mocha_encoder_fwd(g, _lib.ptr(tokens), B, _lib.ptr(encoded), self.prec, wp, wn, self._s()), "encoder")
+        _lib.check(lib.mocha_cnt_features(_lib.ptr(encoded), B, self.ntok, self.D, 1e-5, _lib.ptr(cnt),
+                                          _lib.ptr(self.cnt_mean), _lib.ptr(self.cnt_std), _lib.ptr(cnt_nm),
+                                          self._s()), "cnt_features")
+
+    def _decode(self, src_encoded, cha, decoded, Y):
+        lib, g = self.lib, C.byref(self.gen.struct)
+        wp, wn = self._ws()
+        _lib.check(lib.mocha_decoder_fwd(g, _lib.ptr(src_encoded), _lib.ptr(cha), self.B, _lib.ptr(decoded), self.prec,
+                                         wp, wn, self._s()), "decoder")
+        _lib.check(lib.mocha_to_mot_fwd(g, _lib.ptr(decoded), self.B, None, _lib.ptr(self.Y_mean), _lib.ptr(self.Y_std),
+                                        _lib.ptr(Y), self.prec, wp, wn, self._s()), "to_mot")
+
+    def _match(self):
+        lib, t = self.lib, self.tree
+        wp, wn = self._ws()
+        use_tc = t.use_tensor_cores
+        if use_tc is None:
+            use_tc = self.B * t.N >= t.TC_THRESHOLD_PAIRS
+        if use_tc:
+            t._ensure_bf16()
+            q16 = self.cnt_nm.to(torch.bfloat16)
+            _lib.check(lib.mocha_match_tc(_lib.ptr(self.cnt_nm), _lib.ptr(q16), self.B, _lib.ptr(t._db16),
+                                          _lib.ptr(t.data), _lib.ptr(t._norm), t.N, t.D, 1, t.kc, 0,
+                                          _lib.ptr(self.match_idx), _lib.ptr(self.match_dist), wp, wn, self._s()),
+                       "match_tc")
+        else:
+            _lib.check(lib.mocha_match_exact(_lib.ptr(self.cnt_nm), self.B, _lib.ptr(t.data), t.N, t.D, 1, 0,
+                                             _lib.ptr(self.match_idx), _lib.ptr(self.match_dist), wp, wn, self._s()),
+                       "match_exact")
+
+    def _frame_body(self, init: bool):
+        """Everything between the input buffers and the FrameOut buffer (graph-capturable)."""
+        lib = self.lib
+        self.encode(self.X, self.tokens, self.encoded, self.cnt, self.cnt_nm)
+        self._match()
+        if init or self.with_cm_path:
+            torch.index_select(self.cha_encoded, 0, self.match_idx[:, 0], out=self.cm_cha)
+        if init:
+            # frame 0: the NN result seeds the autoregression (test_fullframework.py:298, :437)
+            self.prev_cha.copy_(self.cm_cha)
+        else:
+            _lib.check(lib.mocha_cvae_condition(_lib.ptr(self.cnt), _lib.ptr(self.prev_cha), _lib.ptr(self.m0),
+                                                _lib.ptr(self.s0), _lib.ptr(self.m1), _lib.ptr(self.s1),
+                                                _lib.ptr(self.cond), self.B, self.ntok, self.D, self._s()), "condition")
+            wp, wn = self._ws()
+            _lib.check(lib.mocha_cvae_sample(C.byref(self.cvae.struct), _lib.ptr(self.cond), self.B, 2 * self.ntok,
+                                             None if self.deterministic else _lib.ptr(self.eps), _lib.ptr(self.cvae_out),
+                                             None, None, _lib.ptr(self.m1), _lib.ptr(self.s1), _lib.ptr(self.prev_cha),
+                                             self.prec, wp, wn, self._s()), "cvae_sample")
+        self._decode(self.encoded, self.prev_cha, self.decoded, self.Y)
+        hv = self.side[:, :self.T * 3]
+        self.src_hips_vel.copy_(hv.view(self.B, self.T, 3))
+        self.src_rvel.copy_(self.side[:, self.T * 3:self.T * 3 + 3])
+        self.src_rang.copy_(self.side[:, self.T * 3 + 3:])
+        self.post.started = not init
+        self.post.step(self.Y, self.src_hips_vel, self.src_rvel, self.src_rang, self.contacts)
+        if self.with_cm_path:
+            self._decode(self.encoded, self.cm_cha, self.decoded, self.cm_Y)
+            self.cm_post.started = not init
+            self.cm_post.step(self.cm_Y, self.src_hips_vel, self.src_rvel, self.src_rang, self.contacts)
+
+    def capture(self):
+        """Capture the steady-state frame (i >= 1) into a CUDA graph. Call after the first frame."""
+        if self.frame == 0:
+            raise _lib.MochaError("capture() needs the init frame to have run (state must exist)")
+        state_backup = (self.prev_cha.clone(), self.post.state.clone(),
+                        self.cm_post.state.clone() if self.cm_post else None)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._frame_body(False)   # warm-up on a side stream (lazy attribute setting, allocator)
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._frame_body(False)
+        # capture does not execute; restore the state the warm-up advanced
+        self.prev_cha.copy_(state_backup[0])
+        self.post.state.copy_(state_backup[1])
+        if self.cm_post:
+            self.cm_post.state.copy_(state_backup[2])
+        self.graph = g
+
+    # ---------------------------------------------------------------------------------------------
+    def step_device(self):
+        """Advance one frame from the static device input buffers (X, side, contacts, eps)."""
+        init = self.frame == 0
+        if self.graph is not None and not init:
+            self.graph.replay()
+        else:
+            self._frame_body(init)
+        self.frame += 1
+
+    def step_host(self, X, src_hips_vel, src_rvel, src_rang, contacts, eps=None):
+        """End-to-end call with HOST (numpy) inputs: pinned staging -> H2D -> frame -> D2H.
+        Returns the frame outputs as a dict of float64 numpy arrays [B, ...]."""
+        B, T = self.B, self.T
+        self.h_X.numpy()[...] = X
+        hs = self.h_side.numpy()
+        hs[:, :T * 3] = np.asarray(src_hips_vel, dtype=np.float32).reshape(B, T * 3)
+        hs[:, T * 3:T * 3 + 3] = src_rvel
+        hs[:, T * 3 + 3:] = src_rang
+        self.h_contacts.numpy()[...] = contacts
+        self.X.copy_(self.h_X, non_blocking=True)
+        self.side.copy_(self.h_side, non_blocking=True)
+        self.contacts.copy_(self.h_contacts, non_blocking=True)
+        if eps is not None:
+            self.h_eps.numpy()[...] = eps
+            self.eps.copy_(self.h_eps, non_blocking=True)
+        elif not self.deterministic:
+            self.eps.normal_()
+        self.step_device()
+        self.h_out.copy_(self.post.out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._decode_out(self.h_out.numpy())
+
+    def h2d_bytes(self):
+        return self.h_X.numel() * 4 + self.h_side.numel() * 4 + self.h_contacts.numel() + self.h_eps.numel() * 4
+
+    def d2h_bytes(self):
+        return self.h_out.numel()
+
+    @staticmethod
+    def _decode_out(raw):
+        dt = np.dtype([("pos", "f8", (25, 3)), ("rot", "f8", (25, 4)), ("vel", "f8", (25, 3)), ("ang", "f8", (25, 3)),
+                       ("blend_pos", "f8", (25, 3)), ("ik_pos", "f8", (25, 3)), ("ik_rot", "f8", (25, 4)),
+                       ("src_root_pos", "f8", (3,)), ("src_root_rot", "f8", (4,)), ("src_root_vel", "f8", (3,)),
+                       ("src_root_ang", "f8", (3,))])
+        rec = raw.view(dt)
+        return {k: rec[k].copy() for k in dt.names}

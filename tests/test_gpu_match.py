@@ -1,0 +1,76 @@
+"""GPU parity of context matching vs sklearn BallTree goldens and the float64 oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import golden_inputs as gi
+from mocha_oracle import matching
+from mocha_sigasia2023_b200.balltree import BallTree
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", list(gi.MATCH_CASES))
+def test_exact_matcher_vs_balltree(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, "match.npz"))
+    db, q = gi.match_inputs(name)
+    k = gi.MATCH_CASES[name][3]
+    tree = BallTree(db, use_tensor_cores=False)
+    dist, idx = tree.query(q, k=k, return_distance=True)
+    assert idx.dtype == np.int64 and idx.shape == (q.shape[0], k)
+    np.testing.assert_array_equal(idx, g[name + "_idx"])          # bit-exact indices
+    np.testing.assert_allclose(dist, g[name + "_dist"], rtol=1e-12, atol=1e-12)
+    only = tree.query(q[:1], k=1, return_distance=False)
+    assert only.shape == (1, 1) and only[0, 0] == g[name + "_idx"][0, 0]
+
+
+def test_reference_call_pattern():
+    # test_fullframework.py:294-296: tree.query(x.reshape(n,-1), k=1, return_distance=False)[:,0][0]
+    db, q = gi.match_inputs("small")
+    tree = BallTree(db.reshape(db.shape[0], -1))
+    fi = tree.query(q[0:1].reshape(1, -1), k=1, return_distance=False)[:, 0][0]
+    want = matching.knn(db, q[0:1], 1)[1][0, 0]
+    assert int(fi) == int(want)
+
+
+@pytest.mark.parametrize("shape", [(4096, 512, 300, 2), (1000, 23040, 130, 1), (777, 192, 5, 3)])
+def test_tensor_core_matcher(shape):
+    N, D, nq, k = shape
+    rng = np.random.default_rng(N + D)
+    db = rng.standard_normal((N, D)).astype(np.float32)
+    pick = rng.integers(0, N, size=nq)
+    q = (db[pick] + 0.05 * rng.standard_normal((nq, D))).astype(np.float32)
+    tree = BallTree(db, use_tensor_cores=True, kc=8)
+    dist, idx = tree.query(q, k=k, return_distance=True)
+    wd, wi = matching.knn_gemm(db, q, k)
+    np.testing.assert_array_equal(idx[:, 0], pick)                 # planted neighbour found
+    margins_ok = np.ones(nq, dtype=bool)
+    if k > 1:
+        margins_ok = (wd[:, 1:] - wd[:, :-1]).min(axis=1) > 1e-5
+    np.testing.assert_array_equal(idx[margins_ok], wi[margins_ok])
+    np.testing.assert_allclose(dist[margins_ok], wd[margins_ok], rtol=1e-9)
+
+
+def test_tensor_core_matcher_iid_recall():
+    # distance-concentrated worst case: report agreement on the margin-filtered subset
+    rng = np.random.default_rng(11)
+    N, D, nq = 20000, 1024, 256
+    db = rng.standard_normal((N, D)).astype(np.float32)
+    q = rng.standard_normal((nq, D)).astype(np.float32)
+    tree = BallTree(db, use_tensor_cores=True, kc=16)
+    idx = tree.query(q, k=1, return_distance=False)[:, 0]
+    wd, wi = matching.knn_gemm(db, q, 2)
+    ok = (wd[:, 1] - wd[:, 0]) > 1e-5
+    agree = (idx[ok] == wi[ok, 0]).mean()
+    assert agree >= 0.98, f"coarse top-16 recall too low: {agree}"
+
+
+def test_query_validation():
+    db, q = gi.match_inputs("ragged")
+    tree = BallTree(db)
+    with pytest.raises(ValueError):
+        tree.query(q[:, :10], k=1)
+    with pytest.raises(ValueError):
+        tree.query(q, k=db.shape[0] + 1)

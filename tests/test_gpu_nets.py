@@ -1,0 +1,122 @@
+"""GPU parity: the CUDA Generator / CVAE behind the C ABI vs the reference goldens and the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import golden_inputs as gi
+from mocha_oracle import nets
+from mocha_sigasia2023_b200 import weights
+from mocha_sigasia2023_b200.model import Generator
+from mocha_sigasia2023_b200.model_CVAE import CVAE
+from mocha_sigasia2023_b200.transformer import mean_variance_norm
+
+pytestmark = pytest.mark.gpu
+
+RTOL_FP32 = 1e-4   # north_star: 1e-4 relative in fp32
+RTOL_BF16 = 2e-2   # 2e-2 in bf16
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "nets.npz"))
+
+
+@pytest.fixture(scope="module")
+def gen():
+    g = Generator(weights.DEFAULT_MODEL_CFG)
+    g.load_state_dict(weights.generator_state_dict(1777), strict=True)
+    return g.to("cuda").eval()
+
+
+@pytest.fixture(scope="module")
+def cvae():
+    c = CVAE(output_seq=90)
+    c.load_state_dict(weights.cvae_state_dict(1778), strict=True)
+    return c.to("cuda").eval()
+
+
+def cu(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def test_mot_embedding(gen, gold):
+    src, _ = gi.pose_windows()
+    tok = gen.mot_embedding(cu(src)).cpu().numpy()
+    assert rel_err(tok, gold["tokens"]) < RTOL_FP32
+
+
+def test_encoder_and_cnt(gen, gold):
+    src, cha = gi.pose_windows()
+    tok = gen.mot_embedding(cu(src))
+    tok = tok + gen.pos_emb[:, :tok.shape[1]]
+    enc = gen.encoder(tok)
+    assert rel_err(enc.cpu().numpy(), gold["src_encoded"]) < RTOL_FP32
+    cnt = mean_variance_norm(enc.permute(0, 2, 1)).permute(0, 2, 1)
+    assert rel_err(cnt.cpu().numpy(), gold["src_cnt"]) < RTOL_FP32
+
+
+def test_decoder_and_to_mot(gen, gold):
+    dec = gen.decoder(cu(gold["src_encoded"]), cu(gold["cha_encoded"]))
+    assert rel_err(dec.cpu().numpy(), gold["decoded"]) < RTOL_FP32
+    y = gen.to_mot(cu(gold["decoded"]))
+    assert rel_err(y.cpu().numpy(), gold["Ytil"]) < RTOL_FP32
+
+
+def test_forward_signature(gen, gold):
+    src, cha = gi.pose_windows()
+    y = gen(cu(src), cu(cha))
+    assert tuple(y.shape) == (2, 60, 24, 15)
+    assert rel_err(y.cpu().numpy(), gold["forward"]) < 2 * RTOL_FP32
+    feats = gen(cu(src), cu(cha), extract_feature=True)
+    assert len(feats) == 4
+    assert rel_err(feats[3].cpu().numpy(), gold["feat_cha_cnt"]) < 2 * RTOL_FP32
+
+
+def test_batch_sizes_against_oracle(gen):
+    sd = {k: v.numpy() for k, v in weights.generator_state_dict(1777).items()}
+    for B, seed in ((1, 5), (3, 6)):
+        src, cha = gi.pose_windows(B=B, seed=seed)
+        want = nets.generator_forward(sd, src, cha)
+        got = gen(cu(src), cu(cha)).cpu().numpy()
+        assert rel_err(got, want) < 2 * RTOL_FP32
+
+
+def test_cvae_sample(cvae, gold):
+    cond, eps = gi.cvae_inputs()
+    out = cvae.sample(cu(cond), deterministic=True).cpu().numpy()
+    assert rel_err(out, gold["cvae_det"]) < RTOL_FP32
+    mu, logvar = cvae.prior(cu(cond))
+    assert rel_err(mu.cpu().numpy(), gold["cvae_mu"]) < RTOL_FP32
+    assert rel_err(logvar.cpu().numpy(), gold["cvae_logvar"]) < RTOL_FP32
+    cvae.eps_fn = lambda shape: torch.from_numpy(eps)
+    try:
+        out_e = cvae.sample(cu(cond), deterministic=False).cpu().numpy()
+    finally:
+        cvae.eps_fn = None
+    assert rel_err(out_e, gold["cvae_eps"]) < RTOL_FP32
+
+
+def test_bf16_tensor_core_mode(gold):
+    g = Generator(weights.DEFAULT_MODEL_CFG, precision="bf16")
+    g.load_state_dict(weights.generator_state_dict(1777), strict=True)
+    g = g.to("cuda").eval()
+    src, cha = gi.pose_windows()
+    tok = g.mot_embedding(cu(src)).cpu().numpy()
+    assert rel_err(tok, gold["tokens"]) < RTOL_BF16
+    dec = g.decoder(cu(gold["src_encoded"]), cu(gold["cha_encoded"])).cpu().numpy()
+    assert rel_err(dec, gold["decoded"]) < RTOL_BF16
+    y = g.to_mot(cu(gold["decoded"])).cpu().numpy()
+    assert rel_err(y, gold["Ytil"]) < RTOL_BF16
+    c = CVAE(output_seq=90, precision="bf16")
+    c.load_state_dict(weights.cvae_state_dict(1778), strict=True)
+    c = c.to("cuda").eval()
+    cond, _ = gi.cvae_inputs()
+    out = c.sample(cu(cond), deterministic=True).cpu().numpy()
+    assert rel_err(out, gold["cvae_det"]) < RTOL_BF16
