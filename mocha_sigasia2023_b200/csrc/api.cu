@@ -42,7 +42,8 @@ extern "C" int mocha_check_device(void) {
 
 // Register the bf16 mirror of an fp32 weight blob so MOCHA_BF16 layers can find W16 for a W pointer.
 extern "C" int mocha_register_bf16_blob(const float* blob32, const void* blob16, size_t elems) {
-  if (!blob32 || !blob16 || elems == 0)
+  // blob16 == NULL unregisters the range (call before freeing the blob)
+  if (!blob32 || elems == 0)
     return mocha::set_error(MOCHA_ERR_ARG, "mocha_register_bf16_blob: bad argument");
   mocha::tc_register_blob(blob32, blob16, elems);
   return MOCHA_OK;

@@ -154,6 +154,14 @@ struct TcShape {
   int tiles_m_total;
 };
 
+// Per-warp epilogue context: each epilogue warp owns a 32-row slab of the 128-row tile.
+struct EpiCtx {
+  float* stage;          // [32][33] floats of shared memory private to the warp
+  int lane;
+  long long slab_row0;   // global output row of the slab's first row
+  int slab_rows;         // valid rows in the slab (0..32)
+};
+
 struct LinearEpi {
   float* C;
   int ldc;
@@ -164,35 +172,51 @@ struct LinearEpi {
   int act;
   struct State {};
   __device__ __forceinline__ void unit_begin(State&) const {}
-  __device__ __forceinline__ void chunk(State&, long long row, bool row_ok, int col0, const uint32_t (&v)[32]) const {
-    if (!row_ok) return;
-    const float* brow = nullptr;
-    if (bias) brow = bias_period > 0 ? bias + (row % bias_period) * (long long)N : bias;
-    float* crow = C + row * (long long)ldc;
-    const float* rrow = res ? res + row * (long long)ldc : nullptr;
-    float o[32];
+  __device__ __forceinline__ float finish(float x, const float* brow, const float* rrow, int c) const {
+    if (brow) x += __ldg(brow + c);
+    if (act == ACT_RELU) x = fmaxf(x, 0.f);
+    else if (act == ACT_GELU) x = gelu_erf(x);
+    else if (act == ACT_LRELU) x = lrelu02(x);
+    if (rrow) x += __ldg(rrow + c);
+    return x;
+  }
+  // Warp-collective: the accumulator slab (lane = row, 32 columns in registers) is transposed
+  // through shared memory so that bias / residual loads and the stores are row-contiguous:
+  // each pass covers 4 rows x 32 columns, 8 lanes x float4 = one full 128 B line per row.
+  __device__ __forceinline__ void chunk(State&, const EpiCtx& e, long long, bool, int col0,
+                                        const uint32_t (&v)[32]) const {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int c = col0 + j;
-      float x = __uint_as_float(v[j]);
-      if (c < N) {
-        if (brow) x += brow[c];
-        if (act == ACT_RELU) x = fmaxf(x, 0.f);
-        else if (act == ACT_GELU) x = gelu_erf(x);
-        else if (act == ACT_LRELU) x = lrelu02(x);
-        if (rrow) x += rrow[c];
+    for (int j = 0; j < 32; ++j) e.stage[e.lane * 33 + j] = __uint_as_float(v[j]);
+    __syncwarp();
+    const int rr = e.lane >> 3, cc = (e.lane & 7) * 4;
+    const int c = col0 + cc;
+    const bool vec = ((ldc & 3) == 0) && (c + 3 < N) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
+                     (!res || (reinterpret_cast<uintptr_t>(res) & 15) == 0);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 4 + rr;
+      if (r < e.slab_rows && c < N) {
+        const long long grow = e.slab_row0 + r;
+        const float* brow = nullptr;
+        if (bias) brow = bias_period > 0 ? bias + (grow % bias_period) * (long long)N : bias;
+        const float* rrow = res ? res + grow * (long long)ldc : nullptr;
+        float* crow = C + grow * (long long)ldc;
+        const float* sp = e.stage + r * 33 + cc;
+        if (vec) {
+          float4 o;
+          o.x = finish(sp[0], brow, rrow, c);
+          o.y = finish(sp[1], brow, rrow, c + 1);
+          o.z = finish(sp[2], brow, rrow, c + 2);
+          o.w = finish(sp[3], brow, rrow, c + 3);
+          *reinterpret_cast<float4*>(crow + c) = o;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (c + k < N) crow[c + k] = finish(sp[k], brow, rrow, c + k);
+        }
       }
-      o[j] = x;
     }
-    if (col0 + 32 <= N && (ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(crow + col0) & 15) == 0)) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(crow + col0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < N) crow[col0 + j] = o[j];
-    }
+    __syncwarp();
   }
   __device__ __forceinline__ void unit_end(State&, long long, bool, int) const {}
 };
@@ -212,7 +236,8 @@ struct MatchEpi {
 #pragma unroll
     for (int t = 0; t < KC; ++t) { st.s[t] = INFINITY; st.i[t] = -1; }
   }
-  __device__ __forceinline__ void chunk(State& st, long long, bool row_ok, int col0, const uint32_t (&v)[32]) const {
+  __device__ __forceinline__ void chunk(State& st, const EpiCtx&, long long, bool row_ok, int col0,
+                                        const uint32_t (&v)[32]) const {
     if (!row_ok) return;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -246,7 +271,8 @@ struct TcSmem {
   static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_STAGE_BYTES = 4 * 32 * 33 * 4;  // per-warp transposition buffers
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
 };
 
 template <int BN, class Epi>
@@ -263,6 +289,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * SM::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -345,6 +372,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int r_in_b = mtb * BLOCK_M + q * 32 + lane;
       const bool row_ok = r_in_b < sh.rows_out_per_b;
       const long long row = (long long)b * sh.rows_out_per_b + r_in_b;
+      EpiCtx ectx;
+      ectx.stage = epi_stage + (warp - 2) * 32 * 33;
+      ectx.lane = lane;
+      ectx.slab_row0 = (long long)b * sh.rows_out_per_b + mtb * BLOCK_M + q * 32;
+      ectx.slab_rows = max(0, min(32, sh.rows_out_per_b - (mtb * BLOCK_M + q * 32)));
       epi.unit_begin(st);
       const int nt_end = min(sh.tiles_n, (split + 1) * sh.tiles_per_unit);
       for (int nt = split * sh.tiles_per_unit; nt < nt_end; ++nt) {
@@ -355,7 +387,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(taddr + (uint32_t)c0, v);
-          epi.chunk(st, row, row_ok, nt * BN + c0, v);
+          epi.chunk(st, ectx, row, row_ok, nt * BN + c0, v);
         }
         tc_fence_before();
         __syncwarp();
@@ -527,14 +559,20 @@ bool tc_linear_supported(int M, int N, int K) { return M >= 1 && N >= 16 && K >=
 size_t tc_scratch_bytes(size_t rows, size_t K) { return align_up(rows * K * 2, 256) + 256; }
 
 void tc_register_blob(const float* blob32, const void* blob16, size_t elems) {
-  for (int i = 0; i < g_nblobs; ++i)
-    if (g_blobs[i].b32 == blob32) {
-      g_blobs[i].b16 = (const __nv_bfloat16*)blob16;
-      g_blobs[i].elems = elems;
-      return;
-    }
-  if (g_nblobs < MAX_BLOBS) g_blobs[g_nblobs++] = Blob{blob32, (const __nv_bfloat16*)blob16, elems};
-  else g_blobs[MAX_BLOBS - 1] = Blob{blob32, (const __nv_bfloat16*)blob16, elems};
+  // drop every entry that overlaps the new range (stale mirrors of freed / re-used allocations)
+  int n = 0;
+  for (int i = 0; i < g_nblobs; ++i) {
+    const Blob& b = g_blobs[i];
+    const bool overlap = blob32 < b.b32 + b.elems && b.b32 < blob32 + elems;
+    if (!overlap) g_blobs[n++] = b;
+  }
+  g_nblobs = n;
+  if (!blob16) return;  // unregister only
+  if (g_nblobs == MAX_BLOBS) {  // evict the oldest
+    for (int i = 1; i < MAX_BLOBS; ++i) g_blobs[i - 1] = g_blobs[i];
+    --g_nblobs;
+  }
+  g_blobs[g_nblobs++] = Blob{blob32, (const __nv_bfloat16*)blob16, elems};
 }
 
 const __nv_bfloat16* tc_lookup_bf16(const float* W) {

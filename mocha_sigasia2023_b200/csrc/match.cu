@@ -15,20 +15,23 @@ namespace {
 constexpr int KMAX = 16;
 constexpr int EXQ = 4;  // queries per pass of the exact kernel
 
-// One warp per DB row; the row is streamed once and compared against EXQ queries.
+// One CTA per (DB row, group of EXQ queries): the row is streamed once with 128-bit loads, each
+// thread accumulating (q - x)^2 in fp64 for its slice of D; warp shuffles + a tiny smem pass reduce.
+// grid = (N, ceil(nq / EXQ)); the DB (35 MB at the reference's size) stays L2-resident across groups.
 __global__ void __launch_bounds__(256)
-match_exact_dist_kernel(const float* __restrict__ Q, int nq, int q0, const float* __restrict__ DB, long long N,
-                        int D, double* __restrict__ dist2) {
+match_exact_dist_kernel(const float* __restrict__ Q, int nq, const float* __restrict__ DB, long long N, int D,
+                        double* __restrict__ dist2) {
+  __shared__ double red[8][EXQ];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * 8 + warp;
-  if (row >= N) return;
+  const long long row = blockIdx.x;
+  const int q0 = blockIdx.y * EXQ;
   const float* x = DB + row * (long long)D;
   double acc[EXQ];
 #pragma unroll
   for (int j = 0; j < EXQ; ++j) acc[j] = 0.0;
   const int nqq = min(EXQ, nq - q0);
-  if ((D & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(Q) & 15) == 0)) {
-    for (int d = lane * 4; d < D; d += 128) {
+  if ((D & 3) == 0 && ((reinterpret_cast<uintptr_t>(DB) & 15) == 0) && ((reinterpret_cast<uintptr_t>(Q) & 15) == 0)) {
+    for (int d = threadIdx.x * 4; d < D; d += 1024) {
       const float4 xv = __ldg(reinterpret_cast<const float4*>(x + d));
 #pragma unroll
       for (int j = 0; j < EXQ; ++j) {
@@ -44,7 +47,7 @@ match_exact_dist_kernel(const float* __restrict__ Q, int nq, int q0, const float
       }
     }
   } else {
-    for (int d = lane; d < D; d += 32) {
+    for (int d = threadIdx.x; d < D; d += 256) {
       const double xv = (double)x[d];
 #pragma unroll
       for (int j = 0; j < EXQ; ++j)
@@ -57,7 +60,14 @@ match_exact_dist_kernel(const float* __restrict__ Q, int nq, int q0, const float
 #pragma unroll
   for (int j = 0; j < EXQ; ++j) {
     const double s = warp_sum(acc[j]);
-    if (lane == 0 && j < nqq) dist2[(long long)(q0 + j) * N + row] = s;
+    if (lane == 0) red[warp][j] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < nqq) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    dist2[(long long)(q0 + threadIdx.x) * N + row] = s;
   }
 }
 
@@ -256,11 +266,9 @@ extern "C" int mocha_match_exact(const float* Q, int nq, const float* DB, long l
     return set_error(MOCHA_ERR_WORKSPACE, "mocha_match_exact: workspace too small (%zu B given, %zu B needed)",
                      workspace_bytes, ws.off);
   cudaStream_t s = (cudaStream_t)stream;
-  const unsigned blocks = (unsigned)((N + 7) / 8);
-  for (int q0 = 0; q0 < nq; q0 += EXQ) {
-    match_exact_dist_kernel<<<blocks, 256, 0, s>>>(Q, nq, q0, DB, N, D, dist2);
-    count_launch();
-  }
+  MOCHA_CHECK_ARG(N <= 2147483647LL && (nq + EXQ - 1) / EXQ <= 65535, "mocha_match_exact: problem too large for the exact kernel (use mocha_match_tc)");
+  match_exact_dist_kernel<<<dim3((unsigned)N, (unsigned)((nq + EXQ - 1) / EXQ)), 256, 0, s>>>(Q, nq, DB, N, D, dist2);
+  count_launch();
   MOCHA_LAUNCH_CHECK("match_exact_dist_kernel");
   topk_rows_kernel<<<nq, 256, 0, s>>>(dist2, N, k, index_offset, idx, dist);
   count_launch();

@@ -36,6 +36,8 @@ int dense(const Ctx& c, const float* A, int lda, const float* W, const float* bi
 // reflect-padded temporal convolution as implicit GEMM (blocks.py:113-118,:132)
 int tconv(const Ctx& c, const float* A, const float* W, const float* bias, int bias_period, float* C, int B,
           int T, int V, int Cin, int Cout, int taps, int tdiv) {
+  if (c.precision == MOCHA_BF16 && tdiv == 1 && tc_tconv_supported(B, T, V, Cin, Cout, taps))
+    return tc_tconv(A, W, bias, bias_period, C, B, T, V, Cin, Cout, taps, *c.ws, c.s);
   GemmParams p;
   p.A = A; p.W = W; p.C = C;
   p.M = B * T * V; p.N = Cout; p.K = taps * Cin;
@@ -101,7 +103,8 @@ extern "C" size_t mocha_embed_workspace_bytes(const mocha_dims* d, int B) {
   n += pad256(R2 * d->D * 4);               // pooled
   n += pad256(R2 * d->Kb * d->D * 4);       // agg2
   n += pad256(R2 * d->D * 4);               // g2
-  n += tc_scratch_bytes(R, d->taps_j * d->D);
+  n += tc_scratch_bytes(R, d->Kj * d->C0 > d->D ? d->Kj * d->C0 : d->D);
+  n += tc_tconv_scratch_bytes(B, d->T, d->V, d->D, d->taps_j);
   return n + 4096;
 }
 
@@ -282,6 +285,7 @@ extern "C" size_t mocha_to_mot_workspace_bytes(const mocha_dims* d, int B) {
   bytes += pad256(R * d->C0 * 4);                         // y4
   bytes += pad256(R * d->Cin * 4);                        // Ytil when the caller only wants Y
   bytes += tc_scratch_bytes(R2, d->Kb * d->D);
+  bytes += tc_tconv_scratch_bytes(B, d->T / d->tp, d->P, d->D, d->taps_b);
   return bytes + 4096;
 }
 
@@ -449,4 +453,16 @@ extern "C" int mocha_linear(const float* A, const float* W, const float* bias, c
   if (rc == MOCHA_OK && ws.overflow)
     return set_error(MOCHA_ERR_WORKSPACE, "mocha_linear: workspace too small");
   return rc;
+}
+
+// Stand-alone entry for the dominant kernel of the batched path (bench.py roofline pass): the
+// reflect-padded temporal convolution of mot_embedding's JointBlock, x [B*T*V, D] -> out [B*T*V, D].
+extern "C" int mocha_bench_tconv(const mocha_generator_weights* w, const float* x, int B, float* out, int precision,
+                                 void* workspace, size_t workspace_bytes, mocha_stream_t stream) {
+  MOCHA_CHECK_ARG(w && x && out && B > 0, "mocha_bench_tconv: null/empty argument");
+  MOCHA_TRY(check_dims(w->dims));
+  const mocha_dims& d = w->dims;
+  Workspace ws(workspace, workspace_bytes);
+  Ctx c{(cudaStream_t)stream, precision, &ws};
+  return tconv(c, x, w->jb_tcn_w, w->jb_tcn_b, 0, out, B, d.T, d.V, d.D, d.D, d.taps_j, 1);
 }

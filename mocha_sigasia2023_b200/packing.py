@@ -35,6 +35,12 @@ class PackedBlob:
             C.c_void_p(self.blob32.data_ptr()), C.c_void_p(self.blob16.data_ptr()), self.blob32.numel()),
             "mocha_register_bf16_blob")
 
+    def __del__(self):
+        try:
+            _lib.load().mocha_register_bf16_blob(C.c_void_p(self.blob32.data_ptr()), None, self.blob32.numel())
+        except Exception:
+            pass
+
     def ptr(self, name: str) -> int:
         return self.blob32.data_ptr() + 4 * self.offsets[name]
 
