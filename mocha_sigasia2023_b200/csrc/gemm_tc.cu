@@ -1,11 +1,11 @@
 // tcgen05 / TMEM / TMA GEMM family for sm_100a (see gemm_tc.cuh).
 //
-// Kernel anatomy (one persistent CTA per SM, 192 threads):
+// Kernel anatomy (one persistent CTA per SM, 320 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2D tiles (128B swizzle) into a STAGES-deep ring
 //   warp 1      MMA issuer:   one elected thread issues tcgen05.mma.cta_group::1.kind::f16
 //               (M=128, N=BN, K=16) x4 per 64-wide k-block; tcgen05.commit frees ring slots and
 //               publishes finished accumulators; also owns tcgen05.alloc / dealloc
-//   warps 2..5  epilogue: tcgen05.ld 32x32b (lane = output row) from one of two TMEM accumulator
+//   warps 2..9  epilogue: tcgen05.ld 32x32b (lane = output row) from one of two TMEM accumulator
 //               buffers, so the epilogue of tile i overlaps the main loop of tile i+1
 // Operands are K-major bf16: A tile 128 x 64, B tile BN x 64, both landing in the canonical
 // SWIZZLE_128B layout the UMMA shared-memory descriptors describe (8-row groups 1024 B apart).
@@ -21,9 +21,8 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle atom row
 constexpr int UMMA_K = 16;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 64 + 8 * 32;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int SMEM_BUDGET = 196 * 1024;
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -154,13 +153,34 @@ struct TcShape {
   int tiles_m_total;
 };
 
-// Per-warp epilogue context: each epilogue warp owns a 32-row slab of the 128-row tile.
+// Per-warp epilogue context. Eight epilogue warps: warp w reads TMEM lane quarter (w & 3), i.e. a
+// 32-row slab of the 128-row tile, and column half (w - 2) / 4 of the tile.
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_LD = 36;  // floats per staged row: 16 B aligned, conflict-free for 128-bit accesses
 struct EpiCtx {
-  float* stage;          // [32][33] floats of shared memory private to the warp
+  uint32_t stage;        // shared-space address of this warp's [32][EPI_LD] float staging buffer
   int lane;
+  int half;              // column half handled by this warp
   long long slab_row0;   // global output row of the slab's first row
   int slab_rows;         // valid rows in the slab (0..32)
 };
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_fn(float x) {
+  if (ACT == ACT_RELU) return fmaxf(x, 0.f);
+  if (ACT == ACT_GELU) return gelu_erf(x);
+  if (ACT == ACT_LRELU) return lrelu02(x);
+  return x;
+}
 
 struct LinearEpi {
   float* C;
@@ -171,54 +191,98 @@ struct LinearEpi {
   const float* res;
   int act;
   struct State {};
+  static constexpr int kStageBytes = EPI_WARPS * 32 * EPI_LD * 4;  // per-warp transposition buffers
   __device__ __forceinline__ void unit_begin(State&) const {}
-  __device__ __forceinline__ float finish(float x, const float* brow, const float* rrow, int c) const {
-    if (brow) x += __ldg(brow + c);
-    if (act == ACT_RELU) x = fmaxf(x, 0.f);
-    else if (act == ACT_GELU) x = gelu_erf(x);
-    else if (act == ACT_LRELU) x = lrelu02(x);
-    if (rrow) x += __ldg(rrow + c);
-    return x;
-  }
-  // Warp-collective: the accumulator slab (lane = row, 32 columns in registers) is transposed
-  // through shared memory so that bias / residual loads and the stores are row-contiguous:
-  // each pass covers 4 rows x 32 columns, 8 lanes x float4 = one full 128 B line per row.
-  __device__ __forceinline__ void chunk(State&, const EpiCtx& e, long long, bool, int col0,
-                                        const uint32_t (&v)[32]) const {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) e.stage[e.lane * 33 + j] = __uint_as_float(v[j]);
-    __syncwarp();
+
+  // Second half of the transposed epilogue, specialised on the activation so the inner loop has no
+  // per-element branching: 8 passes of 4 rows x 32 columns, 8 lanes x float4 = one 128 B line per row.
+  template <int ACT>
+  __device__ __forceinline__ void drain(const EpiCtx& e, int col0) const {
     const int rr = e.lane >> 3, cc = (e.lane & 7) * 4;
     const int c = col0 + cc;
+    if (c >= N) return;
     const bool vec = ((ldc & 3) == 0) && (c + 3 < N) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
-                     (!res || (reinterpret_cast<uintptr_t>(res) & 15) == 0);
+                     (!res || (reinterpret_cast<uintptr_t>(res) & 15) == 0) &&
+                     (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0);
+    const float* bp = bias;
+    const float* rp = res;
+    float4 bcol = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bp && bias_period == 0) {
+      if (vec) bcol = __ldg(reinterpret_cast<const float4*>(bp + c));
+      else {
+        bcol.x = __ldg(bp + c);
+        if (c + 1 < N) bcol.y = __ldg(bp + c + 1);
+        if (c + 2 < N) bcol.z = __ldg(bp + c + 2);
+        if (c + 3 < N) bcol.w = __ldg(bp + c + 3);
+      }
+    }
+    if (vec) {
+      // issue every load of the chunk first (memory-level parallelism), then compute and store
+      float4 o[8], bv[8], rv[8];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int r = it * 4 + rr;
-      if (r < e.slab_rows && c < N) {
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + rr;
+        bv[it] = bcol;
+        rv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < e.slab_rows) {
+          const long long grow = e.slab_row0 + r;
+          if (bp && bias_period > 0)
+            bv[it] = __ldg(reinterpret_cast<const float4*>(bp + (long long)((unsigned)grow % (unsigned)bias_period) * N + c));
+          if (rp) rv[it] = __ldg(reinterpret_cast<const float4*>(rp + grow * (long long)ldc + c));
+        }
+        o[it] = lds128(e.stage + (uint32_t)((r * EPI_LD + cc) * 4));
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + rr;
+        if (r < e.slab_rows) {
+          float4 x = o[it];
+          x.x = act_fn<ACT>(x.x + bv[it].x) + rv[it].x;
+          x.y = act_fn<ACT>(x.y + bv[it].y) + rv[it].y;
+          x.z = act_fn<ACT>(x.z + bv[it].z) + rv[it].z;
+          x.w = act_fn<ACT>(x.w + bv[it].w) + rv[it].w;
+          *reinterpret_cast<float4*>(C + (e.slab_row0 + r) * (long long)ldc + c) = x;
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + rr;
+        if (r >= e.slab_rows) continue;
         const long long grow = e.slab_row0 + r;
-        const float* brow = nullptr;
-        if (bias) brow = bias_period > 0 ? bias + (grow % bias_period) * (long long)N : bias;
-        const float* rrow = res ? res + grow * (long long)ldc : nullptr;
-        float* crow = C + grow * (long long)ldc;
-        const float* sp = e.stage + r * 33 + cc;
-        if (vec) {
-          float4 o;
-          o.x = finish(sp[0], brow, rrow, c);
-          o.y = finish(sp[1], brow, rrow, c + 1);
-          o.z = finish(sp[2], brow, rrow, c + 2);
-          o.w = finish(sp[3], brow, rrow, c + 3);
-          *reinterpret_cast<float4*>(crow + c) = o;
-        } else {
+        const float4 x4 = lds128(e.stage + (uint32_t)((r * EPI_LD + cc) * 4));
+        const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+        const float bs[4] = {bcol.x, bcol.y, bcol.z, bcol.w};
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (c + k < N) crow[c + k] = finish(sp[k], brow, rrow, c + k);
+        for (int k = 0; k < 4; ++k) {
+          if (c + k >= N) break;
+          float x = xs[k];
+          if (bp) x += bias_period > 0 ? __ldg(bp + (long long)((unsigned)grow % (unsigned)bias_period) * N + c + k) : bs[k];
+          x = act_fn<ACT>(x);
+          if (rp) x += __ldg(rp + grow * (long long)ldc + c + k);
+          C[grow * (long long)ldc + c + k] = x;
         }
       }
     }
+  }
+
+  // Warp-collective: the accumulator slab (lane = row, 32 columns in registers) is transposed through
+  // shared memory so that bias / residual loads and the stores are row-contiguous and coalesced.
+  __device__ __forceinline__ void chunk(State&, const EpiCtx& e, long long, bool, int col0,
+                                        const uint32_t (&v)[32]) const {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      sts128(e.stage + (uint32_t)((e.lane * EPI_LD + j) * 4), v[j], v[j + 1], v[j + 2], v[j + 3]);
+    __syncwarp();
+    switch (act) {
+      case ACT_RELU: drain<ACT_RELU>(e, col0); break;
+      case ACT_GELU: drain<ACT_GELU>(e, col0); break;
+      case ACT_LRELU: drain<ACT_LRELU>(e, col0); break;
+      default: drain<ACT_NONE>(e, col0); break;
+    }
     __syncwarp();
   }
-  __device__ __forceinline__ void unit_end(State&, long long, bool, int) const {}
+  __device__ __forceinline__ void unit_end(State&, const EpiCtx&, long long, bool, int) const {}
 };
 
 template <int KC>
@@ -227,7 +291,8 @@ struct MatchEpi {
   long long N;
   float* cand_score;
   int32_t* cand_idx;
-  int splits;
+  int lists;  // candidate lists per query = 2 * splits (one per column half)
+  static constexpr int kStageBytes = 0;
   struct State {
     float s[KC];
     int32_t i[KC];
@@ -238,48 +303,60 @@ struct MatchEpi {
   }
   __device__ __forceinline__ void chunk(State& st, const EpiCtx&, long long, bool row_ok, int col0,
                                         const uint32_t (&v)[32]) const {
-    if (!row_ok) return;
+    if (!row_ok || col0 >= N) return;
+    float nrm[32];
+    if ((long long)col0 + 32 <= N) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(dbnorm + col0 + j));
+        nrm[j] = t.x; nrm[j + 1] = t.y; nrm[j + 2] = t.z; nrm[j + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) nrm[j] = ((long long)col0 + j < N) ? __ldg(dbnorm + col0 + j) : INFINITY;
+    }
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const long long c = (long long)col0 + j;
-      if (c < N) {
-        // coarse squared distance up to the per-query constant ||q||^2
-        float sc = fmaf(-2.f, __uint_as_float(v[j]), __ldg(dbnorm + c));
-        if (sc < st.s[KC - 1]) {
-          int32_t ci = (int32_t)c;
+      // coarse squared distance up to the per-query constant ||q||^2 (+inf beyond the last row)
+      float sc = fmaf(-2.f, __uint_as_float(v[j]), nrm[j]);
+      if (sc < st.s[KC - 1]) {
+        int32_t ci = col0 + j;
 #pragma unroll
-          for (int t = 0; t < KC; ++t) {
-            if (sc < st.s[t]) {
-              const float ts = st.s[t]; st.s[t] = sc; sc = ts;
-              const int32_t ti = st.i[t]; st.i[t] = ci; ci = ti;
-            }
+        for (int t = 0; t < KC; ++t) {
+          if (sc < st.s[t]) {
+            const float ts = st.s[t]; st.s[t] = sc; sc = ts;
+            const int32_t ti = st.i[t]; st.i[t] = ci; ci = ti;
           }
         }
       }
     }
   }
-  __device__ __forceinline__ void unit_end(State& st, long long row, bool row_ok, int split) const {
+  __device__ __forceinline__ void unit_end(State& st, const EpiCtx& e, long long row, bool row_ok, int split) const {
     if (!row_ok) return;
-    const long long o = (row * splits + split) * KC;
+    const long long o = (row * lists + split * 2 + e.half) * KC;
 #pragma unroll
     for (int t = 0; t < KC; ++t) { cand_score[o + t] = st.s[t]; cand_idx[o + t] = st.i[t]; }
   }
 };
 
-template <int BN>
+// Shared-memory plan: as many TMA stages as fit next to the epilogue staging the epilogue needs.
+constexpr int SMEM_LIMIT = 227 * 1024;
+template <int BN, int EPI_BYTES>
 struct TcSmem {
   static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
-  static constexpr int EPI_STAGE_BYTES = 4 * 32 * 33 * 4;  // per-warp transposition buffers
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
+  static constexpr int FIXED = 1024 /*alignment slack*/ + 256 /*barriers*/ + EPI_BYTES;
+  static constexpr int FIT = (SMEM_LIMIT - FIXED) / STAGE_BYTES;
+  static constexpr int STAGES = FIT > 8 ? 8 : FIT;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + FIXED;
+  static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
 };
 
 template <int BN, class Epi>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcShape sh, const int num_kb, const Epi epi) {
-  using SM = TcSmem<BN>;
+  using SM = TcSmem<BN, Epi::kStageBytes>;
   constexpr int STAGES = SM::STAGES;
   constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   extern __shared__ uint8_t smem_raw[];
@@ -289,7 +366,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * SM::STAGE_BYTES + 256);
+  uint8_t* epi_stage = smem + STAGES * SM::STAGE_BYTES + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -297,7 +374,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -362,7 +439,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     int as = 0; uint32_t aphase = 0;
     typename Epi::State st;
@@ -373,8 +450,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool row_ok = r_in_b < sh.rows_out_per_b;
       const long long row = (long long)b * sh.rows_out_per_b + r_in_b;
       EpiCtx ectx;
-      ectx.stage = epi_stage + (warp - 2) * 32 * 33;
+      ectx.stage = smem_u32(epi_stage + (warp - 2) * 32 * EPI_LD * 4);
       ectx.lane = lane;
+      ectx.half = (warp - 2) >> 2;
       ectx.slab_row0 = (long long)b * sh.rows_out_per_b + mtb * BLOCK_M + q * 32;
       ectx.slab_rows = max(0, min(32, sh.rows_out_per_b - (mtb * BLOCK_M + q * 32)));
       epi.unit_begin(st);
@@ -384,7 +462,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        // the tile's BN/32 column chunks are split between the two warps that share a lane quarter
+        constexpr int kSplitCol = ((BN / 32 + 1) / 2) * 32;
+        const int c_begin = ectx.half == 0 ? 0 : kSplitCol, c_end = ectx.half == 0 ? kSplitCol : BN;
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(taddr + (uint32_t)c0, v);
           epi.chunk(st, ectx, row, row_ok, nt * BN + c0, v);
@@ -394,7 +475,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) mbar_arrive(&tempty_bar[as]);
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
-      epi.unit_end(st, row, row_ok, split);
+      epi.unit_end(st, ectx, row, row_ok, split);
     }
   }
 
@@ -457,7 +538,7 @@ int num_sms() {
 template <int BN, class Epi>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcShape& sh, int num_kb, const Epi& epi,
               cudaStream_t s) {
-  using SM = TcSmem<BN>;
+  using SM = TcSmem<BN, Epi::kStageBytes>;
   static bool configured = false;
   if (!configured) {
     MOCHA_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
@@ -669,7 +750,7 @@ int tc_match_splits(int nq, long long N) {
   // recompute so that every split is non-empty
   const long long tpu = (tiles_n + splits - 1) / splits;
   splits = (tiles_n + tpu - 1) / tpu;
-  return (int)splits;
+  return (int)splits * 2;  // x2: the two column halves of a tile keep separate lists
 }
 
 int tc_match_coarse(const __nv_bfloat16* Q16, int nq, const __nv_bfloat16* DB16, const float* dbnorm, long long N,
@@ -692,13 +773,13 @@ int tc_match_coarse(const __nv_bfloat16* Q16, int nq, const __nv_bfloat16* DB16,
   sh.kb_per_tap = ceil_div(D, BLOCK_K);
   sh.tap_row_stride = 0;
   sh.tiles_n = (int)((N + BN - 1) / BN);
-  const int splits = tc_match_splits(nq, N);
+  const int splits = tc_match_splits(nq, N) / 2;
   sh.tiles_per_unit = ceil_div(sh.tiles_n, splits);
   sh.units = sh.tiles_m_total * splits;
   const int num_kb = ceil_div(D, BLOCK_K);
-  if (kc == 4) return launch_tc<BN, MatchEpi<4>>(tmA, tmB, sh, num_kb, MatchEpi<4>{dbnorm, N, cand_score, cand_idx, splits}, s);
-  if (kc == 8) return launch_tc<BN, MatchEpi<8>>(tmA, tmB, sh, num_kb, MatchEpi<8>{dbnorm, N, cand_score, cand_idx, splits}, s);
-  return launch_tc<BN, MatchEpi<16>>(tmA, tmB, sh, num_kb, MatchEpi<16>{dbnorm, N, cand_score, cand_idx, splits}, s);
+  if (kc == 4) return launch_tc<BN, MatchEpi<4>>(tmA, tmB, sh, num_kb, MatchEpi<4>{dbnorm, N, cand_score, cand_idx, 2 * splits}, s);
+  if (kc == 8) return launch_tc<BN, MatchEpi<8>>(tmA, tmB, sh, num_kb, MatchEpi<8>{dbnorm, N, cand_score, cand_idx, 2 * splits}, s);
+  return launch_tc<BN, MatchEpi<16>>(tmA, tmB, sh, num_kb, MatchEpi<16>{dbnorm, N, cand_score, cand_idx, 2 * splits}, s);
 }
 
 }  // namespace mocha
