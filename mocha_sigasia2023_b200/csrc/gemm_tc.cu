@@ -151,6 +151,13 @@ struct TcShape {
   int tiles_per_unit;      // consecutive n-tiles handled by one unit
   int units;               // tiles_m_total * splits
   int tiles_m_total;
+  // batched-head mode (attention): image z = zb * H + zh selects operand windows and the output block
+  int H;                   // 0 = plain mode
+  long long a_rows_h;      // A row offset per head (rows per batch come from src_rows_per_b)
+  int a_cols_h;            // A column offset per head
+  long long b_rows_b, b_rows_h;  // B row offsets per batch / head
+  int b_cols_h;            // B column offset per head
+  long long c_img_b, c_img_h;    // output element offsets per batch / head
 };
 
 // Per-warp epilogue context. Eight epilogue warps: warp w reads TMEM lane quarter (w & 3), i.e. a
@@ -161,8 +168,9 @@ struct EpiCtx {
   uint32_t stage;        // shared-space address of this warp's [32][EPI_LD] float staging buffer
   int lane;
   int half;              // column half handled by this warp
-  long long slab_row0;   // global output row of the slab's first row
+  long long slab_row0;   // output row of the slab's first row (global, or within the image in batched mode)
   int slab_rows;         // valid rows in the slab (0..32)
+  long long c_off;       // element offset of the output block (batched-head mode), else 0
 };
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -201,7 +209,7 @@ struct LinearEpi {
     const int rr = e.lane >> 3, cc = (e.lane & 7) * 4;
     const int c = col0 + cc;
     if (c >= N) return;
-    const bool vec = ((ldc & 3) == 0) && (c + 3 < N) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
+    const bool vec = ((ldc & 3) == 0) && ((e.c_off & 3) == 0) && (c + 3 < N) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
                      (!res || (reinterpret_cast<uintptr_t>(res) & 15) == 0) &&
                      (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0);
     const float* bp = bias;
@@ -228,7 +236,7 @@ struct LinearEpi {
           const long long grow = e.slab_row0 + r;
           if (bp && bias_period > 0)
             bv[it] = __ldg(reinterpret_cast<const float4*>(bp + (long long)((unsigned)grow % (unsigned)bias_period) * N + c));
-          if (rp) rv[it] = __ldg(reinterpret_cast<const float4*>(rp + grow * (long long)ldc + c));
+          if (rp) rv[it] = __ldg(reinterpret_cast<const float4*>(rp + e.c_off + grow * (long long)ldc + c));
         }
         o[it] = lds128(e.stage + (uint32_t)((r * EPI_LD + cc) * 4));
       }
@@ -241,7 +249,7 @@ struct LinearEpi {
           x.y = act_fn<ACT>(x.y + bv[it].y) + rv[it].y;
           x.z = act_fn<ACT>(x.z + bv[it].z) + rv[it].z;
           x.w = act_fn<ACT>(x.w + bv[it].w) + rv[it].w;
-          *reinterpret_cast<float4*>(C + (e.slab_row0 + r) * (long long)ldc + c) = x;
+          *reinterpret_cast<float4*>(C + e.c_off + (e.slab_row0 + r) * (long long)ldc + c) = x;
         }
       }
     } else {
@@ -259,8 +267,8 @@ struct LinearEpi {
           float x = xs[k];
           if (bp) x += bias_period > 0 ? __ldg(bp + (long long)((unsigned)grow % (unsigned)bias_period) * N + c + k) : bs[k];
           x = act_fn<ACT>(x);
-          if (rp) x += __ldg(rp + grow * (long long)ldc + c + k);
-          C[grow * (long long)ldc + c + k] = x;
+          if (rp) x += __ldg(rp + e.c_off + grow * (long long)ldc + c + k);
+          C[e.c_off + grow * (long long)ldc + c + k] = x;
         }
       }
     }
@@ -390,7 +398,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int u = blockIdx.x; u < sh.units; u += gridDim.x) {
         const int mt = u % sh.tiles_m_total, split = u / sh.tiles_m_total;
         const int b = mt / sh.tiles_m_per_b, mtb = mt - b * sh.tiles_m_per_b;
-        const long long a_row0 = (long long)b * sh.src_rows_per_b + (long long)mtb * BLOCK_M;
+        long long a_row0 = (long long)b * sh.src_rows_per_b + (long long)mtb * BLOCK_M;
+        long long b_row0 = 0;
+        int a_col0 = 0, b_col0 = 0;
+        if (sh.H > 0) {
+          const int zb = b / sh.H, zh = b - zb * sh.H;
+          a_row0 = (long long)zb * sh.src_rows_per_b + (long long)zh * sh.a_rows_h + (long long)mtb * BLOCK_M;
+          a_col0 = zh * sh.a_cols_h;
+          b_row0 = (long long)zb * sh.b_rows_b + (long long)zh * sh.b_rows_h;
+          b_col0 = zh * sh.b_cols_h;
+        }
         const int nt_end = min(sh.tiles_n, (split + 1) * sh.tiles_per_unit);
         for (int nt = split * sh.tiles_per_unit; nt < nt_end; ++nt) {
           for (int kb = 0; kb < num_kb; ++kb) {
@@ -399,8 +416,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint8_t* sb = sa + A_STAGE_BYTES;
             mbar_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
             const int tap = kb / sh.kb_per_tap, kc = kb - tap * sh.kb_per_tap;
-            tma_load_2d(sa, &tmA, &full_bar[stage], kc * BLOCK_K, (int)(a_row0 + (long long)tap * sh.tap_row_stride));
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, nt * BN);
+            tma_load_2d(sa, &tmA, &full_bar[stage], a_col0 + kc * BLOCK_K,
+                        (int)(a_row0 + (long long)tap * sh.tap_row_stride));
+            tma_load_2d(sb, &tmB, &full_bar[stage], b_col0 + kb * BLOCK_K, (int)(b_row0 + (long long)nt * BN));
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -455,16 +473,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ectx.half = (warp - 2) >> 2;
       ectx.slab_row0 = (long long)b * sh.rows_out_per_b + mtb * BLOCK_M + q * 32;
       ectx.slab_rows = max(0, min(32, sh.rows_out_per_b - (mtb * BLOCK_M + q * 32)));
+      ectx.c_off = 0;
+      if (sh.H > 0) {
+        const int zb = b / sh.H, zh = b - zb * sh.H;
+        ectx.slab_row0 = mtb * BLOCK_M + q * 32;
+        ectx.c_off = (long long)zb * sh.c_img_b + (long long)zh * sh.c_img_h;
+      }
       epi.unit_begin(st);
       const int nt_end = min(sh.tiles_n, (split + 1) * sh.tiles_per_unit);
       for (int nt = split * sh.tiles_per_unit; nt < nt_end; ++nt) {
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-#pragma unroll 1
         // the tile's BN/32 column chunks are split between the two warps that share a lane quarter
         constexpr int kSplitCol = ((BN / 32 + 1) / 2) * 32;
         const int c_begin = ectx.half == 0 ? 0 : kSplitCol, c_end = ectx.half == 0 ? kSplitCol : BN;
+#pragma unroll 1
         for (int c0 = c_begin; c0 < c_end; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(taddr + (uint32_t)c0, v);
@@ -508,13 +532,15 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // bf16 [rows, K] row-major, box = box_rows x 64 elements, 128B swizzle, OOB reads return zero
-int make_tmap(CUtensorMap* tm, const void* ptr, unsigned long long rows, unsigned long long K, int box_rows) {
+int make_tmap(CUtensorMap* tm, const void* ptr, unsigned long long rows, unsigned long long K, int box_rows,
+              unsigned long long pitch_elems = 0) {
+  if (pitch_elems == 0) pitch_elems = K;
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(MOCHA_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   MOCHA_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "tensor map: base not 16B aligned");
-  MOCHA_CHECK_ARG((K * 2) % 16 == 0, "tensor map: row pitch %llu B not a multiple of 16", K * 2);
+  MOCHA_CHECK_ARG((pitch_elems * 2) % 16 == 0, "tensor map: row pitch %llu B not a multiple of 16", pitch_elems * 2);
   cuuint64_t gdim[2] = {K, rows};
-  cuuint64_t gstride[1] = {K * 2};
+  cuuint64_t gstride[1] = {pitch_elems * 2};
   cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
@@ -572,7 +598,7 @@ __global__ void cast_act_bf16_kernel(const float* __restrict__ x, __nv_bfloat16*
 
 // X fp32 [B,T,V,C] -> bf16 [B, T+2*pad, V, C] with reflect padding along T
 __global__ void reflect_pad_cast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int T, int V,
-                                        int C, int pad, long long total4) {
+                                        int C, int pad, int tdiv, long long total4) {
   const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i4 >= total4) return;
   const long long i = i4 * 4;
@@ -586,7 +612,8 @@ __global__ void reflect_pad_cast_kernel(const float* __restrict__ x, __nv_bfloat
   int t = tp - pad;
   if (t < 0) t = -t;
   if (t >= T) t = 2 * (T - 1) - t;
-  const float4 val = *reinterpret_cast<const float4*>(x + (((b * T + t) * V + v) * (long long)C + c));
+  t /= tdiv;  // nearest-neighbour temporal up-sampling folded into the gather (source has T/tdiv frames)
+  const float4 val = *reinterpret_cast<const float4*>(x + (((b * (T / tdiv) + t) * V + v) * (long long)C + c));
   __nv_bfloat162 lo = __floats2bfloat162_rn(val.x, val.y), hi = __floats2bfloat162_rn(val.z, val.w);
   uint2 pk;
   pk.x = *reinterpret_cast<uint32_t*>(&lo);
@@ -616,9 +643,9 @@ int pick_bn(long long tiles_m, int N) {
 
 template <class Epi>
 int dispatch_bn(int bn, const CUtensorMap& tmA, const void* Wptr, unsigned long long wrows, unsigned long long K,
-                TcShape sh, int N, int num_kb, const Epi& epi, cudaStream_t s) {
+                TcShape sh, int N, int num_kb, const Epi& epi, cudaStream_t s, unsigned long long wpitch = 0) {
   CUtensorMap tmB;
-  MOCHA_TRY(make_tmap(&tmB, Wptr, wrows, K, bn));
+  MOCHA_TRY(make_tmap(&tmB, Wptr, wrows, K, bn, wpitch));
   sh.tiles_n = ceil_div(N, bn);
   sh.tiles_per_unit = 1;
   sh.units = sh.tiles_m_total * sh.tiles_n;
@@ -635,7 +662,7 @@ int dispatch_bn(int bn, const CUtensorMap& tmA, const void* Wptr, unsigned long 
 // ------------------------------------------------------------------------------------------------
 // public (library-internal) API
 // ------------------------------------------------------------------------------------------------
-bool tc_linear_supported(int M, int N, int K) { return M >= 1 && N >= 16 && K >= 64 && (K % 8) == 0; }
+bool tc_linear_supported(int M, int N, int K) { return M >= 1 && N >= 8 && K >= 64 && (K % 8) == 0; }
 
 size_t tc_scratch_bytes(size_t rows, size_t K) { return align_up(rows * K * 2, 256) + 256; }
 
@@ -702,14 +729,15 @@ int tc_linear(const float* A, const float* W, const float* bias, int bias_period
 }
 
 bool tc_tconv_supported(int B, int T, int V, int Cin, int Cout, int taps) {
-  return B >= 1 && (Cin % BLOCK_K) == 0 && Cout >= 16 && (taps & 1) && taps / 2 < T && (long long)T * V >= 1;
+  return B >= 1 && (Cin % BLOCK_K) == 0 && Cout >= 8 && (taps & 1) && taps / 2 < T && (long long)T * V >= 1;
 }
 size_t tc_tconv_scratch_bytes(int B, int T, int V, int Cin, int taps) {
   return align_up((size_t)B * (T + 2 * (taps / 2)) * V * Cin * 2, 256) + 256;
 }
 
 int tc_tconv(const float* X, const float* W, const float* bias, int bias_period, float* C, int B, int T, int V,
-             int Cin, int Cout, int taps, Workspace& ws, cudaStream_t s) {
+             int Cin, int Cout, int taps, int tdiv, Workspace& ws, cudaStream_t s) {
+  MOCHA_CHECK_ARG(tdiv >= 1 && T % tdiv == 0, "tc_tconv: T=%d not a multiple of tdiv=%d", T, tdiv);
   MOCHA_CHECK_ARG(tc_tconv_supported(B, T, V, Cin, Cout, taps), "tc_tconv: unsupported geometry");
   const __nv_bfloat16* W16 = tc_lookup_bf16(W);
   if (!W16) return set_error(MOCHA_ERR_ARG, "tc_tconv: weight %p has no registered bf16 mirror", (const void*)W);
@@ -718,7 +746,7 @@ int tc_tconv(const float* X, const float* W, const float* bias, int bias_period,
   const size_t elems = (size_t)B * Tp * V * Cin;
   __nv_bfloat16* X16 = ws.take<__nv_bfloat16>(elems);
   if (!X16) return set_error(MOCHA_ERR_WORKSPACE, "tc_tconv: workspace too small for the padded bf16 operand");
-  reflect_pad_cast_kernel<<<(unsigned)((elems / 4 + 255) / 256), 256, 0, s>>>(X, X16, T, V, Cin, pad,
+  reflect_pad_cast_kernel<<<(unsigned)((elems / 4 + 255) / 256), 256, 0, s>>>(X, X16, T, V, Cin, pad, tdiv,
                                                                              (long long)(elems / 4));
   count_launch();
   MOCHA_LAUNCH_CHECK("reflect_pad_cast");
@@ -738,6 +766,155 @@ int tc_tconv(const float* X, const float* W, const float* bias, int bias_period,
                        (unsigned long long)taps * Cin, sh, Cout, taps * sh.kb_per_tap, epi, s);
   ws.off = mark;
   return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention on tensor cores: batched-head QK^T -> softmax (bf16 P) -> batched-head PV
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// fp32 [rows, cols] view with row pitch ld -> compact bf16 [rows, cols]
+__global__ void cast_strided_bf16_kernel(const float* __restrict__ x, int ld, int cols, long long total4,
+                                         __nv_bfloat16* __restrict__ y) {
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= total4) return;
+  const int c4 = cols >> 2;
+  const long long r = i4 / c4;
+  const int c = (int)(i4 - r * c4) * 4;
+  const float4 v = *reinterpret_cast<const float4*>(x + r * (long long)ld + c);
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&lo);
+  pk.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(y + r * (long long)cols + c) = pk;
+}
+
+// V fp32 [B*nkv, ldv] (head h at columns h*dh..) -> VT bf16 [B*H, dh, ldp] (kv contiguous, zero padded)
+__global__ void transpose_v_bf16_kernel(const float* __restrict__ v, int ldv, int H, int nkv, int dh, int ldp,
+                                        __nv_bfloat16* __restrict__ vt) {
+  __shared__ float tile[32][33];
+  const int z = blockIdx.z, b = z / H, h = z - b * H;
+  const int j0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int j = j0 + i, d = d0 + tx;
+    tile[i][tx] = (j < nkv && d < dh) ? v[((long long)b * nkv + j) * ldv + h * dh + d] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int d = d0 + i, j = j0 + tx;
+    if (d < dh && j < ldp) vt[((long long)z * dh + d) * ldp + j] = __float2bfloat16_rn(tile[tx][i]);
+  }
+}
+
+// softmax over the last dim of S [rows, ncols] (scaled), written as bf16 P [rows, ldp] with zero padding
+__global__ void softmax_bf16_kernel(const float* __restrict__ S, long long rows, int ncols, int ldp, float scale,
+                                    __nv_bfloat16* __restrict__ P) {
+  const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * warps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* r = S + row * ncols;
+  float v[8];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = c < ncols ? r[c] * scale : -INFINITY;
+    m = fmaxf(m, v[i]);
+  }
+  m = warp_max(m);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = c < ncols ? expf(v[i] - m) : 0.f;
+    sum += v[i];
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = lane + 32 * i;
+    if (c < ldp) P[row * ldp + c] = __float2bfloat16_rn(v[i] * inv);
+  }
+}
+
+}  // namespace
+
+bool tc_attention_supported(int nq, int nkv, int dh) {
+  return nq >= 1 && nkv >= 1 && nkv <= 256 && dh >= 64 && (dh % 64) == 0;
+}
+
+static int attn_ldp(int nkv) { return (nkv + 7) / 8 * 8; }
+
+size_t tc_attention_scratch_bytes(int B, int H, int nq, int nkv, int dh) {
+  const size_t Z = (size_t)B * H, ldp = attn_ldp(nkv);
+  return align_up((size_t)B * nq * H * dh * 2, 256) + align_up((size_t)B * nkv * H * dh * 2, 256) +
+         align_up(Z * dh * ldp * 2, 256) + align_up(Z * nq * ldp * 2, 256) + 1024;
+}
+
+int tc_attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int B, int H, int nq,
+                 int nkv, int dh, float* S, float* out, int ldo, Workspace& ws, cudaStream_t s) {
+  MOCHA_CHECK_ARG(tc_attention_supported(nq, nkv, dh), "tc_attention: unsupported geometry nq=%d nkv=%d dh=%d", nq, nkv, dh);
+  MOCHA_CHECK_ARG((ldq & 3) == 0 && (ldk & 3) == 0 && ((uintptr_t)q & 15) == 0 && ((uintptr_t)k & 15) == 0,
+                  "tc_attention: q/k views must be 16 B aligned");
+  const int inner = H * dh, Z = B * H, ldp = attn_ldp(nkv);
+  const size_t mark = ws.off;
+  __nv_bfloat16* Q16 = ws.take<__nv_bfloat16>((size_t)B * nq * inner);
+  __nv_bfloat16* K16 = ws.take<__nv_bfloat16>((size_t)B * nkv * inner);
+  __nv_bfloat16* VT16 = ws.take<__nv_bfloat16>((size_t)Z * dh * ldp);
+  __nv_bfloat16* P16 = ws.take<__nv_bfloat16>((size_t)Z * nq * ldp);
+  if (ws.overflow) return set_error(MOCHA_ERR_WORKSPACE, "tc_attention: workspace too small");
+  {
+    const long long t4 = (long long)B * nq * inner / 4;
+    cast_strided_bf16_kernel<<<(unsigned)((t4 + 255) / 256), 256, 0, s>>>(q, ldq, inner, t4, Q16);
+    const long long u4 = (long long)B * nkv * inner / 4;
+    cast_strided_bf16_kernel<<<(unsigned)((u4 + 255) / 256), 256, 0, s>>>(k, ldk, inner, u4, K16);
+    dim3 g((ldp + 31) / 32, (dh + 31) / 32, Z);
+    transpose_v_bf16_kernel<<<g, 256, 0, s>>>(v, ldv, H, nkv, dh, ldp, VT16);
+    count_launch(3);
+    MOCHA_LAUNCH_CHECK("attention staging");
+  }
+  // scores S[z] = Q[z] K[z]^T  (fp32, [Z, nq, nkv])
+  {
+    CUtensorMap tmA;
+    MOCHA_TRY(make_tmap(&tmA, Q16, (unsigned long long)B * nq, (unsigned long long)inner, BLOCK_M));
+    TcShape sh{};
+    sh.nb = Z; sh.H = H;
+    sh.rows_out_per_b = nq;
+    sh.tiles_m_per_b = ceil_div(nq, BLOCK_M);
+    sh.tiles_m_total = sh.tiles_m_per_b * Z;
+    sh.src_rows_per_b = nq; sh.a_rows_h = 0; sh.a_cols_h = dh;
+    sh.b_rows_b = nkv; sh.b_rows_h = 0; sh.b_cols_h = dh;
+    sh.c_img_b = (long long)H * nq * nkv; sh.c_img_h = (long long)nq * nkv;
+    sh.taps = 1; sh.kb_per_tap = dh / BLOCK_K; sh.tap_row_stride = 0;
+    LinearEpi epi{S, nkv, nkv, nullptr, 0, nullptr, ACT_NONE};
+    MOCHA_TRY(dispatch_bn(pick_bn(sh.tiles_m_total, nkv), tmA, K16, (unsigned long long)B * nkv,
+                          (unsigned long long)inner, sh, nkv, dh / BLOCK_K, epi, s));
+  }
+  softmax_bf16_kernel<<<(unsigned)(((long long)Z * nq + 7) / 8), 256, 0, s>>>(S, (long long)Z * nq, nkv, ldp,
+                                                                            1.0f / sqrtf((float)dh), P16);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("softmax_bf16_kernel");
+  // out[b, :, h*dh:(h+1)*dh] = P[z] V[z]
+  {
+    CUtensorMap tmA;
+    MOCHA_TRY(make_tmap(&tmA, P16, (unsigned long long)Z * nq, (unsigned long long)ldp, BLOCK_M));
+    TcShape sh{};
+    sh.nb = Z; sh.H = H;
+    sh.rows_out_per_b = nq;
+    sh.tiles_m_per_b = ceil_div(nq, BLOCK_M);
+    sh.tiles_m_total = sh.tiles_m_per_b * Z;
+    sh.src_rows_per_b = (long long)H * nq; sh.a_rows_h = nq; sh.a_cols_h = 0;
+    sh.b_rows_b = (long long)H * dh; sh.b_rows_h = dh; sh.b_cols_h = 0;
+    sh.c_img_b = (long long)nq * ldo; sh.c_img_h = dh;
+    sh.taps = 1; sh.kb_per_tap = ceil_div(ldp, BLOCK_K); sh.tap_row_stride = 0;
+    LinearEpi epi{out, ldo, dh, nullptr, 0, nullptr, ACT_NONE};
+    MOCHA_TRY(dispatch_bn(pick_bn(sh.tiles_m_total, dh), tmA, VT16, (unsigned long long)Z * dh,
+                          (unsigned long long)ldp, sh, dh, ceil_div(ldp, BLOCK_K), epi, s));
+  }
+  ws.off = mark;
+  return MOCHA_OK;
 }
 
 int tc_match_splits(int nq, long long N) {

@@ -32,7 +32,14 @@ int tc_linear_bf16(const __nv_bfloat16* A16, const __nv_bfloat16* W16, const flo
 bool tc_tconv_supported(int B, int T, int V, int Cin, int Cout, int taps);
 size_t tc_tconv_scratch_bytes(int B, int T, int V, int Cin, int taps);
 int tc_tconv(const float* X, const float* W, const float* bias, int bias_period, float* C, int B, int T, int V,
-             int Cin, int Cout, int taps, Workspace& ws, cudaStream_t s);
+             int Cin, int Cout, int taps, int tdiv, Workspace& ws, cudaStream_t s);
+
+// ---- attention: softmax(Q K^T / sqrt(dh)) V for B*H (batch, head) problems on tensor cores ------------
+// q/k/v are fp32 strided views [B*n, ld] with head h at columns h*dh; S is a [B,H,nq,nkv] fp32 scratch.
+bool tc_attention_supported(int nq, int nkv, int dh);
+size_t tc_attention_scratch_bytes(int B, int H, int nq, int nkv, int dh);
+int tc_attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int B, int H, int nq,
+                 int nkv, int dh, float* S, float* out, int ldo, Workspace& ws, cudaStream_t s);
 
 // ---- matcher coarse pass ---------------------------------------------------------------------------
 constexpr int MATCH_KC_MAX = 16;

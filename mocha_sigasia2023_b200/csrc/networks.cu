@@ -36,8 +36,8 @@ int dense(const Ctx& c, const float* A, int lda, const float* W, const float* bi
 // reflect-padded temporal convolution as implicit GEMM (blocks.py:113-118,:132)
 int tconv(const Ctx& c, const float* A, const float* W, const float* bias, int bias_period, float* C, int B,
           int T, int V, int Cin, int Cout, int taps, int tdiv) {
-  if (c.precision == MOCHA_BF16 && tdiv == 1 && tc_tconv_supported(B, T, V, Cin, Cout, taps))
-    return tc_tconv(A, W, bias, bias_period, C, B, T, V, Cin, Cout, taps, *c.ws, c.s);
+  if (c.precision == MOCHA_BF16 && tc_tconv_supported(B, T, V, Cin, Cout, taps))
+    return tc_tconv(A, W, bias, bias_period, C, B, T, V, Cin, Cout, taps, tdiv, *c.ws, c.s);
   GemmParams p;
   p.A = A; p.W = W; p.C = C;
   p.M = B * T * V; p.N = Cout; p.K = taps * Cin;
@@ -51,6 +51,8 @@ int tconv(const Ctx& c, const float* A, const float* W, const float* bias, int b
 // projection buffers. S is a [B,H,nq,nkv] scratch.
 int attention(const Ctx& c, const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int B,
               int H, int nq, int nkv, int dh, float* S, float* out, int ldo) {
+  if (c.precision == MOCHA_BF16 && tc_attention_supported(nq, nkv, dh))
+    return tc_attention(q, ldq, k, ldk, v, ldv, B, H, nq, nkv, dh, S, out, ldo, *c.ws, c.s);
   GemmParams p;
   p.A = q; p.lda = ldq; p.sA1 = (long long)nq * ldq; p.sA2 = dh;
   p.W = k; p.ldw = ldk; p.sW1 = (long long)nkv * ldk; p.sW2 = dh;
@@ -157,6 +159,7 @@ extern "C" size_t mocha_encoder_workspace_bytes(const mocha_dims* d, int B) {
   bytes += pad256(R * d->D * 4) * 2;                   // x ping-pong
   bytes += pad256(R * d->mlp * 4);                     // hidden
   bytes += tc_scratch_bytes(R, inner > (size_t)d->mlp ? inner : d->mlp);
+  bytes += tc_attention_scratch_bytes(B, d->heads, (int)n, (int)n, d->enc_dh);
   return bytes + 4096;
 }
 
@@ -213,6 +216,7 @@ extern "C" size_t mocha_decoder_workspace_bytes(const mocha_dims* d, int B) {
   bytes += pad256((size_t)B * d->heads * n * n * 4);
   bytes += pad256(R * d->mlp * 4);
   bytes += tc_scratch_bytes(R, inner > (size_t)d->mlp ? inner : d->mlp);
+  bytes += tc_attention_scratch_bytes(B, d->heads, (int)n, (int)n, d->dec_dh);
   return bytes + 4096;
 }
 
@@ -286,6 +290,8 @@ extern "C" size_t mocha_to_mot_workspace_bytes(const mocha_dims* d, int B) {
   bytes += pad256(R * d->Cin * 4);                        // Ytil when the caller only wants Y
   bytes += tc_scratch_bytes(R2, d->Kb * d->D);
   bytes += tc_tconv_scratch_bytes(B, d->T / d->tp, d->P, d->D, d->taps_b);
+  bytes += tc_tconv_scratch_bytes(B, d->T, d->V, d->C0, d->taps_j);
+  bytes += tc_scratch_bytes(R, d->C0);
   return bytes + 4096;
 }
 
@@ -342,6 +348,7 @@ extern "C" size_t mocha_cvae_workspace_bytes(const mocha_cvae_weights* w, int B,
   bytes += pad256(Rm * 2 * D * 4);         // memory K|V
   bytes += pad256(Rq * D * 4) * 3;         // decoder x ping-pong + q
   bytes += tc_scratch_bytes(Rp, w->dff);
+  bytes += tc_attention_scratch_bytes(B, w->heads, (int)np, (int)np, (int)(D / w->heads));
   return bytes + 4096;
 }
 

@@ -110,6 +110,8 @@ def test_bf16_tensor_core_mode(gold):
     src, cha = gi.pose_windows()
     tok = g.mot_embedding(cu(src)).cpu().numpy()
     assert rel_err(tok, gold["tokens"]) < RTOL_BF16
+    enc = g.encoder(cu(gold["tokens"]) + g.pos_emb[:, :90]).cpu().numpy()
+    assert rel_err(enc, gold["src_encoded"]) < RTOL_BF16
     dec = g.decoder(cu(gold["src_encoded"]), cu(gold["cha_encoded"])).cpu().numpy()
     assert rel_err(dec, gold["decoded"]) < RTOL_BF16
     y = g.to_mot(cu(gold["decoded"])).cpu().numpy()
