@@ -33,10 +33,12 @@ def make_clip(n_frames: int = 240, seed: int = 0, fps: float = 60.0) -> dict:
     phase = rng.uniform(0.0, 2 * np.pi, size=(J, 3))
     rotations = amp[None] * np.sin(2 * np.pi * freq[None] * t[:, None, None] + phase[None])
     rotations[:, 0, :] *= 0.3                                   # keep the pelvis mostly upright
+    legs = [1, 2, 3, 4, 20, 21, 22, 23]
+    rotations[:, legs, :] *= 0.3                                # slow feet -> stance phases (foot contacts) occur
     rotations[:, 0, 1] += 20.0 * np.sin(2 * np.pi * 0.1 * t + rng.uniform(0, 2 * np.pi))  # slow heading change
     offsets = _OFFSETS_CM + rng.normal(0.0, 1.0, size=_OFFSETS_CM.shape)
     positions = np.repeat(offsets[None], n_frames, axis=0)
-    speed = rng.uniform(80.0, 160.0)                            # cm/s
+    speed = rng.uniform(16.0, 32.0)                             # cm/s (slow walk so toes drop below 0.5 m/s)
     positions[:, 0, 0] = 10.0 * np.sin(2 * np.pi * 0.25 * t)
     positions[:, 0, 1] = offsets[0, 1] + 3.0 * np.sin(2 * np.pi * 1.8 * t)
     positions[:, 0, 2] = speed * t
