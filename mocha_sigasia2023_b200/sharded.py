@@ -1,0 +1,83 @@
+"""Row-sharded context matching across GPUs (BASELINE config 5).
+
+The character feature DB is split by rows over the ranks of a torch.distributed group (one process
+per GPU, NCCL over NVLink); queries are replicated. Every rank finds its local exact top-k
+(distance fp64 + GLOBAL row index int64), the [nq,k] candidate lists are all-gathered — a
+latency-bound exchange of nq*k*16 bytes per rank — and merged by (distance, index) with a small
+CUDA kernel (mocha_topk_merge). The exact fp64 re-rank happens on the shard that owns the row, so
+only final distances travel."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+def shard_bounds(n_rows: int, world: int, rank: int) -> "tuple[int, int]":
+    """Contiguous, balanced row range [lo, hi) of `rank` (first n_rows % world ranks get one extra)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad world/rank")
+    base, extra = divmod(n_rows, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def merge_topk_cuda(all_dist: torch.Tensor, all_idx: torch.Tensor, k: int):
+    """all_dist [S,nq,k] fp64, all_idx [S,nq,k] int64 (-1 = empty) on CUDA -> merged ([nq,k], [nq,k])."""
+    S, nq, kk = all_dist.shape
+    out_d = torch.empty((nq, k), dtype=torch.float64, device=all_dist.device)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=all_dist.device)
+    if kk != k:
+        raise _lib.MochaError("merge_topk_cuda: candidate lists must have length k")
+    _lib.check(_lib.load().mocha_topk_merge(_lib.ptr(all_dist.contiguous()), _lib.ptr(all_idx.contiguous()), S, nq, k,
+                                            _lib.ptr(out_d), _lib.ptr(out_i), _lib.stream_ptr()), "mocha_topk_merge")
+    return out_d, out_i
+
+
+class ShardedMatcher:
+    """k-NN over a DB whose rows live on different ranks.
+
+    local_query(q, k) -> (dist [nq,k'] fp64, idx [nq,k'] int64 LOCAL row ids) with k' = min(k, rows);
+    defaults to this rank's `BallTree.query_device`. merge(all_dist, all_idx, k) defaults to the CUDA
+    merge kernel. Both are injectable so the host-side protocol is testable on CPU with gloo.
+    """
+
+    def __init__(self, n_rows_total: int, local_query, group=None, merge=merge_topk_cuda):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_total = n_rows_total
+        self.lo, self.hi = shard_bounds(n_rows_total, self.world, self.rank)
+        self.local_query = local_query
+        self.merge = merge
+
+    def query(self, q: torch.Tensor, k: int = 1):
+        n_local = self.hi - self.lo
+        kk = min(k, n_local)
+        dev = q.device
+        d_loc = torch.full((q.shape[0], k), float("inf"), dtype=torch.float64, device=dev)
+        i_loc = torch.full((q.shape[0], k), -1, dtype=torch.int64, device=dev)
+        if kk > 0:
+            d, i = self.local_query(q, kk)
+            d_loc[:, :kk] = d
+            i_loc[:, :kk] = i + self.lo          # global row index = local index + shard offset
+        if self.world == 1:
+            return d_loc, i_loc
+        nq = d_loc.shape[0]
+        all_d = torch.empty((self.world * nq, k), dtype=torch.float64, device=dev)
+        all_i = torch.empty((self.world * nq, k), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(all_d, d_loc.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(all_i, i_loc.contiguous(), group=self.group)
+        return self.merge(all_d.view(self.world, nq, k), all_i.view(self.world, nq, k), k)
+
+
+def sharded_balltree(db_rows_local: torch.Tensor, n_rows_total: int, group=None, **tree_kwargs) -> ShardedMatcher:
+    """Build the per-rank BallTree over this rank's rows and wrap it in a ShardedMatcher."""
+    from .balltree import BallTree
+    tree = BallTree(db_rows_local, **tree_kwargs)
+    m = ShardedMatcher(n_rows_total, lambda q, k: tree.query_device(q, k=k, return_distance=True), group=group)
+    if m.hi - m.lo != tree.N:
+        raise _lib.MochaError(f"rank {m.rank} holds {tree.N} rows but its shard is [{m.lo},{m.hi})")
+    m.tree = tree
+    return m

@@ -74,3 +74,22 @@ def test_query_validation():
         tree.query(q[:, :10], k=1)
     with pytest.raises(ValueError):
         tree.query(q, k=db.shape[0] + 1)
+
+
+def test_topk_merge_logical_shards():
+    """Row-sharded matching on ONE device: G logical shards, CUDA merge kernel (SURVEY §4 tier note)."""
+    from mocha_sigasia2023_b200.sharded import merge_topk_cuda, shard_bounds
+    rng = np.random.default_rng(5)
+    N, D, nq, k, G = 1003, 160, 33, 3, 4
+    db = rng.standard_normal((N, D)).astype(np.float32)
+    q = rng.standard_normal((nq, D)).astype(np.float32)
+    qd = torch.from_numpy(q).cuda()
+    ds, ids = [], []
+    for r in range(G):
+        lo, hi = shard_bounds(N, G, r)
+        d, i = BallTree(db[lo:hi], use_tensor_cores=False).query_device(qd, k=k)
+        ds.append(d); ids.append(i + lo)
+    d, i = merge_topk_cuda(torch.stack(ds), torch.stack(ids), k)
+    wd, wi = matching.knn(db, q, k)
+    np.testing.assert_array_equal(i.cpu().numpy(), wi)
+    np.testing.assert_allclose(d.cpu().numpy(), wd, rtol=1e-12)
