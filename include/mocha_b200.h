@@ -159,9 +159,10 @@ int mocha_embed_fwd(const mocha_generator_weights* w, const float* d_X, int B, f
 
 /* The JointBlock temporal convolution of mot_embedding alone (nn.Conv2d (5,1), reflect padding,
  * net/blocks.py:112-118): x [B*T*V, D] channel-last -> out [B*T*V, D]. Used by bench.py to time the
- * dominant kernel of the batched path in isolation. */
+ * dominant kernel of the batched path in isolation: the operand is staged once (bf16 reflect-padded
+ * copy in MOCHA_BF16 mode) and the GEMM kernel is launched gemm_repeats (>= 1) times back to back. */
 int mocha_bench_tconv(const mocha_generator_weights* w, const float* d_x, int B, float* d_out, int precision,
-                      void* workspace, size_t workspace_bytes, mocha_stream_t stream);
+                      int gemm_repeats, void* workspace, size_t workspace_bytes, mocha_stream_t stream);
 
 /* ---- (a3) Generator.encoder = Transformer(adain=False)  net/transformer.py:79-95 ------------ */
 size_t mocha_encoder_workspace_bytes(const mocha_dims* dims, int B);

@@ -115,7 +115,7 @@ SIGNATURES = {
     "mocha_register_bf16_blob": (_I, [_P, _P, _S]),
     "mocha_embed_workspace_bytes": (_S, [C.POINTER(Dims), _I]),
     "mocha_embed_fwd": (_I, [C.POINTER(GeneratorWeights), _P, _I, _P, _I, _I, _P, _S, _P]),
-    "mocha_bench_tconv": (_I, [C.POINTER(GeneratorWeights), _P, _I, _P, _I, _P, _S, _P]),
+    "mocha_bench_tconv": (_I, [C.POINTER(GeneratorWeights), _P, _I, _P, _I, _I, _P, _S, _P]),
     "mocha_encoder_workspace_bytes": (_S, [C.POINTER(Dims), _I]),
     "mocha_encoder_fwd": (_I, [C.POINTER(GeneratorWeights), _P, _I, _P, _I, _P, _S, _P]),
     "mocha_cnt_features": (_I, [_P, _I, _I, _I, _F, _P, _P, _P, _P, _P]),

@@ -32,7 +32,7 @@ int tc_linear_bf16(const __nv_bfloat16* A16, const __nv_bfloat16* W16, const flo
 bool tc_tconv_supported(int B, int T, int V, int Cin, int Cout, int taps);
 size_t tc_tconv_scratch_bytes(int B, int T, int V, int Cin, int taps);
 int tc_tconv(const float* X, const float* W, const float* bias, int bias_period, float* C, int B, int T, int V,
-             int Cin, int Cout, int taps, int tdiv, Workspace& ws, cudaStream_t s);
+             int Cin, int Cout, int taps, int tdiv, Workspace& ws, cudaStream_t s, int repeat = 1);
 
 // ---- attention: softmax(Q K^T / sqrt(dh)) V for B*H (batch, head) problems on tensor cores ------------
 // q/k/v are fp32 strided views [B*n, ld] with head h at columns h*dh; S is a [B,H,nq,nkv] fp32 scratch.

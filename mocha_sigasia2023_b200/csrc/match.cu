@@ -15,59 +15,84 @@ namespace {
 constexpr int KMAX = 16;
 constexpr int EXQ = 4;  // queries per pass of the exact kernel
 
-// One CTA per (DB row, group of EXQ queries): the row is streamed once with 128-bit loads, each
-// thread accumulating (q - x)^2 in fp64 for its slice of D; warp shuffles + a tiny smem pass reduce.
-// grid = (N, ceil(nq / EXQ)); the DB (35 MB at the reference's size) stays L2-resident across groups.
+// One CTA per (RB DB rows, QB queries) tile: every thread owns a slice of D and accumulates the RB x QB
+// squared differences in fp64 registers (rows and queries are loaded once per tile, 128-bit loads,
+// fp32 -> fp64 conversion amortised over the tile); warp shuffles + a small smem pass reduce over D.
+// <1,4> serves batch-1 streaming (385 CTAs for the reference-size DB), <8,8> serves batched queries
+// (L2 traffic per pair drops 5x, which is what bounds the small tile).
+template <int RB, int QB>
 __global__ void __launch_bounds__(256)
-match_exact_dist_kernel(const float* __restrict__ Q, int nq, const float* __restrict__ DB, long long N, int D,
+match_exact_tile_kernel(const float* __restrict__ Q, int nq, const float* __restrict__ DB, long long N, int D,
                         double* __restrict__ dist2) {
-  __shared__ double red[8][EXQ];
+  __shared__ double red[8][RB * QB];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = blockIdx.x;
-  const int q0 = blockIdx.y * EXQ;
-  const float* x = DB + row * (long long)D;
-  double acc[EXQ];
+  const long long row0 = (long long)blockIdx.x * RB;
+  const int q0 = blockIdx.y * QB;
+  const float* xr[RB];
+  const float* qr[QB];
 #pragma unroll
-  for (int j = 0; j < EXQ; ++j) acc[j] = 0.0;
-  const int nqq = min(EXQ, nq - q0);
+  for (int r = 0; r < RB; ++r) xr[r] = DB + (row0 + r < N ? row0 + r : N - 1) * (long long)D;   // clamped: result unused
+#pragma unroll
+  for (int j = 0; j < QB; ++j) qr[j] = Q + (long long)(q0 + j < nq ? q0 + j : nq - 1) * D;
+  double acc[RB][QB];
+#pragma unroll
+  for (int r = 0; r < RB; ++r)
+#pragma unroll
+    for (int j = 0; j < QB; ++j) acc[r][j] = 0.0;
   if ((D & 3) == 0 && ((reinterpret_cast<uintptr_t>(DB) & 15) == 0) && ((reinterpret_cast<uintptr_t>(Q) & 15) == 0)) {
     for (int d = threadIdx.x * 4; d < D; d += 1024) {
-      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + d));
+      double xd[RB][4];
 #pragma unroll
-      for (int j = 0; j < EXQ; ++j) {
-        if (j < nqq) {
-          const float4 qv = __ldg(reinterpret_cast<const float4*>(Q + (long long)(q0 + j) * D + d));
-          const double a = (double)qv.x - (double)xv.x, b = (double)qv.y - (double)xv.y;
-          const double c = (double)qv.z - (double)xv.z, e = (double)qv.w - (double)xv.w;
-          acc[j] = fma(a, a, acc[j]);
-          acc[j] = fma(b, b, acc[j]);
-          acc[j] = fma(c, c, acc[j]);
-          acc[j] = fma(e, e, acc[j]);
+      for (int r = 0; r < RB; ++r) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(xr[r] + d));
+        xd[r][0] = (double)v.x; xd[r][1] = (double)v.y; xd[r][2] = (double)v.z; xd[r][3] = (double)v.w;
+      }
+#pragma unroll
+      for (int j = 0; j < QB; ++j) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(qr[j] + d));
+        const double qd[4] = {(double)v.x, (double)v.y, (double)v.z, (double)v.w};
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const double a = qd[e] - xd[r][e];
+            acc[r][j] = fma(a, a, acc[r][j]);
+          }
         }
       }
     }
   } else {
     for (int d = threadIdx.x; d < D; d += 256) {
-      const double xv = (double)x[d];
+      double xd[RB];
 #pragma unroll
-      for (int j = 0; j < EXQ; ++j)
-        if (j < nqq) {
-          const double a = (double)Q[(long long)(q0 + j) * D + d] - xv;
-          acc[j] = fma(a, a, acc[j]);
+      for (int r = 0; r < RB; ++r) xd[r] = (double)xr[r][d];
+#pragma unroll
+      for (int j = 0; j < QB; ++j) {
+        const double qd = (double)qr[j][d];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          const double a = qd - xd[r];
+          acc[r][j] = fma(a, a, acc[r][j]);
         }
+      }
     }
   }
 #pragma unroll
-  for (int j = 0; j < EXQ; ++j) {
-    const double s = warp_sum(acc[j]);
-    if (lane == 0) red[warp][j] = s;
-  }
-  __syncthreads();
-  if (threadIdx.x < nqq) {
-    double s = 0.0;
+  for (int r = 0; r < RB; ++r)
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-    dist2[(long long)(q0 + threadIdx.x) * N + row] = s;
+    for (int j = 0; j < QB; ++j) {
+      const double v = warp_sum(acc[r][j]);
+      if (lane == 0) red[warp][r * QB + j] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < RB * QB) {
+    const int r = threadIdx.x / QB, j = threadIdx.x - r * QB;
+    if (row0 + r < N && q0 + j < nq) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+      dist2[(long long)(q0 + j) * N + row0 + r] = v;
+    }
   }
 }
 
@@ -267,9 +292,12 @@ extern "C" int mocha_match_exact(const float* Q, int nq, const float* DB, long l
                      workspace_bytes, ws.off);
   cudaStream_t s = (cudaStream_t)stream;
   MOCHA_CHECK_ARG(N <= 2147483647LL && (nq + EXQ - 1) / EXQ <= 65535, "mocha_match_exact: problem too large for the exact kernel (use mocha_match_tc)");
-  match_exact_dist_kernel<<<dim3((unsigned)N, (unsigned)((nq + EXQ - 1) / EXQ)), 256, 0, s>>>(Q, nq, DB, N, D, dist2);
+  if (nq >= 16 && N >= 64)
+    match_exact_tile_kernel<8, 8><<<dim3((unsigned)((N + 7) / 8), (unsigned)((nq + 7) / 8)), 256, 0, s>>>(Q, nq, DB, N, D, dist2);
+  else
+    match_exact_tile_kernel<1, EXQ><<<dim3((unsigned)N, (unsigned)((nq + EXQ - 1) / EXQ)), 256, 0, s>>>(Q, nq, DB, N, D, dist2);
   count_launch();
-  MOCHA_LAUNCH_CHECK("match_exact_dist_kernel");
+  MOCHA_LAUNCH_CHECK("match_exact_tile_kernel");
   topk_rows_kernel<<<nq, 256, 0, s>>>(dist2, N, k, index_offset, idx, dist);
   count_launch();
   MOCHA_LAUNCH_CHECK("topk_rows_kernel");

@@ -465,11 +465,16 @@ extern "C" int mocha_linear(const float* A, const float* W, const float* bias, c
 // Stand-alone entry for the dominant kernel of the batched path (bench.py roofline pass): the
 // reflect-padded temporal convolution of mot_embedding's JointBlock, x [B*T*V, D] -> out [B*T*V, D].
 extern "C" int mocha_bench_tconv(const mocha_generator_weights* w, const float* x, int B, float* out, int precision,
-                                 void* workspace, size_t workspace_bytes, mocha_stream_t stream) {
+                                 int gemm_repeats, void* workspace, size_t workspace_bytes, mocha_stream_t stream) {
   MOCHA_CHECK_ARG(w && x && out && B > 0, "mocha_bench_tconv: null/empty argument");
   MOCHA_TRY(check_dims(w->dims));
   const mocha_dims& d = w->dims;
   Workspace ws(workspace, workspace_bytes);
   Ctx c{(cudaStream_t)stream, precision, &ws};
-  return tconv(c, x, w->jb_tcn_w, w->jb_tcn_b, 0, out, B, d.T, d.V, d.D, d.D, d.taps_j, 1);
+  if (precision == MOCHA_BF16 && tc_tconv_supported(B, d.T, d.V, d.D, d.D, d.taps_j))
+    return tc_tconv(x, w->jb_tcn_w, w->jb_tcn_b, 0, out, B, d.T, d.V, d.D, d.D, d.taps_j, 1, ws, c.s, gemm_repeats);
+  int rc = MOCHA_OK;
+  for (int it = 0; it < (gemm_repeats < 1 ? 1 : gemm_repeats) && rc == MOCHA_OK; ++it)
+    rc = tconv(c, x, w->jb_tcn_w, w->jb_tcn_b, 0, out, B, d.T, d.V, d.D, d.D, d.taps_j, 1);
+  return rc;
 }

@@ -93,3 +93,15 @@ def test_topk_merge_logical_shards():
     wd, wi = matching.knn(db, q, k)
     np.testing.assert_array_equal(i.cpu().numpy(), wi)
     np.testing.assert_allclose(d.cpu().numpy(), wd, rtol=1e-12)
+
+
+@pytest.mark.parametrize("N,D,nq,k", [(385, 23040, 128, 1), (131, 203, 37, 3), (64, 64, 16, 2)])
+def test_exact_matcher_batched_tiles(N, D, nq, k):
+    """nq >= 16 takes the 8x8-tiled fp64 kernel; ragged N, nq and D exercise its clamped edges."""
+    rng = np.random.default_rng(N * 3 + nq)
+    db = rng.standard_normal((N, D)).astype(np.float32)
+    q = rng.standard_normal((nq, D)).astype(np.float32)
+    dist, idx = BallTree(db, use_tensor_cores=False).query(q, k=k, return_distance=True)
+    wd, wi = matching.knn(db, q, k)
+    np.testing.assert_array_equal(idx, wi)
+    np.testing.assert_allclose(dist, wd, rtol=1e-12)
