@@ -228,6 +228,8 @@ struct LinearEpi {
   int bias_period;
   const float* res;
   int act;
+  __nv_bfloat16* C16;   // optional bf16 copy of the output (operand of the next tensor-core layer); C may be null
+  int c16_lrelu;        // store LeakyReLU(0.2)(x) in the bf16 copy (pre-activation consumers)
   struct State {};
   static constexpr int kStageBytes = EPI_WARPS * 32 * EPI_LD * 4;  // per-warp transposition buffers
   __device__ __forceinline__ void unit_begin(State&) const {}
@@ -240,6 +242,7 @@ struct LinearEpi {
     const int c = col0 + cc;
     if (c >= N) return;
     const bool vec = ((ldc & 3) == 0) && ((e.c_off & 3) == 0) && (c + 3 < N) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(C16) & 7) == 0) &&
                      (!res || (reinterpret_cast<uintptr_t>(res) & 15) == 0) &&
                      (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0);
     const float* bp = bias;
@@ -279,7 +282,16 @@ struct LinearEpi {
           x.y = act_fn<ACT>(x.y + bv[it].y) + rv[it].y;
           x.z = act_fn<ACT>(x.z + bv[it].z) + rv[it].z;
           x.w = act_fn<ACT>(x.w + bv[it].w) + rv[it].w;
-          *reinterpret_cast<float4*>(C + e.c_off + (e.slab_row0 + r) * (long long)ldc + c) = x;
+          const long long o_ = e.c_off + (e.slab_row0 + r) * (long long)ldc + c;
+          if (C) *reinterpret_cast<float4*>(C + o_) = x;
+          if (C16) {
+            if (c16_lrelu) { x.x = lrelu02(x.x); x.y = lrelu02(x.y); x.z = lrelu02(x.z); x.w = lrelu02(x.w); }
+            __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(C16 + o_) = pk;
+          }
         }
       }
     } else {
@@ -298,7 +310,8 @@ struct LinearEpi {
           if (bp) x += bias_period > 0 ? __ldg(bp + (long long)((unsigned)grow % (unsigned)bias_period) * N + c + k) : bs[k];
           x = act_fn<ACT>(x);
           if (rp) x += __ldg(rp + e.c_off + grow * (long long)ldc + c + k);
-          C[e.c_off + grow * (long long)ldc + c + k] = x;
+          if (C) C[e.c_off + grow * (long long)ldc + c + k] = x;
+          if (C16) C16[e.c_off + grow * (long long)ldc + c + k] = __float2bfloat16_rn(c16_lrelu ? lrelu02(x) : x);
         }
       }
     }
@@ -654,6 +667,27 @@ __global__ void reflect_pad_cast_kernel(const float* __restrict__ x, __nv_bfloat
   *reinterpret_cast<uint2*>(y + i) = pk;
 }
 
+// bf16 source variant (8 elements = 16 B per thread)
+__global__ void reflect_pad_copy_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int T, int V,
+                                        int C, int pad, int tdiv, long long total8) {
+  const long long i8 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i8 >= total8) return;
+  const long long i = i8 * 8;
+  const int c = (int)(i % C);
+  const long long r = i / C;
+  const int v = (int)(r % V);
+  const long long bt = r / V;
+  const int Tp = T + 2 * pad;
+  const int tp = (int)(bt % Tp);
+  const long long b = bt / Tp;
+  int t = tp - pad;
+  if (t < 0) t = -t;
+  if (t >= T) t = 2 * (T - 1) - t;
+  t /= tdiv;
+  *reinterpret_cast<uint4*>(y + i) =
+      *reinterpret_cast<const uint4*>(x + (((b * (T / tdiv) + t) * V + v) * (long long)C + c));
+}
+
 struct Blob {
   const float* b32;
   const __nv_bfloat16* b16;
@@ -726,12 +760,12 @@ const __nv_bfloat16* tc_lookup_bf16(const float* W) {
   return nullptr;
 }
 
-int tc_linear_bf16(const __nv_bfloat16* A16, const __nv_bfloat16* W16, const float* bias, int bias_period,
-                   const float* res, float* C, int M, int N, int K, int act, cudaStream_t s) {
-  MOCHA_CHECK_ARG(A16 && W16 && C, "tc_linear: null operand");
+int tc_linear_bf16(const __nv_bfloat16* A16, int lda, const __nv_bfloat16* W16, const float* bias, int bias_period,
+                   const float* res, TcOut out, int M, int N, int K, int act, cudaStream_t s) {
+  MOCHA_CHECK_ARG(A16 && W16 && (out.f32 || out.bf16), "tc_linear: null operand");
   MOCHA_CHECK_ARG(tc_linear_supported(M, N, K), "tc_linear: unsupported shape M=%d N=%d K=%d", M, N, K);
   CUtensorMap tmA;
-  MOCHA_TRY(make_tmap(&tmA, A16, (unsigned long long)M, (unsigned long long)K, BLOCK_M));
+  MOCHA_TRY(make_tmap(&tmA, A16, (unsigned long long)M, (unsigned long long)K, BLOCK_M, (unsigned long long)lda));
   TcShape sh{};
   sh.nb = 1;
   sh.rows_out_per_b = M;
@@ -741,7 +775,7 @@ int tc_linear_bf16(const __nv_bfloat16* A16, const __nv_bfloat16* W16, const flo
   sh.taps = 1;
   sh.kb_per_tap = ceil_div(K, BLOCK_K);
   sh.tap_row_stride = 0;
-  LinearEpi epi{C, N, N, bias, bias_period, res, act};
+  LinearEpi epi{out.f32, N, N, bias, bias_period, res, act, out.bf16, out.lrelu};
   return dispatch_bn(pick_bn(sh.tiles_m_total, N), tmA, W16, (unsigned long long)N, (unsigned long long)K, sh, N,
                      ceil_div(K, BLOCK_K), epi, s);
 }
@@ -753,14 +787,18 @@ int tc_linear(const float* A, const float* W, const float* bias, int bias_period
   const size_t mark = ws.off;
   __nv_bfloat16* A16 = ws.take<__nv_bfloat16>((size_t)M * K);
   if (!A16) return set_error(MOCHA_ERR_WORKSPACE, "tc_linear: workspace too small for the bf16 A operand");
-  const long long n = (long long)M * K;
-  MOCHA_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0, "tc_linear: A not 16B aligned");
-  cast_act_bf16_kernel<<<(unsigned)((n / 4 + 255) / 256 + 1), 256, 0, s>>>(A, A16, n, a_lrelu);
-  count_launch();
-  MOCHA_LAUNCH_CHECK("cast_act_bf16");
-  int rc = tc_linear_bf16(A16, W16, bias, bias_period, res, C, M, N, K, act, s);
+  MOCHA_TRY(tc_cast(A, A16, (long long)M * K, a_lrelu, s));
+  int rc = tc_linear_bf16(A16, K, W16, bias, bias_period, res, TcOut{C, nullptr, 0}, M, N, K, act, s);
   ws.off = mark;  // stream order makes the scratch reusable by the next layer
   return rc;
+}
+
+int tc_cast(const float* x, __nv_bfloat16* y, long long n, int lrelu, cudaStream_t s) {
+  MOCHA_CHECK_ARG(x && y && n > 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "tc_cast: bad argument");
+  cast_act_bf16_kernel<<<(unsigned)((n / 4 + 255) / 256 + 1), 256, 0, s>>>(x, y, n, lrelu);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("cast_act_bf16");
+  return MOCHA_OK;
 }
 
 bool tc_tconv_supported(int B, int T, int V, int Cin, int Cout, int taps) {
@@ -772,6 +810,12 @@ size_t tc_tconv_scratch_bytes(int B, int T, int V, int Cin, int taps) {
 
 int tc_tconv(const float* X, const float* W, const float* bias, int bias_period, float* C, int B, int T, int V,
              int Cin, int Cout, int taps, int tdiv, Workspace& ws, cudaStream_t s, int repeat) {
+  return tc_tconv_ex(X, nullptr, W, bias, bias_period, TcOut{C, nullptr, 0}, B, T, V, Cin, Cout, taps, tdiv, ws, s, repeat);
+}
+
+int tc_tconv_ex(const float* X, const __nv_bfloat16* Xh, const float* W, const float* bias, int bias_period, TcOut out,
+                int B, int T, int V, int Cin, int Cout, int taps, int tdiv, Workspace& ws, cudaStream_t s, int repeat) {
+  MOCHA_CHECK_ARG((X || Xh) && (out.f32 || out.bf16), "tc_tconv: null operand");
   MOCHA_CHECK_ARG(tdiv >= 1 && T % tdiv == 0, "tc_tconv: T=%d not a multiple of tdiv=%d", T, tdiv);
   MOCHA_CHECK_ARG(tc_tconv_supported(B, T, V, Cin, Cout, taps), "tc_tconv: unsupported geometry");
   const __nv_bfloat16* W16 = tc_lookup_bf16(W);
@@ -781,8 +825,12 @@ int tc_tconv(const float* X, const float* W, const float* bias, int bias_period,
   const size_t elems = (size_t)B * Tp * V * Cin;
   __nv_bfloat16* X16 = ws.take<__nv_bfloat16>(elems);
   if (!X16) return set_error(MOCHA_ERR_WORKSPACE, "tc_tconv: workspace too small for the padded bf16 operand");
-  reflect_pad_cast_kernel<<<(unsigned)((elems / 4 + 255) / 256), 256, 0, s>>>(X, X16, T, V, Cin, pad, tdiv,
-                                                                             (long long)(elems / 4));
+  if (Xh)
+    reflect_pad_copy_kernel<<<(unsigned)((elems / 8 + 255) / 256), 256, 0, s>>>(Xh, X16, T, V, Cin, pad, tdiv,
+                                                                               (long long)(elems / 8));
+  else
+    reflect_pad_cast_kernel<<<(unsigned)((elems / 4 + 255) / 256), 256, 0, s>>>(X, X16, T, V, Cin, pad, tdiv,
+                                                                               (long long)(elems / 4));
   count_launch();
   MOCHA_LAUNCH_CHECK("reflect_pad_cast");
   CUtensorMap tmA;
@@ -796,7 +844,7 @@ int tc_tconv(const float* X, const float* W, const float* bias, int bias_period,
   sh.taps = taps;
   sh.kb_per_tap = Cin / BLOCK_K;
   sh.tap_row_stride = V;
-  LinearEpi epi{C, Cout, Cout, bias, bias_period, nullptr, ACT_NONE};
+  LinearEpi epi{out.f32, Cout, Cout, bias, bias_period, nullptr, ACT_NONE, out.bf16, out.lrelu};
   int rc = MOCHA_OK;
   for (int it = 0; it < (repeat < 1 ? 1 : repeat) && rc == MOCHA_OK; ++it)  // repeat > 1: bench.py roofline pass
     rc = dispatch_bn(pick_bn(sh.tiles_m_total, Cout), tmA, W16, (unsigned long long)Cout,
@@ -827,7 +875,10 @@ __global__ void cast_strided_bf16_kernel(const float* __restrict__ x, int ld, in
 }
 
 // V fp32 [B*nkv, ldv] (head h at columns h*dh..) -> VT bf16 [B*H, dh, ldp] (kv contiguous, zero padded)
-__global__ void transpose_v_bf16_kernel(const float* __restrict__ v, int ldv, int H, int nkv, int dh, int ldp,
+__device__ __forceinline__ float to_f32(float x) { return x; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 x) { return __bfloat162float(x); }
+template <typename TV>
+__global__ void transpose_v_bf16_kernel(const TV* __restrict__ v, int ldv, int H, int nkv, int dh, int ldp,
                                         __nv_bfloat16* __restrict__ vt) {
   __shared__ float tile[32][33];
   const int z = blockIdx.z, b = z / H, h = z - b * H;
@@ -835,7 +886,7 @@ __global__ void transpose_v_bf16_kernel(const float* __restrict__ v, int ldv, in
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   for (int i = ty; i < 32; i += 8) {
     const int j = j0 + i, d = d0 + tx;
-    tile[i][tx] = (j < nkv && d < dh) ? v[((long long)b * nkv + j) * ldv + h * dh + d] : 0.f;
+    tile[i][tx] = (j < nkv && d < dh) ? to_f32(v[((long long)b * nkv + j) * ldv + h * dh + d]) : 0.f;
   }
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
@@ -892,30 +943,54 @@ size_t tc_attention_scratch_bytes(int B, int H, int nq, int nkv, int dh) {
 
 int tc_attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int B, int H, int nq,
                  int nkv, int dh, float* S, float* out, int ldo, Workspace& ws, cudaStream_t s) {
+  return tc_attention_ex(q, nullptr, ldq, k, nullptr, ldk, v, nullptr, ldv, B, H, nq, nkv, dh, S, TcOut{out, nullptr, 0},
+                         ldo, ws, s);
+}
+
+// Operands may be given as fp32 views (cast / transposed into scratch) or directly as bf16 views
+// (qh/kh feed the TMA descriptors in place through their row pitch; vh is transposed from bf16).
+int tc_attention_ex(const float* q, const __nv_bfloat16* qh, int ldq, const float* k, const __nv_bfloat16* kh, int ldk,
+                    const float* v, const __nv_bfloat16* vh, int ldv, int B, int H, int nq, int nkv, int dh, float* S,
+                    TcOut out, int ldo, Workspace& ws, cudaStream_t s) {
   MOCHA_CHECK_ARG(tc_attention_supported(nq, nkv, dh), "tc_attention: unsupported geometry nq=%d nkv=%d dh=%d", nq, nkv, dh);
-  MOCHA_CHECK_ARG((ldq & 3) == 0 && (ldk & 3) == 0 && ((uintptr_t)q & 15) == 0 && ((uintptr_t)k & 15) == 0,
-                  "tc_attention: q/k views must be 16 B aligned");
+  MOCHA_CHECK_ARG((q || qh) && (k || kh) && (v || vh) && S && (out.f32 || out.bf16), "tc_attention: null operand");
   const int inner = H * dh, Z = B * H, ldp = attn_ldp(nkv);
   const size_t mark = ws.off;
-  __nv_bfloat16* Q16 = ws.take<__nv_bfloat16>((size_t)B * nq * inner);
-  __nv_bfloat16* K16 = ws.take<__nv_bfloat16>((size_t)B * nkv * inner);
+  const __nv_bfloat16* Q16 = qh;
+  const __nv_bfloat16* K16 = kh;
+  int pq = ldq, pk = ldk;
+  if (!qh) {
+    MOCHA_CHECK_ARG((ldq & 3) == 0 && ((uintptr_t)q & 15) == 0, "tc_attention: q view must be 16 B aligned");
+    __nv_bfloat16* t = ws.take<__nv_bfloat16>((size_t)B * nq * inner);
+    if (!t) return set_error(MOCHA_ERR_WORKSPACE, "tc_attention: workspace too small");
+    const long long t4 = (long long)B * nq * inner / 4;
+    cast_strided_bf16_kernel<<<(unsigned)((t4 + 255) / 256), 256, 0, s>>>(q, ldq, inner, t4, t);
+    count_launch();
+    Q16 = t; pq = inner;
+  }
+  if (!kh) {
+    MOCHA_CHECK_ARG((ldk & 3) == 0 && ((uintptr_t)k & 15) == 0, "tc_attention: k view must be 16 B aligned");
+    __nv_bfloat16* t = ws.take<__nv_bfloat16>((size_t)B * nkv * inner);
+    if (!t) return set_error(MOCHA_ERR_WORKSPACE, "tc_attention: workspace too small");
+    const long long u4 = (long long)B * nkv * inner / 4;
+    cast_strided_bf16_kernel<<<(unsigned)((u4 + 255) / 256), 256, 0, s>>>(k, ldk, inner, u4, t);
+    count_launch();
+    K16 = t; pk = inner;
+  }
   __nv_bfloat16* VT16 = ws.take<__nv_bfloat16>((size_t)Z * dh * ldp);
   __nv_bfloat16* P16 = ws.take<__nv_bfloat16>((size_t)Z * nq * ldp);
   if (ws.overflow) return set_error(MOCHA_ERR_WORKSPACE, "tc_attention: workspace too small");
   {
-    const long long t4 = (long long)B * nq * inner / 4;
-    cast_strided_bf16_kernel<<<(unsigned)((t4 + 255) / 256), 256, 0, s>>>(q, ldq, inner, t4, Q16);
-    const long long u4 = (long long)B * nkv * inner / 4;
-    cast_strided_bf16_kernel<<<(unsigned)((u4 + 255) / 256), 256, 0, s>>>(k, ldk, inner, u4, K16);
     dim3 g((ldp + 31) / 32, (dh + 31) / 32, Z);
-    transpose_v_bf16_kernel<<<g, 256, 0, s>>>(v, ldv, H, nkv, dh, ldp, VT16);
-    count_launch(3);
+    if (vh) transpose_v_bf16_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(vh, ldv, H, nkv, dh, ldp, VT16);
+    else transpose_v_bf16_kernel<float><<<g, 256, 0, s>>>(v, ldv, H, nkv, dh, ldp, VT16);
+    count_launch();
     MOCHA_LAUNCH_CHECK("attention staging");
   }
   // scores S[z] = Q[z] K[z]^T  (fp32, [Z, nq, nkv])
   {
     CUtensorMap tmA;
-    MOCHA_TRY(make_tmap(&tmA, Q16, (unsigned long long)B * nq, (unsigned long long)inner, BLOCK_M));
+    MOCHA_TRY(make_tmap(&tmA, Q16, (unsigned long long)B * nq, (unsigned long long)inner, BLOCK_M, (unsigned long long)pq));
     TcShape sh{};
     sh.nb = Z; sh.H = H;
     sh.rows_out_per_b = nq;
@@ -925,9 +1000,9 @@ int tc_attention(const float* q, int ldq, const float* k, int ldk, const float* 
     sh.b_rows_b = nkv; sh.b_rows_h = 0; sh.b_cols_h = dh;
     sh.c_img_b = (long long)H * nq * nkv; sh.c_img_h = (long long)nq * nkv;
     sh.taps = 1; sh.kb_per_tap = dh / BLOCK_K; sh.tap_row_stride = 0;
-    LinearEpi epi{S, nkv, nkv, nullptr, 0, nullptr, ACT_NONE};
+    LinearEpi epi{S, nkv, nkv, nullptr, 0, nullptr, ACT_NONE, nullptr, 0};
     MOCHA_TRY(dispatch_bn(pick_bn(sh.tiles_m_total, nkv), tmA, K16, (unsigned long long)B * nkv,
-                          (unsigned long long)inner, sh, nkv, dh / BLOCK_K, epi, s));
+                          (unsigned long long)inner, sh, nkv, dh / BLOCK_K, epi, s, (unsigned long long)pk));
   }
   softmax_bf16_kernel<<<(unsigned)(((long long)Z * nq + 7) / 8), 256, 0, s>>>(S, (long long)Z * nq, nkv, ldp,
                                                                             1.0f / sqrtf((float)dh), P16);
@@ -946,7 +1021,7 @@ int tc_attention(const float* q, int ldq, const float* k, int ldk, const float* 
     sh.b_rows_b = (long long)H * dh; sh.b_rows_h = dh; sh.b_cols_h = 0;
     sh.c_img_b = (long long)nq * ldo; sh.c_img_h = dh;
     sh.taps = 1; sh.kb_per_tap = ceil_div(ldp, BLOCK_K); sh.tap_row_stride = 0;
-    LinearEpi epi{out, ldo, dh, nullptr, 0, nullptr, ACT_NONE};
+    LinearEpi epi{out.f32, ldo, dh, nullptr, 0, nullptr, ACT_NONE, out.bf16, out.lrelu};
     MOCHA_TRY(dispatch_bn(pick_bn(sh.tiles_m_total, dh), tmA, VT16, (unsigned long long)Z * dh,
                           (unsigned long long)ldp, sh, dh, ceil_div(ldp, BLOCK_K), epi, s));
   }

@@ -23,9 +23,18 @@ const __nv_bfloat16* tc_lookup_bf16(const float* W);
 int tc_linear(const float* A, const float* W, const float* bias, int bias_period, const float* res, float* C,
               int M, int N, int K, int act, int a_lrelu, Workspace& ws, cudaStream_t s);
 
-// Same with operands already in bf16 (A16 [M,K], W16 [N,K], both K-major, 16B-aligned rows).
-int tc_linear_bf16(const __nv_bfloat16* A16, const __nv_bfloat16* W16, const float* bias, int bias_period,
-                   const float* res, float* C, int M, int N, int K, int act, cudaStream_t s);
+// Output of a tensor-core layer: fp32 and/or a bf16 copy (the operand of the next tensor-core layer);
+// lrelu stores LeakyReLU(0.2)(x) in the bf16 copy for pre-activation consumers.
+struct TcOut {
+  float* f32;
+  __nv_bfloat16* bf16;
+  int lrelu;
+};
+// Same with operands already in bf16 (A16 [M,K] with row pitch lda, W16 [N,K], K-major, 16B-aligned rows).
+int tc_linear_bf16(const __nv_bfloat16* A16, int lda, const __nv_bfloat16* W16, const float* bias, int bias_period,
+                   const float* res, TcOut out, int M, int N, int K, int act, cudaStream_t s);
+// fp32 -> bf16 (optionally through LeakyReLU(0.2))
+int tc_cast(const float* x, __nv_bfloat16* y, long long n, int lrelu, cudaStream_t s);
 
 // Reflect-padded temporal convolution on tensor cores: X fp32 [B,T,V,Cin] -> C [B*T*V, Cout].
 // W [Cout, taps*Cin] (tap-major K). Stages a bf16 reflect-padded copy of X in ws.
@@ -33,6 +42,9 @@ bool tc_tconv_supported(int B, int T, int V, int Cin, int Cout, int taps);
 size_t tc_tconv_scratch_bytes(int B, int T, int V, int Cin, int taps);
 int tc_tconv(const float* X, const float* W, const float* bias, int bias_period, float* C, int B, int T, int V,
              int Cin, int Cout, int taps, int tdiv, Workspace& ws, cudaStream_t s, int repeat = 1);
+// X or Xh (bf16 source) may be given; output fp32 and/or bf16
+int tc_tconv_ex(const float* X, const __nv_bfloat16* Xh, const float* W, const float* bias, int bias_period, TcOut out,
+                int B, int T, int V, int Cin, int Cout, int taps, int tdiv, Workspace& ws, cudaStream_t s, int repeat = 1);
 
 // ---- attention: softmax(Q K^T / sqrt(dh)) V for B*H (batch, head) problems on tensor cores ------------
 // q/k/v are fp32 strided views [B*n, ld] with head h at columns h*dh; S is a [B,H,nq,nkv] fp32 scratch.
@@ -40,6 +52,9 @@ bool tc_attention_supported(int nq, int nkv, int dh);
 size_t tc_attention_scratch_bytes(int B, int H, int nq, int nkv, int dh);
 int tc_attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int B, int H, int nq,
                  int nkv, int dh, float* S, float* out, int ldo, Workspace& ws, cudaStream_t s);
+int tc_attention_ex(const float* q, const __nv_bfloat16* qh, int ldq, const float* k, const __nv_bfloat16* kh, int ldk,
+                    const float* v, const __nv_bfloat16* vh, int ldv, int B, int H, int nq, int nkv, int dh, float* S,
+                    TcOut out, int ldo, Workspace& ws, cudaStream_t s);
 
 // ---- matcher coarse pass ---------------------------------------------------------------------------
 constexpr int MATCH_KC_MAX = 16;

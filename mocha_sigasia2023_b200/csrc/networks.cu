@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "gemm_f32.cuh"
 #include "gemm_tc.cuh"
+#include "networks_bf16.cuh"
 #include "ops.cuh"
 
 using namespace mocha;
@@ -117,6 +118,8 @@ extern "C" int mocha_embed_fwd(const mocha_generator_weights* w, const float* X,
   MOCHA_TRY(check_dims(w->dims));
   const mocha_dims& d = w->dims;
   Workspace ws(workspace, workspace_bytes);
+  if (precision == MOCHA_BF16 && bf16_path_supported(d))
+    return embed_bf16(w, X, B, tokens, add_pos_emb, ws, (cudaStream_t)stream);
   Ctx c{(cudaStream_t)stream, precision, &ws};
   const int R = B * d.T * d.V, Tp = d.T / d.tp, R2 = B * Tp * d.P;
   float* h0 = ws.take<float>((size_t)R * d.C0);
@@ -169,6 +172,8 @@ extern "C" int mocha_encoder_fwd(const mocha_generator_weights* w, const float* 
   MOCHA_TRY(check_dims(w->dims));
   const mocha_dims& d = w->dims;
   Workspace ws(workspace, workspace_bytes);
+  if (precision == MOCHA_BF16 && bf16_path_supported(d))
+    return encoder_bf16(w, tokens, B, encoded, ws, (cudaStream_t)stream);
   Ctx c{(cudaStream_t)stream, precision, &ws};
   const int n = ntok(d), R = B * n, inner = d.heads * d.enc_dh;
   float* qkv = ws.take<float>((size_t)R * 3 * inner);
@@ -227,6 +232,8 @@ extern "C" int mocha_decoder_fwd(const mocha_generator_weights* w, const float* 
   MOCHA_TRY(check_dims(w->dims));
   const mocha_dims& d = w->dims;
   Workspace ws(workspace, workspace_bytes);
+  if (precision == MOCHA_BF16 && bf16_path_supported(d))
+    return decoder_bf16(w, src, cha, B, decoded, ws, (cudaStream_t)stream);
   Ctx c{(cudaStream_t)stream, precision, &ws};
   const int n = ntok(d), R = B * n, inner = d.heads * d.dec_dh;
   const float eps = 1e-5f;
@@ -303,6 +310,8 @@ extern "C" int mocha_to_mot_fwd(const mocha_generator_weights* w, const float* t
   MOCHA_TRY(check_dims(w->dims));
   const mocha_dims& d = w->dims;
   Workspace ws(workspace, workspace_bytes);
+  if (precision == MOCHA_BF16 && bf16_path_supported(d))
+    return to_mot_bf16(w, tokens, B, Ytil, Y_mean, Y_std, Y, ws, (cudaStream_t)stream);
   Ctx c{(cudaStream_t)stream, precision, &ws};
   const int Tp = d.T / d.tp, R2 = B * Tp * d.P, R = B * d.T * d.V;
   float* agg = ws.take<float>((size_t)R2 * d.Kb * d.D);
@@ -363,6 +372,12 @@ extern "C" int mocha_cvae_sample(const mocha_cvae_weights* w, const float* cond,
   MOCHA_CHECK_ARG(ncond + 2 <= 256, "mocha_cvae_sample: ncond=%d too long", ncond);
   MOCHA_CHECK_ARG(!out_denorm || (out_mean && out_std), "mocha_cvae_sample: denorm needs its tables");
   Workspace ws(workspace, workspace_bytes);
+  {
+    const int dh_ = w->D / w->heads;
+    if (precision == MOCHA_BF16 && w->D % 64 == 0 && w->dff % 64 == 0 && w->out_seq <= ncond + 2 &&
+        tc_attention_supported(ncond + 2, ncond + 2, dh_) && tc_attention_supported(w->out_seq, ncond + 1, dh_))
+      return cvae_bf16(w, cond, B, ncond, eps, out, mu, logvar, out_mean, out_std, out_denorm, ws, (cudaStream_t)stream);
+  }
   Ctx c{(cudaStream_t)stream, precision, &ws};
   const int D = w->D, H = w->heads, dh = D / H, np = ncond + 2, nm = ncond + 1, nq = w->out_seq;
   const int Rp = B * np, Rm = B * nm, Rq = B * nq;

@@ -1,0 +1,269 @@
+// MOCHA_BF16 (throughput) orchestration of the Generator / CVAE stages: every dense contraction runs on
+// tcgen05 and activations that only feed another tensor-core layer live in bf16 ONLY — the producing
+// epilogue (or normalisation kernel) writes the bf16 operand of its consumer directly, so there are no
+// stand-alone cast kernels and no fp32 round trips between layers. fp32 copies are kept exactly where
+// a residual add, a normalisation or a SIMT kernel reads them. Same math as networks.cu (fp32 mode).
+#include "networks_bf16.cuh"
+
+#include "gemm_f32.cuh"
+#include "gemm_tc.cuh"
+#include "ops.cuh"
+
+namespace mocha {
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+struct Tc {
+  cudaStream_t s;
+  Workspace& ws;
+  // C = act(A16 W^T + bias) (+res); out.f32 and/or out.bf16
+  int lin(const bf16* A16, int lda, const float* W, const float* bias, int period, const float* res, TcOut out, int M,
+          int N, int K, int act) const {
+    const bf16* W16 = tc_lookup_bf16(W);
+    if (!W16) return set_error(MOCHA_ERR_ARG, "bf16 path: weight %p has no registered bf16 mirror", (const void*)W);
+    return tc_linear_bf16(A16, lda, W16, bias, period, res, out, M, N, K, act, s);
+  }
+};
+
+inline TcOut f32(float* p) { return TcOut{p, nullptr, 0}; }
+inline TcOut h16(bf16* p, int lrelu = 0) { return TcOut{nullptr, p, lrelu}; }
+inline TcOut both(float* p, bf16* q) { return TcOut{p, q, 0}; }
+
+#define WS_OK(ws, name)                                                                            \
+  do {                                                                                             \
+    if ((ws).overflow)                                                                             \
+      return set_error(MOCHA_ERR_WORKSPACE, "%s: workspace too small (%zu B given, %zu B needed)", \
+                       name, (ws).cap, (ws).off);                                                  \
+  } while (0)
+
+inline int ntok(const mocha_dims& d) { return (d.T / d.tp) * d.P; }
+
+}  // namespace
+
+bool bf16_path_supported(const mocha_dims& d) {
+  const int n = ntok(d);
+  return d.C0 % 64 == 0 && d.D % 64 == 0 && d.mlp % 64 == 0 && (d.Kj * d.C0) % 64 == 0 && d.enc_dh % 64 == 0 &&
+         d.dec_dh % 64 == 0 && n <= 256 && tc_attention_supported(n, n, d.enc_dh) &&
+         tc_attention_supported(n, n, d.dec_dh);
+}
+
+// ---------------------------------------------------------------------------------------------------
+int embed_bf16(const mocha_generator_weights* w, const float* X, int B, float* tokens, int add_pos_emb, Workspace& ws,
+               cudaStream_t s) {
+  const mocha_dims& d = w->dims;
+  Tc tc{s, ws};
+  const int R = B * d.T * d.V, Tp = d.T / d.tp, R2 = B * Tp * d.P;
+  float* h0 = ws.take<float>((size_t)R * d.C0);
+  bf16* agg = ws.take<bf16>((size_t)R * d.Kj * d.C0);
+  bf16* g = ws.take<bf16>((size_t)R * d.D);
+  float* h1 = ws.take<float>((size_t)R * d.D);
+  float* pooled = ws.take<float>((size_t)R2 * d.D);
+  bf16* agg2 = ws.take<bf16>((size_t)R2 * d.Kb * d.D);
+  bf16* g2 = ws.take<bf16>((size_t)R2 * d.D);
+  WS_OK(ws, "mocha_embed_fwd(bf16)");
+  // Conv2d 1x1 Cin(15)->C0: K is too short for a TMA row; stays on the fp32 kernel
+  {
+    GemmParams p;
+    p.A = X; p.W = w->emb_w; p.C = h0;
+    p.M = R; p.N = d.C0; p.K = d.Cin; p.lda = d.Cin; p.ldw = d.Cin; p.ldc = d.C0;
+    p.bias = w->emb_b;
+    MOCHA_TRY(gemm_f32(p, s));
+  }
+  MOCHA_TRY(graph_agg_first(h0, w->A_j, nullptr, B * d.T, d.V, d.C0, d.Kj, 1, s, agg));
+  MOCHA_TRY(tc.lin(agg, d.Kj * d.C0, w->jb_gcn_w, w->jb_gcn_bias2d, d.V, nullptr, h16(g), R, d.D, d.Kj * d.C0, ACT_NONE));
+  MOCHA_TRY(tc_tconv_ex(nullptr, g, w->jb_tcn_w, w->jb_tcn_b, 0, f32(h1), B, d.T, d.V, d.D, d.D, d.taps_j, 1, ws, s));
+  MOCHA_TRY(pool_joint_body(h1, w->pool_w, pooled, B, d.T, d.V, d.P, d.D, d.tp, s));
+  MOCHA_TRY(graph_agg_first(pooled, w->A_b, nullptr, B * Tp, d.P, d.D, d.Kb, 1, s, agg2));
+  MOCHA_TRY(tc.lin(agg2, d.Kb * d.D, w->bb_gcn_w, w->bb_gcn_bias2d, d.P, nullptr, h16(g2), R2, d.D, d.Kb * d.D, ACT_NONE));
+  if (add_pos_emb)
+    return tc_tconv_ex(nullptr, g2, w->bb_tcn_w, w->tok_bias_pos, Tp * d.P, f32(tokens), B, Tp, d.P, d.D, d.D, d.taps_b, 1, ws, s);
+  return tc_tconv_ex(nullptr, g2, w->bb_tcn_w, w->bb_tcn_b, 0, f32(tokens), B, Tp, d.P, d.D, d.D, d.taps_b, 1, ws, s);
+}
+
+// ---------------------------------------------------------------------------------------------------
+int encoder_bf16(const mocha_generator_weights* w, const float* tokens, int B, float* encoded, Workspace& ws,
+                 cudaStream_t s) {
+  const mocha_dims& d = w->dims;
+  Tc tc{s, ws};
+  const int n = ntok(d), R = B * n, inner = d.heads * d.enc_dh;
+  bf16* x16 = ws.take<bf16>((size_t)R * d.D);
+  bf16* qkv = ws.take<bf16>((size_t)R * 3 * inner);
+  float* S = ws.take<float>((size_t)B * d.heads * n * n);
+  bf16* att = ws.take<bf16>((size_t)R * inner);
+  float* xa = ws.take<float>((size_t)R * d.D);
+  bf16* xa16 = ws.take<bf16>((size_t)R * d.D);
+  float* xb = ws.take<float>((size_t)R * d.D);
+  bf16* hid = ws.take<bf16>((size_t)R * d.mlp);
+  WS_OK(ws, "mocha_encoder_fwd(bf16)");
+  MOCHA_TRY(tc_cast(tokens, x16, (long long)R * d.D, 0, s));
+  const float* x = tokens;
+  for (int l = 0; l < d.enc_depth; ++l) {
+    const mocha_enc_layer& L = w->enc[l];
+    MOCHA_CHECK_ARG(L.wqkv && L.wo && L.bo && L.w1 && L.b1 && L.w2 && L.b2, "mocha_encoder_fwd: layer %d weights missing", l);
+    const bool last = l == d.enc_depth - 1;
+    MOCHA_TRY(tc.lin(x16, d.D, L.wqkv, nullptr, 0, nullptr, h16(qkv), R, 3 * inner, d.D, ACT_NONE));
+    MOCHA_TRY(tc_attention_ex(nullptr, qkv, 3 * inner, nullptr, qkv + inner, 3 * inner, nullptr, qkv + 2 * inner,
+                              3 * inner, B, d.heads, n, n, d.enc_dh, S, h16(att), inner, ws, s));
+    MOCHA_TRY(tc.lin(att, inner, L.wo, L.bo, 0, x, both(xa, xa16), R, d.D, inner, ACT_NONE));
+    MOCHA_TRY(tc.lin(xa16, d.D, L.w1, L.b1, 0, nullptr, h16(hid), R, d.mlp, d.D, ACT_GELU));
+    float* dst = last ? encoded : xb;
+    MOCHA_TRY(tc.lin(hid, d.mlp, L.w2, L.b2, 0, xa, last ? f32(dst) : both(dst, x16), R, d.D, d.mlp, ACT_NONE));
+    x = dst;
+  }
+  return MOCHA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+int decoder_bf16(const mocha_generator_weights* w, const float* src, const float* cha, int B, float* decoded,
+                 Workspace& ws, cudaStream_t s) {
+  const mocha_dims& d = w->dims;
+  Tc tc{s, ws};
+  const int n = ntok(d), R = B * n, inner = d.heads * d.dec_dh;
+  const float eps = 1e-5f;
+  float* smean = ws.take<float>((size_t)B * d.D);
+  bf16* smean16 = ws.take<bf16>((size_t)B * d.D);
+  bf16* shid = ws.take<bf16>((size_t)B * 2 * d.D);
+  float* gb = ws.take<float>((size_t)B * 2 * d.D);
+  bf16* sty_in = ws.take<bf16>((size_t)R * d.D);
+  bf16* cha16 = ws.take<bf16>((size_t)R * d.D);
+  float* x1 = ws.take<float>((size_t)R * d.D);
+  bf16* qin = ws.take<bf16>((size_t)R * d.D);
+  float* x2 = ws.take<float>((size_t)R * d.D);
+  bf16* x2h = ws.take<bf16>((size_t)R * d.D);
+  float* xb = ws.take<float>((size_t)R * d.D);
+  bf16* q = ws.take<bf16>((size_t)R * inner);
+  bf16* k = ws.take<bf16>((size_t)R * inner);
+  bf16* v = ws.take<bf16>((size_t)R * inner);
+  bf16* att = ws.take<bf16>((size_t)R * inner);
+  float* S = ws.take<float>((size_t)B * d.heads * n * n);
+  bf16* hid = ws.take<bf16>((size_t)R * d.mlp);
+  WS_OK(ws, "mocha_decoder_fwd(bf16)");
+  // layer-independent functions of the style tokens
+  MOCHA_TRY(token_mean(cha, B, n, d.D, smean, s));
+  MOCHA_TRY(tc_cast(smean, smean16, (long long)B * d.D, 0, s));
+  MOCHA_TRY(instance_norm_tokens(cha, B, n, d.D, eps, nullptr, nullptr, nullptr, nullptr, nullptr, s, sty_in));
+  MOCHA_TRY(tc_cast(cha, cha16, (long long)R * d.D, 0, s));
+  const float* x = src;
+  for (int l = 0; l < d.dec_depth; ++l) {
+    const mocha_dec_layer& L = w->dec[l];
+    MOCHA_CHECK_ARG(L.sw1 && L.sw2 && L.wq && L.wk && L.wv && L.wo && L.w1 && L.w2, "mocha_decoder_fwd: layer %d weights missing", l);
+    MOCHA_TRY(tc.lin(smean16, d.D, L.sw1, L.sb1, 0, nullptr, h16(shid), B, 2 * d.D, d.D, ACT_LRELU));
+    MOCHA_TRY(tc.lin(shid, 2 * d.D, L.sw2, L.sb2, 0, nullptr, f32(gb), B, 2 * d.D, 2 * d.D, ACT_NONE));
+    MOCHA_TRY(instance_norm_tokens(x, B, n, d.D, eps, gb, x1, nullptr, nullptr, nullptr, s));
+    MOCHA_TRY(instance_norm_tokens(x1, B, n, d.D, eps, nullptr, nullptr, nullptr, nullptr, nullptr, s, qin));
+    MOCHA_TRY(tc.lin(qin, d.D, L.wq, nullptr, 0, nullptr, h16(q), R, inner, d.D, ACT_NONE));
+    MOCHA_TRY(tc.lin(sty_in, d.D, L.wk, nullptr, 0, nullptr, h16(k), R, inner, d.D, ACT_NONE));
+    MOCHA_TRY(tc.lin(cha16, d.D, L.wv, nullptr, 0, nullptr, h16(v), R, inner, d.D, ACT_NONE));
+    MOCHA_TRY(tc_attention_ex(nullptr, q, inner, nullptr, k, inner, nullptr, v, inner, B, d.heads, n, n, d.dec_dh, S,
+                              h16(att), inner, ws, s));
+    MOCHA_TRY(tc.lin(att, inner, L.wo, L.bo, 0, x1, both(x2, x2h), R, d.D, inner, ACT_NONE));
+    MOCHA_TRY(tc.lin(x2h, d.D, L.w1, L.b1, 0, nullptr, h16(hid), R, d.mlp, d.D, ACT_GELU));
+    float* dst = (l == d.dec_depth - 1) ? decoded : xb;
+    MOCHA_TRY(tc.lin(hid, d.mlp, L.w2, L.b2, 0, x2, f32(dst), R, d.D, d.mlp, ACT_NONE));
+    x = dst;
+  }
+  return MOCHA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+int to_mot_bf16(const mocha_generator_weights* w, const float* tokens, int B, float* Ytil, const float* Y_mean,
+                const float* Y_std, float* Y, Workspace& ws, cudaStream_t s) {
+  const mocha_dims& d = w->dims;
+  Tc tc{s, ws};
+  const int Tp = d.T / d.tp, R2 = B * Tp * d.P, R = B * d.T * d.V;
+  bf16* agg = ws.take<bf16>((size_t)R2 * d.Kb * d.D);
+  bf16* y1 = ws.take<bf16>((size_t)R2 * d.D);
+  bf16* y2 = ws.take<bf16>((size_t)R2 * d.D);
+  float* y3 = ws.take<float>((size_t)R2 * d.Kj * d.C0);
+  float* gp = ws.take<float>((size_t)B * Tp * d.V * d.C0);
+  bf16* y4 = ws.take<bf16>((size_t)R * d.C0);
+  float* ytil_ws = Ytil ? nullptr : ws.take<float>((size_t)R * d.Cin);
+  WS_OK(ws, "mocha_to_mot_fwd(bf16)");
+  float* yt = Ytil ? Ytil : ytil_ws;
+  MOCHA_TRY(graph_agg_first(tokens, w->tm_A_b, nullptr, B * Tp, d.P, d.D, d.Kb, 1, s, agg));
+  MOCHA_TRY(tc.lin(agg, d.Kb * d.D, w->tm_bb_gcn_w, w->tm_bb_gcn_bias2d, d.P, nullptr, h16(y1), R2, d.D, d.Kb * d.D, ACT_NONE));
+  // the two consumers below are pre-activation blocks: their bf16 operand is stored through LeakyReLU
+  MOCHA_TRY(tc_tconv_ex(nullptr, y1, w->tm_bb_tcn_w, w->tm_bb_tcn_b, 0, h16(y2, 1), B, Tp, d.P, d.D, d.D, d.taps_b, 1, ws, s));
+  MOCHA_TRY(tc.lin(y2, d.D, w->tm_jb_gcn_w, w->tm_jb_gcn_b, 0, nullptr, f32(y3), R2, d.Kj * d.C0, d.D, ACT_NONE));
+  MOCHA_TRY(graph_agg_kv(y3, w->tm_A2, gp, B * Tp, d.P, d.V, d.C0, d.Kj, s));
+  MOCHA_TRY(tc_tconv_ex(gp, nullptr, w->tm_jb_tcn_w, w->tm_jb_tcn_b, 0, h16(y4, 1), B, d.T, d.V, d.C0, d.C0, d.taps_j, d.tp, ws, s));
+  MOCHA_TRY(tc.lin(y4, d.C0, w->tm_out_w, w->tm_out_b, 0, nullptr, f32(yt), R, d.Cin, d.C0, ACT_NONE));
+  if (Y) MOCHA_TRY(affine_rows(yt, Y_mean, Y_std, Y, R, d.Cin, d.V, s));
+  return MOCHA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+int cvae_bf16(const mocha_cvae_weights* w, const float* cond, int B, int ncond, const float* eps, float* out, float* mu,
+              float* logvar, const float* out_mean, const float* out_std, float* out_denorm, Workspace& ws,
+              cudaStream_t s) {
+  Tc tc{s, ws};
+  const int D = w->D, H = w->heads, dh = D / H, np = ncond + 2, nm = ncond + 1, nq = w->out_seq;
+  const int Rp = B * np, Rm = B * nm, Rq = B * nq;
+  float* xa = ws.take<float>((size_t)Rp * D);
+  float* xb = ws.take<float>((size_t)Rp * D);
+  bf16* xa16 = ws.take<bf16>((size_t)Rp * D);
+  bf16* xb16 = ws.take<bf16>((size_t)Rp * D);
+  bf16* qkv = ws.take<bf16>((size_t)Rp * 3 * D);
+  float* S = ws.take<float>((size_t)B * H * np * np);
+  bf16* att = ws.take<bf16>((size_t)Rp * D);
+  float* proj = ws.take<float>((size_t)Rp * D);
+  bf16* hid = ws.take<bf16>((size_t)Rp * w->dff);
+  bf16* mem = ws.take<bf16>((size_t)Rm * D);
+  bf16* memkv = ws.take<bf16>((size_t)Rm * 2 * D);
+  bf16* dq = ws.take<bf16>((size_t)Rq * D);
+  WS_OK(ws, "mocha_cvae_sample(bf16)");
+
+  // ---- prior network: x (fp32 for the residual / LayerNorm) + x16 (operand of the next GEMM) ----
+  MOCHA_TRY(cvae_prior_tokens(w->mu_token, w->logvar_token, cond, w->pe, xa, B, ncond, D, s, xa16));
+  float* x = xa; bf16* x16 = xa16;
+  float* y = xb; bf16* y16 = xb16;
+  for (int l = 0; l < w->depth; ++l) {
+    const mocha_cvae_enc_layer& L = w->prior[l];
+    MOCHA_CHECK_ARG(L.in_w && L.in_b && L.out_w && L.out_b && L.l1_w && L.l2_w && L.n1_g && L.n2_g,
+                    "mocha_cvae_sample: prior layer %d weights missing", l);
+    MOCHA_TRY(tc.lin(x16, D, L.in_w, L.in_b, 0, nullptr, h16(qkv), Rp, 3 * D, D, ACT_NONE));
+    MOCHA_TRY(tc_attention_ex(nullptr, qkv, 3 * D, nullptr, qkv + D, 3 * D, nullptr, qkv + 2 * D, 3 * D, B, H, np, np, dh,
+                              S, h16(att), D, ws, s));
+    MOCHA_TRY(tc.lin(att, D, L.out_w, L.out_b, 0, x, f32(proj), Rp, D, D, ACT_NONE));      // proj = x + SA(x)
+    MOCHA_TRY(add_layernorm(proj, nullptr, L.n1_g, L.n1_b, y, Rp, D, w->ln_eps, nullptr, nullptr, 0, nullptr, s, y16));
+    MOCHA_TRY(tc.lin(y16, D, L.l1_w, L.l1_b, 0, nullptr, h16(hid), Rp, w->dff, D, ACT_RELU));
+    MOCHA_TRY(tc.lin(hid, w->dff, L.l2_w, L.l2_b, 0, y, f32(proj), Rp, D, w->dff, ACT_NONE)); // proj = y + FF(y)
+    MOCHA_TRY(add_layernorm(proj, nullptr, L.n2_g, L.n2_b, x, Rp, D, w->ln_eps, nullptr, nullptr, 0, nullptr, s, x16));
+  }
+  MOCHA_TRY(cvae_memory(x, np, eps, cond, nullptr, mu, logvar, B, ncond, D, s, mem));
+
+  // ---- decoder (query rows reuse the prior's buffers: Rq <= Rp) ----
+  float* dx = xa; bf16* dx16 = xa16;
+  float* dy = xb; bf16* dy16 = xb16;
+  MOCHA_TRY(broadcast_rows(w->pe, dx, B, (long long)nq * D, s, dx16));
+  for (int l = 0; l < w->depth; ++l) {
+    const mocha_cvae_dec_layer& L = w->dec[l];
+    MOCHA_CHECK_ARG(L.sa_in_w && L.sa_out_w && L.ca_in_w && L.ca_out_w && L.l1_w && L.l2_w && L.n1_g && L.n2_g && L.n3_g,
+                    "mocha_cvae_sample: decoder layer %d weights missing", l);
+    MOCHA_TRY(tc.lin(dx16, D, L.sa_in_w, L.sa_in_b, 0, nullptr, h16(qkv), Rq, 3 * D, D, ACT_NONE));
+    MOCHA_TRY(tc_attention_ex(nullptr, qkv, 3 * D, nullptr, qkv + D, 3 * D, nullptr, qkv + 2 * D, 3 * D, B, H, nq, nq, dh,
+                              S, h16(att), D, ws, s));
+    MOCHA_TRY(tc.lin(att, D, L.sa_out_w, L.sa_out_b, 0, dx, f32(proj), Rq, D, D, ACT_NONE));
+    MOCHA_TRY(add_layernorm(proj, nullptr, L.n1_g, L.n1_b, dy, Rq, D, w->ln_eps, nullptr, nullptr, 0, nullptr, s, dy16));
+    MOCHA_TRY(tc.lin(dy16, D, L.ca_in_w, L.ca_in_b, 0, nullptr, h16(dq), Rq, D, D, ACT_NONE));
+    MOCHA_TRY(tc.lin(mem, D, L.ca_in_w + (size_t)D * D, L.ca_in_b + D, 0, nullptr, h16(memkv), Rm, 2 * D, D, ACT_NONE));
+    MOCHA_TRY(tc_attention_ex(nullptr, dq, D, nullptr, memkv, 2 * D, nullptr, memkv + D, 2 * D, B, H, nq, nm, dh, S,
+                              h16(att), D, ws, s));
+    MOCHA_TRY(tc.lin(att, D, L.ca_out_w, L.ca_out_b, 0, dy, f32(proj), Rq, D, D, ACT_NONE));
+    MOCHA_TRY(add_layernorm(proj, nullptr, L.n2_g, L.n2_b, dx, Rq, D, w->ln_eps, nullptr, nullptr, 0, nullptr, s, dx16));
+    MOCHA_TRY(tc.lin(dx16, D, L.l1_w, L.l1_b, 0, nullptr, h16(hid), Rq, w->dff, D, ACT_RELU));
+    MOCHA_TRY(tc.lin(hid, w->dff, L.l2_w, L.l2_b, 0, dx, f32(proj), Rq, D, w->dff, ACT_NONE));
+    if (l == w->depth - 1) {
+      MOCHA_TRY(add_layernorm(proj, nullptr, L.n3_g, L.n3_b, out, Rq, D, w->ln_eps, out_mean, out_std, nq, out_denorm, s));
+    } else {
+      MOCHA_TRY(add_layernorm(proj, nullptr, L.n3_g, L.n3_b, dy, Rq, D, w->ln_eps, nullptr, nullptr, 0, nullptr, s, dy16));
+      float* t = dx; dx = dy; dy = t;
+      bf16* t16 = dx16; dx16 = dy16; dy16 = t16;
+    }
+  }
+  return MOCHA_OK;
+}
+
+}  // namespace mocha

@@ -8,7 +8,8 @@ namespace {
 // The 'distance' adjacency is sparse (24/46/52 non-zeros of 576 per partition for the joint graph):
 // each (k, w) keeps a compact list of its non-zero sources in shared memory.
 __global__ void graph_agg_first_kernel(const float* __restrict__ in, const float* __restrict__ A,
-                                       float* __restrict__ out, int V, int C, int Kk, int lrelu) {
+                                       float* __restrict__ out, __nv_bfloat16* __restrict__ out16, int V, int C,
+                                       int Kk, int lrelu) {
   extern __shared__ float sm[];
   float* xs = sm;                                   // [V][C]
   float* val = sm + V * C;                          // [Kk*V][V] non-zero values
@@ -31,15 +32,21 @@ __global__ void graph_agg_first_kernel(const float* __restrict__ in, const float
   }
   __syncthreads();
   const int KC = Kk * C;
-  float* dst = out + (long long)bt * V * KC;
-  for (int idx = threadIdx.x; idx < V * KC; idx += blockDim.x) {
-    const int w = idx / KC, rem = idx - w * KC;
-    const int k = rem / C, c = rem - k * C;
-    const int kw = k * V + w;
-    const int n = cnt[kw];
-    float acc = 0.f;
-    for (int i = 0; i < n; ++i) acc = fmaf(xs[src[kw * V + i] * C + c], val[kw * V + i], acc);
-    dst[idx] = acc;
+  float* dst = out ? out + (long long)bt * V * KC : nullptr;
+  __nv_bfloat16* dst16 = out16 ? out16 + (long long)bt * V * KC : nullptr;
+  // thread -> channel c (fastest, coalesced stores) and a node stripe; no divisions in the loops
+  const int c = threadIdx.x % C, stripe = threadIdx.x / C, nstripes = blockDim.x / C;
+  if (stripe < nstripes) {
+    for (int w = stripe; w < V; w += nstripes) {
+      for (int k = 0; k < Kk; ++k) {
+        const int kw = k * V + w;
+        const int n = cnt[kw];
+        float acc = 0.f;
+        for (int i = 0; i < n; ++i) acc = fmaf(xs[src[kw * V + i] * C + c], val[kw * V + i], acc);
+        if (dst) dst[w * KC + k * C + c] = acc;
+        if (dst16) dst16[w * KC + k * C + c] = __float2bfloat16_rn(acc);
+      }
+    }
   }
 }
 
@@ -96,36 +103,60 @@ __global__ void pool_joint_body_kernel(const float* __restrict__ in, const float
   }
 }
 
-__global__ void instance_norm_tokens_kernel(const float* __restrict__ x, int n, int C, float eps,
-                                            const float* __restrict__ gb, float* __restrict__ y,
-                                            const float* __restrict__ tab_mean,
-                                            const float* __restrict__ tab_std, float* __restrict__ y2) {
-  const int b = blockIdx.x;
+// block = (batch b, group of 32 channels); lane = channel (coalesced 128 B rows), the 8 warps split the
+// tokens; two-pass mean / unbiased variance like torch.std, partials combined through shared memory.
+__global__ void __launch_bounds__(256)
+instance_norm_tokens_kernel(const float* __restrict__ x, int n, int C, float eps,
+                            const float* __restrict__ gb, float* __restrict__ y,
+                            const float* __restrict__ tab_mean,
+                            const float* __restrict__ tab_std, float* __restrict__ y2,
+                            __nv_bfloat16* __restrict__ y16) {
+  __shared__ float part[8][32];
+  __shared__ float stat[2][32];
+  const int b = blockIdx.x, c = blockIdx.y * 32 + (threadIdx.x & 31), warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool ok = c < C;
   const float* xb = x + (long long)b * n * C;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f;
-    for (int i = 0; i < n; ++i) s += xb[(long long)i * C + c];
-    const float mean = s / (float)n;
-    float q = 0.f;
-    for (int i = 0; i < n; ++i) {
-      const float d = xb[(long long)i * C + c] - mean;
-      q = fmaf(d, d, q);
-    }
-    const float sd = sqrtf(q / (float)(n - 1));
-    const float den = sd + eps;
-    float g = 1.f, be = 0.f;
-    if (gb) {
-      g = 1.f + gb[(long long)b * 2 * C + c];
-      be = gb[(long long)b * 2 * C + C + c];
-    }
-    for (int i = 0; i < n; ++i) {
-      const long long o = (long long)i * C + c;
-      // same operation order as the reference: divide, then modulate
-      float v = (xb[o] - mean) / den;
-      if (gb) v = g * v + be;
-      if (y) y[(long long)b * n * C + o] = v;
-      if (y2) y2[(long long)b * n * C + o] = (v - tab_mean[o]) / tab_std[o];
-    }
+  float s = 0.f;
+  if (ok) for (int i = warp; i < n; i += 8) s += xb[(long long)i * C + c];
+  part[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += part[w][lane];
+    stat[0][lane] = t / (float)n;
+  }
+  __syncthreads();
+  const float mean = stat[0][lane];
+  float q = 0.f;
+  if (ok) for (int i = warp; i < n; i += 8) {
+    const float d = xb[(long long)i * C + c] - mean;
+    q = fmaf(d, d, q);
+  }
+  part[warp][lane] = q;
+  __syncthreads();
+  if (warp == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += part[w][lane];
+    stat[1][lane] = sqrtf(t / (float)(n - 1)) + eps;
+  }
+  __syncthreads();
+  if (!ok) return;
+  const float den = stat[1][lane];
+  float g = 1.f, be = 0.f;
+  if (gb) {
+    g = 1.f + gb[(long long)b * 2 * C + c];
+    be = gb[(long long)b * 2 * C + C + c];
+  }
+  for (int i = warp; i < n; i += 8) {
+    const long long o = (long long)i * C + c;
+    // same operation order as the reference: divide, then modulate
+    float v = (xb[o] - mean) / den;
+    if (gb) v = g * v + be;
+    if (y) y[(long long)b * n * C + o] = v;
+    if (y16) y16[(long long)b * n * C + o] = __float2bfloat16_rn(v);
+    if (y2) y2[(long long)b * n * C + o] = (v - tab_mean[o]) / tab_std[o];
   }
 }
 
@@ -174,7 +205,7 @@ __global__ void add_layernorm_kernel(const float* __restrict__ x, const float* _
                                      const float* __restrict__ g, const float* __restrict__ b,
                                      float* __restrict__ y, long long rows, int C, float eps,
                                      const float* __restrict__ tab_mean, const float* __restrict__ tab_std,
-                                     int period, float* __restrict__ y2) {
+                                     int period, float* __restrict__ y2, __nv_bfloat16* __restrict__ y16) {
   const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * warps + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -192,6 +223,7 @@ __global__ void add_layernorm_kernel(const float* __restrict__ x, const float* _
   for (int c = lane; c < C; c += 32) {
     const float v = (xr[c] + (rr ? rr[c] : 0.f) - mean) * rstd * g[c] + b[c];
     if (y) y[row * C + c] = v;
+    if (y16) y16[row * C + c] = __float2bfloat16_rn(v);
     if (y2) {
       const long long o = (row % period) * C + c;
       y2[row * C + c] = v * tab_std[o] + tab_mean[o];
@@ -201,7 +233,8 @@ __global__ void add_layernorm_kernel(const float* __restrict__ x, const float* _
 
 __global__ void cvae_prior_tokens_kernel(const float* __restrict__ mu_token, const float* __restrict__ lv_token,
                                          const float* __restrict__ cond, const float* __restrict__ pe,
-                                         float* __restrict__ tok, int ncond, int C, long long total) {
+                                         float* __restrict__ tok, __nv_bfloat16* __restrict__ tok16, int ncond, int C,
+                                         long long total) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int n = ncond + 2;
@@ -212,13 +245,16 @@ __global__ void cvae_prior_tokens_kernel(const float* __restrict__ mu_token, con
   if (t == 0) v = mu_token[c];
   else if (t == 1) v = lv_token[c];
   else v = cond[(b * ncond + (t - 2)) * C + c];
-  tok[i] = v + pe[(long long)t * C + c];
+  v += pe[(long long)t * C + c];
+  tok[i] = v;
+  if (tok16) tok16[i] = __float2bfloat16_rn(v);
 }
 
 __global__ void cvae_memory_kernel(const float* __restrict__ prior_out, int prior_tokens,
                                    const float* __restrict__ eps, const float* __restrict__ cond,
-                                   float* __restrict__ mem, float* __restrict__ mu_out,
-                                   float* __restrict__ lv_out, int ncond, int C, long long total) {
+                                   float* __restrict__ mem, __nv_bfloat16* __restrict__ mem16,
+                                   float* __restrict__ mu_out, float* __restrict__ lv_out, int ncond, int C,
+                                   long long total) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int n = ncond + 1;
@@ -230,11 +266,14 @@ __global__ void cvae_memory_kernel(const float* __restrict__ prior_out, int prio
     const float lv = prior_out[(b * prior_tokens + 1) * C + c];
     float z = mu;
     if (eps) z = mu + eps[b * C + c] * expf(0.5f * lv);
-    mem[i] = z;
+    if (mem) mem[i] = z;
+    if (mem16) mem16[i] = __float2bfloat16_rn(z);
     if (mu_out) mu_out[b * C + c] = mu;
     if (lv_out) lv_out[b * C + c] = lv;
   } else {
-    mem[i] = cond[(b * ncond + (t - 1)) * C + c];
+    const float v = cond[(b * ncond + (t - 1)) * C + c];
+    if (mem) mem[i] = v;
+    if (mem16) mem16[i] = __float2bfloat16_rn(v);
   }
 }
 
@@ -260,11 +299,13 @@ __global__ void affine_rows_kernel(const float* __restrict__ x, const float* __r
   out[i] = x[i] * sd[o] + mu[o];
 }
 
-__global__ void broadcast_rows_kernel(const float* __restrict__ x, float* __restrict__ out, long long n_elems,
-                                      long long total) {
+__global__ void broadcast_rows_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                      __nv_bfloat16* __restrict__ out16, long long n_elems, long long total) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  out[i] = x[i % n_elems];
+  const float v = x[i % n_elems];
+  out[i] = v;
+  if (out16) out16[i] = __float2bfloat16_rn(v);
 }
 
 __global__ void add_table_kernel(const float* __restrict__ a, const float* __restrict__ table,
@@ -293,11 +334,12 @@ inline unsigned blocks_for(long long total, int bs) { return (unsigned)((total +
 }  // namespace
 
 int graph_agg_first(const float* in, const float* A, float* out, int BT, int V, int C, int Kk, int lrelu,
-                    cudaStream_t s) {
-  MOCHA_CHECK_ARG(in && A && out && BT > 0 && V > 0 && C > 0 && Kk > 0, "graph_agg_first: bad args");
+                    cudaStream_t s, __nv_bfloat16* out16) {
+  MOCHA_CHECK_ARG(in && A && (out || out16) && BT > 0 && V > 0 && C > 0 && Kk > 0, "graph_agg_first: bad args");
+  MOCHA_CHECK_ARG(C <= 256, "graph_agg_first: C=%d > 256 unsupported", C);
   size_t smem = (size_t)(V * C + 2 * Kk * V * V + Kk * V) * sizeof(float);
   MOCHA_CHECK_ARG(smem <= 48 * 1024, "graph_agg_first: tile too large (%zu B)", smem);
-  graph_agg_first_kernel<<<BT, 256, smem, s>>>(in, A, out, V, C, Kk, lrelu);
+  graph_agg_first_kernel<<<BT, 256, smem, s>>>(in, A, out, out16, V, C, Kk, lrelu);
   count_launch();
   MOCHA_LAUNCH_CHECK("graph_agg_first");
   return MOCHA_OK;
@@ -326,11 +368,12 @@ int pool_joint_body(const float* in, const float* Wp, float* out, int B, int T, 
 }
 
 int instance_norm_tokens(const float* x, int B, int n, int C, float eps, const float* gb, float* y,
-                         const float* tab_mean, const float* tab_std, float* y2, cudaStream_t s) {
+                         const float* tab_mean, const float* tab_std, float* y2, cudaStream_t s,
+                         __nv_bfloat16* y16) {
   MOCHA_CHECK_ARG(x && B > 0 && n > 1 && C > 0, "instance_norm_tokens: bad args");
-  MOCHA_CHECK_ARG(y || y2, "instance_norm_tokens: no output");
+  MOCHA_CHECK_ARG(y || y2 || y16, "instance_norm_tokens: no output");
   MOCHA_CHECK_ARG(!y2 || (tab_mean && tab_std), "instance_norm_tokens: y2 needs its table");
-  instance_norm_tokens_kernel<<<B, 256, 0, s>>>(x, n, C, eps, gb, y, tab_mean, tab_std, y2);
+  instance_norm_tokens_kernel<<<dim3(B, (C + 31) / 32), 256, 0, s>>>(x, n, C, eps, gb, y, tab_mean, tab_std, y2, y16);
   count_launch();
   MOCHA_LAUNCH_CHECK("instance_norm_tokens");
   return MOCHA_OK;
@@ -355,35 +398,35 @@ int softmax_rows(float* S, long long rows, int ncols, float scale, cudaStream_t 
 
 int add_layernorm(const float* x, const float* r, const float* g, const float* b, float* y, long long rows,
                   int C, float eps, const float* tab_mean, const float* tab_std, int period, float* y2,
-                  cudaStream_t s) {
+                  cudaStream_t s, __nv_bfloat16* y16) {
   MOCHA_CHECK_ARG(x && g && b && rows > 0 && C > 0, "add_layernorm: bad args");
-  MOCHA_CHECK_ARG(y || y2, "add_layernorm: no output");
+  MOCHA_CHECK_ARG(y || y2 || y16, "add_layernorm: no output");
   MOCHA_CHECK_ARG(!y2 || (tab_mean && tab_std && period > 0), "add_layernorm: y2 needs its table");
   add_layernorm_kernel<<<blocks_for(rows, 8), 256, 0, s>>>(x, r, g, b, y, rows, C, eps, tab_mean, tab_std,
-                                                          period, y2);
+                                                          period, y2, y16);
   count_launch();
   MOCHA_LAUNCH_CHECK("add_layernorm");
   return MOCHA_OK;
 }
 
 int cvae_prior_tokens(const float* mu_token, const float* logvar_token, const float* cond, const float* pe,
-                      float* tok, int B, int ncond, int C, cudaStream_t s) {
+                      float* tok, int B, int ncond, int C, cudaStream_t s, __nv_bfloat16* tok16) {
   MOCHA_CHECK_ARG(mu_token && logvar_token && cond && pe && tok && B > 0 && ncond > 0 && C > 0,
                   "cvae_prior_tokens: bad args");
   const long long total = (long long)B * (ncond + 2) * C;
-  cvae_prior_tokens_kernel<<<blocks_for(total, 256), 256, 0, s>>>(mu_token, logvar_token, cond, pe, tok, ncond,
-                                                                  C, total);
+  cvae_prior_tokens_kernel<<<blocks_for(total, 256), 256, 0, s>>>(mu_token, logvar_token, cond, pe, tok, tok16,
+                                                                  ncond, C, total);
   count_launch();
   MOCHA_LAUNCH_CHECK("cvae_prior_tokens");
   return MOCHA_OK;
 }
 
 int cvae_memory(const float* prior_out, int prior_tokens, const float* eps, const float* cond, float* mem,
-                float* mu_out, float* logvar_out, int B, int ncond, int C, cudaStream_t s) {
-  MOCHA_CHECK_ARG(prior_out && cond && mem && B > 0 && ncond > 0 && C > 0 && prior_tokens >= 2,
+                float* mu_out, float* logvar_out, int B, int ncond, int C, cudaStream_t s, __nv_bfloat16* mem16) {
+  MOCHA_CHECK_ARG(prior_out && cond && (mem || mem16) && B > 0 && ncond > 0 && C > 0 && prior_tokens >= 2,
                   "cvae_memory: bad args");
   const long long total = (long long)B * (ncond + 1) * C;
-  cvae_memory_kernel<<<blocks_for(total, 256), 256, 0, s>>>(prior_out, prior_tokens, eps, cond, mem, mu_out,
+  cvae_memory_kernel<<<blocks_for(total, 256), 256, 0, s>>>(prior_out, prior_tokens, eps, cond, mem, mem16, mu_out,
                                                             logvar_out, ncond, C, total);
   count_launch();
   MOCHA_LAUNCH_CHECK("cvae_memory");
@@ -411,10 +454,10 @@ int affine_rows(const float* x, const float* mu, const float* sd, float* out, lo
   return MOCHA_OK;
 }
 
-int broadcast_rows(const float* x, float* out, int B, long long n_elems, cudaStream_t s) {
+int broadcast_rows(const float* x, float* out, int B, long long n_elems, cudaStream_t s, __nv_bfloat16* out16) {
   MOCHA_CHECK_ARG(x && out && B > 0 && n_elems > 0, "broadcast_rows: bad args");
   const long long total = (long long)B * n_elems;
-  broadcast_rows_kernel<<<blocks_for(total, 256), 256, 0, s>>>(x, out, n_elems, total);
+  broadcast_rows_kernel<<<blocks_for(total, 256), 256, 0, s>>>(x, out, out16, n_elems, total);
   count_launch();
   MOCHA_LAUNCH_CHECK("broadcast_rows");
   return MOCHA_OK;

@@ -9,8 +9,9 @@ namespace mocha {
 // out[(bt,w), k*C + c] = sum_u f(in[(bt,u), c]) * A[k,u,w]      (f = LeakyReLU(0.2) if lrelu)
 // Reference: SpatialConv einsum 'nkctv,kvw->nctw' (net/blocks.py:64) commuted in front of the
 // 1x1 convolution, with the pre-activation of STGCN_Block.forward (net/blocks.py:125-129).
+// out and/or out16 (bf16 copy for a tensor-core consumer) may be given
 int graph_agg_first(const float* in, const float* A, float* out, int BT, int V, int C, int Kk,
-                    int lrelu, cudaStream_t s);
+                    int lrelu, cudaStream_t s, __nv_bfloat16* out16 = nullptr);
 
 // out[(bt,w), c] = sum_k sum_u in[(bt,u), k*C + c] * A2[k,u,w]   (U input nodes, Wn output nodes)
 // Same einsum applied after the 1x1 convolution (used by to_mot's JointBlock, where the
@@ -28,7 +29,8 @@ int pool_joint_body(const float* in, const float* Wp, float* out, int B, int T, 
 // y = (1+gamma)*IN(x) + beta with gb = [B, 2C] (gamma | beta) (AdaIN.forward, transformer.py:108-113)
 // and optional second output y2 = (y - tab_mean[n,c]) / tab_std[n,c] (test_fullframework.py:293,442).
 int instance_norm_tokens(const float* x, int B, int n, int C, float eps, const float* gb, float* y,
-                         const float* tab_mean, const float* tab_std, float* y2, cudaStream_t s);
+                         const float* tab_mean, const float* tab_std, float* y2, cudaStream_t s,
+                         __nv_bfloat16* y16 = nullptr);
 
 // mean over tokens: out[b,c] = mean_n x[b,n,c]  (AdaptiveAvgPool1d(1), transformer.py:102)
 int token_mean(const float* x, int B, int n, int C, float* out, cudaStream_t s);
@@ -40,14 +42,15 @@ int softmax_rows(float* S, long long rows, int ncols, float scale, cudaStream_t 
 // optional y2 = y * tab_std[row % period, c] + tab_mean[row % period, c]
 int add_layernorm(const float* x, const float* r, const float* g, const float* b, float* y, long long rows,
                   int C, float eps, const float* tab_mean, const float* tab_std, int period, float* y2,
-                  cudaStream_t s);
+                  cudaStream_t s, __nv_bfloat16* y16 = nullptr);
 
 // CVAE token assembly (model_CVAE.py:70-76, :159-164)
 int cvae_prior_tokens(const float* mu_token, const float* logvar_token, const float* cond, const float* pe,
-                      float* tok, int B, int ncond, int C, cudaStream_t s);
+                      float* tok, int B, int ncond, int C, cudaStream_t s, __nv_bfloat16* tok16 = nullptr);
 // z = mu + eps*exp(0.5*logvar) (eps may be null => z = mu); mem = [z ; cond]
 int cvae_memory(const float* prior_out, int prior_tokens, const float* eps, const float* cond, float* mem,
-                float* mu_out, float* logvar_out, int B, int ncond, int C, cudaStream_t s);
+                float* mu_out, float* logvar_out, int B, int ncond, int C, cudaStream_t s,
+                __nv_bfloat16* mem16 = nullptr);
 // cond = [ (src_cnt - m0)/s0 ; (prev - m1)/s1 ]  (test_fullframework.py:446-447)
 int cvae_condition(const float* src_cnt, const float* prev, const float* m0, const float* s0, const float* m1,
                    const float* s1, float* cond, int B, int n, int C, cudaStream_t s);
@@ -55,7 +58,8 @@ int cvae_condition(const float* src_cnt, const float* prev, const float* m0, con
 int affine_rows(const float* x, const float* mu, const float* sd, float* out, long long rows, int C, int period,
                 cudaStream_t s);
 // out[b, n, c] = x[n, c]  (broadcast a table over the batch)
-int broadcast_rows(const float* x, float* out, int B, long long n_elems, cudaStream_t s);
+int broadcast_rows(const float* x, float* out, int B, long long n_elems, cudaStream_t s,
+                   __nv_bfloat16* out16 = nullptr);
 // out = a + table[(r % period)]
 int add_table(const float* a, const float* table, float* out, long long rows, int C, int period, cudaStream_t s);
 

@@ -229,6 +229,59 @@ class CharacterizationSession:
         torch.cuda.current_stream().synchronize()
         return self._decode_out(self.h_out.numpy())
 
+    # ---------------------------------------------------------------------------------------------
+    # pipelined end-to-end streaming: the H2D copy of frame i+1 overlaps the kernels of frame i
+    # ---------------------------------------------------------------------------------------------
+    def pinned_inputs(self):
+        """A set of pinned host tensors a caller fills for one frame (shapes of step_host's arguments,
+        with src_hips_vel/src_rvel/src_rang packed as `side` [B, T*3+6])."""
+        return {"X": torch.zeros(self.X.shape, dtype=torch.float32).pin_memory(),
+                "side": torch.zeros(self.side.shape, dtype=torch.float32).pin_memory(),
+                "contacts": torch.zeros(self.contacts.shape, dtype=torch.uint8).pin_memory(),
+                "eps": torch.zeros(self.eps.shape, dtype=torch.float32).pin_memory()}
+
+    def _pipe_init(self):
+        dev = self.dev
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        self._slots = []
+        for _ in range(2):
+            self._slots.append({
+                "X": torch.empty_like(self.X), "side": torch.empty_like(self.side),
+                "contacts": torch.empty_like(self.contacts), "eps": torch.empty_like(self.eps),
+                "h_out": torch.zeros(self.post.out.shape, dtype=torch.uint8).pin_memory(),
+                "h2d": torch.cuda.Event(), "consumed": torch.cuda.Event(), "done": torch.cuda.Event(), "used": False})
+        self._ticket = 0
+
+    def submit(self, pinned: dict) -> int:
+        """Enqueue one frame from pinned host inputs (see pinned_inputs()); returns a ticket for collect().
+        The caller must not modify `pinned` until the next-but-one submit."""
+        if not hasattr(self, "_slots"):
+            self._pipe_init()
+        t = self._ticket
+        s = self._slots[t % 2]
+        main = torch.cuda.current_stream()
+        if s["used"]:
+            self._copy_stream.wait_event(s["consumed"])
+        with torch.cuda.stream(self._copy_stream):
+            for k in ("X", "side", "contacts", "eps"):
+                s[k].copy_(pinned[k], non_blocking=True)
+            s["h2d"].record(self._copy_stream)
+        main.wait_event(s["h2d"])
+        self.X.copy_(s["X"]); self.side.copy_(s["side"]); self.contacts.copy_(s["contacts"]); self.eps.copy_(s["eps"])
+        s["consumed"].record(main)
+        self.step_device()
+        s["h_out"].copy_(self.post.out, non_blocking=True)
+        s["done"].record(main)
+        s["used"] = True
+        self._ticket += 1
+        return t
+
+    def collect(self, ticket: int) -> dict:
+        """Wait for a submitted frame and return its outputs (dict of float64 numpy arrays [B, ...])."""
+        s = self._slots[ticket % 2]
+        s["done"].synchronize()
+        return self._decode_out(s["h_out"].numpy())
+
     def h2d_bytes(self):
         return self.h_X.numel() * 4 + self.h_side.numel() * 4 + self.h_contacts.numel() + self.h_eps.numel() * 4
 
