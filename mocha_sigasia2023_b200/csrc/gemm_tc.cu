@@ -559,6 +559,204 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// 2-CTA matcher kernel: a thread-block cluster of two CTAs (one TPC) computes a 256 x 256 tile with
+// tcgen05.mma.cta_group::2. Each CTA stages its own 128 query rows (A) and HALF of the DB rows (B)
+// per k-block, so the shared-memory fill and operand-read traffic per SM drop by 1/3 and 1/3 vs the
+// 1-CTA kernel; the leader CTA's single MMA thread issues for the pair, tcgen05.commit multicasts the
+// "slot free" / "accumulator ready" signals to both CTAs, and each CTA's epilogue warps drain their
+// own 128 TMEM lanes.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+// TMA load whose completion is signalled on the LEADER CTA's mbarrier (same smem offset, peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+  const uint32_t leader_bar = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+constexpr int M2_BN = 256;                               // pair tile: 256 (M) x 256 (N)
+constexpr int M2_STAGE_BYTES = A_STAGE_BYTES + 128 * BLOCK_K * 2;  // 128 A rows + 128 B rows per CTA
+constexpr int M2_STAGES = 6;
+constexpr int M2_SMEM = M2_STAGES * M2_STAGE_BYTES + 1024 + 256;
+
+template <int KC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+tc_match2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcShape sh,
+                 const int num_kb, const MatchEpi<KC> epi) {
+  constexpr int STAGES = M2_STAGES;
+  constexpr int BN = M2_BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * M2_STAGE_BYTES);   // used in the leader
+  uint64_t* empty_bar = full_bar + STAGES;                                            // per CTA
+  uint64_t* tfull_bar = empty_bar + STAGES;                                           // per CTA [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                                               // leader [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 2); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 2 * EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int u = cid; u < sh.units; u += ncl) {
+        int mt, split;
+        decode_unit(sh, u, mt, split);
+        const int a_row0 = mt * 256 + (int)rank * 128;
+        const int nt_end = min(sh.tiles_n, (split + 1) * sh.tiles_per_unit);
+        for (int nt = split * sh.tiles_per_unit; nt < nt_end; ++nt) {
+          const int b_row0 = nt * BN + (int)rank * 128;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * M2_STAGE_BYTES;
+            uint8_t* sb = sa + A_STAGE_BYTES;
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * M2_STAGE_BYTES);
+            tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * BLOCK_K, a_row0);
+            tma_load_2d_pair(sb, &tmB, &full_bar[stage], kb * BLOCK_K, b_row0);
+            if (rank != 0) mbar_arrive_remote(&full_bar[stage], 0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc(256, BN);
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      for (int u = cid; u < sh.units; u += ncl) {
+        int mt, split;
+        decode_unit(sh, u, mt, split);
+        const int nt_end = min(sh.tiles_n, (split + 1) * sh.tiles_per_unit);
+        for (int nt = split * sh.tiles_per_unit; nt < nt_end; ++nt) {
+          mbar_wait(&tempty_bar[as], aphase ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * M2_STAGE_BYTES);
+            const uint64_t adesc = make_smem_desc(sa);
+            const uint64_t bdesc = make_smem_desc(sa + A_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_bf16_pair(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            umma_commit_pair(&empty_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit_pair(&tfull_bar[as]);
+          if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9 of both CTAs) =====================
+    const int q = warp & 3;
+    int as = 0; uint32_t aphase = 0;
+    typename MatchEpi<KC>::State st;
+    EpiCtx ectx;
+    ectx.stage = 0; ectx.lane = lane; ectx.half = (warp - 2) >> 2; ectx.c_off = 0;
+    for (int u = cid; u < sh.units; u += ncl) {
+      int mt, split;
+      decode_unit(sh, u, mt, split);
+      const int r_in = mt * 256 + (int)rank * 128 + q * 32 + lane;
+      const bool row_ok = r_in < sh.rows_out_per_b;
+      const long long row = r_in;
+      ectx.slab_row0 = mt * 256 + (int)rank * 128 + q * 32;
+      ectx.slab_rows = max(0, min(32, sh.rows_out_per_b - (int)ectx.slab_row0));
+      epi.unit_begin(st);
+      const int nt_end = min(sh.tiles_n, (split + 1) * sh.tiles_per_unit);
+      for (int nt = split * sh.tiles_per_unit; nt < nt_end; ++nt) {
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+        const int c_begin = ectx.half * (BN / 2), c_end = c_begin + BN / 2;
+#pragma unroll 1
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + (uint32_t)c0, v);
+          epi.chunk(st, ectx, row, row_ok, nt * BN + c0, v);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(&tempty_bar[as], 0);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+      epi.unit_end(st, ectx, row, row_ok, split);
+    }
+  }
+
+  // the peer must stay resident until the leader's last MMA has read its shared memory
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1042,6 +1240,58 @@ int tc_match_splits(int nq, long long N) {
   return (int)splits * 2;  // x2: the two column halves of a tile keep separate lists
 }
 
+namespace {
+template <int KC>
+int launch_match2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcShape& sh, int num_kb, const MatchEpi<KC>& epi,
+                  cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    MOCHA_CUDA(cudaFuncSetAttribute(tc_match2_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, M2_SMEM));
+    configured = true;
+  }
+  int grid = 2 * sh.units;
+  const int cap = num_sms() & ~1;
+  if (grid > cap) grid = cap;
+  tc_match2_kernel<KC><<<grid, TC_THREADS, M2_SMEM, s>>>(tmA, tmB, sh, num_kb, epi);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("tc_match2_kernel");
+  return MOCHA_OK;
+}
+}  // namespace
+
+// 2-CTA (cta_group::2) variant of the coarse pass: 256 x 256 pair tiles
+int tc_match_coarse_pair(const __nv_bfloat16* Q16, int nq, const __nv_bfloat16* DB16, const float* dbnorm, long long N,
+                         int D, int kc, float* cand_score, int32_t* cand_idx, cudaStream_t s) {
+  CUtensorMap tmA, tmB;
+  MOCHA_TRY(make_tmap(&tmA, Q16, (unsigned long long)nq, (unsigned long long)D, 128));
+  MOCHA_TRY(make_tmap(&tmB, DB16, (unsigned long long)N, (unsigned long long)D, 128));
+  TcShape sh{};
+  sh.nb = 1;
+  sh.rows_out_per_b = nq;
+  sh.tiles_m_per_b = ceil_div(nq, 256);
+  sh.tiles_m_total = sh.tiles_m_per_b;
+  sh.src_rows_per_b = nq;
+  sh.taps = 1;
+  sh.kb_per_tap = ceil_div(D, BLOCK_K);
+  sh.tiles_n = (int)((N + M2_BN - 1) / M2_BN);
+  const int splits = tc_match_splits(nq, N) / 2;
+  sh.tiles_per_unit = ceil_div(sh.tiles_n, splits);
+  sh.units = sh.tiles_m_total * splits;
+  sh.splits = splits;
+  {
+    long long gm = (64LL << 20) / (256LL * D * 2);
+    if (gm < 1) gm = 1;
+    for (long long d = gm; d >= 1; --d)
+      if (sh.tiles_m_total % d == 0) { if (2 * d > gm) gm = d; break; }
+    if (const char* e = getenv("MOCHA_MATCH_GROUP_M")) gm = atoll(e);
+    sh.group_m = (int)(gm < 1 ? 1 : gm);
+  }
+  const int num_kb = ceil_div(D, BLOCK_K);
+  if (kc == 4) return launch_match2<4>(tmA, tmB, sh, num_kb, MatchEpi<4>{dbnorm, N, cand_score, cand_idx, 2 * splits}, s);
+  if (kc == 8) return launch_match2<8>(tmA, tmB, sh, num_kb, MatchEpi<8>{dbnorm, N, cand_score, cand_idx, 2 * splits}, s);
+  return launch_match2<16>(tmA, tmB, sh, num_kb, MatchEpi<16>{dbnorm, N, cand_score, cand_idx, 2 * splits}, s);
+}
+
 int tc_match_coarse(const __nv_bfloat16* Q16, int nq, const __nv_bfloat16* DB16, const float* dbnorm, long long N,
                     int D, int kc, float* cand_score, int32_t* cand_idx, cudaStream_t s) {
   MOCHA_CHECK_ARG(Q16 && DB16 && dbnorm && cand_score && cand_idx, "tc_match_coarse: null operand");
@@ -1049,6 +1299,12 @@ int tc_match_coarse(const __nv_bfloat16* Q16, int nq, const __nv_bfloat16* DB16,
   MOCHA_CHECK_ARG(D >= BLOCK_K && D % 8 == 0, "tc_match_coarse: D=%d must be >= 64 and a multiple of 8", D);
   MOCHA_CHECK_ARG(kc == 4 || kc == 8 || kc == 16, "tc_match_coarse: kc must be 4, 8 or 16");
   constexpr int BN = 256;
+  static int use_pair = -1;
+  if (use_pair < 0) {
+    const char* e = getenv("MOCHA_MATCH_2CTA");
+    use_pair = e ? atoi(e) : 0;
+  }
+  if (use_pair && nq > BLOCK_M) return tc_match_coarse_pair(Q16, nq, DB16, dbnorm, N, D, kc, cand_score, cand_idx, s);
   CUtensorMap tmA, tmB;
   MOCHA_TRY(make_tmap(&tmA, Q16, (unsigned long long)nq, (unsigned long long)D, BLOCK_M));
   MOCHA_TRY(make_tmap(&tmB, DB16, (unsigned long long)N, (unsigned long long)D, BN));
