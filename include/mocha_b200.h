@@ -148,6 +148,10 @@ typedef struct {
   const float* pe;                                   /* sinusoidal table [>=ncond+2, D] (model_CVAE.py:168-186) */
   mocha_cvae_enc_layer prior[MOCHA_MAX_DEPTH];
   mocha_cvae_dec_layer dec[MOCHA_MAX_DEPTH];
+  /* Optional [out_seq, D] table = norm1(pe + self_attn(pe)) of decoder layer 0. The decoder's query is
+   * the constant positional table (model_CVAE.py:161-162), so this block is input-independent; fill it
+   * once with mocha_cvae_precompute_dec0(). NULL = recompute it on every call. */
+  const float* dec0_sa;
 } mocha_cvae_weights;
 
 /* ---- (a1) Generator.mot_embedding  model.py:42-50, call site test_fullframework.py:190 ------ */
@@ -199,6 +203,9 @@ int mocha_cvae_sample(const mocha_cvae_weights* w, const float* d_cond, int B, i
                       const float* d_eps, float* d_out, float* d_mu, float* d_logvar,
                       const float* d_out_mean, const float* d_out_std, float* d_out_denorm,
                       int precision, void* workspace, size_t workspace_bytes, mocha_stream_t stream);
+/* Fills d_table [out_seq, D] for mocha_cvae_weights.dec0_sa (fp32 arithmetic). */
+int mocha_cvae_precompute_dec0(const mocha_cvae_weights* w, float* d_table, void* workspace, size_t workspace_bytes,
+                               mocha_stream_t stream);
 /* condition = cat[(src_cnt-m0)/s0, (prev-m1)/s1] (test_fullframework.py:446-447); tables [n,D] */
 int mocha_cvae_condition(const float* d_src_cnt, const float* d_prev, const float* d_m0, const float* d_s0,
                          const float* d_m1, const float* d_s1, float* d_cond, int B, int n, int D,

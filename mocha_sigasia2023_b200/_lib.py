@@ -67,6 +67,7 @@ class CvaeWeights(C.Structure):
         ("ln_eps", C.c_float),
         ("mu_token", C.c_void_p), ("logvar_token", C.c_void_p), ("pe", C.c_void_p),
         ("prior", CvaeEncLayer * MAX_DEPTH), ("dec", CvaeDecLayer * MAX_DEPTH),
+        ("dec0_sa", C.c_void_p),
     ]
 
 
@@ -125,6 +126,7 @@ SIGNATURES = {
     "mocha_to_mot_fwd": (_I, [C.POINTER(GeneratorWeights), _P, _I, _P, _P, _P, _P, _I, _P, _S, _P]),
     "mocha_cvae_workspace_bytes": (_S, [C.POINTER(CvaeWeights), _I, _I]),
     "mocha_cvae_sample": (_I, [C.POINTER(CvaeWeights), _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _S, _P]),
+    "mocha_cvae_precompute_dec0": (_I, [C.POINTER(CvaeWeights), _P, _P, _S, _P]),
     "mocha_cvae_condition": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "mocha_match_exact_workspace_bytes": (_S, [_I, _L, _I]),
     "mocha_match_exact": (_I, [_P, _I, _P, _L, _I, _I, _L, _P, _P, _P, _S, _P]),

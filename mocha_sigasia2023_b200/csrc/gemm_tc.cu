@@ -76,6 +76,17 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 eviction-priority policies for TMA loads (createpolicy encodings)
+constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
@@ -232,6 +243,7 @@ struct LinearEpi {
   int c16_lrelu;        // store LeakyReLU(0.2)(x) in the bf16 copy (pre-activation consumers)
   struct State {};
   static constexpr int kStageBytes = EPI_WARPS * 32 * EPI_LD * 4;  // per-warp transposition buffers
+  static constexpr uint64_t kHintA = 0, kHintB = 0;                // default L2 policy
   __device__ __forceinline__ void unit_begin(State&) const {}
 
   // Second half of the transposed epilogue, specialised on the activation so the inner loop has no
@@ -344,6 +356,8 @@ struct MatchEpi {
   int32_t* cand_idx;
   int lists;  // candidate lists per query = 2 * splits (one per column half)
   static constexpr int kStageBytes = 0;
+  // query tiles are re-read for every DB tile: keep them in L2; DB rows stream through once per group
+  static constexpr uint64_t kHintA = L2_EVICT_LAST, kHintB = L2_EVICT_FIRST;
   struct State {
     float s[KC];
     int32_t i[KC];
@@ -460,9 +474,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint8_t* sb = sa + A_STAGE_BYTES;
             mbar_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
             const int tap = kb / sh.kb_per_tap, kc = kb - tap * sh.kb_per_tap;
-            tma_load_2d(sa, &tmA, &full_bar[stage], a_col0 + kc * BLOCK_K,
-                        (int)(a_row0 + (long long)tap * sh.tap_row_stride));
-            tma_load_2d(sb, &tmB, &full_bar[stage], b_col0 + kb * BLOCK_K, (int)(b_row0 + (long long)nt * BN));
+            if (Epi::kHintA != 0) {
+              tma_load_2d_hint(sa, &tmA, &full_bar[stage], a_col0 + kc * BLOCK_K,
+                               (int)(a_row0 + (long long)tap * sh.tap_row_stride), Epi::kHintA);
+              tma_load_2d_hint(sb, &tmB, &full_bar[stage], b_col0 + kb * BLOCK_K, (int)(b_row0 + (long long)nt * BN),
+                               Epi::kHintB);
+            } else {
+              tma_load_2d(sa, &tmA, &full_bar[stage], a_col0 + kc * BLOCK_K,
+                          (int)(a_row0 + (long long)tap * sh.tap_row_stride));
+              tma_load_2d(sb, &tmB, &full_bar[stage], b_col0 + kb * BLOCK_K, (int)(b_row0 + (long long)nt * BN));
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -586,11 +607,12 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
       : "memory");
 }
 // TMA load whose completion is signalled on the LEADER CTA's mbarrier (same smem offset, peer bit cleared)
-__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1,
+                                                 uint64_t policy) {
   const uint32_t leader_bar = smem_u32(bar) & 0xFEFFFFFFu;
   asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(leader_bar), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(leader_bar), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
@@ -670,8 +692,8 @@ tc_match2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint8_t* sa = smem + stage * M2_STAGE_BYTES;
             uint8_t* sb = sa + A_STAGE_BYTES;
             if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * M2_STAGE_BYTES);
-            tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * BLOCK_K, a_row0);
-            tma_load_2d_pair(sb, &tmB, &full_bar[stage], kb * BLOCK_K, b_row0);
+            tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * BLOCK_K, a_row0, L2_EVICT_LAST);
+            tma_load_2d_pair(sb, &tmB, &full_bar[stage], kb * BLOCK_K, b_row0, L2_EVICT_FIRST);
             if (rank != 0) mbar_arrive_remote(&full_bar[stage], 0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }

@@ -354,15 +354,19 @@ __device__ void ik_two_bone_dev(D3 bone_root, D3 bone_mid, D3 bone_end, D3 targe
 }
 
 // ------------------------------------------------------------------------------------------------
-// per-frame post-process, one thread per clip
+// per-frame post-process, one WARP per clip: lanes split the 60-frame speed-ratio reduction, the 24
+// joints of the pose assembly, the 25 bones of the blending and the two feet of the contact / IK step;
+// lane 0 integrates the roots. Phases exchange data through the clip's output struct (__syncwarp).
 // ------------------------------------------------------------------------------------------------
-__global__ void post_frame_kernel(const mocha_post_params P, const float* __restrict__ Y,
-                                  const float* __restrict__ src_hips_vel, const float* __restrict__ src_rvel,
-                                  const float* __restrict__ src_rang, const uint8_t* __restrict__ contacts, int B,
-                                  int T, int V, int Cin, int init, mocha_clip_state* __restrict__ states,
-                                  mocha_frame_out* __restrict__ outs) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
+__global__ void __launch_bounds__(128)
+post_frame_kernel(const mocha_post_params P, const float* __restrict__ Y,
+                  const float* __restrict__ src_hips_vel, const float* __restrict__ src_rvel,
+                  const float* __restrict__ src_rang, const uint8_t* __restrict__ contacts, int B,
+                  int T, int V, int Cin, int init, mocha_clip_state* __restrict__ states,
+                  mocha_frame_out* __restrict__ outs) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;  // warp-uniform
   mocha_clip_state& S = states[b];
   mocha_frame_out& O = outs[b];
   const int J = P.J;
@@ -372,28 +376,33 @@ __global__ void post_frame_kernel(const mocha_post_params P, const float* __rest
 
   // speed ratio (test_fullframework.py:492-496): mean |hips vel| over the window, fp32 like NumPy
   float num = 0.f, den = 0.f;
-  for (int t = 0; t < T; ++t) {
+  for (int t = lane; t < T; t += 32) {
     const float* yv = Yb + ((long long)t * V + 0) * Cin + 9;
     num += sqrtf(yv[0] * yv[0] + yv[1] * yv[1] + yv[2] * yv[2]);
     const float* sv = src_hips_vel + ((long long)b * T + t) * 3;
     den += sqrtf(sv[0] * sv[0] + sv[1] * sv[1] + sv[2] * sv[2]);
   }
+  num = warp_sum(num);
+  den = warp_sum(den);
   float ratio = (num / (float)T) / (den / (float)T);
   if (ratio > 3.0f || ratio < 0.33f) ratio = 1.0f;
-  const D3 yrvel = v3<double>((double)(src_rvel[b * 3 + 0] * ratio), (double)(src_rvel[b * 3 + 1] * ratio),
-                              (double)(src_rvel[b * 3 + 2] * ratio));
-  const D3 yrang = v3<double>((double)src_rang[b * 3 + 0], (double)src_rang[b * 3 + 1], (double)src_rang[b * 3 + 2]);
 
-  // root integration (:500-503 / :345-348)
-  const DQ prev_rot = init ? q4<double>(1.0, 0.0, 0.0, 0.0) : ld4(S.root_rot);
-  const D3 prev_pos = init ? v3<double>(0.0, 0.0, 0.0) : ld3(S.root_pos);
-  const D3 rootvel = qrot(prev_rot, yrvel);
-  const D3 rootang = qrot(prev_rot, yrang);
-  const D3 rootpos = prev_pos + dt * rootvel;
-  const DQ rootrot = qmul(prev_rot, q_from_scaled_angle_axis(dt * rootang));
-
-  // source root (:476-483): the reference keeps it in float32 arrays, so it integrates in fp32
-  {
+  DQ rootrot = q4<double>(1.0, 0.0, 0.0, 0.0);
+  D3 rootpos = v3<double>(0.0, 0.0, 0.0);
+  if (lane == 0) {
+    const D3 yrvel = v3<double>((double)(src_rvel[b * 3 + 0] * ratio), (double)(src_rvel[b * 3 + 1] * ratio),
+                                (double)(src_rvel[b * 3 + 2] * ratio));
+    const D3 yrang = v3<double>((double)src_rang[b * 3 + 0], (double)src_rang[b * 3 + 1], (double)src_rang[b * 3 + 2]);
+    // root integration (:500-503 / :345-348)
+    const DQ prev_rot = init ? q4<double>(1.0, 0.0, 0.0, 0.0) : ld4(S.root_rot);
+    const D3 prev_pos = init ? v3<double>(0.0, 0.0, 0.0) : ld3(S.root_pos);
+    const D3 rootvel = qrot(prev_rot, yrvel);
+    const D3 rootang = qrot(prev_rot, yrang);
+    rootpos = prev_pos + dt * rootvel;
+    rootrot = qmul(prev_rot, q_from_scaled_angle_axis(dt * rootang));
+    st3(O.pos[0], rootpos); st3(O.vel[0], rootvel); st4(O.rot[0], rootrot); st3(O.ang[0], rootang);
+  } else if (lane == 1) {
+    // source root (:476-483): the reference keeps it in float32 arrays, so it integrates in fp32
     const V3<float> rv = v3<float>(src_rvel[b * 3 + 0], src_rvel[b * 3 + 1], src_rvel[b * 3 + 2]);
     const V3<float> ra = v3<float>(src_rang[b * 3 + 0], src_rang[b * 3 + 1], src_rang[b * 3 + 2]);
     if (init) {
@@ -420,9 +429,8 @@ __global__ void post_frame_kernel(const mocha_post_params P, const float* __rest
     for (int c = 0; c < 4; ++c) S.src_root_rot[c] = O.src_root_rot[c];
   }
 
-  // assemble the 25-bone pose (:505-508): joint values are fp32 results promoted to fp64
-  st3(O.pos[0], rootpos); st3(O.vel[0], rootvel); st4(O.rot[0], rootrot); st3(O.ang[0], rootang);
-  for (int j = 0; j < V; ++j) {
+  // assemble the 25-bone pose (:505-508): joint values are fp32 results promoted to fp64; lane = joint
+  for (int j = lane; j < V; j += 32) {
     const float* y = last + (long long)j * Cin;
     O.pos[j + 1][0] = (double)y[0]; O.pos[j + 1][1] = (double)y[1]; O.pos[j + 1][2] = (double)y[2];
     const Q4<float> q = q_from_xy(v3<float>(y[3], y[5], y[7]), v3<float>(y[4], y[6], y[8]));
@@ -430,17 +438,19 @@ __global__ void post_frame_kernel(const mocha_post_params P, const float* __rest
     O.vel[j + 1][0] = (double)y[9]; O.vel[j + 1][1] = (double)y[10]; O.vel[j + 1][2] = (double)y[11];
     O.ang[j + 1][0] = (double)y[12]; O.ang[j + 1][1] = (double)y[13]; O.ang[j + 1][2] = (double)y[14];
   }
+  __syncwarp();
 
   if (init) {
     // frame 0 (:375-434): lists start from the raw pose; contacts reset from the toe's FK state
-    for (int j = 0; j < J; ++j)
+    for (int j = lane; j < J; j += 32) {
       for (int c = 0; c < 3; ++c) {
         O.blend_pos[j][c] = O.pos[j][c]; O.ik_pos[j][c] = O.pos[j][c];
         S.prev_pos[j][c] = O.pos[j][c]; S.prev_ik_pos[j][c] = O.pos[j][c];
       }
-    for (int j = 0; j < J; ++j)
       for (int c = 0; c < 4; ++c) O.ik_rot[j][c] = O.rot[j][c];
-    for (int f = 0; f < 2; ++f) {
+    }
+    if (lane < 2) {
+      const int f = lane;
       // quat.fk_vel_bone (motion/quat.py:207-237) along the ancestor chain of the toe
       int chain[MAXJ]; int n = 0;
       for (int j = P.contact_bones[f]; j >= 0; j = P.parents[j]) chain[n++] = j;
@@ -459,63 +469,64 @@ __global__ void post_frame_kernel(const mocha_post_params P, const float* __rest
       st3(S.contact_point[f], gp); st3(S.contact_target[f], gp);
       st3(S.contact_offset_position[f], v3<double>(0, 0, 0)); st3(S.contact_offset_velocity[f], v3<double>(0, 0, 0));
     }
-    st3(S.root_pos, rootpos); st4(S.root_rot, rootrot);
+    if (lane == 0) { st3(S.root_pos, rootpos); st4(S.root_rot, rootrot); }
     return;
   }
 
-  // position blending (:532-536, :626)
-  for (int j = 0; j < J; ++j)
+  // position blending (:532-536, :626); lane = bone
+  for (int j = lane; j < J; j += 32) {
     for (int c = 0; c < 3; ++c) {
       O.ik_pos[j][c] = (S.prev_ik_pos[j][c] + O.vel[j][c] * dt) * 0.5 + O.pos[j][c] * 0.5;
       O.blend_pos[j][c] = (S.prev_pos[j][c] + O.vel[j][c] * dt) * 0.5 + O.pos[j][c] * 0.5;
     }
-  for (int j = 0; j < J; ++j)
     for (int c = 0; c < 4; ++c) O.ik_rot[j][c] = O.rot[j][c];
-
-  if (P.ik_enabled) {
-    for (int f = 0; f < 2; ++f) {
-      const int toe = P.contact_bones[f], heel = P.parents[toe], knee = P.parents[heel], hip = P.parents[knee],
-                rootb = P.parents[hip];
-      // quat.fk_partial (motion/quat.py:241-272) along the toe's ancestor chain, on the blended pose
-      int chain[MAXJ]; int n = 0;
-      for (int j = toe; j >= 0; j = P.parents[j]) chain[n++] = j;
-      D3 gpos[MAXJ]; DQ grot[MAXJ];
-      {
-        const int r = chain[n - 1];
-        gpos[r] = ld3(O.ik_pos[r]); grot[r] = ld4(O.rot[r]);
-        for (int k = n - 2; k >= 0; --k) {
-          const int j = chain[k], p = chain[k + 1];
-          gpos[j] = qrot(grot[p], ld3(O.ik_pos[j])) + gpos[p];
-          grot[j] = qmul(grot[p], ld4(O.rot[j]));
-        }
-      }
-      ContactState c;
-      c.state = S.contact_state[f] != 0; c.lock = S.contact_lock[f] != 0;
-      c.position = ld3(S.contact_position[f]); c.velocity = ld3(S.contact_velocity[f]);
-      c.point = ld3(S.contact_point[f]); c.target = ld3(S.contact_target[f]);
-      c.off_pos = ld3(S.contact_offset_position[f]); c.off_vel = ld3(S.contact_offset_velocity[f]);
-      contact_update_dev(c, gpos[toe], contacts[b * 2 + f] != 0, P.ik_unlock_radius, P.ik_foot_height,
-                         P.ik_blending_halflife, dt);
-      // the clamp aliases contact_positions[bs] in the reference (:581-582): it persists
-      c.position.y = fmax(c.position.y, P.ik_foot_height);
-      S.contact_state[f] = c.state; S.contact_lock[f] = c.lock;
-      st3(S.contact_position[f], c.position); st3(S.contact_velocity[f], c.velocity);
-      st3(S.contact_point[f], c.point); st3(S.contact_target[f], c.target);
-      st3(S.contact_offset_position[f], c.off_pos); st3(S.contact_offset_velocity[f], c.off_vel);
-
-      const D3 target = c.position + (gpos[heel] - gpos[toe]);
-      const D3 fwd = qrot(grot[knee], v3<double>(0.0, 1.0, 0.0));
-      DQ new_hip, new_knee;
-      ik_two_bone_dev(gpos[hip], gpos[knee], gpos[heel], target, fwd, grot[hip], grot[knee], grot[rootb],
-                      P.ik_max_length_buffer, new_hip, new_knee);
-      st4(O.ik_rot[hip], new_hip);
-      st4(O.ik_rot[knee], new_knee);
-    }
   }
+  __syncwarp();
+
+  if (P.ik_enabled && lane < 2) {
+    const int f = lane;  // the two feet touch disjoint bones and disjoint state slots
+    const int toe = P.contact_bones[f], heel = P.parents[toe], knee = P.parents[heel], hip = P.parents[knee],
+              rootb = P.parents[hip];
+    // quat.fk_partial (motion/quat.py:241-272) along the toe's ancestor chain, on the blended pose
+    int chain[MAXJ]; int n = 0;
+    for (int j = toe; j >= 0; j = P.parents[j]) chain[n++] = j;
+    D3 gpos[MAXJ]; DQ grot[MAXJ];
+    {
+      const int r = chain[n - 1];
+      gpos[r] = ld3(O.ik_pos[r]); grot[r] = ld4(O.rot[r]);
+      for (int k = n - 2; k >= 0; --k) {
+        const int j = chain[k], p = chain[k + 1];
+        gpos[j] = qrot(grot[p], ld3(O.ik_pos[j])) + gpos[p];
+        grot[j] = qmul(grot[p], ld4(O.rot[j]));
+      }
+    }
+    ContactState c;
+    c.state = S.contact_state[f] != 0; c.lock = S.contact_lock[f] != 0;
+    c.position = ld3(S.contact_position[f]); c.velocity = ld3(S.contact_velocity[f]);
+    c.point = ld3(S.contact_point[f]); c.target = ld3(S.contact_target[f]);
+    c.off_pos = ld3(S.contact_offset_position[f]); c.off_vel = ld3(S.contact_offset_velocity[f]);
+    contact_update_dev(c, gpos[toe], contacts[b * 2 + f] != 0, P.ik_unlock_radius, P.ik_foot_height,
+                       P.ik_blending_halflife, dt);
+    // the clamp aliases contact_positions[bs] in the reference (:581-582): it persists
+    c.position.y = fmax(c.position.y, P.ik_foot_height);
+    S.contact_state[f] = c.state; S.contact_lock[f] = c.lock;
+    st3(S.contact_position[f], c.position); st3(S.contact_velocity[f], c.velocity);
+    st3(S.contact_point[f], c.point); st3(S.contact_target[f], c.target);
+    st3(S.contact_offset_position[f], c.off_pos); st3(S.contact_offset_velocity[f], c.off_vel);
+
+    const D3 target = c.position + (gpos[heel] - gpos[toe]);
+    const D3 fwd = qrot(grot[knee], v3<double>(0.0, 1.0, 0.0));
+    DQ new_hip, new_knee;
+    ik_two_bone_dev(gpos[hip], gpos[knee], gpos[heel], target, fwd, grot[hip], grot[knee], grot[rootb],
+                    P.ik_max_length_buffer, new_hip, new_knee);
+    st4(O.ik_rot[hip], new_hip);
+    st4(O.ik_rot[knee], new_knee);
+  }
+  __syncwarp();
 
   // carry state
-  st3(S.root_pos, ld3(O.blend_pos[0])); st4(S.root_rot, rootrot);
-  for (int j = 0; j < J; ++j)
+  if (lane == 0) { st3(S.root_pos, ld3(O.blend_pos[0])); st4(S.root_rot, rootrot); }
+  for (int j = lane; j < J; j += 32)
     for (int c = 0; c < 3; ++c) { S.prev_pos[j][c] = O.blend_pos[j][c]; S.prev_ik_pos[j][c] = O.ik_pos[j][c]; }
 }
 
@@ -701,7 +712,7 @@ extern "C" int mocha_post_frame(const mocha_post_params* params, const float* Y,
     MOCHA_CHECK_ARG(params->contact_bones[f] > 0 && params->contact_bones[f] < params->J && depth >= 4,
                     "mocha_post_frame: contact bone %d needs 4 ancestors", params->contact_bones[f]);
   }
-  post_frame_kernel<<<nblk(B, 64), 64, 0, (cudaStream_t)stream>>>(*params, Y, src_hips_vel, src_rvel, src_rang,
+  post_frame_kernel<<<nblk((long long)B * 32, 128), 128, 0, (cudaStream_t)stream>>>(*params, Y, src_hips_vel, src_rvel, src_rang,
                                                                  contacts, B, T, V, Cin, init, state, out);
   count_launch();
   MOCHA_LAUNCH_CHECK("post_frame_kernel");

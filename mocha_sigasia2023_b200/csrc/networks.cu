@@ -419,18 +419,22 @@ extern "C" int mocha_cvae_sample(const mocha_cvae_weights* w, const float* cond,
   MOCHA_TRY(cvae_memory(x, np, eps, cond, mem, mu, logvar, B, ncond, D, c.s));
 
   // ---- decoder ----
-  MOCHA_TRY(broadcast_rows(w->pe, da, B, (long long)nq * D, c.s));  // tgt = zeros + pe[:out_seq]
+  if (!w->dec0_sa) MOCHA_TRY(broadcast_rows(w->pe, da, B, (long long)nq * D, c.s));  // tgt = zeros + pe[:out_seq]
   float* dx = da;
   float* dy = db;
   for (int l = 0; l < w->depth; ++l) {
     const mocha_cvae_dec_layer& L = w->dec[l];
     MOCHA_CHECK_ARG(L.sa_in_w && L.sa_out_w && L.ca_in_w && L.ca_out_w && L.l1_w && L.l2_w && L.n1_g && L.n2_g && L.n3_g,
                     "mocha_cvae_sample: decoder layer %d weights missing", l);
-    // self-attention block
-    MOCHA_TRY(dense(c, dx, D, L.sa_in_w, L.sa_in_b, 0, nullptr, qkv, Rq, 3 * D, D, ACT_NONE));
-    MOCHA_TRY(attention(c, qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, B, H, nq, nq, dh, S, att, D));
-    MOCHA_TRY(dense(c, att, D, L.sa_out_w, L.sa_out_b, 0, nullptr, proj, Rq, D, D, ACT_NONE));
-    MOCHA_TRY(add_layernorm(dx, proj, L.n1_g, L.n1_b, dy, Rq, D, w->ln_eps, nullptr, nullptr, 0, nullptr, c.s));
+    // self-attention block (layer 0 acts on the constant query: use the cached table when provided)
+    if (l == 0 && w->dec0_sa) {
+      MOCHA_TRY(broadcast_rows(w->dec0_sa, dy, B, (long long)nq * D, c.s));
+    } else {
+      MOCHA_TRY(dense(c, dx, D, L.sa_in_w, L.sa_in_b, 0, nullptr, qkv, Rq, 3 * D, D, ACT_NONE));
+      MOCHA_TRY(attention(c, qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, B, H, nq, nq, dh, S, att, D));
+      MOCHA_TRY(dense(c, att, D, L.sa_out_w, L.sa_out_b, 0, nullptr, proj, Rq, D, D, ACT_NONE));
+      MOCHA_TRY(add_layernorm(dx, proj, L.n1_g, L.n1_b, dy, Rq, D, w->ln_eps, nullptr, nullptr, 0, nullptr, c.s));
+    }
     // cross-attention over the memory
     MOCHA_TRY(dense(c, dy, D, L.ca_in_w, L.ca_in_b, 0, nullptr, dq, Rq, D, D, ACT_NONE));
     MOCHA_TRY(dense(c, mem, D, L.ca_in_w + (size_t)D * D, L.ca_in_b + D, 0, nullptr, memkv, Rm, 2 * D, D, ACT_NONE));
@@ -448,6 +452,27 @@ extern "C" int mocha_cvae_sample(const mocha_cvae_weights* w, const float* cond,
     }
   }
   return MOCHA_OK;
+}
+
+extern "C" int mocha_cvae_precompute_dec0(const mocha_cvae_weights* w, float* table, void* workspace,
+                                          size_t workspace_bytes, mocha_stream_t stream) {
+  MOCHA_CHECK_ARG(w && table, "mocha_cvae_precompute_dec0: null argument");
+  MOCHA_CHECK_ARG(w->D > 0 && w->heads > 0 && w->D % w->heads == 0 && w->out_seq > 0 && w->depth >= 1,
+                  "mocha_cvae_precompute_dec0: bad geometry");
+  Workspace ws(workspace, workspace_bytes);
+  Ctx c{(cudaStream_t)stream, MOCHA_FP32, &ws};
+  const int D = w->D, H = w->heads, dh = D / H, nq = w->out_seq;
+  float* qkv = ws.take<float>((size_t)nq * 3 * D);
+  float* S = ws.take<float>((size_t)H * nq * nq);
+  float* att = ws.take<float>((size_t)nq * D);
+  float* proj = ws.take<float>((size_t)nq * D);
+  WS_GUARD(ws, "mocha_cvae_precompute_dec0");
+  const mocha_cvae_dec_layer& L = w->dec[0];
+  MOCHA_CHECK_ARG(L.sa_in_w && L.sa_in_b && L.sa_out_w && L.sa_out_b && L.n1_g && L.n1_b, "mocha_cvae_precompute_dec0: weights missing");
+  MOCHA_TRY(dense(c, w->pe, D, L.sa_in_w, L.sa_in_b, 0, nullptr, qkv, nq, 3 * D, D, ACT_NONE));
+  MOCHA_TRY(attention(c, qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, 1, H, nq, nq, dh, S, att, D));
+  MOCHA_TRY(dense(c, att, D, L.sa_out_w, L.sa_out_b, 0, nullptr, proj, nq, D, D, ACT_NONE));
+  return add_layernorm(w->pe, proj, L.n1_g, L.n1_b, table, nq, D, w->ln_eps, nullptr, nullptr, 0, nullptr, c.s);
 }
 
 extern "C" int mocha_cvae_condition(const float* src_cnt, const float* prev, const float* m0, const float* s0,

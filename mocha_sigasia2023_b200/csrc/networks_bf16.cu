@@ -219,10 +219,37 @@ int cvae_bf16(const mocha_cvae_weights* w, const float* cond, int B, int ncond, 
   MOCHA_TRY(cvae_prior_tokens(w->mu_token, w->logvar_token, cond, w->pe, xa, B, ncond, D, s, xa16));
   float* x = xa; bf16* x16 = xa16;
   float* y = xb; bf16* y16 = xb16;
+  int prior_rows = np;  // rows per batch element in the prior's output tensor
   for (int l = 0; l < w->depth; ++l) {
     const mocha_cvae_enc_layer& L = w->prior[l];
     MOCHA_CHECK_ARG(L.in_w && L.in_b && L.out_w && L.out_b && L.l1_w && L.l2_w && L.n1_g && L.n2_g,
                     "mocha_cvae_sample: prior layer %d weights missing", l);
+    if (l == w->depth - 1) {
+      // Only the mu / logvar rows (tokens 0 and 1) of the last layer are ever read (model_CVAE.py:78):
+      // keys / values still span all tokens, but queries, out-proj, LayerNorms and the FFN run on 2 rows.
+      const int R2 = 2 * B;
+      float* xq = y;          // [2B, D] gathered rows of x (residual)
+      bf16* xq16 = y16;
+      MOCHA_TRY(gather_token_rows(x, x16, np, 2, D, B, xq, xq16, s));
+      bf16* kv = qkv;         // [Rp, 2D]
+      bf16* q2 = att;         // [2B, D]
+      bf16* att2 = hid;       // [2B, D]
+      MOCHA_TRY(tc.lin(x16, D, L.in_w + (size_t)D * D, L.in_b + D, 0, nullptr, h16(kv), Rp, 2 * D, D, ACT_NONE));
+      MOCHA_TRY(tc.lin(xq16, D, L.in_w, L.in_b, 0, nullptr, h16(q2), R2, D, D, ACT_NONE));
+      MOCHA_TRY(tc_attention_ex(nullptr, q2, D, nullptr, kv, 2 * D, nullptr, kv + D, 2 * D, B, H, 2, np, dh, S, h16(att2), D,
+                                ws, s));
+      MOCHA_TRY(tc.lin(att2, D, L.out_w, L.out_b, 0, xq, f32(proj), R2, D, D, ACT_NONE));
+      float* y2 = proj + (size_t)R2 * D;       // proj has Rp*D floats: plenty of room for the 2-row tensors
+      bf16* y2h = q2;
+      MOCHA_TRY(add_layernorm(proj, nullptr, L.n1_g, L.n1_b, y2, R2, D, w->ln_eps, nullptr, nullptr, 0, nullptr, s, y2h));
+      bf16* hid2 = att2 + (size_t)R2 * D;
+      MOCHA_TRY(tc.lin(y2h, D, L.l1_w, L.l1_b, 0, nullptr, h16(hid2), R2, w->dff, D, ACT_RELU));
+      MOCHA_TRY(tc.lin(hid2, w->dff, L.l2_w, L.l2_b, 0, y2, f32(proj), R2, D, w->dff, ACT_NONE));
+      MOCHA_TRY(add_layernorm(proj, nullptr, L.n2_g, L.n2_b, xq, R2, D, w->ln_eps, nullptr, nullptr, 0, nullptr, s));
+      x = xq;
+      prior_rows = 2;
+      break;
+    }
     MOCHA_TRY(tc.lin(x16, D, L.in_w, L.in_b, 0, nullptr, h16(qkv), Rp, 3 * D, D, ACT_NONE));
     MOCHA_TRY(tc_attention_ex(nullptr, qkv, 3 * D, nullptr, qkv + D, 3 * D, nullptr, qkv + 2 * D, 3 * D, B, H, np, np, dh,
                               S, h16(att), D, ws, s));
@@ -232,21 +259,26 @@ int cvae_bf16(const mocha_cvae_weights* w, const float* cond, int B, int ncond, 
     MOCHA_TRY(tc.lin(hid, w->dff, L.l2_w, L.l2_b, 0, y, f32(proj), Rp, D, w->dff, ACT_NONE)); // proj = y + FF(y)
     MOCHA_TRY(add_layernorm(proj, nullptr, L.n2_g, L.n2_b, x, Rp, D, w->ln_eps, nullptr, nullptr, 0, nullptr, s, x16));
   }
-  MOCHA_TRY(cvae_memory(x, np, eps, cond, nullptr, mu, logvar, B, ncond, D, s, mem));
+  MOCHA_TRY(cvae_memory(x, prior_rows, eps, cond, nullptr, mu, logvar, B, ncond, D, s, mem));
 
   // ---- decoder (query rows reuse the prior's buffers: Rq <= Rp) ----
   float* dx = xa; bf16* dx16 = xa16;
   float* dy = xb; bf16* dy16 = xb16;
-  MOCHA_TRY(broadcast_rows(w->pe, dx, B, (long long)nq * D, s, dx16));
+  if (!w->dec0_sa) MOCHA_TRY(broadcast_rows(w->pe, dx, B, (long long)nq * D, s, dx16));
   for (int l = 0; l < w->depth; ++l) {
     const mocha_cvae_dec_layer& L = w->dec[l];
     MOCHA_CHECK_ARG(L.sa_in_w && L.sa_out_w && L.ca_in_w && L.ca_out_w && L.l1_w && L.l2_w && L.n1_g && L.n2_g && L.n3_g,
                     "mocha_cvae_sample: decoder layer %d weights missing", l);
-    MOCHA_TRY(tc.lin(dx16, D, L.sa_in_w, L.sa_in_b, 0, nullptr, h16(qkv), Rq, 3 * D, D, ACT_NONE));
-    MOCHA_TRY(tc_attention_ex(nullptr, qkv, 3 * D, nullptr, qkv + D, 3 * D, nullptr, qkv + 2 * D, 3 * D, B, H, nq, nq, dh,
-                              S, h16(att), D, ws, s));
-    MOCHA_TRY(tc.lin(att, D, L.sa_out_w, L.sa_out_b, 0, dx, f32(proj), Rq, D, D, ACT_NONE));
-    MOCHA_TRY(add_layernorm(proj, nullptr, L.n1_g, L.n1_b, dy, Rq, D, w->ln_eps, nullptr, nullptr, 0, nullptr, s, dy16));
+    if (l == 0 && w->dec0_sa) {
+      // layer 0's self-attention block acts on the constant query: cached table (mocha_cvae_precompute_dec0)
+      MOCHA_TRY(broadcast_rows(w->dec0_sa, dy, B, (long long)nq * D, s, dy16));
+    } else {
+      MOCHA_TRY(tc.lin(dx16, D, L.sa_in_w, L.sa_in_b, 0, nullptr, h16(qkv), Rq, 3 * D, D, ACT_NONE));
+      MOCHA_TRY(tc_attention_ex(nullptr, qkv, 3 * D, nullptr, qkv + D, 3 * D, nullptr, qkv + 2 * D, 3 * D, B, H, nq, nq, dh,
+                                S, h16(att), D, ws, s));
+      MOCHA_TRY(tc.lin(att, D, L.sa_out_w, L.sa_out_b, 0, dx, f32(proj), Rq, D, D, ACT_NONE));
+      MOCHA_TRY(add_layernorm(proj, nullptr, L.n1_g, L.n1_b, dy, Rq, D, w->ln_eps, nullptr, nullptr, 0, nullptr, s, dy16));
+    }
     MOCHA_TRY(tc.lin(dy16, D, L.ca_in_w, L.ca_in_b, 0, nullptr, h16(dq), Rq, D, D, ACT_NONE));
     MOCHA_TRY(tc.lin(mem, D, L.ca_in_w + (size_t)D * D, L.ca_in_b + D, 0, nullptr, h16(memkv), Rm, 2 * D, D, ACT_NONE));
     MOCHA_TRY(tc_attention_ex(nullptr, dq, D, nullptr, memkv, 2 * D, nullptr, memkv + D, 2 * D, B, H, nq, nm, dh, S,

@@ -329,6 +329,20 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16*
   }
 }
 
+// out[b, i, :] = x[b, i, :] for i < take (the first `take` tokens of every batch element), fp32 + bf16
+__global__ void gather_token_rows_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ x16, int n,
+                                         int take, int C, long long total, float* __restrict__ out,
+                                         __nv_bfloat16* __restrict__ out16) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const int t = (int)((i / C) % take);
+  const long long b = i / ((long long)C * take);
+  const long long src = (b * n + t) * C + c;
+  if (out) out[i] = x[src];
+  if (out16) out16[i] = x16 ? x16[src] : __float2bfloat16_rn(x[src]);
+}
+
 inline unsigned blocks_for(long long total, int bs) { return (unsigned)((total + bs - 1) / bs); }
 
 }  // namespace
@@ -470,6 +484,16 @@ int add_table(const float* a, const float* table, float* out, long long rows, in
   add_table_kernel<<<blocks_for(total, 256), 256, 0, s>>>(a, table, out, total, C, period);
   count_launch();
   MOCHA_LAUNCH_CHECK("add_table");
+  return MOCHA_OK;
+}
+
+int gather_token_rows(const float* x, const __nv_bfloat16* x16, int n, int take, int C, int B, float* out,
+                      __nv_bfloat16* out16, cudaStream_t s) {
+  MOCHA_CHECK_ARG(x && (out || out16) && n >= take && take > 0 && C > 0 && B > 0, "gather_token_rows: bad args");
+  const long long total = (long long)B * take * C;
+  gather_token_rows_kernel<<<blocks_for(total, 256), 256, 0, s>>>(x, x16, n, take, C, total, out, out16);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("gather_token_rows");
   return MOCHA_OK;
 }
 

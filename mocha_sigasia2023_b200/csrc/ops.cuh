@@ -63,6 +63,10 @@ int broadcast_rows(const float* x, float* out, int B, long long n_elems, cudaStr
 // out = a + table[(r % period)]
 int add_table(const float* a, const float* table, float* out, long long rows, int C, int period, cudaStream_t s);
 
+// out[b, i, :] = x[b, i, :] for i < take; fp32 and/or bf16 outputs (x16 optional bf16 source)
+int gather_token_rows(const float* x, const __nv_bfloat16* x16, int n, int take, int C, int B, float* out,
+                      __nv_bfloat16* out16, cudaStream_t s);
+
 int cast_f32_bf16(const float* x, __nv_bfloat16* y, long long n, cudaStream_t s);
 
 }  // namespace mocha

@@ -238,4 +238,15 @@ class PackedCVAE:
             for f in ("sa_in_w", "sa_in_b", "sa_out_w", "sa_out_b", "ca_in_w", "ca_in_b", "ca_out_w", "ca_out_b",
                       "l1_w", "l1_b", "l2_w", "l2_b", "n1_g", "n1_b", "n2_g", "n2_b", "n3_g", "n3_b"):
                 setattr(w.dec[l], f, b.ptr(f"de{l}.{f}"))
+        w.dec0_sa = None
         self.struct = w
+        # decoder layer 0's self-attention block acts on the constant positional query: compute it once
+        lib = _lib.load()
+        self.dec0_sa = torch.empty((output_seq, latent_dim), dtype=torch.float32, device=device)
+        ws = torch.empty(16 << 20, dtype=torch.uint8, device=device)
+        _lib.check(lib.mocha_cvae_precompute_dec0(C.byref(w), C.c_void_p(self.dec0_sa.data_ptr()),
+                                                  C.c_void_p(ws.data_ptr()), ws.numel(),
+                                                  C.c_void_p(torch.cuda.current_stream(device).cuda_stream)),
+                   "mocha_cvae_precompute_dec0")
+        torch.cuda.current_stream(device).synchronize()
+        w.dec0_sa = self.dec0_sa.data_ptr()
