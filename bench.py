@@ -361,7 +361,12 @@ def roofline_pass(args, sess, torch, lib, _lib):
         return {"kernel": "tc_gemm_kernel<256,LinearEpi>: mot_embedding JointBlock temporal conv (5 taps, 256->256) as a "
                           "TMA-shifted implicit GEMM on tcgen05 (largest launch of the step, 31 % of its FLOPs)",
                 "bound": "tensor", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": src + " (burst)",
+                "unit": "TFLOP/s", "frac": achieved / peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this launch at 128 clips from one
+                # `ncu --set full` capture (profiles/r01_ncu_tconv_tc_gemm_LinearEpi.txt); algorithmic
+                # bytes are 106 MB (padded bf16 operand) + 189 MB (fp32 output)
+                "traffic": (101479424 + 133293824) * (B / 128.0), "traffic_unit": "B/launch",
+                "peak_source": src + " (burst)",
                 "ms_per_launch": ms, "flops_per_launch": flops}
     return {"kernel": "sgemm_kernel<128,128,8,8> (temporal conv as implicit GEMM, fp32 FFMA)", "bound": "fp32-simt",
             "achieved": achieved, "peak": 80.0, "unit": "TFLOP/s", "frac": achieved / 80.0, "traffic": None,
