@@ -230,6 +230,10 @@ int mocha_match_tc(const float* d_Q, const void* d_Q16, int nq, const void* d_DB
                    const float* d_dbnorm, long long N, int D, int k, int kc, long long index_offset,
                    int64_t* d_idx, double* d_dist, void* workspace, size_t workspace_bytes,
                    mocha_stream_t stream);
+/* fp32-storage mode (BASELINE config 3 "fp32"): pass d_DB16 = d_Q16 = NULL and d_DB32 != NULL; the coarse
+ * pass then feeds the fp32 rows to tcgen05 as TF32 (kind::tf32) and d_dbnorm = ||x||^2 of the fp32 rows
+ * (mocha_db_norms_f32). */
+int mocha_db_norms_f32(const float* d_rows, long long N, int D, float* d_norm, mocha_stream_t stream);
 /* helpers to build the bf16 DB: rows fp32 -> bf16 (+ squared norms of the rounded rows) */
 int mocha_db_pack_bf16(const float* d_rows, long long N, int D, void* d_rows16, float* d_norm,
                        mocha_stream_t stream);

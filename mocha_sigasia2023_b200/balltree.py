@@ -14,7 +14,8 @@ class BallTree:
     # above this many (query x row) pairs the tensor-core path is used
     TC_THRESHOLD_PAIRS = 1 << 22
 
-    def __init__(self, X, leaf_size=40, metric="minkowski", device=None, use_tensor_cores=None, kc=8, **kwargs):
+    def __init__(self, X, leaf_size=40, metric="minkowski", device=None, use_tensor_cores=None, kc=8,
+                 tc_storage="bf16", **kwargs):
         if metric not in ("minkowski", "euclidean", "l2"):
             raise _lib.MochaError(f"BallTree metric {metric!r} unsupported (Euclidean only)")
         if kwargs.get("p", 2) != 2:
@@ -31,6 +32,10 @@ class BallTree:
         self.N, self.D = self.data.shape
         self.use_tensor_cores = use_tensor_cores
         self.kc = kc
+        if tc_storage not in ("bf16", "fp32"):
+            raise _lib.MochaError("tc_storage must be 'bf16' or 'fp32'")
+        self.tc_storage = tc_storage   # operand format of the tensor-core coarse pass (fp32 -> TF32 MMA)
+        self._norm32 = None
         self._db16 = None
         self._norm = None
         self._ws = None
@@ -62,7 +67,16 @@ class BallTree:
         use_tc = self.use_tensor_cores
         if use_tc is None:
             use_tc = nq * self.N >= self.TC_THRESHOLD_PAIRS and self.D % 8 == 0 and self.D >= 64 and k <= self.kc
-        if use_tc:
+        if use_tc and self.tc_storage == "fp32":
+            if self._norm32 is None:
+                self._norm32 = torch.empty((self.N,), dtype=torch.float32, device=self.data.device)
+                _lib.check(lib.mocha_db_norms_f32(_lib.ptr(self.data), self.N, self.D, _lib.ptr(self._norm32),
+                                                  _lib.stream_ptr()), "mocha_db_norms_f32")
+            ws = self._scratch(lib.mocha_match_tc_workspace_bytes(nq, self.N, self.D, self.kc))
+            _lib.check(lib.mocha_match_tc(_lib.ptr(q), None, nq, None, _lib.ptr(self.data), _lib.ptr(self._norm32),
+                                          self.N, self.D, k, self.kc, 0, _lib.ptr(idx), _lib.ptr(dist), _lib.ptr(ws),
+                                          ws.numel(), _lib.stream_ptr()), "mocha_match_tc(tf32)")
+        elif use_tc:
             self._ensure_bf16()
             q16 = q.to(torch.bfloat16)
             ws = self._scratch(lib.mocha_match_tc_workspace_bytes(nq, self.N, self.D, self.kc))

@@ -117,6 +117,18 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with fp32 operands consumed as TF32 (K = 8 per instruction, 32 B per k-step like bf16's 16 x 2 B)
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -144,8 +156,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return d;
 }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// fmt: 1 = BF16 (kind::f16), 2 = TF32 (kind::tf32)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, uint32_t fmt = 1) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -244,6 +257,7 @@ struct LinearEpi {
   struct State {};
   static constexpr int kStageBytes = EPI_WARPS * 32 * EPI_LD * 4;  // per-warp transposition buffers
   static constexpr uint64_t kHintA = 0, kHintB = 0;                // default L2 policy
+  static constexpr bool kTf32 = false;
   __device__ __forceinline__ void unit_begin(State&) const {}
 
   // Second half of the transposed epilogue, specialised on the activation so the inner loop has no
@@ -348,8 +362,9 @@ struct LinearEpi {
   __device__ __forceinline__ void unit_end(State&, const EpiCtx&, long long, bool, int) const {}
 };
 
-template <int KC>
+template <int KC, bool TF32 = false>
 struct MatchEpi {
+  static constexpr bool kTf32 = TF32;  // fp32-storage DB: operands fed to the tensor cores as TF32
   const float* dbnorm;
   long long N;
   float* cand_score;
@@ -424,6 +439,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   using SM = TcSmem<BN, Epi::kStageBytes>;
   constexpr int STAGES = SM::STAGES;
   constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  constexpr int KELEMS = Epi::kTf32 ? 32 : BLOCK_K;  // elements per 128-byte k-block row
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * SM::STAGE_BYTES);
@@ -475,14 +491,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
             const int tap = kb / sh.kb_per_tap, kc = kb - tap * sh.kb_per_tap;
             if (Epi::kHintA != 0) {
-              tma_load_2d_hint(sa, &tmA, &full_bar[stage], a_col0 + kc * BLOCK_K,
+              tma_load_2d_hint(sa, &tmA, &full_bar[stage], a_col0 + kc * KELEMS,
                                (int)(a_row0 + (long long)tap * sh.tap_row_stride), Epi::kHintA);
-              tma_load_2d_hint(sb, &tmB, &full_bar[stage], b_col0 + kb * BLOCK_K, (int)(b_row0 + (long long)nt * BN),
+              tma_load_2d_hint(sb, &tmB, &full_bar[stage], b_col0 + kb * KELEMS, (int)(b_row0 + (long long)nt * BN),
                                Epi::kHintB);
             } else {
-              tma_load_2d(sa, &tmA, &full_bar[stage], a_col0 + kc * BLOCK_K,
+              tma_load_2d(sa, &tmA, &full_bar[stage], a_col0 + kc * KELEMS,
                           (int)(a_row0 + (long long)tap * sh.tap_row_stride));
-              tma_load_2d(sb, &tmB, &full_bar[stage], b_col0 + kb * BLOCK_K, (int)(b_row0 + (long long)nt * BN));
+              tma_load_2d(sb, &tmB, &full_bar[stage], b_col0 + kb * KELEMS, (int)(b_row0 + (long long)nt * BN));
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -492,7 +508,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BLOCK_M, BN);
+      constexpr uint32_t idesc = make_idesc(BLOCK_M, BN, Epi::kTf32 ? 2u : 1u);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
       for (int u = blockIdx.x; u < sh.units; u += gridDim.x) {
@@ -512,7 +528,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
               // advance 32 B (16 bf16) inside the 128 B swizzle atom: +2 in 16 B units
-              umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+              if (Epi::kTf32) umma_tf32(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+              else umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
             }
             umma_commit(&empty_bar[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -799,17 +816,18 @@ EncodeTiledFn get_encode_fn() {
 
 // bf16 [rows, K] row-major, box = box_rows x 64 elements, 128B swizzle, OOB reads return zero
 int make_tmap(CUtensorMap* tm, const void* ptr, unsigned long long rows, unsigned long long K, int box_rows,
-              unsigned long long pitch_elems = 0) {
+              unsigned long long pitch_elems = 0, bool f32 = false) {
   if (pitch_elems == 0) pitch_elems = K;
+  const unsigned long long esz = f32 ? 4 : 2;
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(MOCHA_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   MOCHA_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "tensor map: base not 16B aligned");
-  MOCHA_CHECK_ARG((pitch_elems * 2) % 16 == 0, "tensor map: row pitch %llu B not a multiple of 16", pitch_elems * 2);
+  MOCHA_CHECK_ARG((pitch_elems * esz) % 16 == 0, "tensor map: row pitch %llu B not a multiple of 16", pitch_elems * esz);
   cuuint64_t gdim[2] = {K, rows};
-  cuuint64_t gstride[1] = {pitch_elems * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint64_t gstride[1] = {pitch_elems * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+  CUresult r = fn(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(MOCHA_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -1312,6 +1330,44 @@ int tc_match_coarse_pair(const __nv_bfloat16* Q16, int nq, const __nv_bfloat16* 
   if (kc == 4) return launch_match2<4>(tmA, tmB, sh, num_kb, MatchEpi<4>{dbnorm, N, cand_score, cand_idx, 2 * splits}, s);
   if (kc == 8) return launch_match2<8>(tmA, tmB, sh, num_kb, MatchEpi<8>{dbnorm, N, cand_score, cand_idx, 2 * splits}, s);
   return launch_match2<16>(tmA, tmB, sh, num_kb, MatchEpi<16>{dbnorm, N, cand_score, cand_idx, 2 * splits}, s);
+}
+
+// fp32-storage variant: queries and DB rows stay fp32 in HBM and are consumed as TF32 by tcgen05
+// (kind::tf32, K = 8 per instruction; 32 elements per 128-byte k-block row)
+int tc_match_coarse_tf32(const float* Q, int nq, const float* DB, const float* dbnorm, long long N, int D, int kc,
+                         float* cand_score, int32_t* cand_idx, cudaStream_t s) {
+  MOCHA_CHECK_ARG(Q && DB && dbnorm && cand_score && cand_idx, "tc_match_coarse_tf32: null operand");
+  MOCHA_CHECK_ARG(nq > 0 && N > 0 && N < 2147483647LL, "tc_match_coarse_tf32: bad sizes nq=%d N=%lld", nq, N);
+  MOCHA_CHECK_ARG(D >= 32 && D % 4 == 0, "tc_match_coarse_tf32: D=%d must be >= 32 and a multiple of 4", D);
+  MOCHA_CHECK_ARG(kc == 4 || kc == 8 || kc == 16, "tc_match_coarse_tf32: kc must be 4, 8 or 16");
+  constexpr int BN = 256;
+  CUtensorMap tmA, tmB;
+  MOCHA_TRY(make_tmap(&tmA, Q, (unsigned long long)nq, (unsigned long long)D, BLOCK_M, 0, true));
+  MOCHA_TRY(make_tmap(&tmB, DB, (unsigned long long)N, (unsigned long long)D, BN, 0, true));
+  TcShape sh{};
+  sh.nb = 1;
+  sh.rows_out_per_b = nq;
+  sh.tiles_m_per_b = ceil_div(nq, BLOCK_M);
+  sh.tiles_m_total = sh.tiles_m_per_b;
+  sh.src_rows_per_b = nq;
+  sh.taps = 1;
+  sh.kb_per_tap = ceil_div(D, 32);
+  sh.tiles_n = (int)((N + BN - 1) / BN);
+  const int splits = tc_match_splits(nq, N) / 2;
+  sh.tiles_per_unit = ceil_div(sh.tiles_n, splits);
+  sh.units = sh.tiles_m_total * splits;
+  sh.splits = splits;
+  {
+    long long gm = (64LL << 20) / ((long long)BLOCK_M * D * 4);
+    if (gm < 1) gm = 1;
+    for (long long d = gm; d >= 1; --d)
+      if (sh.tiles_m_total % d == 0) { if (2 * d > gm) gm = d; break; }
+    sh.group_m = (int)gm;
+  }
+  const int num_kb = ceil_div(D, 32);
+  if (kc == 4) return launch_tc<BN, MatchEpi<4, true>>(tmA, tmB, sh, num_kb, MatchEpi<4, true>{dbnorm, N, cand_score, cand_idx, 2 * splits}, s);
+  if (kc == 8) return launch_tc<BN, MatchEpi<8, true>>(tmA, tmB, sh, num_kb, MatchEpi<8, true>{dbnorm, N, cand_score, cand_idx, 2 * splits}, s);
+  return launch_tc<BN, MatchEpi<16, true>>(tmA, tmB, sh, num_kb, MatchEpi<16, true>{dbnorm, N, cand_score, cand_idx, 2 * splits}, s);
 }
 
 int tc_match_coarse(const __nv_bfloat16* Q16, int nq, const __nv_bfloat16* DB16, const float* dbnorm, long long N,

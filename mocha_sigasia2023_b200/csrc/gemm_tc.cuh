@@ -64,4 +64,8 @@ int tc_match_splits(int nq, long long N);
 int tc_match_coarse(const __nv_bfloat16* Q16, int nq, const __nv_bfloat16* DB16, const float* dbnorm,
                     long long N, int D, int kc, float* cand_score, int32_t* cand_idx, cudaStream_t s);
 
+// fp32-storage DB: same pass with fp32 operands consumed as TF32 (dbnorm = ||x||^2 of the fp32 rows)
+int tc_match_coarse_tf32(const float* Q, int nq, const float* DB, const float* dbnorm, long long N, int D, int kc,
+                         float* cand_score, int32_t* cand_idx, cudaStream_t s);
+
 }  // namespace mocha

@@ -315,7 +315,8 @@ extern "C" int mocha_match_tc(const float* Q, const void* Q16, int nq, const voi
                               const float* dbnorm, long long N, int D, int k, int kc, long long index_offset,
                               int64_t* idx, double* dist, void* workspace, size_t workspace_bytes,
                               mocha_stream_t stream) {
-  MOCHA_CHECK_ARG(Q && Q16 && DB16 && dbnorm && idx, "mocha_match_tc: null argument");
+  MOCHA_CHECK_ARG(Q && dbnorm && idx && (DB16 || DB32), "mocha_match_tc: null argument");
+  MOCHA_CHECK_ARG(!DB16 || Q16, "mocha_match_tc: bf16 DB needs the bf16 query copy");
   MOCHA_CHECK_ARG(k >= 1 && k <= kc && kc <= KMAX, "mocha_match_tc: need 1 <= k <= kc <= %d", KMAX);
   MOCHA_CHECK_ARG(k <= N, "mocha_match_tc: k=%d > N=%lld", k, N);
   Workspace ws(workspace, workspace_bytes);
@@ -327,7 +328,10 @@ extern "C" int mocha_match_tc(const float* Q, const void* Q16, int nq, const voi
     return set_error(MOCHA_ERR_WORKSPACE, "mocha_match_tc: workspace too small (%zu B given, %zu B needed)",
                      workspace_bytes, ws.off);
   cudaStream_t s = (cudaStream_t)stream;
-  MOCHA_TRY(tc_match_coarse((const __nv_bfloat16*)Q16, nq, (const __nv_bfloat16*)DB16, dbnorm, N, D, kc, cs, ci, s));
+  if (DB16)
+    MOCHA_TRY(tc_match_coarse((const __nv_bfloat16*)Q16, nq, (const __nv_bfloat16*)DB16, dbnorm, N, D, kc, cs, ci, s));
+  else  // fp32-storage DB: TF32 tensor-core pass straight from the fp32 rows
+    MOCHA_TRY(tc_match_coarse_tf32(Q, nq, DB32, dbnorm, N, D, kc, cs, ci, s));
   match_rerank_kernel<<<nq, 256, 0, s>>>(Q, (const __nv_bfloat16*)DB16, DB32, D, cs, ci, (int)ncand, kc, k,
                                          index_offset, idx, dist);
   count_launch();
@@ -341,6 +345,26 @@ extern "C" int mocha_db_pack_bf16(const float* rows, long long N, int D, void* r
   db_pack_kernel<<<(unsigned)((N + 7) / 8), 256, 0, (cudaStream_t)stream>>>(rows, N, D, (__nv_bfloat16*)rows16, norm);
   count_launch();
   MOCHA_LAUNCH_CHECK("db_pack_kernel");
+  return MOCHA_OK;
+}
+
+// squared norms of fp32 rows (dbnorm for the fp32-storage / TF32 matcher)
+__global__ void __launch_bounds__(256) row_norm_kernel(const float* __restrict__ rows, long long N, int D, float* __restrict__ norm) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 8 + warp;
+  if (r >= N) return;
+  const float* x = rows + r * (long long)D;
+  float acc = 0.f;
+  for (int d = lane; d < D; d += 32) acc = fmaf(x[d], x[d], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) norm[r] = acc;
+}
+
+extern "C" int mocha_db_norms_f32(const float* rows, long long N, int D, float* norm, mocha_stream_t stream) {
+  MOCHA_CHECK_ARG(rows && norm && N > 0 && D > 0, "mocha_db_norms_f32: bad argument");
+  row_norm_kernel<<<(unsigned)((N + 7) / 8), 256, 0, (cudaStream_t)stream>>>(rows, N, D, norm);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("row_norm_kernel");
   return MOCHA_OK;
 }
 

@@ -105,3 +105,19 @@ def test_exact_matcher_batched_tiles(N, D, nq, k):
     wd, wi = matching.knn(db, q, k)
     np.testing.assert_array_equal(idx, wi)
     np.testing.assert_allclose(dist, wd, rtol=1e-12)
+
+
+@pytest.mark.parametrize("shape", [(4096, 512, 300, 2), (1000, 23040, 130, 1)])
+def test_tf32_fp32_storage_matcher(shape):
+    """BASELINE config 3 'fp32' leg: fp32 rows fed to tcgen05 as TF32, exact fp64 re-rank on the fp32 rows."""
+    N, D, nq, k = shape
+    rng = np.random.default_rng(N + D + 1)
+    db = rng.standard_normal((N, D)).astype(np.float32)
+    pick = rng.integers(0, N, size=nq)
+    q = (db[pick] + 0.05 * rng.standard_normal((nq, D))).astype(np.float32)
+    tree = BallTree(db, use_tensor_cores=True, kc=8, tc_storage="fp32")
+    dist, idx = tree.query(q, k=k, return_distance=True)
+    wd, wi = matching.knn_gemm(db, q, k)
+    np.testing.assert_array_equal(idx[:, 0], pick)
+    np.testing.assert_array_equal(idx[:, 0], wi[:, 0])
+    np.testing.assert_allclose(dist[:, 0], wd[:, 0], rtol=1e-9)

@@ -12,21 +12,27 @@ ap.add_argument("--d", type=int, default=23040)
 ap.add_argument("--kc", type=int, default=8)
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--dist", default="planted", choices=["planted", "iid"])
+ap.add_argument("--storage", default="bf16", choices=["bf16", "fp32"])
 a = ap.parse_args()
 lib = _lib.load()
 dev = "cuda"
 N, Q, D = a.n, a.q, a.d
 g = torch.Generator(device=dev).manual_seed(0)
-db16 = torch.empty((N, D), dtype=torch.bfloat16, device=dev)
+F32 = a.storage == "fp32"
+db16 = torch.empty((N, D), dtype=torch.float32 if F32 else torch.bfloat16, device=dev)
 norm = torch.empty((N,), dtype=torch.float32, device=dev)
 CH = 16384
 t0 = time.time()
 for s in range(0, N, CH):
     m = min(CH, N - s)
-    rows = torch.randn((m, D), generator=g, device=dev)
-    _lib.check(lib.mocha_db_pack_bf16(_lib.ptr(rows), m, D, _lib.ptr(db16[s:s + m]), _lib.ptr(norm[s:s + m]), _lib.stream_ptr()))
+    if F32:
+        db16[s:s + m].normal_(generator=g)
+        _lib.check(lib.mocha_db_norms_f32(_lib.ptr(db16[s:s + m]), m, D, _lib.ptr(norm[s:s + m]), _lib.stream_ptr()))
+    else:
+        rows = torch.randn((m, D), generator=g, device=dev)
+        _lib.check(lib.mocha_db_pack_bf16(_lib.ptr(rows), m, D, _lib.ptr(db16[s:s + m]), _lib.ptr(norm[s:s + m]), _lib.stream_ptr()))
 torch.cuda.synchronize()
-print(f"DB built: {N}x{D} bf16 = {db16.numel()*2/1e9:.1f} GB in {time.time()-t0:.1f}s", flush=True)
+print(f"DB built: {N}x{D} {a.storage} = {db16.numel()*db16.element_size()/1e9:.1f} GB in {time.time()-t0:.1f}s", flush=True)
 pick = torch.randint(0, N, (Q,), generator=g, device=dev)
 if a.dist == "planted":
     q = db16[pick].float() + 0.05 * torch.randn((Q, D), generator=g, device=dev)
@@ -41,15 +47,19 @@ times = []
 for i in range(a.iters + 1):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    _lib.check(lib.mocha_match_tc(_lib.ptr(q), _lib.ptr(q16), Q, _lib.ptr(db16), None, _lib.ptr(norm), N, D, 1, a.kc, 0,
-                                  _lib.ptr(idx), _lib.ptr(dist), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+    if F32:
+        _lib.check(lib.mocha_match_tc(_lib.ptr(q), None, Q, None, _lib.ptr(db16), _lib.ptr(norm), N, D, 1, a.kc, 0,
+                                      _lib.ptr(idx), _lib.ptr(dist), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+    else:
+        _lib.check(lib.mocha_match_tc(_lib.ptr(q), _lib.ptr(q16), Q, _lib.ptr(db16), None, _lib.ptr(norm), N, D, 1, a.kc, 0,
+                                      _lib.ptr(idx), _lib.ptr(dist), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
     e1.record()
     torch.cuda.synchronize()
     if i > 0:
         times.append(e0.elapsed_time(e1))
 ms = sum(times) / len(times)
 flops = 2.0 * Q * N * D
-res = {"workload": f"match sweep {Q}q x {N} x {D} bf16 {a.dist}", "ms": ms, "tflops": flops / ms / 1e9,
+res = {"workload": f"match sweep {Q}q x {N} x {D} {a.storage} {a.dist}", "ms": ms, "tflops": flops / ms / 1e9,
        "flops": flops}
 if a.dist == "planted":
     res["planted_found"] = float((idx[:, 0] == pick).float().mean())
