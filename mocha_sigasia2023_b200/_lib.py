@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmocha_b200.so")
+# MOCHA_LIB selects another build of the same library (e.g. the --trace debug build)
+LIB_PATH = os.environ.get("MOCHA_LIB") or os.path.join(_HERE, "libmocha_b200.so")
 
 MOCHA_FP32 = 0
 MOCHA_BF16 = 1

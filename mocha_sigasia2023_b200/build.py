@@ -18,7 +18,7 @@ ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libmocha_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
 
-SOURCES = ["api.cu", "gemm_f32.cu", "ops.cu", "gemm_tc.cu", "match.cu", "networks.cu", "networks_bf16.cu", "kinematics.cu", "stream.cu"]
+SOURCES = ["api.cu", "gemm_f32.cu", "ops.cu", "gemm_tc.cu", "match.cu", "networks.cu", "networks_bf16.cu", "kinematics.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -44,21 +44,25 @@ def _digest(paths) -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, trace: bool = False) -> str:
+    """trace=True builds libmocha_b200_trace.so with -DMOCHA_TRACE (in-kernel time lines for tools/tc_trace.py)."""
+    lib_path = LIB.replace(".so", "_trace.so") if trace else LIB
+    obj_dir = OBJ_DIR + ("_trace" if trace else "")
+    flags = NVCC_FLAGS + (["-DMOCHA_TRACE"] if trace else [])
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
     deps.append(os.path.join(ROOT, "include", "mocha_b200.h"))
-    stamp = os.path.join(OBJ_DIR, "stamp")
+    stamp = os.path.join(obj_dir, "stamp")
     digest = _digest(deps)
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
+    if not force and os.path.exists(lib_path) and os.path.exists(stamp) and open(stamp).read() == digest:
         return LIB
-    os.makedirs(OBJ_DIR, exist_ok=True)
+    os.makedirs(obj_dir, exist_ok=True)
 
     def compile_one(src: str) -> str:
-        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", src, "-o", obj]
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        cmd = [_nvcc(), *flags, "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
-        log = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".ptxas.log")
+        log = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".ptxas.log")
         with open(log, "w") as f:
             f.write(r.stderr)
         if r.returncode != 0:
@@ -69,15 +73,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
-    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    cmd = [_nvcc(), "-shared", "-o", lib_path, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     with open(stamp, "w") as f:
         f.write(digest)
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, trace="--trace" in sys.argv)
     print(path)

@@ -225,7 +225,35 @@ struct EpiCtx {
   long long slab_row0;   // output row of the slab's first row (global, or within the image in batched mode)
   int slab_rows;         // valid rows in the slab (0..32)
   long long c_off;       // element offset of the output block (batched-head mode), else 0
+  uint32_t res_bar;      // shared-space address of this warp's residual-prefetch mbarrier
+  int col_off;           // column offset of the output block inside its TMA map (batched-head PV output)
+  int z;                 // image index b of the tile (batched-head mode: z = zb * H + zh)
+  int img;               // batch image of the tile: third TMA-store coordinate
+  int row0_in_img;       // first row of the slab inside its image: second TMA-store coordinate
 };
+
+// TMA store of one [32 rows x 32 cols] box from shared memory (bulk async-group of the issuing thread)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t smem_addr, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tm),
+               "r"(smem_addr), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until every committed bulk store of this thread has finished READING shared memory
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void sts128f(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -244,7 +272,28 @@ __device__ __forceinline__ float act_fn(float x) {
   return x;
 }
 
-struct LinearEpi {
+#ifdef MOCHA_TRACE
+// Debug build only (python -m mocha_sigasia2023_b200.build --trace): per-CTA clock64 time line of the
+// pipeline roles, read back by tools/tc_trace.py. 32 u64 slots per CTA.
+__device__ unsigned long long* g_tc_trace = nullptr;
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_TRACE(slot, val)                                                         \
+  do {                                                                              \
+    const unsigned long long tv_ = (val);                                           \
+    if (trace_buf && (slot) < 32) trace_buf[(size_t)blockIdx.x * 32 + (slot)] = tv_; \
+  } while (0)
+__device__ unsigned long long g_epi_dbg[16];
+#define EPI_DBG(i) do { if (blockIdx.x == 0 && threadIdx.x == 64) g_epi_dbg[i] = (unsigned long long)clock64(); } while (0)
+#else
+#define EPI_DBG(i) do { } while (0)
+#define TC_TRACE(slot, val) do { } while (0)
+#endif
+
+struct LinearEpiData {
   float* C;
   int ldc;
   int N;
@@ -254,112 +303,460 @@ struct LinearEpi {
   int act;
   __nv_bfloat16* C16;   // optional bf16 copy of the output (operand of the next tensor-core layer); C may be null
   int c16_lrelu;        // store LeakyReLU(0.2)(x) in the bf16 copy (pre-activation consumers)
-  struct State {};
-  static constexpr int kStageBytes = EPI_WARPS * 32 * EPI_LD * 4;  // per-warp transposition buffers
+  // TMA-store path (plain / tconv mode with 16 B-aligned outputs): 3-D maps {cols, rows per image, images}
+  int tma;      // 1: TMA-store path; 2: additionally the residual is TMA-prefetched (needs bias_period == 0)
+  CUtensorMap tmC, tmC16, tmR;
+};
+using LinearEpi = LinearEpiData;
+
+// MODE 0: LSU epilogue; 1: TMA stores; 2: TMA stores + TMA-prefetched residual. One kernel
+// instantiation per mode keeps each epilogue's register footprint and code small.
+template <int MODE>
+struct LinearEpiT : LinearEpiData {
+  struct State {
+    uint32_t rphase;  // parity of the residual-prefetch barrier
+  };
+  // per warp: 4 KB fp32 box [32][128 B] (128 B-swizzled, 1 KB aligned) + 2 KB bf16 box [32][64 B]
+  // (64 B-swizzled) + 4 KB residual box (128 B-swizzled); the LSU path uses a [32][EPI_LD] float
+  // transposition buffer
+  static constexpr int kWarpStageBytes = MODE == 2 ? 10240 : MODE == 1 ? 6144 : 5120;
+  static constexpr int kStageBytes = EPI_WARPS * kWarpStageBytes;
   static constexpr uint64_t kHintA = 0, kHintB = 0;                // default L2 policy
   static constexpr bool kTf32 = false;
+  static constexpr bool kWholeTile = false;
   __device__ __forceinline__ void unit_begin(State&) const {}
+  __device__ __forceinline__ void kernel_begin(State& st) const { st.rphase = 0; }
+  // issue the TMA prefetch of a chunk's residual box (does not depend on the accumulator)
+  __device__ __forceinline__ void prefetch_res(const EpiCtx& e, int col0) const {
+    if (MODE == 2 && col0 >= 0 && col0 < N && e.slab_rows > 0 && e.lane == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(e.res_bar), "r"(4096u) : "memory");
+      tma_load_3d(e.stage + 6144, &tmR, e.res_bar, col0, e.row0_in_img, e.img);
+    }
+  }
 
-  // Second half of the transposed epilogue, specialised on the activation so the inner loop has no
-  // per-element branching: 8 passes of 4 rows x 32 columns, 8 lanes x float4 = one 128 B line per row.
+  // LSU epilogue (batched-head attention outputs and unaligned tensors), second half of the transposed
+  // path: 8 passes of 4 rows x 32 columns, 8 lanes x float4 = one 128 B line per row, as a fixed
+  // sequence of unrolled phases - residual loads, staged reads, bias, activation, stores - with one
+  // base address and constant row strides. Ragged / unaligned chunks take the scalar path below.
   template <int ACT>
-  __device__ __forceinline__ void drain(const EpiCtx& e, int col0) const {
+  __device__ __forceinline__ void drain_fast(const EpiCtx& e, int col0) const {
     const int rr = e.lane >> 3, cc = (e.lane & 7) * 4;
     const int c = col0 + cc;
-    if (c >= N) return;
-    const bool vec = ((ldc & 3) == 0) && ((e.c_off & 3) == 0) && (c + 3 < N) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
-                     ((reinterpret_cast<uintptr_t>(C16) & 7) == 0) &&
-                     (!res || (reinterpret_cast<uintptr_t>(res) & 15) == 0) &&
-                     (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0);
-    const float* bp = bias;
-    const float* rp = res;
-    float4 bcol = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (bp && bias_period == 0) {
-      if (vec) bcol = __ldg(reinterpret_cast<const float4*>(bp + c));
-      else {
-        bcol.x = __ldg(bp + c);
-        if (c + 1 < N) bcol.y = __ldg(bp + c + 1);
-        if (c + 2 < N) bcol.z = __ldg(bp + c + 2);
-        if (c + 3 < N) bcol.w = __ldg(bp + c + 3);
+    const long long step = 4LL * ldc;
+    const uint32_t sbase0 = e.stage + (uint32_t)((rr * EPI_LD + cc) * 4);
+    float4 bc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias && bias_period == 0) bc = __ldg(reinterpret_cast<const float4*>(bias + c));
+    // two half-chunks of 4 passes (16 rows) keep the live set under the 168-register cap of a 320-thread CTA
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const long long base = e.c_off + (e.slab_row0 + rr + 16 * h) * (long long)ldc + c;
+      const int nrows = e.slab_rows - rr - 16 * h;  // pass `it` is live iff 4*it < nrows
+      const uint32_t sbase = sbase0 + (uint32_t)(h * 16 * EPI_LD * 4);
+      float4 rv[4];
+      if (res) {
+        const float* rp = res + base;
+#pragma unroll
+        for (int it = 0; it < 4; ++it)
+          if (4 * it < nrows) rv[it] = __ldg(reinterpret_cast<const float4*>(rp + it * step));
+      }
+      float4 o[4];
+      if (h == 0) EPI_DBG(2);
+#pragma unroll
+      for (int it = 0; it < 4; ++it) o[it] = lds128(sbase + (uint32_t)(it * 4 * EPI_LD * 4));
+      if (h == 0) EPI_DBG(3);
+      if (bias) {
+        if (bias_period == 0) {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) { o[it].x += bc.x; o[it].y += bc.y; o[it].z += bc.z; o[it].w += bc.w; }
+        } else {
+          const unsigned p = (unsigned)bias_period;
+          unsigned m = (unsigned)((unsigned long long)(e.slab_row0 + rr + 16 * h) % p);
+          float4 bv[4];
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            bv[it] = __ldg(reinterpret_cast<const float4*>(bias + (size_t)m * N + c));
+            m += 4;
+            m = m >= p ? m - p : m;
+            m = m >= p ? m - p : m;
+          }
+#pragma unroll
+          for (int it = 0; it < 4; ++it) { o[it].x += bv[it].x; o[it].y += bv[it].y; o[it].z += bv[it].z; o[it].w += bv[it].w; }
+        }
+      }
+      if (ACT != ACT_NONE) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          o[it].x = act_fn<ACT>(o[it].x); o[it].y = act_fn<ACT>(o[it].y);
+          o[it].z = act_fn<ACT>(o[it].z); o[it].w = act_fn<ACT>(o[it].w);
+        }
+      }
+      if (res) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it)
+          if (4 * it < nrows) { o[it].x += rv[it].x; o[it].y += rv[it].y; o[it].z += rv[it].z; o[it].w += rv[it].w; }
+      }
+      if (h == 0) EPI_DBG(4);
+      if (C) {
+        float* cp = C + base;
+#pragma unroll
+        for (int it = 0; it < 4; ++it)
+          if (4 * it < nrows) *reinterpret_cast<float4*>(cp + it * step) = o[it];
+      }
+      if (h == 0) EPI_DBG(5);
+      if (C16) {
+        if (c16_lrelu) {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            o[it].x = lrelu02(o[it].x); o[it].y = lrelu02(o[it].y); o[it].z = lrelu02(o[it].z); o[it].w = lrelu02(o[it].w);
+          }
+        }
+        __nv_bfloat16* cp = C16 + base;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(o[it].x, o[it].y), hi = __floats2bfloat162_rn(o[it].z, o[it].w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          if (4 * it < nrows) *reinterpret_cast<uint2*>(cp + it * step) = pk;
+        }
       }
     }
-    if (vec) {
-      // issue every load of the chunk first (memory-level parallelism), then compute and store
-      float4 o[8], bv[8], rv[8];
+  }
+
+  // TMA-store epilogue. The SM -> L2 write path is 32 B/clk/SM whether driven by STG or by the TMA
+  // engine (tools/probes/store_probe.cu), and a K=256 tile's MMAs take no longer than its stores, so
+  // the stores must never wait for the warps: each warp stages a 32x32 box in shared memory, one lane
+  // hands it to the TMA engine and the warp moves on to the next chunk while the engine drains it.
+  //   pass 1  lane = row: accumulator row -> 128 B-swizzled box (16 B chunk j of row r at j ^ (r & 7))
+  //   pass 2  8 lanes x float4 = one row: coalesced bias / residual loads, activation, in-place write
+  //           back (+ bf16 box), then fence.proxy.async and one elected TMA store per output.
+  template <int ACT>
+  __device__ __forceinline__ void drain_tma(const EpiCtx& e, int col0, const uint32_t (&v)[32]) const {
+    const uint32_t buf32 = e.stage, buf16 = e.stage + 4096;
+    if (e.lane == 0) bulk_wait_read0();  // the previous chunk's stores have left the staging buffers
+    __syncwarp();
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int r = it * 4 + rr;
-        bv[it] = bcol;
-        rv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < e.slab_rows) {
-          const long long grow = e.slab_row0 + r;
-          if (bp && bias_period > 0)
-            bv[it] = __ldg(reinterpret_cast<const float4*>(bp + (long long)((unsigned)grow % (unsigned)bias_period) * N + c));
-          if (rp) rv[it] = __ldg(reinterpret_cast<const float4*>(rp + e.c_off + grow * (long long)ldc + c));
+    for (int j = 0; j < 8; ++j)
+      sts128(buf32 + (uint32_t)(e.lane * 128 + ((j ^ (e.lane & 7)) << 4)), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+    const int rr = e.lane >> 3, cq = e.lane & 7;
+    const int c = col0 + cq * 4;
+    const bool col_ok = c < N;  // N % 4 == 0 on this path
+    if (bias || res || ACT != ACT_NONE || C16) {
+      float4 bc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias && bias_period == 0 && col_ok) bc = __ldg(reinterpret_cast<const float4*>(bias + c));
+      const long long step = 4LL * ldc;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const long long base = e.c_off + (e.slab_row0 + rr + 16 * h) * (long long)ldc + c;
+        const int nrows = col_ok ? e.slab_rows - rr - 16 * h : 0;  // pass `it` is live iff 4*it < nrows
+        float4 rv[4];
+        if (res) {
+          const float* rp = res + base;
+#pragma unroll
+          for (int it = 0; it < 4; ++it)
+            if (4 * it < nrows) rv[it] = __ldg(reinterpret_cast<const float4*>(rp + it * step));
         }
-        o[it] = lds128(e.stage + (uint32_t)((r * EPI_LD + cc) * 4));
-      }
+        float4 o[4];
+        uint32_t addr[4];
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int r = it * 4 + rr;
-        if (r < e.slab_rows) {
-          float4 x = o[it];
-          x.x = act_fn<ACT>(x.x + bv[it].x) + rv[it].x;
-          x.y = act_fn<ACT>(x.y + bv[it].y) + rv[it].y;
-          x.z = act_fn<ACT>(x.z + bv[it].z) + rv[it].z;
-          x.w = act_fn<ACT>(x.w + bv[it].w) + rv[it].w;
-          const long long o_ = e.c_off + (e.slab_row0 + r) * (long long)ldc + c;
-          if (C) *reinterpret_cast<float4*>(C + o_) = x;
-          if (C16) {
-            if (c16_lrelu) { x.x = lrelu02(x.x); x.y = lrelu02(x.y); x.z = lrelu02(x.z); x.w = lrelu02(x.w); }
-            __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
-            uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&lo);
-            pk.y = *reinterpret_cast<uint32_t*>(&hi);
-            *reinterpret_cast<uint2*>(C16 + o_) = pk;
+        for (int it = 0; it < 4; ++it) {
+          const int r = 16 * h + 4 * it + rr;
+          addr[it] = buf32 + (uint32_t)(r * 128 + ((cq ^ (r & 7)) << 4));
+          o[it] = lds128(addr[it]);
+        }
+        if (bias) {
+          if (bias_period == 0) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it) { o[it].x += bc.x; o[it].y += bc.y; o[it].z += bc.z; o[it].w += bc.w; }
+          } else {
+            const unsigned p = (unsigned)bias_period;
+            unsigned m = (unsigned)((unsigned long long)(e.slab_row0 + rr + 16 * h) % p);
+            float4 bv[4];
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              bv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (4 * it < nrows) bv[it] = __ldg(reinterpret_cast<const float4*>(bias + (size_t)m * N + c));
+              m += 4;
+              m = m >= p ? m - p : m;
+              m = m >= p ? m - p : m;
+            }
+#pragma unroll
+            for (int it = 0; it < 4; ++it) { o[it].x += bv[it].x; o[it].y += bv[it].y; o[it].z += bv[it].z; o[it].w += bv[it].w; }
+          }
+        }
+        if (ACT != ACT_NONE) {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            o[it].x = act_fn<ACT>(o[it].x); o[it].y = act_fn<ACT>(o[it].y);
+            o[it].z = act_fn<ACT>(o[it].z); o[it].w = act_fn<ACT>(o[it].w);
+          }
+        }
+        if (res) {
+#pragma unroll
+          for (int it = 0; it < 4; ++it)
+            if (4 * it < nrows) { o[it].x += rv[it].x; o[it].y += rv[it].y; o[it].z += rv[it].z; o[it].w += rv[it].w; }
+        }
+        if (C) {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) sts128f(addr[it], o[it]);
+        }
+        if (C16) {
+          if (c16_lrelu) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              o[it].x = lrelu02(o[it].x); o[it].y = lrelu02(o[it].y); o[it].z = lrelu02(o[it].z); o[it].w = lrelu02(o[it].w);
+            }
+          }
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(o[it].x, o[it].y), hi = __floats2bfloat162_rn(o[it].z, o[it].w);
+            const int r = 16 * h + 4 * it + rr;  // 64 B-swizzled box: 16 B chunk k of row r at k ^ ((r >> 1) & 3)
+            sts64(buf16 + (uint32_t)(r * 64 + (((cq >> 1) ^ ((r >> 1) & 3)) << 4) + (cq & 1) * 8),
+                  *reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
           }
         }
       }
-    } else {
-#pragma unroll 1
-      for (int it = 0; it < 8; ++it) {
-        const int r = it * 4 + rr;
-        if (r >= e.slab_rows) continue;
-        const long long grow = e.slab_row0 + r;
-        const float4 x4 = lds128(e.stage + (uint32_t)((r * EPI_LD + cc) * 4));
-        const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
-        const float bs[4] = {bcol.x, bcol.y, bcol.z, bcol.w};
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (e.lane == 0) {
+      // rows past the image and columns past the tensor are clipped by the tensor map
+      if (C) tma_store_3d(&tmC, buf32, col0 + e.col_off, e.row0_in_img, e.img);
+      if (C16) tma_store_3d(&tmC16, buf16, col0 + e.col_off, e.row0_in_img, e.img);
+      bulk_commit();
+    }
+  }
+
+  // Residual GEMMs (x + f(x) feeding both an fp32 stream and a bf16 operand): the residual box is
+  // TMA-prefetched one chunk ahead into a 128 B-swizzled buffer, so everything stays in the lane = row
+  // layout of tcgen05.ld: v = act(v + bias) + res, fp32 box and 64 B-swizzled bf16 box, TMA stores.
+  template <int ACT>
+  __device__ __forceinline__ void drain_tma_res(State& st, const EpiCtx& e, int col0, int next_col0, uint32_t (&v)[32]) const {
+    const uint32_t buf32 = e.stage, buf16 = e.stage + 4096, bufr = e.stage + 6144;
+    const int sw = e.lane & 7;
+    if (bias) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (c + k >= N) break;
-          float x = xs[k];
-          if (bp) x += bias_period > 0 ? __ldg(bp + (long long)((unsigned)grow % (unsigned)bias_period) * N + c + k) : bs[k];
-          x = act_fn<ACT>(x);
-          if (rp) x += __ldg(rp + e.c_off + grow * (long long)ldc + c + k);
-          if (C) C[e.c_off + grow * (long long)ldc + c + k] = x;
-          if (C16) C16[e.c_off + grow * (long long)ldc + c + k] = __float2bfloat16_rn(c16_lrelu ? lrelu02(x) : x);
+      for (int j = 0; j < 8; ++j) {
+        if (col0 + 4 * j < N) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0) + j);
+          v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + b4.x);
+          v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + b4.y);
+          v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + b4.z);
+          v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + b4.w);
         }
+      }
+    }
+    if (ACT != ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(act_fn<ACT>(__uint_as_float(v[j])));
+    }
+    // residual box landed? (rows / columns past the tensor are zero-filled by the TMA load)
+    {
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.b32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(e.res_bar), "r"(st.rphase)
+            : "memory");
+      }
+      st.rphase ^= 1;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 r4 = lds128(bufr + (uint32_t)(e.lane * 128 + ((j ^ sw) << 4)));
+      v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + r4.x);
+      v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + r4.y);
+      v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + r4.z);
+      v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + r4.w);
+    }
+    __syncwarp();                  // every lane has read the residual box: refill it for the next chunk
+    prefetch_res(e, next_col0);
+    if (e.lane == 0) bulk_wait_read0();  // the previous chunk's stores have left the staging buffers
+    __syncwarp();
+    if (C) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        sts128(buf32 + (uint32_t)(e.lane * 128 + ((j ^ sw) << 4)), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    if (C16) {
+      const int sw16 = (e.lane >> 1) & 3;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float a = __uint_as_float(v[8 * j + 2 * t]), b = __uint_as_float(v[8 * j + 2 * t + 1]);
+          if (c16_lrelu) { a = lrelu02(a); b = lrelu02(b); }
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+          pk[t] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        sts128(buf16 + (uint32_t)(e.lane * 64 + ((j ^ sw16) << 4)), pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (e.lane == 0) {
+      if (C) tma_store_3d(&tmC, buf32, col0 + e.col_off, e.row0_in_img, e.img);
+      if (C16) tma_store_3d(&tmC16, buf16, col0 + e.col_off, e.row0_in_img, e.img);
+      bulk_commit();
+    }
+  }
+
+  // scalar path for ragged / unaligned chunks (attention score tiles, N not a multiple of 4)
+  __device__ __forceinline__ void drain_slow(const EpiCtx& e, int col0) const {
+    const int rr = e.lane >> 3, cc = (e.lane & 7) * 4;
+    const int c = col0 + cc;
+    if (c >= N) return;
+#pragma unroll 1
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 4 + rr;
+      if (r >= e.slab_rows) break;
+      const long long grow = e.slab_row0 + r;
+      const float4 x4 = lds128(e.stage + (uint32_t)((r * EPI_LD + cc) * 4));
+      const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+      const float* bp = !bias ? nullptr : bias_period > 0 ? bias + (size_t)((unsigned long long)grow % (unsigned)bias_period) * N : bias;
+      const long long o_ = e.c_off + grow * (long long)ldc;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (c + k >= N) break;
+        float x = xs[k];
+        if (bp) x += __ldg(bp + c + k);
+        x = act == ACT_RELU ? fmaxf(x, 0.f) : act == ACT_GELU ? gelu_erf(x) : act == ACT_LRELU ? lrelu02(x) : x;
+        if (res) x += __ldg(res + o_ + c + k);
+        if (C) C[o_ + c + k] = x;
+        if (C16) C16[o_ + c + k] = __float2bfloat16_rn(c16_lrelu ? lrelu02(x) : x);
       }
     }
   }
 
   // Warp-collective: the accumulator slab (lane = row, 32 columns in registers) is transposed through
   // shared memory so that bias / residual loads and the stores are row-contiguous and coalesced.
-  __device__ __forceinline__ void chunk(State&, const EpiCtx& e, long long, bool, int col0,
-                                        const uint32_t (&v)[32]) const {
+  __device__ __forceinline__ void chunk(State& st, const EpiCtx& e, long long, bool, int col0, uint32_t (&v)[32],
+                                        int next_col0) const {
+    if (col0 >= N) return;
+    if constexpr (MODE == 2) {
+      if (e.slab_rows <= 0) return;
+      switch (act) {
+        case ACT_RELU: drain_tma_res<ACT_RELU>(st, e, col0, next_col0, v); break;
+        case ACT_GELU: drain_tma_res<ACT_GELU>(st, e, col0, next_col0, v); break;
+        case ACT_LRELU: drain_tma_res<ACT_LRELU>(st, e, col0, next_col0, v); break;
+        default: drain_tma_res<ACT_NONE>(st, e, col0, next_col0, v); break;
+      }
+    } else if constexpr (MODE == 1) {
+      if (e.slab_rows <= 0) return;
+      switch (act) {
+        case ACT_RELU: drain_tma<ACT_RELU>(e, col0, v); break;
+        case ACT_GELU: drain_tma<ACT_GELU>(e, col0, v); break;
+        case ACT_LRELU: drain_tma<ACT_LRELU>(e, col0, v); break;
+        default: drain_tma<ACT_NONE>(e, col0, v); break;
+      }
+    } else {
+    EPI_DBG(0);
 #pragma unroll
     for (int j = 0; j < 32; j += 4)
       sts128(e.stage + (uint32_t)((e.lane * EPI_LD + j) * 4), v[j], v[j + 1], v[j + 2], v[j + 3]);
     __syncwarp();
-    switch (act) {
-      case ACT_RELU: drain<ACT_RELU>(e, col0); break;
-      case ACT_GELU: drain<ACT_GELU>(e, col0); break;
-      case ACT_LRELU: drain<ACT_LRELU>(e, col0); break;
-      default: drain<ACT_NONE>(e, col0); break;
+    EPI_DBG(1);
+    const bool fast = col0 + 32 <= N && ((ldc | N) & 3) == 0 && (e.c_off & 3) == 0 &&
+                      (((reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(C16) & 7) == 0);
+    if (fast) {
+      switch (act) {
+        case ACT_RELU: drain_fast<ACT_RELU>(e, col0); break;
+        case ACT_GELU: drain_fast<ACT_GELU>(e, col0); break;
+        case ACT_LRELU: drain_fast<ACT_LRELU>(e, col0); break;
+        default: drain_fast<ACT_NONE>(e, col0); break;
+      }
+    } else {
+      drain_slow(e, col0);
     }
+    EPI_DBG(6);
     __syncwarp();
+    EPI_DBG(7);
+    }
   }
-  __device__ __forceinline__ void unit_end(State&, const EpiCtx&, long long, bool, int) const {}
+  __device__ __forceinline__ void unit_end(State&, const EpiCtx& e, long long, bool, int) const {
+    if (MODE != 0 && e.lane == 0) bulk_wait_read0();  // staging buffers must outlive the stores that read them
+  }
+};
+
+// Attention scores with the softmax fused into the epilogue: one tile holds every key of its 128
+// query rows (nkv <= BN), so the warp that owns a 32-row TMEM lane quarter makes three passes over
+// the accumulator - row max, row sum, normalised probabilities - without leaving TMEM, and hands the
+// bf16 probabilities P[z, row, 0:ldp] (zero beyond nkv) to the TMA engine. Replaces the fp32 score
+// round trip through HBM and the stand-alone softmax launch.
+struct SoftmaxEpi {
+  float scale_log2e;  // log2(e) / sqrt(dh)
+  int nkv;
+  int ldp;
+  CUtensorMap tmP;    // {ldp, nq, Z} bf16, 64 B-swizzled 32 x 32 boxes
+  struct State {};
+  static constexpr int kStageBytes = EPI_WARPS * 2048;
+  static constexpr uint64_t kHintA = 0, kHintB = 0;
+  static constexpr bool kTf32 = false;
+  static constexpr bool kWholeTile = true;
+  __device__ __forceinline__ void unit_begin(State&) const {}
+  __device__ __forceinline__ void kernel_begin(State&) const {}
+  __device__ __forceinline__ void prefetch_res(const EpiCtx&, int) const {}
+  __device__ __forceinline__ void unit_end(State&, const EpiCtx& e, long long, bool, int) const {
+    if (e.lane == 0) bulk_wait_read0();
+  }
+  __device__ __forceinline__ void tile(State&, const EpiCtx& e, uint32_t taddr) const {
+    if (e.half != 0 || e.slab_rows <= 0) return;  // one warp per lane quarter owns whole rows
+    const int nch = (nkv + 31) >> 5;
+    float m = -INFINITY;
+#pragma unroll 1
+    for (int ch = 0; ch < nch; ++ch) {
+      uint32_t v[32];
+      tmem_ld32(taddr + (uint32_t)(ch * 32), v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (ch * 32 + j < nkv) m = fmaxf(m, __uint_as_float(v[j]));
+    }
+    const float ms = m * scale_log2e;
+    float sum = 0.f;
+#pragma unroll 1
+    for (int ch = 0; ch < nch; ++ch) {
+      uint32_t v[32];
+      tmem_ld32(taddr + (uint32_t)(ch * 32), v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (ch * 32 + j < nkv) sum += exp2f(fmaf(__uint_as_float(v[j]), scale_log2e, -ms));
+    }
+    const float inv = 1.f / sum;
+    const uint32_t buf16 = e.stage;
+    const int sw16 = (e.lane >> 1) & 3;
+    const int nbox = (ldp + 31) >> 5;
+#pragma unroll 1
+    for (int ch = 0; ch < nbox; ++ch) {
+      uint32_t v[32];
+      tmem_ld32(taddr + (uint32_t)(ch * 32), v);
+      if (e.lane == 0) bulk_wait_read0();
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int c = ch * 32 + 8 * j + 2 * t;
+          const float a = c < nkv ? exp2f(fmaf(__uint_as_float(v[8 * j + 2 * t]), scale_log2e, -ms)) * inv : 0.f;
+          const float b = c + 1 < nkv ? exp2f(fmaf(__uint_as_float(v[8 * j + 2 * t + 1]), scale_log2e, -ms)) * inv : 0.f;
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+          pk[t] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        sts128(buf16 + (uint32_t)(e.lane * 64 + ((j ^ sw16) << 4)), pk[0], pk[1], pk[2], pk[3]);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (e.lane == 0) {
+        tma_store_3d(&tmP, buf16, ch * 32, e.row0_in_img, e.z);
+        bulk_commit();
+      }
+    }
+  }
+  __device__ __forceinline__ void chunk(State&, const EpiCtx&, long long, bool, int, const uint32_t (&)[32], int) const {}
 };
 
 template <int KC, bool TF32 = false>
@@ -371,6 +768,7 @@ struct MatchEpi {
   int32_t* cand_idx;
   int lists;  // candidate lists per query = 2 * splits (one per column half)
   static constexpr int kStageBytes = 0;
+  static constexpr bool kWholeTile = false;
   // query tiles are re-read for every DB tile: keep them in L2; DB rows stream through once per group
   static constexpr uint64_t kHintA = L2_EVICT_LAST, kHintB = L2_EVICT_FIRST;
   struct State {
@@ -381,8 +779,10 @@ struct MatchEpi {
 #pragma unroll
     for (int t = 0; t < KC; ++t) { st.s[t] = INFINITY; st.i[t] = -1; }
   }
+  __device__ __forceinline__ void kernel_begin(State&) const {}
+  __device__ __forceinline__ void prefetch_res(const EpiCtx&, int) const {}
   __device__ __forceinline__ void chunk(State& st, const EpiCtx&, long long, bool row_ok, int col0,
-                                        const uint32_t (&v)[32]) const {
+                                        const uint32_t (&v)[32], int) const {
     if (!row_ok || col0 >= N) return;
     float nrm[32];
     if ((long long)col0 + 32 <= N) {
@@ -435,27 +835,34 @@ struct TcSmem {
 template <int BN, class Epi>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const TcShape sh, const int num_kb, const Epi epi) {
+               const TcShape sh, const int num_kb, const __grid_constant__ Epi epi) {
   using SM = TcSmem<BN, Epi::kStageBytes>;
   constexpr int STAGES = SM::STAGES;
   constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   constexpr int KELEMS = Epi::kTf32 ? 32 : BLOCK_K;  // elements per 128-byte k-block row
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * SM::STAGE_BYTES);
+  // [operand stages][epilogue staging (1 KB aligned: stage sizes are multiples of 1 KB)][barriers]
+  uint8_t* epi_stage = smem + STAGES * SM::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + Epi::kStageBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  uint8_t* epi_stage = smem + STAGES * SM::STAGE_BYTES + 256;
+  uint64_t* res_bar = tempty_bar + 2;         // [EPI_WARPS] residual-prefetch barriers (LinearEpi)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + EPI_WARPS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef MOCHA_TRACE
+  unsigned long long* const trace_buf = g_tc_trace;
+  if (threadIdx.x == 0) { TC_TRACE(0, gtimer()); TC_TRACE(1, (unsigned long long)clock64()); }
+#endif
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_WARPS); }
+    for (int i = 0; i < EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -463,6 +870,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+#ifdef MOCHA_TRACE
+  if (threadIdx.x == 0) TC_TRACE(2, (unsigned long long)clock64());
+  int trace_tile = 0;
+#endif
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -502,6 +913,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
+#ifdef MOCHA_TRACE
+          TC_TRACE(4 + trace_tile, (unsigned long long)clock64());  // all loads of the tile issued
+          if (trace_tile < 3) ++trace_tile;
+#endif
         }
       }
     }
@@ -522,6 +937,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
+#ifdef MOCHA_TRACE
+            if (kb == 0) TC_TRACE(8 + trace_tile, (unsigned long long)clock64());  // first operands landed
+#endif
             const uint32_t sa = smem_u32(smem + stage * SM::STAGE_BYTES);
             const uint64_t adesc = make_smem_desc(sa);
             const uint64_t bdesc = make_smem_desc(sa + A_STAGE_BYTES);
@@ -536,6 +954,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           umma_commit(&tfull_bar[as]);
           if (++as == 2) { as = 0; aphase ^= 1; }
+#ifdef MOCHA_TRACE
+          TC_TRACE(12 + trace_tile, (unsigned long long)clock64());  // tile's MMAs issued + committed
+          if (trace_tile < 3) ++trace_tile;
+#endif
         }
       }
     }
@@ -544,6 +966,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     int as = 0; uint32_t aphase = 0;
     typename Epi::State st;
+    epi.kernel_begin(st);
     for (int u = blockIdx.x; u < sh.units; u += gridDim.x) {
       int mt, split;
       decode_unit(sh, u, mt, split);
@@ -552,7 +975,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool row_ok = r_in_b < sh.rows_out_per_b;
       const long long row = (long long)b * sh.rows_out_per_b + r_in_b;
       EpiCtx ectx;
-      ectx.stage = smem_u32(epi_stage + (warp - 2) * 32 * EPI_LD * 4);
+      ectx.stage = smem_u32(epi_stage + (warp - 2) * (Epi::kStageBytes / EPI_WARPS));
+      ectx.res_bar = smem_u32(&res_bar[warp - 2]);
+      ectx.col_off = 0;
+      ectx.z = b;
+      ectx.img = b;
+      ectx.row0_in_img = mtb * BLOCK_M + q * 32;
       ectx.lane = lane;
       ectx.half = (warp - 2) >> 2;
       ectx.slab_row0 = (long long)b * sh.rows_out_per_b + mtb * BLOCK_M + q * 32;
@@ -562,26 +990,44 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int zb = b / sh.H, zh = b - zb * sh.H;
         ectx.slab_row0 = mtb * BLOCK_M + q * 32;
         ectx.c_off = (long long)zb * sh.c_img_b + (long long)zh * sh.c_img_h;
+        ectx.img = zb;                      // TMA-store view of a [B, rows, H*cols] output (host checks the layout)
+        ectx.col_off = zh * (int)sh.c_img_h;
       }
       epi.unit_begin(st);
       const int nt_end = min(sh.tiles_n, (split + 1) * sh.tiles_per_unit);
       for (int nt = split * sh.tiles_per_unit; nt < nt_end; ++nt) {
-        mbar_wait(&tfull_bar[as], aphase);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
         // the tile's BN/32 column chunks are split between the two warps that share a lane quarter
         constexpr int kSplitCol = ((BN / 32 + 1) / 2) * 32;
         const int c_begin = ectx.half == 0 ? 0 : kSplitCol, c_end = ectx.half == 0 ? kSplitCol : BN;
+        if (c_begin < c_end) epi.prefetch_res(ectx, nt * BN + c_begin);  // overlaps the tile's main loop
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+#ifdef MOCHA_TRACE
+        if (warp == 2 && lane == 0) TC_TRACE(16 + trace_tile, (unsigned long long)clock64());  // accumulator ready
+#endif
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+        if constexpr (Epi::kWholeTile) epi.tile(st, ectx, taddr);
 #pragma unroll 1
-        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+        for (int c0 = c_begin; c0 < (Epi::kWholeTile ? c_begin : c_end); c0 += 32) {
           uint32_t v[32];
           tmem_ld32(taddr + (uint32_t)c0, v);
-          epi.chunk(st, ectx, row, row_ok, nt * BN + c0, v);
+#ifdef MOCHA_TRACE
+          if (warp == 2 && lane == 0 && trace_tile == 0 && c0 == c_begin) TC_TRACE(26, (unsigned long long)clock64());
+#endif
+          epi.chunk(st, ectx, row, row_ok, nt * BN + c0, v, c0 + 32 < c_end ? nt * BN + c0 + 32 : -1);
+#ifdef MOCHA_TRACE
+          if (warp == 2 && lane == 0 && trace_tile == 0 && c0 == c_begin) TC_TRACE(27, (unsigned long long)clock64());
+          if (warp == 2 && lane == 0 && trace_tile == 0 && c0 == c_begin + 32) TC_TRACE(28, (unsigned long long)clock64());
+#endif
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[as]);
         if (++as == 2) { as = 0; aphase ^= 1; }
+#ifdef MOCHA_TRACE
+        if (warp == 2 && lane == 0) TC_TRACE(20 + trace_tile, (unsigned long long)clock64());  // tile drained
+        if (trace_tile < 3) ++trace_tile;
+#endif
       }
       epi.unit_end(st, ectx, row, row_ok, split);
     }
@@ -594,6 +1040,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+#ifdef MOCHA_TRACE
+  if (threadIdx.x == 0) { TC_TRACE(24, (unsigned long long)clock64()); TC_TRACE(25, gtimer()); }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -774,7 +1223,7 @@ tc_match2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int c0 = c_begin; c0 < c_end; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(taddr + (uint32_t)c0, v);
-          epi.chunk(st, ectx, row, row_ok, nt * BN + c0, v);
+          epi.chunk(st, ectx, row, row_ok, nt * BN + c0, v, -1);
         }
         tc_fence_before();
         __syncwarp();
@@ -831,6 +1280,45 @@ int make_tmap(CUtensorMap* tm, const void* ptr, unsigned long long rows, unsigne
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(MOCHA_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return MOCHA_OK;
+}
+
+// Output maps of the TMA-store epilogue: {cols, rows per image, images}, box 32 cols x 32 rows x 1.
+// fp32 boxes are 128 B-swizzled (the epilogue transposes through them), bf16 boxes 64 B-swizzled.
+int make_out_tmap(CUtensorMap* tm, const void* ptr, unsigned long long cols, unsigned long long rows_per_img,
+                  unsigned long long imgs, unsigned long long ld_elems, bool f32) {
+  const unsigned long long esz = f32 ? 4 : 2;
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(MOCHA_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gdim[3] = {cols, rows_per_img, imgs};
+  cuuint64_t gstride[2] = {ld_elems * esz, rows_per_img * ld_elems * esz};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim,
+                  gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(MOCHA_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed (%d)", (int)r);
+  return MOCHA_OK;
+}
+
+// Switch a LinearEpi to the TMA-store path when its outputs allow it (plain / tconv mode only).
+int setup_out_tma(LinearEpi& epi, unsigned long long rows_per_img, unsigned long long imgs, unsigned long long cols = 0) {
+  epi.tma = 0;
+  if (cols == 0) cols = (unsigned long long)epi.N;
+  static const bool off = getenv("MOCHA_NO_TMA_STORE") != nullptr;  // debugging aid: force the LSU epilogue
+  if (off) return MOCHA_OK;
+  const bool ok = (epi.N % 4) == 0 && (epi.ldc % 8) == 0 &&
+                  ((reinterpret_cast<uintptr_t>(epi.C) | reinterpret_cast<uintptr_t>(epi.C16) |
+                    reinterpret_cast<uintptr_t>(epi.res) | reinterpret_cast<uintptr_t>(epi.bias)) & 15) == 0;
+  if (!ok) return MOCHA_OK;
+  if (epi.C) MOCHA_TRY(make_out_tmap(&epi.tmC, epi.C, cols, rows_per_img, imgs, (unsigned long long)epi.ldc, true));
+  if (epi.C16) MOCHA_TRY(make_out_tmap(&epi.tmC16, epi.C16, cols, rows_per_img, imgs, (unsigned long long)epi.ldc, false));
+  epi.tma = 1;
+  if (epi.res && epi.bias_period == 0) {
+    MOCHA_TRY(make_out_tmap(&epi.tmR, epi.res, cols, rows_per_img, imgs, (unsigned long long)epi.ldc, true));
+    epi.tma = 2;
+  }
   return MOCHA_OK;
 }
 
@@ -947,7 +1435,7 @@ int pick_bn(long long tiles_m, int N) {
 }
 
 template <class Epi>
-int dispatch_bn(int bn, const CUtensorMap& tmA, const void* Wptr, unsigned long long wrows, unsigned long long K,
+int dispatch_bn_impl(int bn, const CUtensorMap& tmA, const void* Wptr, unsigned long long wrows, unsigned long long K,
                 TcShape sh, int N, int num_kb, const Epi& epi, cudaStream_t s, unsigned long long wpitch = 0) {
   CUtensorMap tmB;
   MOCHA_TRY(make_tmap(&tmB, Wptr, wrows, K, bn, wpitch));
@@ -962,6 +1450,14 @@ int dispatch_bn(int bn, const CUtensorMap& tmA, const void* Wptr, unsigned long 
     case 64: return launch_tc<64, Epi>(tmA, tmB, sh, num_kb, epi, s);
     default: return launch_tc<32, Epi>(tmA, tmB, sh, num_kb, epi, s);
   }
+}
+
+// LinearEpi launches: one kernel family per epilogue mode
+int dispatch_bn(int bn, const CUtensorMap& tmA, const void* Wptr, unsigned long long wrows, unsigned long long K,
+                TcShape sh, int N, int num_kb, const LinearEpi& epi, cudaStream_t s, unsigned long long wpitch = 0) {
+  if (epi.tma == 2) return dispatch_bn_impl(bn, tmA, Wptr, wrows, K, sh, N, num_kb, LinearEpiT<2>{epi}, s, wpitch);
+  if (epi.tma == 1) return dispatch_bn_impl(bn, tmA, Wptr, wrows, K, sh, N, num_kb, LinearEpiT<1>{epi}, s, wpitch);
+  return dispatch_bn_impl(bn, tmA, Wptr, wrows, K, sh, N, num_kb, LinearEpiT<0>{epi}, s, wpitch);
 }
 
 }  // namespace
@@ -1014,6 +1510,7 @@ int tc_linear_bf16(const __nv_bfloat16* A16, int lda, const __nv_bfloat16* W16, 
   sh.kb_per_tap = ceil_div(K, BLOCK_K);
   sh.tap_row_stride = 0;
   LinearEpi epi{out.f32, N, N, bias, bias_period, res, act, out.bf16, out.lrelu};
+  MOCHA_TRY(setup_out_tma(epi, (unsigned long long)M, 1));
   return dispatch_bn(pick_bn(sh.tiles_m_total, N), tmA, W16, (unsigned long long)N, (unsigned long long)K, sh, N,
                      ceil_div(K, BLOCK_K), epi, s);
 }
@@ -1083,6 +1580,7 @@ int tc_tconv_ex(const float* X, const __nv_bfloat16* Xh, const float* W, const f
   sh.kb_per_tap = Cin / BLOCK_K;
   sh.tap_row_stride = V;
   LinearEpi epi{out.f32, Cout, Cout, bias, bias_period, nullptr, ACT_NONE, out.bf16, out.lrelu};
+  MOCHA_TRY(setup_out_tma(epi, (unsigned long long)T * V, (unsigned long long)B));
   int rc = MOCHA_OK;
   for (int it = 0; it < (repeat < 1 ? 1 : repeat) && rc == MOCHA_OK; ++it)  // repeat > 1: bench.py roofline pass
     rc = dispatch_bn(pick_bn(sh.tiles_m_total, Cout), tmA, W16, (unsigned long long)Cout,
@@ -1191,7 +1689,7 @@ int tc_attention_ex(const float* q, const __nv_bfloat16* qh, int ldq, const floa
                     const float* v, const __nv_bfloat16* vh, int ldv, int B, int H, int nq, int nkv, int dh, float* S,
                     TcOut out, int ldo, Workspace& ws, cudaStream_t s) {
   MOCHA_CHECK_ARG(tc_attention_supported(nq, nkv, dh), "tc_attention: unsupported geometry nq=%d nkv=%d dh=%d", nq, nkv, dh);
-  MOCHA_CHECK_ARG((q || qh) && (k || kh) && (v || vh) && S && (out.f32 || out.bf16), "tc_attention: null operand");
+  MOCHA_CHECK_ARG((q || qh) && (k || kh) && (v || vh) && (out.f32 || out.bf16), "tc_attention: null operand");
   const int inner = H * dh, Z = B * H, ldp = attn_ldp(nkv);
   const size_t mark = ws.off;
   const __nv_bfloat16* Q16 = qh;
@@ -1238,14 +1736,18 @@ int tc_attention_ex(const float* q, const __nv_bfloat16* qh, int ldq, const floa
     sh.b_rows_b = nkv; sh.b_rows_h = 0; sh.b_cols_h = dh;
     sh.c_img_b = (long long)H * nq * nkv; sh.c_img_h = (long long)nq * nkv;
     sh.taps = 1; sh.kb_per_tap = dh / BLOCK_K; sh.tap_row_stride = 0;
-    LinearEpi epi{S, nkv, nkv, nullptr, 0, nullptr, ACT_NONE, nullptr, 0};
-    MOCHA_TRY(dispatch_bn(pick_bn(sh.tiles_m_total, nkv), tmA, K16, (unsigned long long)B * nkv,
-                          (unsigned long long)inner, sh, nkv, dh / BLOCK_K, epi, s, (unsigned long long)pk));
+    // softmax fused into the epilogue: one tile spans every key of its rows, P goes out through TMA
+    SoftmaxEpi epi{};
+    epi.scale_log2e = 1.4426950408889634f / sqrtf((float)dh);
+    epi.nkv = nkv;
+    epi.ldp = ldp;
+    MOCHA_TRY(make_out_tmap(&epi.tmP, P16, (unsigned long long)ldp, (unsigned long long)nq, (unsigned long long)Z,
+                            (unsigned long long)ldp, false));
+    const int bn = nkv <= 32 ? 32 : nkv <= 64 ? 64 : nkv <= 128 ? 128 : 256;
+    MOCHA_TRY(dispatch_bn_impl(bn, tmA, K16, (unsigned long long)B * nkv, (unsigned long long)inner, sh, nkv,
+                               dh / BLOCK_K, epi, s, (unsigned long long)pk));
   }
-  softmax_bf16_kernel<<<(unsigned)(((long long)Z * nq + 7) / 8), 256, 0, s>>>(S, (long long)Z * nq, nkv, ldp,
-                                                                            1.0f / sqrtf((float)dh), P16);
-  count_launch();
-  MOCHA_LAUNCH_CHECK("softmax_bf16_kernel");
+  (void)S;  // scores no longer round-trip through HBM
   // out[b, :, h*dh:(h+1)*dh] = P[z] V[z]
   {
     CUtensorMap tmA;
@@ -1260,6 +1762,8 @@ int tc_attention_ex(const float* q, const __nv_bfloat16* qh, int ldq, const floa
     sh.c_img_b = (long long)nq * ldo; sh.c_img_h = dh;
     sh.taps = 1; sh.kb_per_tap = ceil_div(ldp, BLOCK_K); sh.tap_row_stride = 0;
     LinearEpi epi{out.f32, ldo, dh, nullptr, 0, nullptr, ACT_NONE, out.bf16, out.lrelu};
+    // out is [B, nq, H*dh] with the head as a column offset: one {ldo, nq, B} map serves every head
+    if (ldo == H * dh) MOCHA_TRY(setup_out_tma(epi, (unsigned long long)nq, (unsigned long long)B, (unsigned long long)ldo));
     MOCHA_TRY(dispatch_bn(pick_bn(sh.tiles_m_total, dh), tmA, VT16, (unsigned long long)Z * dh,
                           (unsigned long long)ldp, sh, dh, ceil_div(ldp, BLOCK_K), epi, s));
   }
@@ -1417,3 +1921,12 @@ int tc_match_coarse(const __nv_bfloat16* Q16, int nq, const __nv_bfloat16* DB16,
 }
 
 }  // namespace mocha
+
+#ifdef MOCHA_TRACE
+extern "C" int mocha_debug_get_epi(unsigned long long* host16) {
+  return cudaMemcpyFromSymbol(host16, mocha::g_epi_dbg, 16 * sizeof(unsigned long long)) == cudaSuccess ? 0 : 1;
+}
+extern "C" int mocha_debug_set_trace(unsigned long long* buf) {
+  return cudaMemcpyToSymbol(mocha::g_tc_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : 1;
+}
+#endif
