@@ -306,6 +306,10 @@ struct LinearEpiData {
   // TMA-store path (plain / tconv mode with 16 B-aligned outputs): 3-D maps {cols, rows per image, images}
   int tma;      // 1: TMA-store path; 2: additionally the residual is TMA-prefetched (needs bias_period == 0)
   CUtensorMap tmC, tmC16, tmR;
+  // optional per-row scale (TMA-store path only): out = act(acc * row_scale[z * rs_rows + row] + bias) ...
+  // (attention: the softmax denominator is applied to P V here, flash-attention style)
+  const float* row_scale;
+  int rs_rows;
 };
 using LinearEpi = LinearEpiData;
 
@@ -442,7 +446,7 @@ struct LinearEpiT : LinearEpiData {
     const int rr = e.lane >> 3, cq = e.lane & 7;
     const int c = col0 + cq * 4;
     const bool col_ok = c < N;  // N % 4 == 0 on this path
-    if (bias || res || ACT != ACT_NONE || C16) {
+    if (bias || res || ACT != ACT_NONE || C16 || row_scale) {
       float4 bc = make_float4(0.f, 0.f, 0.f, 0.f);
       if (bias && bias_period == 0 && col_ok) bc = __ldg(reinterpret_cast<const float4*>(bias + c));
       const long long step = 4LL * ldc;
@@ -464,6 +468,14 @@ struct LinearEpiT : LinearEpiData {
           const int r = 16 * h + 4 * it + rr;
           addr[it] = buf32 + (uint32_t)(r * 128 + ((cq ^ (r & 7)) << 4));
           o[it] = lds128(addr[it]);
+        }
+        if (row_scale) {
+          const float* rsp = row_scale + (long long)e.z * rs_rows + e.row0_in_img + 16 * h + rr;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const float f = 4 * it < nrows ? __ldg(rsp + 4 * it) : 0.f;
+            o[it].x *= f; o[it].y *= f; o[it].z *= f; o[it].w *= f;
+          }
         }
         if (bias) {
           if (bias_period == 0) {
@@ -682,15 +694,24 @@ struct LinearEpiT : LinearEpiData {
   }
 };
 
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // Attention scores with the softmax fused into the epilogue: one tile holds every key of its 128
 // query rows (nkv <= BN), so the warp that owns a 32-row TMEM lane quarter makes three passes over
-// the accumulator - row max, row sum, normalised probabilities - without leaving TMEM, and hands the
-// bf16 probabilities P[z, row, 0:ldp] (zero beyond nkv) to the TMA engine. Replaces the fp32 score
+// the accumulator - row max, then exp - without leaving TMEM, and hands the unnormalised bf16
+// probabilities P[z, row, 0:ldp] (zero beyond nkv) to the TMA engine; the reciprocal row sums are
+// applied by the P V GEMM's epilogue (flash-attention style). Replaces the fp32 score
 // round trip through HBM and the stand-alone softmax launch.
 struct SoftmaxEpi {
   float scale_log2e;  // log2(e) / sqrt(dh)
   int nkv;
   int ldp;
+  int nq;
+  float* inv_sum;     // [Z, nq] reciprocal softmax denominators, applied by the P V epilogue
   CUtensorMap tmP;    // {ldp, nq, Z} bf16, 64 B-swizzled 32 x 32 boxes
   struct State {};
   static constexpr int kStageBytes = EPI_WARPS * 2048;
@@ -711,28 +732,34 @@ struct SoftmaxEpi {
     for (int ch = 0; ch < nch; ++ch) {
       uint32_t v[32];
       tmem_ld32(taddr + (uint32_t)(ch * 32), v);
+      if (ch * 32 + 32 <= nkv) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (ch * 32 + j < nkv) m = fmaxf(m, __uint_as_float(v[j]));
+        for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (ch * 32 + j < nkv) m = fmaxf(m, __uint_as_float(v[j]));
+      }
     }
     const float ms = m * scale_log2e;
     float sum = 0.f;
-#pragma unroll 1
-    for (int ch = 0; ch < nch; ++ch) {
-      uint32_t v[32];
-      tmem_ld32(taddr + (uint32_t)(ch * 32), v);
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (ch * 32 + j < nkv) sum += exp2f(fmaf(__uint_as_float(v[j]), scale_log2e, -ms));
-    }
-    const float inv = 1.f / sum;
     const uint32_t buf16 = e.stage;
     const int sw16 = (e.lane >> 1) & 3;
     const int nbox = (ldp + 31) >> 5;
+    // one exp per score: unnormalised probabilities go out as bf16, the row sums go to the P V epilogue
 #pragma unroll 1
     for (int ch = 0; ch < nbox; ++ch) {
       uint32_t v[32];
       tmem_ld32(taddr + (uint32_t)(ch * 32), v);
+      float ev[32];
+      if (ch * 32 + 32 <= nkv) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ev[j] = fast_exp2(fmaf(__uint_as_float(v[j]), scale_log2e, -ms));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          ev[j] = ch * 32 + j < nkv ? fast_exp2(fmaf(__uint_as_float(v[j]), scale_log2e, -ms)) : 0.f;
+      }
       if (e.lane == 0) bulk_wait_read0();
       __syncwarp();
 #pragma unroll
@@ -740,10 +767,9 @@ struct SoftmaxEpi {
         uint32_t pk[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          const int c = ch * 32 + 8 * j + 2 * t;
-          const float a = c < nkv ? exp2f(fmaf(__uint_as_float(v[8 * j + 2 * t]), scale_log2e, -ms)) * inv : 0.f;
-          const float b = c + 1 < nkv ? exp2f(fmaf(__uint_as_float(v[8 * j + 2 * t + 1]), scale_log2e, -ms)) * inv : 0.f;
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(ev[8 * j + 2 * t], ev[8 * j + 2 * t + 1]);
+          // the denominator sums what the P V GEMM will actually multiply
+          sum += __low2float(h2) + __high2float(h2);
           pk[t] = *reinterpret_cast<uint32_t*>(&h2);
         }
         sts128(buf16 + (uint32_t)(e.lane * 64 + ((j ^ sw16) << 4)), pk[0], pk[1], pk[2], pk[3]);
@@ -755,6 +781,7 @@ struct SoftmaxEpi {
         bulk_commit();
       }
     }
+    if (e.lane < e.slab_rows) inv_sum[(long long)e.z * nq + e.row0_in_img + e.lane] = 1.f / sum;
   }
   __device__ __forceinline__ void chunk(State&, const EpiCtx&, long long, bool, int, const uint32_t (&)[32], int) const {}
 };
@@ -1674,7 +1701,7 @@ static int attn_ldp(int nkv) { return (nkv + 7) / 8 * 8; }
 size_t tc_attention_scratch_bytes(int B, int H, int nq, int nkv, int dh) {
   const size_t Z = (size_t)B * H, ldp = attn_ldp(nkv);
   return align_up((size_t)B * nq * H * dh * 2, 256) + align_up((size_t)B * nkv * H * dh * 2, 256) +
-         align_up(Z * dh * ldp * 2, 256) + align_up(Z * nq * ldp * 2, 256) + 1024;
+         align_up(Z * dh * ldp * 2, 256) + align_up(Z * nq * ldp * 2, 256) + align_up(Z * nq * 4, 256) + 1024;
 }
 
 int tc_attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int B, int H, int nq,
@@ -1715,7 +1742,10 @@ int tc_attention_ex(const float* q, const __nv_bfloat16* qh, int ldq, const floa
   }
   __nv_bfloat16* VT16 = ws.take<__nv_bfloat16>((size_t)Z * dh * ldp);
   __nv_bfloat16* P16 = ws.take<__nv_bfloat16>((size_t)Z * nq * ldp);
+  float* inv_sum = ws.take<float>((size_t)Z * nq);
   if (ws.overflow) return set_error(MOCHA_ERR_WORKSPACE, "tc_attention: workspace too small");
+  MOCHA_CHECK_ARG(ldo == H * dh && (ldo % 8) == 0 && ((reinterpret_cast<uintptr_t>(out.f32) | reinterpret_cast<uintptr_t>(out.bf16)) & 15) == 0,
+                  "tc_attention: output must be a dense, 16 B-aligned [B, nq, H*dh] tensor");
   {
     dim3 g((ldp + 31) / 32, (dh + 31) / 32, Z);
     if (vh) transpose_v_bf16_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(vh, ldv, H, nkv, dh, ldp, VT16);
@@ -1741,6 +1771,8 @@ int tc_attention_ex(const float* q, const __nv_bfloat16* qh, int ldq, const floa
     epi.scale_log2e = 1.4426950408889634f / sqrtf((float)dh);
     epi.nkv = nkv;
     epi.ldp = ldp;
+    epi.nq = nq;
+    epi.inv_sum = inv_sum;
     MOCHA_TRY(make_out_tmap(&epi.tmP, P16, (unsigned long long)ldp, (unsigned long long)nq, (unsigned long long)Z,
                             (unsigned long long)ldp, false));
     const int bn = nkv <= 32 ? 32 : nkv <= 64 ? 64 : nkv <= 128 ? 128 : 256;
@@ -1763,7 +1795,10 @@ int tc_attention_ex(const float* q, const __nv_bfloat16* qh, int ldq, const floa
     sh.taps = 1; sh.kb_per_tap = ceil_div(ldp, BLOCK_K); sh.tap_row_stride = 0;
     LinearEpi epi{out.f32, ldo, dh, nullptr, 0, nullptr, ACT_NONE, out.bf16, out.lrelu};
     // out is [B, nq, H*dh] with the head as a column offset: one {ldo, nq, B} map serves every head
-    if (ldo == H * dh) MOCHA_TRY(setup_out_tma(epi, (unsigned long long)nq, (unsigned long long)B, (unsigned long long)ldo));
+    epi.row_scale = inv_sum;
+    epi.rs_rows = nq;
+    MOCHA_TRY(setup_out_tma(epi, (unsigned long long)nq, (unsigned long long)B, (unsigned long long)ldo));
+    if (epi.tma != 1) return set_error(MOCHA_ERR_ARG, "tc_attention: TMA-store epilogue unavailable for the output");
     MOCHA_TRY(dispatch_bn(pick_bn(sh.tiles_m_total, dh), tmA, VT16, (unsigned long long)Z * dh,
                           (unsigned long long)ldp, sh, dh, ceil_div(ldp, BLOCK_K), epi, s));
   }
