@@ -155,6 +155,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// MN-major operand (rows of the tile are K, the MN dimension is contiguous), 128 B swizzle: 64-element
+// MN atoms of [8 K-rows x 128 B]; SBO = 1024 B between 8-row K groups, LBO = bytes between MN atoms.
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32_t atom_stride_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((atom_stride_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
 // fmt: 1 = BF16 (kind::f16), 2 = TF32 (kind::tf32)
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, uint32_t fmt = 1) {
@@ -187,6 +198,9 @@ struct TcShape {
   // rows stay L2-resident while every split streams its B rows past them
   int group_m;
   int splits;
+  // B operand given MN-major: tmB describes [K rows, N cols] (N contiguous) and is loaded as 64 x 64
+  // boxes (attention's P V product reads V in place instead of a transposed copy)
+  int b_mn;
 };
 
 // unit -> (m tile, n split). Within a group of group_m m-tiles the m index runs fastest, so CTAs that
@@ -933,6 +947,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                (int)(a_row0 + (long long)tap * sh.tap_row_stride), Epi::kHintA);
               tma_load_2d_hint(sb, &tmB, &full_bar[stage], b_col0 + kb * KELEMS, (int)(b_row0 + (long long)nt * BN),
                                Epi::kHintB);
+            } else if (sh.b_mn) {
+              tma_load_2d(sa, &tmA, &full_bar[stage], a_col0 + kc * KELEMS,
+                          (int)(a_row0 + (long long)tap * sh.tap_row_stride));
+#pragma unroll
+              for (int a = 0; a < (BN >= 64 ? BN / 64 : 1); ++a)
+                tma_load_2d(sb + a * 8192, &tmB, &full_bar[stage], b_col0 + nt * BN + a * 64, (int)(b_row0 + (long long)kb * BLOCK_K));
             } else {
               tma_load_2d(sa, &tmA, &full_bar[stage], a_col0 + kc * KELEMS,
                           (int)(a_row0 + (long long)tap * sh.tap_row_stride));
@@ -969,12 +989,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #endif
             const uint32_t sa = smem_u32(smem + stage * SM::STAGE_BYTES);
             const uint64_t adesc = make_smem_desc(sa);
-            const uint64_t bdesc = make_smem_desc(sa + A_STAGE_BYTES);
+            if (!Epi::kTf32 && sh.b_mn) {
+              // MN-major B: one MMA consumes 16 K-rows = 2 KB of every 64-column atom
+              const uint64_t bdesc = make_smem_desc_mn(sa + A_STAGE_BYTES, 8192);
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              // advance 32 B (16 bf16) inside the 128 B swizzle atom: +2 in 16 B units
-              if (Epi::kTf32) umma_tf32(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-              else umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(128 * k), idesc | (1u << 16), (kb | k) != 0);
+            } else {
+              const uint64_t bdesc = make_smem_desc(sa + A_STAGE_BYTES);
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                // advance 32 B (16 bf16) inside the 128 B swizzle atom: +2 in 16 B units
+                if (Epi::kTf32) umma_tf32(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                else umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+              }
             }
             umma_commit(&empty_bar[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -1465,7 +1493,7 @@ template <class Epi>
 int dispatch_bn_impl(int bn, const CUtensorMap& tmA, const void* Wptr, unsigned long long wrows, unsigned long long K,
                 TcShape sh, int N, int num_kb, const Epi& epi, cudaStream_t s, unsigned long long wpitch = 0) {
   CUtensorMap tmB;
-  MOCHA_TRY(make_tmap(&tmB, Wptr, wrows, K, bn, wpitch));
+  MOCHA_TRY(make_tmap(&tmB, Wptr, wrows, K, sh.b_mn ? 64 : bn, wpitch));
   sh.tiles_n = ceil_div(N, bn);
   sh.tiles_per_unit = 1;
   sh.units = sh.tiles_m_total * sh.tiles_n;
@@ -1740,13 +1768,14 @@ int tc_attention_ex(const float* q, const __nv_bfloat16* qh, int ldq, const floa
     count_launch();
     K16 = t; pk = inner;
   }
-  __nv_bfloat16* VT16 = ws.take<__nv_bfloat16>((size_t)Z * dh * ldp);
+  const bool v_in_place = vh != nullptr && (ldv % 8) == 0 && (reinterpret_cast<uintptr_t>(vh) & 15) == 0;
+  __nv_bfloat16* VT16 = v_in_place ? nullptr : ws.take<__nv_bfloat16>((size_t)Z * dh * ldp);
   __nv_bfloat16* P16 = ws.take<__nv_bfloat16>((size_t)Z * nq * ldp);
   float* inv_sum = ws.take<float>((size_t)Z * nq);
   if (ws.overflow) return set_error(MOCHA_ERR_WORKSPACE, "tc_attention: workspace too small");
   MOCHA_CHECK_ARG(ldo == H * dh && (ldo % 8) == 0 && ((reinterpret_cast<uintptr_t>(out.f32) | reinterpret_cast<uintptr_t>(out.bf16)) & 15) == 0,
                   "tc_attention: output must be a dense, 16 B-aligned [B, nq, H*dh] tensor");
-  {
+  if (!v_in_place) {
     dim3 g((ldp + 31) / 32, (dh + 31) / 32, Z);
     if (vh) transpose_v_bf16_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(vh, ldv, H, nkv, dh, ldp, VT16);
     else transpose_v_bf16_kernel<float><<<g, 256, 0, s>>>(v, ldv, H, nkv, dh, ldp, VT16);
@@ -1799,8 +1828,16 @@ int tc_attention_ex(const float* q, const __nv_bfloat16* qh, int ldq, const floa
     epi.rs_rows = nq;
     MOCHA_TRY(setup_out_tma(epi, (unsigned long long)nq, (unsigned long long)B, (unsigned long long)ldo));
     if (epi.tma != 1) return set_error(MOCHA_ERR_ARG, "tc_attention: TMA-store epilogue unavailable for the output");
-    MOCHA_TRY(dispatch_bn(pick_bn(sh.tiles_m_total, dh), tmA, VT16, (unsigned long long)Z * dh,
-                          (unsigned long long)ldp, sh, dh, ceil_div(ldp, BLOCK_K), epi, s));
+    if (v_in_place) {
+      // V is read where the projection left it: [B*nkv tokens, H*dh] with the head as a column offset
+      sh.b_mn = 1;
+      sh.b_rows_b = nkv; sh.b_rows_h = 0; sh.b_cols_h = dh;
+      MOCHA_TRY(dispatch_bn(dh >= 256 ? 256 : dh >= 128 ? 128 : 64, tmA, vh, (unsigned long long)B * nkv,
+                            (unsigned long long)inner, sh, dh, ceil_div(ldp, BLOCK_K), epi, s, (unsigned long long)ldv));
+    } else {
+      MOCHA_TRY(dispatch_bn(pick_bn(sh.tiles_m_total, dh), tmA, VT16, (unsigned long long)Z * dh,
+                            (unsigned long long)ldp, sh, dh, ceil_div(ldp, BLOCK_K), epi, s));
+    }
   }
   ws.off = mark;
   return MOCHA_OK;
