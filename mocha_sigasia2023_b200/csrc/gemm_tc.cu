@@ -1992,6 +1992,77 @@ int tc_match_coarse(const __nv_bfloat16* Q16, int nq, const __nv_bfloat16* DB16,
   return launch_tc<BN, MatchEpi<16>>(tmA, tmB, sh, num_kb, MatchEpi<16>{dbnorm, N, cand_score, cand_idx, 2 * splits}, s);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Split-K coarse pass for small problems (few query x row tiles, very long rows): the batched
+// characterization step matches 128 queries against a 385-row DB of 23040-d rows - 4 output tiles,
+// 360 k-blocks each. The K range is cut into slices that run as independent images of the
+// batched-head GEMM (slice z reads columns [z*Ks, (z+1)*Ks) of both operands and writes partial
+// image z), and a reduction kernel forms ||x||^2 - 2 q.x as one candidate list per query.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int slices, int nq, int Np, long long N,
+                                     const float* __restrict__ dbnorm, float* __restrict__ cand_score,
+                                     int32_t* __restrict__ cand_idx) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)nq * Np) return;
+  const int n = (int)(i % Np);
+  float acc = 0.f;
+  const long long img = (long long)nq * Np;
+  for (int z = 0; z < slices; ++z) acc += partial[z * img + i];
+  const bool ok = n < N;
+  cand_score[i] = ok ? fmaf(-2.f, acc, __ldg(dbnorm + n)) : INFINITY;
+  cand_idx[i] = ok ? n : -1;
+}
+}  // namespace
+
+int tc_match_splitk_slices(int nq, long long N, int D) {
+  static const bool off = getenv("MOCHA_NO_SPLITK") != nullptr;
+  if (off || N > 8192 || D % 8 != 0) return 0;
+  const int num_kb = ceil_div(D, BLOCK_K);
+  const long long units0 = (long long)ceil_div(nq, BLOCK_M) * ((N + 127) / 128);
+  if (num_kb < 16 || units0 * 2 > num_sms()) return 0;
+  int slices = (int)((num_sms() + units0 - 1) / units0);
+  if (slices > num_kb / 4) slices = num_kb / 4;
+  if (slices < 2) return 0;
+  const int kb_per = ceil_div(num_kb, slices);
+  return ceil_div(num_kb, kb_per);
+}
+
+size_t tc_match_splitk_ws_bytes(int nq, long long N, int D) {
+  const int slices = tc_match_splitk_slices(nq, N, D);
+  if (!slices) return 0;
+  const size_t Np = (size_t)((N + 127) / 128) * 128;
+  return align_up((size_t)slices * nq * Np * 4, 256) + 256;
+}
+
+// candidate lists: cand_score / cand_idx are [nq, Np] with Np = round_up(N, 128) (index -1 past N)
+int tc_match_coarse_splitk(const __nv_bfloat16* Q16, int nq, const __nv_bfloat16* DB16, const float* dbnorm, long long N,
+                           int D, float* partial, float* cand_score, int32_t* cand_idx, cudaStream_t s) {
+  const int slices = tc_match_splitk_slices(nq, N, D);
+  MOCHA_CHECK_ARG(slices >= 2 && Q16 && DB16 && partial, "tc_match_coarse_splitk: not applicable");
+  constexpr int BN = 128;
+  const int num_kb = ceil_div(D, BLOCK_K), kb_per = ceil_div(num_kb, slices);
+  const int Np = (int)((N + BN - 1) / BN) * BN;
+  CUtensorMap tmA;
+  MOCHA_TRY(make_tmap(&tmA, Q16, (unsigned long long)nq, (unsigned long long)D, BLOCK_M));
+  TcShape sh{};
+  sh.nb = slices; sh.H = slices;
+  sh.rows_out_per_b = nq;
+  sh.tiles_m_per_b = ceil_div(nq, BLOCK_M);
+  sh.tiles_m_total = sh.tiles_m_per_b * slices;
+  sh.src_rows_per_b = 0; sh.a_rows_h = 0; sh.a_cols_h = kb_per * BLOCK_K;
+  sh.b_rows_b = 0; sh.b_rows_h = 0; sh.b_cols_h = kb_per * BLOCK_K;
+  sh.c_img_b = 0; sh.c_img_h = (long long)nq * Np;
+  sh.taps = 1; sh.kb_per_tap = kb_per; sh.tap_row_stride = 0;
+  LinearEpi epi{partial, Np, Np, nullptr, 0, nullptr, ACT_NONE, nullptr, 0};
+  MOCHA_TRY(dispatch_bn(BN, tmA, DB16, (unsigned long long)N, (unsigned long long)D, sh, Np, kb_per, epi, s));
+  const long long total = (long long)nq * Np;
+  splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(partial, slices, nq, Np, N, dbnorm, cand_score, cand_idx);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("splitk_reduce_kernel");
+  return MOCHA_OK;
+}
+
 }  // namespace mocha
 
 #ifdef MOCHA_TRACE

@@ -60,6 +60,11 @@ int tc_attention_ex(const float* q, const __nv_bfloat16* qh, int ldq, const floa
 constexpr int MATCH_KC_MAX = 16;
 // Number of N-splits the coarse pass will use for (nq, N); candidates are [nq, splits, kc].
 int tc_match_splits(int nq, long long N);
+// split-K coarse pass for small problems (0 slices = not applicable); candidates are [nq, round_up(N,128)]
+int tc_match_splitk_slices(int nq, long long N, int D);
+size_t tc_match_splitk_ws_bytes(int nq, long long N, int D);
+int tc_match_coarse_splitk(const __nv_bfloat16* Q16, int nq, const __nv_bfloat16* DB16, const float* dbnorm, long long N,
+                           int D, float* partial, float* cand_score, int32_t* cand_idx, cudaStream_t s);
 // cand_score [nq, splits, kc] fp32 (ascending), cand_idx [nq, splits, kc] int32 (-1 = empty)
 int tc_match_coarse(const __nv_bfloat16* Q16, int nq, const __nv_bfloat16* DB16, const float* dbnorm,
                     long long N, int D, int kc, float* cand_score, int32_t* cand_idx, cudaStream_t s);

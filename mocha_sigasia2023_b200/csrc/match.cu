@@ -305,10 +305,11 @@ extern "C" int mocha_match_exact(const float* Q, int nq, const float* DB, long l
 }
 
 extern "C" size_t mocha_match_tc_workspace_bytes(int nq, long long N, int D, int kc) {
-  (void)D;
   if (nq <= 0 || N <= 0 || kc <= 0) return 0;
   const size_t ncand = (size_t)tc_match_splits(nq, N) * kc;
-  return 2 * (align_up((size_t)nq * ncand * 4, 256)) + 512;
+  const size_t np = (size_t)((N + 127) / 128) * 128;  // split-K path: one candidate per (padded) row
+  const size_t lists = ncand > np ? ncand : np;
+  return 2 * (align_up((size_t)nq * lists * 4, 256)) + tc_match_splitk_ws_bytes(nq, N, D) + 512;
 }
 
 extern "C" int mocha_match_tc(const float* Q, const void* Q16, int nq, const void* DB16, const float* DB32,
@@ -320,6 +321,23 @@ extern "C" int mocha_match_tc(const float* Q, const void* Q16, int nq, const voi
   MOCHA_CHECK_ARG(k >= 1 && k <= kc && kc <= KMAX, "mocha_match_tc: need 1 <= k <= kc <= %d", KMAX);
   MOCHA_CHECK_ARG(k <= N, "mocha_match_tc: k=%d > N=%lld", k, N);
   Workspace ws(workspace, workspace_bytes);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (DB16 && tc_match_splitk_slices(nq, N, D) > 0) {
+    // small problem: K-sliced coarse pass, every row is a candidate of the fp64 re-rank's top-kc merge
+    const size_t np = (size_t)((N + 127) / 128) * 128;
+    float* cs = ws.take<float>((size_t)nq * np);
+    int32_t* ci = ws.take<int32_t>((size_t)nq * np);
+    float* partial = ws.take<float>(tc_match_splitk_ws_bytes(nq, N, D) / 4 - 64);
+    if (ws.overflow)
+      return set_error(MOCHA_ERR_WORKSPACE, "mocha_match_tc: workspace too small (%zu B given, %zu B needed)",
+                       workspace_bytes, ws.off);
+    MOCHA_TRY(tc_match_coarse_splitk((const __nv_bfloat16*)Q16, nq, (const __nv_bfloat16*)DB16, dbnorm, N, D, partial, cs, ci, s));
+    match_rerank_kernel<<<nq, 256, 0, s>>>(Q, (const __nv_bfloat16*)DB16, DB32, D, cs, ci, (int)np, kc, k, index_offset,
+                                           idx, dist);
+    count_launch();
+    MOCHA_LAUNCH_CHECK("match_rerank_kernel");
+    return MOCHA_OK;
+  }
   const int splits = tc_match_splits(nq, N);
   const size_t ncand = (size_t)splits * kc;
   float* cs = ws.take<float>((size_t)nq * ncand);
@@ -327,7 +345,6 @@ extern "C" int mocha_match_tc(const float* Q, const void* Q16, int nq, const voi
   if (ws.overflow)
     return set_error(MOCHA_ERR_WORKSPACE, "mocha_match_tc: workspace too small (%zu B given, %zu B needed)",
                      workspace_bytes, ws.off);
-  cudaStream_t s = (cudaStream_t)stream;
   if (DB16)
     MOCHA_TRY(tc_match_coarse((const __nv_bfloat16*)Q16, nq, (const __nv_bfloat16*)DB16, dbnorm, N, D, kc, cs, ci, s));
   else  // fp32-storage DB: TF32 tensor-core pass straight from the fp32 rows

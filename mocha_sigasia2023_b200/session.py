@@ -131,7 +131,10 @@ class CharacterizationSession:
         wp, wn = self._ws()
         use_tc = t.use_tensor_cores
         if use_tc is None:
-            use_tc = self.B * t.N >= t.TC_THRESHOLD_PAIRS
+            # throughput mode: tensor-core coarse pass + fp64 re-rank (split-K when the DB is small);
+            # parity mode (fp32) keeps the brute-force fp64 kernel unless the problem is large
+            use_tc = self.B * t.N >= t.TC_THRESHOLD_PAIRS or (
+                self.prec == _lib.MOCHA_BF16 and self.B >= 16 and t.D % 8 == 0 and t.D >= 1024)
         if use_tc:
             t._ensure_bf16()
             q16 = self.cnt_nm.to(torch.bfloat16)

@@ -35,7 +35,9 @@ def test_reference_call_pattern():
     assert int(fi) == int(want)
 
 
-@pytest.mark.parametrize("shape", [(4096, 512, 300, 2), (1000, 23040, 130, 1), (777, 192, 5, 3)])
+# the 23040-d cases with few rows take the split-K coarse pass (tc_match_coarse_splitk)
+@pytest.mark.parametrize("shape", [(4096, 512, 300, 2), (1000, 23040, 130, 1), (777, 192, 5, 3), (385, 23040, 128, 2),
+                                   (385, 23040, 1, 1)])
 def test_tensor_core_matcher(shape):
     N, D, nq, k = shape
     rng = np.random.default_rng(N + D)
