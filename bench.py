@@ -31,8 +31,8 @@ UNIT = "frames/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--clips", type=int, default=128, help="clips per GPU (config 4: 1024 clips / 8 GPUs)")
     ap.add_argument("--db-rows", type=int, default=385, help="character DB rows (400-frame character clip)")
@@ -78,17 +78,37 @@ class ClockSampler:
         except Exception:
             self.p = None
 
+    def wait_first_sample(self, timeout_s=3.0):
+        """nvidia-smi needs ~0.1-0.5 s to emit its first line; block until it has, then mark the offset so
+        that only samples taken after this point (the timed region) are reported."""
+        self.skip = 0
+        if self.p is None:
+            return
+        t0 = time.time()
+        while time.time() - t0 < timeout_s:
+            try:
+                if os.path.getsize(self.f.name) > 0:
+                    break
+            except OSError:
+                pass
+            time.sleep(0.02)
+        try:
+            self.skip = os.path.getsize(self.f.name)
+        except OSError:
+            self.skip = 0
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
+        time.sleep(0.03)  # let the sample in flight land
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
         except Exception:
             self.p.kill()
         self.f.flush()
-        self.f.seek(0)
+        self.f.seek(getattr(self, "skip", 0))
         sm, mx, reasons, power = [], [], set(), []
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
@@ -233,9 +253,10 @@ def run_b200(args):
 
     # ---- device-resident throughput ("value") ----
     sampler = ClockSampler(local) if rank == 0 else None
-    barrier()
     if sampler:
         sampler.start()
+        sampler.wait_first_sample()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):

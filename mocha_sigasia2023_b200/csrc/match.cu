@@ -188,23 +188,50 @@ match_rerank_kernel(const float* __restrict__ Q, const __nv_bfloat16* __restrict
     if (id >= 0) local_insert(ls, li, kc, (double)cs[n], (long long)id);
   }
   block_topk_pop<256>(ls, li, kc, od, oi, red_d, red_i, red_t);
-  // exact squared distances of the kc survivors, one warp per candidate
+  // exact squared distances of the kc survivors: the whole block walks one candidate row at a time
+  // (4 consecutive elements per thread, two fp64 accumulators) so the fp64 chains stay short
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* qv = Q + (long long)q * D;
-  for (int c = warp; c < kc; c += 8) {
+  const bool vec4 = (D & 3) == 0 && ((reinterpret_cast<uintptr_t>(qv) & 15) == 0) &&
+                    (DB32 ? (reinterpret_cast<uintptr_t>(DB32) & 15) == 0 : (reinterpret_cast<uintptr_t>(DB16) & 7) == 0);
+  for (int c = 0; c < kc; ++c) {
     const long long id = oi[c];
-    double acc = 0.0;
+    double a0 = 0.0, a1 = 0.0;
     if (id >= 0) {
-      if (DB32) {
+      if (vec4) {
+        for (int d = threadIdx.x * 4; d < D; d += 1024) {
+          const float4 qq = *reinterpret_cast<const float4*>(qv + d);
+          float4 xx;
+          if (DB32) {
+            xx = __ldg(reinterpret_cast<const float4*>(DB32 + id * (long long)D + d));
+          } else {
+            const uint2 raw = __ldg(reinterpret_cast<const uint2*>(DB16 + id * (long long)D + d));
+            const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+            const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+            xx = make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+          }
+          const double e0 = (double)qq.x - (double)xx.x, e1 = (double)qq.y - (double)xx.y;
+          const double e2 = (double)qq.z - (double)xx.z, e3 = (double)qq.w - (double)xx.w;
+          a0 = fma(e0, e0, a0); a1 = fma(e1, e1, a1);
+          a0 = fma(e2, e2, a0); a1 = fma(e3, e3, a1);
+        }
+      } else if (DB32) {
         const float* x = DB32 + id * (long long)D;
-        for (int d = lane; d < D; d += 32) { const double a = (double)qv[d] - (double)x[d]; acc = fma(a, a, acc); }
+        for (int d = threadIdx.x; d < D; d += 256) { const double a = (double)qv[d] - (double)x[d]; a0 = fma(a, a, a0); }
       } else {
         const __nv_bfloat16* x = DB16 + id * (long long)D;
-        for (int d = lane; d < D; d += 32) { const double a = (double)qv[d] - (double)__bfloat162float(x[d]); acc = fma(a, a, acc); }
+        for (int d = threadIdx.x; d < D; d += 256) { const double a = (double)qv[d] - (double)__bfloat162float(x[d]); a0 = fma(a, a, a0); }
       }
     }
-    acc = warp_sum(acc);
-    if (lane == 0) exact[c] = id >= 0 ? acc : INFINITY;
+    double acc = warp_sum(a0 + a1);
+    if (lane == 0) red_d[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += red_d[w];
+      exact[c] = id >= 0 ? t : INFINITY;
+    }
+    __syncthreads();
   }
   __syncthreads();
   if (threadIdx.x == 0) {
