@@ -290,6 +290,7 @@ __device__ __forceinline__ float act_fn(float x) {
 // Debug build only (python -m mocha_sigasia2023_b200.build --trace): per-CTA clock64 time line of the
 // pipeline roles, read back by tools/tc_trace.py. 32 u64 slots per CTA.
 __device__ unsigned long long* g_tc_trace = nullptr;
+__device__ int g_tc_dbg_mode = 0;  // 1: no TMA loads (pure MMA rate), 2: no MMAs (pure fill rate), 3: no epilogue work
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -337,7 +338,9 @@ struct LinearEpiT : LinearEpiData {
   // per warp: 4 KB fp32 box [32][128 B] (128 B-swizzled, 1 KB aligned) + 2 KB bf16 box [32][64 B]
   // (64 B-swizzled) + 4 KB residual box (128 B-swizzled); the LSU path uses a [32][EPI_LD] float
   // transposition buffer
-  static constexpr int kWarpStageBytes = MODE == 2 ? 10240 : MODE == 1 ? 6144 : 5120;
+  // MODE 1 writes one output per launch (the host falls back to MODE 0 otherwise), so its bf16 box
+  // aliases the fp32 box and a fourth operand stage fits beside a 128 x 256 tile's staging
+  static constexpr int kWarpStageBytes = MODE == 2 ? 10240 : MODE == 1 ? 4096 : 5120;
   static constexpr int kStageBytes = EPI_WARPS * kWarpStageBytes;
   static constexpr uint64_t kHintA = 0, kHintB = 0;                // default L2 policy
   static constexpr bool kTf32 = false;
@@ -450,7 +453,9 @@ struct LinearEpiT : LinearEpiData {
   //           back (+ bf16 box), then fence.proxy.async and one elected TMA store per output.
   template <int ACT>
   __device__ __forceinline__ void drain_tma(const EpiCtx& e, int col0, const uint32_t (&v)[32]) const {
-    const uint32_t buf32 = e.stage, buf16 = e.stage + 4096;
+    // bf16 box aliases the fp32 box: rows 16h..16h+15 of the bf16 box cover fp32 rows 8h..8h+7, which
+    // the warp has already read when half h is written back (warp-synchronous, program order)
+    const uint32_t buf32 = e.stage, buf16 = e.stage;
     if (e.lane == 0) bulk_wait_read0();  // the previous chunk's stores have left the staging buffers
     __syncwarp();
 #pragma unroll
@@ -895,6 +900,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef MOCHA_TRACE
   unsigned long long* const trace_buf = g_tc_trace;
+  const int dbg_mode = g_tc_dbg_mode;
   if (threadIdx.x == 0) { TC_TRACE(0, gtimer()); TC_TRACE(1, (unsigned long long)clock64()); }
 #endif
 
@@ -940,6 +946,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * SM::STAGE_BYTES;
             uint8_t* sb = sa + A_STAGE_BYTES;
+#ifdef MOCHA_TRACE
+            if (dbg_mode == 1) {
+              mbar_arrive(&full_bar[stage]);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              continue;
+            }
+#endif
             mbar_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
             const int tap = kb / sh.kb_per_tap, kc = kb - tap * sh.kb_per_tap;
             if (Epi::kHintA != 0) {
@@ -989,6 +1002,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #endif
             const uint32_t sa = smem_u32(smem + stage * SM::STAGE_BYTES);
             const uint64_t adesc = make_smem_desc(sa);
+#ifdef MOCHA_TRACE
+            if (dbg_mode == 2) {
+              mbar_arrive(&empty_bar[stage]);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              continue;
+            }
+#endif
             if (!Epi::kTf32 && sh.b_mn) {
               // MN-major B: one MMA consumes 16 K-rows = 2 KB of every 64-column atom
               const uint64_t bdesc = make_smem_desc_mn(sa + A_STAGE_BYTES, 8192);
@@ -1062,8 +1082,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #endif
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
         if constexpr (Epi::kWholeTile) epi.tile(st, ectx, taddr);
+#ifdef MOCHA_TRACE
+        const int c_stop = dbg_mode == 3 ? c_begin : c_end;
+#else
+        const int c_stop = c_end;
+#endif
 #pragma unroll 1
-        for (int c0 = c_begin; c0 < (Epi::kWholeTile ? c_begin : c_end); c0 += 32) {
+        for (int c0 = c_begin; c0 < (Epi::kWholeTile ? c_begin : c_stop); c0 += 32) {
           uint32_t v[32];
           tmem_ld32(taddr + (uint32_t)c0, v);
 #ifdef MOCHA_TRACE
@@ -1163,32 +1188,51 @@ __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, 
 
 constexpr int M2_BN = 256;                               // pair tile: 256 (M) x 256 (N)
 constexpr int M2_STAGE_BYTES = A_STAGE_BYTES + 128 * BLOCK_K * 2;  // 128 A rows + 128 B rows per CTA
-constexpr int M2_STAGES = 6;
-constexpr int M2_SMEM = M2_STAGES * M2_STAGE_BYTES + 1024 + 256;
+template <int EPI_BYTES>
+struct PairSmem {
+  static constexpr int FIXED = 1024 /*alignment slack*/ + 256 /*barriers*/ + EPI_BYTES;
+  static constexpr int FIT = (SMEM_LIMIT - FIXED) / M2_STAGE_BYTES;
+  static constexpr int STAGES = FIT > 6 ? 6 : FIT;
+  static constexpr int TOTAL = STAGES * M2_STAGE_BYTES + FIXED;
+};
 
-template <int KC>
+// Works on the same TcShape as the 1-CTA kernel with tiles_m_per_b counted in 256-row PAIR tiles
+// (plain / tconv mode; no batched-head mode). CTA `rank` of the pair owns rows [rank*128, +128) of the
+// pair tile and stages B rows [rank*128, +128) of the 256-wide n-tile.
+template <class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
-tc_match2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcShape sh,
-                 const int num_kb, const MatchEpi<KC> epi) {
-  constexpr int STAGES = M2_STAGES;
+tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcShape sh,
+                const int num_kb, const __grid_constant__ Epi epi) {
+  using SM = PairSmem<Epi::kStageBytes>;
+  constexpr int STAGES = SM::STAGES;
   constexpr int BN = M2_BN;
+  constexpr uint64_t kPolA = Epi::kHintA ? Epi::kHintA : L2_EVICT_NORMAL;
+  constexpr uint64_t kPolB = Epi::kHintB ? Epi::kHintB : L2_EVICT_NORMAL;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * M2_STAGE_BYTES);   // used in the leader
+  uint8_t* epi_stage = smem + STAGES * M2_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + Epi::kStageBytes);     // used in the leader
   uint64_t* empty_bar = full_bar + STAGES;                                            // per CTA
   uint64_t* tfull_bar = empty_bar + STAGES;                                           // per CTA [2]
   uint64_t* tempty_bar = tfull_bar + 2;                                               // leader [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_bar = tempty_bar + 2;                                                 // per CTA [EPI_WARPS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + EPI_WARPS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+#ifdef MOCHA_TRACE
+  unsigned long long* const trace_buf = g_tc_trace;
+  if (threadIdx.x == 0) { TC_TRACE(0, gtimer()); TC_TRACE(1, (unsigned long long)clock64()); }
+  int trace_tile = 0;
+#endif
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 2); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 2 * EPI_WARPS); }
+    for (int i = 0; i < EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
@@ -1196,6 +1240,9 @@ tc_match2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+#ifdef MOCHA_TRACE
+  if (threadIdx.x == 0) TC_TRACE(2, (unsigned long long)clock64());
+#endif
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -1204,7 +1251,8 @@ tc_match2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int u = cid; u < sh.units; u += ncl) {
         int mt, split;
         decode_unit(sh, u, mt, split);
-        const int a_row0 = mt * 256 + (int)rank * 128;
+        const int b = mt / sh.tiles_m_per_b, mtb = mt - b * sh.tiles_m_per_b;
+        const long long a_row0 = (long long)b * sh.src_rows_per_b + (long long)mtb * 256 + (int)rank * 128;
         const int nt_end = min(sh.tiles_n, (split + 1) * sh.tiles_per_unit);
         for (int nt = split * sh.tiles_per_unit; nt < nt_end; ++nt) {
           const int b_row0 = nt * BN + (int)rank * 128;
@@ -1213,11 +1261,16 @@ tc_match2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint8_t* sa = smem + stage * M2_STAGE_BYTES;
             uint8_t* sb = sa + A_STAGE_BYTES;
             if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * M2_STAGE_BYTES);
-            tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * BLOCK_K, a_row0, L2_EVICT_LAST);
-            tma_load_2d_pair(sb, &tmB, &full_bar[stage], kb * BLOCK_K, b_row0, L2_EVICT_FIRST);
+            const int tap = kb / sh.kb_per_tap, kc = kb - tap * sh.kb_per_tap;
+            tma_load_2d_pair(sa, &tmA, &full_bar[stage], kc * BLOCK_K, (int)(a_row0 + (long long)tap * sh.tap_row_stride), kPolA);
+            tma_load_2d_pair(sb, &tmB, &full_bar[stage], kb * BLOCK_K, b_row0, kPolB);
             if (rank != 0) mbar_arrive_remote(&full_bar[stage], 0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
+#ifdef MOCHA_TRACE
+          TC_TRACE(4 + trace_tile, (unsigned long long)clock64());
+          if (trace_tile < 3) ++trace_tile;
+#endif
         }
       }
     }
@@ -1238,6 +1291,9 @@ tc_match2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
+#ifdef MOCHA_TRACE
+            if (kb == 0) TC_TRACE(8 + trace_tile, (unsigned long long)clock64());
+#endif
             const uint32_t sa = smem_u32(smem + stage * M2_STAGE_BYTES);
             const uint64_t adesc = make_smem_desc(sa);
             const uint64_t bdesc = make_smem_desc(sa + A_STAGE_BYTES);
@@ -1249,6 +1305,10 @@ tc_match2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           umma_commit_pair(&tfull_bar[as]);
           if (++as == 2) { as = 0; aphase ^= 1; }
+#ifdef MOCHA_TRACE
+          TC_TRACE(12 + trace_tile, (unsigned long long)clock64());
+          if (trace_tile < 3) ++trace_tile;
+#endif
         }
       }
     }
@@ -1256,34 +1316,47 @@ tc_match2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== epilogue (warps 2..9 of both CTAs) =====================
     const int q = warp & 3;
     int as = 0; uint32_t aphase = 0;
-    typename MatchEpi<KC>::State st;
+    typename Epi::State st;
+    epi.kernel_begin(st);
     EpiCtx ectx;
-    ectx.stage = 0; ectx.lane = lane; ectx.half = (warp - 2) >> 2; ectx.c_off = 0;
+    ectx.stage = smem_u32(epi_stage + (warp - 2) * (Epi::kStageBytes / EPI_WARPS));
+    ectx.res_bar = smem_u32(&res_bar[warp - 2]);
+    ectx.lane = lane; ectx.half = (warp - 2) >> 2; ectx.c_off = 0; ectx.col_off = 0;
     for (int u = cid; u < sh.units; u += ncl) {
       int mt, split;
       decode_unit(sh, u, mt, split);
-      const int r_in = mt * 256 + (int)rank * 128 + q * 32 + lane;
-      const bool row_ok = r_in < sh.rows_out_per_b;
-      const long long row = r_in;
-      ectx.slab_row0 = mt * 256 + (int)rank * 128 + q * 32;
-      ectx.slab_rows = max(0, min(32, sh.rows_out_per_b - (int)ectx.slab_row0));
+      const int b = mt / sh.tiles_m_per_b, mtb = mt - b * sh.tiles_m_per_b;
+      const int r0 = mtb * 256 + (int)rank * 128 + q * 32;   // first row of the slab inside its image
+      const bool row_ok = r0 + lane < sh.rows_out_per_b;
+      const long long row = (long long)b * sh.rows_out_per_b + r0 + lane;
+      ectx.slab_row0 = (long long)b * sh.rows_out_per_b + r0;
+      ectx.slab_rows = max(0, min(32, sh.rows_out_per_b - r0));
+      ectx.img = b; ectx.z = b; ectx.row0_in_img = r0;
       epi.unit_begin(st);
       const int nt_end = min(sh.tiles_n, (split + 1) * sh.tiles_per_unit);
       for (int nt = split * sh.tiles_per_unit; nt < nt_end; ++nt) {
+        const int c_begin = ectx.half * (BN / 2), c_end = c_begin + BN / 2;
+        epi.prefetch_res(ectx, nt * BN + c_begin);
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
+#ifdef MOCHA_TRACE
+        if (warp == 2 && lane == 0) TC_TRACE(16 + trace_tile, (unsigned long long)clock64());
+#endif
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-        const int c_begin = ectx.half * (BN / 2), c_end = c_begin + BN / 2;
 #pragma unroll 1
         for (int c0 = c_begin; c0 < c_end; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(taddr + (uint32_t)c0, v);
-          epi.chunk(st, ectx, row, row_ok, nt * BN + c0, v, -1);
+          epi.chunk(st, ectx, row, row_ok, nt * BN + c0, v, c0 + 32 < c_end ? nt * BN + c0 + 32 : -1);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(&tempty_bar[as], 0);
         if (++as == 2) { as = 0; aphase ^= 1; }
+#ifdef MOCHA_TRACE
+        if (warp == 2 && lane == 0) TC_TRACE(20 + trace_tile, (unsigned long long)clock64());
+        if (trace_tile < 3) ++trace_tile;
+#endif
       }
       epi.unit_end(st, ectx, row, row_ok, split);
     }
@@ -1297,6 +1370,9 @@ tc_match2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, 512);
   }
+#ifdef MOCHA_TRACE
+  if (threadIdx.x == 0) { TC_TRACE(24, (unsigned long long)clock64()); TC_TRACE(25, gtimer()); }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1367,10 +1443,12 @@ int setup_out_tma(LinearEpi& epi, unsigned long long rows_per_img, unsigned long
                   ((reinterpret_cast<uintptr_t>(epi.C) | reinterpret_cast<uintptr_t>(epi.C16) |
                     reinterpret_cast<uintptr_t>(epi.res) | reinterpret_cast<uintptr_t>(epi.bias)) & 15) == 0;
   if (!ok) return MOCHA_OK;
+  const bool with_res = epi.res && epi.bias_period == 0;
+  if (epi.C && epi.C16 && !with_res) return MOCHA_OK;  // two outputs without a residual: LSU epilogue
   if (epi.C) MOCHA_TRY(make_out_tmap(&epi.tmC, epi.C, cols, rows_per_img, imgs, (unsigned long long)epi.ldc, true));
   if (epi.C16) MOCHA_TRY(make_out_tmap(&epi.tmC16, epi.C16, cols, rows_per_img, imgs, (unsigned long long)epi.ldc, false));
   epi.tma = 1;
-  if (epi.res && epi.bias_period == 0) {
+  if (with_res) {
     MOCHA_TRY(make_out_tmap(&epi.tmR, epi.res, cols, rows_per_img, imgs, (unsigned long long)epi.ldc, true));
     epi.tma = 2;
   }
@@ -1402,6 +1480,29 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcShape& sh,
   count_launch();
   MOCHA_LAUNCH_CHECK("tc_gemm_kernel");
   return MOCHA_OK;
+}
+
+template <class Epi>
+int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcShape& sh, int num_kb, const Epi& epi,
+                cudaStream_t s) {
+  using SM = PairSmem<Epi::kStageBytes>;
+  static bool configured = false;
+  if (!configured) {
+    MOCHA_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    configured = true;
+  }
+  int grid = 2 * sh.units;
+  const int cap = num_sms() & ~1;
+  if (grid > cap) grid = cap;
+  tc_gemm2_kernel<Epi><<<grid, TC_THREADS, SM::TOTAL, s>>>(tmA, tmB, sh, num_kb, epi);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("tc_gemm2_kernel");
+  return MOCHA_OK;
+}
+template <int KC>
+int launch_match2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcShape& sh, int num_kb, const MatchEpi<KC>& epi,
+                  cudaStream_t s) {
+  return launch_pair(tmA, tmB, sh, num_kb, epi, s);
 }
 
 __global__ void cast_act_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n,
@@ -1637,6 +1738,26 @@ int tc_tconv_ex(const float* X, const __nv_bfloat16* Xh, const float* W, const f
   LinearEpi epi{out.f32, Cout, Cout, bias, bias_period, nullptr, ACT_NONE, out.bf16, out.lrelu};
   MOCHA_TRY(setup_out_tma(epi, (unsigned long long)T * V, (unsigned long long)B));
   int rc = MOCHA_OK;
+  // long-K, wide-N convolutions are bound by the shared-memory fill rate (~64 B/clk/SM) with 128 x 256
+  // tiles: a CTA pair (cta_group::2) stages half of the weight rows each and runs 256 x 256 tiles
+  static const bool no_pair = getenv("MOCHA_NO_PAIR_GEMM") != nullptr;
+  const int pair_tiles = ceil_div(T * V, 256) * B;
+  if (!no_pair && epi.tma == 1 && Cout % 256 == 0 && taps * sh.kb_per_tap >= 8 && pair_tiles >= num_sms() / 2) {
+    CUtensorMap tmB;
+    MOCHA_TRY(make_tmap(&tmB, W16, (unsigned long long)Cout, (unsigned long long)taps * Cin, 128));
+    TcShape sp = sh;
+    sp.tiles_m_per_b = ceil_div(T * V, 256);
+    sp.tiles_m_total = sp.tiles_m_per_b * B;
+    sp.tiles_n = Cout / 256;
+    sp.tiles_per_unit = 1;
+    sp.units = sp.tiles_m_total * sp.tiles_n;
+    sp.splits = sp.tiles_n;
+    sp.group_m = 0;
+    for (int it = 0; it < (repeat < 1 ? 1 : repeat) && rc == MOCHA_OK; ++it)
+      rc = launch_pair(tmA, tmB, sp, taps * sh.kb_per_tap, LinearEpiT<1>{epi}, s);
+    ws.off = mark;
+    return rc;
+  }
   for (int it = 0; it < (repeat < 1 ? 1 : repeat) && rc == MOCHA_OK; ++it)  // repeat > 1: bench.py roofline pass
     rc = dispatch_bn(pick_bn(sh.tiles_m_total, Cout), tmA, W16, (unsigned long long)Cout,
                      (unsigned long long)taps * Cin, sh, Cout, taps * sh.kb_per_tap, epi, s);
@@ -1856,25 +1977,6 @@ int tc_match_splits(int nq, long long N) {
   return (int)splits * 2;  // x2: the two column halves of a tile keep separate lists
 }
 
-namespace {
-template <int KC>
-int launch_match2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcShape& sh, int num_kb, const MatchEpi<KC>& epi,
-                  cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    MOCHA_CUDA(cudaFuncSetAttribute(tc_match2_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, M2_SMEM));
-    configured = true;
-  }
-  int grid = 2 * sh.units;
-  const int cap = num_sms() & ~1;
-  if (grid > cap) grid = cap;
-  tc_match2_kernel<KC><<<grid, TC_THREADS, M2_SMEM, s>>>(tmA, tmB, sh, num_kb, epi);
-  count_launch();
-  MOCHA_LAUNCH_CHECK("tc_match2_kernel");
-  return MOCHA_OK;
-}
-}  // namespace
-
 // 2-CTA (cta_group::2) variant of the coarse pass: 256 x 256 pair tiles
 int tc_match_coarse_pair(const __nv_bfloat16* Q16, int nq, const __nv_bfloat16* DB16, const float* dbnorm, long long N,
                          int D, int kc, float* cand_score, int32_t* cand_idx, cudaStream_t s) {
@@ -2068,6 +2170,9 @@ int tc_match_coarse_splitk(const __nv_bfloat16* Q16, int nq, const __nv_bfloat16
 #ifdef MOCHA_TRACE
 extern "C" int mocha_debug_get_epi(unsigned long long* host16) {
   return cudaMemcpyFromSymbol(host16, mocha::g_epi_dbg, 16 * sizeof(unsigned long long)) == cudaSuccess ? 0 : 1;
+}
+extern "C" int mocha_debug_set_mode(int mode) {
+  return cudaMemcpyToSymbol(mocha::g_tc_dbg_mode, &mode, sizeof(mode)) == cudaSuccess ? 0 : 1;
 }
 extern "C" int mocha_debug_set_trace(unsigned long long* buf) {
   return cudaMemcpyToSymbol(mocha::g_tc_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : 1;

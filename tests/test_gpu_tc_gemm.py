@@ -72,3 +72,28 @@ def test_tcgen05_linear(M, N, K, act):
     want = torch_ref(A.to(torch.bfloat16).float(), W16.float(), b, r, act)
     err = (out.double() - want).abs().max() / want.abs().max()
     assert err < 2e-5, err
+
+
+@pytest.mark.parametrize("B", [2, 16])
+def test_tconv_pair_kernel_vs_fp32_path(B):
+    """JointBlock temporal conv through mocha_bench_tconv: B=16 gives 96 pair tiles, enough for the 2-CTA
+    (cta_group::2) kernel; B=2 stays on the 1-CTA kernel. Both must agree with the fp32 SIMT path on
+    bf16-rounded inputs (weights are bf16-rounded by the tensor-core path: tolerance 2e-2 of the range)."""
+    from mocha_sigasia2023_b200 import packing, weights
+    lib = _lib.load()
+    pk = packing.PackedGenerator(weights.generator_state_dict(1777), weights.DEFAULT_MODEL_CFG, torch.device("cuda"))
+    d = pk.struct.dims
+    rows = B * d.T * d.V
+    g = torch.Generator(device="cuda").manual_seed(B)
+    x = torch.randn((rows, d.D), generator=g, device="cuda").to(torch.bfloat16).float()
+    ws = torch.empty(lib.mocha_embed_workspace_bytes(C.byref(d), B), dtype=torch.uint8, device="cuda")
+    outs = []
+    for prec in (_lib.MOCHA_FP32, _lib.MOCHA_BF16):
+        out = torch.full((rows, d.D), float("nan"), device="cuda")
+        _lib.check(lib.mocha_bench_tconv(C.byref(pk.struct), _lib.ptr(x), B, _lib.ptr(out), prec, 1, _lib.ptr(ws), ws.numel(),
+                                         _lib.stream_ptr()), "mocha_bench_tconv")
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert torch.isfinite(outs[1]).all()
+    err = (outs[1] - outs[0]).abs().max() / outs[0].abs().max()
+    assert err < 2e-2, err
