@@ -294,7 +294,7 @@ extern "C" size_t mocha_to_mot_workspace_bytes(const mocha_dims* d, int B) {
   bytes += pad256(R2 * d->Kj * d->C0 * 4);                // y3
   bytes += pad256((size_t)B * (d->T / d->tp) * d->V * d->C0 * 4);  // g'
   bytes += pad256(R * d->C0 * 4);                         // y4
-  bytes += pad256(R * d->Cin * 4);                        // Ytil when the caller only wants Y
+  bytes += pad256(R * ((d->Cin + 7) / 8 * 8) * 4);        // Ytil (rows padded to 8 floats on the bf16 path)
   bytes += tc_scratch_bytes(R2, d->Kb * d->D);
   bytes += tc_tconv_scratch_bytes(B, d->T / d->tp, d->P, d->D, d->taps_b);
   bytes += tc_tconv_scratch_bytes(B, d->T, d->V, d->C0, d->taps_j);

@@ -55,7 +55,6 @@ int embed_bf16(const mocha_generator_weights* w, const float* X, int B, float* t
   const mocha_dims& d = w->dims;
   Tc tc{s, ws};
   const int R = B * d.T * d.V, Tp = d.T / d.tp, R2 = B * Tp * d.P;
-  float* h0 = ws.take<float>((size_t)R * d.C0);
   bf16* agg = ws.take<bf16>((size_t)R * d.Kj * d.C0);
   bf16* g = ws.take<bf16>((size_t)R * d.D);
   float* h1 = ws.take<float>((size_t)R * d.D);
@@ -63,15 +62,8 @@ int embed_bf16(const mocha_generator_weights* w, const float* X, int B, float* t
   bf16* agg2 = ws.take<bf16>((size_t)R2 * d.Kb * d.D);
   bf16* g2 = ws.take<bf16>((size_t)R2 * d.D);
   WS_OK(ws, "mocha_embed_fwd(bf16)");
-  // Conv2d 1x1 Cin(15)->C0: K is too short for a TMA row; stays on the fp32 kernel
-  {
-    GemmParams p;
-    p.A = X; p.W = w->emb_w; p.C = h0;
-    p.M = R; p.N = d.C0; p.K = d.Cin; p.lda = d.Cin; p.ldw = d.Cin; p.ldc = d.C0;
-    p.bias = w->emb_b;
-    MOCHA_TRY(gemm_f32(p, s));
-  }
-  MOCHA_TRY(graph_agg_first(h0, w->A_j, nullptr, B * d.T, d.V, d.C0, d.Kj, 1, s, agg));
+  // Conv2d 1x1 Cin(15)->C0 + LeakyReLU + graph aggregation in one kernel (K = 15 is too short for a TMA row)
+  MOCHA_TRY(embed_graph_agg(X, w->emb_w, w->emb_b, w->A_j, agg, B * d.T, d.V, d.Cin, d.C0, d.Kj, s));
   MOCHA_TRY(tc.lin(agg, d.Kj * d.C0, w->jb_gcn_w, w->jb_gcn_bias2d, d.V, nullptr, h16(g), R, d.D, d.Kj * d.C0, ACT_NONE));
   MOCHA_TRY(tc_tconv_ex(nullptr, g, w->jb_tcn_w, w->jb_tcn_b, 0, f32(h1), B, d.T, d.V, d.D, d.D, d.taps_j, 1, ws, s));
   MOCHA_TRY(pool_joint_body(h1, w->pool_w, pooled, B, d.T, d.V, d.P, d.D, d.tp, s));
@@ -179,9 +171,11 @@ int to_mot_bf16(const mocha_generator_weights* w, const float* tokens, int B, fl
   float* y3 = ws.take<float>((size_t)R2 * d.Kj * d.C0);
   float* gp = ws.take<float>((size_t)B * Tp * d.V * d.C0);
   bf16* y4 = ws.take<bf16>((size_t)R * d.C0);
-  float* ytil_ws = Ytil ? nullptr : ws.take<float>((size_t)R * d.Cin);
+  // the 64 -> Cin(15) output conv writes rows padded to 16 floats so that its epilogue can use TMA stores;
+  // the de-normalisation pass below reads the padded rows and emits the dense tensors
+  const int Cp = (d.Cin + 7) / 8 * 8;
+  float* ytp = ws.take<float>((size_t)R * Cp);
   WS_OK(ws, "mocha_to_mot_fwd(bf16)");
-  float* yt = Ytil ? Ytil : ytil_ws;
   MOCHA_TRY(graph_agg_first(tokens, w->tm_A_b, nullptr, B * Tp, d.P, d.D, d.Kb, 1, s, agg));
   MOCHA_TRY(tc.lin(agg, d.Kb * d.D, w->tm_bb_gcn_w, w->tm_bb_gcn_bias2d, d.P, nullptr, h16(y1), R2, d.D, d.Kb * d.D, ACT_NONE));
   // the two consumers below are pre-activation blocks: their bf16 operand is stored through LeakyReLU
@@ -189,8 +183,8 @@ int to_mot_bf16(const mocha_generator_weights* w, const float* tokens, int B, fl
   MOCHA_TRY(tc.lin(y2, d.D, w->tm_jb_gcn_w, w->tm_jb_gcn_b, 0, nullptr, f32(y3), R2, d.Kj * d.C0, d.D, ACT_NONE));
   MOCHA_TRY(graph_agg_kv(y3, w->tm_A2, gp, B * Tp, d.P, d.V, d.C0, d.Kj, s));
   MOCHA_TRY(tc_tconv_ex(gp, nullptr, w->tm_jb_tcn_w, w->tm_jb_tcn_b, 0, h16(y4, 1), B, d.T, d.V, d.C0, d.C0, d.taps_j, d.tp, ws, s));
-  MOCHA_TRY(tc.lin(y4, d.C0, w->tm_out_w, w->tm_out_b, 0, nullptr, f32(yt), R, d.Cin, d.C0, ACT_NONE));
-  if (Y) MOCHA_TRY(affine_rows(yt, Y_mean, Y_std, Y, R, d.Cin, d.V, s));
+  MOCHA_TRY(tc.lin(y4, d.C0, w->tm_out_w, w->tm_out_b, 0, nullptr, f32(ytp), R, Cp, d.C0, ACT_NONE));
+  if (Y || Ytil) MOCHA_TRY(affine_rows(ytp, Y_mean, Y_std, Y, R, d.Cin, d.V, s, Cp, Ytil));
   return MOCHA_OK;
 }
 

@@ -50,6 +50,72 @@ __global__ void graph_agg_first_kernel(const float* __restrict__ in, const float
   }
 }
 
+// Fused front of mot_embedding's JointBlock for the tensor-core path (model.py:42-44, blocks.py:125-129):
+//   h0 = Conv2d 1x1 (Cin -> C0) of the pose window, LeakyReLU(0.2), graph aggregation with the sparse
+//   adjacency -> bf16 operand [BT*V, Kk*C0] of the 1x1 graph convolution GEMM.
+// One block owns G consecutive frames: the adjacency lists, the 1x1 weights and the G x V x Cin inputs
+// are staged once, h0 never leaves shared memory (saves a 2 x 47 MB round trip per 128 clips).
+template <int G>
+__global__ void __launch_bounds__(256)
+embed_graph_agg_kernel(const float* __restrict__ X, const float* __restrict__ Wemb, const float* __restrict__ bemb,
+                       const float* __restrict__ A, __nv_bfloat16* __restrict__ out16, int BT, int V, int Cin, int C,
+                       int Kk) {
+  extern __shared__ float sm[];
+  float* xs = sm;                                     // [G][V][C]   activated h0
+  float* xin = xs + G * V * C;                        // [G][V][Cin] raw inputs
+  float* wt = xin + G * V * Cin;                      // [Cin][C]    transposed 1x1 weights
+  float* val = wt + Cin * C;                          // [Kk*V][V]   non-zero adjacency values
+  int* src = reinterpret_cast<int*>(val + Kk * V * V);  // [Kk*V][V] their source nodes
+  int* cnt = src + Kk * V * V;                        // [Kk*V]
+  const int bt0 = blockIdx.x * G;
+  const int g_live = min(G, BT - bt0);
+  for (int i = threadIdx.x; i < g_live * V * Cin; i += blockDim.x) xin[i] = X[(long long)bt0 * V * Cin + i];
+  for (int i = threadIdx.x; i < C * Cin; i += blockDim.x) {
+    const int c = i / Cin, k = i - c * Cin;
+    wt[k * C + c] = Wemb[i];
+  }
+  for (int kw = threadIdx.x; kw < Kk * V; kw += blockDim.x) {
+    const int k = kw / V, w = kw - k * V;
+    int n = 0;
+    for (int u = 0; u < V; ++u) {
+      const float a = A[(k * V + u) * V + w];
+      if (a != 0.f) { val[kw * V + n] = a; src[kw * V + n] = u; ++n; }
+    }
+    cnt[kw] = n;
+  }
+  __syncthreads();
+  // h0 = lrelu(x W^T + b): thread -> channel c (fastest) and a row stripe
+  {
+    const int c = threadIdx.x % C, stripe = threadIdx.x / C, nstripes = blockDim.x / C;
+    const float b = bemb ? bemb[c] : 0.f;
+    if (stripe < nstripes)
+      for (int r = stripe; r < g_live * V; r += nstripes) {
+        float acc = b;
+        for (int k = 0; k < Cin; ++k) acc = fmaf(xin[r * Cin + k], wt[k * C + c], acc);
+        xs[r * C + c] = lrelu02(acc);
+      }
+  }
+  __syncthreads();
+  // aggregation: thread -> channel pair (bf162 stores, 128 B per 32 lanes) and a (frame, node, k) stripe
+  const int KC = Kk * C, half = C / 2;
+  const int cp = threadIdx.x % half, stripe = threadIdx.x / half, nstripes = blockDim.x / half;
+  for (int item = stripe; item < g_live * V * Kk; item += nstripes) {
+    const int g = item / (V * Kk), rem = item - g * V * Kk;
+    const int w = rem / Kk, k = rem - w * Kk;
+    const int kw = k * V + w, n = cnt[kw];
+    const float* xg = xs + g * V * C;
+    float a0 = 0.f, a1 = 0.f;
+    for (int i = 0; i < n; ++i) {
+      const float2 x2 = *reinterpret_cast<const float2*>(xg + src[kw * V + i] * C + 2 * cp);
+      const float av = val[kw * V + i];
+      a0 = fmaf(x2.x, av, a0);
+      a1 = fmaf(x2.y, av, a1);
+    }
+    *reinterpret_cast<__nv_bfloat162*>(out16 + ((long long)(bt0 + g) * V + w) * KC + k * C + 2 * cp) =
+        __floats2bfloat162_rn(a0, a1);
+  }
+}
+
 __global__ void graph_agg_kv_kernel(const float* __restrict__ in, const float* __restrict__ A2,
                                     float* __restrict__ out, int U, int Wn, int C, int Kk) {
   extern __shared__ float sm[];
@@ -292,11 +358,14 @@ __global__ void cvae_condition_kernel(const float* __restrict__ src_cnt, const f
 
 __global__ void affine_rows_kernel(const float* __restrict__ x, const float* __restrict__ mu,
                                    const float* __restrict__ sd, float* __restrict__ out, long long total,
-                                   int C, int period) {
+                                   int C, int period, int ld_in, float* __restrict__ copy) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const long long o = i % ((long long)period * C);
-  out[i] = x[i] * sd[o] + mu[o];
+  const long long r = i / C;
+  const float v = x[r * ld_in + (i - r * C)];
+  if (out) out[i] = v * sd[o] + mu[o];
+  if (copy) copy[i] = v;
 }
 
 __global__ void broadcast_rows_kernel(const float* __restrict__ x, float* __restrict__ out,
@@ -356,6 +425,25 @@ int graph_agg_first(const float* in, const float* A, float* out, int BT, int V, 
   graph_agg_first_kernel<<<BT, 256, smem, s>>>(in, A, out, out16, V, C, Kk, lrelu);
   count_launch();
   MOCHA_LAUNCH_CHECK("graph_agg_first");
+  return MOCHA_OK;
+}
+
+int embed_graph_agg(const float* X, const float* Wemb, const float* bemb, const float* A, __nv_bfloat16* out16, int BT,
+                    int V, int Cin, int C, int Kk, cudaStream_t s) {
+  MOCHA_CHECK_ARG(X && Wemb && A && out16 && BT > 0 && V > 0 && Cin > 0 && Kk > 0, "embed_graph_agg: bad args");
+  MOCHA_CHECK_ARG(C >= 2 && C <= 256 && (C & 1) == 0 && 256 % C == 0, "embed_graph_agg: C=%d unsupported", C);
+  constexpr int G = 4;
+  const size_t smem = (size_t)(G * V * C + G * V * Cin + Cin * C + 2 * Kk * V * V + Kk * V) * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    MOCHA_CHECK_ARG(smem <= 200 * 1024, "embed_graph_agg: tile too large (%zu B)", smem);
+    if (smem > 48 * 1024)
+      MOCHA_CUDA(cudaFuncSetAttribute(embed_graph_agg_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  embed_graph_agg_kernel<G><<<(BT + G - 1) / G, 256, smem, s>>>(X, Wemb, bemb, A, out16, BT, V, Cin, C, Kk);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("embed_graph_agg");
   return MOCHA_OK;
 }
 
@@ -459,10 +547,10 @@ int cvae_condition(const float* src_cnt, const float* prev, const float* m0, con
 }
 
 int affine_rows(const float* x, const float* mu, const float* sd, float* out, long long rows, int C, int period,
-                cudaStream_t s) {
-  MOCHA_CHECK_ARG(x && mu && sd && out && rows > 0 && C > 0 && period > 0, "affine_rows: bad args");
+                cudaStream_t s, int ld_in, float* copy) {
+  MOCHA_CHECK_ARG(x && (copy || (mu && sd && out)) && rows > 0 && C > 0 && period > 0, "affine_rows: bad args");
   const long long total = rows * C;
-  affine_rows_kernel<<<blocks_for(total, 256), 256, 0, s>>>(x, mu, sd, out, total, C, period);
+  affine_rows_kernel<<<blocks_for(total, 256), 256, 0, s>>>(x, mu, sd, out, total, C, period, ld_in > 0 ? ld_in : C, copy);
   count_launch();
   MOCHA_LAUNCH_CHECK("affine_rows");
   return MOCHA_OK;

@@ -13,6 +13,11 @@ namespace mocha {
 int graph_agg_first(const float* in, const float* A, float* out, int BT, int V, int C, int Kk,
                     int lrelu, cudaStream_t s, __nv_bfloat16* out16 = nullptr);
 
+// Fused Conv2d 1x1 (Cin -> C) + LeakyReLU + graph aggregation of the tensor-core path:
+// out16[(bt,w), k*C + c] = sum_u lrelu(X[(bt,u), :] . Wemb[c, :] + bemb[c]) * A[k,u,w]
+int embed_graph_agg(const float* X, const float* Wemb, const float* bemb, const float* A, __nv_bfloat16* out16, int BT,
+                    int V, int Cin, int C, int Kk, cudaStream_t s);
+
 // out[(bt,w), c] = sum_k sum_u in[(bt,u), k*C + c] * A2[k,u,w]   (U input nodes, Wn output nodes)
 // Same einsum applied after the 1x1 convolution (used by to_mot's JointBlock, where the
 // body-part -> joint un-pooling is folded into A2 on the host).
@@ -55,8 +60,9 @@ int cvae_memory(const float* prior_out, int prior_tokens, const float* eps, cons
 int cvae_condition(const float* src_cnt, const float* prev, const float* m0, const float* s0, const float* m1,
                    const float* s1, float* cond, int B, int n, int C, cudaStream_t s);
 // out[r, c] = x[r, c] * sd[(r % period), c] + mu[(r % period), c]
+// x may be a padded view (row pitch ld_in >= C); `copy` optionally receives the dense [rows, C] copy of x
 int affine_rows(const float* x, const float* mu, const float* sd, float* out, long long rows, int C, int period,
-                cudaStream_t s);
+                cudaStream_t s, int ld_in = 0, float* copy = nullptr);
 // out[b, n, c] = x[n, c]  (broadcast a table over the batch)
 int broadcast_rows(const float* x, float* out, int B, long long n_elems, cudaStream_t s,
                    __nv_bfloat16* out16 = nullptr);
