@@ -57,17 +57,16 @@ int embed_bf16(const mocha_generator_weights* w, const float* X, int B, float* t
   const int R = B * d.T * d.V, Tp = d.T / d.tp, R2 = B * Tp * d.P;
   bf16* agg = ws.take<bf16>((size_t)R * d.Kj * d.C0);
   bf16* g = ws.take<bf16>((size_t)R * d.D);
-  float* h1 = ws.take<float>((size_t)R * d.D);
-  float* pooled = ws.take<float>((size_t)R2 * d.D);
+  bf16* h1 = ws.take<bf16>((size_t)R * d.D);
   bf16* agg2 = ws.take<bf16>((size_t)R2 * d.Kb * d.D);
   bf16* g2 = ws.take<bf16>((size_t)R2 * d.D);
   WS_OK(ws, "mocha_embed_fwd(bf16)");
   // Conv2d 1x1 Cin(15)->C0 + LeakyReLU + graph aggregation in one kernel (K = 15 is too short for a TMA row)
   MOCHA_TRY(embed_graph_agg(X, w->emb_w, w->emb_b, w->A_j, agg, B * d.T, d.V, d.Cin, d.C0, d.Kj, s));
   MOCHA_TRY(tc.lin(agg, d.Kj * d.C0, w->jb_gcn_w, w->jb_gcn_bias2d, d.V, nullptr, h16(g), R, d.D, d.Kj * d.C0, ACT_NONE));
-  MOCHA_TRY(tc_tconv_ex(nullptr, g, w->jb_tcn_w, w->jb_tcn_b, 0, f32(h1), B, d.T, d.V, d.D, d.D, d.taps_j, 1, ws, s));
-  MOCHA_TRY(pool_joint_body(h1, w->pool_w, pooled, B, d.T, d.V, d.P, d.D, d.tp, s));
-  MOCHA_TRY(graph_agg_first(pooled, w->A_b, nullptr, B * Tp, d.P, d.D, d.Kb, 1, s, agg2));
+  MOCHA_TRY(tc_tconv_ex(nullptr, g, w->jb_tcn_w, w->jb_tcn_b, 0, h16(h1), B, d.T, d.V, d.D, d.D, d.taps_j, 1, ws, s));
+  // joint -> body-part pooling + the BodyBlock's LeakyReLU and graph aggregation in one pass over h1
+  MOCHA_TRY(pool_graph_agg(h1, w->pool_w, w->A_b, agg2, B, d.T, d.V, d.P, d.D, d.tp, d.Kb, s));
   MOCHA_TRY(tc.lin(agg2, d.Kb * d.D, w->bb_gcn_w, w->bb_gcn_bias2d, d.P, nullptr, h16(g2), R2, d.D, d.Kb * d.D, ACT_NONE));
   if (add_pos_emb)
     return tc_tconv_ex(nullptr, g2, w->bb_tcn_w, w->tok_bias_pos, Tp * d.P, f32(tokens), B, Tp, d.P, d.D, d.D, d.taps_b, 1, ws, s);

@@ -55,64 +55,96 @@ __global__ void graph_agg_first_kernel(const float* __restrict__ in, const float
 //   adjacency -> bf16 operand [BT*V, Kk*C0] of the 1x1 graph convolution GEMM.
 // One block owns G consecutive frames: the adjacency lists, the 1x1 weights and the G x V x Cin inputs
 // are staged once, h0 never leaves shared memory (saves a 2 x 47 MB round trip per 128 clips).
+constexpr int EMB_MAXCIN = 16;
 template <int G>
 __global__ void __launch_bounds__(256)
 embed_graph_agg_kernel(const float* __restrict__ X, const float* __restrict__ Wemb, const float* __restrict__ bemb,
                        const float* __restrict__ A, __nv_bfloat16* __restrict__ out16, int BT, int V, int Cin, int C,
                        int Kk) {
   extern __shared__ float sm[];
-  float* xs = sm;                                     // [G][V][C]   activated h0
-  float* xin = xs + G * V * C;                        // [G][V][Cin] raw inputs
-  float* wt = xin + G * V * Cin;                      // [Cin][C]    transposed 1x1 weights
-  float* val = wt + Cin * C;                          // [Kk*V][V]   non-zero adjacency values
+  float* xs = sm;                                     // [G*V][C]   activated h0
+  float* xin = xs + G * V * C;                        // [G*V][16]  raw inputs, rows padded to 16 floats
+  float* val = xin + G * V * EMB_MAXCIN;              // [Kk*V][V]  non-zero adjacency values
   int* src = reinterpret_cast<int*>(val + Kk * V * V);  // [Kk*V][V] their source nodes
   int* cnt = src + Kk * V * V;                        // [Kk*V]
+  __shared__ int nmax_s;
   const int bt0 = blockIdx.x * G;
-  const int g_live = min(G, BT - bt0);
-  for (int i = threadIdx.x; i < g_live * V * Cin; i += blockDim.x) xin[i] = X[(long long)bt0 * V * Cin + i];
-  for (int i = threadIdx.x; i < C * Cin; i += blockDim.x) {
-    const int c = i / Cin, k = i - c * Cin;
-    wt[k * C + c] = Wemb[i];
+  const int rows = min(G, BT - bt0) * V;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) nmax_s = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < rows * EMB_MAXCIN; i += blockDim.x) {
+    const int r = i / EMB_MAXCIN, k = i - r * EMB_MAXCIN;
+    xin[i] = k < Cin ? X[((long long)bt0 * V + r) * Cin + k] : 0.f;
   }
-  for (int kw = threadIdx.x; kw < Kk * V; kw += blockDim.x) {
+  // compact neighbour lists, one warp per (k, w): ballot keeps the sources in ascending order
+  for (int kw = warp; kw < Kk * V; kw += 8) {
     const int k = kw / V, w = kw - k * V;
     int n = 0;
-    for (int u = 0; u < V; ++u) {
-      const float a = A[(k * V + u) * V + w];
-      if (a != 0.f) { val[kw * V + n] = a; src[kw * V + n] = u; ++n; }
+    for (int u0 = 0; u0 < V; u0 += 32) {
+      const int u = u0 + lane;
+      const float a = u < V ? A[(k * V + u) * V + w] : 0.f;
+      const unsigned m = __ballot_sync(0xffffffffu, a != 0.f);
+      if (a != 0.f) {
+        const int pos = n + __popc(m & ((1u << lane) - 1u));
+        val[kw * V + pos] = a; src[kw * V + pos] = u;
+      }
+      n += __popc(m);
     }
-    cnt[kw] = n;
+    // pad the list with zero-weight entries so that every list can be walked with one uniform, unrolled
+    // trip count (independent loads instead of a dependent index -> value chain per neighbour)
+    for (int i = n + lane; i < V; i += 32) { val[kw * V + i] = 0.f; src[kw * V + i] = 0; }
+    if (lane == 0) { cnt[kw] = n; atomicMax(&nmax_s, n); }
   }
   __syncthreads();
-  // h0 = lrelu(x W^T + b): thread -> channel c (fastest) and a row stripe
+  const int nmax4 = min(V, (nmax_s + 3) & ~3);
+  // h0 = lrelu(x W^T + b): thread = channel c with its Cin weights in registers, rows striped over the block
   {
     const int c = threadIdx.x % C, stripe = threadIdx.x / C, nstripes = blockDim.x / C;
+    float wr[EMB_MAXCIN];
+#pragma unroll
+    for (int k = 0; k < EMB_MAXCIN; ++k) wr[k] = k < Cin ? Wemb[c * Cin + k] : 0.f;
     const float b = bemb ? bemb[c] : 0.f;
     if (stripe < nstripes)
-      for (int r = stripe; r < g_live * V; r += nstripes) {
+#pragma unroll 4
+      for (int r = stripe; r < rows; r += nstripes) {
+        const float4* xr = reinterpret_cast<const float4*>(xin + r * EMB_MAXCIN);
         float acc = b;
-        for (int k = 0; k < Cin; ++k) acc = fmaf(xin[r * Cin + k], wt[k * C + c], acc);
+#pragma unroll
+        for (int k4 = 0; k4 < EMB_MAXCIN / 4; ++k4) {
+          const float4 x4 = xr[k4];
+          acc = fmaf(x4.x, wr[4 * k4], acc); acc = fmaf(x4.y, wr[4 * k4 + 1], acc);
+          acc = fmaf(x4.z, wr[4 * k4 + 2], acc); acc = fmaf(x4.w, wr[4 * k4 + 3], acc);
+        }
         xs[r * C + c] = lrelu02(acc);
       }
   }
   __syncthreads();
-  // aggregation: thread -> channel pair (bf162 stores, 128 B per 32 lanes) and a (frame, node, k) stripe
-  const int KC = Kk * C, half = C / 2;
-  const int cp = threadIdx.x % half, stripe = threadIdx.x / half, nstripes = blockDim.x / half;
-  for (int item = stripe; item < g_live * V * Kk; item += nstripes) {
-    const int g = item / (V * Kk), rem = item - g * V * Kk;
-    const int w = rem / Kk, k = rem - w * Kk;
-    const int kw = k * V + w, n = cnt[kw];
+  // aggregation: warp = output row (frame, node), lane = channel pair (bf162 stores, 128 B per warp)
+  const int KC = Kk * C;
+  for (int r = warp; r < rows; r += 8) {
+    const int g = r / V, w = r - g * V;
     const float* xg = xs + g * V * C;
-    float a0 = 0.f, a1 = 0.f;
-    for (int i = 0; i < n; ++i) {
-      const float2 x2 = *reinterpret_cast<const float2*>(xg + src[kw * V + i] * C + 2 * cp);
-      const float av = val[kw * V + i];
-      a0 = fmaf(x2.x, av, a0);
-      a1 = fmaf(x2.y, av, a1);
+    __nv_bfloat16* dst = out16 + ((long long)bt0 * V + r) * KC;
+    for (int k = 0; k < Kk; ++k) {
+      const int kw = k * V + w;
+      for (int cp = lane; cp < C / 2; cp += 32) {
+        float a0 = 0.f, a1 = 0.f;
+        for (int i = 0; i < nmax4; i += 4) {
+          const int4 s4 = *reinterpret_cast<const int4*>(src + kw * V + i);
+          const float4 v4 = *reinterpret_cast<const float4*>(val + kw * V + i);
+          const float2 x0 = *reinterpret_cast<const float2*>(xg + s4.x * C + 2 * cp);
+          const float2 x1 = *reinterpret_cast<const float2*>(xg + s4.y * C + 2 * cp);
+          const float2 x2 = *reinterpret_cast<const float2*>(xg + s4.z * C + 2 * cp);
+          const float2 x3 = *reinterpret_cast<const float2*>(xg + s4.w * C + 2 * cp);
+          a0 = fmaf(x0.x, v4.x, a0); a1 = fmaf(x0.y, v4.x, a1);
+          a0 = fmaf(x1.x, v4.y, a0); a1 = fmaf(x1.y, v4.y, a1);
+          a0 = fmaf(x2.x, v4.z, a0); a1 = fmaf(x2.y, v4.z, a1);
+          a0 = fmaf(x3.x, v4.w, a0); a1 = fmaf(x3.y, v4.w, a1);
+        }
+        *reinterpret_cast<__nv_bfloat162*>(dst + k * C + 2 * cp) = __floats2bfloat162_rn(a0, a1);
+      }
     }
-    *reinterpret_cast<__nv_bfloat162*>(out16 + ((long long)(bt0 + g) * V + w) * KC + k * C + 2 * cp) =
-        __floats2bfloat162_rn(a0, a1);
   }
 }
 
@@ -166,6 +198,68 @@ __global__ void pool_joint_body_kernel(const float* __restrict__ in, const float
 #pragma unroll
     for (int p = 0; p < POOL_MAXP; ++p)
       if (p < P) dst[(long long)p * C] = acc[p] * inv;
+  }
+}
+
+// Tensor-core path: joint -> body-part pooling (graph.py:463-465 + AvgPool2d((tp,1)), model.py:47) of the
+// bf16 JointBlock output fused with the BodyBlock's pre-activation and graph aggregation
+// (blocks.py:125-129, :64): out16[(b,t2,w), k*C + c] = sum_u lrelu(pooled[b,t2,u,c]) * A[k,u,w].
+// Block = one (b, t2); thread = a channel pair (bf162 loads, 128 B per warp row).
+__global__ void __launch_bounds__(128)
+pool_graph_agg_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ Wp, const float* __restrict__ A,
+                      __nv_bfloat16* __restrict__ out16, int T, int V, int P, int C, int tp, int Kk) {
+  extern __shared__ float ws[];
+  float* As = ws;                                   // [Kk][P][P] adjacency
+  float* mw = As + Kk * P * P;                      // [P][V] member weights of each body part (compact)
+  int* mv = reinterpret_cast<int*>(mw + P * V);     // [P][V] member joints
+  int* mc = mv + P * V;                             // [P]
+  for (int i = threadIdx.x; i < Kk * P * P; i += blockDim.x) As[i] = A[i];
+  if (threadIdx.x < P) {
+    // the pooling matrix is a (weighted) membership table: a handful of joints per part
+    const int p = threadIdx.x;
+    int n = 0;
+    for (int v = 0; v < V; ++v) {
+      const float wv = Wp[v * P + p];
+      if (wv != 0.f) { mw[p * V + n] = wv; mv[p * V + n] = v; ++n; }
+    }
+    mc[p] = n;
+  }
+  __syncthreads();
+  const int Tp = T / tp;
+  const int b = blockIdx.x / Tp, t2 = blockIdx.x % Tp;
+  const float inv = 1.f / (float)tp;
+  const int KC = Kk * C, C2 = C / 2;
+  for (int c2 = threadIdx.x; c2 < C2; c2 += blockDim.x) {
+    float a0[POOL_MAXP], a1[POOL_MAXP];
+    const __nv_bfloat162* src = reinterpret_cast<const __nv_bfloat162*>(in + ((long long)(b * T + t2 * tp) * V) * C) + c2;
+#pragma unroll
+    for (int p = 0; p < POOL_MAXP; ++p) {
+      a0[p] = 0.f; a1[p] = 0.f;
+      if (p < P) {
+        const int n = mc[p];
+        for (int dt = 0; dt < tp; ++dt) {
+          const __nv_bfloat162* sd = src + (long long)dt * V * C2;
+#pragma unroll 4
+          for (int i = 0; i < n; ++i) {
+            const float2 x = __bfloat1622float2(sd[(long long)mv[p * V + i] * C2]);
+            const float wv = mw[p * V + i];
+            a0[p] = fmaf(x.x, wv, a0[p]);
+            a1[p] = fmaf(x.y, wv, a1[p]);
+          }
+        }
+        a0[p] = lrelu02(a0[p] * inv);
+        a1[p] = lrelu02(a1[p] * inv);
+      }
+    }
+    __nv_bfloat16* dst = out16 + ((long long)(b * Tp + t2) * P) * KC + 2 * c2;
+    for (int k = 0; k < Kk; ++k)
+      for (int w = 0; w < P; ++w) {
+        float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+        for (int u = 0; u < POOL_MAXP; ++u)
+          if (u < P) { const float av = As[(k * P + u) * P + w]; o0 = fmaf(a0[u], av, o0); o1 = fmaf(a1[u], av, o1); }
+        *reinterpret_cast<__nv_bfloat162*>(dst + (long long)w * KC + k * C) = __floats2bfloat162_rn(o0, o1);
+      }
   }
 }
 
@@ -432,8 +526,10 @@ int embed_graph_agg(const float* X, const float* Wemb, const float* bemb, const 
                     int V, int Cin, int C, int Kk, cudaStream_t s) {
   MOCHA_CHECK_ARG(X && Wemb && A && out16 && BT > 0 && V > 0 && Cin > 0 && Kk > 0, "embed_graph_agg: bad args");
   MOCHA_CHECK_ARG(C >= 2 && C <= 256 && (C & 1) == 0 && 256 % C == 0, "embed_graph_agg: C=%d unsupported", C);
+  MOCHA_CHECK_ARG(Cin <= EMB_MAXCIN, "embed_graph_agg: Cin=%d > %d unsupported", Cin, EMB_MAXCIN);
+  MOCHA_CHECK_ARG(V % 4 == 0, "embed_graph_agg: V=%d must be a multiple of 4", V);
   constexpr int G = 4;
-  const size_t smem = (size_t)(G * V * C + G * V * Cin + Cin * C + 2 * Kk * V * V + Kk * V) * sizeof(float);
+  const size_t smem = (size_t)(G * V * C + G * V * EMB_MAXCIN + 2 * Kk * V * V + Kk * V) * sizeof(float);
   static size_t configured = 0;
   if (smem > configured) {
     MOCHA_CHECK_ARG(smem <= 200 * 1024, "embed_graph_agg: tile too large (%zu B)", smem);
@@ -466,6 +562,18 @@ int pool_joint_body(const float* in, const float* Wp, float* out, int B, int T, 
   pool_joint_body_kernel<<<B * (T / tp), 256, (size_t)V * P * sizeof(float), s>>>(in, Wp, out, T, V, P, C, tp);
   count_launch();
   MOCHA_LAUNCH_CHECK("pool_joint_body");
+  return MOCHA_OK;
+}
+
+int pool_graph_agg(const __nv_bfloat16* in, const float* Wp, const float* A, __nv_bfloat16* out16, int B, int T, int V,
+                   int P, int C, int tp, int Kk, cudaStream_t s) {
+  MOCHA_CHECK_ARG(in && Wp && A && out16 && B > 0 && T > 0 && V > 0 && C > 0 && (C & 1) == 0 && Kk > 0, "pool_graph_agg: bad args");
+  MOCHA_CHECK_ARG(P > 0 && P <= POOL_MAXP, "pool_graph_agg: P=%d unsupported (max %d)", P, POOL_MAXP);
+  MOCHA_CHECK_ARG(tp > 0 && T % tp == 0, "pool_graph_agg: T=%d not a multiple of tp=%d", T, tp);
+  const size_t smem = (size_t)(Kk * P * P + 2 * P * V + P) * sizeof(float);
+  pool_graph_agg_kernel<<<B * (T / tp), 128, smem, s>>>(in, Wp, A, out16, T, V, P, C, tp, Kk);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("pool_graph_agg");
   return MOCHA_OK;
 }
 

@@ -29,6 +29,11 @@ int graph_agg_kv(const float* in, const float* A2, float* out, int BT, int U, in
 int pool_joint_body(const float* in, const float* Wp, float* out, int B, int T, int V, int P, int C,
                     int tp, cudaStream_t s);
 
+// bf16 input variant fused with the next block's LeakyReLU + graph aggregation (tensor-core path):
+// out16[(b,t',w), k*C + c] = sum_u lrelu(pool(in)[b,t',u,c]) * A[k,u,w]
+int pool_graph_agg(const __nv_bfloat16* in, const float* Wp, const float* A, __nv_bfloat16* out16, int B, int T, int V,
+                   int P, int C, int tp, int Kk, cudaStream_t s);
+
 // Instance norm over tokens per (b, channel): unbiased std, eps added to std
 // (mean_variance_norm, net/transformer.py:13-20). Optional AdaIN modulation
 // y = (1+gamma)*IN(x) + beta with gb = [B, 2C] (gamma | beta) (AdaIN.forward, transformer.py:108-113)
