@@ -379,14 +379,15 @@ def roofline_pass(args, sess, torch, lib, _lib):
     achieved = flops / (ms * 1e-3) / 1e12
     if sess.prec == _lib.MOCHA_BF16:
         peak = peaks.get("bf16_tflops", 1590.0)
-        return {"kernel": "tc_gemm_kernel<256,LinearEpi>: mot_embedding JointBlock temporal conv (5 taps, 256->256) as a "
-                          "TMA-shifted implicit GEMM on tcgen05 (largest launch of the step, 31 % of its FLOPs)",
+        return {"kernel": "tc_gemm2_kernel<LinearEpiT<1>> (cta_group::2, 256x256 pair tiles, TMA-store epilogue): mot_embedding "
+                          "JointBlock temporal conv (5 taps, 256->256) as a TMA-shifted implicit GEMM on tcgen05 "
+                          "(largest launch of the step, 31 % of its FLOPs)",
                 "bound": "tensor", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of this launch at 128 clips from one
-                # `ncu --set full` capture (profiles/r01_ncu_tconv_tc_gemm_LinearEpi.txt); algorithmic
-                # bytes are 106 MB (padded bf16 operand) + 189 MB (fp32 output)
-                "traffic": (101479424 + 133293824) * (B / 128.0), "traffic_unit": "B/launch",
+                # `ncu --set full` capture (profiles/r01_ncu_tconv_pair_tc_gemm2_LinearEpiT1.txt); algorithmic
+                # bytes are 106 MB (padded bf16 operand) + 189 MB (fp32 output of the stand-alone entry)
+                "traffic": (101463040 + 135415040) * (B / 128.0), "traffic_unit": "B/launch",
                 "peak_source": src + " (burst)",
                 "ms_per_launch": ms, "flops_per_launch": flops}
     return {"kernel": "sgemm_kernel<128,128,8,8> (temporal conv as implicit GEMM, fp32 FFMA)", "bound": "fp32-simt",
