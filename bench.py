@@ -216,7 +216,8 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line
+        # keep stdout to the single JSON line: NCCL prints its version banner to stdout at any debug level
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/mocha_bench_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
     _lib.check(lib.mocha_check_device(), "mocha_check_device")
