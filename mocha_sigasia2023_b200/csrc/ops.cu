@@ -320,6 +320,72 @@ instance_norm_tokens_kernel(const float* __restrict__ x, int n, int C, float eps
   }
 }
 
+// same statistics with the block's tokens held in registers (n <= 128): one pass over global memory
+__global__ void __launch_bounds__(256)
+instance_norm_tokens_reg_kernel(const float* __restrict__ x, int n, int C, float eps,
+                                const float* __restrict__ gb, float* __restrict__ y,
+                                const float* __restrict__ tab_mean,
+                                const float* __restrict__ tab_std, float* __restrict__ y2,
+                                __nv_bfloat16* __restrict__ y16) {
+  __shared__ float part[8][32];
+  __shared__ float stat[2][32];
+  const int b = blockIdx.x, c = blockIdx.y * 32 + (threadIdx.x & 31), warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool ok = c < C;
+  const float* xb = x + (long long)b * n * C;
+  float v[16];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int i = warp + 8 * j;
+    v[j] = (ok && i < n) ? xb[(long long)i * C + c] : 0.f;
+    s += v[j];
+  }
+  part[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += part[w][lane];
+    stat[0][lane] = t / (float)n;
+  }
+  __syncthreads();
+  const float mean = stat[0][lane];
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float d = v[j] - mean;
+    if (warp + 8 * j < n) q = fmaf(d, d, q);
+  }
+  part[warp][lane] = q;
+  __syncthreads();
+  if (warp == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += part[w][lane];
+    stat[1][lane] = sqrtf(t / (float)(n - 1)) + eps;
+  }
+  __syncthreads();
+  if (!ok) return;
+  const float den = stat[1][lane];
+  float g = 1.f, be = 0.f;
+  if (gb) {
+    g = 1.f + gb[(long long)b * 2 * C + c];
+    be = gb[(long long)b * 2 * C + C + c];
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int i = warp + 8 * j;
+    if (i < n) {
+      const long long o = (long long)i * C + c;
+      float u = (v[j] - mean) / den;   // same operation order as the reference: divide, then modulate
+      if (gb) u = g * u + be;
+      if (y) y[(long long)b * n * C + o] = u;
+      if (y16) y16[(long long)b * n * C + o] = __float2bfloat16_rn(u);
+      if (y2) y2[(long long)b * n * C + o] = (u - tab_mean[o]) / tab_std[o];
+    }
+  }
+}
+
 __global__ void token_mean_kernel(const float* __restrict__ x, int n, int C, float* __restrict__ out) {
   const int b = blockIdx.x;
   const float* xb = x + (long long)b * n * C;
@@ -391,6 +457,62 @@ __global__ void add_layernorm_kernel(const float* __restrict__ x, const float* _
   }
 }
 
+__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* p, const float4& v) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&lo);
+  pk.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = pk;
+}
+__device__ __host__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// C = 128 * NJ: the row lives in registers (float4 per lane per 128-column group), one pass over global memory
+template <int NJ>
+__global__ void __launch_bounds__(256)
+add_layernorm_reg_kernel(const float* __restrict__ x, const float* __restrict__ r, const float* __restrict__ g,
+                         const float* __restrict__ b, float* __restrict__ y, long long rows, float eps,
+                         const float* __restrict__ tab_mean, const float* __restrict__ tab_std, int period,
+                         float* __restrict__ y2, __nv_bfloat16* __restrict__ y16) {
+  constexpr int C = 128 * NJ;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+  const float4* rr = r ? reinterpret_cast<const float4*>(r + row * C) : nullptr;
+  float4 v[NJ];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    v[j] = xr[lane + 32 * j];
+    if (rr) { const float4 t = rr[lane + 32 * j]; v[j].x += t.x; v[j].y += t.y; v[j].z += t.z; v[j].w += t.w; }
+    s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+    q = fmaf(v[j].x, v[j].x, q); q = fmaf(v[j].y, v[j].y, q); q = fmaf(v[j].z, v[j].z, q); q = fmaf(v[j].w, v[j].w, q);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  const long long prow = y2 ? row % period : 0;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int c4 = lane + 32 * j;
+    const float4 gg = reinterpret_cast<const float4*>(g)[c4], bb = reinterpret_cast<const float4*>(b)[c4];
+    float4 o;
+    o.x = v[j].x * rstd * gg.x + bb.x; o.y = v[j].y * rstd * gg.y + bb.y;
+    o.z = v[j].z * rstd * gg.z + bb.z; o.w = v[j].w * rstd * gg.w + bb.w;
+    if (y) reinterpret_cast<float4*>(y + row * C)[c4] = o;
+    if (y16) store_bf16x4(y16 + row * C + 4 * c4, o);
+    if (y2) {
+      const float4 sd = reinterpret_cast<const float4*>(tab_std + prow * C)[c4];
+      const float4 mu = reinterpret_cast<const float4*>(tab_mean + prow * C)[c4];
+      reinterpret_cast<float4*>(y2 + row * C)[c4] = make_float4(o.x * sd.x + mu.x, o.y * sd.y + mu.y, o.z * sd.z + mu.z, o.w * sd.w + mu.w);
+    }
+  }
+}
+
 __global__ void cvae_prior_tokens_kernel(const float* __restrict__ mu_token, const float* __restrict__ lv_token,
                                          const float* __restrict__ cond, const float* __restrict__ pe,
                                          float* __restrict__ tok, __nv_bfloat16* __restrict__ tok16, int ncond, int C,
@@ -449,6 +571,68 @@ __global__ void cvae_condition_kernel(const float* __restrict__ src_cnt, const f
   if (r < per) cond[i] = (src_cnt[b * per + r] - m0[r]) / s0[r];
   else cond[i] = (prev[b * per + (r - per)] - m1[r - per]) / s1[r - per];
 }
+
+// ---- float4 / 32-bit-index variants of the three CVAE assembly kernels (C % 4 == 0, < 2^31 elements) ----
+
+__global__ void cvae_prior_tokens_v4_kernel(const float4* __restrict__ mu_token, const float4* __restrict__ lv_token,
+                                            const float4* __restrict__ cond, const float4* __restrict__ pe,
+                                            float4* __restrict__ tok, __nv_bfloat16* __restrict__ tok16, unsigned ncond,
+                                            unsigned C4, unsigned total4) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const unsigned n = ncond + 2;
+  const unsigned row = i / C4, c = i - row * C4;
+  const unsigned b = row / n, t = row - b * n;
+  float4 v = t == 0 ? mu_token[c] : t == 1 ? lv_token[c] : cond[(b * ncond + (t - 2)) * C4 + c];
+  const float4 p = pe[t * C4 + c];
+  v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+  tok[i] = v;
+  if (tok16) store_bf16x4(tok16 + 4ull * i, v);
+}
+
+__global__ void cvae_memory_v4_kernel(const float4* __restrict__ prior_out, unsigned prior_tokens,
+                                      const float4* __restrict__ eps, const float4* __restrict__ cond,
+                                      float4* __restrict__ mem, __nv_bfloat16* __restrict__ mem16,
+                                      float4* __restrict__ mu_out, float4* __restrict__ lv_out, unsigned ncond, unsigned C4,
+                                      unsigned total4) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const unsigned n = ncond + 1;
+  const unsigned row = i / C4, c = i - row * C4;
+  const unsigned b = row / n, t = row - b * n;
+  float4 v;
+  if (t == 0) {
+    const float4 mu = prior_out[(b * prior_tokens + 0) * C4 + c];
+    const float4 lv = prior_out[(b * prior_tokens + 1) * C4 + c];
+    v = mu;
+    if (eps) {
+      const float4 e = eps[b * C4 + c];
+      v.x = mu.x + e.x * expf(0.5f * lv.x); v.y = mu.y + e.y * expf(0.5f * lv.y);
+      v.z = mu.z + e.z * expf(0.5f * lv.z); v.w = mu.w + e.w * expf(0.5f * lv.w);
+    }
+    if (mu_out) mu_out[b * C4 + c] = mu;
+    if (lv_out) lv_out[b * C4 + c] = lv;
+  } else {
+    v = cond[(b * ncond + (t - 1)) * C4 + c];
+  }
+  if (mem) mem[i] = v;
+  if (mem16) store_bf16x4(mem16 + 4ull * i, v);
+}
+
+__global__ void cvae_condition_v4_kernel(const float4* __restrict__ src_cnt, const float4* __restrict__ prev,
+                                         const float4* __restrict__ m0, const float4* __restrict__ s0,
+                                         const float4* __restrict__ m1, const float4* __restrict__ s1,
+                                         float4* __restrict__ cond, unsigned per4, unsigned total4) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const unsigned b = i / (2 * per4);
+  unsigned r = i - b * 2 * per4;
+  float4 x, m, sd;
+  if (r < per4) { x = src_cnt[b * per4 + r]; m = m0[r]; sd = s0[r]; }
+  else { r -= per4; x = prev[b * per4 + r]; m = m1[r]; sd = s1[r]; }
+  cond[i] = make_float4((x.x - m.x) / sd.x, (x.y - m.y) / sd.y, (x.z - m.z) / sd.z, (x.w - m.w) / sd.w);
+}
+
 
 __global__ void affine_rows_kernel(const float* __restrict__ x, const float* __restrict__ mu,
                                    const float* __restrict__ sd, float* __restrict__ out, long long total,
@@ -583,7 +767,10 @@ int instance_norm_tokens(const float* x, int B, int n, int C, float eps, const f
   MOCHA_CHECK_ARG(x && B > 0 && n > 1 && C > 0, "instance_norm_tokens: bad args");
   MOCHA_CHECK_ARG(y || y2 || y16, "instance_norm_tokens: no output");
   MOCHA_CHECK_ARG(!y2 || (tab_mean && tab_std), "instance_norm_tokens: y2 needs its table");
-  instance_norm_tokens_kernel<<<dim3(B, (C + 31) / 32), 256, 0, s>>>(x, n, C, eps, gb, y, tab_mean, tab_std, y2, y16);
+  if (n <= 128)
+    instance_norm_tokens_reg_kernel<<<dim3(B, (C + 31) / 32), 256, 0, s>>>(x, n, C, eps, gb, y, tab_mean, tab_std, y2, y16);
+  else
+    instance_norm_tokens_kernel<<<dim3(B, (C + 31) / 32), 256, 0, s>>>(x, n, C, eps, gb, y, tab_mean, tab_std, y2, y16);
   count_launch();
   MOCHA_LAUNCH_CHECK("instance_norm_tokens");
   return MOCHA_OK;
@@ -612,8 +799,17 @@ int add_layernorm(const float* x, const float* r, const float* g, const float* b
   MOCHA_CHECK_ARG(x && g && b && rows > 0 && C > 0, "add_layernorm: bad args");
   MOCHA_CHECK_ARG(y || y2 || y16, "add_layernorm: no output");
   MOCHA_CHECK_ARG(!y2 || (tab_mean && tab_std && period > 0), "add_layernorm: y2 needs its table");
-  add_layernorm_kernel<<<blocks_for(rows, 8), 256, 0, s>>>(x, r, g, b, y, rows, C, eps, tab_mean, tab_std,
-                                                          period, y2, y16);
+  const bool vec = aligned16(x) && aligned16(r) && aligned16(g) && aligned16(b) && aligned16(y) && aligned16(y2) &&
+                   aligned16(tab_mean) && aligned16(tab_std) && (reinterpret_cast<uintptr_t>(y16) & 7) == 0;
+  if (vec && C == 256)
+    add_layernorm_reg_kernel<2><<<blocks_for(rows, 8), 256, 0, s>>>(x, r, g, b, y, rows, eps, tab_mean, tab_std, period, y2, y16);
+  else if (vec && C == 128)
+    add_layernorm_reg_kernel<1><<<blocks_for(rows, 8), 256, 0, s>>>(x, r, g, b, y, rows, eps, tab_mean, tab_std, period, y2, y16);
+  else if (vec && C == 512)
+    add_layernorm_reg_kernel<4><<<blocks_for(rows, 8), 256, 0, s>>>(x, r, g, b, y, rows, eps, tab_mean, tab_std, period, y2, y16);
+  else
+    add_layernorm_kernel<<<blocks_for(rows, 8), 256, 0, s>>>(x, r, g, b, y, rows, C, eps, tab_mean, tab_std,
+                                                            period, y2, y16);
   count_launch();
   MOCHA_LAUNCH_CHECK("add_layernorm");
   return MOCHA_OK;
@@ -624,6 +820,17 @@ int cvae_prior_tokens(const float* mu_token, const float* logvar_token, const fl
   MOCHA_CHECK_ARG(mu_token && logvar_token && cond && pe && tok && B > 0 && ncond > 0 && C > 0,
                   "cvae_prior_tokens: bad args");
   const long long total = (long long)B * (ncond + 2) * C;
+  if ((C & 3) == 0 && total < (1LL << 31) && aligned16(mu_token) && aligned16(logvar_token) && aligned16(cond) &&
+      aligned16(pe) && aligned16(tok) && (!tok16 || (reinterpret_cast<uintptr_t>(tok16) & 7) == 0)) {
+    const unsigned total4 = (unsigned)(total / 4);
+    cvae_prior_tokens_v4_kernel<<<(total4 + 255) / 256, 256, 0, s>>>(
+        reinterpret_cast<const float4*>(mu_token), reinterpret_cast<const float4*>(logvar_token),
+        reinterpret_cast<const float4*>(cond), reinterpret_cast<const float4*>(pe), reinterpret_cast<float4*>(tok), tok16,
+        (unsigned)ncond, (unsigned)(C / 4), total4);
+    count_launch();
+    MOCHA_LAUNCH_CHECK("cvae_prior_tokens");
+    return MOCHA_OK;
+  }
   cvae_prior_tokens_kernel<<<blocks_for(total, 256), 256, 0, s>>>(mu_token, logvar_token, cond, pe, tok, tok16,
                                                                   ncond, C, total);
   count_launch();
@@ -636,6 +843,17 @@ int cvae_memory(const float* prior_out, int prior_tokens, const float* eps, cons
   MOCHA_CHECK_ARG(prior_out && cond && (mem || mem16) && B > 0 && ncond > 0 && C > 0 && prior_tokens >= 2,
                   "cvae_memory: bad args");
   const long long total = (long long)B * (ncond + 1) * C;
+  if ((C & 3) == 0 && total < (1LL << 31) && aligned16(prior_out) && aligned16(eps) && aligned16(cond) && aligned16(mem) &&
+      aligned16(mu_out) && aligned16(logvar_out) && (reinterpret_cast<uintptr_t>(mem16) & 7) == 0) {
+    const unsigned total4 = (unsigned)(total / 4);
+    cvae_memory_v4_kernel<<<(total4 + 255) / 256, 256, 0, s>>>(
+        reinterpret_cast<const float4*>(prior_out), (unsigned)prior_tokens, reinterpret_cast<const float4*>(eps),
+        reinterpret_cast<const float4*>(cond), reinterpret_cast<float4*>(mem), mem16, reinterpret_cast<float4*>(mu_out),
+        reinterpret_cast<float4*>(logvar_out), (unsigned)ncond, (unsigned)(C / 4), total4);
+    count_launch();
+    MOCHA_LAUNCH_CHECK("cvae_memory");
+    return MOCHA_OK;
+  }
   cvae_memory_kernel<<<blocks_for(total, 256), 256, 0, s>>>(prior_out, prior_tokens, eps, cond, mem, mem16, mu_out,
                                                             logvar_out, ncond, C, total);
   count_launch();
@@ -648,6 +866,17 @@ int cvae_condition(const float* src_cnt, const float* prev, const float* m0, con
   MOCHA_CHECK_ARG(src_cnt && prev && m0 && s0 && m1 && s1 && cond && B > 0 && n > 0 && C > 0,
                   "cvae_condition: bad args");
   const long long total = (long long)B * 2 * n * C;
+  if ((C & 3) == 0 && total < (1LL << 31) && aligned16(src_cnt) && aligned16(prev) && aligned16(m0) && aligned16(s0) &&
+      aligned16(m1) && aligned16(s1) && aligned16(cond)) {
+    const unsigned total4 = (unsigned)(total / 4);
+    cvae_condition_v4_kernel<<<(total4 + 255) / 256, 256, 0, s>>>(
+        reinterpret_cast<const float4*>(src_cnt), reinterpret_cast<const float4*>(prev), reinterpret_cast<const float4*>(m0),
+        reinterpret_cast<const float4*>(s0), reinterpret_cast<const float4*>(m1), reinterpret_cast<const float4*>(s1),
+        reinterpret_cast<float4*>(cond), (unsigned)((long long)n * C / 4), total4);
+    count_launch();
+    MOCHA_LAUNCH_CHECK("cvae_condition");
+    return MOCHA_OK;
+  }
   cvae_condition_kernel<<<blocks_for(total, 256), 256, 0, s>>>(src_cnt, prev, m0, s0, m1, s1, cond, n, C, total);
   count_launch();
   MOCHA_LAUNCH_CHECK("cvae_condition");
