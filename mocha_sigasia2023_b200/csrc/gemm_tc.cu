@@ -240,6 +240,7 @@ struct EpiCtx {
   int slab_rows;         // valid rows in the slab (0..32)
   long long c_off;       // element offset of the output block (batched-head mode), else 0
   uint32_t res_bar;      // shared-space address of this warp's residual-prefetch mbarrier
+  uint32_t bias_smem;    // shared-space address of this warp's 512 B column-bias slice (TMA epilogues)
   int col_off;           // column offset of the output block inside its TMA map (batched-head PV output)
   int z;                 // image index b of the tile (batched-head mode: z = zb * H + zh)
   int img;               // batch image of the tile: third TMA-store coordinate
@@ -334,19 +335,23 @@ template <int MODE>
 struct LinearEpiT : LinearEpiData {
   struct State {
     uint32_t rphase;  // parity of the residual-prefetch barrier
+    int col_begin;    // first column of this warp's share of the current tile
+    float rs;         // this lane's row scale for the current tile
   };
   // per warp: 4 KB fp32 box [32][128 B] (128 B-swizzled, 1 KB aligned) + 2 KB bf16 box [32][64 B]
   // (64 B-swizzled) + 4 KB residual box (128 B-swizzled); the LSU path uses a [32][EPI_LD] float
   // transposition buffer
   // MODE 1 writes one output per launch (the host falls back to MODE 0 otherwise), so its bf16 box
   // aliases the fp32 box and a fourth operand stage fits beside a 128 x 256 tile's staging
-  static constexpr int kWarpStageBytes = MODE == 2 ? 10240 : MODE == 1 ? 4096 : 5120;
+  // + 512 B per warp for the tile's column-bias slice
+  static constexpr int kWarpStageBytes = MODE == 2 ? 10752 : MODE == 1 ? 4608 : 5120;
+  static constexpr int kBiasOff = MODE == 2 ? 10240 : 4096;
   static constexpr int kStageBytes = EPI_WARPS * kWarpStageBytes;
   static constexpr uint64_t kHintA = 0, kHintB = 0;                // default L2 policy
   static constexpr bool kTf32 = false;
   static constexpr bool kWholeTile = false;
   __device__ __forceinline__ void unit_begin(State&) const {}
-  __device__ __forceinline__ void kernel_begin(State& st) const { st.rphase = 0; }
+  __device__ __forceinline__ void kernel_begin(State& st) const { st.rphase = 0; st.col_begin = 0; st.rs = 1.f; }
   // issue the TMA prefetch of a chunk's residual box (does not depend on the accumulator)
   __device__ __forceinline__ void prefetch_res(const EpiCtx& e, int col0) const {
     if (MODE == 2 && col0 >= 0 && col0 < N && e.slab_rows > 0 && e.lane == 0) {
@@ -354,6 +359,25 @@ struct LinearEpiT : LinearEpiData {
       tma_load_3d(e.stage + 6144, &tmR, e.res_bar, col0, e.row0_in_img, e.img);
     }
   }
+  // Global loads issued from the epilogue see multi-thousand-cycle latencies while every SM is streaming
+  // stores, so nothing on a chunk's critical path may come from global memory: the warp's slice of the
+  // column bias is staged in shared memory once per tile BEFORE the accumulator is waited for (the load
+  // overlaps the tile's main loop), and in MODE 2 the residual box is TMA-prefetched one chunk ahead.
+  __device__ __forceinline__ void tile_begin(State& st, const EpiCtx& e, int col_begin, int ncols) const {
+    st.col_begin = col_begin;
+    if (MODE == 1 && row_scale)
+      st.rs = e.lane < e.slab_rows ? __ldg(row_scale + (long long)e.z * rs_rows + e.row0_in_img + e.lane) : 0.f;
+    if (MODE != 0 && bias && bias_period == 0) {
+      const int c = col_begin + 4 * e.lane;
+      if (4 * e.lane < ncols) {
+        const float4 b4 = c < N ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        sts128f(e.bias_smem + 16u * e.lane, b4);
+      }
+      __syncwarp();
+    }
+    prefetch_res(e, col_begin);
+  }
+  __device__ __forceinline__ void prefetch_chunk(State&, const EpiCtx& e, int col0) const { prefetch_res(e, col0); }
 
   // LSU epilogue (batched-head attention outputs and unaligned tensors), second half of the transposed
   // path: 8 passes of 4 rows x 32 columns, 8 lanes x float4 = one 128 B line per row, as a fixed
@@ -452,22 +476,84 @@ struct LinearEpiT : LinearEpiData {
   //   pass 2  8 lanes x float4 = one row: coalesced bias / residual loads, activation, in-place write
   //           back (+ bf16 box), then fence.proxy.async and one elected TMA store per output.
   template <int ACT>
-  __device__ __forceinline__ void drain_tma(const EpiCtx& e, int col0, const uint32_t (&v)[32]) const {
+  __device__ __forceinline__ void drain_tma(State& st, const EpiCtx& e, int col0, int next_col0, const uint32_t (&v)[32]) const {
+    EPI_DBG(14);
+    if (bias_period == 0 || !bias) {
+      // lane = row all the way (no transposed pass): column bias by shuffle from the prefetching lanes,
+      // row scale is one scalar per lane, results go straight into the TMA boxes
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      if (row_scale) {
+        const float rs = st.rs;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] *= rs;
+      }
+      if (bias) {
+        const uint32_t bs = e.bias_smem + (uint32_t)((col0 - st.col_begin) * 4);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b4 = lds128(bs + 16u * j);   // same address in every lane: broadcast
+          f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
+        }
+      }
+      if (ACT != ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = act_fn<ACT>(f[j]);
+      }
+      EPI_DBG(8);
+      if (e.lane == 0) bulk_wait_read0();  // the previous chunk's store has left the staging buffer
+      __syncwarp();
+      EPI_DBG(9);
+      if (C) {
+        const int sw = e.lane & 7;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          sts128(e.stage + (uint32_t)(e.lane * 128 + ((j ^ sw) << 4)), __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
+                 __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
+      } else {
+        const int sw16 = (e.lane >> 1) & 3;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            float a = f[8 * j + 2 * t], b = f[8 * j + 2 * t + 1];
+            if (c16_lrelu) { a = lrelu02(a); b = lrelu02(b); }
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+            pk[t] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          sts128(e.stage + (uint32_t)(e.lane * 64 + ((j ^ sw16) << 4)), pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      EPI_DBG(11);
+      fence_async_smem();
+      __syncwarp();
+      EPI_DBG(12);
+      if (e.lane == 0) {
+        if (C) tma_store_3d(&tmC, e.stage, col0 + e.col_off, e.row0_in_img, e.img);
+        else tma_store_3d(&tmC16, e.stage, col0 + e.col_off, e.row0_in_img, e.img);
+        bulk_commit();
+      }
+      EPI_DBG(13);
+      return;
+    }
     // bf16 box aliases the fp32 box: rows 16h..16h+15 of the bf16 box cover fp32 rows 8h..8h+7, which
     // the warp has already read when half h is written back (warp-synchronous, program order)
     const uint32_t buf32 = e.stage, buf16 = e.stage;
+    EPI_DBG(8);
     if (e.lane == 0) bulk_wait_read0();  // the previous chunk's stores have left the staging buffers
     __syncwarp();
+    EPI_DBG(9);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       sts128(buf32 + (uint32_t)(e.lane * 128 + ((j ^ (e.lane & 7)) << 4)), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     __syncwarp();
+    EPI_DBG(10);
     const int rr = e.lane >> 3, cq = e.lane & 7;
     const int c = col0 + cq * 4;
     const bool col_ok = c < N;  // N % 4 == 0 on this path
     if (bias || res || ACT != ACT_NONE || C16 || row_scale) {
-      float4 bc = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (bias && bias_period == 0 && col_ok) bc = __ldg(reinterpret_cast<const float4*>(bias + c));
       const long long step = 4LL * ldc;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -497,11 +583,8 @@ struct LinearEpiT : LinearEpiData {
           }
         }
         if (bias) {
-          if (bias_period == 0) {
-#pragma unroll
-            for (int it = 0; it < 4; ++it) { o[it].x += bc.x; o[it].y += bc.y; o[it].z += bc.z; o[it].w += bc.w; }
-          } else {
-            const unsigned p = (unsigned)bias_period;
+          {
+            const unsigned p = (unsigned)bias_period;   // column biases take the single-pass path above
             unsigned m = (unsigned)((unsigned long long)(e.slab_row0 + rr + 16 * h) % p);
             float4 bv[4];
 #pragma unroll
@@ -549,14 +632,17 @@ struct LinearEpiT : LinearEpiData {
         }
       }
     }
+    EPI_DBG(11);
     fence_async_smem();
     __syncwarp();
+    EPI_DBG(12);
     if (e.lane == 0) {
       // rows past the image and columns past the tensor are clipped by the tensor map
       if (C) tma_store_3d(&tmC, buf32, col0 + e.col_off, e.row0_in_img, e.img);
       if (C16) tma_store_3d(&tmC16, buf16, col0 + e.col_off, e.row0_in_img, e.img);
       bulk_commit();
     }
+    EPI_DBG(13);
   }
 
   // Residual GEMMs (x + f(x) feeding both an fp32 stream and a bf16 operand): the residual box is
@@ -567,15 +653,14 @@ struct LinearEpiT : LinearEpiData {
     const uint32_t buf32 = e.stage, buf16 = e.stage + 4096, bufr = e.stage + 6144;
     const int sw = e.lane & 7;
     if (bias) {
+      const uint32_t bs = e.bias_smem + (uint32_t)((col0 - st.col_begin) * 4);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        if (col0 + 4 * j < N) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0) + j);
-          v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + b4.x);
-          v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + b4.y);
-          v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + b4.z);
-          v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + b4.w);
-        }
+        const float4 b4 = lds128(bs + 16u * j);   // same address in every lane: broadcast
+        v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + b4.x);
+        v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + b4.y);
+        v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + b4.z);
+        v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + b4.w);
       }
     }
     if (ACT != ACT_NONE) {
@@ -603,7 +688,7 @@ struct LinearEpiT : LinearEpiData {
       v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + r4.w);
     }
     __syncwarp();                  // every lane has read the residual box: refill it for the next chunk
-    prefetch_res(e, next_col0);
+    prefetch_chunk(st, e, next_col0);
     if (e.lane == 0) bulk_wait_read0();  // the previous chunk's stores have left the staging buffers
     __syncwarp();
     if (C) {
@@ -678,10 +763,10 @@ struct LinearEpiT : LinearEpiData {
     } else if constexpr (MODE == 1) {
       if (e.slab_rows <= 0) return;
       switch (act) {
-        case ACT_RELU: drain_tma<ACT_RELU>(e, col0, v); break;
-        case ACT_GELU: drain_tma<ACT_GELU>(e, col0, v); break;
-        case ACT_LRELU: drain_tma<ACT_LRELU>(e, col0, v); break;
-        default: drain_tma<ACT_NONE>(e, col0, v); break;
+        case ACT_RELU: drain_tma<ACT_RELU>(st, e, col0, next_col0, v); break;
+        case ACT_GELU: drain_tma<ACT_GELU>(st, e, col0, next_col0, v); break;
+        case ACT_LRELU: drain_tma<ACT_LRELU>(st, e, col0, next_col0, v); break;
+        default: drain_tma<ACT_NONE>(st, e, col0, next_col0, v); break;
       }
     } else {
     EPI_DBG(0);
@@ -739,7 +824,7 @@ struct SoftmaxEpi {
   static constexpr bool kWholeTile = true;
   __device__ __forceinline__ void unit_begin(State&) const {}
   __device__ __forceinline__ void kernel_begin(State&) const {}
-  __device__ __forceinline__ void prefetch_res(const EpiCtx&, int) const {}
+  __device__ __forceinline__ void tile_begin(State&, const EpiCtx&, int, int) const {}
   __device__ __forceinline__ void unit_end(State&, const EpiCtx& e, long long, bool, int) const {
     if (e.lane == 0) bulk_wait_read0();
   }
@@ -826,7 +911,7 @@ struct MatchEpi {
     for (int t = 0; t < KC; ++t) { st.s[t] = INFINITY; st.i[t] = -1; }
   }
   __device__ __forceinline__ void kernel_begin(State&) const {}
-  __device__ __forceinline__ void prefetch_res(const EpiCtx&, int) const {}
+  __device__ __forceinline__ void tile_begin(State&, const EpiCtx&, int, int) const {}
   __device__ __forceinline__ void chunk(State& st, const EpiCtx&, long long, bool row_ok, int col0,
                                         const uint32_t (&v)[32], int) const {
     if (!row_ok || col0 >= N) return;
@@ -1052,6 +1137,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       EpiCtx ectx;
       ectx.stage = smem_u32(epi_stage + (warp - 2) * (Epi::kStageBytes / EPI_WARPS));
       ectx.res_bar = smem_u32(&res_bar[warp - 2]);
+      ectx.bias_smem = ectx.stage + (uint32_t)(Epi::kStageBytes / EPI_WARPS) - 512u;
       ectx.col_off = 0;
       ectx.z = b;
       ectx.img = b;
@@ -1074,7 +1160,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // the tile's BN/32 column chunks are split between the two warps that share a lane quarter
         constexpr int kSplitCol = ((BN / 32 + 1) / 2) * 32;
         const int c_begin = ectx.half == 0 ? 0 : kSplitCol, c_end = ectx.half == 0 ? kSplitCol : BN;
-        if (c_begin < c_end) epi.prefetch_res(ectx, nt * BN + c_begin);  // overlaps the tile's main loop
+        if (c_begin < c_end) epi.tile_begin(st, ectx, nt * BN + c_begin, c_end - c_begin);  // overlaps the main loop
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
 #ifdef MOCHA_TRACE
@@ -1321,6 +1407,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     EpiCtx ectx;
     ectx.stage = smem_u32(epi_stage + (warp - 2) * (Epi::kStageBytes / EPI_WARPS));
     ectx.res_bar = smem_u32(&res_bar[warp - 2]);
+    ectx.bias_smem = ectx.stage + (uint32_t)(Epi::kStageBytes / EPI_WARPS) - 512u;
     ectx.lane = lane; ectx.half = (warp - 2) >> 2; ectx.c_off = 0; ectx.col_off = 0;
     for (int u = cid; u < sh.units; u += ncl) {
       int mt, split;
@@ -1336,7 +1423,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int nt_end = min(sh.tiles_n, (split + 1) * sh.tiles_per_unit);
       for (int nt = split * sh.tiles_per_unit; nt < nt_end; ++nt) {
         const int c_begin = ectx.half * (BN / 2), c_end = c_begin + BN / 2;
-        epi.prefetch_res(ectx, nt * BN + c_begin);
+        epi.tile_begin(st, ectx, nt * BN + c_begin, c_end - c_begin);
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
 #ifdef MOCHA_TRACE
@@ -2170,6 +2257,12 @@ int tc_match_coarse_splitk(const __nv_bfloat16* Q16, int nq, const __nv_bfloat16
 #ifdef MOCHA_TRACE
 extern "C" int mocha_debug_get_epi(unsigned long long* host16) {
   return cudaMemcpyFromSymbol(host16, mocha::g_epi_dbg, 16 * sizeof(unsigned long long)) == cudaSuccess ? 0 : 1;
+}
+// trace build only: bf16-in / bf16-out linear layer as the bf16 path runs it (A16 [M,K], W16 [N,K], out16 [M,N])
+extern "C" int mocha_debug_linear_bf16(const void* A16, const void* W16, const float* bias, const float* res, float* out32,
+                                       void* out16, int M, int N, int K, int act, void* stream) {
+  return mocha::tc_linear_bf16((const __nv_bfloat16*)A16, K, (const __nv_bfloat16*)W16, bias, 0, res,
+                               mocha::TcOut{out32, (__nv_bfloat16*)out16, 0}, M, N, K, act, (cudaStream_t)stream);
 }
 extern "C" int mocha_debug_set_mode(int mode) {
   return cudaMemcpyToSymbol(mocha::g_tc_dbg_mode, &mode, sizeof(mode)) == cudaSuccess ? 0 : 1;
