@@ -343,9 +343,10 @@ struct LinearEpiT : LinearEpiData {
   // transposition buffer
   // MODE 1 writes one output per launch (the host falls back to MODE 0 otherwise), so its bf16 box
   // aliases the fp32 box and a fourth operand stage fits beside a 128 x 256 tile's staging
-  // + 512 B per warp for the tile's column-bias slice
-  static constexpr int kWarpStageBytes = MODE == 2 ? 10752 : MODE == 1 ? 4608 : 5120;
-  static constexpr int kBiasOff = MODE == 2 ? 10240 : 4096;
+  // + 512 B per warp for the tile's column-bias slice; the per-warp stride stays a multiple of 1 KB
+  // because the 128 B-swizzled boxes must be 1 KB aligned
+  static constexpr int kWarpStageBytes = MODE == 2 ? 11264 : 5120;
+  static_assert(kWarpStageBytes % 1024 == 0, "swizzled TMA boxes need 1 KB alignment");
   static constexpr int kStageBytes = EPI_WARPS * kWarpStageBytes;
   static constexpr uint64_t kHintA = 0, kHintB = 0;                // default L2 policy
   static constexpr bool kTf32 = false;
@@ -1137,7 +1138,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       EpiCtx ectx;
       ectx.stage = smem_u32(epi_stage + (warp - 2) * (Epi::kStageBytes / EPI_WARPS));
       ectx.res_bar = smem_u32(&res_bar[warp - 2]);
-      ectx.bias_smem = ectx.stage + (uint32_t)(Epi::kStageBytes / EPI_WARPS) - 512u;
+      ectx.bias_smem = ectx.stage + (uint32_t)(Epi::kStageBytes / EPI_WARPS) - 1024u;
       ectx.col_off = 0;
       ectx.z = b;
       ectx.img = b;
@@ -1407,7 +1408,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     EpiCtx ectx;
     ectx.stage = smem_u32(epi_stage + (warp - 2) * (Epi::kStageBytes / EPI_WARPS));
     ectx.res_bar = smem_u32(&res_bar[warp - 2]);
-    ectx.bias_smem = ectx.stage + (uint32_t)(Epi::kStageBytes / EPI_WARPS) - 512u;
+    ectx.bias_smem = ectx.stage + (uint32_t)(Epi::kStageBytes / EPI_WARPS) - 1024u;
     ectx.lane = lane; ectx.half = (warp - 2) >> 2; ectx.c_off = 0; ectx.col_off = 0;
     for (int u = cid; u < sh.units; u += ncl) {
       int mt, split;
@@ -1698,6 +1699,7 @@ int dispatch_bn_impl(int bn, const CUtensorMap& tmA, const void* Wptr, unsigned 
 // LinearEpi launches: one kernel family per epilogue mode
 int dispatch_bn(int bn, const CUtensorMap& tmA, const void* Wptr, unsigned long long wrows, unsigned long long K,
                 TcShape sh, int N, int num_kb, const LinearEpi& epi, cudaStream_t s, unsigned long long wpitch = 0) {
+  if (epi.tma == 2 && bn == 256) bn = 128;  // the residual / two-output staging leaves room for 32 KB stages only
   if (epi.tma == 2) return dispatch_bn_impl(bn, tmA, Wptr, wrows, K, sh, N, num_kb, LinearEpiT<2>{epi}, s, wpitch);
   if (epi.tma == 1) return dispatch_bn_impl(bn, tmA, Wptr, wrows, K, sh, N, num_kb, LinearEpiT<1>{epi}, s, wpitch);
   return dispatch_bn_impl(bn, tmA, Wptr, wrows, K, sh, N, num_kb, LinearEpiT<0>{epi}, s, wpitch);
