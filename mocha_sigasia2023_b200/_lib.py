@@ -48,6 +48,7 @@ class GeneratorWeights(C.Structure):
         + [(n, C.c_void_p) for n in (
             "tm_A_b", "tm_bb_gcn_w", "tm_bb_gcn_bias2d", "tm_bb_tcn_w", "tm_bb_tcn_b", "tm_jb_gcn_w",
             "tm_jb_gcn_b", "tm_A2", "tm_jb_tcn_w", "tm_jb_tcn_b", "tm_out_w", "tm_out_b")]
+        + [("jb_gcn_w_aug", C.c_void_p), ("jb_gcn_kaug", C.c_int)]
     )
 
 

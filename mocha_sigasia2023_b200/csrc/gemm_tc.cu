@@ -1505,12 +1505,13 @@ int make_tmap(CUtensorMap* tm, const void* ptr, unsigned long long rows, unsigne
 // Output maps of the TMA-store epilogue: {cols, rows per image, images}, box 32 cols x 32 rows x 1.
 // fp32 boxes are 128 B-swizzled (the epilogue transposes through them), bf16 boxes 64 B-swizzled.
 int make_out_tmap(CUtensorMap* tm, const void* ptr, unsigned long long cols, unsigned long long rows_per_img,
-                  unsigned long long imgs, unsigned long long ld_elems, bool f32) {
+                  unsigned long long imgs, unsigned long long ld_elems, bool f32, unsigned long long img_pitch_rows = 0) {
+  if (img_pitch_rows == 0) img_pitch_rows = rows_per_img;
   const unsigned long long esz = f32 ? 4 : 2;
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(MOCHA_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t gdim[3] = {cols, rows_per_img, imgs};
-  cuuint64_t gstride[2] = {ld_elems * esz, rows_per_img * ld_elems * esz};
+  cuuint64_t gstride[2] = {ld_elems * esz, img_pitch_rows * ld_elems * esz};
   cuuint32_t box[3] = {32, 32, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim,
@@ -1522,7 +1523,8 @@ int make_out_tmap(CUtensorMap* tm, const void* ptr, unsigned long long cols, uns
 }
 
 // Switch a LinearEpi to the TMA-store path when its outputs allow it (plain / tconv mode only).
-int setup_out_tma(LinearEpi& epi, unsigned long long rows_per_img, unsigned long long imgs, unsigned long long cols = 0) {
+int setup_out_tma(LinearEpi& epi, unsigned long long rows_per_img, unsigned long long imgs, unsigned long long cols = 0,
+                  unsigned long long img_pitch_rows = 0) {
   epi.tma = 0;
   if (cols == 0) cols = (unsigned long long)epi.N;
   static const bool off = getenv("MOCHA_NO_TMA_STORE") != nullptr;  // debugging aid: force the LSU epilogue
@@ -1533,11 +1535,11 @@ int setup_out_tma(LinearEpi& epi, unsigned long long rows_per_img, unsigned long
   if (!ok) return MOCHA_OK;
   const bool with_res = epi.res && epi.bias_period == 0;
   if (epi.C && epi.C16 && !with_res) return MOCHA_OK;  // two outputs without a residual: LSU epilogue
-  if (epi.C) MOCHA_TRY(make_out_tmap(&epi.tmC, epi.C, cols, rows_per_img, imgs, (unsigned long long)epi.ldc, true));
-  if (epi.C16) MOCHA_TRY(make_out_tmap(&epi.tmC16, epi.C16, cols, rows_per_img, imgs, (unsigned long long)epi.ldc, false));
+  if (epi.C) MOCHA_TRY(make_out_tmap(&epi.tmC, epi.C, cols, rows_per_img, imgs, (unsigned long long)epi.ldc, true, img_pitch_rows));
+  if (epi.C16) MOCHA_TRY(make_out_tmap(&epi.tmC16, epi.C16, cols, rows_per_img, imgs, (unsigned long long)epi.ldc, false, img_pitch_rows));
   epi.tma = 1;
   if (with_res) {
-    MOCHA_TRY(make_out_tmap(&epi.tmR, epi.res, cols, rows_per_img, imgs, (unsigned long long)epi.ldc, true));
+    MOCHA_TRY(make_out_tmap(&epi.tmR, epi.res, cols, rows_per_img, imgs, (unsigned long long)epi.ldc, true, img_pitch_rows));
     epi.tma = 2;
   }
   return MOCHA_OK;
@@ -1760,6 +1762,31 @@ int tc_linear_bf16(const __nv_bfloat16* A16, int lda, const __nv_bfloat16* W16, 
                      ceil_div(K, BLOCK_K), epi, s);
 }
 
+// Same GEMM over `nb` images of rows_per_img rows each (A dense [nb*rows_per_img, K]); image b's output
+// rows start at out + b * out_img_pitch_rows * N, so the result can land inside a larger (e.g. time-padded)
+// tensor. TMA-store epilogue only (column bias or none, one output).
+int tc_linear_bf16_img(const __nv_bfloat16* A16, int lda, const __nv_bfloat16* W16, const float* bias, TcOut out, int nb,
+                       int rows_per_img, long long out_img_pitch_rows, int N, int K, int act, cudaStream_t s) {
+  MOCHA_CHECK_ARG(A16 && W16 && (out.f32 || out.bf16) && !(out.f32 && out.bf16), "tc_linear_img: bad operands");
+  MOCHA_CHECK_ARG(tc_linear_supported(rows_per_img, N, K) && nb > 0, "tc_linear_img: unsupported shape");
+  CUtensorMap tmA;
+  MOCHA_TRY(make_tmap(&tmA, A16, (unsigned long long)nb * rows_per_img, (unsigned long long)K, BLOCK_M, (unsigned long long)lda));
+  TcShape sh{};
+  sh.nb = nb;
+  sh.rows_out_per_b = rows_per_img;
+  sh.tiles_m_per_b = ceil_div(rows_per_img, BLOCK_M);
+  sh.tiles_m_total = sh.tiles_m_per_b * nb;
+  sh.src_rows_per_b = rows_per_img;
+  sh.taps = 1;
+  sh.kb_per_tap = ceil_div(K, BLOCK_K);
+  sh.tap_row_stride = 0;
+  LinearEpi epi{out.f32, N, N, bias, 0, nullptr, act, out.bf16, out.lrelu};
+  MOCHA_TRY(setup_out_tma(epi, (unsigned long long)rows_per_img, (unsigned long long)nb, 0, (unsigned long long)out_img_pitch_rows));
+  if (epi.tma != 1) return set_error(MOCHA_ERR_ARG, "tc_linear_img: output is not TMA-storable");
+  return dispatch_bn(pick_bn(sh.tiles_m_total, N), tmA, W16, (unsigned long long)N, (unsigned long long)K, sh, N,
+                     ceil_div(K, BLOCK_K), epi, s);
+}
+
 int tc_linear(const float* A, const float* W, const float* bias, int bias_period, const float* res, float* C, int M,
               int N, int K, int act, int a_lrelu, Workspace& ws, cudaStream_t s) {
   const __nv_bfloat16* W16 = tc_lookup_bf16(W);
@@ -1794,7 +1821,8 @@ int tc_tconv(const float* X, const float* W, const float* bias, int bias_period,
 }
 
 int tc_tconv_ex(const float* X, const __nv_bfloat16* Xh, const float* W, const float* bias, int bias_period, TcOut out,
-                int B, int T, int V, int Cin, int Cout, int taps, int tdiv, Workspace& ws, cudaStream_t s, int repeat) {
+                int B, int T, int V, int Cin, int Cout, int taps, int tdiv, Workspace& ws, cudaStream_t s, int repeat,
+                bool xh_is_padded) {
   MOCHA_CHECK_ARG((X || Xh) && (out.f32 || out.bf16), "tc_tconv: null operand");
   MOCHA_CHECK_ARG(tdiv >= 1 && T % tdiv == 0, "tc_tconv: T=%d not a multiple of tdiv=%d", T, tdiv);
   MOCHA_CHECK_ARG(tc_tconv_supported(B, T, V, Cin, Cout, taps), "tc_tconv: unsupported geometry");
@@ -1803,18 +1831,24 @@ int tc_tconv_ex(const float* X, const __nv_bfloat16* Xh, const float* W, const f
   const int pad = taps / 2, Tp = T + 2 * pad;
   const size_t mark = ws.off;
   const size_t elems = (size_t)B * Tp * V * Cin;
-  __nv_bfloat16* X16 = ws.take<__nv_bfloat16>(elems);
-  if (!X16) return set_error(MOCHA_ERR_WORKSPACE, "tc_tconv: workspace too small for the padded bf16 operand");
-  if (Xh)
+  MOCHA_CHECK_ARG(!xh_is_padded || (Xh && tdiv == 1), "tc_tconv: a pre-padded operand must be bf16 with tdiv = 1");
+  const __nv_bfloat16* X16c = xh_is_padded ? Xh : nullptr;   // [B, Tp, V, Cin] reflect-padded by the producer
+  __nv_bfloat16* X16 = xh_is_padded ? nullptr : ws.take<__nv_bfloat16>(elems);
+  if (!xh_is_padded && !X16) return set_error(MOCHA_ERR_WORKSPACE, "tc_tconv: workspace too small for the padded bf16 operand");
+  if (xh_is_padded) {
+  } else if (Xh)
     reflect_pad_copy_kernel<<<(unsigned)((elems / 8 + 255) / 256), 256, 0, s>>>(Xh, X16, T, V, Cin, pad, tdiv,
                                                                                (long long)(elems / 8));
   else
     reflect_pad_cast_kernel<<<(unsigned)((elems / 4 + 255) / 256), 256, 0, s>>>(X, X16, T, V, Cin, pad, tdiv,
                                                                                (long long)(elems / 4));
-  count_launch();
-  MOCHA_LAUNCH_CHECK("reflect_pad_cast");
+  if (!xh_is_padded) {
+    count_launch();
+    MOCHA_LAUNCH_CHECK("reflect_pad_cast");
+    X16c = X16;
+  }
   CUtensorMap tmA;
-  MOCHA_TRY(make_tmap(&tmA, X16, (unsigned long long)B * Tp * V, (unsigned long long)Cin, BLOCK_M));
+  MOCHA_TRY(make_tmap(&tmA, X16c, (unsigned long long)B * Tp * V, (unsigned long long)Cin, BLOCK_M));
   TcShape sh{};
   sh.nb = B;
   sh.rows_out_per_b = T * V;

@@ -44,7 +44,11 @@ int tc_tconv(const float* X, const float* W, const float* bias, int bias_period,
              int Cin, int Cout, int taps, int tdiv, Workspace& ws, cudaStream_t s, int repeat = 1);
 // X or Xh (bf16 source) may be given; output fp32 and/or bf16
 int tc_tconv_ex(const float* X, const __nv_bfloat16* Xh, const float* W, const float* bias, int bias_period, TcOut out,
-                int B, int T, int V, int Cin, int Cout, int taps, int tdiv, Workspace& ws, cudaStream_t s, int repeat = 1);
+                int B, int T, int V, int Cin, int Cout, int taps, int tdiv, Workspace& ws, cudaStream_t s, int repeat = 1,
+                bool xh_is_padded = false);  // Xh already is the reflect-padded [B, T + 2*(taps/2), V, Cin] tensor
+// GEMM over nb images whose outputs land at out + b * out_img_pitch_rows * N (TMA-store epilogue, column bias)
+int tc_linear_bf16_img(const __nv_bfloat16* A16, int lda, const __nv_bfloat16* W16, const float* bias, TcOut out, int nb,
+                       int rows_per_img, long long out_img_pitch_rows, int N, int K, int act, cudaStream_t s);
 
 // ---- attention: softmax(Q K^T / sqrt(dh)) V for B*H (batch, head) problems on tensor cores ------------
 // q/k/v are fp32 strided views [B*n, ld] with head h at columns h*dh; S is a [B,H,nq,nkv] fp32 scratch.

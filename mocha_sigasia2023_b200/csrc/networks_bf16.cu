@@ -55,16 +55,34 @@ int embed_bf16(const mocha_generator_weights* w, const float* X, int B, float* t
   const mocha_dims& d = w->dims;
   Tc tc{s, ws};
   const int R = B * d.T * d.V, Tp = d.T / d.tp, R2 = B * Tp * d.P;
-  bf16* agg = ws.take<bf16>((size_t)R * d.Kj * d.C0);
-  bf16* g = ws.take<bf16>((size_t)R * d.D);
   bf16* h1 = ws.take<bf16>((size_t)R * d.D);
   bf16* agg2 = ws.take<bf16>((size_t)R2 * d.Kb * d.D);
   bf16* g2 = ws.take<bf16>((size_t)R2 * d.D);
   WS_OK(ws, "mocha_embed_fwd(bf16)");
-  // Conv2d 1x1 Cin(15)->C0 + LeakyReLU + graph aggregation in one kernel (K = 15 is too short for a TMA row)
-  MOCHA_TRY(embed_graph_agg(X, w->emb_w, w->emb_b, w->A_j, agg, B * d.T, d.V, d.Cin, d.C0, d.Kj, s));
-  MOCHA_TRY(tc.lin(agg, d.Kj * d.C0, w->jb_gcn_w, w->jb_gcn_bias2d, d.V, nullptr, h16(g), R, d.D, d.Kj * d.C0, ACT_NONE));
-  MOCHA_TRY(tc_tconv_ex(nullptr, g, w->jb_tcn_w, w->jb_tcn_b, 0, h16(h1), B, d.T, d.V, d.D, d.D, d.taps_j, 1, ws, s));
+  const int KC = d.Kj * d.C0;
+  if (w->jb_gcn_w_aug && w->jb_gcn_kaug >= KC + d.Kj && w->jb_gcn_kaug % 64 == 0 && (d.taps_j & 1)) {
+    // bias folded into the GEMM (Kj extra K columns x adjacency column sums) -> plain single-pass epilogue,
+    // and the GEMM's TMA stores land directly in the interior of the temporal conv's reflect-padded input
+    const int Ka = w->jb_gcn_kaug, pad = d.taps_j / 2, Tpad = d.T + 2 * pad;
+    const __nv_bfloat16* W16 = tc_lookup_bf16(w->jb_gcn_w_aug);
+    if (!W16) return set_error(MOCHA_ERR_ARG, "mocha_embed_fwd: jb_gcn_w_aug has no registered bf16 mirror");
+    bf16* agga = ws.take<bf16>((size_t)R * Ka);
+    bf16* gpad = ws.take<bf16>((size_t)B * Tpad * d.V * d.D);
+    WS_OK(ws, "mocha_embed_fwd(bf16)");
+    MOCHA_TRY(embed_graph_agg(X, w->emb_w, w->emb_b, w->A_j, agga, B * d.T, d.V, d.Cin, d.C0, d.Kj, s, Ka));
+    MOCHA_TRY(tc_linear_bf16_img(agga, Ka, W16, nullptr, h16(gpad + (size_t)pad * d.V * d.D), B, d.T * d.V,
+                                 (long long)Tpad * d.V, d.D, Ka, ACT_NONE, s));
+    MOCHA_TRY(reflect_border_fill(gpad, B, d.T, pad, (long long)d.V * d.D, s));
+    MOCHA_TRY(tc_tconv_ex(nullptr, gpad, w->jb_tcn_w, w->jb_tcn_b, 0, h16(h1), B, d.T, d.V, d.D, d.D, d.taps_j, 1, ws, s, 1, true));
+  } else {
+    // Conv2d 1x1 Cin(15)->C0 + LeakyReLU + graph aggregation in one kernel (K = 15 is too short for a TMA row)
+    bf16* agg = ws.take<bf16>((size_t)R * KC);
+    bf16* g = ws.take<bf16>((size_t)R * d.D);
+    WS_OK(ws, "mocha_embed_fwd(bf16)");
+    MOCHA_TRY(embed_graph_agg(X, w->emb_w, w->emb_b, w->A_j, agg, B * d.T, d.V, d.Cin, d.C0, d.Kj, s));
+    MOCHA_TRY(tc.lin(agg, KC, w->jb_gcn_w, w->jb_gcn_bias2d, d.V, nullptr, h16(g), R, d.D, KC, ACT_NONE));
+    MOCHA_TRY(tc_tconv_ex(nullptr, g, w->jb_tcn_w, w->jb_tcn_b, 0, h16(h1), B, d.T, d.V, d.D, d.D, d.taps_j, 1, ws, s));
+  }
   // joint -> body-part pooling + the BodyBlock's LeakyReLU and graph aggregation in one pass over h1
   MOCHA_TRY(pool_graph_agg(h1, w->pool_w, w->A_b, agg2, B, d.T, d.V, d.P, d.D, d.tp, d.Kb, s));
   MOCHA_TRY(tc.lin(agg2, d.Kb * d.D, w->bb_gcn_w, w->bb_gcn_bias2d, d.P, nullptr, h16(g2), R2, d.D, d.Kb * d.D, ACT_NONE));

@@ -60,7 +60,7 @@ template <int G>
 __global__ void __launch_bounds__(256)
 embed_graph_agg_kernel(const float* __restrict__ X, const float* __restrict__ Wemb, const float* __restrict__ bemb,
                        const float* __restrict__ A, __nv_bfloat16* __restrict__ out16, int BT, int V, int Cin, int C,
-                       int Kk) {
+                       int Kk, int ldo) {
   extern __shared__ float sm[];
   float* xs = sm;                                     // [G*V][C]   activated h0
   float* xin = xs + G * V * C;                        // [G*V][16]  raw inputs, rows padded to 16 floats
@@ -125,7 +125,15 @@ embed_graph_agg_kernel(const float* __restrict__ X, const float* __restrict__ We
   for (int r = warp; r < rows; r += 8) {
     const int g = r / V, w = r - g * V;
     const float* xg = xs + g * V * C;
-    __nv_bfloat16* dst = out16 + ((long long)bt0 * V + r) * KC;
+    __nv_bfloat16* dst = out16 + ((long long)bt0 * V + r) * ldo;
+    // tail columns [KC, ldo): the Kk adjacency column sums of node w (they multiply the per-partition
+    // biases folded into the GEMM weights), then zeros
+    for (int t = 2 * lane; t < ldo - KC; t += 64) {
+      float c0 = 0.f, c1 = 0.f;
+      if (t < Kk) for (int i = 0; i < cnt[t * V + w]; ++i) c0 += val[(t * V + w) * V + i];
+      if (t + 1 < Kk) for (int i = 0; i < cnt[(t + 1) * V + w]; ++i) c1 += val[((t + 1) * V + w) * V + i];
+      *reinterpret_cast<__nv_bfloat162*>(dst + KC + t) = __floats2bfloat162_rn(c0, c1);
+    }
     for (int k = 0; k < Kk; ++k) {
       const int kw = k * V + w;
       for (int cp = lane; cp < C / 2; cp += 32) {
@@ -707,7 +715,9 @@ int graph_agg_first(const float* in, const float* A, float* out, int BT, int V, 
 }
 
 int embed_graph_agg(const float* X, const float* Wemb, const float* bemb, const float* A, __nv_bfloat16* out16, int BT,
-                    int V, int Cin, int C, int Kk, cudaStream_t s) {
+                    int V, int Cin, int C, int Kk, cudaStream_t s, int ldo) {
+  if (ldo <= 0) ldo = Kk * C;
+  MOCHA_CHECK_ARG(ldo >= Kk * C && (ldo & 1) == 0, "embed_graph_agg: bad output pitch %d", ldo);
   MOCHA_CHECK_ARG(X && Wemb && A && out16 && BT > 0 && V > 0 && Cin > 0 && Kk > 0, "embed_graph_agg: bad args");
   MOCHA_CHECK_ARG(C >= 2 && C <= 256 && (C & 1) == 0 && 256 % C == 0, "embed_graph_agg: C=%d unsupported", C);
   MOCHA_CHECK_ARG(Cin <= EMB_MAXCIN, "embed_graph_agg: Cin=%d > %d unsupported", Cin, EMB_MAXCIN);
@@ -721,9 +731,34 @@ int embed_graph_agg(const float* X, const float* Wemb, const float* bemb, const 
       MOCHA_CUDA(cudaFuncSetAttribute(embed_graph_agg_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  embed_graph_agg_kernel<G><<<(BT + G - 1) / G, 256, smem, s>>>(X, Wemb, bemb, A, out16, BT, V, Cin, C, Kk);
+  embed_graph_agg_kernel<G><<<(BT + G - 1) / G, 256, smem, s>>>(X, Wemb, bemb, A, out16, BT, V, Cin, C, Kk, ldo);
   count_launch();
   MOCHA_LAUNCH_CHECK("embed_graph_agg");
+  return MOCHA_OK;
+}
+
+// reflect-pad borders of a [B, T + 2*pad, V*C] bf16 tensor whose interior rows are already written
+__global__ void reflect_border_kernel(__nv_bfloat16* __restrict__ xp, int T, int pad, long long row8, long long total8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const long long e = i % row8;
+  const long long r = i / row8;
+  const int j = (int)(r % (2 * pad));
+  const long long b = r / (2 * pad);
+  const int Tp = T + 2 * pad;
+  const int tp = j < pad ? j : T + j;           // padded index of the border frame
+  int t = tp - pad;
+  t = t < 0 ? -t : 2 * (T - 1) - t;             // reflected source frame
+  uint4* base = reinterpret_cast<uint4*>(xp) + b * Tp * row8;
+  base[(long long)tp * row8 + e] = base[(long long)(t + pad) * row8 + e];
+}
+
+int reflect_border_fill(__nv_bfloat16* xp, int B, int T, int pad, long long row_elems, cudaStream_t s) {
+  MOCHA_CHECK_ARG(xp && B > 0 && T > pad && pad > 0 && row_elems % 8 == 0, "reflect_border_fill: bad args");
+  const long long row8 = row_elems / 8, total8 = (long long)B * 2 * pad * row8;
+  reflect_border_kernel<<<blocks_for(total8, 256), 256, 0, s>>>(xp, T, pad, row8, total8);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("reflect_border_fill");
   return MOCHA_OK;
 }
 

@@ -15,8 +15,12 @@ int graph_agg_first(const float* in, const float* A, float* out, int BT, int V, 
 
 // Fused Conv2d 1x1 (Cin -> C) + LeakyReLU + graph aggregation of the tensor-core path:
 // out16[(bt,w), k*C + c] = sum_u lrelu(X[(bt,u), :] . Wemb[c, :] + bemb[c]) * A[k,u,w]
+// ldo > Kk*C: rows are padded to ldo columns; columns Kk*C .. Kk*C+Kk-1 hold sum_u A[k,u,w] (for biases folded
+// into the following GEMM as extra K columns), the rest zeros
 int embed_graph_agg(const float* X, const float* Wemb, const float* bemb, const float* A, __nv_bfloat16* out16, int BT,
-                    int V, int Cin, int C, int Kk, cudaStream_t s);
+                    int V, int Cin, int C, int Kk, cudaStream_t s, int ldo = 0);
+// copies the 2*pad reflect-padding frames of xp [B, T + 2*pad, row_elems] from its already written interior
+int reflect_border_fill(__nv_bfloat16* xp, int B, int T, int pad, long long row_elems, cudaStream_t s);
 
 // out[(bt,w), c] = sum_k sum_u in[(bt,u), k*C + c] * A2[k,u,w]   (U input nodes, Wn output nodes)
 // Same einsum applied after the 1x1 convolution (used by to_mot's JointBlock, where the

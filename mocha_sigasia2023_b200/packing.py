@@ -74,6 +74,19 @@ def _gcn_first(w: torch.Tensor, b: torch.Tensor, A: torch.Tensor):
     return wp, bias2d
 
 
+def _gcn_first_aug(w: torch.Tensor, b: torch.Tensor, A: torch.Tensor) -> torch.Tensor:
+    """W' of _gcn_first with K extra columns holding the per-partition biases b[k*Cout+co] (they multiply the
+    adjacency column sums that the aggregation kernel appends to its rows), zero-padded to a multiple of 64."""
+    K = A.shape[0]
+    wp, _ = _gcn_first(w, b, A)
+    co = wp.shape[0]
+    kaug = (wp.shape[1] + K + 63) // 64 * 64
+    out = torch.zeros((co, kaug), dtype=torch.float32)
+    out[:, :wp.shape[1]] = wp
+    out[:, wp.shape[1]:wp.shape[1] + K] = b.reshape(K, co).t()
+    return out.contiguous()
+
+
 def generator_tensors(sd: "dict[str, torch.Tensor]", cfg: dict) -> "dict[str, torch.Tensor]":
     sd = {k: v.detach().to(torch.float32).cpu() for k, v in sd.items()}
     out = {}
@@ -82,6 +95,9 @@ def generator_tensors(sd: "dict[str, torch.Tensor]", cfg: dict) -> "dict[str, to
     A_j = sd["mot_embedding.2.A_j"]
     out["A_j"] = A_j
     out["jb_gcn_w"], out["jb_gcn_bias2d"] = _gcn_first(
+        sd["mot_embedding.2.blk.gcn.conv.weight"], sd["mot_embedding.2.blk.gcn.conv.bias"], A_j)
+    # tensor-core path: bias folded into the GEMM (extra K columns x adjacency column sums), K padded to 64
+    out["jb_gcn_w_aug"] = _gcn_first_aug(
         sd["mot_embedding.2.blk.gcn.conv.weight"], sd["mot_embedding.2.blk.gcn.conv.bias"], A_j)
     out["jb_tcn_w"] = _conv_as_gemm(sd["mot_embedding.2.blk.tcn.weight"])
     out["jb_tcn_b"] = sd["mot_embedding.2.blk.tcn.bias"]
@@ -173,6 +189,8 @@ class PackedGenerator:
                      "tm_bb_gcn_w", "tm_bb_gcn_bias2d", "tm_bb_tcn_w", "tm_bb_tcn_b", "tm_jb_gcn_w", "tm_jb_gcn_b",
                      "tm_A2", "tm_jb_tcn_w", "tm_jb_tcn_b", "tm_out_w", "tm_out_b"):
             setattr(w, name, b.ptr(name))
+        w.jb_gcn_w_aug = b.ptr("jb_gcn_w_aug")
+        w.jb_gcn_kaug = int(b.shapes["jb_gcn_w_aug"][1])
         for l in range(cfg["encoder_depth"]):
             for f in ("wqkv", "wo", "bo", "w1", "b1", "w2", "b2"):
                 setattr(w.enc[l], f, b.ptr(f"enc{l}.{f}"))
