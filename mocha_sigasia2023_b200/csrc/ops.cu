@@ -56,6 +56,10 @@ __global__ void graph_agg_first_kernel(const float* __restrict__ in, const float
 // One block owns G consecutive frames: the adjacency lists, the 1x1 weights and the G x V x Cin inputs
 // are staged once, h0 never leaves shared memory (saves a 2 x 47 MB round trip per 128 clips).
 constexpr int EMB_MAXCIN = 16;
+// The kernel is issue-bound (ncu: 81 % issue slots busy), so the layout minimises instructions per
+// output: phase 2 computes 2 channels x 12 rows per thread with the 1x1 weights in registers, phase 3
+// gives each half-warp one output row with 4 channels per lane (LDS.128 / 8 B stores) and walks exactly
+// the non-zero neighbours; the padded tail of a row is copied from a per-node table.
 template <int G>
 __global__ void __launch_bounds__(256)
 embed_graph_agg_kernel(const float* __restrict__ X, const float* __restrict__ Wemb, const float* __restrict__ bemb,
@@ -64,95 +68,90 @@ embed_graph_agg_kernel(const float* __restrict__ X, const float* __restrict__ We
   extern __shared__ float sm[];
   float* xs = sm;                                     // [G*V][C]   activated h0
   float* xin = xs + G * V * C;                        // [G*V][16]  raw inputs, rows padded to 16 floats
-  float* val = xin + G * V * EMB_MAXCIN;              // [Kk*V][V]  non-zero adjacency values
-  int* src = reinterpret_cast<int*>(val + Kk * V * V);  // [Kk*V][V] their source nodes
+  float* val = xin + G * V * EMB_MAXCIN;              // [Kk*V][V]  adjacency A[k][u][w] staged as [k][w][u], then compacted
+  int* src = reinterpret_cast<int*>(val + Kk * V * V);  // [Kk*V][V] source nodes of the non-zeros
   int* cnt = src + Kk * V * V;                        // [Kk*V]
-  __shared__ int nmax_s;
+  __nv_bfloat16* tails = reinterpret_cast<__nv_bfloat16*>(cnt + Kk * V);  // [V][ldo - Kk*C] row tails
   const int bt0 = blockIdx.x * G;
   const int rows = min(G, BT - bt0) * V;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) nmax_s = 0;
-  __syncthreads();
+  const int KC = Kk * C, tail = ldo - KC;
   for (int i = threadIdx.x; i < rows * EMB_MAXCIN; i += blockDim.x) {
     const int r = i / EMB_MAXCIN, k = i - r * EMB_MAXCIN;
     xin[i] = k < Cin ? X[((long long)bt0 * V + r) * Cin + k] : 0.f;
   }
-  // compact neighbour lists, one warp per (k, w): ballot keeps the sources in ascending order
-  for (int kw = warp; kw < Kk * V; kw += 8) {
-    const int k = kw / V, w = kw - k * V;
-    int n = 0;
-    for (int u0 = 0; u0 < V; u0 += 32) {
-      const int u = u0 + lane;
-      const float a = u < V ? A[(k * V + u) * V + w] : 0.f;
-      const unsigned m = __ballot_sync(0xffffffffu, a != 0.f);
-      if (a != 0.f) {
-        const int pos = n + __popc(m & ((1u << lane) - 1u));
-        val[kw * V + pos] = a; src[kw * V + pos] = u;
-      }
-      n += __popc(m);
-    }
-    // pad the list with zero-weight entries so that every list can be walked with one uniform, unrolled
-    // trip count (independent loads instead of a dependent index -> value chain per neighbour)
-    for (int i = n + lane; i < V; i += 32) { val[kw * V + i] = 0.f; src[kw * V + i] = 0; }
-    if (lane == 0) { cnt[kw] = n; atomicMax(&nmax_s, n); }
+  for (int i = threadIdx.x; i < Kk * V * V; i += blockDim.x) {   // coalesced read, transposed to [k][w][u]
+    const int k = i / (V * V), rem = i - k * V * V, u = rem / V, w = rem - u * V;
+    val[(k * V + w) * V + u] = A[i];
   }
   __syncthreads();
-  const int nmax4 = min(V, (nmax_s + 3) & ~3);
-  // h0 = lrelu(x W^T + b): thread = channel c with its Cin weights in registers, rows striped over the block
+  if (threadIdx.x < Kk * V) {   // one thread compacts one (k, w) list in place (ascending sources)
+    const int kw = threadIdx.x;
+    int n = 0;
+    float sum = 0.f;
+    for (int u = 0; u < V; ++u) {
+      const float a = val[kw * V + u];
+      if (a != 0.f) { val[kw * V + n] = a; src[kw * V + n] = u * C; sum += a; ++n; }
+    }
+    cnt[kw] = n;
+    // tail of node w's rows: the Kk adjacency column sums (bias columns of the GEMM), then zeros
+    const int k = kw / V, w = kw - k * V;
+    if (k < tail) tails[w * tail + k] = __float2bfloat16_rn(sum);
+  }
+  for (int i = threadIdx.x; i < V * tail; i += blockDim.x)
+    if (i % tail >= Kk) tails[i] = __float2bfloat16_rn(0.f);
+  // h0 = lrelu(x W^T + b): thread = channel pair (weights in registers), rows striped over the block
   {
-    const int c = threadIdx.x % C, stripe = threadIdx.x / C, nstripes = blockDim.x / C;
-    float wr[EMB_MAXCIN];
+    const int C2 = C / 2;
+    const int cp = threadIdx.x % C2, stripe = threadIdx.x / C2, nstripes = blockDim.x / C2;
+    float w0[EMB_MAXCIN], w1[EMB_MAXCIN];
 #pragma unroll
-    for (int k = 0; k < EMB_MAXCIN; ++k) wr[k] = k < Cin ? Wemb[c * Cin + k] : 0.f;
-    const float b = bemb ? bemb[c] : 0.f;
+    for (int k = 0; k < EMB_MAXCIN; ++k) {
+      w0[k] = k < Cin ? Wemb[(2 * cp) * Cin + k] : 0.f;
+      w1[k] = k < Cin ? Wemb[(2 * cp + 1) * Cin + k] : 0.f;
+    }
+    const float b0 = bemb ? bemb[2 * cp] : 0.f, b1 = bemb ? bemb[2 * cp + 1] : 0.f;
     if (stripe < nstripes)
-#pragma unroll 4
       for (int r = stripe; r < rows; r += nstripes) {
         const float4* xr = reinterpret_cast<const float4*>(xin + r * EMB_MAXCIN);
-        float acc = b;
+        float a0 = b0, a1 = b1;
 #pragma unroll
         for (int k4 = 0; k4 < EMB_MAXCIN / 4; ++k4) {
           const float4 x4 = xr[k4];
-          acc = fmaf(x4.x, wr[4 * k4], acc); acc = fmaf(x4.y, wr[4 * k4 + 1], acc);
-          acc = fmaf(x4.z, wr[4 * k4 + 2], acc); acc = fmaf(x4.w, wr[4 * k4 + 3], acc);
+          a0 = fmaf(x4.x, w0[4 * k4], a0); a1 = fmaf(x4.x, w1[4 * k4], a1);
+          a0 = fmaf(x4.y, w0[4 * k4 + 1], a0); a1 = fmaf(x4.y, w1[4 * k4 + 1], a1);
+          a0 = fmaf(x4.z, w0[4 * k4 + 2], a0); a1 = fmaf(x4.z, w1[4 * k4 + 2], a1);
+          a0 = fmaf(x4.w, w0[4 * k4 + 3], a0); a1 = fmaf(x4.w, w1[4 * k4 + 3], a1);
         }
-        xs[r * C + c] = lrelu02(acc);
+        *reinterpret_cast<float2*>(xs + r * C + 2 * cp) = make_float2(lrelu02(a0), lrelu02(a1));
       }
   }
   __syncthreads();
-  // aggregation: warp = output row (frame, node), lane = channel pair (bf162 stores, 128 B per warp)
-  const int KC = Kk * C;
-  for (int r = warp; r < rows; r += 8) {
+  // aggregation: a group of C/4 lanes owns one output row, 4 channels per lane
+  const int C4 = C / 4, gpw = 32 / C4;                 // lanes per row, rows per warp pass
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane / C4, l4 = (lane - grp * C4) * 4;
+  const int ngroups = (blockDim.x >> 5) * gpw;
+  for (int r = warp * gpw + grp; r < rows; r += ngroups) {
     const int g = r / V, w = r - g * V;
-    const float* xg = xs + g * V * C;
-    __nv_bfloat16* dst = out16 + ((long long)bt0 * V + r) * ldo;
-    // tail columns [KC, ldo): the Kk adjacency column sums of node w (they multiply the per-partition
-    // biases folded into the GEMM weights), then zeros
-    for (int t = 2 * lane; t < ldo - KC; t += 64) {
-      float c0 = 0.f, c1 = 0.f;
-      if (t < Kk) for (int i = 0; i < cnt[t * V + w]; ++i) c0 += val[(t * V + w) * V + i];
-      if (t + 1 < Kk) for (int i = 0; i < cnt[(t + 1) * V + w]; ++i) c1 += val[((t + 1) * V + w) * V + i];
-      *reinterpret_cast<__nv_bfloat162*>(dst + KC + t) = __floats2bfloat162_rn(c0, c1);
-    }
+    const float* xg = xs + g * V * C + l4;
+    __nv_bfloat16* dst = out16 + ((long long)bt0 * V + r) * ldo + l4;
     for (int k = 0; k < Kk; ++k) {
-      const int kw = k * V + w;
-      for (int cp = lane; cp < C / 2; cp += 32) {
-        float a0 = 0.f, a1 = 0.f;
-        for (int i = 0; i < nmax4; i += 4) {
-          const int4 s4 = *reinterpret_cast<const int4*>(src + kw * V + i);
-          const float4 v4 = *reinterpret_cast<const float4*>(val + kw * V + i);
-          const float2 x0 = *reinterpret_cast<const float2*>(xg + s4.x * C + 2 * cp);
-          const float2 x1 = *reinterpret_cast<const float2*>(xg + s4.y * C + 2 * cp);
-          const float2 x2 = *reinterpret_cast<const float2*>(xg + s4.z * C + 2 * cp);
-          const float2 x3 = *reinterpret_cast<const float2*>(xg + s4.w * C + 2 * cp);
-          a0 = fmaf(x0.x, v4.x, a0); a1 = fmaf(x0.y, v4.x, a1);
-          a0 = fmaf(x1.x, v4.y, a0); a1 = fmaf(x1.y, v4.y, a1);
-          a0 = fmaf(x2.x, v4.z, a0); a1 = fmaf(x2.y, v4.z, a1);
-          a0 = fmaf(x3.x, v4.w, a0); a1 = fmaf(x3.y, v4.w, a1);
-        }
-        *reinterpret_cast<__nv_bfloat162*>(dst + k * C + 2 * cp) = __floats2bfloat162_rn(a0, a1);
+      const int kw = k * V + w, n = cnt[kw];
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < n; ++i) {
+        const float4 x = *reinterpret_cast<const float4*>(xg + src[kw * V + i]);
+        const float av = val[kw * V + i];
+        acc.x = fmaf(x.x, av, acc.x); acc.y = fmaf(x.y, av, acc.y);
+        acc.z = fmaf(x.z, av, acc.z); acc.w = fmaf(x.w, av, acc.w);
       }
+      __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y), hi = __floats2bfloat162_rn(acc.z, acc.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(dst + k * C) = pk;
     }
+    for (int t = l4; t < tail; t += C)   // tail <= C in practice: one 8 B copy per lane
+      *reinterpret_cast<uint2*>(dst + KC - l4 + t) = *reinterpret_cast<const uint2*>(tails + w * tail + t);
   }
 }
 
@@ -717,13 +716,14 @@ int graph_agg_first(const float* in, const float* A, float* out, int BT, int V, 
 int embed_graph_agg(const float* X, const float* Wemb, const float* bemb, const float* A, __nv_bfloat16* out16, int BT,
                     int V, int Cin, int C, int Kk, cudaStream_t s, int ldo) {
   if (ldo <= 0) ldo = Kk * C;
-  MOCHA_CHECK_ARG(ldo >= Kk * C && (ldo & 1) == 0, "embed_graph_agg: bad output pitch %d", ldo);
+  MOCHA_CHECK_ARG(ldo >= Kk * C && (ldo & 3) == 0, "embed_graph_agg: bad output pitch %d", ldo);
   MOCHA_CHECK_ARG(X && Wemb && A && out16 && BT > 0 && V > 0 && Cin > 0 && Kk > 0, "embed_graph_agg: bad args");
-  MOCHA_CHECK_ARG(C >= 2 && C <= 256 && (C & 1) == 0 && 256 % C == 0, "embed_graph_agg: C=%d unsupported", C);
+  MOCHA_CHECK_ARG(C >= 8 && C <= 128 && (C & 3) == 0 && 128 % C == 0, "embed_graph_agg: C=%d unsupported", C);
   MOCHA_CHECK_ARG(Cin <= EMB_MAXCIN, "embed_graph_agg: Cin=%d > %d unsupported", Cin, EMB_MAXCIN);
   MOCHA_CHECK_ARG(V % 4 == 0, "embed_graph_agg: V=%d must be a multiple of 4", V);
   constexpr int G = 4;
-  const size_t smem = (size_t)(G * V * C + G * V * EMB_MAXCIN + 2 * Kk * V * V + Kk * V) * sizeof(float);
+  const size_t smem = (size_t)(G * V * C + G * V * EMB_MAXCIN + 2 * Kk * V * V + Kk * V) * sizeof(float) +
+                      (size_t)V * (ldo - Kk * C) * 2 + 16;
   static size_t configured = 0;
   if (smem > configured) {
     MOCHA_CHECK_ARG(smem <= 200 * 1024, "embed_graph_agg: tile too large (%zu B)", smem);
