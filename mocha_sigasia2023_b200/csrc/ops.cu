@@ -244,14 +244,28 @@ pool_graph_agg_kernel(const __nv_bfloat16* __restrict__ in, const float* __restr
       a0[p] = 0.f; a1[p] = 0.f;
       if (p < P) {
         const int n = mc[p];
-        for (int dt = 0; dt < tp; ++dt) {
-          const __nv_bfloat162* sd = src + (long long)dt * V * C2;
-#pragma unroll 4
+        if (tp == 4) {
+          // four frames of one member joint = four independent loads in flight per step
+          const long long fs = (long long)V * C2;
+#pragma unroll 2
           for (int i = 0; i < n; ++i) {
-            const float2 x = __bfloat1622float2(sd[(long long)mv[p * V + i] * C2]);
+            const __nv_bfloat162* sj = src + (long long)mv[p * V + i] * C2;
             const float wv = mw[p * V + i];
-            a0[p] = fmaf(x.x, wv, a0[p]);
-            a1[p] = fmaf(x.y, wv, a1[p]);
+            const float2 x0 = __bfloat1622float2(sj[0]), x1 = __bfloat1622float2(sj[fs]);
+            const float2 x2 = __bfloat1622float2(sj[2 * fs]), x3 = __bfloat1622float2(sj[3 * fs]);
+            a0[p] = fmaf((x0.x + x1.x) + (x2.x + x3.x), wv, a0[p]);
+            a1[p] = fmaf((x0.y + x1.y) + (x2.y + x3.y), wv, a1[p]);
+          }
+        } else {
+          for (int dt = 0; dt < tp; ++dt) {
+            const __nv_bfloat162* sd = src + (long long)dt * V * C2;
+#pragma unroll 4
+            for (int i = 0; i < n; ++i) {
+              const float2 x = __bfloat1622float2(sd[(long long)mv[p * V + i] * C2]);
+              const float wv = mw[p * V + i];
+              a0[p] = fmaf(x.x, wv, a0[p]);
+              a1[p] = fmaf(x.y, wv, a1[p]);
+            }
           }
         }
         a0[p] = lrelu02(a0[p] * inv);
