@@ -240,7 +240,8 @@ struct EpiCtx {
   int slab_rows;         // valid rows in the slab (0..32)
   long long c_off;       // element offset of the output block (batched-head mode), else 0
   uint32_t res_bar;      // shared-space address of this warp's residual-prefetch mbarrier
-  uint32_t bias_smem;    // shared-space address of this warp's 512 B column-bias slice (TMA epilogues)
+  uint32_t bias_smem;    // shared-space address of the CTA's staged column bias (TMA epilogues)
+  int etid;              // thread index among the epilogue warps (0..255)
   int col_off;           // column offset of the output block inside its TMA map (batched-head PV output)
   int z;                 // image index b of the tile (batched-head mode: z = zb * H + zh)
   int img;               // batch image of the tile: third TMA-store coordinate
@@ -326,6 +327,10 @@ struct LinearEpiData {
   // (attention: the softmax denominator is applied to P V here, flash-attention style)
   const float* row_scale;
   int rs_rows;
+  // bf16-only outputs with N % 64 == 0 and tiles >= 128 wide: two 32-column chunks share one 64-column
+  // (128 B rows, 128 B-swizzled) TMA box, halving the fence / issue / wait overhead per byte
+  int c16_wide;
+  CUtensorMap tmC16w;
 };
 using LinearEpi = LinearEpiData;
 
@@ -343,16 +348,27 @@ struct LinearEpiT : LinearEpiData {
   // transposition buffer
   // MODE 1 writes one output per launch (the host falls back to MODE 0 otherwise), so its bf16 box
   // aliases the fp32 box and a fourth operand stage fits beside a 128 x 256 tile's staging
-  // + 512 B per warp for the tile's column-bias slice; the per-warp stride stays a multiple of 1 KB
-  // because the 128 B-swizzled boxes must be 1 KB aligned
-  static constexpr int kWarpStageBytes = MODE == 2 ? 11264 : 5120;
+  // The per-warp stride is a multiple of 1 KB (128 B-swizzled boxes must be 1 KB aligned); the whole column
+  // bias (N <= 2048) is staged once per CTA in an 8 KB area behind the warps' buffers.
+  static constexpr int kWarpStageBytes = MODE == 2 ? 10240 : MODE == 1 ? 4096 : 5120;
   static_assert(kWarpStageBytes % 1024 == 0, "swizzled TMA boxes need 1 KB alignment");
-  static constexpr int kStageBytes = EPI_WARPS * kWarpStageBytes;
+  static constexpr int kBiasBytes = MODE == 0 ? 0 : 8192;
+  static constexpr int kStageBytes = EPI_WARPS * kWarpStageBytes + kBiasBytes;
   static constexpr uint64_t kHintA = 0, kHintB = 0;                // default L2 policy
   static constexpr bool kTf32 = false;
   static constexpr bool kWholeTile = false;
   __device__ __forceinline__ void unit_begin(State&) const {}
-  __device__ __forceinline__ void kernel_begin(State& st) const { st.rphase = 0; st.col_begin = 0; st.rs = 1.f; }
+  __device__ __forceinline__ void kernel_begin(State& st, const EpiCtx& e) const {
+    st.rphase = 0; st.col_begin = 0; st.rs = 1.f;
+    if (MODE != 0) {
+      // the epilogue's only global loads that are not TMA: the column bias, once per CTA, while the first
+      // tile's main loop runs (per-chunk or per-tile loads see >1000-cycle latencies under store traffic)
+      if (bias && bias_period == 0)
+        for (int c = 4 * e.etid; c < N; c += 4 * EPI_WARPS * 32)
+          sts128f(e.bias_smem + 4u * c, __ldg(reinterpret_cast<const float4*>(bias + c)));
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps only
+    }
+  }
   // issue the TMA prefetch of a chunk's residual box (does not depend on the accumulator)
   __device__ __forceinline__ void prefetch_res(const EpiCtx& e, int col0) const {
     if (MODE == 2 && col0 >= 0 && col0 < N && e.slab_rows > 0 && e.lane == 0) {
@@ -368,14 +384,7 @@ struct LinearEpiT : LinearEpiData {
     st.col_begin = col_begin;
     if (MODE == 1 && row_scale)
       st.rs = e.lane < e.slab_rows ? __ldg(row_scale + (long long)e.z * rs_rows + e.row0_in_img + e.lane) : 0.f;
-    if (MODE != 0 && bias && bias_period == 0) {
-      const int c = col_begin + 4 * e.lane;
-      if (4 * e.lane < ncols) {
-        const float4 b4 = c < N ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        sts128f(e.bias_smem + 16u * e.lane, b4);
-      }
-      __syncwarp();
-    }
+    (void)ncols;
     prefetch_res(e, col_begin);
   }
   __device__ __forceinline__ void prefetch_chunk(State&, const EpiCtx& e, int col0) const { prefetch_res(e, col0); }
@@ -491,7 +500,7 @@ struct LinearEpiT : LinearEpiData {
         for (int j = 0; j < 32; ++j) f[j] *= rs;
       }
       if (bias) {
-        const uint32_t bs = e.bias_smem + (uint32_t)((col0 - st.col_begin) * 4);
+        const uint32_t bs = e.bias_smem + (uint32_t)(col0 * 4);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 b4 = lds128(bs + 16u * j);   // same address in every lane: broadcast
@@ -503,8 +512,10 @@ struct LinearEpiT : LinearEpiData {
         for (int j = 0; j < 32; ++j) f[j] = act_fn<ACT>(f[j]);
       }
       EPI_DBG(8);
-      if (e.lane == 0) bulk_wait_read0();  // the previous chunk's store has left the staging buffer
-      __syncwarp();
+      if (!(c16_wide && !C && (((col0 - st.col_begin) >> 5) & 1))) {
+        if (e.lane == 0) bulk_wait_read0();  // the previous store has left the staging buffer
+        __syncwarp();
+      }
       EPI_DBG(9);
       if (C) {
         const int sw = e.lane & 7;
@@ -512,6 +523,29 @@ struct LinearEpiT : LinearEpiData {
         for (int j = 0; j < 8; ++j)
           sts128(e.stage + (uint32_t)(e.lane * 128 + ((j ^ sw) << 4)), __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
                  __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
+      } else if (c16_wide) {
+        const int hcol = ((col0 - st.col_begin) >> 5) & 1;   // which half of the 64-column box
+        const int sw = e.lane & 7;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            float a = f[8 * j + 2 * t], b = f[8 * j + 2 * t + 1];
+            if (c16_lrelu) { a = lrelu02(a); b = lrelu02(b); }
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+            pk[t] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          sts128(e.stage + (uint32_t)(e.lane * 128 + (((j + 4 * hcol) ^ sw) << 4)), pk[0], pk[1], pk[2], pk[3]);
+        }
+        if (hcol == 0) return;   // the box goes out with its second half
+        fence_async_smem();
+        __syncwarp();
+        if (e.lane == 0) {
+          tma_store_3d(&tmC16w, e.stage, col0 - 32 + e.col_off, e.row0_in_img, e.img);
+          bulk_commit();
+        }
+        return;
       } else {
         const int sw16 = (e.lane >> 1) & 3;
 #pragma unroll
@@ -654,7 +688,7 @@ struct LinearEpiT : LinearEpiData {
     const uint32_t buf32 = e.stage, buf16 = e.stage + 4096, bufr = e.stage + 6144;
     const int sw = e.lane & 7;
     if (bias) {
-      const uint32_t bs = e.bias_smem + (uint32_t)((col0 - st.col_begin) * 4);
+      const uint32_t bs = e.bias_smem + (uint32_t)(col0 * 4);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 b4 = lds128(bs + 16u * j);   // same address in every lane: broadcast
@@ -794,8 +828,11 @@ struct LinearEpiT : LinearEpiData {
     EPI_DBG(7);
     }
   }
-  __device__ __forceinline__ void unit_end(State&, const EpiCtx& e, long long, bool, int) const {
-    if (MODE != 0 && e.lane == 0) bulk_wait_read0();  // staging buffers must outlive the stores that read them
+  __device__ __forceinline__ void unit_end(State&, const EpiCtx&, long long, bool, int) const {}
+  // staging buffers must outlive the stores that read them: one wait when the CTA is done, not one per
+  // tile (a store needs ~1000 cycles to leave shared memory; every chunk already waits before re-filling)
+  __device__ __forceinline__ void kernel_end(const EpiCtx& e) const {
+    if (MODE != 0 && e.lane == 0) bulk_wait_read0();
   }
 };
 
@@ -819,14 +856,16 @@ struct SoftmaxEpi {
   float* inv_sum;     // [Z, nq] reciprocal softmax denominators, applied by the P V epilogue
   CUtensorMap tmP;    // {ldp, nq, Z} bf16, 64 B-swizzled 32 x 32 boxes
   struct State {};
-  static constexpr int kStageBytes = EPI_WARPS * 2048;
+  static constexpr int kWarpStageBytes = 2048;
+  static constexpr int kStageBytes = EPI_WARPS * kWarpStageBytes;
   static constexpr uint64_t kHintA = 0, kHintB = 0;
   static constexpr bool kTf32 = false;
   static constexpr bool kWholeTile = true;
   __device__ __forceinline__ void unit_begin(State&) const {}
-  __device__ __forceinline__ void kernel_begin(State&) const {}
+  __device__ __forceinline__ void kernel_begin(State&, const EpiCtx&) const {}
   __device__ __forceinline__ void tile_begin(State&, const EpiCtx&, int, int) const {}
-  __device__ __forceinline__ void unit_end(State&, const EpiCtx& e, long long, bool, int) const {
+  __device__ __forceinline__ void unit_end(State&, const EpiCtx&, long long, bool, int) const {}
+  __device__ __forceinline__ void kernel_end(const EpiCtx& e) const {
     if (e.lane == 0) bulk_wait_read0();
   }
   __device__ __forceinline__ void tile(State&, const EpiCtx& e, uint32_t taddr) const {
@@ -899,6 +938,7 @@ struct MatchEpi {
   float* cand_score;
   int32_t* cand_idx;
   int lists;  // candidate lists per query = 2 * splits (one per column half)
+  static constexpr int kWarpStageBytes = 0;
   static constexpr int kStageBytes = 0;
   static constexpr bool kWholeTile = false;
   // query tiles are re-read for every DB tile: keep them in L2; DB rows stream through once per group
@@ -911,7 +951,7 @@ struct MatchEpi {
 #pragma unroll
     for (int t = 0; t < KC; ++t) { st.s[t] = INFINITY; st.i[t] = -1; }
   }
-  __device__ __forceinline__ void kernel_begin(State&) const {}
+  __device__ __forceinline__ void kernel_begin(State&, const EpiCtx&) const {}
   __device__ __forceinline__ void tile_begin(State&, const EpiCtx&, int, int) const {}
   __device__ __forceinline__ void chunk(State& st, const EpiCtx&, long long, bool row_ok, int col0,
                                         const uint32_t (&v)[32], int) const {
@@ -943,6 +983,7 @@ struct MatchEpi {
       }
     }
   }
+  __device__ __forceinline__ void kernel_end(const EpiCtx&) const {}
   __device__ __forceinline__ void unit_end(State& st, const EpiCtx& e, long long row, bool row_ok, int split) const {
     if (!row_ok) return;
     const long long o = (row * lists + split * 2 + e.half) * KC;
@@ -1127,7 +1168,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     int as = 0; uint32_t aphase = 0;
     typename Epi::State st;
-    epi.kernel_begin(st);
+    EpiCtx ectx;
+    ectx.stage = smem_u32(epi_stage + (warp - 2) * Epi::kWarpStageBytes);
+    ectx.res_bar = smem_u32(&res_bar[warp - 2]);
+    ectx.bias_smem = smem_u32(epi_stage + EPI_WARPS * Epi::kWarpStageBytes);
+    ectx.etid = (int)threadIdx.x - 64;
+    ectx.lane = lane;
+    epi.kernel_begin(st, ectx);
     for (int u = blockIdx.x; u < sh.units; u += gridDim.x) {
       int mt, split;
       decode_unit(sh, u, mt, split);
@@ -1135,10 +1182,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int r_in_b = mtb * BLOCK_M + q * 32 + lane;
       const bool row_ok = r_in_b < sh.rows_out_per_b;
       const long long row = (long long)b * sh.rows_out_per_b + r_in_b;
-      EpiCtx ectx;
-      ectx.stage = smem_u32(epi_stage + (warp - 2) * (Epi::kStageBytes / EPI_WARPS));
-      ectx.res_bar = smem_u32(&res_bar[warp - 2]);
-      ectx.bias_smem = ectx.stage + (uint32_t)(Epi::kStageBytes / EPI_WARPS) - 1024u;
       ectx.col_off = 0;
       ectx.z = b;
       ectx.img = b;
@@ -1198,6 +1241,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       epi.unit_end(st, ectx, row, row_ok, split);
     }
+    epi.kernel_end(ectx);
   }
 
   tc_fence_before();
@@ -1404,12 +1448,13 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int q = warp & 3;
     int as = 0; uint32_t aphase = 0;
     typename Epi::State st;
-    epi.kernel_begin(st);
     EpiCtx ectx;
-    ectx.stage = smem_u32(epi_stage + (warp - 2) * (Epi::kStageBytes / EPI_WARPS));
+    ectx.stage = smem_u32(epi_stage + (warp - 2) * Epi::kWarpStageBytes);
     ectx.res_bar = smem_u32(&res_bar[warp - 2]);
-    ectx.bias_smem = ectx.stage + (uint32_t)(Epi::kStageBytes / EPI_WARPS) - 1024u;
+    ectx.bias_smem = smem_u32(epi_stage + EPI_WARPS * Epi::kWarpStageBytes);
+    ectx.etid = (int)threadIdx.x - 64;
     ectx.lane = lane; ectx.half = (warp - 2) >> 2; ectx.c_off = 0; ectx.col_off = 0;
+    epi.kernel_begin(st, ectx);
     for (int u = cid; u < sh.units; u += ncl) {
       int mt, split;
       decode_unit(sh, u, mt, split);
@@ -1448,6 +1493,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       epi.unit_end(st, ectx, row, row_ok, split);
     }
+    epi.kernel_end(ectx);
   }
 
   // the peer must stay resident until the leader's last MMA has read its shared memory
@@ -1505,18 +1551,19 @@ int make_tmap(CUtensorMap* tm, const void* ptr, unsigned long long rows, unsigne
 // Output maps of the TMA-store epilogue: {cols, rows per image, images}, box 32 cols x 32 rows x 1.
 // fp32 boxes are 128 B-swizzled (the epilogue transposes through them), bf16 boxes 64 B-swizzled.
 int make_out_tmap(CUtensorMap* tm, const void* ptr, unsigned long long cols, unsigned long long rows_per_img,
-                  unsigned long long imgs, unsigned long long ld_elems, bool f32, unsigned long long img_pitch_rows = 0) {
+                  unsigned long long imgs, unsigned long long ld_elems, bool f32, unsigned long long img_pitch_rows = 0,
+                  bool wide16 = false) {
   if (img_pitch_rows == 0) img_pitch_rows = rows_per_img;
   const unsigned long long esz = f32 ? 4 : 2;
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(MOCHA_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t gdim[3] = {cols, rows_per_img, imgs};
   cuuint64_t gstride[2] = {ld_elems * esz, img_pitch_rows * ld_elems * esz};
-  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t box[3] = {wide16 ? 64u : 32u, 32, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim,
                   gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  (f32 || wide16) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(MOCHA_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed (%d)", (int)r);
   return MOCHA_OK;
@@ -1529,7 +1576,7 @@ int setup_out_tma(LinearEpi& epi, unsigned long long rows_per_img, unsigned long
   if (cols == 0) cols = (unsigned long long)epi.N;
   static const bool off = getenv("MOCHA_NO_TMA_STORE") != nullptr;  // debugging aid: force the LSU epilogue
   if (off) return MOCHA_OK;
-  const bool ok = (epi.N % 4) == 0 && (epi.ldc % 8) == 0 &&
+  const bool ok = (epi.N % 4) == 0 && (epi.ldc % 8) == 0 && (epi.N <= 2048 || !epi.bias || epi.bias_period > 0) &&
                   ((reinterpret_cast<uintptr_t>(epi.C) | reinterpret_cast<uintptr_t>(epi.C16) |
                     reinterpret_cast<uintptr_t>(epi.res) | reinterpret_cast<uintptr_t>(epi.bias)) & 15) == 0;
   if (!ok) return MOCHA_OK;
@@ -1538,6 +1585,12 @@ int setup_out_tma(LinearEpi& epi, unsigned long long rows_per_img, unsigned long
   if (epi.C) MOCHA_TRY(make_out_tmap(&epi.tmC, epi.C, cols, rows_per_img, imgs, (unsigned long long)epi.ldc, true, img_pitch_rows));
   if (epi.C16) MOCHA_TRY(make_out_tmap(&epi.tmC16, epi.C16, cols, rows_per_img, imgs, (unsigned long long)epi.ldc, false, img_pitch_rows));
   epi.tma = 1;
+  epi.c16_wide = 0;
+  if (epi.C16 && !epi.C && !with_res && epi.bias_period == 0 && epi.N % 64 == 0 && cols % 64 == 0) {
+    // the launcher clears this again when the tile is narrower than 128 columns (odd chunk count per warp)
+    MOCHA_TRY(make_out_tmap(&epi.tmC16w, epi.C16, cols, rows_per_img, imgs, (unsigned long long)epi.ldc, false, img_pitch_rows, true));
+    epi.c16_wide = 1;
+  }
   if (with_res) {
     MOCHA_TRY(make_out_tmap(&epi.tmR, epi.res, cols, rows_per_img, imgs, (unsigned long long)epi.ldc, true, img_pitch_rows));
     epi.tma = 2;
@@ -1702,6 +1755,11 @@ int dispatch_bn_impl(int bn, const CUtensorMap& tmA, const void* Wptr, unsigned 
 int dispatch_bn(int bn, const CUtensorMap& tmA, const void* Wptr, unsigned long long wrows, unsigned long long K,
                 TcShape sh, int N, int num_kb, const LinearEpi& epi, cudaStream_t s, unsigned long long wpitch = 0) {
   if (epi.tma == 2 && bn == 256) bn = 128;  // the residual / two-output staging leaves room for 32 KB stages only
+  if (epi.c16_wide && bn < 128) {
+    LinearEpi e2 = epi;
+    e2.c16_wide = 0;
+    return dispatch_bn_impl(bn, tmA, Wptr, wrows, K, sh, N, num_kb, LinearEpiT<1>{e2}, s, wpitch);
+  }
   if (epi.tma == 2) return dispatch_bn_impl(bn, tmA, Wptr, wrows, K, sh, N, num_kb, LinearEpiT<2>{epi}, s, wpitch);
   if (epi.tma == 1) return dispatch_bn_impl(bn, tmA, Wptr, wrows, K, sh, N, num_kb, LinearEpiT<1>{epi}, s, wpitch);
   return dispatch_bn_impl(bn, tmA, Wptr, wrows, K, sh, N, num_kb, LinearEpiT<0>{epi}, s, wpitch);
