@@ -203,12 +203,28 @@ struct TcShape {
   int b_mn;
 };
 
+// n / d for 0 <= n < 2^22 and d >= 1 through a float reciprocal with an integer correction step: the tile
+// bookkeeping of every role runs once per tile, and four dependent hardware-less integer divisions were
+// ~770 cycles between two tiles of the epilogue warps
+__device__ __forceinline__ int fast_div(int n, int d) {
+  int q = __float2int_rz(__int2float_rn(n) * __frcp_rn(__int2float_rn(d)));
+  int r = n - q * d;
+  if (r < 0) { --q; r += d; }
+  if (r >= d) ++q;
+  return q;
+}
+
 // unit -> (m tile, n split). Within a group of group_m m-tiles the m index runs fastest, so CTAs that
 // run concurrently share both the group's A tiles and the same few B ranges.
 __device__ __forceinline__ void decode_unit(const TcShape& sh, int u, int& mt, int& split) {
   if (sh.group_m <= 0 || sh.group_m >= sh.tiles_m_total) {
-    mt = u % sh.tiles_m_total;
-    split = u / sh.tiles_m_total;
+    if (u < (1 << 22)) {
+      split = fast_div(u, sh.tiles_m_total);
+      mt = u - split * sh.tiles_m_total;
+    } else {
+      mt = u % sh.tiles_m_total;
+      split = u / sh.tiles_m_total;
+    }
     return;
   }
   const int per_group = sh.group_m * sh.splits;
@@ -1056,12 +1072,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int u = blockIdx.x; u < sh.units; u += gridDim.x) {
         int mt, split;
         decode_unit(sh, u, mt, split);
-        const int b = mt / sh.tiles_m_per_b, mtb = mt - b * sh.tiles_m_per_b;
+        const int b = sh.nb == 1 ? 0 : fast_div(mt, sh.tiles_m_per_b), mtb = mt - b * sh.tiles_m_per_b;
         long long a_row0 = (long long)b * sh.src_rows_per_b + (long long)mtb * BLOCK_M;
         long long b_row0 = 0;
         int a_col0 = 0, b_col0 = 0;
         if (sh.H > 0) {
-          const int zb = b / sh.H, zh = b - zb * sh.H;
+          const int zb = fast_div(b, sh.H), zh = b - zb * sh.H;
           a_row0 = (long long)zb * sh.src_rows_per_b + (long long)zh * sh.a_rows_h + (long long)mtb * BLOCK_M;
           a_col0 = zh * sh.a_cols_h;
           b_row0 = (long long)zb * sh.b_rows_b + (long long)zh * sh.b_rows_h;
@@ -1178,7 +1194,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int u = blockIdx.x; u < sh.units; u += gridDim.x) {
       int mt, split;
       decode_unit(sh, u, mt, split);
-      const int b = mt / sh.tiles_m_per_b, mtb = mt - b * sh.tiles_m_per_b;
+      const int b = sh.nb == 1 ? 0 : fast_div(mt, sh.tiles_m_per_b), mtb = mt - b * sh.tiles_m_per_b;
       const int r_in_b = mtb * BLOCK_M + q * 32 + lane;
       const bool row_ok = r_in_b < sh.rows_out_per_b;
       const long long row = (long long)b * sh.rows_out_per_b + r_in_b;
@@ -1192,7 +1208,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ectx.slab_rows = max(0, min(32, sh.rows_out_per_b - (mtb * BLOCK_M + q * 32)));
       ectx.c_off = 0;
       if (sh.H > 0) {
-        const int zb = b / sh.H, zh = b - zb * sh.H;
+        const int zb = fast_div(b, sh.H), zh = b - zb * sh.H;
         ectx.slab_row0 = mtb * BLOCK_M + q * 32;
         ectx.c_off = (long long)zb * sh.c_img_b + (long long)zh * sh.c_img_h;
         ectx.img = zb;                      // TMA-store view of a [B, rows, H*cols] output (host checks the layout)
@@ -1204,7 +1220,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // the tile's BN/32 column chunks are split between the two warps that share a lane quarter
         constexpr int kSplitCol = ((BN / 32 + 1) / 2) * 32;
         const int c_begin = ectx.half == 0 ? 0 : kSplitCol, c_end = ectx.half == 0 ? kSplitCol : BN;
+#ifdef MOCHA_TRACE
+        if (warp == 2 && lane == 0 && trace_tile == 1) TC_TRACE(29, (unsigned long long)clock64());
+#endif
         if (c_begin < c_end) epi.tile_begin(st, ectx, nt * BN + c_begin, c_end - c_begin);  // overlaps the main loop
+#ifdef MOCHA_TRACE
+        if (warp == 2 && lane == 0 && trace_tile == 1) TC_TRACE(30, (unsigned long long)clock64());
+#endif
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
 #ifdef MOCHA_TRACE
@@ -1382,7 +1404,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int u = cid; u < sh.units; u += ncl) {
         int mt, split;
         decode_unit(sh, u, mt, split);
-        const int b = mt / sh.tiles_m_per_b, mtb = mt - b * sh.tiles_m_per_b;
+        const int b = sh.nb == 1 ? 0 : fast_div(mt, sh.tiles_m_per_b), mtb = mt - b * sh.tiles_m_per_b;
         const long long a_row0 = (long long)b * sh.src_rows_per_b + (long long)mtb * 256 + (int)rank * 128;
         const int nt_end = min(sh.tiles_n, (split + 1) * sh.tiles_per_unit);
         for (int nt = split * sh.tiles_per_unit; nt < nt_end; ++nt) {
@@ -1458,7 +1480,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int u = cid; u < sh.units; u += ncl) {
       int mt, split;
       decode_unit(sh, u, mt, split);
-      const int b = mt / sh.tiles_m_per_b, mtb = mt - b * sh.tiles_m_per_b;
+      const int b = sh.nb == 1 ? 0 : fast_div(mt, sh.tiles_m_per_b), mtb = mt - b * sh.tiles_m_per_b;
       const int r0 = mtb * 256 + (int)rank * 128 + q * 32;   // first row of the slab inside its image
       const bool row_ok = r0 + lane < sh.rows_out_per_b;
       const long long row = (long long)b * sh.rows_out_per_b + r0 + lane;

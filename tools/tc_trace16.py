@@ -13,7 +13,7 @@ lib.mocha_debug_set_trace.argtypes = [C.c_void_p]
 lib.mocha_debug_linear_bf16.restype = C.c_int
 lib.mocha_debug_linear_bf16.argtypes = [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p]
 trace = torch.zeros((148, 32), dtype=torch.int64, device="cuda")
-NAMES = {2: "setup done", 8: "operands landed t0", 12: "mma committed t0", 16: "acc ready t0", 20: "drained t0",
+NAMES = {29: "  t1: unit decoded", 30: "  t1: tile_begin done", 2: "setup done", 8: "operands landed t0", 12: "mma committed t0", 16: "acc ready t0", 20: "drained t0",
          9: "operands landed t1", 13: "mma committed t1", 17: "acc ready t1", 21: "drained t1",
          10: "operands landed t2", 14: "mma committed t2", 18: "acc ready t2", 22: "drained t2", 24: "cta end"}
 for spec in sys.argv[1:]:
@@ -38,7 +38,7 @@ for spec in sys.argv[1:]:
     t = trace.cpu(); t = t[t[:, 1] != 0]
     g0 = t[:, 0].min()
     print(f"== {spec}: {e0.elapsed_time(e1)*1e3:.1f} us (events), {t.shape[0]} CTAs, last CTA end {int(t[:,25].max()-g0)} ns after first start")
-    for slot in (2, 8, 12, 16, 20, 9, 13, 17, 21, 10, 14, 18, 22, 24):
+    for slot in (2, 8, 12, 16, 20, 29, 30, 9, 13, 17, 21, 10, 14, 18, 22, 24):
         v = t[:, slot]; ok = v != 0
         if ok.any():
             d = (v[ok] - t[ok, 1]).float()
