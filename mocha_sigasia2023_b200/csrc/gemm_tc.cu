@@ -296,10 +296,26 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   return v;
 }
 
+// GELU(x) = x/2 (1 + erf(x/sqrt 2)) for the bf16 tensor-core path: erf through Abramowitz & Stegun 7.1.28,
+// erf(t) = 1 - (1 + a1 t + ... + a6 t^6)^-16 for t >= 0 (|error| <= 3e-7, two orders below bf16's half ulp),
+// ~16 instructions and one MUFU instead of erff's ~28 on the issue-bound epilogue. The fp32 path keeps erff.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float t = fabsf(x) * 0.70710678118654752f;
+  float p = fmaf(0.0000430638f, t, 0.0002765672f);
+  p = fmaf(p, t, 0.0001520143f);
+  p = fmaf(p, t, 0.0092705272f);
+  p = fmaf(p, t, 0.0422820123f);
+  p = fmaf(p, t, 0.0705230784f);
+  p = fmaf(p, t, 1.0f);
+  p *= p; p *= p; p *= p; p *= p;                 // ^16 (overflows to +inf for large |x|: erf -> 1)
+  const float e = 1.0f - __frcp_rn(p);            // erf(|x| / sqrt 2)
+  return 0.5f * x * (1.0f + copysignf(e, x));
+}
+
 template <int ACT>
 __device__ __forceinline__ float act_fn(float x) {
   if (ACT == ACT_RELU) return fmaxf(x, 0.f);
-  if (ACT == ACT_GELU) return gelu_erf(x);
+  if (ACT == ACT_GELU) return gelu_fast(x);
   if (ACT == ACT_LRELU) return lrelu02(x);
   return x;
 }
