@@ -318,6 +318,7 @@ def run_b200(args):
         line["roofline"] = roofline_pass(args, sess, torch, lib, _lib)
         if not args.no_latency:
             line["latency_batch1"] = latency_pass(args, dev, torch, workload)
+            line["latency_batch1_bf16"] = latency_pass(args, dev, torch, workload, precision="bf16")
         if world == 1 and not args.no_cpu_baseline:
             rate, _ = cpu_port_rate(args, 2, 3, 1)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": host_threads(), "kind": "port",
@@ -396,10 +397,10 @@ def roofline_pass(args, sess, torch, lib, _lib):
             "peak_source": "nominal fp32 FFMA", "ms_per_launch": ms, "flops_per_launch": flops}
 
 
-def latency_pass(args, dev, torch, workload):
+def latency_pass(args, dev, torch, workload, precision="fp32"):
     """BASELINE config 2: batch-1 streaming, one CUDA graph per frame; per-frame latency with CUDA
     events (H2D of the new window + frame + D2H of the pose inside the timed region)."""
-    sess, *_ = workload.build_session(1, n_db=args.db_rows, precision="fp32", device=dev, seed=99)
+    sess, *_ = workload.build_session(1, n_db=args.db_rows, precision=precision, device=dev, seed=99)
     pool = [workload.step_inputs(1, seed=7000 + i) for i in range(8)]
     h = pool[0]
     sess.step_host(h["X"], h["src_hips_vel"], h["src_rvel"], h["src_rang"], h["contacts"], h["eps"])
@@ -428,7 +429,7 @@ def latency_pass(args, dev, torch, workload):
     p50, p99 = run(args.latency_frames, True)
     w50, w99 = run(args.latency_frames, False)
     return {"p50_ms": p50, "p99_ms": p99, "p50_ms_l2_warm": w50, "p99_ms_l2_warm": w99, "frames": args.latency_frames,
-            "precision": "fp32", "db_rows": args.db_rows, "budget_ms": 33.3,
+            "precision": precision, "db_rows": args.db_rows, "budget_ms": 33.3,
             "note": "L2 flushed (256 MB write) before every timed frame for p50_ms; *_l2_warm without flush"}
 
 

@@ -245,6 +245,26 @@ int mocha_db_pack_bf16(const float* d_rows, long long N, int D, void* d_rows16, 
 int mocha_topk_merge(const double* d_dist, const int64_t* d_idx, int nshard, int nq, int k,
                      double* d_out_dist, int64_t* d_out_idx, mocha_stream_t stream);
 
+/* ---- peer-memory exchange of the DB-sharded matcher (one process per GPU, NVLink / NVSwitch P2P) ----
+ * Fused replacement of "all-gather the [nq,k] lists, then merge" (sharded.py): ONE kernel per rank stores
+ * its local lists into a slot of every peer's exchange buffer (plain P2P stores over NVLink), raises a
+ * system-scope arrival counter on the peer, waits for the peers' counters in its own buffer and merges.
+ * Buffers come from mocha_peer_alloc (cudaMalloc + CUDA IPC handle, 64 bytes, to be exchanged by the host
+ * side, e.g. torch.distributed.all_gather_object) and are mapped with mocha_peer_open.
+ * Layout of a buffer of mocha_topk_exchange_bytes(world, nq, k) bytes: 2 parities x world slots x
+ * (nq*k fp64 + nq*k int64), then 2 x world uint32 arrival counters (zero-initialised by mocha_peer_alloc).
+ * `epoch` counts calls on this group (0, 1, 2, ...): consecutive calls alternate between the two parities, so
+ * a fast rank can never overwrite lists a slow rank is still merging. Every rank must launch with the same
+ * nq, k, epoch; the grid is fixed (all blocks co-resident), so the cross-GPU wait cannot deadlock. */
+size_t mocha_topk_exchange_bytes(int world, int nq, int k);
+int mocha_peer_alloc(size_t bytes, void** d_ptr, unsigned char handle_out[64]);
+int mocha_peer_open(const unsigned char handle[64], void** d_ptr);
+int mocha_peer_close(void* d_ptr);
+int mocha_peer_free(void* d_ptr);
+int mocha_topk_exchange_merge(const double* d_local_dist, const int64_t* d_local_idx, int nq, int k, int rank, int world,
+                              void* const* peer_bufs /* HOST array [world] of device pointers: every rank's buffer, own included */,
+                              unsigned int epoch, double* d_out_dist, int64_t* d_out_idx, mocha_stream_t stream);
+
 /* ---- dense primitive exposed for tests / reuse ----------------------------------------------- */
 /* C[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ residual). act: 0 none, 1 relu, 2 gelu(erf), 3 lrelu(0.2) */
 int mocha_linear(const float* d_A, const float* d_W, const float* d_bias, const float* d_res, float* d_C,

@@ -137,6 +137,12 @@ SIGNATURES = {
     "mocha_db_norms_f32": (_I, [_P, _L, _I, _P, _P]),
     "mocha_db_pack_bf16": (_I, [_P, _L, _I, _P, _P, _P]),
     "mocha_topk_merge": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    "mocha_topk_exchange_bytes": (_S, [_I, _I, _I]),
+    "mocha_peer_alloc": (_I, [_S, C.POINTER(C.c_void_p), C.c_char_p]),
+    "mocha_peer_open": (_I, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "mocha_peer_close": (_I, [_P]),
+    "mocha_peer_free": (_I, [_P]),
+    "mocha_topk_exchange_merge": (_I, [_P, _P, _I, _I, _I, _I, _P, C.c_uint, _P, _P, _P]),
     "mocha_linear": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _S, _P]),
     "mocha_linear_workspace_bytes": (_S, [_I, _I, _I, _I]),
     "mocha_xy_to_quat": (_I, [_P, _L, _P, _P]),

@@ -421,3 +421,145 @@ extern "C" int mocha_topk_merge(const double* dist, const int64_t* idx, int nsha
   MOCHA_LAUNCH_CHECK("topk_merge_kernel");
   return MOCHA_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Peer-memory exchange + merge of the DB-sharded matcher (see include/mocha_b200.h)
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int XCHG_BLOCKS = 16;   // fixed grid: all blocks co-resident on any GPU, so the cross-GPU wait is safe
+constexpr int XCHG_MAX_WORLD = 16;
+
+struct XchgPtrs {
+  unsigned char* buf[XCHG_MAX_WORLD];
+};
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_sys_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// One kernel per rank: (1) P2P-store the local [nq,k] lists into slot `rank` of every rank's buffer,
+// (2) release-increment the peer's arrival counter, (3) acquire-wait for every source's counter in the own
+// buffer, (4) merge the world lists of this block's queries.
+__global__ void __launch_bounds__(256)
+topk_exchange_merge_kernel(const double* __restrict__ ld, const long long* __restrict__ li, int nq, int k, int rank,
+                           int world, XchgPtrs peers, unsigned epoch, double* __restrict__ out_d,
+                           long long* __restrict__ out_i) {
+  const unsigned parity = epoch & 1u;
+  const size_t list = (size_t)nq * k;                      // elements per list
+  const size_t slot_bytes = list * 16;
+  const size_t parity_bytes = (size_t)world * slot_bytes;
+  const size_t flags_off = 2 * parity_bytes;
+  // ---- (1) push: 16 B per thread-step, this block's contiguous share of the two arrays
+  {
+    const size_t n2 = list / 2 * 2;   // uint4 = 2 elements of 8 B
+    for (int p = 0; p < world; ++p) {
+      unsigned char* dst = peers.buf[p] + parity * parity_bytes + (size_t)rank * slot_bytes;
+      double* dd = reinterpret_cast<double*>(dst);
+      long long* di = reinterpret_cast<long long*>(dst + list * 8);
+      for (size_t e = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; e < n2; e += (size_t)gridDim.x * blockDim.x * 2) {
+        *reinterpret_cast<uint4*>(dd + e) = *reinterpret_cast<const uint4*>(ld + e);
+        *reinterpret_cast<uint4*>(di + e) = *reinterpret_cast<const uint4*>(li + e);
+      }
+      if (blockIdx.x == 0 && threadIdx.x == 0 && n2 < list) { dd[n2] = ld[n2]; di[n2] = li[n2]; }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  // ---- (2) signal: one release-add per block and peer; (3) wait for gridDim.x arrivals per source and call
+  const unsigned expected = (epoch / 2 + 1) * gridDim.x;
+  if (threadIdx.x < world) {
+    unsigned* peer_flag = reinterpret_cast<unsigned*>(peers.buf[threadIdx.x] + flags_off) + parity * world + rank;
+    red_release_sys_add(peer_flag, 1u);
+    const unsigned* my_flag = reinterpret_cast<const unsigned*>(peers.buf[rank] + flags_off) + parity * world + threadIdx.x;
+    long long t0 = clock64();
+    while (ld_acquire_sys(my_flag) < expected) {
+      if (clock64() - t0 > 20000000000LL) {   // ~10 s: a peer never launched - report instead of hanging the GPU
+        printf("mocha topk exchange: rank %d timed out waiting for rank %d\n", rank, (int)threadIdx.x);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  // ---- (4) merge: one thread per query
+  const unsigned char* mine = peers.buf[rank] + parity * parity_bytes;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+    double bd[KMAX]; long long bi[KMAX];
+#pragma unroll
+    for (int t = 0; t < KMAX; ++t) { bd[t] = INFINITY; bi[t] = -1; }
+    for (int sidx = 0; sidx < world; ++sidx) {
+      const double* sd = reinterpret_cast<const double*>(mine + (size_t)sidx * slot_bytes);
+      const long long* si = reinterpret_cast<const long long*>(mine + (size_t)sidx * slot_bytes + list * 8);
+      for (int j = 0; j < k; ++j) {
+        const long long id = __ldcv(si + (size_t)q * k + j);
+        if (id >= 0) local_insert(bd, bi, k, __ldcv(sd + (size_t)q * k + j), id);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < KMAX; ++t)
+      if (t < k) { out_d[(size_t)q * k + t] = bd[t]; out_i[(size_t)q * k + t] = bi[t]; }
+  }
+}
+}  // namespace
+
+extern "C" size_t mocha_topk_exchange_bytes(int world, int nq, int k) {
+  if (world < 1 || nq < 1 || k < 1) return 0;
+  return 2 * (size_t)world * nq * k * 16 + 2 * (size_t)world * 4 + 256;
+}
+
+extern "C" int mocha_peer_alloc(size_t bytes, void** d_ptr, unsigned char handle_out[64]) {
+  MOCHA_CHECK_ARG(bytes > 0 && d_ptr && handle_out, "mocha_peer_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  void* p = nullptr;
+  MOCHA_CUDA(cudaMalloc(&p, bytes));
+  MOCHA_CUDA(cudaMemset(p, 0, bytes));
+  cudaIpcMemHandle_t h;
+  MOCHA_CUDA(cudaIpcGetMemHandle(&h, p));
+  memcpy(handle_out, &h, 64);
+  *d_ptr = p;
+  return MOCHA_OK;
+}
+
+extern "C" int mocha_peer_open(const unsigned char handle[64], void** d_ptr) {
+  MOCHA_CHECK_ARG(handle && d_ptr, "mocha_peer_open: bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  MOCHA_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return MOCHA_OK;
+}
+
+extern "C" int mocha_peer_close(void* d_ptr) {
+  MOCHA_CUDA(cudaIpcCloseMemHandle(d_ptr));
+  return MOCHA_OK;
+}
+
+extern "C" int mocha_peer_free(void* d_ptr) {
+  MOCHA_CUDA(cudaFree(d_ptr));
+  return MOCHA_OK;
+}
+
+extern "C" int mocha_topk_exchange_merge(const double* d_local_dist, const int64_t* d_local_idx, int nq, int k, int rank,
+                                         int world, void* const* d_peer_bufs, unsigned int epoch, double* d_out_dist,
+                                         int64_t* d_out_idx, mocha_stream_t stream) {
+  MOCHA_CHECK_ARG(d_local_dist && d_local_idx && d_peer_bufs && d_out_dist && d_out_idx, "mocha_topk_exchange_merge: null argument");
+  MOCHA_CHECK_ARG(nq > 0 && k >= 1 && k <= KMAX && world >= 1 && world <= XCHG_MAX_WORLD && rank >= 0 && rank < world,
+                  "mocha_topk_exchange_merge: bad sizes");
+  MOCHA_CHECK_ARG(((reinterpret_cast<uintptr_t>(d_local_dist) | reinterpret_cast<uintptr_t>(d_local_idx)) & 15) == 0,
+                  "mocha_topk_exchange_merge: local lists must be 16 B aligned");
+  // d_peer_bufs is a HOST array of device pointers (copied into the kernel's parameter space)
+  XchgPtrs peers{};
+  for (int p = 0; p < world; ++p) {
+    MOCHA_CHECK_ARG(d_peer_bufs[p], "mocha_topk_exchange_merge: peer buffer %d is null", p);
+    peers.buf[p] = static_cast<unsigned char*>(d_peer_bufs[p]);
+  }
+  topk_exchange_merge_kernel<<<XCHG_BLOCKS, 256, 0, (cudaStream_t)stream>>>(
+      d_local_dist, reinterpret_cast<const long long*>(d_local_idx), nq, k, rank, world, peers, epoch, d_out_dist,
+      reinterpret_cast<long long*>(d_out_idx));
+  count_launch();
+  MOCHA_LAUNCH_CHECK("topk_exchange_merge_kernel");
+  return MOCHA_OK;
+}

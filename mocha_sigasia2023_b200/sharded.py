@@ -35,6 +35,65 @@ def merge_topk_cuda(all_dist: torch.Tensor, all_idx: torch.Tensor, k: int):
     return out_d, out_i
 
 
+class PeerExchange:
+    """Peer-memory replacement of all-gather + merge (one fused kernel per rank, include/mocha_b200.h).
+
+    Every rank allocates one exchange buffer with CUDA IPC (mocha_peer_alloc), the 64-byte handles are
+    all-gathered through the process group (host side, once), and each rank maps its peers' buffers. A call then
+    costs ONE kernel: P2P stores of the local lists into every peer's slot over NVLink, a system-scope
+    arrival counter, and the merge. Needs one process per GPU on a single node with P2P access."""
+
+    def __init__(self, nq: int, k: int, group=None):
+        import ctypes as C
+        self.lib = _lib.load()
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.nq, self.k = nq, k
+        self.epoch = 0
+        nbytes = self.lib.mocha_topk_exchange_bytes(self.world, nq, k)
+        own = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        _lib.check(self.lib.mocha_peer_alloc(nbytes, C.byref(own), handle), "mocha_peer_alloc")
+        self._own = own
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self._opened = []
+        ptrs = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                ptrs.append(own.value)
+                continue
+            p = C.c_void_p()
+            _lib.check(self.lib.mocha_peer_open(C.create_string_buffer(h, 64), C.byref(p)), "mocha_peer_open")
+            self._opened.append(p)
+            ptrs.append(p.value)
+        self._ptrs = (C.c_void_p * self.world)(*ptrs)
+        dist.barrier(group=group)   # every buffer is mapped (and zeroed) before the first exchange
+
+    def exchange_merge(self, d_loc: torch.Tensor, i_loc: torch.Tensor):
+        nq, k = d_loc.shape
+        if (nq, k) != (self.nq, self.k):
+            raise _lib.MochaError("PeerExchange: list shape differs from the one the buffers were sized for")
+        out_d = torch.empty_like(d_loc)
+        out_i = torch.empty_like(i_loc)
+        _lib.check(self.lib.mocha_topk_exchange_merge(_lib.ptr(d_loc.contiguous()), _lib.ptr(i_loc.contiguous()), nq, k,
+                                                      self.rank, self.world, self._ptrs, self.epoch, _lib.ptr(out_d),
+                                                      _lib.ptr(out_i), _lib.stream_ptr()), "mocha_topk_exchange_merge")
+        self.epoch += 1
+        return out_d, out_i
+
+    def close(self):
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for p in self._opened:
+            self.lib.mocha_peer_close(p)
+        self._opened = []
+        if self._own is not None:
+            self.lib.mocha_peer_free(self._own)
+            self._own = None
+
+
 class ShardedMatcher:
     """k-NN over a DB whose rows live on different ranks.
 
@@ -43,7 +102,11 @@ class ShardedMatcher:
     merge kernel. Both are injectable so the host-side protocol is testable on CPU with gloo.
     """
 
-    def __init__(self, n_rows_total: int, local_query, group=None, merge=merge_topk_cuda):
+    def __init__(self, n_rows_total: int, local_query, group=None, merge=merge_topk_cuda, exchange="nccl"):
+        if exchange not in ("nccl", "peer"):
+            raise ValueError("exchange must be 'nccl' (all-gather + merge kernel) or 'peer' (fused P2P kernel)")
+        self.exchange = exchange
+        self._peer = None
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -65,6 +128,12 @@ class ShardedMatcher:
         if self.world == 1:
             return d_loc, i_loc
         nq = d_loc.shape[0]
+        if self.exchange == "peer":
+            if self._peer is None or (self._peer.nq, self._peer.k) != (nq, k):
+                if self._peer is not None:
+                    self._peer.close()
+                self._peer = PeerExchange(nq, k, group=self.group)
+            return self._peer.exchange_merge(d_loc, i_loc)
         all_d = torch.empty((self.world * nq, k), dtype=torch.float64, device=dev)
         all_i = torch.empty((self.world * nq, k), dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(all_d, d_loc.contiguous(), group=self.group)

@@ -123,3 +123,53 @@ def test_tf32_fp32_storage_matcher(shape):
     np.testing.assert_array_equal(idx[:, 0], pick)
     np.testing.assert_array_equal(idx[:, 0], wi[:, 0])
     np.testing.assert_allclose(dist[:, 0], wd[:, 0], rtol=1e-9)
+
+
+def test_peer_exchange_two_logical_ranks_on_one_gpu():
+    """mocha_topk_exchange_merge (fused P2P store / signal / merge kernel of the DB-sharded matcher): two
+    logical ranks on ONE GPU, their kernels on two streams so that both are resident and signal each other
+    through their exchange buffers, three consecutive epochs; result = merge of the two shards' lists."""
+    import ctypes as C
+    from mocha_sigasia2023_b200 import _lib
+    lib = _lib.load()
+    world, nq, k = 2, 300, 3
+    nbytes = lib.mocha_topk_exchange_bytes(world, nq, k)
+    bufs, handles = [], []
+    for r in range(world):
+        p = C.c_void_p(); h = C.create_string_buffer(64)
+        _lib.check(lib.mocha_peer_alloc(nbytes, C.byref(p), h), "mocha_peer_alloc")
+        bufs.append(p); handles.append(h)
+    ptrs = (C.c_void_p * world)(*[b.value for b in bufs])
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    rng = np.random.default_rng(5)
+    try:
+        for epoch in range(3):
+            d_np = np.sort(rng.random((world, nq, k)), axis=2)
+            i_np = rng.integers(0, 10_000, size=(world, nq, k)).astype(np.int64)
+            i_np[1, ::7, -1] = -1                      # a shard with fewer than k rows for some queries
+            d_np[1, ::7, -1] = np.inf
+            d = torch.from_numpy(d_np).cuda(); i = torch.from_numpy(i_np).cuda()
+            outs = []
+            torch.cuda.synchronize()
+            for r in range(world):
+                od = torch.empty((nq, k), dtype=torch.float64, device="cuda")
+                oi = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+                with torch.cuda.stream(streams[r]):
+                    _lib.check(lib.mocha_topk_exchange_merge(_lib.ptr(d[r]), _lib.ptr(i[r]), nq, k, r, world, ptrs, epoch,
+                                                             _lib.ptr(od), _lib.ptr(oi), C.c_void_p(streams[r].cuda_stream)),
+                               "mocha_topk_exchange_merge")
+                outs.append((od, oi))
+            torch.cuda.synchronize()
+            # oracle: merge by (distance, index)
+            cd = d_np.transpose(1, 0, 2).reshape(nq, world * k)
+            ci = i_np.transpose(1, 0, 2).reshape(nq, world * k)
+            cd = np.where(ci >= 0, cd, np.inf)
+            order = np.lexsort((ci, cd), axis=1)[:, :k]
+            want_d = np.take_along_axis(cd, order, axis=1)
+            want_i = np.take_along_axis(ci, order, axis=1)
+            for od, oi in outs:
+                np.testing.assert_array_equal(oi.cpu().numpy(), want_i)
+                np.testing.assert_array_equal(od.cpu().numpy(), want_d)
+    finally:
+        for b in bufs:
+            lib.mocha_peer_free(b)

@@ -15,6 +15,8 @@ ap.add_argument("--rows-per-gpu", type=int, default=2_000_000)
 ap.add_argument("--q", type=int, default=4096)
 ap.add_argument("--d", type=int, default=23040)
 ap.add_argument("--iters", type=int, default=3)
+ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer", "both"],
+                help="nccl: all-gather + merge kernel; peer: one fused P2P store/signal/merge kernel; both: run and compare")
 a = ap.parse_args()
 world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -52,27 +54,57 @@ def local_query(qt, k):
     return dd, idx
 
 
-m = ShardedMatcher(N, local_query)
-times = []
-for it in range(a.iters + 1):
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    d, i = m.query(q, k=2)
-    e1.record()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    if it > 0:
-        times.append(float(t.item()))
+modes = ["nccl", "peer"] if a.exchange == "both" else [a.exchange]
+results = {}
+for mode in modes:
+  m = ShardedMatcher(N, local_query, exchange=mode if world > 1 else "nccl")
+  times = []
+  xt = []
+  for it in range(a.iters + 1):
+      if world > 1:
+          dist.barrier()
+      torch.cuda.synchronize()
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record()
+      d, i = m.query(q, k=2)
+      e1.record()
+      torch.cuda.synchronize()
+      t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+      if world > 1:
+          dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      if it > 0:
+          times.append(float(t.item()))
+  results[mode] = (sum(times) / len(times), d.clone(), i.clone())
+  # the exchange alone (local lists already computed): time 20 back-to-back calls
+  if world > 1:
+      dl, il = local_query(q, 2)
+      il = il + m.lo
+      torch.cuda.synchronize(); dist.barrier()
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record()
+      for _ in range(20):
+          if mode == "peer":
+              m._peer.exchange_merge(dl, il)
+          else:
+              all_d = torch.empty((world * Q, 2), dtype=torch.float64, device=dev)
+              all_i = torch.empty((world * Q, 2), dtype=torch.int64, device=dev)
+              dist.all_gather_into_tensor(all_d, dl); dist.all_gather_into_tensor(all_i, il)
+              m.merge(all_d.view(world, Q, 2), all_i.view(world, Q, 2), 2)
+      e1.record(); torch.cuda.synchronize()
+      xt = e0.elapsed_time(e1) / 20 * 1e3
+      results[mode] = results[mode] + (xt,)
+  if getattr(m, "_peer", None) is not None:
+      m._peer.close()
+ms, d, i = results[modes[0]][:3]
 want = owner * Nl + row      # shard_bounds is contiguous and equal-sized here
 found = float((i[:, 0] == want).float().mean())
+same = True
+if len(modes) == 2:
+    same = bool((results["nccl"][2] == results["peer"][2]).all()) and bool((results["nccl"][1] == results["peer"][1]).all())
 if rank == 0:
-    ms = sum(times) / len(times)
-    print(json.dumps({"workload": f"DB-sharded match {Q}q x {N} rows ({Nl}/GPU) x {D} bf16, k=2, NCCL all-gather merge",
+    print(json.dumps({"workload": f"DB-sharded match {Q}q x {N} rows ({Nl}/GPU) x {D} bf16, k=2, exchange={a.exchange}",
+                      "exchange_us": {mo: (results[mo][3] if len(results[mo]) > 3 else None) for mo in modes},
+                      "ms_by_mode": {mo: results[mo][0] for mo in modes}, "peer_equals_nccl": same,
                       "n_gpus": world, "ms": ms, "tflops_total": 2.0 * Q * N * D / ms / 1e9,
                       "tflops_per_gpu": 2.0 * Q * Nl * D / ms / 1e9, "planted_found": found}))
 if world > 1:
