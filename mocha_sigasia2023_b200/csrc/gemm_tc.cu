@@ -902,8 +902,10 @@ struct SoftmaxEpi {
   __device__ __forceinline__ void kernel_end(const EpiCtx& e) const {
     if (e.lane == 0) bulk_wait_read0();
   }
-  __device__ __forceinline__ void tile(State&, const EpiCtx& e, uint32_t taddr) const {
-    if (e.half != 0 || e.slab_rows <= 0) return;  // one warp per lane quarter owns whole rows
+  __device__ __forceinline__ void tile(State&, const EpiCtx& e, uint32_t taddr, int acc_stage) const {
+    // one warp per lane quarter owns whole rows of a tile; the two warps of a quarter alternate tiles
+    // (accumulator stage 0 / 1), so two tiles' softmax passes run concurrently
+    if (e.half != acc_stage || e.slab_rows <= 0) return;
     const int nch = (nkv + 31) >> 5;
     float m = -INFINITY;
 #pragma unroll 1
@@ -1251,7 +1253,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (warp == 2 && lane == 0) TC_TRACE(16 + trace_tile, (unsigned long long)clock64());  // accumulator ready
 #endif
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-        if constexpr (Epi::kWholeTile) epi.tile(st, ectx, taddr);
+        if constexpr (Epi::kWholeTile) epi.tile(st, ectx, taddr, as);
 #ifdef MOCHA_TRACE
         const int c_stop = dbg_mode == 3 ? c_begin : c_end;
 #else
