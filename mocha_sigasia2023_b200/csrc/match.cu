@@ -96,24 +96,26 @@ match_exact_tile_kernel(const float* __restrict__ Q, int nq, const float* __rest
   }
 }
 
-__device__ __forceinline__ bool better(double d0, long long i0, double d1, long long i1) {
+template <class T, class I>
+__device__ __forceinline__ bool better(T d0, I i0, T d1, I i1) {
   return d0 < d1 || (d0 == d1 && i0 < i1);
 }
 
 // Block-wide top-k of (value, index) pairs by (value asc, index asc). Each thread feeds its own
 // candidates through `local insert`, then k rounds of block arg-min pop the winners.
-template <int NT>
-__device__ void block_topk_pop(double (&ls)[KMAX], long long (&li)[KMAX], int k, double* out_d, long long* out_i,
-                               double* red_d, long long* red_i, int* red_t) {
+// The key type is a template parameter: fp64 compares issue on the slow FP64 pipe of this part, so lists
+// whose values are fp32 (the tensor-core coarse scores) are merged with float keys and int indices.
+template <int NT, class T, class I>
+__device__ void block_topk_pop(T (&ls)[KMAX], I (&li)[KMAX], int k, T* out_d, I* out_i, T* red_d, I* red_i, int* red_t) {
   for (int r = 0; r < k; ++r) {
     // every thread proposes the head of its (ascending) local list
-    double d = ls[0];
-    long long i = li[0];
+    T d = ls[0];
+    I i = li[0];
     int t = threadIdx.x;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      const double d2 = __shfl_xor_sync(0xffffffffu, d, o);
-      const long long i2 = __shfl_xor_sync(0xffffffffu, i, o);
+      const T d2 = __shfl_xor_sync(0xffffffffu, d, o);
+      const I i2 = __shfl_xor_sync(0xffffffffu, i, o);
       const int t2 = __shfl_xor_sync(0xffffffffu, t, o);
       const bool take = (i2 >= 0) && (i < 0 || better(d2, i2, d, i));
       if (take) { d = d2; i = i2; t = t2; }
@@ -121,7 +123,7 @@ __device__ void block_topk_pop(double (&ls)[KMAX], long long (&li)[KMAX], int k,
     if ((threadIdx.x & 31) == 0) { red_d[threadIdx.x >> 5] = d; red_i[threadIdx.x >> 5] = i; red_t[threadIdx.x >> 5] = t; }
     __syncthreads();
     if (threadIdx.x == 0) {
-      double bd = red_d[0]; long long bi = red_i[0]; int bt = red_t[0];
+      T bd = red_d[0]; I bi = red_i[0]; int bt = red_t[0];
       for (int w = 1; w < NT / 32; ++w) {
         if (red_i[w] >= 0 && (bi < 0 || better(red_d[w], red_i[w], bd, bi))) { bd = red_d[w]; bi = red_i[w]; bt = red_t[w]; }
       }
@@ -139,12 +141,13 @@ __device__ void block_topk_pop(double (&ls)[KMAX], long long (&li)[KMAX], int k,
 }
 
 // keep the k best (ascending by (value, index)) in ls/li; slots >= k stay empty
-__device__ __forceinline__ void local_insert(double (&ls)[KMAX], long long (&li)[KMAX], int k, double d, long long i) {
+template <class T, class I>
+__device__ __forceinline__ void local_insert(T (&ls)[KMAX], I (&li)[KMAX], int k, T d, I i) {
 #pragma unroll
   for (int t = 0; t < KMAX; ++t) {
     if (t < k && i >= 0 && (li[t] < 0 || better(d, i, ls[t], li[t]))) {
-      const double td = ls[t]; ls[t] = d; d = td;
-      const long long ti = li[t]; li[t] = i; i = ti;
+      const T td = ls[t]; ls[t] = d; d = td;
+      const I ti = li[t]; li[t] = i; i = ti;
     }
   }
 }
@@ -161,7 +164,7 @@ topk_rows_kernel(const double* __restrict__ dist2, long long N, int k, long long
 #pragma unroll
   for (int t = 0; t < KMAX; ++t) { ls[t] = INFINITY; li[t] = -1; }
   for (long long n = threadIdx.x; n < N; n += 256) local_insert(ls, li, k, row[n], n);
-  block_topk_pop<256>(ls, li, k, od, oi, red_d, red_i, red_t);
+  block_topk_pop<256, double, long long>(ls, li, k, od, oi, red_d, red_i, red_t);
   if (threadIdx.x < k) {
     out_idx[(long long)q * k + threadIdx.x] = oi[threadIdx.x] >= 0 ? oi[threadIdx.x] + index_offset : -1;
     if (out_dist) out_dist[(long long)q * k + threadIdx.x] = sqrt(od[threadIdx.x]);
@@ -180,25 +183,123 @@ match_rerank_kernel(const float* __restrict__ Q, const __nv_bfloat16* __restrict
   const int q = blockIdx.x;
   const float* cs = cand_score + (long long)q * ncand;
   const int32_t* ci = cand_idx + (long long)q * ncand;
-  double ls[KMAX]; long long li[KMAX];
+  {
+    // merge of the coarse lists on float keys / int indices (same (value, index) order as the fp64 version)
+    __shared__ float fred_d[8]; __shared__ int fred_i[8];
+    __shared__ float fod[KMAX]; __shared__ int foi[KMAX];
+    float ls[KMAX]; int li[KMAX];
 #pragma unroll
-  for (int t = 0; t < KMAX; ++t) { ls[t] = INFINITY; li[t] = -1; }
-  for (int n = threadIdx.x; n < ncand; n += 256) {
-    const int32_t id = ci[n];
-    if (id >= 0) local_insert(ls, li, kc, (double)cs[n], (long long)id);
+    for (int t = 0; t < KMAX; ++t) { ls[t] = INFINITY; li[t] = -1; }
+    for (int n = threadIdx.x; n < ncand; n += 256) {
+      const int32_t id = ci[n];
+      if (id >= 0) local_insert(ls, li, kc, cs[n], (int)id);
+    }
+    block_topk_pop<256, float, int>(ls, li, kc, fod, foi, fred_d, fred_i, red_t);
+    if (threadIdx.x < KMAX) { od[threadIdx.x] = (double)fod[threadIdx.x]; oi[threadIdx.x] = (long long)foi[threadIdx.x]; }
+    __syncthreads();
   }
-  block_topk_pop<256>(ls, li, kc, od, oi, red_d, red_i, red_t);
   // exact squared distances of the kc survivors: the whole block walks one candidate row at a time
   // (4 consecutive elements per thread, two fp64 accumulators) so the fp64 chains stay short
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* qv = Q + (long long)q * D;
   const bool vec4 = (D & 3) == 0 && ((reinterpret_cast<uintptr_t>(qv) & 15) == 0) &&
                     (DB32 ? (reinterpret_cast<uintptr_t>(DB32) & 15) == 0 : (reinterpret_cast<uintptr_t>(DB16) & 7) == 0);
+  // Certified fp32 pre-filter. The FP64 pipe of this part sustains only ~4 ops/clk/SM (the exact pass over
+  // kc rows of 23040 values was pipe-bound: 55 us for 128 queries), so the kc survivors are first measured
+  // in fp32 (one accumulator of <= ceil(D/1024)*4 terms per thread, then 5 + 8 tree adds): the relative
+  // error of such a sum of non-negative terms is below (ceil(D/1024)*4 + 20) * 2^-24. A row whose fp32
+  // distance exceeds the k-th smallest fp32 one by more than twice that bound (x4 safety) cannot be among
+  // the exact top k; only the rest - k rows unless there are near-ties - is re-evaluated in fp64.
+  __shared__ float d32[KMAX];
+  __shared__ int keep[KMAX];
+  if (vec4 && DB32 && kc > k) {
+    // all survivors at once: the query segment is loaded once and kc row segments are in flight per thread
+    // (the loop is load-latency-bound: one block per SM streams kc rows of 92 KB)
+    float f[KMAX];
+    const float* xr[KMAX];
+#pragma unroll
+    for (int c = 0; c < KMAX; ++c) {
+      f[c] = 0.f;
+      const long long id = c < kc ? oi[c] : -1;
+      xr[c] = DB32 + (id >= 0 ? id : 0) * (long long)D;
+    }
+    for (int d = threadIdx.x * 4; d < D; d += 1024) {
+      const float4 qq = *reinterpret_cast<const float4*>(qv + d);
+      float4 xx[KMAX];
+#pragma unroll
+      for (int c = 0; c < KMAX; ++c)
+        if (c < kc) xx[c] = __ldg(reinterpret_cast<const float4*>(xr[c] + d));
+#pragma unroll
+      for (int c = 0; c < KMAX; ++c)
+        if (c < kc) {
+          const float e0 = qq.x - xx[c].x, e1 = qq.y - xx[c].y, e2 = qq.z - xx[c].z, e3 = qq.w - xx[c].w;
+          f[c] = fmaf(e0, e0, f[c]); f[c] = fmaf(e1, e1, f[c]);
+          f[c] = fmaf(e2, e2, f[c]); f[c] = fmaf(e3, e3, f[c]);
+        }
+    }
+    __shared__ float fpart[8][KMAX];
+#pragma unroll
+    for (int c = 0; c < KMAX; ++c) {
+      const float acc = warp_sum(f[c]);
+      if (lane == 0) fpart[warp][c] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x < kc) {
+      float t = 0.f;
+      for (int w = 0; w < 8; ++w) t += fpart[w][threadIdx.x];
+      d32[threadIdx.x] = oi[threadIdx.x] >= 0 ? t : INFINITY;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float kth = INFINITY;   // k-th smallest fp32 distance (kc <= 16: selection by counting)
+      for (int c = 0; c < kc; ++c) {
+        int below = 0;
+        for (int j = 0; j < kc; ++j) below += (d32[j] < d32[c]) || (d32[j] == d32[c] && j < c);
+        if (below == k - 1) kth = d32[c];
+      }
+      const float eps = (float)(((D + 1023) / 1024) * 4 + 20) * 5.9604645e-8f;
+      const float bound = kth * (1.f + 8.f * eps);
+      for (int c = 0; c < kc; ++c) keep[c] = d32[c] <= bound;
+    }
+  } else {
+    if (threadIdx.x < KMAX) keep[threadIdx.x] = 1;
+  }
+  __syncthreads();
   for (int c = 0; c < kc; ++c) {
+    if (!keep[c]) {   // uniform across the block
+      if (threadIdx.x == 0) { exact[c] = INFINITY; oi[c] = -1; }
+      continue;
+    }
     const long long id = oi[c];
     double a0 = 0.0, a1 = 0.0;
     if (id >= 0) {
-      if (vec4) {
+      if (vec4 && DB32) {
+        const float* xrow = DB32 + id * (long long)D;
+        int d = threadIdx.x * 4;
+        for (; d + 3 * 1024 < D; d += 4 * 1024) {   // four row segments in flight per thread
+          float4 qq[4], xx[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            qq[u] = *reinterpret_cast<const float4*>(qv + d + u * 1024);
+            xx[u] = __ldg(reinterpret_cast<const float4*>(xrow + d + u * 1024));
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const double e0 = (double)qq[u].x - (double)xx[u].x, e1 = (double)qq[u].y - (double)xx[u].y;
+            const double e2 = (double)qq[u].z - (double)xx[u].z, e3 = (double)qq[u].w - (double)xx[u].w;
+            a0 = fma(e0, e0, a0); a1 = fma(e1, e1, a1);
+            a0 = fma(e2, e2, a0); a1 = fma(e3, e3, a1);
+          }
+        }
+        for (; d < D; d += 1024) {
+          const float4 qq = *reinterpret_cast<const float4*>(qv + d);
+          const float4 xx = __ldg(reinterpret_cast<const float4*>(xrow + d));
+          const double e0 = (double)qq.x - (double)xx.x, e1 = (double)qq.y - (double)xx.y;
+          const double e2 = (double)qq.z - (double)xx.z, e3 = (double)qq.w - (double)xx.w;
+          a0 = fma(e0, e0, a0); a1 = fma(e1, e1, a1);
+          a0 = fma(e2, e2, a0); a1 = fma(e3, e3, a1);
+        }
+      } else if (vec4) {
         for (int d = threadIdx.x * 4; d < D; d += 1024) {
           const float4 qq = *reinterpret_cast<const float4*>(qv + d);
           float4 xx;
