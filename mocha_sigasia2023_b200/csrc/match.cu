@@ -214,7 +214,7 @@ match_rerank_kernel(const float* __restrict__ Q, const __nv_bfloat16* __restrict
   __shared__ int keep[KMAX];
   if (vec4 && DB32 && kc > k) {
     // all survivors at once: the query segment is loaded once and kc row segments are in flight per thread
-    // (the loop is load-latency-bound: one block per SM streams kc rows of 92 KB)
+    // (the loop is load-latency-bound: one block per SM streams kc rows of 92 KB); kc <= 8 doubles the depth
     float f[KMAX];
     const float* xr[KMAX];
 #pragma unroll
@@ -223,7 +223,30 @@ match_rerank_kernel(const float* __restrict__ Q, const __nv_bfloat16* __restrict
       const long long id = c < kc ? oi[c] : -1;
       xr[c] = DB32 + (id >= 0 ? id : 0) * (long long)D;
     }
-    for (int d = threadIdx.x * 4; d < D; d += 1024) {
+    int d = threadIdx.x * 4;
+    if (kc <= 8) {
+      for (; d + 1024 < D; d += 2048) {
+        const float4 q0 = *reinterpret_cast<const float4*>(qv + d), q1 = *reinterpret_cast<const float4*>(qv + d + 1024);
+        float4 x0[8], x1[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c < kc) {
+            x0[c] = __ldg(reinterpret_cast<const float4*>(xr[c] + d));
+            x1[c] = __ldg(reinterpret_cast<const float4*>(xr[c] + d + 1024));
+          }
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c < kc) {
+            float e0 = q0.x - x0[c].x, e1 = q0.y - x0[c].y, e2 = q0.z - x0[c].z, e3 = q0.w - x0[c].w;
+            f[c] = fmaf(e0, e0, f[c]); f[c] = fmaf(e1, e1, f[c]);
+            f[c] = fmaf(e2, e2, f[c]); f[c] = fmaf(e3, e3, f[c]);
+            e0 = q1.x - x1[c].x; e1 = q1.y - x1[c].y; e2 = q1.z - x1[c].z; e3 = q1.w - x1[c].w;
+            f[c] = fmaf(e0, e0, f[c]); f[c] = fmaf(e1, e1, f[c]);
+            f[c] = fmaf(e2, e2, f[c]); f[c] = fmaf(e3, e3, f[c]);
+          }
+      }
+    }
+    for (; d < D; d += 1024) {
       const float4 qq = *reinterpret_cast<const float4*>(qv + d);
       float4 xx[KMAX];
 #pragma unroll
