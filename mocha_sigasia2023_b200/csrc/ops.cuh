@@ -46,6 +46,11 @@ int instance_norm_tokens(const float* x, int B, int n, int C, float eps, const f
                          const float* tab_mean, const float* tab_std, float* y2, cudaStream_t s,
                          __nv_bfloat16* y16 = nullptr);
 
+// Tensor-core path: y = AdaIN(x) (fp32) and q16 = IN(y) (bf16) from ONE pass over x (n <= 128, C % 64 == 0):
+// IN(g u + be) = u * g / (|g| std_u + eps) with u = IN(x), std_u = std / (std + eps)
+int adain_norm_tokens(const float* x, int B, int n, int C, float eps, const float* gb, float* y, __nv_bfloat16* q16,
+                      cudaStream_t s);
+
 // mean over tokens: out[b,c] = mean_n x[b,n,c]  (AdaptiveAvgPool1d(1), transformer.py:102)
 int token_mean(const float* x, int B, int n, int C, float* out, cudaStream_t s);
 
