@@ -292,7 +292,8 @@ extern "C" size_t mocha_to_mot_workspace_bytes(const mocha_dims* d, int B) {
   bytes += pad256(R2 * d->Kb * d->D * 4);                 // agg
   bytes += pad256(R2 * d->D * 4) * 2;                     // y1, y2
   bytes += pad256(R2 * d->Kj * d->C0 * 4);                // y3
-  bytes += pad256((size_t)B * (d->T / d->tp) * d->V * d->C0 * 4);  // g'
+  bytes += pad256((size_t)B * (d->T / d->tp) * d->V * d->C0 * 4);  // g' (fp32 path)
+  bytes += pad256((size_t)B * (d->T + d->taps_j) * d->V * d->C0 * 2);  // g' as the padded bf16 conv operand (bf16 path)
   bytes += pad256(R * d->C0 * 4);                         // y4
   bytes += pad256(R * ((d->Cin + 7) / 8 * 8) * 4);        // Ytil (rows padded to 8 floats on the bf16 path)
   bytes += tc_scratch_bytes(R2, d->Kb * d->D);

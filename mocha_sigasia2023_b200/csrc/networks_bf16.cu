@@ -191,7 +191,8 @@ int to_mot_bf16(const mocha_generator_weights* w, const float* tokens, int B, fl
   bf16* y1 = ws.take<bf16>((size_t)R2 * d.D);
   bf16* y2 = ws.take<bf16>((size_t)R2 * d.D);
   float* y3 = ws.take<float>((size_t)R2 * d.Kj * d.C0);
-  float* gp = ws.take<float>((size_t)B * Tp * d.V * d.C0);
+  const int padj = d.taps_j / 2;
+  bf16* gp16 = ws.take<bf16>((size_t)B * (d.T + 2 * padj) * d.V * d.C0);   // reflect-padded, up-sampled conv input
   bf16* y4 = ws.take<bf16>((size_t)R * d.C0);
   // the 64 -> Cin(15) output conv writes rows padded to 16 floats so that its epilogue can use TMA stores;
   // the de-normalisation pass below reads the padded rows and emits the dense tensors
@@ -203,8 +204,9 @@ int to_mot_bf16(const mocha_generator_weights* w, const float* tokens, int B, fl
   // the two consumers below are pre-activation blocks: their bf16 operand is stored through LeakyReLU
   MOCHA_TRY(tc_tconv_ex(nullptr, y1, w->tm_bb_tcn_w, w->tm_bb_tcn_b, 0, h16(y2, 1), B, Tp, d.P, d.D, d.D, d.taps_b, 1, ws, s));
   MOCHA_TRY(tc.lin(y2, d.D, w->tm_jb_gcn_w, w->tm_jb_gcn_b, 0, nullptr, f32(y3), R2, d.Kj * d.C0, d.D, ACT_NONE));
-  MOCHA_TRY(graph_agg_kv(y3, w->tm_A2, gp, B * Tp, d.P, d.V, d.C0, d.Kj, s));
-  MOCHA_TRY(tc_tconv_ex(gp, nullptr, w->tm_jb_tcn_w, w->tm_jb_tcn_b, 0, h16(y4, 1), B, d.T, d.V, d.C0, d.C0, d.taps_j, d.tp, ws, s));
+  MOCHA_TRY(graph_agg_kv_pad16(y3, w->tm_A2, gp16, B, Tp, d.tp, padj, d.P, d.V, d.C0, d.Kj, s));
+  MOCHA_TRY(tc_tconv_ex(nullptr, gp16, w->tm_jb_tcn_w, w->tm_jb_tcn_b, 0, h16(y4, 1), B, d.T, d.V, d.C0, d.C0, d.taps_j, 1, ws, s, 1,
+                        true));
   MOCHA_TRY(tc.lin(y4, d.C0, w->tm_out_w, w->tm_out_b, 0, nullptr, f32(ytp), R, Cp, d.C0, ACT_NONE));
   if (Y || Ytil) MOCHA_TRY(affine_rows(ytp, Y_mean, Y_std, Y, R, d.Cin, d.V, s, Cp, Ytil));
   return MOCHA_OK;

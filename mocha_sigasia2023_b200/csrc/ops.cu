@@ -841,6 +841,55 @@ int embed_graph_agg(const float* X, const float* Wemb, const float* bemb, const 
   return MOCHA_OK;
 }
 
+// to_mot's JointBlock input for the tensor-core path: the graph aggregation after the 1x1 conv (un-pooling
+// folded into A2) written directly as the temporal conv's operand - bf16, nearest x tdiv up-sampling in time
+// and reflect padding included - instead of an fp32 tensor plus a pad / cast pass.
+// in [B*Ts, U, Kk*C] fp32 -> out16 [B, T + 2*pad, Wn, C] with T = Ts * tdiv.
+__global__ void __launch_bounds__(256)
+graph_agg_kv_pad16_kernel(const float* __restrict__ in, const float* __restrict__ A2, __nv_bfloat16* __restrict__ out16,
+                          int Ts, int tdiv, int pad, int U, int Wn, int C, int Kk) {
+  extern __shared__ float sm[];
+  const int KC = Kk * C;
+  float* xs = sm;               // [U][Kk*C]
+  float* As = sm + U * KC;      // [Kk][U][Wn]
+  __shared__ int dst_tp[16];
+  __shared__ int n_dst;
+  const int b = blockIdx.x / Ts, t2 = blockIdx.x - b * Ts;
+  const int T = Ts * tdiv, Tp = T + 2 * pad;
+  const float* src = in + (long long)blockIdx.x * U * KC;
+  for (int i = threadIdx.x; i < U * KC; i += blockDim.x) xs[i] = src[i];
+  for (int i = threadIdx.x; i < Kk * U * Wn; i += blockDim.x) As[i] = A2[i];
+  if (threadIdx.x == 0) {
+    // padded frames whose (reflected, down-sampled) source frame is t2: tdiv interior ones plus borders
+    int n = 0;
+    for (int tp = 0; tp < Tp && n < 16; ++tp) {
+      int t = tp - pad;
+      if (t < 0) t = -t;
+      if (t >= T) t = 2 * (T - 1) - t;
+      if (t / tdiv == t2) dst_tp[n++] = tp;
+    }
+    n_dst = n;
+  }
+  __syncthreads();
+  const int C2 = C / 2;
+  for (int idx = threadIdx.x; idx < Wn * C2; idx += blockDim.x) {
+    const int w = idx / C2, c = (idx - w * C2) * 2;
+    float a0 = 0.f, a1 = 0.f;
+    for (int k = 0; k < Kk; ++k)
+      for (int u = 0; u < U; ++u) {
+        const float av = As[(k * U + u) * Wn + w];
+        if (av != 0.f) {
+          const float2 x = *reinterpret_cast<const float2*>(xs + u * KC + k * C + c);
+          a0 = fmaf(x.x, av, a0);
+          a1 = fmaf(x.y, av, a1);
+        }
+      }
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a0, a1);
+    for (int j = 0; j < n_dst; ++j)
+      *reinterpret_cast<__nv_bfloat162*>(out16 + (((long long)b * Tp + dst_tp[j]) * Wn + w) * C + c) = v;
+  }
+}
+
 // reflect-pad borders of a [B, T + 2*pad, V*C] bf16 tensor whose interior rows are already written
 __global__ void reflect_border_kernel(__nv_bfloat16* __restrict__ xp, int T, int pad, long long row8, long long total8) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -874,6 +923,19 @@ int graph_agg_kv(const float* in, const float* A2, float* out, int BT, int U, in
   graph_agg_kv_kernel<<<BT, 256, smem, s>>>(in, A2, out, U, Wn, C, Kk);
   count_launch();
   MOCHA_LAUNCH_CHECK("graph_agg_kv");
+  return MOCHA_OK;
+}
+
+int graph_agg_kv_pad16(const float* in, const float* A2, __nv_bfloat16* out16, int B, int Ts, int tdiv, int pad, int U,
+                       int Wn, int C, int Kk, cudaStream_t s) {
+  MOCHA_CHECK_ARG(in && A2 && out16 && B > 0 && Ts > 0 && tdiv >= 1 && pad >= 0 && U > 0 && Wn > 0 && C > 0 && (C & 1) == 0 && Kk > 0,
+                  "graph_agg_kv_pad16: bad args");
+  MOCHA_CHECK_ARG(tdiv + 2 * pad <= 16 && pad < Ts * tdiv, "graph_agg_kv_pad16: tdiv / pad too large");
+  const size_t smem = (size_t)(U * Kk * C + Kk * U * Wn) * sizeof(float);
+  MOCHA_CHECK_ARG(smem <= 48 * 1024, "graph_agg_kv_pad16: tile too large (%zu B)", smem);
+  graph_agg_kv_pad16_kernel<<<B * Ts, 256, smem, s>>>(in, A2, out16, Ts, tdiv, pad, U, Wn, C, Kk);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("graph_agg_kv_pad16");
   return MOCHA_OK;
 }
 

@@ -28,6 +28,11 @@ int reflect_border_fill(__nv_bfloat16* xp, int B, int T, int pad, long long row_
 int graph_agg_kv(const float* in, const float* A2, float* out, int BT, int U, int Wn, int C, int Kk,
                  cudaStream_t s);
 
+// Same aggregation emitted as the next temporal conv's bf16 operand: out16 [B, Ts*tdiv + 2*pad, Wn, C] with
+// nearest x tdiv up-sampling in time and reflect padding (tensor-core path of to_mot)
+int graph_agg_kv_pad16(const float* in, const float* A2, __nv_bfloat16* out16, int B, int Ts, int tdiv, int pad, int U,
+                       int Wn, int C, int Kk, cudaStream_t s);
+
 // out[b,t',p,c] = (1/tp) * sum_{dt<tp} sum_v in[b, tp*t'+dt, v, c] * Wp[v,p]
 // Reference: PoolJointToBodypart.forward (net/graph.py:463-465) + nn.AvgPool2d((tp,1)) (model.py:47).
 int pool_joint_body(const float* in, const float* Wp, float* out, int B, int T, int V, int P, int C,
