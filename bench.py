@@ -216,7 +216,9 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        # keep stdout to the single JSON line: NCCL prints its version banner to stdout at any debug level
+        # keep stdout to the single JSON line: with NCCL_DEBUG set (VERSION / WARN / INFO) NCCL prints its
+        # version banner to stdout, so the variable is dropped for this process and anything else goes to a file
+        os.environ.pop("NCCL_DEBUG", None)
         os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/mocha_bench_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
