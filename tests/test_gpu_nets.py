@@ -122,3 +122,27 @@ def test_bf16_tensor_core_mode(gold):
     cond, _ = gi.cvae_inputs()
     out = c.sample(cu(cond), deterministic=True).cpu().numpy()
     assert rel_err(out, gold["cvae_det"]) < RTOL_BF16
+
+
+def test_bf16_mode_at_bench_batch_sizes():
+    """The batched step takes kernel variants small batches never reach (CTA-pair temporal conv from 13 clips,
+    64-column bf16 TMA boxes, split-K matcher from 16): the whole Generator at B = 16 in bf16 tensor-core mode
+    must agree with the fp32 parity mode on the same inputs (2e-2 of the range, north_star's bf16 tolerance)."""
+    B = 16
+    src, cha = gi.pose_windows()
+    rng = np.random.default_rng(16)
+    x = np.concatenate([src, cha] * (B // 2), axis=0)[:B].astype(np.float32)
+    x = x + 0.01 * rng.standard_normal(x.shape).astype(np.float32)
+    outs = {}
+    for prec in ("fp32", "bf16"):
+        g = Generator(weights.DEFAULT_MODEL_CFG, precision=prec)
+        g.load_state_dict(weights.generator_state_dict(1777), strict=True)
+        g = g.to("cuda").eval()
+        tok = g.mot_embedding(cu(x))
+        enc = g.encoder(tok + g.pos_emb[:, :90])
+        dec = g.decoder(enc, enc.flip(0))
+        y = g.to_mot(dec)
+        outs[prec] = [t.cpu().numpy() for t in (tok, enc, dec, y)]
+    for name, a, b in zip(("tokens", "encoded", "decoded", "Ytil"), outs["bf16"], outs["fp32"]):
+        assert np.isfinite(a).all(), name
+        assert rel_err(a, b) < RTOL_BF16, (name, rel_err(a, b))
