@@ -1211,10 +1211,33 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ectx.etid = (int)threadIdx.x - 64;
     ectx.lane = lane;
     epi.kernel_begin(st, ectx);
-    for (int u = blockIdx.x; u < sh.units; u += gridDim.x) {
-      int mt, split;
-      decode_unit(sh, u, mt, split);
-      const int b = sh.nb == 1 ? 0 : fast_div(mt, sh.tiles_m_per_b), mtb = mt - b * sh.tiles_m_per_b;
+    // Tile bookkeeping off the critical path: the unit -> (m tile, split, image) decode is ~200 dependent
+    // scalar instructions (~1000 cycles between two tiles of a warp that has only one partner on its
+    // scheduler). Lane i decodes the CTA's i-th unit once, up front, while the first main loop runs; each
+    // tile then fetches its numbers with four shuffles.
+    int pre_mt = 0, pre_split = 0, pre_b = 0, pre_zb = 0;
+    {
+      const long long u = (long long)blockIdx.x + (long long)lane * gridDim.x;
+      if (u < sh.units) {
+        decode_unit(sh, (int)u, pre_mt, pre_split);
+        pre_b = sh.nb == 1 ? 0 : fast_div(pre_mt, sh.tiles_m_per_b);
+        pre_zb = sh.H > 0 ? fast_div(pre_b, sh.H) : 0;
+      }
+    }
+    int unit_it = 0;
+    for (int u = blockIdx.x; u < sh.units; u += gridDim.x, ++unit_it) {
+      int mt, split, b, zb_pre;
+      if (unit_it < 32) {
+        mt = __shfl_sync(0xffffffffu, pre_mt, unit_it);
+        split = __shfl_sync(0xffffffffu, pre_split, unit_it);
+        b = __shfl_sync(0xffffffffu, pre_b, unit_it);
+        zb_pre = __shfl_sync(0xffffffffu, pre_zb, unit_it);
+      } else {
+        decode_unit(sh, u, mt, split);
+        b = sh.nb == 1 ? 0 : fast_div(mt, sh.tiles_m_per_b);
+        zb_pre = sh.H > 0 ? fast_div(b, sh.H) : 0;
+      }
+      const int mtb = mt - b * sh.tiles_m_per_b;
       const int r_in_b = mtb * BLOCK_M + q * 32 + lane;
       const bool row_ok = r_in_b < sh.rows_out_per_b;
       const long long row = (long long)b * sh.rows_out_per_b + r_in_b;
@@ -1228,7 +1251,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ectx.slab_rows = max(0, min(32, sh.rows_out_per_b - (mtb * BLOCK_M + q * 32)));
       ectx.c_off = 0;
       if (sh.H > 0) {
-        const int zb = fast_div(b, sh.H), zh = b - zb * sh.H;
+        const int zb = zb_pre, zh = b - zb * sh.H;
         ectx.slab_row0 = mtb * BLOCK_M + q * 32;
         ectx.c_off = (long long)zb * sh.c_img_b + (long long)zh * sh.c_img_h;
         ectx.img = zb;                      // TMA-store view of a [B, rows, H*cols] output (host checks the layout)
@@ -1497,10 +1520,27 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     ectx.etid = (int)threadIdx.x - 64;
     ectx.lane = lane; ectx.half = (warp - 2) >> 2; ectx.c_off = 0; ectx.col_off = 0;
     epi.kernel_begin(st, ectx);
-    for (int u = cid; u < sh.units; u += ncl) {
-      int mt, split;
-      decode_unit(sh, u, mt, split);
-      const int b = sh.nb == 1 ? 0 : fast_div(mt, sh.tiles_m_per_b), mtb = mt - b * sh.tiles_m_per_b;
+    // lane i decodes the cluster's i-th unit up front (see tc_gemm_kernel); tiles fetch it with shuffles
+    int pre_mt = 0, pre_split = 0, pre_b = 0;
+    {
+      const long long u = (long long)cid + (long long)lane * ncl;
+      if (u < sh.units) {
+        decode_unit(sh, (int)u, pre_mt, pre_split);
+        pre_b = sh.nb == 1 ? 0 : fast_div(pre_mt, sh.tiles_m_per_b);
+      }
+    }
+    int unit_it = 0;
+    for (int u = cid; u < sh.units; u += ncl, ++unit_it) {
+      int mt, split, b;
+      if (unit_it < 32) {
+        mt = __shfl_sync(0xffffffffu, pre_mt, unit_it);
+        split = __shfl_sync(0xffffffffu, pre_split, unit_it);
+        b = __shfl_sync(0xffffffffu, pre_b, unit_it);
+      } else {
+        decode_unit(sh, u, mt, split);
+        b = sh.nb == 1 ? 0 : fast_div(mt, sh.tiles_m_per_b);
+      }
+      const int mtb = mt - b * sh.tiles_m_per_b;
       const int r0 = mtb * 256 + (int)rank * 128 + q * 32;   // first row of the slab inside its image
       const bool row_ok = r0 + lane < sh.rows_out_per_b;
       const long long row = (long long)b * sh.rows_out_per_b + r0 + lane;
