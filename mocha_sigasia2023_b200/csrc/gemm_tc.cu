@@ -2070,38 +2070,6 @@ __global__ void transpose_v_bf16_kernel(const TV* __restrict__ v, int ldv, int H
   }
 }
 
-// softmax over the last dim of S [rows, ncols] (scaled), written as bf16 P [rows, ldp] with zero padding
-__global__ void softmax_bf16_kernel(const float* __restrict__ S, long long rows, int ncols, int ldp, float scale,
-                                    __nv_bfloat16* __restrict__ P) {
-  const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * warps + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const float* r = S + row * ncols;
-  float v[8];
-  float m = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = lane + 32 * i;
-    v[i] = c < ncols ? r[c] * scale : -INFINITY;
-    m = fmaxf(m, v[i]);
-  }
-  m = warp_max(m);
-  float sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = lane + 32 * i;
-    v[i] = c < ncols ? expf(v[i] - m) : 0.f;
-    sum += v[i];
-  }
-  sum = warp_sum(sum);
-  const float inv = 1.f / sum;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = lane + 32 * i;
-    if (c < ldp) P[row * ldp + c] = __float2bfloat16_rn(v[i] * inv);
-  }
-}
-
 }  // namespace
 
 bool tc_attention_supported(int nq, int nkv, int dh) {

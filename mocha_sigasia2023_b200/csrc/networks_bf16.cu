@@ -99,7 +99,7 @@ int encoder_bf16(const mocha_generator_weights* w, const float* tokens, int B, f
   const int n = ntok(d), R = B * n, inner = d.heads * d.enc_dh;
   bf16* x16 = ws.take<bf16>((size_t)R * d.D);
   bf16* qkv = ws.take<bf16>((size_t)R * 3 * inner);
-  float* S = ws.take<float>((size_t)B * d.heads * n * n);
+  float* S = nullptr;   // scores stay in TMEM (softmax fused into the Q K^T epilogue)
   bf16* att = ws.take<bf16>((size_t)R * inner);
   float* xa = ws.take<float>((size_t)R * d.D);
   bf16* xa16 = ws.take<bf16>((size_t)R * d.D);
@@ -146,7 +146,7 @@ int decoder_bf16(const mocha_generator_weights* w, const float* src, const float
   bf16* k = ws.take<bf16>((size_t)R * inner);
   bf16* v = ws.take<bf16>((size_t)R * inner);
   bf16* att = ws.take<bf16>((size_t)R * inner);
-  float* S = ws.take<float>((size_t)B * d.heads * n * n);
+  float* S = nullptr;   // scores stay in TMEM (softmax fused into the Q K^T epilogue)
   bf16* hid = ws.take<bf16>((size_t)R * d.mlp);
   WS_OK(ws, "mocha_decoder_fwd(bf16)");
   // layer-independent functions of the style tokens
@@ -224,7 +224,7 @@ int cvae_bf16(const mocha_cvae_weights* w, const float* cond, int B, int ncond, 
   bf16* xa16 = ws.take<bf16>((size_t)Rp * D);
   bf16* xb16 = ws.take<bf16>((size_t)Rp * D);
   bf16* qkv = ws.take<bf16>((size_t)Rp * 3 * D);
-  float* S = ws.take<float>((size_t)B * H * np * np);
+  float* S = nullptr;   // scores stay in TMEM (softmax fused into the Q K^T epilogue)
   bf16* att = ws.take<bf16>((size_t)Rp * D);
   float* proj = ws.take<float>((size_t)Rp * D);
   bf16* hid = ws.take<bf16>((size_t)Rp * w->dff);

@@ -1,6 +1,5 @@
-"""Launch one bf16-in / bf16-out tcgen05 linear layer through the session-level path (for ncu source views).
-Uses Generator-free inputs: mocha_linear (fp32 in/out) is NOT what the bf16 path runs, so this goes through
-mocha_encoder_fwd-sized shapes via the attention-free helper below."""
+"""Run the bf16 tensor-core encoder (mocha_encoder_fwd, 128 clips) three times - a target for
+`ncu -k regex:tc_gemm_kernel --set full --import-source on` source-level views of the GEMM epilogues."""
 import sys, os, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
