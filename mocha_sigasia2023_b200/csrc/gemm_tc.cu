@@ -384,7 +384,10 @@ struct LinearEpiT : LinearEpiData {
   // aliases the fp32 box and a fourth operand stage fits beside a 128 x 256 tile's staging
   // The per-warp stride is a multiple of 1 KB (128 B-swizzled boxes must be 1 KB aligned); the whole column
   // bias (N <= 2048) is staged once per CTA in an 8 KB area behind the warps' buffers.
-  static constexpr int kWarpStageBytes = MODE == 2 ? 10240 : MODE == 1 ? 4096 : 5120;
+  // MODE 3 = MODE 2 without a bf16 output (no bf16 box): 8 KB per warp leaves room for 128 x 256 tiles
+  static constexpr bool kRes = MODE == 2 || MODE == 3;
+  static constexpr int kResOff = MODE == 3 ? 4096 : 6144;
+  static constexpr int kWarpStageBytes = MODE == 2 ? 10240 : MODE == 3 ? 8192 : MODE == 1 ? 4096 : 5120;
   static_assert(kWarpStageBytes % 1024 == 0, "swizzled TMA boxes need 1 KB alignment");
   static constexpr int kBiasBytes = MODE == 0 ? 0 : 8192;
   static constexpr int kStageBytes = EPI_WARPS * kWarpStageBytes + kBiasBytes;
@@ -405,9 +408,9 @@ struct LinearEpiT : LinearEpiData {
   }
   // issue the TMA prefetch of a chunk's residual box (does not depend on the accumulator)
   __device__ __forceinline__ void prefetch_res(const EpiCtx& e, int col0) const {
-    if (MODE == 2 && col0 >= 0 && col0 < N && e.slab_rows > 0 && e.lane == 0) {
+    if (kRes && col0 >= 0 && col0 < N && e.slab_rows > 0 && e.lane == 0) {
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(e.res_bar), "r"(4096u) : "memory");
-      tma_load_3d(e.stage + 6144, &tmR, e.res_bar, col0, e.row0_in_img, e.img);
+      tma_load_3d(e.stage + kResOff, &tmR, e.res_bar, col0, e.row0_in_img, e.img);
     }
   }
   // Global loads issued from the epilogue see multi-thousand-cycle latencies while every SM is streaming
@@ -719,7 +722,7 @@ struct LinearEpiT : LinearEpiData {
   // layout of tcgen05.ld: v = act(v + bias) + res, fp32 box and 64 B-swizzled bf16 box, TMA stores.
   template <int ACT>
   __device__ __forceinline__ void drain_tma_res(State& st, const EpiCtx& e, int col0, int next_col0, uint32_t (&v)[32]) const {
-    const uint32_t buf32 = e.stage, buf16 = e.stage + 4096, bufr = e.stage + 6144;
+    const uint32_t buf32 = e.stage, buf16 = e.stage + 4096, bufr = e.stage + kResOff;   // MODE 3 never has C16
     const int sw = e.lane & 7;
     if (bias) {
       const uint32_t bs = e.bias_smem + (uint32_t)(col0 * 4);
@@ -821,7 +824,7 @@ struct LinearEpiT : LinearEpiData {
   __device__ __forceinline__ void chunk(State& st, const EpiCtx& e, long long, bool, int col0, uint32_t (&v)[32],
                                         int next_col0) const {
     if (col0 >= N) return;
-    if constexpr (MODE == 2) {
+    if constexpr (kRes) {
       if (e.slab_rows <= 0) return;
       switch (act) {
         case ACT_RELU: drain_tma_res<ACT_RELU>(st, e, col0, next_col0, v); break;
@@ -1804,8 +1807,13 @@ constexpr int MAX_BLOBS = 16;
 Blob g_blobs[MAX_BLOBS];
 int g_nblobs = 0;
 
-int pick_bn(long long tiles_m, int N) {
+// k_blocks > 0 lets long-K problems keep 256-wide tiles below one wave: a 128-wide tile needs twice the
+// shared-memory fill per MMA (fill-bound at ~64 B/clk/SM), measured 16.3 -> 12.0 us on 11520 x 256 x 1024
+int pick_bn(long long tiles_m, int N, int k_blocks = 0) {
+  static const int forced = getenv("MOCHA_FORCE_BN") ? atoi(getenv("MOCHA_FORCE_BN")) : 0;  // tuning aid
+  if (forced == 32 || forced == 64 || forced == 128 || forced == 256) return forced;
   // largest BN that still gives about one wave of CTAs; tiles that would be mostly padding are skipped
+  if (k_blocks >= 8 && N >= 256 && tiles_m * ((N + 255) / 256) * 2 >= num_sms()) return 256;
   const int cands[4] = {256, 128, 64, 32};
   for (int i = 0; i < 4; ++i) {
     const int bn = cands[i];
@@ -1836,6 +1844,8 @@ int dispatch_bn_impl(int bn, const CUtensorMap& tmA, const void* Wptr, unsigned 
 // LinearEpi launches: one kernel family per epilogue mode
 int dispatch_bn(int bn, const CUtensorMap& tmA, const void* Wptr, unsigned long long wrows, unsigned long long K,
                 TcShape sh, int N, int num_kb, const LinearEpi& epi, cudaStream_t s, unsigned long long wpitch = 0) {
+  if (epi.tma == 2 && !epi.C16)   // residual, fp32 output only: no bf16 box, 128 x 256 tiles fit
+    return dispatch_bn_impl(bn, tmA, Wptr, wrows, K, sh, N, num_kb, LinearEpiT<3>{epi}, s, wpitch);
   if (epi.tma == 2 && bn == 256) bn = 128;  // the residual / two-output staging leaves room for 32 KB stages only
   if (epi.c16_wide && bn < 128) {
     LinearEpi e2 = epi;
@@ -1898,7 +1908,7 @@ int tc_linear_bf16(const __nv_bfloat16* A16, int lda, const __nv_bfloat16* W16, 
   sh.tap_row_stride = 0;
   LinearEpi epi{out.f32, N, N, bias, bias_period, res, act, out.bf16, out.lrelu};
   MOCHA_TRY(setup_out_tma(epi, (unsigned long long)M, 1));
-  return dispatch_bn(pick_bn(sh.tiles_m_total, N), tmA, W16, (unsigned long long)N, (unsigned long long)K, sh, N,
+  return dispatch_bn(pick_bn(sh.tiles_m_total, N, ceil_div(K, BLOCK_K)), tmA, W16, (unsigned long long)N, (unsigned long long)K, sh, N,
                      ceil_div(K, BLOCK_K), epi, s);
 }
 
@@ -1923,7 +1933,7 @@ int tc_linear_bf16_img(const __nv_bfloat16* A16, int lda, const __nv_bfloat16* W
   LinearEpi epi{out.f32, N, N, bias, 0, nullptr, act, out.bf16, out.lrelu};
   MOCHA_TRY(setup_out_tma(epi, (unsigned long long)rows_per_img, (unsigned long long)nb, 0, (unsigned long long)out_img_pitch_rows));
   if (epi.tma != 1) return set_error(MOCHA_ERR_ARG, "tc_linear_img: output is not TMA-storable");
-  return dispatch_bn(pick_bn(sh.tiles_m_total, N), tmA, W16, (unsigned long long)N, (unsigned long long)K, sh, N,
+  return dispatch_bn(pick_bn(sh.tiles_m_total, N, ceil_div(K, BLOCK_K)), tmA, W16, (unsigned long long)N, (unsigned long long)K, sh, N,
                      ceil_div(K, BLOCK_K), epi, s);
 }
 
