@@ -46,3 +46,9 @@ def test_session_fp32_cuda_graph():
 
 def test_session_bf16():
     _run("bf16", frames=3, B=2, use_graph=False, tol=3e-2)
+
+
+def test_session_bf16_batched_kernel_variants():
+    """16 clips reach the kernel variants of the batched step that small batches never take (split-K
+    tensor-core matcher, CTA-pair temporal conv, 64-column TMA boxes); one frame against the CPU oracle."""
+    _run("bf16", frames=1, B=16, use_graph=False, tol=3e-2)
