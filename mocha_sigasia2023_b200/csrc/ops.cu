@@ -849,17 +849,30 @@ __global__ void __launch_bounds__(256)
 graph_agg_kv_pad16_kernel(const float* __restrict__ in, const float* __restrict__ A2, __nv_bfloat16* __restrict__ out16,
                           int Ts, int tdiv, int pad, int U, int Wn, int C, int Kk) {
   extern __shared__ float sm[];
-  const int KC = Kk * C;
-  float* xs = sm;               // [U][Kk*C]
-  float* As = sm + U * KC;      // [Kk][U][Wn]
+  const int KC = Kk * C, KU = Kk * U;
+  float* xs = sm;                                   // [U][Kk*C]
+  float* lval = sm + U * KC;                        // [Wn][Kk*U] non-zero weights of output node w
+  int* loff = reinterpret_cast<int*>(lval + Wn * KU);  // [Wn][Kk*U] their source offsets u*KC + k*C
+  int* lcnt = loff + Wn * KU;                       // [Wn]
   __shared__ int dst_tp[16];
   __shared__ int n_dst;
   const int b = blockIdx.x / Ts, t2 = blockIdx.x - b * Ts;
   const int T = Ts * tdiv, Tp = T + 2 * pad;
   const float* src = in + (long long)blockIdx.x * U * KC;
-  for (int i = threadIdx.x; i < U * KC; i += blockDim.x) xs[i] = src[i];
-  for (int i = threadIdx.x; i < Kk * U * Wn; i += blockDim.x) As[i] = A2[i];
-  if (threadIdx.x == 0) {
+  for (int i = threadIdx.x * 4; i < U * KC; i += blockDim.x * 4)
+    *reinterpret_cast<float4*>(xs + i) = *reinterpret_cast<const float4*>(src + i);
+  if (threadIdx.x < Wn) {
+    // compact list of the (k, u) pairs that feed output node w (ascending (k, u): fixed summation order)
+    const int w = threadIdx.x;
+    int n = 0;
+    for (int k = 0; k < Kk; ++k)
+      for (int u = 0; u < U; ++u) {
+        const float av = A2[(k * U + u) * Wn + w];
+        if (av != 0.f) { lval[w * KU + n] = av; loff[w * KU + n] = u * KC + k * C; ++n; }
+      }
+    lcnt[w] = n;
+  }
+  if (threadIdx.x == 255) {
     // padded frames whose (reflected, down-sampled) source frame is t2: tdiv interior ones plus borders
     int n = 0;
     for (int tp = 0; tp < Tp && n < 16; ++tp) {
@@ -871,22 +884,22 @@ graph_agg_kv_pad16_kernel(const float* __restrict__ in, const float* __restrict_
     n_dst = n;
   }
   __syncthreads();
-  const int C2 = C / 2;
-  for (int idx = threadIdx.x; idx < Wn * C2; idx += blockDim.x) {
-    const int w = idx / C2, c = (idx - w * C2) * 2;
-    float a0 = 0.f, a1 = 0.f;
-    for (int k = 0; k < Kk; ++k)
-      for (int u = 0; u < U; ++u) {
-        const float av = As[(k * U + u) * Wn + w];
-        if (av != 0.f) {
-          const float2 x = *reinterpret_cast<const float2*>(xs + u * KC + k * C + c);
-          a0 = fmaf(x.x, av, a0);
-          a1 = fmaf(x.y, av, a1);
-        }
-      }
-    const __nv_bfloat162 v = __floats2bfloat162_rn(a0, a1);
+  const int C4 = C / 4;
+  for (int idx = threadIdx.x; idx < Wn * C4; idx += blockDim.x) {
+    const int w = idx / C4, c = (idx - w * C4) * 4;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int n = lcnt[w];
+    for (int i = 0; i < n; ++i) {
+      const float4 x = *reinterpret_cast<const float4*>(xs + loff[w * KU + i] + c);
+      const float av = lval[w * KU + i];
+      a.x = fmaf(x.x, av, a.x); a.y = fmaf(x.y, av, a.y); a.z = fmaf(x.z, av, a.z); a.w = fmaf(x.w, av, a.w);
+    }
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
     for (int j = 0; j < n_dst; ++j)
-      *reinterpret_cast<__nv_bfloat162*>(out16 + (((long long)b * Tp + dst_tp[j]) * Wn + w) * C + c) = v;
+      *reinterpret_cast<uint2*>(out16 + (((long long)b * Tp + dst_tp[j]) * Wn + w) * C + c) = pk;
   }
 }
 
@@ -928,10 +941,11 @@ int graph_agg_kv(const float* in, const float* A2, float* out, int BT, int U, in
 
 int graph_agg_kv_pad16(const float* in, const float* A2, __nv_bfloat16* out16, int B, int Ts, int tdiv, int pad, int U,
                        int Wn, int C, int Kk, cudaStream_t s) {
-  MOCHA_CHECK_ARG(in && A2 && out16 && B > 0 && Ts > 0 && tdiv >= 1 && pad >= 0 && U > 0 && Wn > 0 && C > 0 && (C & 1) == 0 && Kk > 0,
+  MOCHA_CHECK_ARG(in && A2 && out16 && B > 0 && Ts > 0 && tdiv >= 1 && pad >= 0 && U > 0 && Wn > 0 && Wn <= 255 && C > 0 &&
+                      (C & 3) == 0 && Kk > 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0,
                   "graph_agg_kv_pad16: bad args");
   MOCHA_CHECK_ARG(tdiv + 2 * pad <= 16 && pad < Ts * tdiv, "graph_agg_kv_pad16: tdiv / pad too large");
-  const size_t smem = (size_t)(U * Kk * C + Kk * U * Wn) * sizeof(float);
+  const size_t smem = (size_t)(U * Kk * C + 2 * Kk * U * Wn + Wn) * sizeof(float);
   MOCHA_CHECK_ARG(smem <= 48 * 1024, "graph_agg_kv_pad16: tile too large (%zu B)", smem);
   graph_agg_kv_pad16_kernel<<<B * Ts, 256, smem, s>>>(in, A2, out16, Ts, tdiv, pad, U, Wn, C, Kk);
   count_launch();
