@@ -526,7 +526,7 @@ struct LinearEpiT : LinearEpiData {
   __device__ __forceinline__ void drain_tma(State& st, const EpiCtx& e, int col0, int next_col0, const uint32_t (&v)[32]) const {
     EPI_DBG(14);
     if (bias_period == 0 || !bias) {
-      // lane = row all the way (no transposed pass): column bias by shuffle from the prefetching lanes,
+      // lane = row all the way (no transposed pass): column bias broadcast from the CTA's shared-memory copy,
       // row scale is one scalar per lane, results go straight into the TMA boxes
       float f[32];
 #pragma unroll
