@@ -179,9 +179,10 @@ int mocha_encoder_fwd(const mocha_generator_weights* w, const float* d_tokens, i
 
 /* ---- (a4) mean_variance_norm  net/transformer.py:13-20 (+ matcher scaling :293,:442) ---------- */
 /* x [B,n,C] normalised over n per (b,c). d_cnt and/or d_cnt_nm may be NULL.
- * d_cnt_nm = (cnt - cnt_mean)/cnt_std with tables [n,C]. */
+ * d_cnt_nm = (cnt - cnt_mean)/cnt_std with tables [n,C]; d_cnt_nm16 (optional, bf16 [B,n*C]) is the
+ * same query rounded to bf16, the operand of the tensor-core matcher (mocha_match_tc's d_Q16). */
 int mocha_cnt_features(const float* d_x, int B, int n, int C, float eps, float* d_cnt,
-                       const float* d_cnt_mean, const float* d_cnt_std, float* d_cnt_nm,
+                       const float* d_cnt_mean, const float* d_cnt_std, float* d_cnt_nm, void* d_cnt_nm16,
                        mocha_stream_t stream);
 
 /* ---- (a8) Generator.decoder = Transformer(adain=True)  transformer.py:79-113 ---------------- */
@@ -341,6 +342,12 @@ int mocha_post_frame(const mocha_post_params* params, const float* d_Y, const fl
                      const float* d_src_rvel, const float* d_src_rang, const uint8_t* d_contacts, int B,
                      int T, int V, int Cin, int init, mocha_clip_state* d_state, mocha_frame_out* d_out,
                      mocha_stream_t stream);
+
+/* Same, with the source-motion inputs packed one row per clip: d_side [B, side_stride] floats =
+ * [src_Yvel[i,:,1] (T*3) | src_Yrvel[i,-1] (3) | src_Yrang[i,-1] (3)], side_stride >= T*3+6. */
+int mocha_post_frame_packed(const mocha_post_params* params, const float* d_Y, const float* d_side, int side_stride,
+                            const uint8_t* d_contacts, int B, int T, int V, int Cin, int init,
+                            mocha_clip_state* d_state, mocha_frame_out* d_out, mocha_stream_t stream);
 
 /* ---- (a15) Inertialization.contact_update  motion/Inertialization.py:300-377 ----------------- */
 /* Batched over n feet; state arrays are in/out, fp64; flags int32. */

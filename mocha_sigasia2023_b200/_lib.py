@@ -121,7 +121,7 @@ SIGNATURES = {
     "mocha_bench_tconv": (_I, [C.POINTER(GeneratorWeights), _P, _I, _P, _I, _I, _P, _S, _P]),
     "mocha_encoder_workspace_bytes": (_S, [C.POINTER(Dims), _I]),
     "mocha_encoder_fwd": (_I, [C.POINTER(GeneratorWeights), _P, _I, _P, _I, _P, _S, _P]),
-    "mocha_cnt_features": (_I, [_P, _I, _I, _I, _F, _P, _P, _P, _P, _P]),
+    "mocha_cnt_features": (_I, [_P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
     "mocha_decoder_workspace_bytes": (_S, [C.POINTER(Dims), _I]),
     "mocha_decoder_fwd": (_I, [C.POINTER(GeneratorWeights), _P, _P, _I, _P, _I, _P, _S, _P]),
     "mocha_to_mot_workspace_bytes": (_S, [C.POINTER(Dims), _I]),
@@ -151,6 +151,7 @@ SIGNATURES = {
     "mocha_fk_vel": (_I, [_P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _P, _P]),
     "mocha_ik": (_I, [_P, _P, _P, _L, _I, _P, _P, _P]),
     "mocha_post_frame": (_I, [C.POINTER(PostParams), _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "mocha_post_frame_packed": (_I, [C.POINTER(PostParams), _P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "mocha_contact_update": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _D, _D, _D, _D, _P]),
     "mocha_ik_two_bone": (_I, [_P] * 10 + [_D, _L, _P, _P, _P]),
     "mocha_pose_transition": (_I, [_P] * 16 + [_L, _I, _P, _P, _P, _P, _P]),

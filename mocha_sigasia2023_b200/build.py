@@ -55,7 +55,7 @@ def build(force: bool = False, verbose: bool = False, trace: bool = False) -> st
     stamp = os.path.join(obj_dir, "stamp")
     digest = _digest(deps)
     if not force and os.path.exists(lib_path) and os.path.exists(stamp) and open(stamp).read() == digest:
-        return LIB
+        return lib_path
     os.makedirs(obj_dir, exist_ok=True)
 
     def compile_one(src: str) -> str:

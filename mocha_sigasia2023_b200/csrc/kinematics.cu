@@ -363,7 +363,7 @@ post_frame_kernel(const mocha_post_params P, const float* __restrict__ Y,
                   const float* __restrict__ src_hips_vel, const float* __restrict__ src_rvel,
                   const float* __restrict__ src_rang, const uint8_t* __restrict__ contacts, int B,
                   int T, int V, int Cin, int init, mocha_clip_state* __restrict__ states,
-                  mocha_frame_out* __restrict__ outs) {
+                  mocha_frame_out* __restrict__ outs, int hv_stride, int rv_stride) {
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (b >= B) return;  // warp-uniform
@@ -379,7 +379,7 @@ post_frame_kernel(const mocha_post_params P, const float* __restrict__ Y,
   for (int t = lane; t < T; t += 32) {
     const float* yv = Yb + ((long long)t * V + 0) * Cin + 9;
     num += sqrtf(yv[0] * yv[0] + yv[1] * yv[1] + yv[2] * yv[2]);
-    const float* sv = src_hips_vel + ((long long)b * T + t) * 3;
+    const float* sv = src_hips_vel + (long long)b * hv_stride + t * 3;
     den += sqrtf(sv[0] * sv[0] + sv[1] * sv[1] + sv[2] * sv[2]);
   }
   num = warp_sum(num);
@@ -390,9 +390,9 @@ post_frame_kernel(const mocha_post_params P, const float* __restrict__ Y,
   DQ rootrot = q4<double>(1.0, 0.0, 0.0, 0.0);
   D3 rootpos = v3<double>(0.0, 0.0, 0.0);
   if (lane == 0) {
-    const D3 yrvel = v3<double>((double)(src_rvel[b * 3 + 0] * ratio), (double)(src_rvel[b * 3 + 1] * ratio),
-                                (double)(src_rvel[b * 3 + 2] * ratio));
-    const D3 yrang = v3<double>((double)src_rang[b * 3 + 0], (double)src_rang[b * 3 + 1], (double)src_rang[b * 3 + 2]);
+    const D3 yrvel = v3<double>((double)(src_rvel[(long long)b * rv_stride + 0] * ratio), (double)(src_rvel[(long long)b * rv_stride + 1] * ratio),
+                                (double)(src_rvel[(long long)b * rv_stride + 2] * ratio));
+    const D3 yrang = v3<double>((double)src_rang[(long long)b * rv_stride + 0], (double)src_rang[(long long)b * rv_stride + 1], (double)src_rang[(long long)b * rv_stride + 2]);
     // root integration (:500-503 / :345-348)
     const DQ prev_rot = init ? q4<double>(1.0, 0.0, 0.0, 0.0) : ld4(S.root_rot);
     const D3 prev_pos = init ? v3<double>(0.0, 0.0, 0.0) : ld3(S.root_pos);
@@ -403,8 +403,8 @@ post_frame_kernel(const mocha_post_params P, const float* __restrict__ Y,
     st3(O.pos[0], rootpos); st3(O.vel[0], rootvel); st4(O.rot[0], rootrot); st3(O.ang[0], rootang);
   } else if (lane == 1) {
     // source root (:476-483): the reference keeps it in float32 arrays, so it integrates in fp32
-    const V3<float> rv = v3<float>(src_rvel[b * 3 + 0], src_rvel[b * 3 + 1], src_rvel[b * 3 + 2]);
-    const V3<float> ra = v3<float>(src_rang[b * 3 + 0], src_rang[b * 3 + 1], src_rang[b * 3 + 2]);
+    const V3<float> rv = v3<float>(src_rvel[(long long)b * rv_stride + 0], src_rvel[(long long)b * rv_stride + 1], src_rvel[(long long)b * rv_stride + 2]);
+    const V3<float> ra = v3<float>(src_rang[(long long)b * rv_stride + 0], src_rang[(long long)b * rv_stride + 1], src_rang[(long long)b * rv_stride + 2]);
     if (init) {
       const D3 p0 = dt * v3<double>((double)rv.x, (double)rv.y, (double)rv.z);
       const DQ r0 = q_from_scaled_angle_axis(dt * v3<double>((double)ra.x, (double)ra.y, (double)ra.z));
@@ -694,10 +694,10 @@ extern "C" int mocha_ik(const float* grot, const float* gpos, const int32_t* par
   return MOCHA_OK;
 }
 
-extern "C" int mocha_post_frame(const mocha_post_params* params, const float* Y, const float* src_hips_vel,
-                                const float* src_rvel, const float* src_rang, const uint8_t* contacts, int B, int T,
-                                int V, int Cin, int init, mocha_clip_state* state, mocha_frame_out* out,
-                                mocha_stream_t stream) {
+namespace {
+int post_frame_launch(const mocha_post_params* params, const float* Y, const float* src_hips_vel, const float* src_rvel,
+                      const float* src_rang, int hv_stride, int rv_stride, const uint8_t* contacts, int B, int T, int V,
+                      int Cin, int init, mocha_clip_state* state, mocha_frame_out* out, mocha_stream_t stream) {
   MOCHA_CHECK_ARG(params && Y && src_hips_vel && src_rvel && src_rang && contacts && state && out && B > 0,
                   "mocha_post_frame: null/empty argument");
   MOCHA_CHECK_ARG(params->J == V + 1 && params->J <= 25, "mocha_post_frame: J=%d must equal V+1=%d and be <= 25",
@@ -713,10 +713,29 @@ extern "C" int mocha_post_frame(const mocha_post_params* params, const float* Y,
                     "mocha_post_frame: contact bone %d needs 4 ancestors", params->contact_bones[f]);
   }
   post_frame_kernel<<<nblk((long long)B * 32, 128), 128, 0, (cudaStream_t)stream>>>(*params, Y, src_hips_vel, src_rvel, src_rang,
-                                                                 contacts, B, T, V, Cin, init, state, out);
+                                                                 contacts, B, T, V, Cin, init, state, out, hv_stride, rv_stride);
   count_launch();
   MOCHA_LAUNCH_CHECK("post_frame_kernel");
   return MOCHA_OK;
+}
+}  // namespace
+
+extern "C" int mocha_post_frame(const mocha_post_params* params, const float* Y, const float* src_hips_vel,
+                                const float* src_rvel, const float* src_rang, const uint8_t* contacts, int B, int T,
+                                int V, int Cin, int init, mocha_clip_state* state, mocha_frame_out* out,
+                                mocha_stream_t stream) {
+  return post_frame_launch(params, Y, src_hips_vel, src_rvel, src_rang, T * 3, 3, contacts, B, T, V, Cin, init, state, out,
+                           stream);
+}
+
+// Same with the three per-clip source-motion inputs packed in ONE row per clip, [hips vel T*3 | rvel 3 | rang 3]
+// (what a streaming caller uploads with a single H2D copy): no slicing copies in front of the kernel.
+extern "C" int mocha_post_frame_packed(const mocha_post_params* params, const float* Y, const float* side, int side_stride,
+                                       const uint8_t* contacts, int B, int T, int V, int Cin, int init,
+                                       mocha_clip_state* state, mocha_frame_out* out, mocha_stream_t stream) {
+  MOCHA_CHECK_ARG(side && side_stride >= T * 3 + 6, "mocha_post_frame_packed: side rows need T*3+6 floats");
+  return post_frame_launch(params, Y, side, side + T * 3, side + T * 3 + 3, side_stride, side_stride, contacts, B, T, V,
+                           Cin, init, state, out, stream);
 }
 
 extern "C" int mocha_contact_update(int32_t* state, int32_t* lock, double* position, double* velocity, double* point,

@@ -575,7 +575,8 @@ topk_exchange_merge_kernel(const double* __restrict__ ld, const long long* __res
                            long long* __restrict__ out_i) {
   const unsigned parity = epoch & 1u;
   const size_t list = (size_t)nq * k;                      // elements per list
-  const size_t slot_bytes = list * 16;
+  const size_t half_bytes = (list * 8 + 15) & ~(size_t)15; // each array starts 16 B aligned (uint4 stores), odd lists too
+  const size_t slot_bytes = 2 * half_bytes;
   const size_t parity_bytes = (size_t)world * slot_bytes;
   const size_t flags_off = 2 * parity_bytes;
   // ---- (1) push: 16 B per thread-step, this block's contiguous share of the two arrays
@@ -584,7 +585,7 @@ topk_exchange_merge_kernel(const double* __restrict__ ld, const long long* __res
     for (int p = 0; p < world; ++p) {
       unsigned char* dst = peers.buf[p] + parity * parity_bytes + (size_t)rank * slot_bytes;
       double* dd = reinterpret_cast<double*>(dst);
-      long long* di = reinterpret_cast<long long*>(dst + list * 8);
+      long long* di = reinterpret_cast<long long*>(dst + half_bytes);
       for (size_t e = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; e < n2; e += (size_t)gridDim.x * blockDim.x * 2) {
         *reinterpret_cast<uint4*>(dd + e) = *reinterpret_cast<const uint4*>(ld + e);
         *reinterpret_cast<uint4*>(di + e) = *reinterpret_cast<const uint4*>(li + e);
@@ -617,7 +618,7 @@ topk_exchange_merge_kernel(const double* __restrict__ ld, const long long* __res
     for (int t = 0; t < KMAX; ++t) { bd[t] = INFINITY; bi[t] = -1; }
     for (int sidx = 0; sidx < world; ++sidx) {
       const double* sd = reinterpret_cast<const double*>(mine + (size_t)sidx * slot_bytes);
-      const long long* si = reinterpret_cast<const long long*>(mine + (size_t)sidx * slot_bytes + list * 8);
+      const long long* si = reinterpret_cast<const long long*>(mine + (size_t)sidx * slot_bytes + half_bytes);
       for (int j = 0; j < k; ++j) {
         const long long id = __ldcv(si + (size_t)q * k + j);
         if (id >= 0) local_insert(bd, bi, k, __ldcv(sd + (size_t)q * k + j), id);
@@ -632,7 +633,8 @@ topk_exchange_merge_kernel(const double* __restrict__ ld, const long long* __res
 
 extern "C" size_t mocha_topk_exchange_bytes(int world, int nq, int k) {
   if (world < 1 || nq < 1 || k < 1) return 0;
-  return 2 * (size_t)world * nq * k * 16 + 2 * (size_t)world * 4 + 256;
+  const size_t half_bytes = ((size_t)nq * k * 8 + 15) & ~(size_t)15;   // kernel layout: [dist | idx], each 16 B aligned
+  return 2 * (size_t)world * 2 * half_bytes + 2 * (size_t)world * 4 + 256;
 }
 
 extern "C" int mocha_peer_alloc(size_t bytes, void** d_ptr, unsigned char handle_out[64]) {

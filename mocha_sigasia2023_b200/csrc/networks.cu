@@ -201,9 +201,10 @@ extern "C" int mocha_encoder_fwd(const mocha_generator_weights* w, const float* 
 }
 
 extern "C" int mocha_cnt_features(const float* x, int B, int n, int C, float eps, float* cnt,
-                                  const float* cnt_mean, const float* cnt_std, float* cnt_nm,
+                                  const float* cnt_mean, const float* cnt_std, float* cnt_nm, void* cnt_nm16,
                                   mocha_stream_t stream) {
-  return instance_norm_tokens(x, B, n, C, eps, nullptr, cnt, cnt_mean, cnt_std, cnt_nm, (cudaStream_t)stream);
+  return instance_norm_tokens(x, B, n, C, eps, nullptr, cnt, cnt_mean, cnt_std, cnt_nm, (cudaStream_t)stream, nullptr,
+                              static_cast<__nv_bfloat16*>(cnt_nm16));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -348,16 +349,22 @@ extern "C" size_t mocha_cvae_workspace_bytes(const mocha_cvae_weights* w, int B,
   if (!w || B <= 0 || ncond <= 0) return 0;
   const size_t D = w->D, np = ncond + 2, nm = ncond + 1, nq = w->out_seq;
   const size_t Rp = (size_t)B * np, Rm = (size_t)B * nm, Rq = (size_t)B * nq;
+  // qkv / scores / att / proj / hidden are shared by the prior (Rp rows) and the decoder (Rq rows, nq x nq and
+  // nq x nm scores): size them for whichever is larger (out_seq may exceed ncond + 2 through the drop-in)
+  const size_t Rx = Rp > Rq ? Rp : Rq;
+  size_t sc = np * np;
+  if (nq * nq > sc) sc = nq * nq;
+  if (nq * nm > sc) sc = nq * nm;
   size_t bytes = 0;
   bytes += pad256(Rp * D * 4) * 3;         // tok, xa, xb
-  bytes += pad256(Rp * 3 * D * 4);         // qkv (also reused by the decoder)
-  bytes += pad256((size_t)B * w->heads * np * np * 4);  // scores
-  bytes += pad256(Rp * D * 4) * 2;         // att, proj
-  bytes += pad256(Rp * w->dff * 4);        // hidden
+  bytes += pad256(Rx * 3 * D * 4);         // qkv (also reused by the decoder)
+  bytes += pad256((size_t)B * w->heads * sc * 4);  // scores
+  bytes += pad256(Rx * D * 4) * 2;         // att, proj
+  bytes += pad256(Rx * w->dff * 4);        // hidden
   bytes += pad256(Rm * D * 4);             // memory
   bytes += pad256(Rm * 2 * D * 4);         // memory K|V
   bytes += pad256(Rq * D * 4) * 3;         // decoder x ping-pong + q
-  bytes += tc_scratch_bytes(Rp, w->dff);
+  bytes += tc_scratch_bytes(Rx, w->dff);
   bytes += tc_attention_scratch_bytes(B, w->heads, (int)np, (int)np, (int)(D / w->heads));
   return bytes + 4096;
 }
@@ -385,11 +392,15 @@ extern "C" int mocha_cvae_sample(const mocha_cvae_weights* w, const float* cond,
   float* tok = ws.take<float>((size_t)Rp * D);
   float* xa = ws.take<float>((size_t)Rp * D);
   float* xb = ws.take<float>((size_t)Rp * D);
-  float* qkv = ws.take<float>((size_t)Rp * 3 * D);
-  float* S = ws.take<float>((size_t)B * H * np * np);
-  float* att = ws.take<float>((size_t)Rp * D);
-  float* proj = ws.take<float>((size_t)Rp * D);
-  float* hid = ws.take<float>((size_t)Rp * w->dff);
+  const int Rx = Rp > Rq ? Rp : Rq;   // buffers shared by the prior (Rp rows) and the decoder (Rq rows)
+  size_t sc = (size_t)np * np;
+  if ((size_t)nq * nq > sc) sc = (size_t)nq * nq;
+  if ((size_t)nq * nm > sc) sc = (size_t)nq * nm;
+  float* qkv = ws.take<float>((size_t)Rx * 3 * D);
+  float* S = ws.take<float>((size_t)B * H * sc);
+  float* att = ws.take<float>((size_t)Rx * D);
+  float* proj = ws.take<float>((size_t)Rx * D);
+  float* hid = ws.take<float>((size_t)Rx * w->dff);
   float* mem = ws.take<float>((size_t)Rm * D);
   float* memkv = ws.take<float>((size_t)Rm * 2 * D);
   float* da = ws.take<float>((size_t)Rq * D);

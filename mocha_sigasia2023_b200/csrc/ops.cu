@@ -291,7 +291,7 @@ instance_norm_tokens_kernel(const float* __restrict__ x, int n, int C, float eps
                             const float* __restrict__ gb, float* __restrict__ y,
                             const float* __restrict__ tab_mean,
                             const float* __restrict__ tab_std, float* __restrict__ y2,
-                            __nv_bfloat16* __restrict__ y16) {
+                            __nv_bfloat16* __restrict__ y16, __nv_bfloat16* __restrict__ y2h) {
   __shared__ float part[8][32];
   __shared__ float stat[2][32];
   const int b = blockIdx.x, c = blockIdx.y * 32 + (threadIdx.x & 31), warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -337,7 +337,11 @@ instance_norm_tokens_kernel(const float* __restrict__ x, int n, int C, float eps
     if (gb) v = g * v + be;
     if (y) y[(long long)b * n * C + o] = v;
     if (y16) y16[(long long)b * n * C + o] = __float2bfloat16_rn(v);
-    if (y2) y2[(long long)b * n * C + o] = (v - tab_mean[o]) / tab_std[o];
+    if (y2 || y2h) {
+      const float w = (v - tab_mean[o]) / tab_std[o];
+      if (y2) y2[(long long)b * n * C + o] = w;
+      if (y2h) y2h[(long long)b * n * C + o] = __float2bfloat16_rn(w);
+    }
   }
 }
 
@@ -347,7 +351,7 @@ instance_norm_tokens_reg_kernel(const float* __restrict__ x, int n, int C, float
                                 const float* __restrict__ gb, float* __restrict__ y,
                                 const float* __restrict__ tab_mean,
                                 const float* __restrict__ tab_std, float* __restrict__ y2,
-                                __nv_bfloat16* __restrict__ y16) {
+                                __nv_bfloat16* __restrict__ y16, __nv_bfloat16* __restrict__ y2h) {
   __shared__ float part[8][32];
   __shared__ float stat[2][32];
   const int b = blockIdx.x, c = blockIdx.y * 32 + (threadIdx.x & 31), warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -402,7 +406,11 @@ instance_norm_tokens_reg_kernel(const float* __restrict__ x, int n, int C, float
       if (gb) u = g * u + be;
       if (y) y[(long long)b * n * C + o] = u;
       if (y16) y16[(long long)b * n * C + o] = __float2bfloat16_rn(u);
-      if (y2) y2[(long long)b * n * C + o] = (u - tab_mean[o]) / tab_std[o];
+      if (y2 || y2h) {
+        const float w = (u - tab_mean[o]) / tab_std[o];
+        if (y2) y2[(long long)b * n * C + o] = w;
+        if (y2h) y2h[(long long)b * n * C + o] = __float2bfloat16_rn(w);
+      }
     }
   }
 }
@@ -978,18 +986,18 @@ int pool_graph_agg(const __nv_bfloat16* in, const float* Wp, const float* A, __n
 
 int instance_norm_tokens(const float* x, int B, int n, int C, float eps, const float* gb, float* y,
                          const float* tab_mean, const float* tab_std, float* y2, cudaStream_t s,
-                         __nv_bfloat16* y16) {
+                         __nv_bfloat16* y16, __nv_bfloat16* y2h) {
   MOCHA_CHECK_ARG(x && B > 0 && n > 1 && C > 0, "instance_norm_tokens: bad args");
-  MOCHA_CHECK_ARG(y || y2 || y16, "instance_norm_tokens: no output");
-  MOCHA_CHECK_ARG(!y2 || (tab_mean && tab_std), "instance_norm_tokens: y2 needs its table");
+  MOCHA_CHECK_ARG(y || y2 || y16 || y2h, "instance_norm_tokens: no output");
+  MOCHA_CHECK_ARG(!(y2 || y2h) || (tab_mean && tab_std), "instance_norm_tokens: y2 needs its table");
   const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gb)) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(y16) & 7) == 0;
-  if (n <= 128 && y16 && !y2 && (C % 64) == 0 && al)   // tensor-core path (bf16 twin requested): float4 kernel
+  if (n <= 128 && y16 && !y2 && !y2h && (C % 64) == 0 && al)   // tensor-core path (bf16 twin requested): float4 kernel
     instance_norm_tokens_v4_kernel<<<dim3(B, C / 64), 256, 0, s>>>(x, n, C, eps, gb, y, y16, nullptr);
   else if (n <= 128)
-    instance_norm_tokens_reg_kernel<<<dim3(B, (C + 31) / 32), 256, 0, s>>>(x, n, C, eps, gb, y, tab_mean, tab_std, y2, y16);
+    instance_norm_tokens_reg_kernel<<<dim3(B, (C + 31) / 32), 256, 0, s>>>(x, n, C, eps, gb, y, tab_mean, tab_std, y2, y16, y2h);
   else
-    instance_norm_tokens_kernel<<<dim3(B, (C + 31) / 32), 256, 0, s>>>(x, n, C, eps, gb, y, tab_mean, tab_std, y2, y16);
+    instance_norm_tokens_kernel<<<dim3(B, (C + 31) / 32), 256, 0, s>>>(x, n, C, eps, gb, y, tab_mean, tab_std, y2, y16, y2h);
   count_launch();
   MOCHA_LAUNCH_CHECK("instance_norm_tokens");
   return MOCHA_OK;

@@ -72,6 +72,7 @@ class CharacterizationSession:
         self.encoded = torch.empty((B, n, D), **f32)
         self.cnt = torch.empty((B, n, D), **f32)
         self.cnt_nm = torch.empty((B, n * D), **f32)
+        self.cnt_nm16 = torch.empty((B, n * D), dtype=torch.bfloat16, device=dev)   # tensor-core matcher operand
         self.match_idx = torch.zeros((B, 1), dtype=torch.int64, device=dev)
         self.match_dist = torch.zeros((B, 1), dtype=torch.float64, device=dev)
         self.cond = torch.empty((B, 2 * n, D), **f32)
@@ -108,7 +109,7 @@ class CharacterizationSession:
     def _ws(self):
         return _lib.ptr(self.ws), self.ws.numel()
 
-    def encode(self, X, tokens, encoded, cnt, cnt_nm):
+    def encode(self, X, tokens, encoded, cnt, cnt_nm, cnt_nm16=None):
         lib, g = self.lib, C.byref(self.gen.struct)
         B = X.shape[0]
         wp, wn = self._ws()
@@ -116,7 +117,7 @@ class CharacterizationSession:
         _lib.check(lib.mocha_encoder_fwd(g, _lib.ptr(tokens), B, _lib.ptr(encoded), self.prec, wp, wn, self._s()), "encoder")
         _lib.check(lib.mocha_cnt_features(_lib.ptr(encoded), B, self.ntok, self.D, 1e-5, _lib.ptr(cnt),
                                           _lib.ptr(self.cnt_mean), _lib.ptr(self.cnt_std), _lib.ptr(cnt_nm),
-                                          self._s()), "cnt_features")
+                                          None if cnt_nm16 is None else _lib.ptr(cnt_nm16), self._s()), "cnt_features")
 
     def _decode(self, src_encoded, cha, decoded, Y):
         lib, g = self.lib, C.byref(self.gen.struct)
@@ -137,8 +138,7 @@ class CharacterizationSession:
                 self.prec == _lib.MOCHA_BF16 and self.B >= 16 and t.D % 8 == 0 and t.D >= 1024)
         if use_tc:
             t._ensure_bf16()
-            q16 = self.cnt_nm.to(torch.bfloat16)
-            _lib.check(lib.mocha_match_tc(_lib.ptr(self.cnt_nm), _lib.ptr(q16), self.B, _lib.ptr(t._db16),
+            _lib.check(lib.mocha_match_tc(_lib.ptr(self.cnt_nm), _lib.ptr(self.cnt_nm16), self.B, _lib.ptr(t._db16),
                                           _lib.ptr(t.data), _lib.ptr(t._norm), t.N, t.D, 1, t.kc, 0,
                                           _lib.ptr(self.match_idx), _lib.ptr(self.match_dist), wp, wn, self._s()),
                        "match_tc")
@@ -150,7 +150,7 @@ class CharacterizationSession:
     def _frame_body(self, init: bool):
         """Everything between the input buffers and the FrameOut buffer (graph-capturable)."""
         lib = self.lib
-        self.encode(self.X, self.tokens, self.encoded, self.cnt, self.cnt_nm)
+        self.encode(self.X, self.tokens, self.encoded, self.cnt, self.cnt_nm, self.cnt_nm16)
         self._match()
         if init or self.with_cm_path:
             torch.index_select(self.cha_encoded, 0, self.match_idx[:, 0], out=self.cm_cha)
@@ -167,16 +167,13 @@ class CharacterizationSession:
                                              None, None, _lib.ptr(self.m1), _lib.ptr(self.s1), _lib.ptr(self.prev_cha),
                                              self.prec, wp, wn, self._s()), "cvae_sample")
         self._decode(self.encoded, self.prev_cha, self.decoded, self.Y)
-        hv = self.side[:, :self.T * 3]
-        self.src_hips_vel.copy_(hv.view(self.B, self.T, 3))
-        self.src_rvel.copy_(self.side[:, self.T * 3:self.T * 3 + 3])
-        self.src_rang.copy_(self.side[:, self.T * 3 + 3:])
+        # the kernel reads the packed `side` rows in place (no slicing copies inside the captured frame)
         self.post.started = not init
-        self.post.step(self.Y, self.src_hips_vel, self.src_rvel, self.src_rang, self.contacts)
+        self.post.step_packed(self.Y, self.side, self.contacts)
         if self.with_cm_path:
             self._decode(self.encoded, self.cm_cha, self.decoded, self.cm_Y)
             self.cm_post.started = not init
-            self.cm_post.step(self.cm_Y, self.src_hips_vel, self.src_rvel, self.src_rang, self.contacts)
+            self.cm_post.step_packed(self.cm_Y, self.side, self.contacts)
 
     def capture(self):
         """Capture the steady-state frame (i >= 1) into a CUDA graph. Call after the first frame."""
