@@ -291,6 +291,15 @@ int mocha_fk_vel(const float* d_lrot, const float* d_lpos, const float* d_lvel, 
 int mocha_ik(const float* d_grot, const float* d_gpos, const int32_t* d_parents, long long F, int J,
              float* d_lrot, float* d_lpos, mocha_stream_t stream);
 
+/* float64 variants (same layouts): the reference's final FK runs on float64 arrays (test_fullframework.py:672-694). */
+int mocha_fk_f64(const double* d_lrot, const double* d_lpos, const int32_t* d_parents, long long F, int J,
+                 double* d_grot, double* d_gpos, mocha_stream_t stream);
+int mocha_fk_vel_f64(const double* d_lrot, const double* d_lpos, const double* d_lvel, const double* d_lang,
+                     const int32_t* d_parents, long long F, int J, double* d_grot, double* d_gpos, double* d_gvel,
+                     double* d_gang, mocha_stream_t stream);
+int mocha_ik_f64(const double* d_grot, const double* d_gpos, const int32_t* d_parents, long long F, int J,
+                 double* d_lrot, double* d_lpos, mocha_stream_t stream);
+
 /* ---- (a10,a12-a16) per-frame post-process: test_fullframework.py:457-462, :492-509, :532-623 -- */
 /* Persistent per-clip state carried frame to frame (all fp64 like the reference's NumPy state). */
 typedef struct {
@@ -348,6 +357,22 @@ int mocha_post_frame(const mocha_post_params* params, const float* d_Y, const fl
 int mocha_post_frame_packed(const mocha_post_params* params, const float* d_Y, const float* d_side, int side_stride,
                             const uint8_t* d_contacts, int B, int T, int V, int Cin, int init,
                             mocha_clip_state* d_state, mocha_frame_out* d_out, mocha_stream_t stream);
+
+/* ---- element-wise quaternion algebra of motion/quat.py in the caller's precision ------------- */
+/* out[i] = op(a[i], b[i]) for i < n; dense [n, width] arrays, float32 (is_f64 == 0) or float64. Ops and widths
+ * (a, b, out): 0 mul (4,4,4) quat.py:112 | 1 inv_mul :122 | 2 mul_inv :125 | 3 mul_vec (4,3,3) :128 |
+ * 4 inv_mul_vec :132 | 5 inv (4,-,4) :109 | 6 abs :18 | 7 normalize quaternion (eps = param) :15 |
+ * 8 normalize 3-vector (3,-,3) | 9 exp (3,-,4; eps = param) :154 | 10 log (4,-,3; eps = param) :149 |
+ * 11 between (3,3,4) :143 | 12 from_angle_axis (1,3,4) :21 | 13 to_xform (4,-,9) :27 | 14 from_xform (9,-,4) :69 |
+ * 15 to_euler 'xyz' (4,-,3) :346 | 16 to_euler 'yzx' | 17 _fast_cross (3,3,3) :3 | 18 to_xform_xy (4,-,6) :42 |
+ * 19 from_xform_xy (6,-,4) :96 | 20 length of 3-vectors (3,-,1) :12 | 21 length of quaternions (4,-,1). */
+int mocha_quat_op(int op, int is_f64, const void* d_a, const void* d_b, long long n, double param, void* d_out,
+                  mocha_stream_t stream);
+
+/* quat.fk_partial's chain walk (quat.py:241-272): n chains of m bones (bone c's parent is bone c-1); element 0
+ * hangs off (d_start_pos [n,3], d_start_rot [n,4]) or, when both are NULL, is a root bone (global = local). */
+int mocha_fk_chain(int is_f64, const void* d_start_pos, const void* d_start_rot, const void* d_lpos, const void* d_lrot,
+                   long long n, int m, void* d_gpos, void* d_grot, mocha_stream_t stream);
 
 /* ---- (a15) Inertialization.contact_update  motion/Inertialization.py:300-377 ----------------- */
 /* Batched over n feet; state arrays are in/out, fp64; flags int32. */

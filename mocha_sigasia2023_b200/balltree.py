@@ -1,7 +1,9 @@
 """Drop-in for `sklearn.neighbors.BallTree` as used by the reference's context matching
 (test_fullframework.py:293-296, :440-443; train_CVAE.py:207-211): exact Euclidean k-NN with float64
 arithmetic on the float32 feature rows. No tree is built — the DB is streamed from HBM (fp64 brute
-force) or, for large DBs / query batches, ranked on tcgen05 tensor cores and re-ranked exactly."""
+force, the default: exact like sklearn) or, opt-in for large DBs / query batches (use_tensor_cores=True /
+"auto"), ranked on tcgen05 tensor cores by a bf16 / TF32 coarse score whose kc best rows are re-ranked
+exactly in fp64 (approximate only in that a true neighbour must survive the coarse cut)."""
 from __future__ import annotations
 
 import numpy as np
@@ -40,6 +42,17 @@ class BallTree:
         self._norm = None
         self._ws = None
 
+    @classmethod
+    def from_feature_db(cls, fdb, **kwargs):
+        """Tree over the local rows of a feature_db.FeatureDB without re-packing: the builder already wrote the
+        fp32 rows, the bf16 rows and their norms in the matcher's layout."""
+        if fdb.rows32 is None:
+            raise _lib.MochaError("BallTree.from_feature_db needs the fp32 rows (keep_fp32=True)")
+        t = cls(fdb.rows32, **kwargs)
+        if fdb.rows16 is not None and fdb.norms is not None:
+            t._db16, t._norm = fdb.rows16, fdb.norms
+        return t
+
     def _scratch(self, nbytes):
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=self.data.device)
@@ -66,6 +79,12 @@ class BallTree:
         dist = torch.empty((nq, k), dtype=torch.float64, device=q.device)
         use_tc = self.use_tensor_cores
         if use_tc is None:
+            # The drop-in stays EXACT by default, like sklearn's BallTree: the tensor-core path keeps the kc best rows
+            # of a bf16 / TF32 coarse score and re-ranks those exactly, which finds the true neighbours only when
+            # they survive the coarse cut (measured: tests/test_gpu_match_large.py, bench.py match_sweep) - it is
+            # opt-in (use_tensor_cores=True, or "auto" for the size-based switch of the throughput path).
+            use_tc = False
+        elif use_tc == "auto":
             use_tc = nq * self.N >= self.TC_THRESHOLD_PAIRS and self.D % 8 == 0 and self.D >= 64 and k <= self.kc
         if use_tc and self.tc_storage == "fp32":
             if self._norm32 is None:

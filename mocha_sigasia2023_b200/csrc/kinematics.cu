@@ -134,15 +134,18 @@ __global__ void quat_to_xy_kernel(const float* __restrict__ quat, long long n, f
 constexpr int MAXJ = 32;
 constexpr int FK_WARPS = 4;
 
+template <typename T>
 struct SkelSmem {
-  float rot[MAXJ][4], pos[MAXJ][3], vel[MAXJ][3], ang[MAXJ][3];
-  float grot[MAXJ][4], gpos[MAXJ][3], gvel[MAXJ][3], gang[MAXJ][3];
+  T rot[MAXJ][4], pos[MAXJ][3], vel[MAXJ][3], ang[MAXJ][3];
+  T grot[MAXJ][4], gpos[MAXJ][3], gvel[MAXJ][3], gang[MAXJ][3];
 };
 
-__device__ __forceinline__ void warp_copy_in(float* dst, const float* __restrict__ src, int n, int lane) {
+template <typename T>
+__device__ __forceinline__ void warp_copy_in(T* dst, const T* __restrict__ src, int n, int lane) {
   for (int i = lane; i < n; i += 32) dst[i] = src[i];
 }
-__device__ __forceinline__ void warp_copy_out(float* __restrict__ dst, const float* src, int n, int lane) {
+template <typename T>
+__device__ __forceinline__ void warp_copy_out(T* __restrict__ dst, const T* src, int n, int lane) {
   for (int i = lane; i < n; i += 32) dst[i] = src[i];
 }
 
@@ -153,12 +156,12 @@ __device__ __forceinline__ int joint_depth(const int32_t* par, int j, int J) {
   return d;
 }
 
-template <bool WITH_VEL>
+template <bool WITH_VEL, typename T>
 __global__ void __launch_bounds__(FK_WARPS * 32)
-fk_kernel(const float* __restrict__ lrot, const float* __restrict__ lpos, const float* __restrict__ lvel,
-          const float* __restrict__ lang, const int32_t* __restrict__ parents, long long F, int J,
-          float* __restrict__ grot, float* __restrict__ gpos, float* __restrict__ gvel, float* __restrict__ gang) {
-  __shared__ SkelSmem sm[FK_WARPS];
+fk_kernel(const T* __restrict__ lrot, const T* __restrict__ lpos, const T* __restrict__ lvel,
+          const T* __restrict__ lang, const int32_t* __restrict__ parents, long long F, int J,
+          T* __restrict__ grot, T* __restrict__ gpos, T* __restrict__ gvel, T* __restrict__ gang) {
+  __shared__ SkelSmem<T> sm[FK_WARPS];
   __shared__ int32_t par[MAXJ];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < J) par[threadIdx.x] = parents[threadIdx.x];
@@ -167,7 +170,7 @@ fk_kernel(const float* __restrict__ lrot, const float* __restrict__ lpos, const 
   int maxd = depth;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) maxd = max(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
-  SkelSmem& s = sm[warp];
+  SkelSmem<T>& s = sm[warp];
   for (long long f = (long long)blockIdx.x * FK_WARPS + warp; f < F; f += (long long)gridDim.x * FK_WARPS) {
     warp_copy_in(&s.rot[0][0], lrot + f * J * 4, J * 4, lane);
     warp_copy_in(&s.pos[0][0], lpos + f * J * 3, J * 3, lane);
@@ -180,8 +183,8 @@ fk_kernel(const float* __restrict__ lrot, const float* __restrict__ lpos, const 
     for (int lvl = 0; lvl <= maxd; ++lvl) {
       if (lane < J && depth == lvl) {
         const int j = lane;
-        const Q4<float> lr = q4<float>(s.rot[j][0], s.rot[j][1], s.rot[j][2], s.rot[j][3]);
-        const V3<float> lp = v3<float>(s.pos[j][0], s.pos[j][1], s.pos[j][2]);
+        const Q4<T> lr = q4<T>(s.rot[j][0], s.rot[j][1], s.rot[j][2], s.rot[j][3]);
+        const V3<T> lp = v3<T>(s.pos[j][0], s.pos[j][1], s.pos[j][2]);
         if (lvl == 0) {
           s.grot[j][0] = lr.w; s.grot[j][1] = lr.x; s.grot[j][2] = lr.y; s.grot[j][3] = lr.z;
           s.gpos[j][0] = lp.x; s.gpos[j][1] = lp.y; s.gpos[j][2] = lp.z;
@@ -190,20 +193,20 @@ fk_kernel(const float* __restrict__ lrot, const float* __restrict__ lpos, const 
           }
         } else {
           const int p = par[j];
-          const Q4<float> pr = q4<float>(s.grot[p][0], s.grot[p][1], s.grot[p][2], s.grot[p][3]);
-          const V3<float> pp = v3<float>(s.gpos[p][0], s.gpos[p][1], s.gpos[p][2]);
-          const V3<float> rp = qrot(pr, lp);
-          const V3<float> gp = rp + pp;
-          const Q4<float> gr = qmul(pr, lr);
+          const Q4<T> pr = q4<T>(s.grot[p][0], s.grot[p][1], s.grot[p][2], s.grot[p][3]);
+          const V3<T> pp = v3<T>(s.gpos[p][0], s.gpos[p][1], s.gpos[p][2]);
+          const V3<T> rp = qrot(pr, lp);
+          const V3<T> gp = rp + pp;
+          const Q4<T> gr = qmul(pr, lr);
           s.gpos[j][0] = gp.x; s.gpos[j][1] = gp.y; s.gpos[j][2] = gp.z;
           s.grot[j][0] = gr.w; s.grot[j][1] = gr.x; s.grot[j][2] = gr.y; s.grot[j][3] = gr.z;
           if (WITH_VEL) {
-            const V3<float> lv = v3<float>(s.vel[j][0], s.vel[j][1], s.vel[j][2]);
-            const V3<float> la = v3<float>(s.ang[j][0], s.ang[j][1], s.ang[j][2]);
-            const V3<float> pv = v3<float>(s.gvel[p][0], s.gvel[p][1], s.gvel[p][2]);
-            const V3<float> pa = v3<float>(s.gang[p][0], s.gang[p][1], s.gang[p][2]);
-            const V3<float> gv = qrot(pr, lv) + cross(pa, rp) + pv;
-            const V3<float> ga = qrot(pr, la) + pa;
+            const V3<T> lv = v3<T>(s.vel[j][0], s.vel[j][1], s.vel[j][2]);
+            const V3<T> la = v3<T>(s.ang[j][0], s.ang[j][1], s.ang[j][2]);
+            const V3<T> pv = v3<T>(s.gvel[p][0], s.gvel[p][1], s.gvel[p][2]);
+            const V3<T> pa = v3<T>(s.gang[p][0], s.gang[p][1], s.gang[p][2]);
+            const V3<T> gv = qrot(pr, lv) + cross(pa, rp) + pv;
+            const V3<T> ga = qrot(pr, la) + pa;
             s.gvel[j][0] = gv.x; s.gvel[j][1] = gv.y; s.gvel[j][2] = gv.z;
             s.gang[j][0] = ga.x; s.gang[j][1] = ga.y; s.gang[j][2] = ga.z;
           }
@@ -222,32 +225,33 @@ fk_kernel(const float* __restrict__ lrot, const float* __restrict__ lpos, const 
 }
 
 // quat.ik (motion/quat.py:175-187)
+template <typename T>
 __global__ void __launch_bounds__(FK_WARPS * 32)
-ik_kernel(const float* __restrict__ grot, const float* __restrict__ gpos, const int32_t* __restrict__ parents,
-          long long F, int J, float* __restrict__ lrot, float* __restrict__ lpos) {
-  __shared__ SkelSmem sm[FK_WARPS];
+ik_kernel(const T* __restrict__ grot, const T* __restrict__ gpos, const int32_t* __restrict__ parents,
+          long long F, int J, T* __restrict__ lrot, T* __restrict__ lpos) {
+  __shared__ SkelSmem<T> sm[FK_WARPS];
   __shared__ int32_t par[MAXJ];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < J) par[threadIdx.x] = parents[threadIdx.x];
   __syncthreads();
-  SkelSmem& s = sm[warp];
+  SkelSmem<T>& s = sm[warp];
   for (long long f = (long long)blockIdx.x * FK_WARPS + warp; f < F; f += (long long)gridDim.x * FK_WARPS) {
     warp_copy_in(&s.grot[0][0], grot + f * J * 4, J * 4, lane);
     warp_copy_in(&s.gpos[0][0], gpos + f * J * 3, J * 3, lane);
     __syncwarp();
     if (lane < J) {
       const int j = lane;
-      const Q4<float> gr = q4<float>(s.grot[j][0], s.grot[j][1], s.grot[j][2], s.grot[j][3]);
-      const V3<float> gp = v3<float>(s.gpos[j][0], s.gpos[j][1], s.gpos[j][2]);
+      const Q4<T> gr = q4<T>(s.grot[j][0], s.grot[j][1], s.grot[j][2], s.grot[j][3]);
+      const V3<T> gp = v3<T>(s.gpos[j][0], s.gpos[j][1], s.gpos[j][2]);
       if (par[j] < 0) {
         s.rot[j][0] = gr.w; s.rot[j][1] = gr.x; s.rot[j][2] = gr.y; s.rot[j][3] = gr.z;
         s.pos[j][0] = gp.x; s.pos[j][1] = gp.y; s.pos[j][2] = gp.z;
       } else {
         const int p = par[j];
-        const Q4<float> pinv = qinv(q4<float>(s.grot[p][0], s.grot[p][1], s.grot[p][2], s.grot[p][3]));
-        const V3<float> pp = v3<float>(s.gpos[p][0], s.gpos[p][1], s.gpos[p][2]);
-        const Q4<float> lr = qmul(pinv, gr);
-        const V3<float> lp = qrot(pinv, gp - pp);
+        const Q4<T> pinv = qinv(q4<T>(s.grot[p][0], s.grot[p][1], s.grot[p][2], s.grot[p][3]));
+        const V3<T> pp = v3<T>(s.gpos[p][0], s.gpos[p][1], s.gpos[p][2]);
+        const Q4<T> lr = qmul(pinv, gr);
+        const V3<T> lp = qrot(pinv, gp - pp);
         s.rot[j][0] = lr.w; s.rot[j][1] = lr.x; s.rot[j][2] = lr.y; s.rot[j][3] = lr.z;
         s.pos[j][0] = lp.x; s.pos[j][1] = lp.y; s.pos[j][2] = lp.z;
       }
@@ -665,7 +669,7 @@ extern "C" int mocha_fk(const float* lrot, const float* lpos, const int32_t* par
                         float* gpos, mocha_stream_t stream) {
   MOCHA_CHECK_ARG(lrot && lpos && grot && gpos && F > 0, "mocha_fk: bad argument");
   MOCHA_TRY(check_parents_arg(parents, J));
-  fk_kernel<false><<<fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream>>>(lrot, lpos, nullptr, nullptr, parents, F, J,
+  fk_kernel<false, float><<<fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream>>>(lrot, lpos, nullptr, nullptr, parents, F, J,
                                                                           grot, gpos, nullptr, nullptr);
   count_launch();
   MOCHA_LAUNCH_CHECK("fk_kernel");
@@ -677,7 +681,7 @@ extern "C" int mocha_fk_vel(const float* lrot, const float* lpos, const float* l
                             float* gang, mocha_stream_t stream) {
   MOCHA_CHECK_ARG(lrot && lpos && lvel && lang && grot && gpos && gvel && gang && F > 0, "mocha_fk_vel: bad argument");
   MOCHA_TRY(check_parents_arg(parents, J));
-  fk_kernel<true><<<fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream>>>(lrot, lpos, lvel, lang, parents, F, J, grot,
+  fk_kernel<true, float><<<fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream>>>(lrot, lpos, lvel, lang, parents, F, J, grot,
                                                                          gpos, gvel, gang);
   count_launch();
   MOCHA_LAUNCH_CHECK("fk_vel_kernel");
@@ -688,7 +692,7 @@ extern "C" int mocha_ik(const float* grot, const float* gpos, const int32_t* par
                         float* lpos, mocha_stream_t stream) {
   MOCHA_CHECK_ARG(lrot && lpos && grot && gpos && F > 0, "mocha_ik: bad argument");
   MOCHA_TRY(check_parents_arg(parents, J));
-  ik_kernel<<<fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream>>>(grot, gpos, parents, F, J, lrot, lpos);
+  ik_kernel<float><<<fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream>>>(grot, gpos, parents, F, J, lrot, lpos);
   count_launch();
   MOCHA_LAUNCH_CHECK("ik_kernel");
   return MOCHA_OK;
@@ -753,6 +757,41 @@ extern "C" int mocha_contact_update(int32_t* state, int32_t* lock, double* posit
   return MOCHA_OK;
 }
 
+// float64 variants of the three batch operators: the reference driver's final FK (test_fullframework.py:672-694)
+// runs on float64 arrays, and a drop-in must not narrow them
+extern "C" int mocha_fk_f64(const double* lrot, const double* lpos, const int32_t* parents, long long F, int J, double* grot,
+                            double* gpos, mocha_stream_t stream) {
+  MOCHA_CHECK_ARG(lrot && lpos && grot && gpos && F > 0, "mocha_fk_f64: bad argument");
+  MOCHA_TRY(check_parents_arg(parents, J));
+  fk_kernel<false, double><<<fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream>>>(lrot, lpos, nullptr, nullptr, parents, F, J,
+                                                                                  grot, gpos, nullptr, nullptr);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("fk_kernel<double>");
+  return MOCHA_OK;
+}
+
+extern "C" int mocha_fk_vel_f64(const double* lrot, const double* lpos, const double* lvel, const double* lang,
+                                const int32_t* parents, long long F, int J, double* grot, double* gpos, double* gvel,
+                                double* gang, mocha_stream_t stream) {
+  MOCHA_CHECK_ARG(lrot && lpos && lvel && lang && grot && gpos && gvel && gang && F > 0, "mocha_fk_vel_f64: bad argument");
+  MOCHA_TRY(check_parents_arg(parents, J));
+  fk_kernel<true, double><<<fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream>>>(lrot, lpos, lvel, lang, parents, F, J, grot,
+                                                                                 gpos, gvel, gang);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("fk_vel_kernel<double>");
+  return MOCHA_OK;
+}
+
+extern "C" int mocha_ik_f64(const double* grot, const double* gpos, const int32_t* parents, long long F, int J, double* lrot,
+                            double* lpos, mocha_stream_t stream) {
+  MOCHA_CHECK_ARG(lrot && lpos && grot && gpos && F > 0, "mocha_ik_f64: bad argument");
+  MOCHA_TRY(check_parents_arg(parents, J));
+  ik_kernel<double><<<fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream>>>(grot, gpos, parents, F, J, lrot, lpos);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("ik_kernel<double>");
+  return MOCHA_OK;
+}
+
 extern "C" int mocha_ik_two_bone(const double* root_lr, const double* mid_lr, const double* root, const double* mid,
                                  const double* end, const double* target, const double* fwd, const double* root_gr,
                                  const double* mid_gr, const double* par_gr, double max_length_buffer, long long n,
@@ -801,5 +840,250 @@ extern "C" int mocha_pose_update(double* pos, double* vel, double* rot, double* 
                                                                         halflife, dt, n, J);
   count_launch();
   MOCHA_LAUNCH_CHECK("pose_update_kernel");
+  return MOCHA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Element-wise quaternion algebra of motion/quat.py in the CALLER'S precision (float32 or float64): the
+// reference driver's per-frame loop works on float64 NumPy arrays (test_fullframework.py:321-353, :476-509),
+// so the drop-in `quat` module must not round its operands to float32. One thread per item; operands are dense
+// [n, width] arrays (the host expands broadcasts). Widths per op: see quat_op_widths().
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+enum QuatOp {
+  QOP_MUL = 0,          // quat.mul            (quat.py:112-120)  a[4] b[4] -> [4]
+  QOP_INV_MUL = 1,      // quat.inv_mul        (:122-123)
+  QOP_MUL_INV = 2,      // quat.mul_inv        (:125-126)
+  QOP_MUL_VEC = 3,      // quat.mul_vec        (:128-130)         a[4] b[3] -> [3]
+  QOP_INV_MUL_VEC = 4,  // quat.inv_mul_vec    (:132-133)
+  QOP_INV = 5,          // quat.inv            (:109-110)         a[4] -> [4]
+  QOP_ABS = 6,          // quat.abs            (:18-19)
+  QOP_NORMALIZE4 = 7,   // quat.normalize on quaternions (:15-16); eps in `param`
+  QOP_NORMALIZE3 = 8,   // quat.normalize on 3-vectors
+  QOP_EXP = 9,          // quat.exp            (:154-158)         a[3] -> [4]; eps in `param`
+  QOP_LOG = 10,         // quat.log            (:149-152)         a[4] -> [3]; eps in `param`
+  QOP_BETWEEN = 11,     // quat.between        (:143-147)         a[3] b[3] -> [4]
+  QOP_ANGLE_AXIS = 12,  // quat.from_angle_axis(:21-25)           a[1] b[3] -> [4]
+  QOP_TO_XFORM = 13,    // quat.to_xform       (:27-40)           a[4] -> [9]
+  QOP_FROM_XFORM = 14,  // quat.from_xform     (:69-94)           a[9] -> [4]
+  QOP_TO_EULER_XYZ = 15,// quat.to_euler       (:346-358)         a[4] -> [3]
+  QOP_TO_EULER_YZX = 16,
+  QOP_CROSS = 17,       // quat._fast_cross    (:3-7)             a[3] b[3] -> [3]
+  QOP_TO_XFORM_XY = 18, // quat.to_xform_xy    (:42-55)           a[4] -> [6]
+  QOP_FROM_XFORM_XY = 19,// quat.from_xform_xy (:96-107)          a[6] -> [4]
+  QOP_LENGTH3 = 20,     // quat.length         (:12-13)           a[3] -> [1]
+  QOP_LENGTH4 = 21,     //                                        a[4] -> [1]
+  QOP_COUNT = 22
+};
+
+struct QuatOpWidths { int a, b, o; };
+__host__ __device__ inline QuatOpWidths quat_op_widths(int op) {
+  switch (op) {
+    case QOP_MUL: case QOP_INV_MUL: case QOP_MUL_INV: return {4, 4, 4};
+    case QOP_MUL_VEC: case QOP_INV_MUL_VEC: return {4, 3, 3};
+    case QOP_INV: case QOP_ABS: case QOP_NORMALIZE4: return {4, 0, 4};
+    case QOP_NORMALIZE3: return {3, 0, 3};
+    case QOP_EXP: return {3, 0, 4};
+    case QOP_LOG: return {4, 0, 3};
+    case QOP_BETWEEN: return {3, 3, 4};
+    case QOP_ANGLE_AXIS: return {1, 3, 4};
+    case QOP_TO_XFORM: return {4, 0, 9};
+    case QOP_FROM_XFORM: return {9, 0, 4};
+    case QOP_TO_EULER_XYZ: case QOP_TO_EULER_YZX: return {4, 0, 3};
+    case QOP_CROSS: return {3, 3, 3};
+    case QOP_TO_XFORM_XY: return {4, 0, 6};
+    case QOP_FROM_XFORM_XY: return {6, 0, 4};
+    case QOP_LENGTH3: return {3, 0, 1};
+    case QOP_LENGTH4: return {4, 0, 1};
+    default: return {0, 0, 0};
+  }
+}
+
+template <typename T> __device__ __forceinline__ T clamp1(T x) { return x < (T)-1 ? (T)-1 : x > (T)1 ? (T)1 : x; }
+
+template <typename T>
+__global__ void quat_op_kernel(int op, const T* __restrict__ a, const T* __restrict__ b, long long n, T param,
+                               T* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const QuatOpWidths w = quat_op_widths(op);
+  const T* pa = a + i * w.a;
+  const T* pb = b ? b + i * w.b : nullptr;
+  T* po = out + i * w.o;
+  switch (op) {
+    case QOP_MUL: case QOP_INV_MUL: case QOP_MUL_INV: {
+      Q4<T> x = q4<T>(pa[0], pa[1], pa[2], pa[3]), y = q4<T>(pb[0], pb[1], pb[2], pb[3]);
+      if (op == QOP_INV_MUL) x = qinv(x);
+      if (op == QOP_MUL_INV) y = qinv(y);
+      const Q4<T> r = qmul(x, y);
+      po[0] = r.w; po[1] = r.x; po[2] = r.y; po[3] = r.z;
+      break;
+    }
+    case QOP_MUL_VEC: case QOP_INV_MUL_VEC: {
+      Q4<T> q = q4<T>(pa[0], pa[1], pa[2], pa[3]);
+      if (op == QOP_INV_MUL_VEC) q = qinv(q);
+      const V3<T> r = qrot(q, v3<T>(pb[0], pb[1], pb[2]));
+      po[0] = r.x; po[1] = r.y; po[2] = r.z;
+      break;
+    }
+    case QOP_INV: po[0] = pa[0]; po[1] = -pa[1]; po[2] = -pa[2]; po[3] = -pa[3]; break;
+    case QOP_ABS: {
+      const T s = pa[0] > (T)0 ? (T)1 : (T)-1;
+      po[0] = s * pa[0]; po[1] = s * pa[1]; po[2] = s * pa[2]; po[3] = s * pa[3];
+      break;
+    }
+    case QOP_NORMALIZE4: {
+      const T d = sqrt(pa[0] * pa[0] + pa[1] * pa[1] + pa[2] * pa[2] + pa[3] * pa[3]) + param;
+      po[0] = pa[0] / d; po[1] = pa[1] / d; po[2] = pa[2] / d; po[3] = pa[3] / d;
+      break;
+    }
+    case QOP_NORMALIZE3: {
+      const T d = sqrt(pa[0] * pa[0] + pa[1] * pa[1] + pa[2] * pa[2]) + param;
+      po[0] = pa[0] / d; po[1] = pa[1] / d; po[2] = pa[2] / d;
+      break;
+    }
+    case QOP_EXP: {
+      const T h = sqrt(pa[0] * pa[0] + pa[1] * pa[1] + pa[2] * pa[2]);
+      const T c = h < param ? (T)1 : cos(h);
+      const T s = h < param ? (T)1 : sin(h) / h;
+      po[0] = c; po[1] = s * pa[0]; po[2] = s * pa[1]; po[3] = s * pa[2];
+      break;
+    }
+    case QOP_LOG: {
+      const T len = sqrt(pa[1] * pa[1] + pa[2] * pa[2] + pa[3] * pa[3]);
+      const T ha = len < param ? (T)1 : atan2(len, pa[0]) / len;
+      po[0] = ha * pa[1]; po[1] = ha * pa[2]; po[2] = ha * pa[3];
+      break;
+    }
+    case QOP_BETWEEN: {
+      const V3<T> x = v3<T>(pa[0], pa[1], pa[2]), y = v3<T>(pb[0], pb[1], pb[2]);
+      const V3<T> c = cross(x, y);
+      po[0] = sqrt(dot(x, x) * dot(y, y)) + dot(x, y); po[1] = c.x; po[2] = c.y; po[3] = c.z;
+      break;
+    }
+    case QOP_ANGLE_AXIS: {
+      const Q4<T> r = q_angle_axis(pa[0], v3<T>(pb[0], pb[1], pb[2]));
+      po[0] = r.w; po[1] = r.x; po[2] = r.y; po[3] = r.z;
+      break;
+    }
+    case QOP_TO_XFORM: case QOP_TO_XFORM_XY: {
+      const T qw = pa[0], qx = pa[1], qy = pa[2], qz = pa[3];
+      const T x2 = qx + qx, y2 = qy + qy, z2 = qz + qz;
+      const T xx = qx * x2, yy = qy * y2, wx = qw * x2;
+      const T xy = qx * y2, yz = qy * z2, wy = qw * y2;
+      const T xz = qx * z2, zz = qz * z2, wz = qw * z2;
+      if (op == QOP_TO_XFORM) {
+        po[0] = (T)1 - (yy + zz); po[1] = xy - wz; po[2] = xz + wy;
+        po[3] = xy + wz; po[4] = (T)1 - (xx + zz); po[5] = yz - wx;
+        po[6] = xz - wy; po[7] = yz + wx; po[8] = (T)1 - (xx + yy);
+      } else {
+        po[0] = (T)1 - (yy + zz); po[1] = xy - wz;
+        po[2] = xy + wz; po[3] = (T)1 - (xx + zz);
+        po[4] = xz - wy; po[5] = yz + wx;
+      }
+      break;
+    }
+    case QOP_FROM_XFORM: {
+      const T m[3][3] = {{pa[0], pa[1], pa[2]}, {pa[3], pa[4], pa[5]}, {pa[6], pa[7], pa[8]}};
+      const Q4<T> r = q_from_xform(m);
+      po[0] = r.w; po[1] = r.x; po[2] = r.y; po[3] = r.z;
+      break;
+    }
+    case QOP_FROM_XFORM_XY: {
+      const Q4<T> r = q_from_xy(v3<T>(pa[0], pa[2], pa[4]), v3<T>(pa[1], pa[3], pa[5]));
+      po[0] = r.w; po[1] = r.x; po[2] = r.y; po[3] = r.z;
+      break;
+    }
+    case QOP_TO_EULER_XYZ: {
+      const T q0 = pa[0], q1 = pa[1], q2 = pa[2], q3 = pa[3];
+      po[0] = atan2((T)2 * (q0 * q1 + q2 * q3), (T)1 - (T)2 * (q1 * q1 + q2 * q2));
+      po[1] = asin(clamp1((T)2 * (q0 * q2 - q3 * q1)));
+      po[2] = atan2((T)2 * (q0 * q3 + q1 * q2), (T)1 - (T)2 * (q2 * q2 + q3 * q3));
+      break;
+    }
+    case QOP_TO_EULER_YZX: {
+      const T q0 = pa[0], q1 = pa[1], q2 = pa[2], q3 = pa[3];
+      po[0] = atan2((T)2 * (q1 * q0 - q2 * q3), -q1 * q1 + q2 * q2 - q3 * q3 + q0 * q0);
+      po[1] = atan2((T)2 * (q2 * q0 - q1 * q3), q1 * q1 - q2 * q2 - q3 * q3 + q0 * q0);
+      po[2] = asin(clamp1((T)2 * (q1 * q2 + q3 * q0)));
+      break;
+    }
+    case QOP_CROSS: {
+      const V3<T> c = cross(v3<T>(pa[0], pa[1], pa[2]), v3<T>(pb[0], pb[1], pb[2]));
+      po[0] = c.x; po[1] = c.y; po[2] = c.z;
+      break;
+    }
+    case QOP_LENGTH3: po[0] = sqrt(pa[0] * pa[0] + pa[1] * pa[1] + pa[2] * pa[2]); break;
+    case QOP_LENGTH4: po[0] = sqrt(pa[0] * pa[0] + pa[1] * pa[1] + pa[2] * pa[2] + pa[3] * pa[3]); break;
+    default: break;
+  }
+}
+
+// quat.fk_partial's chain walk (quat.py:241-272): n independent chains of m bones, bone c's parent is bone c-1 of
+// the chain; chain element 0 hangs off (start_pos, start_rot) when has_start != 0, else it is a root bone whose
+// global transform equals its local one. Sequential per chain (m <= 32), one thread per chain.
+template <typename T>
+__global__ void fk_chain_kernel(const T* __restrict__ start_pos, const T* __restrict__ start_rot, int has_start,
+                                const T* __restrict__ lpos, const T* __restrict__ lrot, long long n, int m,
+                                T* __restrict__ gpos, T* __restrict__ grot) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  V3<T> pp = v3<T>((T)0, (T)0, (T)0);
+  Q4<T> pr = q4<T>((T)1, (T)0, (T)0, (T)0);
+  if (has_start) {
+    pp = v3<T>(start_pos[i * 3], start_pos[i * 3 + 1], start_pos[i * 3 + 2]);
+    pr = q4<T>(start_rot[i * 4], start_rot[i * 4 + 1], start_rot[i * 4 + 2], start_rot[i * 4 + 3]);
+  }
+  for (int c = 0; c < m; ++c) {
+    const T* lp = lpos + (i * m + c) * 3;
+    const T* lr = lrot + (i * m + c) * 4;
+    V3<T> gp = v3<T>(lp[0], lp[1], lp[2]);
+    Q4<T> gr = q4<T>(lr[0], lr[1], lr[2], lr[3]);
+    if (has_start || c > 0) {
+      gp = qrot(pr, gp) + pp;
+      gr = qmul(pr, gr);
+    }
+    T* op = gpos + (i * m + c) * 3;
+    T* orr = grot + (i * m + c) * 4;
+    op[0] = gp.x; op[1] = gp.y; op[2] = gp.z;
+    orr[0] = gr.w; orr[1] = gr.x; orr[2] = gr.y; orr[3] = gr.z;
+    pp = gp; pr = gr;
+  }
+}
+
+}  // namespace
+
+extern "C" int mocha_quat_op(int op, int is_f64, const void* a, const void* b, long long n, double param, void* out,
+                             mocha_stream_t stream) {
+  MOCHA_CHECK_ARG(op >= 0 && op < QOP_COUNT, "mocha_quat_op: unknown op %d", op);
+  const QuatOpWidths w = quat_op_widths(op);
+  MOCHA_CHECK_ARG(a && out && n > 0 && (w.b == 0 || b), "mocha_quat_op: null/empty argument");
+  const unsigned grid = (unsigned)((n + 127) / 128);
+  if (is_f64)
+    quat_op_kernel<double><<<grid, 128, 0, (cudaStream_t)stream>>>(op, (const double*)a, (const double*)b, n, param, (double*)out);
+  else
+    quat_op_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>(op, (const float*)a, (const float*)b, n, (float)param, (float*)out);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("quat_op_kernel");
+  return MOCHA_OK;
+}
+
+extern "C" int mocha_fk_chain(int is_f64, const void* start_pos, const void* start_rot, const void* lpos, const void* lrot,
+                              long long n, int m, void* gpos, void* grot, mocha_stream_t stream) {
+  MOCHA_CHECK_ARG(lpos && lrot && gpos && grot && n > 0 && m >= 1 && m <= 64, "mocha_fk_chain: bad argument");
+  MOCHA_CHECK_ARG((start_pos == nullptr) == (start_rot == nullptr), "mocha_fk_chain: start transform needs both parts");
+  const unsigned grid = (unsigned)((n + 63) / 64);
+  const int hs = start_pos != nullptr;
+  if (is_f64)
+    fk_chain_kernel<double><<<grid, 64, 0, (cudaStream_t)stream>>>((const double*)start_pos, (const double*)start_rot, hs,
+                                                                    (const double*)lpos, (const double*)lrot, n, m,
+                                                                    (double*)gpos, (double*)grot);
+  else
+    fk_chain_kernel<float><<<grid, 64, 0, (cudaStream_t)stream>>>((const float*)start_pos, (const float*)start_rot, hs,
+                                                                   (const float*)lpos, (const float*)lrot, n, m, (float*)gpos,
+                                                                   (float*)grot);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("fk_chain_kernel");
   return MOCHA_OK;
 }

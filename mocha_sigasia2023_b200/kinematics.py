@@ -47,35 +47,86 @@ def quat_to_xy(q: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def _fp(ts):
+    """All tensors float32 or all float64 (CUDA, contiguous); returns (tensors, suffix of the ABI entry)."""
+    ts = [t.contiguous() for t in ts]
+    for t in ts:
+        _lib.require_cuda(t)
+    dt = ts[0].dtype
+    if dt not in (torch.float32, torch.float64) or any(t.dtype != dt for t in ts):
+        raise _lib.MochaError("expected CUDA tensors of one floating type (float32 or float64)")
+    return ts, ("_f64" if dt == torch.float64 else "")
+
+
 def fk(lrot, lpos, parents):
-    lrot, lpos = _f32(lrot.contiguous()), _f32(lpos.contiguous())
+    (lrot, lpos), sfx = _fp((lrot, lpos))
     J = lrot.shape[-2]
     F = lrot.numel() // (4 * J)
     grot, gpos = torch.empty_like(lrot), torch.empty_like(lpos)
-    _lib.check(_lib.load().mocha_fk(_lib.ptr(lrot), _lib.ptr(lpos), _lib.ptr(parents), F, J, _lib.ptr(grot),
-                                    _lib.ptr(gpos), _lib.stream_ptr()), "mocha_fk")
+    _lib.check(getattr(_lib.load(), "mocha_fk" + sfx)(_lib.ptr(lrot), _lib.ptr(lpos), _lib.ptr(parents), F, J,
+                                                      _lib.ptr(grot), _lib.ptr(gpos), _lib.stream_ptr()), "mocha_fk")
     return grot, gpos
 
 
 def fk_vel(lrot, lpos, lvel, lang, parents):
-    lrot, lpos, lvel, lang = (_f32(t.contiguous()) for t in (lrot, lpos, lvel, lang))
+    (lrot, lpos, lvel, lang), sfx = _fp((lrot, lpos, lvel, lang))
     J = lrot.shape[-2]
     F = lrot.numel() // (4 * J)
     grot, gpos, gvel, gang = (torch.empty_like(t) for t in (lrot, lpos, lvel, lang))
-    _lib.check(_lib.load().mocha_fk_vel(_lib.ptr(lrot), _lib.ptr(lpos), _lib.ptr(lvel), _lib.ptr(lang),
-                                        _lib.ptr(parents), F, J, _lib.ptr(grot), _lib.ptr(gpos), _lib.ptr(gvel),
-                                        _lib.ptr(gang), _lib.stream_ptr()), "mocha_fk_vel")
+    _lib.check(getattr(_lib.load(), "mocha_fk_vel" + sfx)(
+        _lib.ptr(lrot), _lib.ptr(lpos), _lib.ptr(lvel), _lib.ptr(lang), _lib.ptr(parents), F, J, _lib.ptr(grot),
+        _lib.ptr(gpos), _lib.ptr(gvel), _lib.ptr(gang), _lib.stream_ptr()), "mocha_fk_vel")
     return grot, gpos, gvel, gang
 
 
 def ik(grot, gpos, parents):
-    grot, gpos = _f32(grot.contiguous()), _f32(gpos.contiguous())
+    (grot, gpos), sfx = _fp((grot, gpos))
     J = grot.shape[-2]
     F = grot.numel() // (4 * J)
     lrot, lpos = torch.empty_like(grot), torch.empty_like(gpos)
-    _lib.check(_lib.load().mocha_ik(_lib.ptr(grot), _lib.ptr(gpos), _lib.ptr(parents), F, J, _lib.ptr(lrot),
-                                    _lib.ptr(lpos), _lib.stream_ptr()), "mocha_ik")
+    _lib.check(getattr(_lib.load(), "mocha_ik" + sfx)(_lib.ptr(grot), _lib.ptr(gpos), _lib.ptr(parents), F, J,
+                                                      _lib.ptr(lrot), _lib.ptr(lpos), _lib.stream_ptr()), "mocha_ik")
     return lrot, lpos
+
+
+QOPS = {"mul": 0, "inv_mul": 1, "mul_inv": 2, "mul_vec": 3, "inv_mul_vec": 4, "inv": 5, "abs": 6, "normalize4": 7,
+        "normalize3": 8, "exp": 9, "log": 10, "between": 11, "from_angle_axis": 12, "to_xform": 13, "from_xform": 14,
+        "to_euler_xyz": 15, "to_euler_yzx": 16, "cross": 17, "to_xform_xy": 18, "from_xform_xy": 19, "length3": 20,
+        "length4": 21}
+_QWIDTH = {0: (4, 4, 4), 1: (4, 4, 4), 2: (4, 4, 4), 3: (4, 3, 3), 4: (4, 3, 3), 5: (4, 0, 4), 6: (4, 0, 4), 7: (4, 0, 4),
+           8: (3, 0, 3), 9: (3, 0, 4), 10: (4, 0, 3), 11: (3, 3, 4), 12: (1, 3, 4), 13: (4, 0, 9), 14: (9, 0, 4),
+           15: (4, 0, 3), 16: (4, 0, 3), 17: (3, 3, 3), 18: (4, 0, 6), 19: (6, 0, 4), 20: (3, 0, 1), 21: (4, 0, 1)}
+
+
+def quat_op(name: str, a: torch.Tensor, b: torch.Tensor | None = None, param: float = 0.0) -> torch.Tensor:
+    """Element-wise quaternion algebra in the tensors' own precision (mocha_quat_op). a: [n, wa], b: [n, wb]
+    dense CUDA tensors of one dtype (float32 / float64); returns [n, wo]."""
+    op = QOPS[name]
+    wa, wb, wo = _QWIDTH[op]
+    ts, sfx = _fp((a,) if b is None else (a, b))
+    a = ts[0]
+    if a.dim() != 2 or a.shape[1] != wa or (wb and (ts[1].shape != (a.shape[0], wb))):
+        raise _lib.MochaError(f"quat_op {name}: operand shapes {tuple(a.shape)} / "
+                              f"{None if b is None else tuple(b.shape)} do not match widths {(wa, wb)}")
+    n = a.shape[0]
+    out = torch.empty((n, wo), dtype=a.dtype, device=a.device)
+    if n:
+        _lib.check(_lib.load().mocha_quat_op(op, int(sfx == "_f64"), _lib.ptr(a), None if b is None else _lib.ptr(ts[1]),
+                                             n, float(param), _lib.ptr(out), _lib.stream_ptr()), "mocha_quat_op")
+    return out
+
+
+def fk_chain(lpos: torch.Tensor, lrot: torch.Tensor, start_pos=None, start_rot=None):
+    """quat.fk_partial's chain walk: lpos [n,m,3], lrot [n,m,4]; bone c hangs off bone c-1, bone 0 off
+    (start_pos [n,3], start_rot [n,4]) or is a root when they are None. Returns (gpos, grot)."""
+    ts = (lpos, lrot) if start_pos is None else (lpos, lrot, start_pos, start_rot)
+    ts, sfx = _fp(ts)
+    n, m = ts[0].shape[0], ts[0].shape[1]
+    gpos, grot = torch.empty_like(ts[0]), torch.empty_like(ts[1])
+    _lib.check(_lib.load().mocha_fk_chain(int(sfx == "_f64"), None if start_pos is None else _lib.ptr(ts[2]),
+                                          None if start_pos is None else _lib.ptr(ts[3]), _lib.ptr(ts[0]), _lib.ptr(ts[1]),
+                                          n, m, _lib.ptr(gpos), _lib.ptr(grot), _lib.stream_ptr()), "mocha_fk_chain")
+    return gpos, grot
 
 
 def contact_update(state, lock, position, velocity, point, target, off_pos, off_vel, input_position, input_state,

@@ -1,34 +1,62 @@
 """Drop-in for the reference's `motion/quat.py` (NumPy in, NumPy out, same positional signatures,
-quaternions [w,x,y,z]) computing on the GPU through libmocha_b200 / CUDA tensors.
+quaternions [w,x,y,z]) computing on the GPU through libmocha_b200.
 
-Batch operators of the hot path run in the library's kernels:
-from_xform_xy, to_xform_xy, fk, fk_vel, ik, ik_two_bone, fk_partial / fk_vel_bone (via the FK
-kernels). Small element-wise helpers run as CUDA tensor expressions (tq.py). Kernels compute in
-float32 (float64 for ik_two_bone); results come back in the input's dtype."""
+Every function computes in the precision NumPy would have used for the same call: float32 operands stay
+float32, anything else (float64 arrays, integer constants such as `np.array([1, 0, 0, 0])`) is float64 -
+the reference driver's per-frame loop runs on float64 state (test_fullframework.py:321-353, :476-509) and a
+drop-in must not narrow it. Element-wise algebra goes through `mocha_quat_op` (one templated kernel family,
+float32 / float64), the batch operators of the hot path through
+`mocha_fk*`, `mocha_ik*`, `mocha_fk_chain`, `mocha_ik_two_bone`, `mocha_xy_to_quat`, `mocha_quat_to_xy`."""
 from __future__ import annotations
+
+import builtins
 
 import numpy as np
 import torch
 
 from . import kinematics as kin
-from . import tq
 
 
-def _cu(a, dtype=torch.float32):
-    return torch.as_tensor(np.ascontiguousarray(np.asarray(a)), dtype=dtype).cuda()
+# ---------------------------------------------------------------------------------------------------
+# marshalling
+# ---------------------------------------------------------------------------------------------------
+def _wdt(*arrays):
+    """NumPy's result dtype for these operands, restricted to the two precisions the kernels have."""
+    dt = np.result_type(*[np.asarray(a).dtype for a in arrays])
+    return np.float32 if dt == np.float32 else np.float64
 
 
-def _back(t, like):
-    out = t.cpu().numpy()
-    like = np.asarray(like)
-    return out.astype(like.dtype if like.dtype.kind == "f" else np.float64)
+def _cu(a, dt):
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(a), dtype=dt)).cuda()
 
 
-def _bin(fn, a, b):
-    ta, tb = _cu(a), _cu(b)
-    shape = np.broadcast_shapes(ta.shape[:-1], tb.shape[:-1])
-    ta, tb = ta.expand(shape + ta.shape[-1:]), tb.expand(shape + tb.shape[-1:])
-    return _back(fn(ta, tb), np.zeros(1, dtype=np.result_type(np.asarray(a).dtype, np.asarray(b).dtype, np.float32)))
+def _unary(name, x, wa, wo, param=0.0, dt=None):
+    x = np.asarray(x)
+    dt = dt or _wdt(x)
+    lead = x.shape[:-1]
+    if x.shape[-1] != wa:
+        raise ValueError(f"quat.{name}: last axis must have {wa} elements, got {x.shape}")
+    out = kin.quat_op(name, _cu(x.reshape(-1, wa), dt), None, param)
+    return out.cpu().numpy().reshape(lead + (wo,))
+
+
+def _binary(name, a, b, wa, wb, wo, dt=None):
+    a, b = np.asarray(a), np.asarray(b)
+    dt = dt or _wdt(a, b)
+    if a.shape[-1] != wa or b.shape[-1] != wb:
+        raise ValueError(f"quat.{name}: operand shapes {a.shape} / {b.shape} need last axes {wa} / {wb}")
+    lead = np.broadcast_shapes(a.shape[:-1], b.shape[:-1])
+    a = np.broadcast_to(a, lead + (wa,)).reshape(-1, wa)
+    b = np.broadcast_to(b, lead + (wb,)).reshape(-1, wb)
+    out = kin.quat_op(name, _cu(a, dt), _cu(b, dt))
+    return out.cpu().numpy().reshape(lead + (wo,))
+
+
+# ---------------------------------------------------------------------------------------------------
+# element-wise algebra (motion/quat.py:3-164, :346-368)
+# ---------------------------------------------------------------------------------------------------
+def _fast_cross(a, b):
+    return _binary("cross", a, b, 3, 3, 3)
 
 
 def eye(shape, dtype=np.float32):
@@ -36,63 +64,58 @@ def eye(shape, dtype=np.float32):
 
 
 def length(x):
-    return _back(torch.sqrt((_cu(x) ** 2).sum(-1)), x)
+    x = np.asarray(x)
+    if x.shape[-1] not in (3, 4):
+        raise ValueError("quat.length: last axis must have 3 or 4 elements")
+    return _unary("length%d" % x.shape[-1], x, x.shape[-1], 1)[..., 0]
 
 
 def normalize(x, eps=1e-8):
-    t = _cu(x)
-    return _back(t / (torch.sqrt((t * t).sum(-1, keepdim=True)) + eps), x)
+    x = np.asarray(x)
+    if x.shape[-1] not in (3, 4):
+        raise ValueError("quat.normalize: last axis must have 3 or 4 elements")
+    return _unary("normalize%d" % x.shape[-1], x, x.shape[-1], x.shape[-1], eps)
 
 
 def abs(x):
-    t = _cu(x)
-    return _back(torch.where(t[..., 0:1] > 0.0, t, -t), x)
+    return _unary("abs", x, 4, 4)
 
 
 def inv(q):
-    return _back(tq.inv(_cu(q)), q)
+    return _unary("inv", q, 4, 4)
 
 
 def mul(x, y):
-    return _bin(tq.mul, x, y)
+    return _binary("mul", x, y, 4, 4, 4)
 
 
 def inv_mul(x, y):
-    return _bin(lambda a, b: tq.mul(tq.inv(a), b), x, y)
+    return _binary("inv_mul", x, y, 4, 4, 4)
 
 
 def mul_inv(x, y):
-    return _bin(lambda a, b: tq.mul(a, tq.inv(b)), x, y)
+    return _binary("mul_inv", x, y, 4, 4, 4)
 
 
 def mul_vec(q, x):
-    return _bin(tq.mul_vec, q, x)
+    return _binary("mul_vec", q, x, 4, 3, 3)
 
 
 def inv_mul_vec(q, x):
-    return _bin(lambda a, b: tq.mul_vec(tq.inv(a), b), q, x)
+    return _binary("inv_mul_vec", q, x, 4, 3, 3)
 
 
 def from_angle_axis(angle, axis):
-    a = _cu(angle)
-    ax = _cu(axis).expand(a.shape + (3,))
-    return _back(torch.cat([torch.cos(a / 2.0)[..., None], torch.sin(a / 2.0)[..., None] * ax], dim=-1), angle)
+    angle, axis = np.asarray(angle), np.asarray(axis)
+    return _binary("from_angle_axis", angle[..., np.newaxis], axis, 1, 3, 4)
 
 
 def exp(x, eps=1e-5):
-    t = _cu(x)
-    h = torch.sqrt((t * t).sum(-1, keepdim=True))
-    c = torch.where(h < eps, torch.ones_like(h), torch.cos(h))
-    s = torch.where(h < eps, torch.ones_like(h), torch.sin(h) / torch.where(h < eps, torch.ones_like(h), h))
-    return _back(torch.cat([c, s * t], dim=-1), x)
+    return _unary("exp", x, 3, 4, eps)
 
 
 def log(x, eps=1e-5):
-    t = _cu(x)
-    ln = torch.sqrt((t[..., 1:] ** 2).sum(-1, keepdim=True))
-    safe = torch.where(ln < eps, torch.ones_like(ln), ln)
-    half = torch.where(ln < eps, torch.ones_like(ln), torch.atan2(ln, t[..., 0:1]) / safe)
-    return _back(half * t[..., 1:], x)
+    return _unary("log", x, 4, 3, eps)
 
 
 def to_scaled_angle_axis(x, eps=1e-5):
@@ -104,70 +127,35 @@ def from_scaled_angle_axis(x, eps=1e-5):
 
 
 def between(x, y):
-    a, b = _cu(x), _cu(y)
-    shape = np.broadcast_shapes(a.shape, b.shape)
-    a, b = a.expand(shape), b.expand(shape)
-    w = torch.sqrt((a * a).sum(-1) * (b * b).sum(-1))[..., None] + (a * b).sum(-1)[..., None]
-    return _back(torch.cat([w, tq.cross(a, b)], dim=-1), x)
+    return _binary("between", x, y, 3, 3, 4)
+
+
+def to_xform(x):
+    x = np.asarray(x)
+    return _unary("to_xform", x, 4, 9).reshape(x.shape[:-1] + (3, 3))
+
+
+def from_xform(ts):
+    ts = np.asarray(ts)
+    if ts.shape[-2:] != (3, 3):
+        raise ValueError("quat.from_xform expects [..., 3, 3] rotation matrices")
+    return _unary("from_xform", ts.reshape(ts.shape[:-2] + (9,)), 9, 4)
 
 
 def to_xform_xy(x):
-    return _back(kin.quat_to_xy(_cu(x)), x)
+    x = np.asarray(x)
+    if _wdt(x) == np.float32:       # batch path of the driver's set-up (:156, :161): dedicated float4 kernel
+        return kin.quat_to_xy(_cu(x, np.float32)).cpu().numpy()
+    return _unary("to_xform_xy", x, 4, 6).reshape(x.shape[:-1] + (3, 2))
 
 
 def from_xform_xy(x):
-    return _back(kin.xy_to_quat(_cu(x)), x)
-
-
-def fk(lrot, lpos, parents):
-    par = kin.parents_tensor(parents, "cuda")
-    gr, gp = kin.fk(_cu(lrot), _cu(lpos), par)
-    return _back(gr, lrot), _back(gp, lpos)
-
-
-def ik(grot, gpos, parents):
-    par = kin.parents_tensor(parents, "cuda")
-    lr, lp = kin.ik(_cu(grot), _cu(gpos), par)
-    return _back(lr, grot), _back(lp, gpos)
-
-
-def fk_vel(lrot, lpos, lvel, lang, parents):
-    par = kin.parents_tensor(parents, "cuda")
-    out = kin.fk_vel(_cu(lrot), _cu(lpos), _cu(lvel), _cu(lang), par)
-    return tuple(_back(t, lrot) for t in out)
-
-
-def fk_vel_bone(bone_positions, bone_velocities, bone_rotations, bone_angular_velocities, bone_parents, bone):
-    gr, gp, gv, ga = fk_vel(np.asarray(bone_rotations)[None], np.asarray(bone_positions)[None],
-                            np.asarray(bone_velocities)[None], np.asarray(bone_angular_velocities)[None], bone_parents)
-    return gp[0, bone], gv[0, bone], gr[0, bone], ga[0, bone]
-
-
-def fk_partial(global_bone_positions, global_bone_rotations, global_bone_computed, local_bone_positions,
-               local_bone_rotations, bone_parents, bone):
-    """Fills (in place, like the reference) the global transforms of `bone` and of every ancestor not
-    yet marked computed."""
-    gr, gp = fk(np.asarray(local_bone_rotations)[None], np.asarray(local_bone_positions)[None], bone_parents)
-    j = int(bone)
-    chain = []
-    while j != -1:
-        chain.append(j)
-        j = int(bone_parents[j])
-    for idx, j in enumerate(chain):
-        if idx == 0 or not global_bone_computed[j]:
-            global_bone_positions[j] = gp[0, j]
-            global_bone_rotations[j] = gr[0, j]
-            global_bone_computed[j] = True
-    return global_bone_positions, global_bone_rotations, global_bone_computed
-
-
-def ik_two_bone(bone_root_lr, bone_mid_lr, bone_root, bone_mid, bone_end, target, fwd, bone_root_gr, bone_mid_gr,
-                bone_par_gr, max_length_buffer):
-    f64 = torch.float64
-    args = [_cu(np.asarray(a, dtype=np.float64)[None], f64) for a in
-            (bone_root, bone_mid, bone_end, target, fwd, bone_root_gr, bone_mid_gr, bone_par_gr)]
-    a, b = kin.ik_two_bone(*args, float(max_length_buffer))
-    return a[0].cpu().numpy(), b[0].cpu().numpy()
+    x = np.asarray(x)
+    if x.shape[-2:] != (3, 2):
+        raise ValueError("quat.from_xform_xy expects [..., 3, 2]")
+    if _wdt(x) == np.float32:       # per-frame path (:461): dedicated kernel
+        return kin.xy_to_quat(_cu(x, np.float32)).cpu().numpy()
+    return _unary("from_xform_xy", x.reshape(x.shape[:-2] + (6,)), 6, 4)
 
 
 def from_euler(e, order="zyx"):
@@ -181,25 +169,91 @@ def from_euler(e, order="zyx"):
 
 
 def unroll(x):
-    t = _cu(x)
-    y = t.clone()
-    for i in range(1, y.shape[0]):
-        flip = (y[i] * y[i - 1]).sum(-1) < 0.0
-        y[i][flip] = -y[i][flip]
-    return _back(y, x)
+    """Keep consecutive frames on one hemisphere (:135-141): frame i is negated when it opposes the
+    already-unrolled frame i-1, i.e. sign_i = sign_{i-1} * sign(<x_i, x_{i-1}>) - a cumulative product."""
+    x = np.asarray(x)
+    t = _cu(x, _wdt(x))
+    d = (t[1:] * t[:-1]).sum(-1)
+    sgn = torch.where(d < 0, -torch.ones_like(d), torch.ones_like(d))
+    s = torch.cat([torch.ones_like(sgn[:1]), torch.cumprod(sgn, dim=0)], dim=0)
+    return (t * s[..., None]).cpu().numpy()
 
 
 def to_euler(x, order="xyz"):
-    t = _cu(x)
-    q0, q1, q2, q3 = t[..., 0:1], t[..., 1:2], t[..., 2:3], t[..., 3:4]
-    if order == "xyz":
-        out = torch.cat([torch.atan2(2 * (q0 * q1 + q2 * q3), 1 - 2 * (q1 * q1 + q2 * q2)),
-                         torch.asin((2 * (q0 * q2 - q3 * q1)).clamp(-1, 1)),
-                         torch.atan2(2 * (q0 * q3 + q1 * q2), 1 - 2 * (q2 * q2 + q3 * q3))], dim=-1)
-    elif order == "yzx":
-        out = torch.cat([torch.atan2(2 * (q1 * q0 - q2 * q3), -q1 * q1 + q2 * q2 - q3 * q3 + q0 * q0),
-                         torch.atan2(2 * (q2 * q0 - q1 * q3), q1 * q1 - q2 * q2 - q3 * q3 + q0 * q0),
-                         torch.asin((2 * (q1 * q2 + q3 * q0)).clamp(-1, 1))], dim=-1)
-    else:
+    if order not in ("xyz", "yzx"):
         raise NotImplementedError("Cannot convert from ordering %s" % order)
-    return _back(out, x)
+    return _unary("to_euler_" + order, x, 4, 3)
+
+
+# ---------------------------------------------------------------------------------------------------
+# kinematics (motion/quat.py:166-343)
+# ---------------------------------------------------------------------------------------------------
+def fk(lrot, lpos, parents):
+    dt = _wdt(lrot, lpos)
+    par = kin.parents_tensor(parents, "cuda")
+    gr, gp = kin.fk(_cu(lrot, dt), _cu(lpos, dt), par)
+    return gr.cpu().numpy(), gp.cpu().numpy()
+
+
+def ik(grot, gpos, parents):
+    dt = _wdt(grot, gpos)
+    par = kin.parents_tensor(parents, "cuda")
+    lr, lp = kin.ik(_cu(grot, dt), _cu(gpos, dt), par)
+    return lr.cpu().numpy(), lp.cpu().numpy()
+
+
+def fk_vel(lrot, lpos, lvel, lang, parents):
+    dt = _wdt(lrot, lpos, lvel, lang)
+    par = kin.parents_tensor(parents, "cuda")
+    out = kin.fk_vel(_cu(lrot, dt), _cu(lpos, dt), _cu(lvel, dt), _cu(lang, dt), par)
+    return tuple(t.cpu().numpy() for t in out)
+
+
+def fk_vel_bone(bone_positions, bone_velocities, bone_rotations, bone_angular_velocities, bone_parents, bone):
+    gr, gp, gv, ga = fk_vel(np.asarray(bone_rotations)[None], np.asarray(bone_positions)[None],
+                            np.asarray(bone_velocities)[None], np.asarray(bone_angular_velocities)[None], bone_parents)
+    return gp[0, bone], gv[0, bone], gr[0, bone], ga[0, bone]
+
+
+def fk_partial(global_bone_positions, global_bone_rotations, global_bone_computed, local_bone_positions,
+               local_bone_rotations, bone_parents, bone):
+    """(:241-272) In place, like the reference: `bone` is always recomputed; the walk towards the root stops at
+    the first ancestor already marked computed and continues from that ancestor's STORED global transform."""
+    chain = [int(bone)]
+    while bone_parents[chain[-1]] != -1 and not global_bone_computed[bone_parents[chain[-1]]]:
+        chain.append(int(bone_parents[chain[-1]]))
+    chain.reverse()                                   # top of the chain first
+    top_parent = int(bone_parents[chain[0]])
+    dt = _wdt(global_bone_positions, global_bone_rotations, local_bone_positions, local_bone_rotations)
+    lpos = _cu(np.asarray(local_bone_positions)[chain][None], dt)
+    lrot = _cu(np.asarray(local_bone_rotations)[chain][None], dt)
+    if top_parent == -1:
+        gpos, grot = kin.fk_chain(lpos, lrot)
+    else:
+        gpos, grot = kin.fk_chain(lpos, lrot, _cu(np.asarray(global_bone_positions)[top_parent][None], dt),
+                                  _cu(np.asarray(global_bone_rotations)[top_parent][None], dt))
+    gpos, grot = gpos.cpu().numpy()[0], grot.cpu().numpy()[0]
+    for c, j in enumerate(chain):
+        global_bone_positions[j] = gpos[c]
+        global_bone_rotations[j] = grot[c]
+        global_bone_computed[j] = True
+    return global_bone_positions, global_bone_rotations, global_bone_computed
+
+
+def ik_look_at(bone_rotation, global_parent_rotation, global_rotation, global_position, child_position,
+               target_position, eps=1e-5):
+    """(:276-290)"""
+    curr_dir = normalize(np.asarray(child_position) - np.asarray(global_position))
+    targ_dir = normalize(np.asarray(target_position) - np.asarray(global_position))
+    if builtins.abs(1.0 - float(np.dot(curr_dir, targ_dir))) > eps:
+        bone_rotation = inv_mul(global_parent_rotation, mul(between(curr_dir, targ_dir), global_rotation))
+    return bone_rotation
+
+
+def ik_two_bone(bone_root_lr, bone_mid_lr, bone_root, bone_mid, bone_end, target, fwd, bone_root_gr, bone_mid_gr,
+                bone_par_gr, max_length_buffer):
+    """(:295-343) float64 kernel; the reference's inputs here are float64 state."""
+    args = [_cu(np.asarray(a, dtype=np.float64)[None], np.float64) for a in
+            (bone_root, bone_mid, bone_end, target, fwd, bone_root_gr, bone_mid_gr, bone_par_gr)]
+    a, b = kin.ik_two_bone(*args, float(max_length_buffer))
+    return a[0].cpu().numpy(), b[0].cpu().numpy()

@@ -56,8 +56,11 @@ class CharacterizationSession:
         self.m0, self.s0 = tab(stats.src_cnt_mean), tab(stats.src_cnt_std)
         self.m1, self.s1 = tab(stats.cha_encoded_mean), tab(stats.cha_encoded_std)
         self.cha_encoded = torch.as_tensor(cha_encoded, dtype=torch.float32).to(dev).contiguous()
-        self.tree = BallTree(torch.as_tensor(cha_cnt_nm, dtype=torch.float32).to(dev), device=dev,
-                             use_tensor_cores=match_tensor_cores)
+        if isinstance(cha_cnt_nm, BallTree):      # a ready tree (e.g. BallTree.from_feature_db)
+            self.tree = cha_cnt_nm
+        else:
+            self.tree = BallTree(torch.as_tensor(cha_cnt_nm, dtype=torch.float32).to(dev), device=dev,
+                                 use_tensor_cores=match_tensor_cores)
         self.with_cm_path = with_cm_path
         B, n, D = batch, self.ntok, self.D
         # static I/O buffers (graph-capturable)
@@ -131,7 +134,7 @@ class CharacterizationSession:
         lib, t = self.lib, self.tree
         wp, wn = self._ws()
         use_tc = t.use_tensor_cores
-        if use_tc is None:
+        if use_tc is None or use_tc == "auto":
             # throughput mode: tensor-core coarse pass + fp64 re-rank (split-K when the DB is small);
             # parity mode (fp32) keeps the brute-force fp64 kernel unless the problem is large
             use_tc = self.B * t.N >= t.TC_THRESHOLD_PAIRS or (

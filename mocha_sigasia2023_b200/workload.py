@@ -50,32 +50,22 @@ def step_inputs(B: int, seed: int) -> dict:
 
 
 def build_session(batch: int, n_db: int = 385, precision: str = "fp32", device="cuda", seed: int = 0,
-                  with_cm_path: bool = False, match_tensor_cores=None, gen_seed: int = 1777, cvae_seed: int = 1778):
+                  with_cm_path: bool = False, match_tensor_cores=None, gen_seed: int = 1777, cvae_seed: int = 1778,
+                  db_precision: str = "fp32", db_batch: int = 64):
     """Session on random-init weights with a character DB of n_db encoded synthetic windows
-    (n_db = 385 is what a 400-frame character clip yields)."""
+    (n_db = 385 is what a 400-frame character clip yields). The DB comes from the
+    feature-DB builder (feature_db.build_feature_db: same CUDA encoder, matcher layout)."""
+    from . import feature_db
+    from .balltree import BallTree
     gen_sd = weights.generator_state_dict(gen_seed)
     cvae_sd = weights.cvae_state_dict(cvae_seed)
     stats = driver_stats()
-    # bootstrap session (1-row dummy DB) only to run the CUDA encoder over the character windows
-    dummy_enc = torch.zeros((1, 90, 256))
-    dummy_db = torch.zeros((1, 90 * 256))
-    boot = CharacterizationSession(gen_sd, cvae_sd, weights.DEFAULT_MODEL_CFG, stats, dummy_enc, dummy_db,
-                                   batch=min(n_db, 64), device=device, precision="fp32")
-    encs, nms = [], []
     cha_X = pose_windows(n_db, seed + 5000)
-    bs = boot.B
-    for s in range(0, n_db, bs):
-        chunk = np.zeros((bs, 60, 24, 15), dtype=np.float32)
-        m = min(bs, n_db - s)
-        chunk[:m] = cha_X[s:s + m]
-        boot.X.copy_(torch.from_numpy(chunk))
-        boot.encode(boot.X, boot.tokens, boot.encoded, boot.cnt, boot.cnt_nm)
-        encs.append(boot.encoded[:m].clone())
-        nms.append(boot.cnt_nm[:m].clone())
-    cha_encoded = torch.cat(encs)
-    cha_cnt_nm = torch.cat(nms)
-    del boot
-    sess = CharacterizationSession(gen_sd, cvae_sd, weights.DEFAULT_MODEL_CFG, stats, cha_encoded, cha_cnt_nm,
+    fdb = feature_db.build_feature_db(gen_sd, weights.DEFAULT_MODEL_CFG, stats.cnt_mean, stats.cnt_std, cha_X,
+                                      batch=db_batch, precision=db_precision, device=device)
+    sess = CharacterizationSession(gen_sd, cvae_sd, weights.DEFAULT_MODEL_CFG, stats, fdb.encoded,
+                                   BallTree.from_feature_db(fdb, device=device, use_tensor_cores=match_tensor_cores),
                                    batch=batch, device=device, precision=precision, with_cm_path=with_cm_path,
                                    match_tensor_cores=match_tensor_cores)
+    sess.feature_db = fdb
     return sess, gen_sd, cvae_sd, stats

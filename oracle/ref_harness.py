@@ -1,5 +1,14 @@
-"""Run the UNMODIFIED reference driver (test_fullframework.main) on CPU under a stub harness and
-record its outputs as the end-to-end golden (tests/golden/e2e.npz). Build container only.
+"""Run the UNMODIFIED reference driver (test_fullframework.main) under a stub harness.
+
+Three uses:
+  * `python oracle/ref_harness.py` (build container): record the end-to-end golden tests/golden/e2e.npz from
+    the reference on CPU;
+  * `--patched --out x.npz`: Level-1 drop-in proof - the same unmodified `main()` with BallTree, quat,
+    Inertialization, Trainer, CVAE and mean_variance_norm of its namespace replaced by this package
+    (tests/test_gpu_level1.py compares the result with e2e.npz; the reparameterisation noise is replayed);
+  * `--time --out x.json`: time the reference's own per-frame loop on the host cores (bench.py reference arm).
+The tree is /root/reference in the build container, else the staged copy oracle/_ref/reference
+(oracle/stage_reference.py).
 
 Nothing in the reference is edited. What the harness supplies:
   * a scratch working directory with symlinks to the reference tree, holding the files main() opens:
@@ -22,8 +31,11 @@ import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF = os.environ.get("MOCHA_REFERENCE", "/root/reference")
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import stage_reference  # noqa: E402
+
+REF = stage_reference.reference_root()
 
 SRC_FRAMES, CHA_FRAMES = 240, 400
 SRC_SEED, CHA_SEED = 0, 1
@@ -54,8 +66,14 @@ def _scratch():
     return d
 
 
-def run_reference_main():
+def run_reference_main(patched: bool = False, eps_replay=None, timing: dict | None = None, threads: int = 8):
+    """patched: replace the hot-path symbols of the driver's namespace by this package (GPU).
+    eps_replay [frames, 256]: noise handed to the patched CVAE instead of fresh draws.
+    timing: dict that receives perf_counter stamps of every BallTree.query call (loop timing)."""
+    import time
     from mocha_sigasia2023_b200 import synthetic
+    if REF is None:
+        raise RuntimeError("reference tree unavailable: neither /root/reference nor oracle/_ref/reference exists")
     d = _scratch()
     os.chdir(d)
     for p in ("", "etc", "motion", "preprocess", "net"):
@@ -70,7 +88,7 @@ def run_reference_main():
 
     def spy_randn_like(t, *a, **k):
         out = real_randn_like(t, *a, **k)
-        rec["eps"].append(out.detach().clone().numpy())
+        rec["eps"].append(out.detach().cpu().clone().numpy())
         return out
 
     torch.randn_like = spy_randn_like
@@ -93,6 +111,35 @@ def run_reference_main():
     bvh.load, bvh.save = fake_load, fake_save
     tf.bvh.load, tf.bvh.save = fake_load, fake_save
 
+    if patched:
+        import mocha_sigasia2023_b200 as pkg
+        from mocha_sigasia2023_b200 import Inertialization as our_inert, quat as our_quat
+        from mocha_sigasia2023_b200.balltree import BallTree as OurTree
+        from mocha_sigasia2023_b200.model_CVAE import CVAE as OurCVAE
+        from mocha_sigasia2023_b200.trainer import Trainer as OurTrainer
+        from mocha_sigasia2023_b200.transformer import mean_variance_norm as our_mvn
+        replay = {"i": 0}
+
+        tf.BallTree, tf.quat, tf.inert = OurTree, our_quat, our_inert
+        tf.Trainer, tf.CVAE, tf.mean_variance_norm = OurTrainer, OurCVAE, our_mvn
+        rec["patched_package"] = pkg.__name__
+        _orig_cvae_init = OurCVAE.__init__
+
+        def _init_with_replay(self, *a, **k):
+            _orig_cvae_init(self, *a, **k)
+            if eps_replay is not None:
+                def eps_fn(shape):
+                    e = torch.as_tensor(eps_replay[replay["i"]], dtype=torch.float32).reshape(shape)
+                    replay["i"] += 1
+                    rec["eps"].append(e.numpy().copy())
+                    return e
+                self.eps_fn = eps_fn
+
+        OurCVAE.__init__ = _init_with_replay
+        # the reference picks its device from torch.cuda.is_available(): make sure the patched run is on the GPU
+        assert torch.cuda.is_available(), "the patched (Level-1) run needs a GPU: the package has no CPU fallback"
+        tf.device = torch.device("cuda")
+
     RealTree = tf.BallTree
 
     class SpyTree:
@@ -101,6 +148,8 @@ def run_reference_main():
             rec["db_shape"] = np.array(X.shape)
 
         def query(self, q, *a, **k):
+            if timing is not None:
+                timing.setdefault("query_t", []).append(time.perf_counter())
             r = self._t.query(q, *a, **k)
             rec["match"].append(np.array(r).reshape(-1)[0])
             return r
@@ -112,8 +161,8 @@ def run_reference_main():
     def spy_sample(self, c, deterministic=False):
         out = real_sample(self, c, deterministic)
         if len(rec["cvae_out"]) < 6:
-            rec["cvae_cond"].append(c.detach().clone().numpy())
-            rec["cvae_out"].append(out.detach().clone().numpy())
+            rec["cvae_cond"].append(c.detach().cpu().clone().numpy())
+            rec["cvae_out"].append(out.detach().cpu().clone().numpy())
         return out
 
     tf.CVAE.sample = spy_sample
@@ -126,20 +175,28 @@ def run_reference_main():
 
         def spy_to_mot(x):
             y = real_to_mot(x)
-            rec["Ytil"].append(y.detach().clone().numpy()[0, -1])     # last frame row only (24,15)
+            rec["Ytil"].append(y.detach().cpu().clone().numpy()[0, -1])     # last frame row only (24,15)
             return y
 
         self.gen_ema.to_mot.forward = spy_to_mot
 
     tf.Trainer.__init__ = spy_trainer_init
-    torch.set_num_threads(8)
+    torch.set_num_threads(threads)
+    if timing is not None:
+        timing["t_main0"] = time.perf_counter()
     tf.main()
+    if timing is not None:
+        timing["t_main1"] = time.perf_counter()
+        timing["threads"] = torch.get_num_threads()
     torch.randn_like = real_randn_like
+    tf.Trainer.__init__ = real_trainer_init
+    if patched:
+        OurCVAE.__init__ = _orig_cvae_init
     return rec
 
 
-def generate(out_path):
-    rec = run_reference_main()
+def generate(out_path, **kw):
+    rec = run_reference_main(**kw)
     saves = {s["path"].split("_")[0]: s for s in rec["saves"]}
     out = {
         "src_rotations": saves["Src"]["rotations"], "src_positions": saves["Src"]["positions"],
@@ -154,5 +211,34 @@ def generate(out_path):
     print("e2e.npz", {k: v.shape for k, v in out.items()})
 
 
+def time_reference_loop(threads: int) -> dict:
+    """frames/s of the reference's own per-frame loop (test_fullframework.py:438-641) on the host cores: the
+    loop starts every frame with `tree_cnt.query(...)` (:443), so the interval between the first and the last
+    in-loop query call covers frames 1..223 exactly, set-up and BVH export excluded. Nothing is modified."""
+    timing = {}
+    run_reference_main(timing=timing, threads=threads)
+    q = timing["query_t"]            # q[0]: frame-0 initialisation (:296); q[1:]: one per loop iteration
+    frames = len(q) - 2
+    loop_s = q[-1] - q[1]
+    return {"frames": frames, "loop_s": loop_s, "frames_per_s": frames / loop_s, "ms_per_frame": 1e3 * loop_s / frames,
+            "main_s": timing["t_main1"] - timing["t_main0"], "threads": timing["threads"]}
+
+
 if __name__ == "__main__":
-    generate(os.path.join(ROOT, "tests", "golden", "e2e.npz"))
+    import argparse
+    import json
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--patched", action="store_true")
+    ap.add_argument("--time", action="store_true")
+    ap.add_argument("--threads", type=int, default=8)
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+    if a.time:
+        res = time_reference_loop(a.threads)
+        with open(a.out, "w") as f:
+            json.dump(res, f)
+    elif a.patched:
+        g = np.load(os.path.join(ROOT, "tests", "golden", "e2e.npz"))
+        generate(a.out, patched=True, eps_replay=g["eps"])
+    else:
+        generate(a.out or os.path.join(ROOT, "tests", "golden", "e2e.npz"))
