@@ -180,10 +180,11 @@ int mocha_encoder_fwd(const mocha_generator_weights* w, const float* d_tokens, i
 /* ---- (a4) mean_variance_norm  net/transformer.py:13-20 (+ matcher scaling :293,:442) ---------- */
 /* x [B,n,C] normalised over n per (b,c). d_cnt and/or d_cnt_nm may be NULL.
  * d_cnt_nm = (cnt - cnt_mean)/cnt_std with tables [n,C]; d_cnt_nm16 (optional, bf16 [B,n*C]) is the
- * same query rounded to bf16, the operand of the tensor-core matcher (mocha_match_tc's d_Q16). */
+ * same query minus d_cnt_nm16_center ([n*C], optional) rounded to bf16: the operand of the tensor-core
+ * matcher (mocha_match_tc's d_Q16) relative to the origin the bf16 DB rows were packed around. */
 int mocha_cnt_features(const float* d_x, int B, int n, int C, float eps, float* d_cnt,
                        const float* d_cnt_mean, const float* d_cnt_std, float* d_cnt_nm, void* d_cnt_nm16,
-                       mocha_stream_t stream);
+                       const float* d_cnt_nm16_center, mocha_stream_t stream);
 
 /* ---- (a8) Generator.decoder = Transformer(adain=True)  transformer.py:79-113 ---------------- */
 size_t mocha_decoder_workspace_bytes(const mocha_dims* dims, int B);
@@ -229,7 +230,12 @@ int mocha_match_exact(const float* d_Q, int nq, const float* d_DB, long long N, 
  * fp32 accumulate in TMEM) with a fused per-row running top-kc epilogue, cross-tile merge, then an
  * exact fp64 re-rank of the kc candidates in difference form against the stored rows.
  * d_Q16/d_DB16: bf16 copies [nq,D]/[N,D] (D % 64 == 0); d_dbnorm [N] = ||x||^2 of the bf16 rows;
- * exact re-rank reads d_Q (fp32) and, if d_DB32 != NULL, the fp32 rows, else the bf16 rows. */
+ * exact re-rank reads d_Q (fp32) and, if d_DB32 != NULL, the fp32 rows, else the bf16 rows.
+ * The bf16 operands only rank candidates, so they may be expressed relative to ANY common origin c
+ * (d_Q16 = bf16(q - c), d_DB16 = bf16(x - c), d_dbnorm of those rows): distances do not depend on c, and
+ * centring a DB whose rows share a large common component (feature DBs do: ||x|| >> ||x - x'||) removes
+ * most of the bf16 rounding error from the ranking (BallTree / feature_db use the DB mean). With
+ * d_DB32 == NULL the re-rank reads d_DB16 against d_Q, which must then share that origin. */
 size_t mocha_match_tc_workspace_bytes(int nq, long long N, int D, int kc);
 int mocha_match_tc(const float* d_Q, const void* d_Q16, int nq, const void* d_DB16, const float* d_DB32,
                    const float* d_dbnorm, long long N, int D, int k, int kc, long long index_offset,

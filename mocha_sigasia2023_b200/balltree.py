@@ -38,6 +38,7 @@ class BallTree:
             raise _lib.MochaError("tc_storage must be 'bf16' or 'fp32'")
         self.tc_storage = tc_storage   # operand format of the tensor-core coarse pass (fp32 -> TF32 MMA)
         self._norm32 = None
+        self.center = None       # origin of the bf16 operands (set by _ensure_bf16 / from_feature_db)
         self._db16 = None
         self._norm = None
         self._ws = None
@@ -50,7 +51,7 @@ class BallTree:
             raise _lib.MochaError("BallTree.from_feature_db needs the fp32 rows (keep_fp32=True)")
         t = cls(fdb.rows32, **kwargs)
         if fdb.rows16 is not None and fdb.norms is not None:
-            t._db16, t._norm = fdb.rows16, fdb.norms
+            t._db16, t._norm, t.center = fdb.rows16, fdb.norms, fdb.center
         return t
 
     def _scratch(self, nbytes):
@@ -59,12 +60,22 @@ class BallTree:
         return self._ws
 
     def _ensure_bf16(self):
+        """bf16 rows + norms for the tensor-core coarse pass, packed around the DB mean (`self.center`): feature
+        rows share a large common component (||x|| ~ 370 vs ||x - x'|| ~ 2 on the synthetic character DB), and
+        rounding x - mean instead of x keeps the bf16 error on the part that decides the ranking."""
         if self._db16 is None:
             lib = _lib.load()
-            self._db16 = torch.empty((self.N, self.D), dtype=torch.bfloat16, device=self.data.device)
-            self._norm = torch.empty((self.N,), dtype=torch.float32, device=self.data.device)
-            _lib.check(lib.mocha_db_pack_bf16(_lib.ptr(self.data), self.N, self.D, _lib.ptr(self._db16),
-                                              _lib.ptr(self._norm), _lib.stream_ptr()), "mocha_db_pack_bf16")
+            dev = self.data.device
+            self.center = self.data.mean(dim=0, dtype=torch.float32).contiguous() if self.N > 1 else None
+            self._db16 = torch.empty((self.N, self.D), dtype=torch.bfloat16, device=dev)
+            self._norm = torch.empty((self.N,), dtype=torch.float32, device=dev)
+            step = max(1, (256 << 20) // (4 * self.D))        # centred fp32 scratch of <= 256 MB at a time
+            for s in range(0, self.N, step):
+                rows = self.data[s:s + step]
+                if self.center is not None:
+                    rows = (rows - self.center).contiguous()
+                _lib.check(lib.mocha_db_pack_bf16(_lib.ptr(rows), rows.shape[0], self.D, _lib.ptr(self._db16[s:s + step]),
+                                                  _lib.ptr(self._norm[s:s + step]), _lib.stream_ptr()), "mocha_db_pack_bf16")
 
     def query_device(self, q: torch.Tensor, k: int = 1, return_distance: bool = True):
         """Same as query() but takes/returns CUDA tensors (no host round trip)."""
@@ -97,7 +108,7 @@ class BallTree:
                                           ws.numel(), _lib.stream_ptr()), "mocha_match_tc(tf32)")
         elif use_tc:
             self._ensure_bf16()
-            q16 = q.to(torch.bfloat16)
+            q16 = (q if self.center is None else q - self.center).to(torch.bfloat16)
             ws = self._scratch(lib.mocha_match_tc_workspace_bytes(nq, self.N, self.D, self.kc))
             _lib.check(lib.mocha_match_tc(_lib.ptr(q), _lib.ptr(q16), nq, _lib.ptr(self._db16), _lib.ptr(self.data),
                                           _lib.ptr(self._norm), self.N, self.D, k, self.kc, 0, _lib.ptr(idx),

@@ -202,9 +202,9 @@ extern "C" int mocha_encoder_fwd(const mocha_generator_weights* w, const float* 
 
 extern "C" int mocha_cnt_features(const float* x, int B, int n, int C, float eps, float* cnt,
                                   const float* cnt_mean, const float* cnt_std, float* cnt_nm, void* cnt_nm16,
-                                  mocha_stream_t stream) {
+                                  const float* cnt_nm16_center, mocha_stream_t stream) {
   return instance_norm_tokens(x, B, n, C, eps, nullptr, cnt, cnt_mean, cnt_std, cnt_nm, (cudaStream_t)stream, nullptr,
-                              static_cast<__nv_bfloat16*>(cnt_nm16));
+                              static_cast<__nv_bfloat16*>(cnt_nm16), cnt_nm16_center);
 }
 
 // ------------------------------------------------------------------------------------------------

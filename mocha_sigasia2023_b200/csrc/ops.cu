@@ -291,7 +291,8 @@ instance_norm_tokens_kernel(const float* __restrict__ x, int n, int C, float eps
                             const float* __restrict__ gb, float* __restrict__ y,
                             const float* __restrict__ tab_mean,
                             const float* __restrict__ tab_std, float* __restrict__ y2,
-                            __nv_bfloat16* __restrict__ y16, __nv_bfloat16* __restrict__ y2h) {
+                            __nv_bfloat16* __restrict__ y16, __nv_bfloat16* __restrict__ y2h,
+                            const float* __restrict__ y2h_center) {
   __shared__ float part[8][32];
   __shared__ float stat[2][32];
   const int b = blockIdx.x, c = blockIdx.y * 32 + (threadIdx.x & 31), warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -340,7 +341,7 @@ instance_norm_tokens_kernel(const float* __restrict__ x, int n, int C, float eps
     if (y2 || y2h) {
       const float w = (v - tab_mean[o]) / tab_std[o];
       if (y2) y2[(long long)b * n * C + o] = w;
-      if (y2h) y2h[(long long)b * n * C + o] = __float2bfloat16_rn(w);
+      if (y2h) y2h[(long long)b * n * C + o] = __float2bfloat16_rn(y2h_center ? w - y2h_center[o] : w);
     }
   }
 }
@@ -351,7 +352,8 @@ instance_norm_tokens_reg_kernel(const float* __restrict__ x, int n, int C, float
                                 const float* __restrict__ gb, float* __restrict__ y,
                                 const float* __restrict__ tab_mean,
                                 const float* __restrict__ tab_std, float* __restrict__ y2,
-                                __nv_bfloat16* __restrict__ y16, __nv_bfloat16* __restrict__ y2h) {
+                                __nv_bfloat16* __restrict__ y16, __nv_bfloat16* __restrict__ y2h,
+                            const float* __restrict__ y2h_center) {
   __shared__ float part[8][32];
   __shared__ float stat[2][32];
   const int b = blockIdx.x, c = blockIdx.y * 32 + (threadIdx.x & 31), warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -409,7 +411,7 @@ instance_norm_tokens_reg_kernel(const float* __restrict__ x, int n, int C, float
       if (y2 || y2h) {
         const float w = (u - tab_mean[o]) / tab_std[o];
         if (y2) y2[(long long)b * n * C + o] = w;
-        if (y2h) y2h[(long long)b * n * C + o] = __float2bfloat16_rn(w);
+        if (y2h) y2h[(long long)b * n * C + o] = __float2bfloat16_rn(y2h_center ? w - y2h_center[o] : w);
       }
     }
   }
@@ -986,7 +988,7 @@ int pool_graph_agg(const __nv_bfloat16* in, const float* Wp, const float* A, __n
 
 int instance_norm_tokens(const float* x, int B, int n, int C, float eps, const float* gb, float* y,
                          const float* tab_mean, const float* tab_std, float* y2, cudaStream_t s,
-                         __nv_bfloat16* y16, __nv_bfloat16* y2h) {
+                         __nv_bfloat16* y16, __nv_bfloat16* y2h, const float* y2h_center) {
   MOCHA_CHECK_ARG(x && B > 0 && n > 1 && C > 0, "instance_norm_tokens: bad args");
   MOCHA_CHECK_ARG(y || y2 || y16 || y2h, "instance_norm_tokens: no output");
   MOCHA_CHECK_ARG(!(y2 || y2h) || (tab_mean && tab_std), "instance_norm_tokens: y2 needs its table");
@@ -995,9 +997,9 @@ int instance_norm_tokens(const float* x, int B, int n, int C, float eps, const f
   if (n <= 128 && y16 && !y2 && !y2h && (C % 64) == 0 && al)   // tensor-core path (bf16 twin requested): float4 kernel
     instance_norm_tokens_v4_kernel<<<dim3(B, C / 64), 256, 0, s>>>(x, n, C, eps, gb, y, y16, nullptr);
   else if (n <= 128)
-    instance_norm_tokens_reg_kernel<<<dim3(B, (C + 31) / 32), 256, 0, s>>>(x, n, C, eps, gb, y, tab_mean, tab_std, y2, y16, y2h);
+    instance_norm_tokens_reg_kernel<<<dim3(B, (C + 31) / 32), 256, 0, s>>>(x, n, C, eps, gb, y, tab_mean, tab_std, y2, y16, y2h, y2h_center);
   else
-    instance_norm_tokens_kernel<<<dim3(B, (C + 31) / 32), 256, 0, s>>>(x, n, C, eps, gb, y, tab_mean, tab_std, y2, y16, y2h);
+    instance_norm_tokens_kernel<<<dim3(B, (C + 31) / 32), 256, 0, s>>>(x, n, C, eps, gb, y, tab_mean, tab_std, y2, y16, y2h, y2h_center);
   count_launch();
   MOCHA_LAUNCH_CHECK("instance_norm_tokens");
   return MOCHA_OK;

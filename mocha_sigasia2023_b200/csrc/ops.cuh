@@ -49,7 +49,8 @@ int pool_graph_agg(const __nv_bfloat16* in, const float* Wp, const float* A, __n
 // and optional second output y2 = (y - tab_mean[n,c]) / tab_std[n,c] (test_fullframework.py:293,442).
 int instance_norm_tokens(const float* x, int B, int n, int C, float eps, const float* gb, float* y,
                          const float* tab_mean, const float* tab_std, float* y2, cudaStream_t s,
-                         __nv_bfloat16* y16 = nullptr, __nv_bfloat16* y2h = nullptr);
+                         __nv_bfloat16* y16 = nullptr, __nv_bfloat16* y2h = nullptr,
+                         const float* y2h_center = nullptr);
 
 // Tensor-core path: y = AdaIN(x) (fp32) and q16 = IN(y) (bf16) from ONE pass over x (n <= 128, C % 64 == 0):
 // IN(g u + be) = u * g / (|g| std_u + eps) with u = IN(x), std_u = std / (std + eps)

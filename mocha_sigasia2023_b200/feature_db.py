@@ -10,7 +10,10 @@ GPU with the same CUDA stages the per-frame path uses, written straight into
   * `cnt`      [n, 90, 256]  fp32   (optional; the raw context feature, for `cnt_norm.npz` statistics)
   * `rows32`   [n, 23040]    fp32   `(cnt - cnt_mean) / cnt_std` flattened: the exact matcher / re-rank operand
   * `rows16`   [n, 23040]    bf16 + `norms` [n] = ||row16||^2: the tensor-core matcher's operand (row-major,
-                                    K contiguous - what the TMA descriptors of mocha_match_tc expect)
+                                    K contiguous - what the TMA descriptors of mocha_match_tc expect), packed
+                                    around `center` = the mean row when the fp32 rows are kept (see
+                                    include/mocha_b200.h, mocha_match_tc: any common origin ranks identically in
+                                    exact arithmetic, the mean minimises the bf16 rounding error of the ranking)
 
 Rows are split over ranks with `sharded.shard_bounds` (contiguous, balanced), so `build_feature_db(...,
 shard=(rank, world))` on every rank yields exactly the DB-sharded matcher's layout (config 5)."""
@@ -36,6 +39,7 @@ class FeatureDB:
     rows32: torch.Tensor | None
     rows16: torch.Tensor | None
     norms: torch.Tensor | None
+    center: torch.Tensor | None = None   # origin the bf16 rows are expressed around (None: the true origin)
 
     @property
     def n_local(self) -> int:
@@ -98,7 +102,7 @@ class FeatureEncoder:
         _lib.check(lib.mocha_cnt_features(_lib.ptr(enc), self.B, self.n, self.D, 1e-5,
                                           None if c_buf is None else _lib.ptr(c_buf), _lib.ptr(self.cnt_mean),
                                           _lib.ptr(self.cnt_std), None if r32_buf is None else _lib.ptr(r32_buf),
-                                          None if r16_buf is None else _lib.ptr(r16_buf), s), "cnt_features")
+                                          None if r16_buf is None else _lib.ptr(r16_buf), None, s), "cnt_features")
         if not full:
             encoded.copy_(enc[:m])
             for buf, dst in ((c_buf, c_dst), (r32_buf, r32_dst), (r16_buf, r16_dst)):
@@ -124,17 +128,23 @@ def build_feature_db(gen_sd, cfg, cnt_mean, cnt_std, windows, batch: int = 256, 
     cnt = torch.empty((n, nt, D), **f32) if keep_cnt else None
     rows32 = torch.empty((n, nt * D), **f32) if keep_fp32 else None
     rows16 = torch.empty((n, nt * D), dtype=torch.bfloat16, device=dev) if keep_bf16 else None
+    center_rows = keep_fp32 and keep_bf16 and n > 1
     for s in range(0, n, encd.B):
         m = min(encd.B, n - s)
         X = windows[lo + s:lo + s + m]
         X = torch.as_tensor(np.ascontiguousarray(X) if isinstance(X, np.ndarray) else X, dtype=torch.float32).to(dev)
         encd.encode_into(X, encoded[s:s + m], None if cnt is None else cnt[s:s + m],
-                         None if rows32 is None else rows32[s:s + m], None if rows16 is None else rows16[s:s + m])
-    norms = None
+                         None if rows32 is None else rows32[s:s + m],
+                         None if (rows16 is None or center_rows) else rows16[s:s + m])
+    norms = center = None
     if rows16 is not None and n > 0:
-        # ||row16||^2 of the ROUNDED rows, accumulated in fp32 like mocha_db_pack_bf16 does
         norms = torch.empty((n,), **f32)
+        if center_rows:
+            center = rows32.mean(dim=0, dtype=torch.float32).contiguous()
         for s in range(0, n, 8192):
+            if center_rows:
+                rows16[s:s + 8192] = (rows32[s:s + 8192] - center).to(torch.bfloat16)
+            # ||row16||^2 of the ROUNDED rows, accumulated in fp32 like mocha_db_pack_bf16 does
             r = rows16[s:s + 8192].float()
             norms[s:s + 8192] = (r * r).sum(dim=1)
-    return FeatureDB(lo, hi, N, encoded if keep_encoded else None, cnt, rows32, rows16, norms)
+    return FeatureDB(lo, hi, N, encoded if keep_encoded else None, cnt, rows32, rows16, norms, center)

@@ -61,6 +61,18 @@ class CharacterizationSession:
         else:
             self.tree = BallTree(torch.as_tensor(cha_cnt_nm, dtype=torch.float32).to(dev), device=dev,
                                  use_tensor_cores=match_tensor_cores)
+        # matcher choice is fixed here: the tensor-core path needs the bf16 DB packed (which fixes the origin,
+        # tree.center, of the bf16 query the encode stage emits) before the first frame runs
+        t = self.tree
+        use_tc = t.use_tensor_cores
+        if use_tc is None or use_tc == "auto":
+            # throughput mode: tensor-core coarse pass + fp64 re-rank (split-K when the DB is small);
+            # parity mode (fp32) keeps the brute-force fp64 kernel unless the problem is large
+            use_tc = batch * t.N >= t.TC_THRESHOLD_PAIRS or (
+                self.prec == _lib.MOCHA_BF16 and batch >= 16 and t.D % 8 == 0 and t.D >= 1024)
+        self._use_tc = bool(use_tc)
+        if self._use_tc:
+            t._ensure_bf16()
         self.with_cm_path = with_cm_path
         B, n, D = batch, self.ntok, self.D
         # static I/O buffers (graph-capturable)
@@ -120,7 +132,9 @@ class CharacterizationSession:
         _lib.check(lib.mocha_encoder_fwd(g, _lib.ptr(tokens), B, _lib.ptr(encoded), self.prec, wp, wn, self._s()), "encoder")
         _lib.check(lib.mocha_cnt_features(_lib.ptr(encoded), B, self.ntok, self.D, 1e-5, _lib.ptr(cnt),
                                           _lib.ptr(self.cnt_mean), _lib.ptr(self.cnt_std), _lib.ptr(cnt_nm),
-                                          None if cnt_nm16 is None else _lib.ptr(cnt_nm16), self._s()), "cnt_features")
+                                          None if cnt_nm16 is None else _lib.ptr(cnt_nm16),
+                                          None if (cnt_nm16 is None or self.tree.center is None) else _lib.ptr(self.tree.center),
+                                          self._s()), "cnt_features")
 
     def _decode(self, src_encoded, cha, decoded, Y):
         lib, g = self.lib, C.byref(self.gen.struct)
@@ -133,12 +147,7 @@ class CharacterizationSession:
     def _match(self):
         lib, t = self.lib, self.tree
         wp, wn = self._ws()
-        use_tc = t.use_tensor_cores
-        if use_tc is None or use_tc == "auto":
-            # throughput mode: tensor-core coarse pass + fp64 re-rank (split-K when the DB is small);
-            # parity mode (fp32) keeps the brute-force fp64 kernel unless the problem is large
-            use_tc = self.B * t.N >= t.TC_THRESHOLD_PAIRS or (
-                self.prec == _lib.MOCHA_BF16 and self.B >= 16 and t.D % 8 == 0 and t.D >= 1024)
+        use_tc = self._use_tc
         if use_tc:
             t._ensure_bf16()
             _lib.check(lib.mocha_match_tc(_lib.ptr(self.cnt_nm), _lib.ptr(self.cnt_nm16), self.B, _lib.ptr(t._db16),

@@ -29,6 +29,6 @@ def mean_variance_norm(input, eps=1e-5):
         tok = tok.contiguous()
     out = torch.empty_like(tok)
     lib = _lib.load()
-    _lib.check(lib.mocha_cnt_features(_lib.ptr(tok), B, n, Cc, float(eps), _lib.ptr(out), None, None, None, None,
+    _lib.check(lib.mocha_cnt_features(_lib.ptr(tok), B, n, Cc, float(eps), _lib.ptr(out), None, None, None, None, None,
                                       _lib.stream_ptr()), "mocha_cnt_features")
     return out.permute(0, 2, 1).reshape(size)

@@ -33,8 +33,9 @@ def test_fp32_db_vs_oracle(setup):
     for got, want in ((fdb.encoded, enc), (fdb.cnt, cnt), (fdb.rows32, rows)):
         got = got.cpu().numpy()
         assert np.abs(got - want).max() / np.abs(want).max() < 1e-4
-    # the bf16 rows are the fp32 rows rounded to nearest-even, the norms those of the ROUNDED rows
-    r16 = fdb.rows32.to(torch.bfloat16)
+    # the bf16 rows are the fp32 rows minus the mean row, rounded to nearest-even; the norms those of the ROUNDED rows
+    assert torch.allclose(fdb.center, fdb.rows32.mean(0), rtol=1e-5, atol=1e-5)
+    r16 = (fdb.rows32 - fdb.center).to(torch.bfloat16)
     assert torch.equal(fdb.rows16, r16)
     np.testing.assert_allclose(fdb.norms.cpu().numpy(), (r16.double() ** 2).sum(1).cpu().numpy(), rtol=1e-5)
     mean, std = fdb.cnt_statistics()
