@@ -172,6 +172,12 @@ int mocha_embed_fwd(const mocha_generator_weights* w, const float* d_X, int B, f
 int mocha_bench_tconv(const mocha_generator_weights* w, const float* d_x, int B, float* d_out, int precision,
                       int gemm_repeats, void* workspace, size_t workspace_bytes, mocha_stream_t stream);
 
+/* bench.py `hbm_kernels`: `repeats` stand-alone launches of a bandwidth-bound kernel of the batched path at the
+ * step's shapes; *algo_bytes = algorithmic bytes of ONE launch. which: 0 embed_graph_agg, 1 pool_graph_agg,
+ * 2 add_layernorm (CVAE prior rows), 3 graph_agg_kv_pad16, 4 adain_norm_tokens, 5 instance_norm_tokens (bf16 out). */
+int mocha_bench_hbm_kernel(const mocha_generator_weights* w, int which, int B, int repeats, void* workspace,
+                           size_t workspace_bytes, double* algo_bytes, mocha_stream_t stream);
+
 /* ---- (a3) Generator.encoder = Transformer(adain=False)  net/transformer.py:79-95 ------------ */
 size_t mocha_encoder_workspace_bytes(const mocha_dims* dims, int B);
 int mocha_encoder_fwd(const mocha_generator_weights* w, const float* d_tokens, int B, float* d_encoded,

@@ -119,6 +119,7 @@ SIGNATURES = {
     "mocha_embed_workspace_bytes": (_S, [C.POINTER(Dims), _I]),
     "mocha_embed_fwd": (_I, [C.POINTER(GeneratorWeights), _P, _I, _P, _I, _I, _P, _S, _P]),
     "mocha_bench_tconv": (_I, [C.POINTER(GeneratorWeights), _P, _I, _P, _I, _I, _P, _S, _P]),
+    "mocha_bench_hbm_kernel": (_I, [C.POINTER(GeneratorWeights), _I, _I, _I, _P, _S, C.POINTER(C.c_double), _P]),
     "mocha_encoder_workspace_bytes": (_S, [C.POINTER(Dims), _I]),
     "mocha_encoder_fwd": (_I, [C.POINTER(GeneratorWeights), _P, _I, _P, _I, _P, _S, _P]),
     "mocha_cnt_features": (_I, [_P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P]),

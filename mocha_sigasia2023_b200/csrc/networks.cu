@@ -530,3 +530,88 @@ extern "C" int mocha_bench_tconv(const mocha_generator_weights* w, const float* 
     rc = tconv(c, x, w->jb_tcn_w, w->jb_tcn_b, 0, out, B, d.T, d.V, d.D, d.D, d.taps_j, 1);
   return rc;
 }
+
+// Stand-alone launches of the bandwidth-bound kernels of the batched path at the step's shapes (bench.py
+// `hbm_kernels`): `repeats` back-to-back launches on the caller's stream; *algo_bytes receives the ALGORITHMIC bytes
+// of one launch (every input element read once + every output element written once).
+// which: 0 embed_graph_agg (1x1 embed conv + LeakyReLU + joint-graph aggregation), 1 pool_graph_agg,
+// 2 add_layernorm (CVAE prior rows, fp32 + bf16 outputs), 3 graph_agg_kv_pad16 (to_mot), 4 adain_norm_tokens,
+// 5 instance_norm_tokens -> bf16 (decoder style tokens)
+extern "C" int mocha_bench_hbm_kernel(const mocha_generator_weights* w, int which, int B, int repeats, void* workspace,
+                                      size_t workspace_bytes, double* algo_bytes, mocha_stream_t stream) {
+  MOCHA_CHECK_ARG(w && B > 0 && repeats >= 1 && algo_bytes, "mocha_bench_hbm_kernel: bad argument");
+  MOCHA_TRY(check_dims(w->dims));
+  const mocha_dims& d = w->dims;
+  Workspace ws(workspace, workspace_bytes);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int R = B * d.T * d.V, Tp = d.T / d.tp, R2 = B * Tp * d.P, n = Tp * d.P;
+  typedef __nv_bfloat16 bf16;
+  int rc = MOCHA_OK;
+  switch (which) {
+    case 0: {
+      const int KC = d.Kj * d.C0;
+      const int Ka = (w->jb_gcn_w_aug && w->jb_gcn_kaug >= KC + d.Kj) ? w->jb_gcn_kaug : KC;
+      float* X = ws.take<float>((size_t)R * d.Cin);
+      bf16* out = ws.take<bf16>((size_t)R * Ka);
+      WS_GUARD(ws, "mocha_bench_hbm_kernel");
+      MOCHA_CUDA(cudaMemsetAsync(X, 0, (size_t)R * d.Cin * 4, s));
+      for (int i = 0; i < repeats && rc == MOCHA_OK; ++i)
+        rc = embed_graph_agg(X, w->emb_w, w->emb_b, w->A_j, out, B * d.T, d.V, d.Cin, d.C0, d.Kj, s, Ka == KC ? 0 : Ka);
+      *algo_bytes = (double)R * d.Cin * 4 + (double)R * Ka * 2;
+      break;
+    }
+    case 1: {
+      bf16* h1 = ws.take<bf16>((size_t)R * d.D);
+      bf16* out = ws.take<bf16>((size_t)R2 * d.Kb * d.D);
+      WS_GUARD(ws, "mocha_bench_hbm_kernel");
+      MOCHA_CUDA(cudaMemsetAsync(h1, 0, (size_t)R * d.D * 2, s));
+      for (int i = 0; i < repeats && rc == MOCHA_OK; ++i)
+        rc = pool_graph_agg(h1, w->pool_w, w->A_b, out, B, d.T, d.V, d.P, d.D, d.tp, d.Kb, s);
+      *algo_bytes = (double)R * d.D * 2 + (double)R2 * d.Kb * d.D * 2;
+      break;
+    }
+    case 2: {
+      const long long rows = (long long)B * (2 * n + 2);
+      float* x = ws.take<float>((size_t)rows * d.D);
+      float* y = ws.take<float>((size_t)rows * d.D);
+      bf16* y16 = ws.take<bf16>((size_t)rows * d.D);
+      float* g = ws.take<float>((size_t)2 * d.D);
+      WS_GUARD(ws, "mocha_bench_hbm_kernel");
+      MOCHA_CUDA(cudaMemsetAsync(x, 0, (size_t)rows * d.D * 4, s));
+      MOCHA_CUDA(cudaMemsetAsync(g, 0, (size_t)2 * d.D * 4, s));
+      for (int i = 0; i < repeats && rc == MOCHA_OK; ++i)
+        rc = add_layernorm(x, nullptr, g, g + d.D, y, rows, d.D, 1e-5f, nullptr, nullptr, 0, nullptr, s, y16);
+      *algo_bytes = (double)rows * d.D * (4 + 4 + 2);
+      break;
+    }
+    case 3: {
+      const int padj = d.taps_j / 2;
+      float* y3 = ws.take<float>((size_t)R2 * d.Kj * d.C0);
+      bf16* gp = ws.take<bf16>((size_t)B * (d.T + 2 * padj) * d.V * d.C0);
+      WS_GUARD(ws, "mocha_bench_hbm_kernel");
+      MOCHA_CUDA(cudaMemsetAsync(y3, 0, (size_t)R2 * d.Kj * d.C0 * 4, s));
+      for (int i = 0; i < repeats && rc == MOCHA_OK; ++i)
+        rc = graph_agg_kv_pad16(y3, w->tm_A2, gp, B, Tp, d.tp, padj, d.P, d.V, d.C0, d.Kj, s);
+      *algo_bytes = (double)R2 * d.Kj * d.C0 * 4 + (double)B * (d.T + 2 * padj) * d.V * d.C0 * 2;
+      break;
+    }
+    case 4: case 5: {
+      float* x = ws.take<float>((size_t)B * n * d.D);
+      float* gb = ws.take<float>((size_t)B * 2 * d.D);
+      float* y = ws.take<float>((size_t)B * n * d.D);
+      bf16* q16 = ws.take<bf16>((size_t)B * n * d.D);
+      WS_GUARD(ws, "mocha_bench_hbm_kernel");
+      // a ramp, not zeros: a constant channel has zero variance
+      MOCHA_TRY(broadcast_rows(w->pos_emb, x, B, (long long)n * d.D, s));
+      MOCHA_CUDA(cudaMemsetAsync(gb, 0, (size_t)B * 2 * d.D * 4, s));
+      for (int i = 0; i < repeats && rc == MOCHA_OK; ++i)
+        rc = which == 4 ? adain_norm_tokens(x, B, n, d.D, 1e-5f, gb, y, q16, s)
+                        : instance_norm_tokens(x, B, n, d.D, 1e-5f, nullptr, nullptr, nullptr, nullptr, nullptr, s, q16);
+      *algo_bytes = which == 4 ? (double)B * n * d.D * (4 + 4 + 2) : (double)B * n * d.D * (4 + 2);
+      break;
+    }
+    default:
+      return set_error(MOCHA_ERR_ARG, "mocha_bench_hbm_kernel: unknown kernel %d", which);
+  }
+  return rc;
+}
