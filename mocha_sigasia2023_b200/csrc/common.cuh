@@ -46,6 +46,36 @@ const char* last_error();
 // launch counter (bench.py reports "gpu_launches" from it)
 void count_launch(int n = 1);
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): every kernel of the library is launched with the programmatic-stream-
+// serialization attribute, so its CTAs may become resident as soon as the previous kernel's CTAs have called
+// pdl_trigger() (or exited) and run their prologue (barrier init, TMEM allocation, descriptor prefetch, weight
+// staging) under the previous kernel's tail. Contract, kept by every kernel:
+//   * nothing produced by an earlier kernel is read, and no global memory is written, before pdl_wait() returns
+//     (griddepcontrol.wait = the previous grid has completed and its memory is visible);
+//   * every kernel executes pdl_wait() before it exits, so completion stays transitive along the stream.
+// A ~110-launch frame captured in a CUDA graph keeps these edges as programmatic dependencies.
+// MOCHA_PDL=0 in the environment launches everything with plain stream serialization (A/B switch).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface through MOCHA_LAUNCH_CHECK
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -17,6 +17,8 @@ __device__ __forceinline__ int reflect_idx(int t, int T) {
 template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 sgemm_kernel(const GemmParams p) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int TXN = BN / TN;                 // threads along N
   constexpr int AV = (BM * BK) / (4 * NT);     // float4 loads of A per thread
@@ -278,7 +280,7 @@ sgemm_kernel(const GemmParams p) {
 template <int BM, int BN, int TM, int TN>
 int launch(const GemmParams& p, cudaStream_t s) {
   dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM), p.nz);
-  sgemm_kernel<BM, BN, TM, TN><<<grid, (BM / TM) * (BN / TN), 0, s>>>(p);
+  launch_k(sgemm_kernel<BM, BN, TM, TN>, grid, (BM / TM) * (BN / TN), 0, s, p);
   count_launch();
   MOCHA_LAUNCH_CHECK("sgemm_kernel");
   return MOCHA_OK;

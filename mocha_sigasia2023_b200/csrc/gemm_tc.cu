@@ -279,6 +279,8 @@ __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until every committed bulk store of this thread has finished READING shared memory
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... until at most ONE committed bulk store of this thread is still reading shared memory (double-buffered staging)
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
@@ -368,15 +370,20 @@ struct LinearEpiData {
 };
 using LinearEpi = LinearEpiData;
 
-// MODE 0: LSU epilogue; 1: TMA stores; 2: TMA stores + TMA-prefetched residual. One kernel
-// instantiation per mode keeps each epilogue's register footprint and code small.
+// MODE 0: LSU epilogue; 1: TMA stores; 2: TMA stores + TMA-prefetched residual; 4: MODE 1 with TWO staging boxes per
+// warp - a TMA store needs ~1000 cycles to finish reading its box, and with one box every chunk (64 bf16 / 32 fp32
+// columns) stalled on the previous chunk's store; with two the warp only waits for the store before last.
+// One kernel instantiation per mode keeps each epilogue's register footprint and code small.
 template <int MODE>
 struct LinearEpiT : LinearEpiData {
   struct State {
     uint32_t rphase;  // parity of the residual-prefetch barrier
     int col_begin;    // first column of this warp's share of the current tile
     float rs;         // this lane's row scale for the current tile
+    uint32_t par;     // MODE 4: which of the two staging boxes the next chunk fills
   };
+  static constexpr bool kM1 = MODE == 1 || MODE == 4;   // single-output TMA-store epilogue
+  static constexpr bool kDouble = MODE == 4;
   // per warp: 4 KB fp32 box [32][128 B] (128 B-swizzled, 1 KB aligned) + 2 KB bf16 box [32][64 B]
   // (64 B-swizzled) + 4 KB residual box (128 B-swizzled); the LSU path uses a [32][EPI_LD] float
   // transposition buffer
@@ -387,7 +394,7 @@ struct LinearEpiT : LinearEpiData {
   // MODE 3 = MODE 2 without a bf16 output (no bf16 box): 8 KB per warp leaves room for 128 x 256 tiles
   static constexpr bool kRes = MODE == 2 || MODE == 3;
   static constexpr int kResOff = MODE == 3 ? 4096 : 6144;
-  static constexpr int kWarpStageBytes = MODE == 2 ? 10240 : MODE == 3 ? 8192 : MODE == 1 ? 4096 : 5120;
+  static constexpr int kWarpStageBytes = MODE == 2 ? 10240 : MODE == 3 ? 8192 : MODE == 1 ? 4096 : MODE == 4 ? 8192 : 5120;
   static_assert(kWarpStageBytes % 1024 == 0, "swizzled TMA boxes need 1 KB alignment");
   static constexpr int kBiasBytes = MODE == 0 ? 0 : 8192;
   static constexpr int kStageBytes = EPI_WARPS * kWarpStageBytes + kBiasBytes;
@@ -396,7 +403,7 @@ struct LinearEpiT : LinearEpiData {
   static constexpr bool kWholeTile = false;
   __device__ __forceinline__ void unit_begin(State&) const {}
   __device__ __forceinline__ void kernel_begin(State& st, const EpiCtx& e) const {
-    st.rphase = 0; st.col_begin = 0; st.rs = 1.f;
+    st.rphase = 0; st.col_begin = 0; st.rs = 1.f; st.par = 0;
     if (MODE != 0) {
       // the epilogue's only global loads that are not TMA: the column bias, once per CTA, while the first
       // tile's main loop runs (per-chunk or per-tile loads see >1000-cycle latencies under store traffic)
@@ -419,7 +426,7 @@ struct LinearEpiT : LinearEpiData {
   // overlaps the tile's main loop), and in MODE 2 the residual box is TMA-prefetched one chunk ahead.
   __device__ __forceinline__ void tile_begin(State& st, const EpiCtx& e, int col_begin, int ncols) const {
     st.col_begin = col_begin;
-    if (MODE == 1 && row_scale)
+    if (kM1 && row_scale)
       st.rs = e.lane < e.slab_rows ? __ldg(row_scale + (long long)e.z * rs_rows + e.row0_in_img + e.lane) : 0.f;
     (void)ncols;
     prefetch_res(e, col_begin);
@@ -549,8 +556,10 @@ struct LinearEpiT : LinearEpiData {
         for (int j = 0; j < 32; ++j) f[j] = act_fn<ACT>(f[j]);
       }
       EPI_DBG(8);
+      const uint32_t sbuf = e.stage + (kDouble ? st.par * 4096u : 0u);   // this chunk's staging box
       if (!(c16_wide && !C && (((col0 - st.col_begin) >> 5) & 1))) {
-        if (e.lane == 0) bulk_wait_read0();  // the previous store has left the staging buffer
+        // the store that last used this box has finished reading it (double-buffered: the store before last)
+        if (e.lane == 0) { if (kDouble) bulk_wait_read1(); else bulk_wait_read0(); }
         __syncwarp();
       }
       EPI_DBG(9);
@@ -558,7 +567,7 @@ struct LinearEpiT : LinearEpiData {
         const int sw = e.lane & 7;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          sts128(e.stage + (uint32_t)(e.lane * 128 + ((j ^ sw) << 4)), __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
+          sts128(sbuf + (uint32_t)(e.lane * 128 + ((j ^ sw) << 4)), __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
                  __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
       } else if (c16_wide) {
         const int hcol = ((col0 - st.col_begin) >> 5) & 1;   // which half of the 64-column box
@@ -573,15 +582,16 @@ struct LinearEpiT : LinearEpiData {
             __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
             pk[t] = *reinterpret_cast<uint32_t*>(&h2);
           }
-          sts128(e.stage + (uint32_t)(e.lane * 128 + (((j + 4 * hcol) ^ sw) << 4)), pk[0], pk[1], pk[2], pk[3]);
+          sts128(sbuf + (uint32_t)(e.lane * 128 + (((j + 4 * hcol) ^ sw) << 4)), pk[0], pk[1], pk[2], pk[3]);
         }
         if (hcol == 0) return;   // the box goes out with its second half
         fence_async_smem();
         __syncwarp();
         if (e.lane == 0) {
-          tma_store_3d(&tmC16w, e.stage, col0 - 32 + e.col_off, e.row0_in_img, e.img);
+          tma_store_3d(&tmC16w, sbuf, col0 - 32 + e.col_off, e.row0_in_img, e.img);
           bulk_commit();
         }
+        if (kDouble) st.par ^= 1u;
         return;
       } else {
         const int sw16 = (e.lane >> 1) & 3;
@@ -595,7 +605,7 @@ struct LinearEpiT : LinearEpiData {
             __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
             pk[t] = *reinterpret_cast<uint32_t*>(&h2);
           }
-          sts128(e.stage + (uint32_t)(e.lane * 64 + ((j ^ sw16) << 4)), pk[0], pk[1], pk[2], pk[3]);
+          sts128(sbuf + (uint32_t)(e.lane * 64 + ((j ^ sw16) << 4)), pk[0], pk[1], pk[2], pk[3]);
         }
       }
       EPI_DBG(11);
@@ -603,10 +613,11 @@ struct LinearEpiT : LinearEpiData {
       __syncwarp();
       EPI_DBG(12);
       if (e.lane == 0) {
-        if (C) tma_store_3d(&tmC, e.stage, col0 + e.col_off, e.row0_in_img, e.img);
-        else tma_store_3d(&tmC16, e.stage, col0 + e.col_off, e.row0_in_img, e.img);
+        if (C) tma_store_3d(&tmC, sbuf, col0 + e.col_off, e.row0_in_img, e.img);
+        else tma_store_3d(&tmC16, sbuf, col0 + e.col_off, e.row0_in_img, e.img);
         bulk_commit();
       }
+      if (kDouble) st.par ^= 1u;
       EPI_DBG(13);
       return;
     }
@@ -832,7 +843,7 @@ struct LinearEpiT : LinearEpiData {
         case ACT_LRELU: drain_tma_res<ACT_LRELU>(st, e, col0, next_col0, v); break;
         default: drain_tma_res<ACT_NONE>(st, e, col0, next_col0, v); break;
       }
-    } else if constexpr (MODE == 1) {
+    } else if constexpr (kM1) {
       if (e.slab_rows <= 0) return;
       switch (act) {
         case ACT_RELU: drain_tma<ACT_RELU>(st, e, col0, next_col0, v); break;
@@ -1064,6 +1075,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + EPI_WARPS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
 #ifdef MOCHA_TRACE
   unsigned long long* const trace_buf = g_tc_trace;
   const int dbg_mode = g_tc_dbg_mode;
@@ -1083,6 +1095,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above (barriers, TMEM, descriptor prefetch) ran under the previous kernel's tail; operands and
+  // outputs may only be touched once that kernel has completed
+  pdl_wait();
 #ifdef MOCHA_TRACE
   if (threadIdx.x == 0) TC_TRACE(2, (unsigned long long)clock64());
   int trace_tile = 0;
@@ -1402,6 +1417,7 @@ template <class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcShape sh,
                 const int num_kb, const __grid_constant__ Epi epi) {
+  pdl_trigger();
   using SM = PairSmem<Epi::kStageBytes>;
   constexpr int STAGES = SM::STAGES;
   constexpr int BN = M2_BN;
@@ -1439,6 +1455,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // PDL: the prologue above overlaps the previous kernel's tail (see tc_gemm_kernel)
 #ifdef MOCHA_TRACE
   if (threadIdx.x == 0) TC_TRACE(2, (unsigned long long)clock64());
 #endif
@@ -1704,7 +1721,7 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcShape& sh,
     configured = true;
   }
   const int grid = sh.units < num_sms() ? sh.units : num_sms();
-  tc_gemm_kernel<BN, Epi><<<grid, TC_THREADS, SM::TOTAL, s>>>(tmA, tmB, sh, num_kb, epi);
+  launch_k(tc_gemm_kernel<BN, Epi>, grid, TC_THREADS, SM::TOTAL, s, tmA, tmB, sh, num_kb, epi);
   count_launch();
   MOCHA_LAUNCH_CHECK("tc_gemm_kernel");
   return MOCHA_OK;
@@ -1722,7 +1739,7 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcShape& s
   int grid = 2 * sh.units;
   const int cap = num_sms() & ~1;
   if (grid > cap) grid = cap;
-  tc_gemm2_kernel<Epi><<<grid, TC_THREADS, SM::TOTAL, s>>>(tmA, tmB, sh, num_kb, epi);
+  launch_k(tc_gemm2_kernel<Epi>, grid, TC_THREADS, SM::TOTAL, s, tmA, tmB, sh, num_kb, epi);
   count_launch();
   MOCHA_LAUNCH_CHECK("tc_gemm2_kernel");
   return MOCHA_OK;
@@ -1735,6 +1752,8 @@ int launch_match2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcShape&
 
 __global__ void cast_act_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n,
                                      int lrelu) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     float4 v = *reinterpret_cast<const float4*>(x + i);
@@ -1755,6 +1774,8 @@ __global__ void cast_act_bf16_kernel(const float* __restrict__ x, __nv_bfloat16*
 // X fp32 [B,T,V,C] -> bf16 [B, T+2*pad, V, C] with reflect padding along T
 __global__ void reflect_pad_cast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int T, int V,
                                         int C, int pad, int tdiv, long long total4) {
+  pdl_trigger();
+  pdl_wait();
   const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i4 >= total4) return;
   const long long i = i4 * 4;
@@ -1780,6 +1801,8 @@ __global__ void reflect_pad_cast_kernel(const float* __restrict__ x, __nv_bfloat
 // bf16 source variant (8 elements = 16 B per thread)
 __global__ void reflect_pad_copy_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int T, int V,
                                         int C, int pad, int tdiv, long long total8) {
+  pdl_trigger();
+  pdl_wait();
   const long long i8 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i8 >= total8) return;
   const long long i = i8 * 8;
@@ -1850,10 +1873,10 @@ int dispatch_bn(int bn, const CUtensorMap& tmA, const void* Wptr, unsigned long 
   if (epi.c16_wide && bn < 128) {
     LinearEpi e2 = epi;
     e2.c16_wide = 0;
-    return dispatch_bn_impl(bn, tmA, Wptr, wrows, K, sh, N, num_kb, LinearEpiT<1>{e2}, s, wpitch);
+    return dispatch_bn_impl(bn, tmA, Wptr, wrows, K, sh, N, num_kb, LinearEpiT<4>{e2}, s, wpitch);
   }
   if (epi.tma == 2) return dispatch_bn_impl(bn, tmA, Wptr, wrows, K, sh, N, num_kb, LinearEpiT<2>{epi}, s, wpitch);
-  if (epi.tma == 1) return dispatch_bn_impl(bn, tmA, Wptr, wrows, K, sh, N, num_kb, LinearEpiT<1>{epi}, s, wpitch);
+  if (epi.tma == 1) return dispatch_bn_impl(bn, tmA, Wptr, wrows, K, sh, N, num_kb, LinearEpiT<4>{epi}, s, wpitch);
   return dispatch_bn_impl(bn, tmA, Wptr, wrows, K, sh, N, num_kb, LinearEpiT<0>{epi}, s, wpitch);
 }
 
@@ -1952,7 +1975,7 @@ int tc_linear(const float* A, const float* W, const float* bias, int bias_period
 
 int tc_cast(const float* x, __nv_bfloat16* y, long long n, int lrelu, cudaStream_t s) {
   MOCHA_CHECK_ARG(x && y && n > 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "tc_cast: bad argument");
-  cast_act_bf16_kernel<<<(unsigned)((n / 4 + 255) / 256 + 1), 256, 0, s>>>(x, y, n, lrelu);
+  launch_k(cast_act_bf16_kernel, (unsigned)((n / 4 + 255) / 256 + 1), 256, 0, s, x, y, n, lrelu);
   count_launch();
   MOCHA_LAUNCH_CHECK("cast_act_bf16");
   return MOCHA_OK;
@@ -1987,10 +2010,10 @@ int tc_tconv_ex(const float* X, const __nv_bfloat16* Xh, const float* W, const f
   if (!xh_is_padded && !X16) return set_error(MOCHA_ERR_WORKSPACE, "tc_tconv: workspace too small for the padded bf16 operand");
   if (xh_is_padded) {
   } else if (Xh)
-    reflect_pad_copy_kernel<<<(unsigned)((elems / 8 + 255) / 256), 256, 0, s>>>(Xh, X16, T, V, Cin, pad, tdiv,
+    launch_k(reflect_pad_copy_kernel, (unsigned)((elems / 8 + 255) / 256), 256, 0, s, Xh, X16, T, V, Cin, pad, tdiv,
                                                                                (long long)(elems / 8));
   else
-    reflect_pad_cast_kernel<<<(unsigned)((elems / 4 + 255) / 256), 256, 0, s>>>(X, X16, T, V, Cin, pad, tdiv,
+    launch_k(reflect_pad_cast_kernel, (unsigned)((elems / 4 + 255) / 256), 256, 0, s, X, X16, T, V, Cin, pad, tdiv,
                                                                                (long long)(elems / 4));
   if (!xh_is_padded) {
     count_launch();
@@ -2046,6 +2069,8 @@ namespace {
 // fp32 [rows, cols] view with row pitch ld -> compact bf16 [rows, cols]
 __global__ void cast_strided_bf16_kernel(const float* __restrict__ x, int ld, int cols, long long total4,
                                          __nv_bfloat16* __restrict__ y) {
+  pdl_trigger();
+  pdl_wait();
   const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i4 >= total4) return;
   const int c4 = cols >> 2;
@@ -2065,6 +2090,8 @@ __device__ __forceinline__ float to_f32(__nv_bfloat16 x) { return __bfloat162flo
 template <typename TV>
 __global__ void transpose_v_bf16_kernel(const TV* __restrict__ v, int ldv, int H, int nkv, int dh, int ldp,
                                         __nv_bfloat16* __restrict__ vt) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int z = blockIdx.z, b = z / H, h = z - b * H;
   const int j0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
@@ -2117,7 +2144,7 @@ int tc_attention_ex(const float* q, const __nv_bfloat16* qh, int ldq, const floa
     __nv_bfloat16* t = ws.take<__nv_bfloat16>((size_t)B * nq * inner);
     if (!t) return set_error(MOCHA_ERR_WORKSPACE, "tc_attention: workspace too small");
     const long long t4 = (long long)B * nq * inner / 4;
-    cast_strided_bf16_kernel<<<(unsigned)((t4 + 255) / 256), 256, 0, s>>>(q, ldq, inner, t4, t);
+    launch_k(cast_strided_bf16_kernel, (unsigned)((t4 + 255) / 256), 256, 0, s, q, ldq, inner, t4, t);
     count_launch();
     Q16 = t; pq = inner;
   }
@@ -2126,7 +2153,7 @@ int tc_attention_ex(const float* q, const __nv_bfloat16* qh, int ldq, const floa
     __nv_bfloat16* t = ws.take<__nv_bfloat16>((size_t)B * nkv * inner);
     if (!t) return set_error(MOCHA_ERR_WORKSPACE, "tc_attention: workspace too small");
     const long long u4 = (long long)B * nkv * inner / 4;
-    cast_strided_bf16_kernel<<<(unsigned)((u4 + 255) / 256), 256, 0, s>>>(k, ldk, inner, u4, t);
+    launch_k(cast_strided_bf16_kernel, (unsigned)((u4 + 255) / 256), 256, 0, s, k, ldk, inner, u4, t);
     count_launch();
     K16 = t; pk = inner;
   }
@@ -2139,8 +2166,8 @@ int tc_attention_ex(const float* q, const __nv_bfloat16* qh, int ldq, const floa
                   "tc_attention: output must be a dense, 16 B-aligned [B, nq, H*dh] tensor");
   if (!v_in_place) {
     dim3 g((ldp + 31) / 32, (dh + 31) / 32, Z);
-    if (vh) transpose_v_bf16_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(vh, ldv, H, nkv, dh, ldp, VT16);
-    else transpose_v_bf16_kernel<float><<<g, 256, 0, s>>>(v, ldv, H, nkv, dh, ldp, VT16);
+    if (vh) launch_k(transpose_v_bf16_kernel<__nv_bfloat16>, g, 256, 0, s, vh, ldv, H, nkv, dh, ldp, VT16);
+    else launch_k(transpose_v_bf16_kernel<float>, g, 256, 0, s, v, ldv, H, nkv, dh, ldp, VT16);
     count_launch();
     MOCHA_LAUNCH_CHECK("attention staging");
   }
@@ -2346,6 +2373,8 @@ namespace {
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int slices, int nq, int Np, long long N,
                                      const float* __restrict__ dbnorm, float* __restrict__ cand_score,
                                      int32_t* __restrict__ cand_idx) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)nq * Np) return;
   const int n = (int)(i % Np);
@@ -2400,7 +2429,7 @@ int tc_match_coarse_splitk(const __nv_bfloat16* Q16, int nq, const __nv_bfloat16
   LinearEpi epi{partial, Np, Np, nullptr, 0, nullptr, ACT_NONE, nullptr, 0};
   MOCHA_TRY(dispatch_bn(BN, tmA, DB16, (unsigned long long)N, (unsigned long long)D, sh, Np, kb_per, epi, s));
   const long long total = (long long)nq * Np;
-  splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(partial, slices, nq, Np, N, dbnorm, cand_score, cand_idx);
+  launch_k(splitk_reduce_kernel, (unsigned)((total + 255) / 256), 256, 0, s, partial, slices, nq, Np, N, dbnorm, cand_score, cand_idx);
   count_launch();
   MOCHA_LAUNCH_CHECK("splitk_reduce_kernel");
   return MOCHA_OK;

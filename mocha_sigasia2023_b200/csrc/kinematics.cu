@@ -105,6 +105,8 @@ template <typename T> __device__ __forceinline__ Q4<T> q_from_xy(V3<T> c0, V3<T>
 // element-wise rotation format conversions
 // ------------------------------------------------------------------------------------------------
 __global__ void xy_to_quat_kernel(const float* __restrict__ xy, long long n, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float* p = xy + i * 6;  // [3][2]
@@ -114,6 +116,8 @@ __global__ void xy_to_quat_kernel(const float* __restrict__ xy, long long n, flo
 
 // quat.to_xform_xy (motion/quat.py:42-55)
 __global__ void quat_to_xy_kernel(const float* __restrict__ quat, long long n, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 q = reinterpret_cast<const float4*>(quat)[i];
@@ -161,6 +165,8 @@ __global__ void __launch_bounds__(FK_WARPS * 32)
 fk_kernel(const T* __restrict__ lrot, const T* __restrict__ lpos, const T* __restrict__ lvel,
           const T* __restrict__ lang, const int32_t* __restrict__ parents, long long F, int J,
           T* __restrict__ grot, T* __restrict__ gpos, T* __restrict__ gvel, T* __restrict__ gang) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ SkelSmem<T> sm[FK_WARPS];
   __shared__ int32_t par[MAXJ];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -229,6 +235,8 @@ template <typename T>
 __global__ void __launch_bounds__(FK_WARPS * 32)
 ik_kernel(const T* __restrict__ grot, const T* __restrict__ gpos, const int32_t* __restrict__ parents,
           long long F, int J, T* __restrict__ lrot, T* __restrict__ lpos) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ SkelSmem<T> sm[FK_WARPS];
   __shared__ int32_t par[MAXJ];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -368,6 +376,8 @@ post_frame_kernel(const mocha_post_params P, const float* __restrict__ Y,
                   const float* __restrict__ src_rang, const uint8_t* __restrict__ contacts, int B,
                   int T, int V, int Cin, int init, mocha_clip_state* __restrict__ states,
                   mocha_frame_out* __restrict__ outs, int hv_stride, int rv_stride) {
+  pdl_trigger();
+  pdl_wait();
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (b >= B) return;  // warp-uniform
@@ -541,6 +551,8 @@ __global__ void contact_update_kernel(int32_t* state, int32_t* lock, double* pos
                                       double* point, double* target, double* off_pos, double* off_vel,
                                       const double* input_position, const int32_t* input_state, long long n,
                                       double unlock_radius, double foot_height, double halflife, double dt) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   ContactState c;
@@ -557,6 +569,8 @@ __global__ void ik_two_bone_kernel(const double* root, const double* mid, const 
                                    const double* fwd, const double* root_gr, const double* mid_gr,
                                    const double* par_gr, double max_length_buffer, long long n, double* out_root_lr,
                                    double* out_mid_lr) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   DQ a, b;
@@ -574,6 +588,8 @@ __global__ void pose_transition_kernel(double* off_pos, double* off_vel, double*
                                        const double* dst_vel, const double* dst_rot, const double* dst_ang,
                                        long long n, int J, double* tr_src_pos, double* tr_src_rot,
                                        double* tr_dst_pos, double* tr_dst_rot) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * J) return;
   const long long s = i / J;
@@ -609,6 +625,8 @@ __global__ void pose_update_kernel(double* pos, double* vel, double* rot, double
                                    const double* in_vel, const double* in_rot, const double* in_ang,
                                    const double* tr_src_pos, const double* tr_src_rot, const double* tr_dst_pos,
                                    const double* tr_dst_rot, double halflife, double dt, long long n, int J) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * J) return;
   const long long s = i / J;
@@ -644,7 +662,7 @@ inline unsigned nblk(long long n, int bs) { return (unsigned)((n + bs - 1) / bs)
 extern "C" int mocha_xy_to_quat(const float* xy, long long n, float* quat, mocha_stream_t stream) {
   MOCHA_CHECK_ARG(xy && quat && n > 0, "mocha_xy_to_quat: bad argument");
   MOCHA_CHECK_ARG((reinterpret_cast<uintptr_t>(quat) & 15) == 0, "mocha_xy_to_quat: output not 16B aligned");
-  xy_to_quat_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(xy, n, quat);
+  launch_k(xy_to_quat_kernel, nblk(n, 256), 256, 0, (cudaStream_t)stream, xy, n, quat);
   count_launch();
   MOCHA_LAUNCH_CHECK("xy_to_quat_kernel");
   return MOCHA_OK;
@@ -653,7 +671,7 @@ extern "C" int mocha_xy_to_quat(const float* xy, long long n, float* quat, mocha
 extern "C" int mocha_quat_to_xy(const float* quat, long long n, float* xy, mocha_stream_t stream) {
   MOCHA_CHECK_ARG(xy && quat && n > 0, "mocha_quat_to_xy: bad argument");
   MOCHA_CHECK_ARG((reinterpret_cast<uintptr_t>(quat) & 15) == 0, "mocha_quat_to_xy: input not 16B aligned");
-  quat_to_xy_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(quat, n, xy);
+  launch_k(quat_to_xy_kernel, nblk(n, 256), 256, 0, (cudaStream_t)stream, quat, n, xy);
   count_launch();
   MOCHA_LAUNCH_CHECK("quat_to_xy_kernel");
   return MOCHA_OK;
@@ -669,7 +687,7 @@ extern "C" int mocha_fk(const float* lrot, const float* lpos, const int32_t* par
                         float* gpos, mocha_stream_t stream) {
   MOCHA_CHECK_ARG(lrot && lpos && grot && gpos && F > 0, "mocha_fk: bad argument");
   MOCHA_TRY(check_parents_arg(parents, J));
-  fk_kernel<false, float><<<fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream>>>(lrot, lpos, nullptr, nullptr, parents, F, J,
+  launch_k(fk_kernel<false, float>, fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream, lrot, lpos, nullptr, nullptr, parents, F, J,
                                                                           grot, gpos, nullptr, nullptr);
   count_launch();
   MOCHA_LAUNCH_CHECK("fk_kernel");
@@ -681,7 +699,7 @@ extern "C" int mocha_fk_vel(const float* lrot, const float* lpos, const float* l
                             float* gang, mocha_stream_t stream) {
   MOCHA_CHECK_ARG(lrot && lpos && lvel && lang && grot && gpos && gvel && gang && F > 0, "mocha_fk_vel: bad argument");
   MOCHA_TRY(check_parents_arg(parents, J));
-  fk_kernel<true, float><<<fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream>>>(lrot, lpos, lvel, lang, parents, F, J, grot,
+  launch_k(fk_kernel<true, float>, fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream, lrot, lpos, lvel, lang, parents, F, J, grot,
                                                                          gpos, gvel, gang);
   count_launch();
   MOCHA_LAUNCH_CHECK("fk_vel_kernel");
@@ -692,7 +710,7 @@ extern "C" int mocha_ik(const float* grot, const float* gpos, const int32_t* par
                         float* lpos, mocha_stream_t stream) {
   MOCHA_CHECK_ARG(lrot && lpos && grot && gpos && F > 0, "mocha_ik: bad argument");
   MOCHA_TRY(check_parents_arg(parents, J));
-  ik_kernel<float><<<fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream>>>(grot, gpos, parents, F, J, lrot, lpos);
+  launch_k(ik_kernel<float>, fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream, grot, gpos, parents, F, J, lrot, lpos);
   count_launch();
   MOCHA_LAUNCH_CHECK("ik_kernel");
   return MOCHA_OK;
@@ -716,7 +734,7 @@ int post_frame_launch(const mocha_post_params* params, const float* Y, const flo
     MOCHA_CHECK_ARG(params->contact_bones[f] > 0 && params->contact_bones[f] < params->J && depth >= 4,
                     "mocha_post_frame: contact bone %d needs 4 ancestors", params->contact_bones[f]);
   }
-  post_frame_kernel<<<nblk((long long)B * 32, 128), 128, 0, (cudaStream_t)stream>>>(*params, Y, src_hips_vel, src_rvel, src_rang,
+  launch_k(post_frame_kernel, nblk((long long)B * 32, 128), 128, 0, (cudaStream_t)stream, *params, Y, src_hips_vel, src_rvel, src_rang,
                                                                  contacts, B, T, V, Cin, init, state, out, hv_stride, rv_stride);
   count_launch();
   MOCHA_LAUNCH_CHECK("post_frame_kernel");
@@ -749,7 +767,7 @@ extern "C" int mocha_contact_update(int32_t* state, int32_t* lock, double* posit
   MOCHA_CHECK_ARG(state && lock && position && velocity && point && target && off_pos && off_vel && input_position &&
                       input_state && n > 0,
                   "mocha_contact_update: null/empty argument");
-  contact_update_kernel<<<nblk(n, 128), 128, 0, (cudaStream_t)stream>>>(state, lock, position, velocity, point, target,
+  launch_k(contact_update_kernel, nblk(n, 128), 128, 0, (cudaStream_t)stream, state, lock, position, velocity, point, target,
                                                                        off_pos, off_vel, input_position, input_state,
                                                                        n, unlock_radius, foot_height, halflife, dt);
   count_launch();
@@ -763,7 +781,7 @@ extern "C" int mocha_fk_f64(const double* lrot, const double* lpos, const int32_
                             double* gpos, mocha_stream_t stream) {
   MOCHA_CHECK_ARG(lrot && lpos && grot && gpos && F > 0, "mocha_fk_f64: bad argument");
   MOCHA_TRY(check_parents_arg(parents, J));
-  fk_kernel<false, double><<<fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream>>>(lrot, lpos, nullptr, nullptr, parents, F, J,
+  launch_k(fk_kernel<false, double>, fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream, lrot, lpos, nullptr, nullptr, parents, F, J,
                                                                                   grot, gpos, nullptr, nullptr);
   count_launch();
   MOCHA_LAUNCH_CHECK("fk_kernel<double>");
@@ -775,7 +793,7 @@ extern "C" int mocha_fk_vel_f64(const double* lrot, const double* lpos, const do
                                 double* gang, mocha_stream_t stream) {
   MOCHA_CHECK_ARG(lrot && lpos && lvel && lang && grot && gpos && gvel && gang && F > 0, "mocha_fk_vel_f64: bad argument");
   MOCHA_TRY(check_parents_arg(parents, J));
-  fk_kernel<true, double><<<fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream>>>(lrot, lpos, lvel, lang, parents, F, J, grot,
+  launch_k(fk_kernel<true, double>, fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream, lrot, lpos, lvel, lang, parents, F, J, grot,
                                                                                  gpos, gvel, gang);
   count_launch();
   MOCHA_LAUNCH_CHECK("fk_vel_kernel<double>");
@@ -786,7 +804,7 @@ extern "C" int mocha_ik_f64(const double* grot, const double* gpos, const int32_
                             double* lpos, mocha_stream_t stream) {
   MOCHA_CHECK_ARG(lrot && lpos && grot && gpos && F > 0, "mocha_ik_f64: bad argument");
   MOCHA_TRY(check_parents_arg(parents, J));
-  ik_kernel<double><<<fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream>>>(grot, gpos, parents, F, J, lrot, lpos);
+  launch_k(ik_kernel<double>, fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream, grot, gpos, parents, F, J, lrot, lpos);
   count_launch();
   MOCHA_LAUNCH_CHECK("ik_kernel<double>");
   return MOCHA_OK;
@@ -799,7 +817,7 @@ extern "C" int mocha_ik_two_bone(const double* root_lr, const double* mid_lr, co
   (void)root_lr; (void)mid_lr;  // inputs the reference accepts but overwrites (motion/quat.py:340-341)
   MOCHA_CHECK_ARG(root && mid && end && target && fwd && root_gr && mid_gr && par_gr && out_root_lr && out_mid_lr && n > 0,
                   "mocha_ik_two_bone: null/empty argument");
-  ik_two_bone_kernel<<<nblk(n, 128), 128, 0, (cudaStream_t)stream>>>(root, mid, end, target, fwd, root_gr, mid_gr,
+  launch_k(ik_two_bone_kernel, nblk(n, 128), 128, 0, (cudaStream_t)stream, root, mid, end, target, fwd, root_gr, mid_gr,
                                                                     par_gr, max_length_buffer, n, out_root_lr,
                                                                     out_mid_lr);
   count_launch();
@@ -818,8 +836,7 @@ extern "C" int mocha_pose_transition(double* off_pos, double* off_vel, double* o
                       src_vel && src_rot && src_ang && dst_pos && dst_vel && dst_rot && dst_ang && tr_src_pos &&
                       tr_src_rot && tr_dst_pos && tr_dst_rot && n > 0 && J > 0,
                   "mocha_pose_transition: null/empty argument");
-  pose_transition_kernel<<<nblk(n * J, 128), 128, 0, (cudaStream_t)stream>>>(
-      off_pos, off_vel, off_rot, off_ang, root_pos, root_vel, root_rot, root_ang, src_pos, src_vel, src_rot, src_ang,
+  launch_k(pose_transition_kernel, nblk(n * J, 128), 128, 0, (cudaStream_t)stream, off_pos, off_vel, off_rot, off_ang, root_pos, root_vel, root_rot, root_ang, src_pos, src_vel, src_rot, src_ang,
       dst_pos, dst_vel, dst_rot, dst_ang, n, J, tr_src_pos, tr_src_rot, tr_dst_pos, tr_dst_rot);
   count_launch();
   MOCHA_LAUNCH_CHECK("pose_transition_kernel");
@@ -834,7 +851,7 @@ extern "C" int mocha_pose_update(double* pos, double* vel, double* rot, double* 
   MOCHA_CHECK_ARG(pos && vel && rot && ang && off_pos && off_vel && off_rot && off_ang && in_pos && in_vel && in_rot &&
                       in_ang && tr_src_pos && tr_src_rot && tr_dst_pos && tr_dst_rot && n > 0 && J > 0,
                   "mocha_pose_update: null/empty argument");
-  pose_update_kernel<<<nblk(n * J, 128), 128, 0, (cudaStream_t)stream>>>(pos, vel, rot, ang, off_pos, off_vel, off_rot,
+  launch_k(pose_update_kernel, nblk(n * J, 128), 128, 0, (cudaStream_t)stream, pos, vel, rot, ang, off_pos, off_vel, off_rot,
                                                                         off_ang, in_pos, in_vel, in_rot, in_ang,
                                                                         tr_src_pos, tr_src_rot, tr_dst_pos, tr_dst_rot,
                                                                         halflife, dt, n, J);
@@ -905,6 +922,8 @@ template <typename T> __device__ __forceinline__ T clamp1(T x) { return x < (T)-
 template <typename T>
 __global__ void quat_op_kernel(int op, const T* __restrict__ a, const T* __restrict__ b, long long n, T param,
                                T* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const QuatOpWidths w = quat_op_widths(op);
@@ -1027,6 +1046,8 @@ template <typename T>
 __global__ void fk_chain_kernel(const T* __restrict__ start_pos, const T* __restrict__ start_rot, int has_start,
                                 const T* __restrict__ lpos, const T* __restrict__ lrot, long long n, int m,
                                 T* __restrict__ gpos, T* __restrict__ grot) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   V3<T> pp = v3<T>((T)0, (T)0, (T)0);
@@ -1061,9 +1082,9 @@ extern "C" int mocha_quat_op(int op, int is_f64, const void* a, const void* b, l
   MOCHA_CHECK_ARG(a && out && n > 0 && (w.b == 0 || b), "mocha_quat_op: null/empty argument");
   const unsigned grid = (unsigned)((n + 127) / 128);
   if (is_f64)
-    quat_op_kernel<double><<<grid, 128, 0, (cudaStream_t)stream>>>(op, (const double*)a, (const double*)b, n, param, (double*)out);
+    launch_k(quat_op_kernel<double>, grid, 128, 0, (cudaStream_t)stream, op, (const double*)a, (const double*)b, n, param, (double*)out);
   else
-    quat_op_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>(op, (const float*)a, (const float*)b, n, (float)param, (float*)out);
+    launch_k(quat_op_kernel<float>, grid, 128, 0, (cudaStream_t)stream, op, (const float*)a, (const float*)b, n, (float)param, (float*)out);
   count_launch();
   MOCHA_LAUNCH_CHECK("quat_op_kernel");
   return MOCHA_OK;
@@ -1076,11 +1097,11 @@ extern "C" int mocha_fk_chain(int is_f64, const void* start_pos, const void* sta
   const unsigned grid = (unsigned)((n + 63) / 64);
   const int hs = start_pos != nullptr;
   if (is_f64)
-    fk_chain_kernel<double><<<grid, 64, 0, (cudaStream_t)stream>>>((const double*)start_pos, (const double*)start_rot, hs,
+    launch_k(fk_chain_kernel<double>, grid, 64, 0, (cudaStream_t)stream, (const double*)start_pos, (const double*)start_rot, hs,
                                                                     (const double*)lpos, (const double*)lrot, n, m,
                                                                     (double*)gpos, (double*)grot);
   else
-    fk_chain_kernel<float><<<grid, 64, 0, (cudaStream_t)stream>>>((const float*)start_pos, (const float*)start_rot, hs,
+    launch_k(fk_chain_kernel<float>, grid, 64, 0, (cudaStream_t)stream, (const float*)start_pos, (const float*)start_rot, hs,
                                                                    (const float*)lpos, (const float*)lrot, n, m, (float*)gpos,
                                                                    (float*)grot);
   count_launch();

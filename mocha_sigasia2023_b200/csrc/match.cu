@@ -24,6 +24,8 @@ template <int RB, int QB>
 __global__ void __launch_bounds__(256)
 match_exact_tile_kernel(const float* __restrict__ Q, int nq, const float* __restrict__ DB, long long N, int D,
                         double* __restrict__ dist2) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double red[8][RB * QB];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row0 = (long long)blockIdx.x * RB;
@@ -156,6 +158,8 @@ __device__ __forceinline__ void local_insert(T (&ls)[KMAX], I (&li)[KMAX], int k
 __global__ void __launch_bounds__(256)
 topk_rows_kernel(const double* __restrict__ dist2, long long N, int k, long long index_offset,
                  int64_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double red_d[8]; __shared__ long long red_i[8]; __shared__ int red_t[8];
   __shared__ double od[KMAX]; __shared__ long long oi[KMAX];
   const int q = blockIdx.x;
@@ -177,6 +181,8 @@ match_rerank_kernel(const float* __restrict__ Q, const __nv_bfloat16* __restrict
                     const float* __restrict__ DB32, int D, const float* __restrict__ cand_score,
                     const int32_t* __restrict__ cand_idx, int ncand, int kc, int k, long long index_offset,
                     int64_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double red_d[8]; __shared__ long long red_i[8]; __shared__ int red_t[8];
   __shared__ double od[KMAX]; __shared__ long long oi[KMAX];
   __shared__ double exact[KMAX];
@@ -383,6 +389,8 @@ match_rerank_kernel(const float* __restrict__ Q, const __nv_bfloat16* __restrict
 __global__ void __launch_bounds__(256)
 db_pack_kernel(const float* __restrict__ rows, long long N, int D, __nv_bfloat16* __restrict__ rows16,
                float* __restrict__ norm) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * 8 + warp;
   if (r >= N) return;
@@ -402,6 +410,8 @@ db_pack_kernel(const float* __restrict__ rows, long long N, int D, __nv_bfloat16
 // thread per query: merge nshard sorted (dist, idx) lists of length k
 __global__ void topk_merge_kernel(const double* __restrict__ dist, const int64_t* __restrict__ idx, int nshard,
                                   int nq, int k, double* __restrict__ out_dist, int64_t* __restrict__ out_idx) {
+  pdl_trigger();
+  pdl_wait();
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nq) return;
   int head[64];
@@ -444,12 +454,12 @@ extern "C" int mocha_match_exact(const float* Q, int nq, const float* DB, long l
   cudaStream_t s = (cudaStream_t)stream;
   MOCHA_CHECK_ARG(N <= 2147483647LL && (nq + EXQ - 1) / EXQ <= 65535, "mocha_match_exact: problem too large for the exact kernel (use mocha_match_tc)");
   if (nq >= 16 && N >= 64)
-    match_exact_tile_kernel<8, 8><<<dim3((unsigned)((N + 7) / 8), (unsigned)((nq + 7) / 8)), 256, 0, s>>>(Q, nq, DB, N, D, dist2);
+    launch_k(match_exact_tile_kernel<8, 8>, dim3((unsigned)((N + 7) / 8), (unsigned)((nq + 7) / 8)), 256, 0, s, Q, nq, DB, N, D, dist2);
   else
-    match_exact_tile_kernel<1, EXQ><<<dim3((unsigned)N, (unsigned)((nq + EXQ - 1) / EXQ)), 256, 0, s>>>(Q, nq, DB, N, D, dist2);
+    launch_k(match_exact_tile_kernel<1, EXQ>, dim3((unsigned)N, (unsigned)((nq + EXQ - 1) / EXQ)), 256, 0, s, Q, nq, DB, N, D, dist2);
   count_launch();
   MOCHA_LAUNCH_CHECK("match_exact_tile_kernel");
-  topk_rows_kernel<<<nq, 256, 0, s>>>(dist2, N, k, index_offset, idx, dist);
+  launch_k(topk_rows_kernel, nq, 256, 0, s, dist2, N, k, index_offset, idx, dist);
   count_launch();
   MOCHA_LAUNCH_CHECK("topk_rows_kernel");
   return MOCHA_OK;
@@ -483,7 +493,7 @@ extern "C" int mocha_match_tc(const float* Q, const void* Q16, int nq, const voi
       return set_error(MOCHA_ERR_WORKSPACE, "mocha_match_tc: workspace too small (%zu B given, %zu B needed)",
                        workspace_bytes, ws.off);
     MOCHA_TRY(tc_match_coarse_splitk((const __nv_bfloat16*)Q16, nq, (const __nv_bfloat16*)DB16, dbnorm, N, D, partial, cs, ci, s));
-    match_rerank_kernel<<<nq, 256, 0, s>>>(Q, (const __nv_bfloat16*)DB16, DB32, D, cs, ci, (int)np, kc, k, index_offset,
+    launch_k(match_rerank_kernel, nq, 256, 0, s, Q, (const __nv_bfloat16*)DB16, DB32, D, cs, ci, (int)np, kc, k, index_offset,
                                            idx, dist);
     count_launch();
     MOCHA_LAUNCH_CHECK("match_rerank_kernel");
@@ -500,7 +510,7 @@ extern "C" int mocha_match_tc(const float* Q, const void* Q16, int nq, const voi
     MOCHA_TRY(tc_match_coarse((const __nv_bfloat16*)Q16, nq, (const __nv_bfloat16*)DB16, dbnorm, N, D, kc, cs, ci, s));
   else  // fp32-storage DB: TF32 tensor-core pass straight from the fp32 rows
     MOCHA_TRY(tc_match_coarse_tf32(Q, nq, DB32, dbnorm, N, D, kc, cs, ci, s));
-  match_rerank_kernel<<<nq, 256, 0, s>>>(Q, (const __nv_bfloat16*)DB16, DB32, D, cs, ci, (int)ncand, kc, k,
+  launch_k(match_rerank_kernel, nq, 256, 0, s, Q, (const __nv_bfloat16*)DB16, DB32, D, cs, ci, (int)ncand, kc, k,
                                          index_offset, idx, dist);
   count_launch();
   MOCHA_LAUNCH_CHECK("match_rerank_kernel");
@@ -510,7 +520,7 @@ extern "C" int mocha_match_tc(const float* Q, const void* Q16, int nq, const voi
 extern "C" int mocha_db_pack_bf16(const float* rows, long long N, int D, void* rows16, float* norm,
                                   mocha_stream_t stream) {
   MOCHA_CHECK_ARG(rows && rows16 && N > 0 && D > 0, "mocha_db_pack_bf16: bad argument");
-  db_pack_kernel<<<(unsigned)((N + 7) / 8), 256, 0, (cudaStream_t)stream>>>(rows, N, D, (__nv_bfloat16*)rows16, norm);
+  launch_k(db_pack_kernel, (unsigned)((N + 7) / 8), 256, 0, (cudaStream_t)stream, rows, N, D, (__nv_bfloat16*)rows16, norm);
   count_launch();
   MOCHA_LAUNCH_CHECK("db_pack_kernel");
   return MOCHA_OK;
@@ -518,6 +528,8 @@ extern "C" int mocha_db_pack_bf16(const float* rows, long long N, int D, void* r
 
 // squared norms of fp32 rows (dbnorm for the fp32-storage / TF32 matcher)
 __global__ void __launch_bounds__(256) row_norm_kernel(const float* __restrict__ rows, long long N, int D, float* __restrict__ norm) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * 8 + warp;
   if (r >= N) return;
@@ -530,7 +542,7 @@ __global__ void __launch_bounds__(256) row_norm_kernel(const float* __restrict__
 
 extern "C" int mocha_db_norms_f32(const float* rows, long long N, int D, float* norm, mocha_stream_t stream) {
   MOCHA_CHECK_ARG(rows && norm && N > 0 && D > 0, "mocha_db_norms_f32: bad argument");
-  row_norm_kernel<<<(unsigned)((N + 7) / 8), 256, 0, (cudaStream_t)stream>>>(rows, N, D, norm);
+  launch_k(row_norm_kernel, (unsigned)((N + 7) / 8), 256, 0, (cudaStream_t)stream, rows, N, D, norm);
   count_launch();
   MOCHA_LAUNCH_CHECK("row_norm_kernel");
   return MOCHA_OK;
@@ -540,7 +552,7 @@ extern "C" int mocha_topk_merge(const double* dist, const int64_t* idx, int nsha
                                 int64_t* out_idx, mocha_stream_t stream) {
   MOCHA_CHECK_ARG(dist && idx && out_idx, "mocha_topk_merge: null argument");
   MOCHA_CHECK_ARG(nshard >= 1 && nshard <= 64 && nq > 0 && k >= 1 && k <= KMAX, "mocha_topk_merge: bad sizes");
-  topk_merge_kernel<<<(nq + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dist, idx, nshard, nq, k, out_dist, out_idx);
+  launch_k(topk_merge_kernel, (nq + 127) / 128, 128, 0, (cudaStream_t)stream, dist, idx, nshard, nq, k, out_dist, out_idx);
   count_launch();
   MOCHA_LAUNCH_CHECK("topk_merge_kernel");
   return MOCHA_OK;
@@ -573,6 +585,8 @@ __global__ void __launch_bounds__(256)
 topk_exchange_merge_kernel(const double* __restrict__ ld, const long long* __restrict__ li, int nq, int k, int rank,
                            int world, XchgPtrs peers, unsigned epoch, double* __restrict__ out_d,
                            long long* __restrict__ out_i) {
+  pdl_trigger();
+  pdl_wait();
   const unsigned parity = epoch & 1u;
   const size_t list = (size_t)nq * k;                      // elements per list
   const size_t half_bytes = (list * 8 + 15) & ~(size_t)15; // each array starts 16 B aligned (uint4 stores), odd lists too
@@ -682,8 +696,7 @@ extern "C" int mocha_topk_exchange_merge(const double* d_local_dist, const int64
     MOCHA_CHECK_ARG(d_peer_bufs[p], "mocha_topk_exchange_merge: peer buffer %d is null", p);
     peers.buf[p] = static_cast<unsigned char*>(d_peer_bufs[p]);
   }
-  topk_exchange_merge_kernel<<<XCHG_BLOCKS, 256, 0, (cudaStream_t)stream>>>(
-      d_local_dist, reinterpret_cast<const long long*>(d_local_idx), nq, k, rank, world, peers, epoch, d_out_dist,
+  launch_k(topk_exchange_merge_kernel, XCHG_BLOCKS, 256, 0, (cudaStream_t)stream, d_local_dist, reinterpret_cast<const long long*>(d_local_idx), nq, k, rank, world, peers, epoch, d_out_dist,
       reinterpret_cast<long long*>(d_out_idx));
   count_launch();
   MOCHA_LAUNCH_CHECK("topk_exchange_merge_kernel");

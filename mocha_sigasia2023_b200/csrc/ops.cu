@@ -10,6 +10,8 @@ namespace {
 __global__ void graph_agg_first_kernel(const float* __restrict__ in, const float* __restrict__ A,
                                        float* __restrict__ out, __nv_bfloat16* __restrict__ out16, int V, int C,
                                        int Kk, int lrelu) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   float* xs = sm;                                   // [V][C]
   float* val = sm + V * C;                          // [Kk*V][V] non-zero values
@@ -65,6 +67,8 @@ __global__ void __launch_bounds__(256)
 embed_graph_agg_kernel(const float* __restrict__ X, const float* __restrict__ Wemb, const float* __restrict__ bemb,
                        const float* __restrict__ A, __nv_bfloat16* __restrict__ out16, int BT, int V, int Cin, int C,
                        int Kk, int ldo) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   float* xs = sm;                                     // [G*V][C]   activated h0
   float* xin = xs + G * V * C;                        // [G*V][16]  raw inputs, rows padded to 16 floats
@@ -157,6 +161,8 @@ embed_graph_agg_kernel(const float* __restrict__ X, const float* __restrict__ We
 
 __global__ void graph_agg_kv_kernel(const float* __restrict__ in, const float* __restrict__ A2,
                                     float* __restrict__ out, int U, int Wn, int C, int Kk) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   const int KC = Kk * C;
   float* xs = sm;               // [U][Kk*C]
@@ -182,6 +188,8 @@ __global__ void graph_agg_kv_kernel(const float* __restrict__ in, const float* _
 constexpr int POOL_MAXP = 8;
 __global__ void pool_joint_body_kernel(const float* __restrict__ in, const float* __restrict__ Wp,
                                        float* __restrict__ out, int T, int V, int P, int C, int tp) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float ws[];  // [V][P]
   for (int i = threadIdx.x; i < V * P; i += blockDim.x) ws[i] = Wp[i];
   __syncthreads();
@@ -215,6 +223,8 @@ __global__ void pool_joint_body_kernel(const float* __restrict__ in, const float
 __global__ void __launch_bounds__(128)
 pool_graph_agg_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ Wp, const float* __restrict__ A,
                       __nv_bfloat16* __restrict__ out16, int T, int V, int P, int C, int tp, int Kk) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float ws[];
   float* As = ws;                                   // [Kk][P][P] adjacency
   float* mw = As + Kk * P * P;                      // [P][V] member weights of each body part (compact)
@@ -293,6 +303,8 @@ instance_norm_tokens_kernel(const float* __restrict__ x, int n, int C, float eps
                             const float* __restrict__ tab_std, float* __restrict__ y2,
                             __nv_bfloat16* __restrict__ y16, __nv_bfloat16* __restrict__ y2h,
                             const float* __restrict__ y2h_center) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float part[8][32];
   __shared__ float stat[2][32];
   const int b = blockIdx.x, c = blockIdx.y * 32 + (threadIdx.x & 31), warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -354,6 +366,8 @@ instance_norm_tokens_reg_kernel(const float* __restrict__ x, int n, int C, float
                                 const float* __restrict__ tab_std, float* __restrict__ y2,
                                 __nv_bfloat16* __restrict__ y16, __nv_bfloat16* __restrict__ y2h,
                             const float* __restrict__ y2h_center) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float part[8][32];
   __shared__ float stat[2][32];
   const int b = blockIdx.x, c = blockIdx.y * 32 + (threadIdx.x & 31), warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -424,6 +438,8 @@ instance_norm_tokens_reg_kernel(const float* __restrict__ x, int n, int C, float
 __global__ void __launch_bounds__(256)
 instance_norm_tokens_v4_kernel(const float* __restrict__ x, int n, int C, float eps, const float* __restrict__ gb,
                                float* __restrict__ y, __nv_bfloat16* __restrict__ y16, __nv_bfloat16* __restrict__ q16) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float4 part[16][16];
   __shared__ float4 stat[2][16];
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -508,6 +524,8 @@ instance_norm_tokens_v4_kernel(const float* __restrict__ x, int n, int C, float 
 }
 
 __global__ void token_mean_kernel(const float* __restrict__ x, int n, int C, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   const float* xb = x + (long long)b * n * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -519,6 +537,8 @@ __global__ void token_mean_kernel(const float* __restrict__ x, int n, int C, flo
 
 constexpr int SM_MAXPL = 8;  // up to 256 columns per row
 __global__ void softmax_rows_kernel(float* __restrict__ S, long long rows, int ncols, float scale) {
+  pdl_trigger();
+  pdl_wait();
   const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * warps + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -553,6 +573,8 @@ __global__ void add_layernorm_kernel(const float* __restrict__ x, const float* _
                                      float* __restrict__ y, long long rows, int C, float eps,
                                      const float* __restrict__ tab_mean, const float* __restrict__ tab_std,
                                      int period, float* __restrict__ y2, __nv_bfloat16* __restrict__ y16) {
+  pdl_trigger();
+  pdl_wait();
   const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * warps + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -594,6 +616,8 @@ add_layernorm_reg_kernel(const float* __restrict__ x, const float* __restrict__ 
                          const float* __restrict__ b, float* __restrict__ y, long long rows, float eps,
                          const float* __restrict__ tab_mean, const float* __restrict__ tab_std, int period,
                          float* __restrict__ y2, __nv_bfloat16* __restrict__ y16) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int C = 128 * NJ;
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -638,6 +662,8 @@ __global__ void cvae_prior_tokens_kernel(const float* __restrict__ mu_token, con
                                          const float* __restrict__ cond, const float* __restrict__ pe,
                                          float* __restrict__ tok, __nv_bfloat16* __restrict__ tok16, int ncond, int C,
                                          long long total) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int n = ncond + 2;
@@ -658,6 +684,8 @@ __global__ void cvae_memory_kernel(const float* __restrict__ prior_out, int prio
                                    float* __restrict__ mem, __nv_bfloat16* __restrict__ mem16,
                                    float* __restrict__ mu_out, float* __restrict__ lv_out, int ncond, int C,
                                    long long total) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int n = ncond + 1;
@@ -684,6 +712,8 @@ __global__ void cvae_condition_kernel(const float* __restrict__ src_cnt, const f
                                       const float* __restrict__ m0, const float* __restrict__ s0,
                                       const float* __restrict__ m1, const float* __restrict__ s1,
                                       float* __restrict__ cond, int n, int C, long long total) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const long long per = (long long)n * C;
@@ -699,6 +729,8 @@ __global__ void cvae_prior_tokens_v4_kernel(const float4* __restrict__ mu_token,
                                             const float4* __restrict__ cond, const float4* __restrict__ pe,
                                             float4* __restrict__ tok, __nv_bfloat16* __restrict__ tok16, unsigned ncond,
                                             unsigned C4, unsigned total4) {
+  pdl_trigger();
+  pdl_wait();
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const unsigned n = ncond + 2;
@@ -716,6 +748,8 @@ __global__ void cvae_memory_v4_kernel(const float4* __restrict__ prior_out, unsi
                                       float4* __restrict__ mem, __nv_bfloat16* __restrict__ mem16,
                                       float4* __restrict__ mu_out, float4* __restrict__ lv_out, unsigned ncond, unsigned C4,
                                       unsigned total4) {
+  pdl_trigger();
+  pdl_wait();
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const unsigned n = ncond + 1;
@@ -744,6 +778,8 @@ __global__ void cvae_condition_v4_kernel(const float4* __restrict__ src_cnt, con
                                          const float4* __restrict__ m0, const float4* __restrict__ s0,
                                          const float4* __restrict__ m1, const float4* __restrict__ s1,
                                          float4* __restrict__ cond, unsigned per4, unsigned total4) {
+  pdl_trigger();
+  pdl_wait();
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const unsigned b = i / (2 * per4);
@@ -758,6 +794,8 @@ __global__ void cvae_condition_v4_kernel(const float4* __restrict__ src_cnt, con
 __global__ void affine_rows_kernel(const float* __restrict__ x, const float* __restrict__ mu,
                                    const float* __restrict__ sd, float* __restrict__ out, long long total,
                                    int C, int period, int ld_in, float* __restrict__ copy) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const long long o = i % ((long long)period * C);
@@ -769,6 +807,8 @@ __global__ void affine_rows_kernel(const float* __restrict__ x, const float* __r
 
 __global__ void broadcast_rows_kernel(const float* __restrict__ x, float* __restrict__ out,
                                       __nv_bfloat16* __restrict__ out16, long long n_elems, long long total) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const float v = x[i % n_elems];
@@ -778,12 +818,16 @@ __global__ void broadcast_rows_kernel(const float* __restrict__ x, float* __rest
 
 __global__ void add_table_kernel(const float* __restrict__ a, const float* __restrict__ table,
                                  float* __restrict__ out, long long total, int C, int period) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   out[i] = a[i] + table[i % ((long long)period * C)];
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     const float4 v = *reinterpret_cast<const float4*>(x + i);
@@ -801,6 +845,8 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16*
 __global__ void gather_token_rows_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ x16, int n,
                                          int take, int C, long long total, float* __restrict__ out,
                                          __nv_bfloat16* __restrict__ out16) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c = (int)(i % C);
@@ -821,7 +867,7 @@ int graph_agg_first(const float* in, const float* A, float* out, int BT, int V, 
   MOCHA_CHECK_ARG(C <= 256, "graph_agg_first: C=%d > 256 unsupported", C);
   size_t smem = (size_t)(V * C + 2 * Kk * V * V + Kk * V) * sizeof(float);
   MOCHA_CHECK_ARG(smem <= 48 * 1024, "graph_agg_first: tile too large (%zu B)", smem);
-  graph_agg_first_kernel<<<BT, 256, smem, s>>>(in, A, out, out16, V, C, Kk, lrelu);
+  launch_k(graph_agg_first_kernel, BT, 256, smem, s, in, A, out, out16, V, C, Kk, lrelu);
   count_launch();
   MOCHA_LAUNCH_CHECK("graph_agg_first");
   return MOCHA_OK;
@@ -845,7 +891,7 @@ int embed_graph_agg(const float* X, const float* Wemb, const float* bemb, const 
       MOCHA_CUDA(cudaFuncSetAttribute(embed_graph_agg_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  embed_graph_agg_kernel<G><<<(BT + G - 1) / G, 256, smem, s>>>(X, Wemb, bemb, A, out16, BT, V, Cin, C, Kk, ldo);
+  launch_k(embed_graph_agg_kernel<G>, (BT + G - 1) / G, 256, smem, s, X, Wemb, bemb, A, out16, BT, V, Cin, C, Kk, ldo);
   count_launch();
   MOCHA_LAUNCH_CHECK("embed_graph_agg");
   return MOCHA_OK;
@@ -858,6 +904,8 @@ int embed_graph_agg(const float* X, const float* Wemb, const float* bemb, const 
 __global__ void __launch_bounds__(256)
 graph_agg_kv_pad16_kernel(const float* __restrict__ in, const float* __restrict__ A2, __nv_bfloat16* __restrict__ out16,
                           int Ts, int tdiv, int pad, int U, int Wn, int C, int Kk) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   const int KC = Kk * C, KU = Kk * U;
   float* xs = sm;                                   // [U][Kk*C]
@@ -915,6 +963,8 @@ graph_agg_kv_pad16_kernel(const float* __restrict__ in, const float* __restrict_
 
 // reflect-pad borders of a [B, T + 2*pad, V*C] bf16 tensor whose interior rows are already written
 __global__ void reflect_border_kernel(__nv_bfloat16* __restrict__ xp, int T, int pad, long long row8, long long total8) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total8) return;
   const long long e = i % row8;
@@ -932,7 +982,7 @@ __global__ void reflect_border_kernel(__nv_bfloat16* __restrict__ xp, int T, int
 int reflect_border_fill(__nv_bfloat16* xp, int B, int T, int pad, long long row_elems, cudaStream_t s) {
   MOCHA_CHECK_ARG(xp && B > 0 && T > pad && pad > 0 && row_elems % 8 == 0, "reflect_border_fill: bad args");
   const long long row8 = row_elems / 8, total8 = (long long)B * 2 * pad * row8;
-  reflect_border_kernel<<<blocks_for(total8, 256), 256, 0, s>>>(xp, T, pad, row8, total8);
+  launch_k(reflect_border_kernel, blocks_for(total8, 256), 256, 0, s, xp, T, pad, row8, total8);
   count_launch();
   MOCHA_LAUNCH_CHECK("reflect_border_fill");
   return MOCHA_OK;
@@ -943,7 +993,7 @@ int graph_agg_kv(const float* in, const float* A2, float* out, int BT, int U, in
   MOCHA_CHECK_ARG(in && A2 && out && BT > 0 && U > 0 && Wn > 0 && C > 0 && Kk > 0, "graph_agg_kv: bad args");
   size_t smem = (size_t)(U * Kk * C + Kk * U * Wn) * sizeof(float);
   MOCHA_CHECK_ARG(smem <= 48 * 1024, "graph_agg_kv: tile too large (%zu B)", smem);
-  graph_agg_kv_kernel<<<BT, 256, smem, s>>>(in, A2, out, U, Wn, C, Kk);
+  launch_k(graph_agg_kv_kernel, BT, 256, smem, s, in, A2, out, U, Wn, C, Kk);
   count_launch();
   MOCHA_LAUNCH_CHECK("graph_agg_kv");
   return MOCHA_OK;
@@ -957,7 +1007,7 @@ int graph_agg_kv_pad16(const float* in, const float* A2, __nv_bfloat16* out16, i
   MOCHA_CHECK_ARG(tdiv + 2 * pad <= 16 && pad < Ts * tdiv, "graph_agg_kv_pad16: tdiv / pad too large");
   const size_t smem = (size_t)(U * Kk * C + 2 * Kk * U * Wn + Wn) * sizeof(float);
   MOCHA_CHECK_ARG(smem <= 48 * 1024, "graph_agg_kv_pad16: tile too large (%zu B)", smem);
-  graph_agg_kv_pad16_kernel<<<B * Ts, 256, smem, s>>>(in, A2, out16, Ts, tdiv, pad, U, Wn, C, Kk);
+  launch_k(graph_agg_kv_pad16_kernel, B * Ts, 256, smem, s, in, A2, out16, Ts, tdiv, pad, U, Wn, C, Kk);
   count_launch();
   MOCHA_LAUNCH_CHECK("graph_agg_kv_pad16");
   return MOCHA_OK;
@@ -968,7 +1018,7 @@ int pool_joint_body(const float* in, const float* Wp, float* out, int B, int T, 
   MOCHA_CHECK_ARG(in && Wp && out && B > 0 && T > 0 && V > 0 && C > 0, "pool_joint_body: bad args");
   MOCHA_CHECK_ARG(P > 0 && P <= POOL_MAXP, "pool_joint_body: P=%d unsupported (max %d)", P, POOL_MAXP);
   MOCHA_CHECK_ARG(tp > 0 && T % tp == 0, "pool_joint_body: T=%d not a multiple of tp=%d", T, tp);
-  pool_joint_body_kernel<<<B * (T / tp), 256, (size_t)V * P * sizeof(float), s>>>(in, Wp, out, T, V, P, C, tp);
+  launch_k(pool_joint_body_kernel, B * (T / tp), 256, (size_t)V * P * sizeof(float), s, in, Wp, out, T, V, P, C, tp);
   count_launch();
   MOCHA_LAUNCH_CHECK("pool_joint_body");
   return MOCHA_OK;
@@ -980,7 +1030,7 @@ int pool_graph_agg(const __nv_bfloat16* in, const float* Wp, const float* A, __n
   MOCHA_CHECK_ARG(P > 0 && P <= POOL_MAXP, "pool_graph_agg: P=%d unsupported (max %d)", P, POOL_MAXP);
   MOCHA_CHECK_ARG(tp > 0 && T % tp == 0, "pool_graph_agg: T=%d not a multiple of tp=%d", T, tp);
   const size_t smem = (size_t)(Kk * P * P + 2 * P * V + P) * sizeof(float);
-  pool_graph_agg_kernel<<<B * (T / tp), 128, smem, s>>>(in, Wp, A, out16, T, V, P, C, tp, Kk);
+  launch_k(pool_graph_agg_kernel, B * (T / tp), 128, smem, s, in, Wp, A, out16, T, V, P, C, tp, Kk);
   count_launch();
   MOCHA_LAUNCH_CHECK("pool_graph_agg");
   return MOCHA_OK;
@@ -995,11 +1045,11 @@ int instance_norm_tokens(const float* x, int B, int n, int C, float eps, const f
   const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gb)) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(y16) & 7) == 0;
   if (n <= 128 && y16 && !y2 && !y2h && (C % 64) == 0 && al)   // tensor-core path (bf16 twin requested): float4 kernel
-    instance_norm_tokens_v4_kernel<<<dim3(B, C / 64), 256, 0, s>>>(x, n, C, eps, gb, y, y16, nullptr);
+    launch_k(instance_norm_tokens_v4_kernel, dim3(B, C / 64), 256, 0, s, x, n, C, eps, gb, y, y16, nullptr);
   else if (n <= 128)
-    instance_norm_tokens_reg_kernel<<<dim3(B, (C + 31) / 32), 256, 0, s>>>(x, n, C, eps, gb, y, tab_mean, tab_std, y2, y16, y2h, y2h_center);
+    launch_k(instance_norm_tokens_reg_kernel, dim3(B, (C + 31) / 32), 256, 0, s, x, n, C, eps, gb, y, tab_mean, tab_std, y2, y16, y2h, y2h_center);
   else
-    instance_norm_tokens_kernel<<<dim3(B, (C + 31) / 32), 256, 0, s>>>(x, n, C, eps, gb, y, tab_mean, tab_std, y2, y16, y2h, y2h_center);
+    launch_k(instance_norm_tokens_kernel, dim3(B, (C + 31) / 32), 256, 0, s, x, n, C, eps, gb, y, tab_mean, tab_std, y2, y16, y2h, y2h_center);
   count_launch();
   MOCHA_LAUNCH_CHECK("instance_norm_tokens");
   return MOCHA_OK;
@@ -1010,7 +1060,7 @@ int adain_norm_tokens(const float* x, int B, int n, int C, float eps, const floa
   MOCHA_CHECK_ARG(x && gb && y && q16 && B > 0 && n > 1 && n <= 128 && (C % 64) == 0, "adain_norm_tokens: bad args");
   MOCHA_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gb)) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(q16) & 7) == 0, "adain_norm_tokens: operands must be 16 B aligned");
-  instance_norm_tokens_v4_kernel<<<dim3(B, C / 64), 256, 0, s>>>(x, n, C, eps, gb, y, nullptr, q16);
+  launch_k(instance_norm_tokens_v4_kernel, dim3(B, C / 64), 256, 0, s, x, n, C, eps, gb, y, nullptr, q16);
   count_launch();
   MOCHA_LAUNCH_CHECK("adain_norm_tokens");
   return MOCHA_OK;
@@ -1018,7 +1068,7 @@ int adain_norm_tokens(const float* x, int B, int n, int C, float eps, const floa
 
 int token_mean(const float* x, int B, int n, int C, float* out, cudaStream_t s) {
   MOCHA_CHECK_ARG(x && out && B > 0 && n > 0 && C > 0, "token_mean: bad args");
-  token_mean_kernel<<<B, 256, 0, s>>>(x, n, C, out);
+  launch_k(token_mean_kernel, B, 256, 0, s, x, n, C, out);
   count_launch();
   MOCHA_LAUNCH_CHECK("token_mean");
   return MOCHA_OK;
@@ -1027,7 +1077,7 @@ int token_mean(const float* x, int B, int n, int C, float* out, cudaStream_t s) 
 int softmax_rows(float* S, long long rows, int ncols, float scale, cudaStream_t s) {
   MOCHA_CHECK_ARG(S && rows > 0 && ncols > 0, "softmax_rows: bad args");
   MOCHA_CHECK_ARG(ncols <= 32 * SM_MAXPL, "softmax_rows: ncols=%d > %d", ncols, 32 * SM_MAXPL);
-  softmax_rows_kernel<<<blocks_for(rows, 8), 256, 0, s>>>(S, rows, ncols, scale);
+  launch_k(softmax_rows_kernel, blocks_for(rows, 8), 256, 0, s, S, rows, ncols, scale);
   count_launch();
   MOCHA_LAUNCH_CHECK("softmax_rows");
   return MOCHA_OK;
@@ -1042,13 +1092,13 @@ int add_layernorm(const float* x, const float* r, const float* g, const float* b
   const bool vec = aligned16(x) && aligned16(r) && aligned16(g) && aligned16(b) && aligned16(y) && aligned16(y2) &&
                    aligned16(tab_mean) && aligned16(tab_std) && (reinterpret_cast<uintptr_t>(y16) & 7) == 0;
   if (vec && C == 256)
-    add_layernorm_reg_kernel<2><<<blocks_for(rows, 8), 256, 0, s>>>(x, r, g, b, y, rows, eps, tab_mean, tab_std, period, y2, y16);
+    launch_k(add_layernorm_reg_kernel<2>, blocks_for(rows, 8), 256, 0, s, x, r, g, b, y, rows, eps, tab_mean, tab_std, period, y2, y16);
   else if (vec && C == 128)
-    add_layernorm_reg_kernel<1><<<blocks_for(rows, 8), 256, 0, s>>>(x, r, g, b, y, rows, eps, tab_mean, tab_std, period, y2, y16);
+    launch_k(add_layernorm_reg_kernel<1>, blocks_for(rows, 8), 256, 0, s, x, r, g, b, y, rows, eps, tab_mean, tab_std, period, y2, y16);
   else if (vec && C == 512)
-    add_layernorm_reg_kernel<4><<<blocks_for(rows, 8), 256, 0, s>>>(x, r, g, b, y, rows, eps, tab_mean, tab_std, period, y2, y16);
+    launch_k(add_layernorm_reg_kernel<4>, blocks_for(rows, 8), 256, 0, s, x, r, g, b, y, rows, eps, tab_mean, tab_std, period, y2, y16);
   else
-    add_layernorm_kernel<<<blocks_for(rows, 8), 256, 0, s>>>(x, r, g, b, y, rows, C, eps, tab_mean, tab_std,
+    launch_k(add_layernorm_kernel, blocks_for(rows, 8), 256, 0, s, x, r, g, b, y, rows, C, eps, tab_mean, tab_std,
                                                             period, y2, y16);
   count_launch();
   MOCHA_LAUNCH_CHECK("add_layernorm");
@@ -1063,15 +1113,14 @@ int cvae_prior_tokens(const float* mu_token, const float* logvar_token, const fl
   if ((C & 3) == 0 && total < (1LL << 31) && aligned16(mu_token) && aligned16(logvar_token) && aligned16(cond) &&
       aligned16(pe) && aligned16(tok) && (!tok16 || (reinterpret_cast<uintptr_t>(tok16) & 7) == 0)) {
     const unsigned total4 = (unsigned)(total / 4);
-    cvae_prior_tokens_v4_kernel<<<(total4 + 255) / 256, 256, 0, s>>>(
-        reinterpret_cast<const float4*>(mu_token), reinterpret_cast<const float4*>(logvar_token),
+    launch_k(cvae_prior_tokens_v4_kernel, (total4 + 255) / 256, 256, 0, s, reinterpret_cast<const float4*>(mu_token), reinterpret_cast<const float4*>(logvar_token),
         reinterpret_cast<const float4*>(cond), reinterpret_cast<const float4*>(pe), reinterpret_cast<float4*>(tok), tok16,
         (unsigned)ncond, (unsigned)(C / 4), total4);
     count_launch();
     MOCHA_LAUNCH_CHECK("cvae_prior_tokens");
     return MOCHA_OK;
   }
-  cvae_prior_tokens_kernel<<<blocks_for(total, 256), 256, 0, s>>>(mu_token, logvar_token, cond, pe, tok, tok16,
+  launch_k(cvae_prior_tokens_kernel, blocks_for(total, 256), 256, 0, s, mu_token, logvar_token, cond, pe, tok, tok16,
                                                                   ncond, C, total);
   count_launch();
   MOCHA_LAUNCH_CHECK("cvae_prior_tokens");
@@ -1086,15 +1135,14 @@ int cvae_memory(const float* prior_out, int prior_tokens, const float* eps, cons
   if ((C & 3) == 0 && total < (1LL << 31) && aligned16(prior_out) && aligned16(eps) && aligned16(cond) && aligned16(mem) &&
       aligned16(mu_out) && aligned16(logvar_out) && (reinterpret_cast<uintptr_t>(mem16) & 7) == 0) {
     const unsigned total4 = (unsigned)(total / 4);
-    cvae_memory_v4_kernel<<<(total4 + 255) / 256, 256, 0, s>>>(
-        reinterpret_cast<const float4*>(prior_out), (unsigned)prior_tokens, reinterpret_cast<const float4*>(eps),
+    launch_k(cvae_memory_v4_kernel, (total4 + 255) / 256, 256, 0, s, reinterpret_cast<const float4*>(prior_out), (unsigned)prior_tokens, reinterpret_cast<const float4*>(eps),
         reinterpret_cast<const float4*>(cond), reinterpret_cast<float4*>(mem), mem16, reinterpret_cast<float4*>(mu_out),
         reinterpret_cast<float4*>(logvar_out), (unsigned)ncond, (unsigned)(C / 4), total4);
     count_launch();
     MOCHA_LAUNCH_CHECK("cvae_memory");
     return MOCHA_OK;
   }
-  cvae_memory_kernel<<<blocks_for(total, 256), 256, 0, s>>>(prior_out, prior_tokens, eps, cond, mem, mem16, mu_out,
+  launch_k(cvae_memory_kernel, blocks_for(total, 256), 256, 0, s, prior_out, prior_tokens, eps, cond, mem, mem16, mu_out,
                                                             logvar_out, ncond, C, total);
   count_launch();
   MOCHA_LAUNCH_CHECK("cvae_memory");
@@ -1109,15 +1157,14 @@ int cvae_condition(const float* src_cnt, const float* prev, const float* m0, con
   if ((C & 3) == 0 && total < (1LL << 31) && aligned16(src_cnt) && aligned16(prev) && aligned16(m0) && aligned16(s0) &&
       aligned16(m1) && aligned16(s1) && aligned16(cond)) {
     const unsigned total4 = (unsigned)(total / 4);
-    cvae_condition_v4_kernel<<<(total4 + 255) / 256, 256, 0, s>>>(
-        reinterpret_cast<const float4*>(src_cnt), reinterpret_cast<const float4*>(prev), reinterpret_cast<const float4*>(m0),
+    launch_k(cvae_condition_v4_kernel, (total4 + 255) / 256, 256, 0, s, reinterpret_cast<const float4*>(src_cnt), reinterpret_cast<const float4*>(prev), reinterpret_cast<const float4*>(m0),
         reinterpret_cast<const float4*>(s0), reinterpret_cast<const float4*>(m1), reinterpret_cast<const float4*>(s1),
         reinterpret_cast<float4*>(cond), (unsigned)((long long)n * C / 4), total4);
     count_launch();
     MOCHA_LAUNCH_CHECK("cvae_condition");
     return MOCHA_OK;
   }
-  cvae_condition_kernel<<<blocks_for(total, 256), 256, 0, s>>>(src_cnt, prev, m0, s0, m1, s1, cond, n, C, total);
+  launch_k(cvae_condition_kernel, blocks_for(total, 256), 256, 0, s, src_cnt, prev, m0, s0, m1, s1, cond, n, C, total);
   count_launch();
   MOCHA_LAUNCH_CHECK("cvae_condition");
   return MOCHA_OK;
@@ -1127,7 +1174,7 @@ int affine_rows(const float* x, const float* mu, const float* sd, float* out, lo
                 cudaStream_t s, int ld_in, float* copy) {
   MOCHA_CHECK_ARG(x && (copy || (mu && sd && out)) && rows > 0 && C > 0 && period > 0, "affine_rows: bad args");
   const long long total = rows * C;
-  affine_rows_kernel<<<blocks_for(total, 256), 256, 0, s>>>(x, mu, sd, out, total, C, period, ld_in > 0 ? ld_in : C, copy);
+  launch_k(affine_rows_kernel, blocks_for(total, 256), 256, 0, s, x, mu, sd, out, total, C, period, ld_in > 0 ? ld_in : C, copy);
   count_launch();
   MOCHA_LAUNCH_CHECK("affine_rows");
   return MOCHA_OK;
@@ -1136,7 +1183,7 @@ int affine_rows(const float* x, const float* mu, const float* sd, float* out, lo
 int broadcast_rows(const float* x, float* out, int B, long long n_elems, cudaStream_t s, __nv_bfloat16* out16) {
   MOCHA_CHECK_ARG(x && out && B > 0 && n_elems > 0, "broadcast_rows: bad args");
   const long long total = (long long)B * n_elems;
-  broadcast_rows_kernel<<<blocks_for(total, 256), 256, 0, s>>>(x, out, out16, n_elems, total);
+  launch_k(broadcast_rows_kernel, blocks_for(total, 256), 256, 0, s, x, out, out16, n_elems, total);
   count_launch();
   MOCHA_LAUNCH_CHECK("broadcast_rows");
   return MOCHA_OK;
@@ -1146,7 +1193,7 @@ int add_table(const float* a, const float* table, float* out, long long rows, in
               cudaStream_t s) {
   MOCHA_CHECK_ARG(a && table && out && rows > 0 && C > 0 && period > 0, "add_table: bad args");
   const long long total = rows * C;
-  add_table_kernel<<<blocks_for(total, 256), 256, 0, s>>>(a, table, out, total, C, period);
+  launch_k(add_table_kernel, blocks_for(total, 256), 256, 0, s, a, table, out, total, C, period);
   count_launch();
   MOCHA_LAUNCH_CHECK("add_table");
   return MOCHA_OK;
@@ -1156,7 +1203,7 @@ int gather_token_rows(const float* x, const __nv_bfloat16* x16, int n, int take,
                       __nv_bfloat16* out16, cudaStream_t s) {
   MOCHA_CHECK_ARG(x && (out || out16) && n >= take && take > 0 && C > 0 && B > 0, "gather_token_rows: bad args");
   const long long total = (long long)B * take * C;
-  gather_token_rows_kernel<<<blocks_for(total, 256), 256, 0, s>>>(x, x16, n, take, C, total, out, out16);
+  launch_k(gather_token_rows_kernel, blocks_for(total, 256), 256, 0, s, x, x16, n, take, C, total, out, out16);
   count_launch();
   MOCHA_LAUNCH_CHECK("gather_token_rows");
   return MOCHA_OK;
@@ -1165,7 +1212,7 @@ int gather_token_rows(const float* x, const __nv_bfloat16* x16, int n, int take,
 int cast_f32_bf16(const float* x, __nv_bfloat16* y, long long n, cudaStream_t s) {
   MOCHA_CHECK_ARG(x && y && n > 0, "cast_f32_bf16: bad args");
   MOCHA_CHECK_ARG((((uintptr_t)x) & 15) == 0 && (((uintptr_t)y) & 7) == 0, "cast_f32_bf16: misaligned");
-  cast_f32_bf16_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, s>>>(x, y, n);
+  launch_k(cast_f32_bf16_kernel, blocks_for((n + 3) / 4, 256), 256, 0, s, x, y, n);
   count_launch();
   MOCHA_LAUNCH_CHECK("cast_f32_bf16");
   return MOCHA_OK;
