@@ -192,6 +192,18 @@ int mocha_cnt_features(const float* d_x, int B, int n, int C, float eps, float* 
                        const float* d_cnt_mean, const float* d_cnt_std, float* d_cnt_nm, void* d_cnt_nm16,
                        const float* d_cnt_nm16_center, mocha_stream_t stream);
 
+/* ---- fused transformer building blocks (bf16 operands, tcgen05; used by the bf16 stage bodies) ------- */
+/* Block tail of a transformer layer in ONE launch (net/transformer.py:23-34,:70-76; nn.TransformerEncoder/
+ * DecoderLayer of model_CVAE.py:70-79,:159-165), width 256:
+ *   Y = LN1?(A0 W0^T + b0 + R0);  Z = LN2?(Y + act(Y W1^T + b1) W2^T + b2)   (FFN skipped when Hd == 0)
+ * d_A0 bf16 [M,K0] (row pitch lda), d_W0 bf16 [256,K0], d_R0 fp32 [M,256] or NULL, d_W1 bf16 [Hd,256],
+ * d_W2 bf16 [256,Hd]; g/be pairs select the LayerNorms (NULL = none); act: 0 none, 1 ReLU, 2 GELU, 3 LeakyReLU.
+ * Outputs of the last stage: d_O32 fp32 and / or d_O16 bf16 [M,256]. K0 % 64 == 0, Hd % 128 == 0. */
+int mocha_block_tail(const void* d_A0, int lda, int K0, const void* d_W0, const float* d_b0, const float* d_R0,
+                     const float* d_g1, const float* d_be1, int Hd, int act, const void* d_W1, const float* d_b1,
+                     const void* d_W2, const float* d_b2, const float* d_g2, const float* d_be2, float eps,
+                     float* d_O32, void* d_O16, int M, mocha_stream_t stream);
+
 /* ---- (a8) Generator.decoder = Transformer(adain=True)  transformer.py:79-113 ---------------- */
 size_t mocha_decoder_workspace_bytes(const mocha_dims* dims, int B);
 int mocha_decoder_fwd(const mocha_generator_weights* w, const float* d_src_encoded,

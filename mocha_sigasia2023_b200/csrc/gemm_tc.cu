@@ -1885,6 +1885,18 @@ int dispatch_bn(int bn, const CUtensorMap& tmA, const void* Wptr, unsigned long 
 // ------------------------------------------------------------------------------------------------
 // public (library-internal) API
 // ------------------------------------------------------------------------------------------------
+// tensor-map builders shared with the fused kernels (fused_tail.cu, fused_attn.cu)
+int tc_make_tmap(CUtensorMap* tm, const void* ptr, unsigned long long rows, unsigned long long K, int box_rows,
+                 unsigned long long pitch_elems, bool f32) {
+  return make_tmap(tm, ptr, rows, K, box_rows, pitch_elems, f32);
+}
+int tc_make_out_tmap(CUtensorMap* tm, const void* ptr, unsigned long long cols, unsigned long long rows_per_img,
+                     unsigned long long imgs, unsigned long long ld_elems, bool f32, unsigned long long img_pitch_rows,
+                     bool wide16) {
+  return make_out_tmap(tm, ptr, cols, rows_per_img, imgs, ld_elems, f32, img_pitch_rows, wide16);
+}
+int tc_num_sms() { return num_sms(); }
+
 bool tc_linear_supported(int M, int N, int K) { return M >= 1 && N >= 8 && K >= 64 && (K % 8) == 0; }
 
 size_t tc_scratch_bytes(size_t rows, size_t K) { return align_up(rows * K * 2, 256) + 256; }

@@ -6,9 +6,22 @@
 //              (taps shifted TMA row windows over a reflect-padded channel-last activation)
 //   * matcher: coarse squared distances ||x||^2 - 2 q.x with a fused per-row running top-kc
 #pragma once
+#include <cuda.h>
 #include "common.cuh"
 
 namespace mocha {
+
+// ---- tensor maps (shared with the fused kernels) -------------------------------------------------------
+// operand map: [rows, K] row-major (row pitch pitch_elems, 0 = dense), box = box_rows x 128 bytes, 128 B swizzle,
+// out-of-bounds reads return zero
+int tc_make_tmap(CUtensorMap* tm, const void* ptr, unsigned long long rows, unsigned long long K, int box_rows,
+                 unsigned long long pitch_elems = 0, bool f32 = false);
+// output map {cols, rows per image, images}: boxes of 32 rows x 32 columns (fp32: 128 B-swizzled; bf16: 64 B-swizzled,
+// or 64 columns / 128 B-swizzled with wide16); rows and columns past the tensor are clipped
+int tc_make_out_tmap(CUtensorMap* tm, const void* ptr, unsigned long long cols, unsigned long long rows_per_img,
+                     unsigned long long imgs, unsigned long long ld_elems, bool f32, unsigned long long img_pitch_rows = 0,
+                     bool wide16 = false);
+int tc_num_sms();
 
 // ---- linear ------------------------------------------------------------------------------------
 bool tc_linear_supported(int M, int N, int K);

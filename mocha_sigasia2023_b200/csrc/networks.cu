@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "gemm_f32.cuh"
 #include "gemm_tc.cuh"
+#include "fused.cuh"
 #include "networks_bf16.cuh"
 #include "ops.cuh"
 
@@ -614,4 +615,14 @@ extern "C" int mocha_bench_hbm_kernel(const mocha_generator_weights* w, int whic
       return set_error(MOCHA_ERR_ARG, "mocha_bench_hbm_kernel: unknown kernel %d", which);
   }
   return rc;
+}
+
+// Stand-alone entry of the fused block-tail kernel (unit tests, bench.py): operands already bf16.
+extern "C" int mocha_block_tail(const void* A0, int lda, int K0, const void* W0, const float* b0, const float* R0,
+                                const float* g1, const float* be1, int Hd, int act, const void* W1, const float* b1,
+                                const void* W2, const float* b2, const float* g2, const float* be2, float eps, float* O32,
+                                void* O16, int M, mocha_stream_t stream) {
+  return tc_tail((const __nv_bfloat16*)A0, lda, K0, (const __nv_bfloat16*)W0, b0, R0, g1, be1, Hd, act,
+                 (const __nv_bfloat16*)W1, b1, (const __nv_bfloat16*)W2, b2, g2, be2, eps, O32, (__nv_bfloat16*)O16, M,
+                 (cudaStream_t)stream);
 }

@@ -5,6 +5,9 @@
 // a residual add, a normalisation or a SIMT kernel reads them. Same math as networks.cu (fp32 mode).
 #include "networks_bf16.cuh"
 
+#include <cstdlib>
+
+#include "fused.cuh"
 #include "gemm_f32.cuh"
 #include "gemm_tc.cuh"
 #include "ops.cuh"
@@ -39,6 +42,24 @@ inline TcOut both(float* p, bf16* q) { return TcOut{p, q, 0}; }
   } while (0)
 
 inline int ntok(const mocha_dims& d) { return (d.T / d.tp) * d.P; }
+
+// MOCHA_NO_FUSED_TAIL=1 keeps the unfused launch sequence (out-projection, LayerNorm, FFN GEMMs) for A/B runs
+inline bool use_fused_tail(int D) {
+  static const bool off = getenv("MOCHA_NO_FUSED_TAIL") != nullptr;
+  return !off && D == 256;
+}
+
+// fused block tail (fused_tail.cu) on fp32 weight pointers: looks up the registered bf16 mirrors
+int tail(cudaStream_t s, const bf16* A0, int K0, const float* W0, const float* b0, const float* R0, const float* g1,
+         const float* be1, int Hd, int act, const float* W1, const float* b1, const float* W2, const float* b2,
+         const float* g2, const float* be2, float eps, float* O32, bf16* O16, int M) {
+  const bf16* W016 = tc_lookup_bf16(W0);
+  const bf16* W116 = Hd > 0 ? tc_lookup_bf16(W1) : nullptr;
+  const bf16* W216 = Hd > 0 ? tc_lookup_bf16(W2) : nullptr;
+  if (!W016 || (Hd > 0 && (!W116 || !W216)))
+    return set_error(MOCHA_ERR_ARG, "bf16 path: a block-tail weight has no registered bf16 mirror");
+  return tc_tail(A0, K0, K0, W016, b0, R0, g1, be1, Hd, act, W116, b1, W216, b2, g2, be2, eps, O32, O16, M, s);
+}
 
 }  // namespace
 
@@ -115,10 +136,16 @@ int encoder_bf16(const mocha_generator_weights* w, const float* tokens, int B, f
     MOCHA_TRY(tc.lin(x16, d.D, L.wqkv, nullptr, 0, nullptr, h16(qkv), R, 3 * inner, d.D, ACT_NONE));
     MOCHA_TRY(tc_attention_ex(nullptr, qkv, 3 * inner, nullptr, qkv + inner, 3 * inner, nullptr, qkv + 2 * inner,
                               3 * inner, B, d.heads, n, n, d.enc_dh, S, h16(att), inner, ws, s));
-    MOCHA_TRY(tc.lin(att, inner, L.wo, L.bo, 0, x, both(xa, xa16), R, d.D, inner, ACT_NONE));
-    MOCHA_TRY(tc.lin(xa16, d.D, L.w1, L.b1, 0, nullptr, h16(hid), R, d.mlp, d.D, ACT_GELU));
     float* dst = last ? encoded : xb;
-    MOCHA_TRY(tc.lin(hid, d.mlp, L.w2, L.b2, 0, xa, last ? f32(dst) : both(dst, x16), R, d.D, d.mlp, ACT_NONE));
+    if (use_fused_tail(d.D) && tc_tail_supported(R, inner, d.mlp)) {
+      // out-projection + residual + GELU FFN + residual in one launch (x and dst may alias: tiles are row-local)
+      MOCHA_TRY(tail(s, att, inner, L.wo, L.bo, x, nullptr, nullptr, d.mlp, ACT_GELU, L.w1, L.b1, L.w2, L.b2, nullptr, nullptr,
+                     0.f, dst, last ? nullptr : x16, R));
+    } else {
+      MOCHA_TRY(tc.lin(att, inner, L.wo, L.bo, 0, x, both(xa, xa16), R, d.D, inner, ACT_NONE));
+      MOCHA_TRY(tc.lin(xa16, d.D, L.w1, L.b1, 0, nullptr, h16(hid), R, d.mlp, d.D, ACT_GELU));
+      MOCHA_TRY(tc.lin(hid, d.mlp, L.w2, L.b2, 0, xa, last ? f32(dst) : both(dst, x16), R, d.D, d.mlp, ACT_NONE));
+    }
     x = dst;
   }
   return MOCHA_OK;
@@ -172,10 +199,15 @@ int decoder_bf16(const mocha_generator_weights* w, const float* src, const float
     MOCHA_TRY(tc.lin(cha16, d.D, L.wv, nullptr, 0, nullptr, h16(v), R, inner, d.D, ACT_NONE));
     MOCHA_TRY(tc_attention_ex(nullptr, q, inner, nullptr, k, inner, nullptr, v, inner, B, d.heads, n, n, d.dec_dh, S,
                               h16(att), inner, ws, s));
-    MOCHA_TRY(tc.lin(att, inner, L.wo, L.bo, 0, x1, both(x2, x2h), R, d.D, inner, ACT_NONE));
-    MOCHA_TRY(tc.lin(x2h, d.D, L.w1, L.b1, 0, nullptr, h16(hid), R, d.mlp, d.D, ACT_GELU));
     float* dst = (l == d.dec_depth - 1) ? decoded : xb;
-    MOCHA_TRY(tc.lin(hid, d.mlp, L.w2, L.b2, 0, x2, f32(dst), R, d.D, d.mlp, ACT_NONE));
+    if (use_fused_tail(d.D) && tc_tail_supported(R, inner, d.mlp)) {
+      MOCHA_TRY(tail(s, att, inner, L.wo, L.bo, x1, nullptr, nullptr, d.mlp, ACT_GELU, L.w1, L.b1, L.w2, L.b2, nullptr, nullptr,
+                     0.f, dst, nullptr, R));
+    } else {
+      MOCHA_TRY(tc.lin(att, inner, L.wo, L.bo, 0, x1, both(x2, x2h), R, d.D, inner, ACT_NONE));
+      MOCHA_TRY(tc.lin(x2h, d.D, L.w1, L.b1, 0, nullptr, h16(hid), R, d.mlp, d.D, ACT_GELU));
+      MOCHA_TRY(tc.lin(hid, d.mlp, L.w2, L.b2, 0, x2, f32(dst), R, d.D, d.mlp, ACT_NONE));
+    }
     x = dst;
   }
   return MOCHA_OK;
@@ -256,14 +288,19 @@ int cvae_bf16(const mocha_cvae_weights* w, const float* cond, int B, int ncond, 
       MOCHA_TRY(tc.lin(xq16, D, L.in_w, L.in_b, 0, nullptr, h16(q2), R2, D, D, ACT_NONE));
       MOCHA_TRY(tc_attention_ex(nullptr, q2, D, nullptr, kv, 2 * D, nullptr, kv + D, 2 * D, B, H, 2, np, dh, S, h16(att2), D,
                                 ws, s));
-      MOCHA_TRY(tc.lin(att2, D, L.out_w, L.out_b, 0, xq, f32(proj), R2, D, D, ACT_NONE));
-      float* y2 = proj + (size_t)R2 * D;       // proj has Rp*D floats: plenty of room for the 2-row tensors
-      bf16* y2h = q2;
-      MOCHA_TRY(add_layernorm(proj, nullptr, L.n1_g, L.n1_b, y2, R2, D, w->ln_eps, nullptr, nullptr, 0, nullptr, s, y2h));
-      bf16* hid2 = att2 + (size_t)R2 * D;
-      MOCHA_TRY(tc.lin(y2h, D, L.l1_w, L.l1_b, 0, nullptr, h16(hid2), R2, w->dff, D, ACT_RELU));
-      MOCHA_TRY(tc.lin(hid2, w->dff, L.l2_w, L.l2_b, 0, y2, f32(proj), R2, D, w->dff, ACT_NONE));
-      MOCHA_TRY(add_layernorm(proj, nullptr, L.n2_g, L.n2_b, xq, R2, D, w->ln_eps, nullptr, nullptr, 0, nullptr, s));
+      if (use_fused_tail(D) && tc_tail_supported(R2, D, w->dff)) {
+        MOCHA_TRY(tail(s, att2, D, L.out_w, L.out_b, xq, L.n1_g, L.n1_b, w->dff, ACT_RELU, L.l1_w, L.l1_b, L.l2_w, L.l2_b,
+                       L.n2_g, L.n2_b, w->ln_eps, xq, nullptr, R2));
+      } else {
+        MOCHA_TRY(tc.lin(att2, D, L.out_w, L.out_b, 0, xq, f32(proj), R2, D, D, ACT_NONE));
+        float* y2 = proj + (size_t)R2 * D;       // proj has Rp*D floats: plenty of room for the 2-row tensors
+        bf16* y2h = q2;
+        MOCHA_TRY(add_layernorm(proj, nullptr, L.n1_g, L.n1_b, y2, R2, D, w->ln_eps, nullptr, nullptr, 0, nullptr, s, y2h));
+        bf16* hid2 = att2 + (size_t)R2 * D;
+        MOCHA_TRY(tc.lin(y2h, D, L.l1_w, L.l1_b, 0, nullptr, h16(hid2), R2, w->dff, D, ACT_RELU));
+        MOCHA_TRY(tc.lin(hid2, w->dff, L.l2_w, L.l2_b, 0, y2, f32(proj), R2, D, w->dff, ACT_NONE));
+        MOCHA_TRY(add_layernorm(proj, nullptr, L.n2_g, L.n2_b, xq, R2, D, w->ln_eps, nullptr, nullptr, 0, nullptr, s));
+      }
       x = xq;
       prior_rows = 2;
       break;
@@ -271,11 +308,17 @@ int cvae_bf16(const mocha_cvae_weights* w, const float* cond, int B, int ncond, 
     MOCHA_TRY(tc.lin(x16, D, L.in_w, L.in_b, 0, nullptr, h16(qkv), Rp, 3 * D, D, ACT_NONE));
     MOCHA_TRY(tc_attention_ex(nullptr, qkv, 3 * D, nullptr, qkv + D, 3 * D, nullptr, qkv + 2 * D, 3 * D, B, H, np, np, dh,
                               S, h16(att), D, ws, s));
-    MOCHA_TRY(tc.lin(att, D, L.out_w, L.out_b, 0, x, f32(proj), Rp, D, D, ACT_NONE));      // proj = x + SA(x)
-    MOCHA_TRY(add_layernorm(proj, nullptr, L.n1_g, L.n1_b, y, Rp, D, w->ln_eps, nullptr, nullptr, 0, nullptr, s, y16));
-    MOCHA_TRY(tc.lin(y16, D, L.l1_w, L.l1_b, 0, nullptr, h16(hid), Rp, w->dff, D, ACT_RELU));
-    MOCHA_TRY(tc.lin(hid, w->dff, L.l2_w, L.l2_b, 0, y, f32(proj), Rp, D, w->dff, ACT_NONE)); // proj = y + FF(y)
-    MOCHA_TRY(add_layernorm(proj, nullptr, L.n2_g, L.n2_b, x, Rp, D, w->ln_eps, nullptr, nullptr, 0, nullptr, s, x16));
+    if (use_fused_tail(D) && tc_tail_supported(Rp, D, w->dff)) {
+      // x <- LN2(y + FF(y)), y = LN1(x + SA(x)): one launch, in place (tiles are row-local)
+      MOCHA_TRY(tail(s, att, D, L.out_w, L.out_b, x, L.n1_g, L.n1_b, w->dff, ACT_RELU, L.l1_w, L.l1_b, L.l2_w, L.l2_b, L.n2_g,
+                     L.n2_b, w->ln_eps, x, x16, Rp));
+    } else {
+      MOCHA_TRY(tc.lin(att, D, L.out_w, L.out_b, 0, x, f32(proj), Rp, D, D, ACT_NONE));      // proj = x + SA(x)
+      MOCHA_TRY(add_layernorm(proj, nullptr, L.n1_g, L.n1_b, y, Rp, D, w->ln_eps, nullptr, nullptr, 0, nullptr, s, y16));
+      MOCHA_TRY(tc.lin(y16, D, L.l1_w, L.l1_b, 0, nullptr, h16(hid), Rp, w->dff, D, ACT_RELU));
+      MOCHA_TRY(tc.lin(hid, w->dff, L.l2_w, L.l2_b, 0, y, f32(proj), Rp, D, w->dff, ACT_NONE)); // proj = y + FF(y)
+      MOCHA_TRY(add_layernorm(proj, nullptr, L.n2_g, L.n2_b, x, Rp, D, w->ln_eps, nullptr, nullptr, 0, nullptr, s, x16));
+    }
   }
   MOCHA_TRY(cvae_memory(x, prior_rows, eps, cond, nullptr, mu, logvar, B, ncond, D, s, mem));
 
@@ -294,17 +337,35 @@ int cvae_bf16(const mocha_cvae_weights* w, const float* cond, int B, int ncond, 
       MOCHA_TRY(tc.lin(dx16, D, L.sa_in_w, L.sa_in_b, 0, nullptr, h16(qkv), Rq, 3 * D, D, ACT_NONE));
       MOCHA_TRY(tc_attention_ex(nullptr, qkv, 3 * D, nullptr, qkv + D, 3 * D, nullptr, qkv + 2 * D, 3 * D, B, H, nq, nq, dh,
                                 S, h16(att), D, ws, s));
-      MOCHA_TRY(tc.lin(att, D, L.sa_out_w, L.sa_out_b, 0, dx, f32(proj), Rq, D, D, ACT_NONE));
-      MOCHA_TRY(add_layernorm(proj, nullptr, L.n1_g, L.n1_b, dy, Rq, D, w->ln_eps, nullptr, nullptr, 0, nullptr, s, dy16));
+      if (use_fused_tail(D) && tc_tail_supported(Rq, D, 0)) {
+        MOCHA_TRY(tail(s, att, D, L.sa_out_w, L.sa_out_b, dx, L.n1_g, L.n1_b, 0, ACT_NONE, nullptr, nullptr, nullptr, nullptr,
+                       nullptr, nullptr, w->ln_eps, dy, dy16, Rq));
+      } else {
+        MOCHA_TRY(tc.lin(att, D, L.sa_out_w, L.sa_out_b, 0, dx, f32(proj), Rq, D, D, ACT_NONE));
+        MOCHA_TRY(add_layernorm(proj, nullptr, L.n1_g, L.n1_b, dy, Rq, D, w->ln_eps, nullptr, nullptr, 0, nullptr, s, dy16));
+      }
     }
     MOCHA_TRY(tc.lin(dy16, D, L.ca_in_w, L.ca_in_b, 0, nullptr, h16(dq), Rq, D, D, ACT_NONE));
     MOCHA_TRY(tc.lin(mem, D, L.ca_in_w + (size_t)D * D, L.ca_in_b + D, 0, nullptr, h16(memkv), Rm, 2 * D, D, ACT_NONE));
     MOCHA_TRY(tc_attention_ex(nullptr, dq, D, nullptr, memkv, 2 * D, nullptr, memkv + D, 2 * D, B, H, nq, nm, dh, S,
                               h16(att), D, ws, s));
-    MOCHA_TRY(tc.lin(att, D, L.ca_out_w, L.ca_out_b, 0, dy, f32(proj), Rq, D, D, ACT_NONE));
-    MOCHA_TRY(add_layernorm(proj, nullptr, L.n2_g, L.n2_b, dx, Rq, D, w->ln_eps, nullptr, nullptr, 0, nullptr, s, dx16));
-    MOCHA_TRY(tc.lin(dx16, D, L.l1_w, L.l1_b, 0, nullptr, h16(hid), Rq, w->dff, D, ACT_RELU));
-    MOCHA_TRY(tc.lin(hid, w->dff, L.l2_w, L.l2_b, 0, dx, f32(proj), Rq, D, w->dff, ACT_NONE));
+    const bool fused = use_fused_tail(D) && tc_tail_supported(Rq, D, w->dff);
+    const bool last = l == w->depth - 1;
+    if (fused) {
+      // cross-attention out-projection + LN2 + ReLU FFN (+ LN3 unless the de-normalising last LayerNorm follows)
+      MOCHA_TRY(tail(s, att, D, L.ca_out_w, L.ca_out_b, dy, L.n2_g, L.n2_b, w->dff, ACT_RELU, L.l1_w, L.l1_b, L.l2_w, L.l2_b,
+                     last ? nullptr : L.n3_g, last ? nullptr : L.n3_b, w->ln_eps, last ? proj : dy, last ? nullptr : dy16, Rq));
+      if (!last) {
+        float* t = dx; dx = dy; dy = t;
+        bf16* t16 = dx16; dx16 = dy16; dy16 = t16;
+        continue;
+      }
+    } else {
+      MOCHA_TRY(tc.lin(att, D, L.ca_out_w, L.ca_out_b, 0, dy, f32(proj), Rq, D, D, ACT_NONE));
+      MOCHA_TRY(add_layernorm(proj, nullptr, L.n2_g, L.n2_b, dx, Rq, D, w->ln_eps, nullptr, nullptr, 0, nullptr, s, dx16));
+      MOCHA_TRY(tc.lin(dx16, D, L.l1_w, L.l1_b, 0, nullptr, h16(hid), Rq, w->dff, D, ACT_RELU));
+      MOCHA_TRY(tc.lin(hid, w->dff, L.l2_w, L.l2_b, 0, dx, f32(proj), Rq, D, w->dff, ACT_NONE));
+    }
     if (l == w->depth - 1) {
       MOCHA_TRY(add_layernorm(proj, nullptr, L.n3_g, L.n3_b, out, Rq, D, w->ln_eps, out_mean, out_std, nq, out_denorm, s));
     } else {

@@ -213,20 +213,26 @@ class PostProcessor:
             "mocha_post_frame")
         self.started = True
 
-    def step_packed(self, Y, side, contacts):
+    def step_packed(self, Y, side, contacts, lo: int = 0, init=None):
         """Same as step() with the source-motion inputs packed one row per clip:
-        side [B, T*3+6] = [src_hips_vel | src_rvel | src_rang] (mocha_post_frame_packed)."""
+        side [B', T*3+6] = [src_hips_vel | src_rvel | src_rang] (mocha_post_frame_packed). The B' clips are clips
+        lo .. lo+B'-1 of this processor's state / output arrays (sub-batch lanes); init overrides `started`."""
         _f32(Y)
         _f32(side)
         _lib.require_cuda(contacts)
         B, T, V, Cin = Y.shape
         if side.dim() != 2 or side.shape[0] != B or side.shape[1] < T * 3 + 6 or side.stride(1) != 1:
             raise _lib.MochaError(f"side must be [B, >= T*3+6] with unit column stride, got {tuple(side.shape)}")
-        init = 0 if self.started else 1
+        if lo < 0 or lo + B > self.B:
+            raise _lib.MochaError("step_packed: clip range outside this processor's state")
+        init = (0 if self.started else 1) if init is None else int(bool(init))
         _lib.check(_lib.load().mocha_post_frame_packed(
             C.byref(self.params), _lib.ptr(Y), _lib.ptr(side), side.stride(0), _lib.ptr(contacts), B, T, V, Cin, init,
-            _lib.ptr(self.state), _lib.ptr(self.out), _lib.stream_ptr()), "mocha_post_frame_packed")
-        self.started = True
+            C.c_void_p(self.state.data_ptr() + lo * C.sizeof(_lib.ClipState)),
+            C.c_void_p(self.out.data_ptr() + lo * C.sizeof(_lib.FrameOut)),
+            _lib.stream_ptr()), "mocha_post_frame_packed")
+        if lo == 0 and B == self.B:
+            self.started = True
 
     def read(self):
         """Copy the frame outputs to the host as a dict of float64 numpy arrays [B, ...]."""

@@ -34,7 +34,8 @@ class NormStats:
 
 class CharacterizationSession:
     def __init__(self, gen_sd, cvae_sd, cfg, stats: NormStats, cha_encoded, cha_cnt_nm, batch: int,
-                 device="cuda", precision="fp32", with_cm_path=False, match_tensor_cores=None, post_params=None):
+                 device="cuda", precision="fp32", with_cm_path=False, match_tensor_cores=None, post_params=None,
+                 lanes: int = 1):
         """gen_sd / cvae_sd: reference-layout state dicts. cha_encoded [N,90,256] and cha_cnt_nm [N,23040]
         (already (cnt-mean)/std scaled): the target character's feature DB, CUDA or CPU tensors."""
         self.lib = _lib.load()
@@ -106,6 +107,14 @@ class CharacterizationSession:
                      self.lib.mocha_match_exact_workspace_bytes(B, self.tree.N, 1),
                      self.lib.mocha_match_tc_workspace_bytes(B, self.tree.N, self.tree.D, self.tree.kc))
         self.ws = torch.empty(nbytes + 4096, dtype=torch.uint8, device=dev)
+        # Sub-batch lanes: clips are independent, so the batch can be cut into `lanes` contiguous groups whose frames
+        # run concurrently on separate streams (forked / joined inside the captured graph). Most kernels of the frame
+        # are latency-bound on <= 148 CTAs with idle SMs in their ramps and tails; a second lane fills them.
+        lanes = max(1, min(int(lanes), batch))
+        cuts = [round(i * batch / lanes) for i in range(lanes + 1)]
+        self.parts = [(cuts[i], cuts[i + 1]) for i in range(lanes) if cuts[i + 1] > cuts[i]]
+        self.lane_ws = [self.ws] + [torch.empty_like(self.ws) for _ in self.parts[1:]]
+        self.lane_streams = [torch.cuda.Stream(device=dev) for _ in self.parts[1:]]
         self.frame = 0
         self.graph = None
         self.deterministic = False
@@ -121,13 +130,14 @@ class CharacterizationSession:
     def _s(self):
         return _lib.stream_ptr()
 
-    def _ws(self):
-        return _lib.ptr(self.ws), self.ws.numel()
+    def _ws(self, ws=None):
+        ws = self.ws if ws is None else ws
+        return _lib.ptr(ws), ws.numel()
 
-    def encode(self, X, tokens, encoded, cnt, cnt_nm, cnt_nm16=None):
+    def encode(self, X, tokens, encoded, cnt, cnt_nm, cnt_nm16=None, ws=None):
         lib, g = self.lib, C.byref(self.gen.struct)
         B = X.shape[0]
-        wp, wn = self._ws()
+        wp, wn = self._ws(ws)
         _lib.check(lib.mocha_embed_fwd(g, _lib.ptr(X), B, _lib.ptr(tokens), 1, self.prec, wp, wn, self._s()), "embed")
         _lib.check(lib.mocha_encoder_fwd(g, _lib.ptr(tokens), B, _lib.ptr(encoded), self.prec, wp, wn, self._s()), "encoder")
         _lib.check(lib.mocha_cnt_features(_lib.ptr(encoded), B, self.ntok, self.D, 1e-5, _lib.ptr(cnt),
@@ -136,56 +146,77 @@ class CharacterizationSession:
                                           None if (cnt_nm16 is None or self.tree.center is None) else _lib.ptr(self.tree.center),
                                           self._s()), "cnt_features")
 
-    def _decode(self, src_encoded, cha, decoded, Y):
+    def _decode(self, src_encoded, cha, decoded, Y, ws=None):
         lib, g = self.lib, C.byref(self.gen.struct)
-        wp, wn = self._ws()
-        _lib.check(lib.mocha_decoder_fwd(g, _lib.ptr(src_encoded), _lib.ptr(cha), self.B, _lib.ptr(decoded), self.prec,
+        wp, wn = self._ws(ws)
+        B = src_encoded.shape[0]
+        _lib.check(lib.mocha_decoder_fwd(g, _lib.ptr(src_encoded), _lib.ptr(cha), B, _lib.ptr(decoded), self.prec,
                                          wp, wn, self._s()), "decoder")
-        _lib.check(lib.mocha_to_mot_fwd(g, _lib.ptr(decoded), self.B, None, _lib.ptr(self.Y_mean), _lib.ptr(self.Y_std),
+        _lib.check(lib.mocha_to_mot_fwd(g, _lib.ptr(decoded), B, None, _lib.ptr(self.Y_mean), _lib.ptr(self.Y_std),
                                         _lib.ptr(Y), self.prec, wp, wn, self._s()), "to_mot")
 
-    def _match(self):
+    def _match(self, lo=0, hi=None, ws=None):
         lib, t = self.lib, self.tree
-        wp, wn = self._ws()
-        use_tc = self._use_tc
-        if use_tc:
+        hi = self.B if hi is None else hi
+        wp, wn = self._ws(ws)
+        q, q16 = self.cnt_nm[lo:hi], self.cnt_nm16[lo:hi]
+        idx, dist = self.match_idx[lo:hi], self.match_dist[lo:hi]
+        if self._use_tc:
             t._ensure_bf16()
-            _lib.check(lib.mocha_match_tc(_lib.ptr(self.cnt_nm), _lib.ptr(self.cnt_nm16), self.B, _lib.ptr(t._db16),
+            _lib.check(lib.mocha_match_tc(_lib.ptr(q), _lib.ptr(q16), hi - lo, _lib.ptr(t._db16),
                                           _lib.ptr(t.data), _lib.ptr(t._norm), t.N, t.D, 1, t.kc, 0,
-                                          _lib.ptr(self.match_idx), _lib.ptr(self.match_dist), wp, wn, self._s()),
+                                          _lib.ptr(idx), _lib.ptr(dist), wp, wn, self._s()),
                        "match_tc")
         else:
-            _lib.check(lib.mocha_match_exact(_lib.ptr(self.cnt_nm), self.B, _lib.ptr(t.data), t.N, t.D, 1, 0,
-                                             _lib.ptr(self.match_idx), _lib.ptr(self.match_dist), wp, wn, self._s()),
+            _lib.check(lib.mocha_match_exact(_lib.ptr(q), hi - lo, _lib.ptr(t.data), t.N, t.D, 1, 0,
+                                             _lib.ptr(idx), _lib.ptr(dist), wp, wn, self._s()),
                        "match_exact")
 
-    def _frame_body(self, init: bool):
-        """Everything between the input buffers and the FrameOut buffer (graph-capturable)."""
+    def _frame_part(self, init: bool, lo: int, hi: int, ws):
+        """One lane: clips [lo, hi) from the input buffers to the FrameOut buffer, on the current stream."""
         lib = self.lib
-        self.encode(self.X, self.tokens, self.encoded, self.cnt, self.cnt_nm, self.cnt_nm16)
-        self._match()
+        sl = slice(lo, hi)
+        Bp = hi - lo
+        self.encode(self.X[sl], self.tokens[sl], self.encoded[sl], self.cnt[sl], self.cnt_nm[sl], self.cnt_nm16[sl], ws)
+        self._match(lo, hi, ws)
         if init or self.with_cm_path:
-            torch.index_select(self.cha_encoded, 0, self.match_idx[:, 0], out=self.cm_cha)
+            torch.index_select(self.cha_encoded, 0, self.match_idx[sl, 0], out=self.cm_cha[sl])
         if init:
             # frame 0: the NN result seeds the autoregression (test_fullframework.py:298, :437)
-            self.prev_cha.copy_(self.cm_cha)
+            self.prev_cha[sl].copy_(self.cm_cha[sl])
         else:
-            _lib.check(lib.mocha_cvae_condition(_lib.ptr(self.cnt), _lib.ptr(self.prev_cha), _lib.ptr(self.m0),
+            _lib.check(lib.mocha_cvae_condition(_lib.ptr(self.cnt[sl]), _lib.ptr(self.prev_cha[sl]), _lib.ptr(self.m0),
                                                 _lib.ptr(self.s0), _lib.ptr(self.m1), _lib.ptr(self.s1),
-                                                _lib.ptr(self.cond), self.B, self.ntok, self.D, self._s()), "condition")
-            wp, wn = self._ws()
-            _lib.check(lib.mocha_cvae_sample(C.byref(self.cvae.struct), _lib.ptr(self.cond), self.B, 2 * self.ntok,
-                                             None if self.deterministic else _lib.ptr(self.eps), _lib.ptr(self.cvae_out),
-                                             None, None, _lib.ptr(self.m1), _lib.ptr(self.s1), _lib.ptr(self.prev_cha),
-                                             self.prec, wp, wn, self._s()), "cvae_sample")
-        self._decode(self.encoded, self.prev_cha, self.decoded, self.Y)
+                                                _lib.ptr(self.cond[sl]), Bp, self.ntok, self.D, self._s()), "condition")
+            wp, wn = self._ws(ws)
+            _lib.check(lib.mocha_cvae_sample(C.byref(self.cvae.struct), _lib.ptr(self.cond[sl]), Bp, 2 * self.ntok,
+                                             None if self.deterministic else _lib.ptr(self.eps[sl]),
+                                             _lib.ptr(self.cvae_out[sl]), None, None, _lib.ptr(self.m1), _lib.ptr(self.s1),
+                                             _lib.ptr(self.prev_cha[sl]), self.prec, wp, wn, self._s()), "cvae_sample")
+        self._decode(self.encoded[sl], self.prev_cha[sl], self.decoded[sl], self.Y[sl], ws)
         # the kernel reads the packed `side` rows in place (no slicing copies inside the captured frame)
-        self.post.started = not init
-        self.post.step_packed(self.Y, self.side, self.contacts)
+        self.post.step_packed(self.Y[sl], self.side[sl], self.contacts[sl], lo=lo, init=init)
         if self.with_cm_path:
-            self._decode(self.encoded, self.cm_cha, self.decoded, self.cm_Y)
-            self.cm_post.started = not init
-            self.cm_post.step_packed(self.cm_Y, self.side, self.contacts)
+            self._decode(self.encoded[sl], self.cm_cha[sl], self.decoded[sl], self.cm_Y[sl], ws)
+            self.cm_post.step_packed(self.cm_Y[sl], self.side[sl], self.contacts[sl], lo=lo, init=init)
+
+    def _frame_body(self, init: bool):
+        """Everything between the input buffers and the FrameOut buffer (graph-capturable): the lanes' frames, forked
+        onto their streams and joined back into the current one."""
+        cur = torch.cuda.current_stream()
+        for s in self.lane_streams:
+            s.wait_stream(cur)
+        for k, (lo, hi) in enumerate(self.parts):
+            if k == 0:
+                self._frame_part(init, lo, hi, self.lane_ws[0])
+            else:
+                with torch.cuda.stream(self.lane_streams[k - 1]):
+                    self._frame_part(init, lo, hi, self.lane_ws[k])
+        for s in self.lane_streams:
+            cur.wait_stream(s)
+        self.post.started = True
+        if self.cm_post:
+            self.cm_post.started = True
 
     def capture(self):
         """Capture the steady-state frame (i >= 1) into a CUDA graph. Call after the first frame."""

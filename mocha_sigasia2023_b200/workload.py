@@ -51,7 +51,7 @@ def step_inputs(B: int, seed: int) -> dict:
 
 def build_session(batch: int, n_db: int = 385, precision: str = "fp32", device="cuda", seed: int = 0,
                   with_cm_path: bool = False, match_tensor_cores=None, gen_seed: int = 1777, cvae_seed: int = 1778,
-                  db_precision: str = "fp32", db_batch: int = 64):
+                  db_precision: str = "fp32", db_batch: int = 64, lanes: int = 1):
     """Session on random-init weights with a character DB of n_db encoded synthetic windows
     (n_db = 385 is what a 400-frame character clip yields). The DB comes from the
     feature-DB builder (feature_db.build_feature_db: same CUDA encoder, matcher layout)."""
@@ -66,6 +66,6 @@ def build_session(batch: int, n_db: int = 385, precision: str = "fp32", device="
     sess = CharacterizationSession(gen_sd, cvae_sd, weights.DEFAULT_MODEL_CFG, stats, fdb.encoded,
                                    BallTree.from_feature_db(fdb, device=device, use_tensor_cores=match_tensor_cores),
                                    batch=batch, device=device, precision=precision, with_cm_path=with_cm_path,
-                                   match_tensor_cores=match_tensor_cores)
+                                   match_tensor_cores=match_tensor_cores, lanes=lanes)
     sess.feature_db = fdb
     return sess, gen_sd, cvae_sd, stats
