@@ -268,21 +268,30 @@ tail_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     mbar_init(&bar[B_HEMPTY], 1);
     mbar_init(&bar[B_ACC2], 1);
     fence_barrier_init();
+  }
+  if (warp == 0) {
     // Weights are constants: pull every tile this CTA will stream into L2 now, under the previous kernel's tail. All
-    // CTAs of the launch walk the same weight tiles in lockstep, so without this each ring refill was a fresh HBM miss
-    // for everybody (~3000 cycles per 32 KB slot); the prefetches of different CTAs coalesce in L2.
-    for (int kb = 0; kb < nkb0; ++kb) tma_prefetch_l2_2d(&tmW0, kb * 64, 0);
-    for (int j = 0; j < nch; ++j) {
-      for (int kb = 0; kb < 4; ++kb) tma_prefetch_l2_2d(&tmW1, kb * 64, j * 128);
-      for (int kk = 0; kk < 2; ++kk) tma_prefetch_l2_2d(&tmW2, j * 128 + kk * 64, 0);
+    // CTAs of the launch walk the same weight tiles in lockstep, so without this each ring refill is a fresh HBM miss
+    // for everybody; the prefetches of different CTAs coalesce in L2. One box per lane: the issue cost stays off the
+    // producer's critical path.
+    const int nbox = nkb0 + nch * 6;
+    for (int i = lane; i < nbox; i += 32) {
+      if (i < nkb0) {
+        tma_prefetch_l2_2d(&tmW0, i * 64, 0);
+      } else {
+        const int j = (i - nkb0) / 6, r = (i - nkb0) % 6;
+        if (r < 4) tma_prefetch_l2_2d(&tmW1, r * 64, j * 128);
+        else tma_prefetch_l2_2d(&tmW2, j * 128 + (r - 4) * 64, 0);
+      }
     }
   }
   if (warp >= 2) {
     // bias / LayerNorm vectors -> shared memory (constants too: loaded before the grid dependency is waited for)
     float* par = reinterpret_cast<float*>(smem + FT_OFF_PAR);
     const int t = (int)threadIdx.x - 64;
-    for (int i4 = t; i4 < PV_COUNT / 4; i4 += 256) {
-      const int i = i4 * 4;
+#pragma unroll
+    for (int it = 0; it < PV_COUNT / 4 / 256; ++it) {
+      const int i = (t + it * 256) * 4;
       const float* src = i < PV_G1 ? p.b0 : i < PV_BE1 ? p.g1 : i < PV_B1 ? p.be1 : i < PV_B2 ? p.b1 : i < PV_G2 ? p.b2 : i < PV_BE2 ? p.g2 : p.be2;
       const int base = i < PV_G1 ? PV_B0 : i < PV_BE1 ? PV_G1 : i < PV_B1 ? PV_BE1 : i < PV_B2 ? PV_B1 : i < PV_G2 ? PV_B2 : i < PV_BE2 ? PV_G2 : PV_BE2;
       const int len = base == PV_B1 ? p.Hd : FT_D;
