@@ -382,6 +382,17 @@ int mocha_post_frame_packed(const mocha_post_params* params, const float* d_Y, c
                             const uint8_t* d_contacts, int B, int T, int V, int Cin, int init,
                             mocha_clip_state* d_state, mocha_frame_out* d_out, mocha_stream_t stream);
 
+/* ---- window feature extraction: re-rooting block of the driver's set-up (test_fullframework.py:148-158,:180-186) ---
+ * Inputs are quat.fk_vel's outputs over all frames of all windows, [W,T,J,{4,3,3,3}] fp32. Every window is expressed
+ * relative to the simulation root of its last frame; d_X [W,T,J-1,15] receives (concat(Xpos, Xtxy, Xvel, Xang) -
+ * X_mean)/X_std for joints 1.. (tables [J,15] as in norm.npz), d_xrot [W,T,J,4] / d_xpos [W,T,J,3] the re-rooted
+ * rotations / positions the following quat.ik (:160) needs (either may be NULL).
+ * d_X_mean == NULL selects the training-side twin convert_YtilToX (trainer.py:337-374): every FRAME relative to its own
+ * root, all J joints, no normalisation: d_X [W,T,J,15]. */
+int mocha_window_features(const float* d_grot, const float* d_gpos, const float* d_gvel, const float* d_gang, long long W,
+                          int T, int J, const float* d_X_mean, const float* d_X_std, float* d_X, float* d_xrot,
+                          float* d_xpos, mocha_stream_t stream);
+
 /* ---- element-wise quaternion algebra of motion/quat.py in the caller's precision ------------- */
 /* out[i] = op(a[i], b[i]) for i < n; dense [n, width] arrays, float32 (is_f64 == 0) or float64. Ops and widths
  * (a, b, out): 0 mul (4,4,4) quat.py:112 | 1 inv_mul :122 | 2 mul_inv :125 | 3 mul_vec (4,3,3) :128 |

@@ -156,6 +156,7 @@ SIGNATURES = {
     "mocha_fk_vel_f64": (_I, [_P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _P, _P]),
     "mocha_ik_f64": (_I, [_P, _P, _P, _L, _I, _P, _P, _P]),
     "mocha_post_frame": (_I, [C.POINTER(PostParams), _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "mocha_window_features": (_I, [_P, _P, _P, _P, _L, _I, _I, _P, _P, _P, _P, _P, _P]),
     "mocha_quat_op": (_I, [_I, _I, _P, _P, _L, C.c_double, _P, _P]),
     "mocha_fk_chain": (_I, [_I, _P, _P, _P, _P, _L, _I, _P, _P, _P]),
     "mocha_post_frame_packed": (_I, [C.POINTER(PostParams), _P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P]),

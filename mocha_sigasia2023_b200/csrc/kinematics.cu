@@ -1108,3 +1108,82 @@ extern "C" int mocha_fk_chain(int is_f64, const void* start_pos, const void* sta
   MOCHA_LAUNCH_CHECK("fk_chain_kernel");
   return MOCHA_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Window feature extraction: the re-rooting block of the driver's set-up,
+// test_fullframework.py:148-158 + :180-186. Input: global transforms / velocities of every frame of every window
+// (quat.fk_vel, :146). Every window is expressed relative to the simulation root of its LAST frame:
+//   root := G[w, T-1, 0];  G[w, t, 0] := root for all t (:148-151)
+//   Xpos = R0^-1 (Gpos - P0), Xrot = R0^-1 Grot, Xtxy = first two columns of Xrot's matrix, Xvel = R0^-1 Gvel,
+//   Xang = R0^-1 Gang;  X = (concat(Xpos, Xtxy, Xvel, Xang)[joints 1..] - X_mean[1..]) / X_std[1..]
+// One thread per (window, frame, joint); writes the normalised 15-channel rows the embedding reads and the re-rooted
+// rotations / positions the following quat.ik (:160) needs.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256)
+window_reroot_kernel(const float* __restrict__ grot, const float* __restrict__ gpos, const float* __restrict__ gvel,
+                     const float* __restrict__ gang, long long W, int T, int J, const float* __restrict__ X_mean,
+                     const float* __restrict__ X_std, float* __restrict__ X, float* __restrict__ xrot, float* __restrict__ xpos,
+                     int per_frame_root) {
+  pdl_trigger();
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = W * T * J;
+  if (i >= total) return;
+  const int j = (int)(i % J);
+  const long long wt = i / J;
+  const long long w = wt / T;
+  // joint 0 of the window's last frame, or (training twin convert_YtilToX, trainer.py:356-362) of the frame itself
+  const long long rootf = per_frame_root ? wt * J : (w * T + (T - 1)) * J;
+  const Q4<float> r0 = q4<float>(grot[rootf * 4], grot[rootf * 4 + 1], grot[rootf * 4 + 2], grot[rootf * 4 + 3]);
+  const Q4<float> r0i = qinv(r0);
+  const V3<float> p0 = v3<float>(gpos[rootf * 3], gpos[rootf * 3 + 1], gpos[rootf * 3 + 2]);
+  const long long src = j == 0 ? rootf : i;               // the root row of every frame is the last frame's root
+  const Q4<float> gr = q4<float>(grot[src * 4], grot[src * 4 + 1], grot[src * 4 + 2], grot[src * 4 + 3]);
+  const V3<float> gp = v3<float>(gpos[src * 3], gpos[src * 3 + 1], gpos[src * 3 + 2]);
+  const V3<float> gv = v3<float>(gvel[src * 3], gvel[src * 3 + 1], gvel[src * 3 + 2]);
+  const V3<float> ga = v3<float>(gang[src * 3], gang[src * 3 + 1], gang[src * 3 + 2]);
+  const V3<float> xp = qrot(r0i, gp - p0);
+  const Q4<float> xr = qmul(r0i, gr);
+  const V3<float> xv = qrot(r0i, gv);
+  const V3<float> xa = qrot(r0i, ga);
+  if (xrot) { xrot[i * 4] = xr.w; xrot[i * 4 + 1] = xr.x; xrot[i * 4 + 2] = xr.y; xrot[i * 4 + 3] = xr.z; }
+  if (xpos) { xpos[i * 3] = xp.x; xpos[i * 3 + 1] = xp.y; xpos[i * 3 + 2] = xp.z; }
+  if (j == 0 && !per_frame_root) return;                  // X drops the simulation root (:186)
+  const float qw = xr.w, qx = xr.x, qy = xr.y, qz = xr.z;
+  const float x2 = qx + qx, y2 = qy + qy, z2 = qz + qz;
+  const float xx = qx * x2, yy = qy * y2, wx = qw * x2;
+  const float xy = qx * y2, yz = qy * z2, wy = qw * y2;
+  const float xz = qx * z2, zz = qz * z2, wz = qw * z2;
+  const float f[15] = {xp.x, xp.y, xp.z,
+                       1.0f - (yy + zz), xy - wz, xy + wz, 1.0f - (xx + zz), xz - wy, yz + wx,
+                       xv.x, xv.y, xv.z, xa.x, xa.y, xa.z};
+  if (per_frame_root) {                                   // all J joints, not normalised (trainer.py:364-372)
+    float* o = X + i * 15;
+#pragma unroll
+    for (int c = 0; c < 15; ++c) o[c] = f[c];
+    return;
+  }
+  float* o = X + (wt * (J - 1) + (j - 1)) * 15;
+  const float* mu = X_mean + j * 15;
+  const float* sd = X_std + j * 15;
+#pragma unroll
+  for (int c = 0; c < 15; ++c) o[c] = (f[c] - mu[c]) / sd[c];
+}
+}  // namespace
+
+extern "C" int mocha_window_features(const float* grot, const float* gpos, const float* gvel, const float* gang, long long W,
+                                     int T, int J, const float* X_mean, const float* X_std, float* X, float* xrot, float* xpos,
+                                     mocha_stream_t stream) {
+  MOCHA_CHECK_ARG(grot && gpos && gvel && gang && X, "mocha_window_features: null argument");
+  MOCHA_CHECK_ARG(W > 0 && T > 0 && J > 1 && J <= MAXJ, "mocha_window_features: bad sizes W=%lld T=%d J=%d", W, T, J);
+  // X_mean == NULL selects the training twin (trainer.py:337-374): per-frame root, all joints, no normalisation
+  const int per_frame = X_mean == nullptr;
+  MOCHA_CHECK_ARG(per_frame || X_std, "mocha_window_features: X_std missing");
+  const long long total = W * T * J;
+  launch_k(window_reroot_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, grot, gpos, gvel, gang, W,
+           T, J, X_mean, X_std, X, xrot, xpos, per_frame);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("window_reroot_kernel");
+  return MOCHA_OK;
+}

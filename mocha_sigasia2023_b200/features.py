@@ -3,15 +3,16 @@
 its last frame's simulation root, inverse kinematics back to local space, 6-D rotation encoding,
 central-difference velocities and normalisation. SURVEY §8(f) "next" row 2.
 
-Heavy parts (fk_vel, ik, to_xform_xy over nwin*60 skeletons) run in the library's kernels; the
-re-rooting algebra is element-wise torch on CUDA tensors."""
+Everything runs in the library's kernels: `mocha_fk_vel` (world space), `mocha_window_features` (re-rooting on
+the window's last root + 6-D rotation encoding + normalisation, one pass), `mocha_ik` (back to local space),
+`mocha_quat_op` (body-frame root velocities); only the 3-point central differences are torch expressions."""
 from __future__ import annotations
 
 import numpy as np
 import torch
 
 from . import kinematics as kin
-from . import skeleton, tq
+from . import _lib, skeleton
 
 
 def _central_diff_time(x):
@@ -35,24 +36,21 @@ def extract(windows: dict, X_mean: np.ndarray, X_std: np.ndarray, device="cuda")
     par = kin.parents_tensor(windows.get("parents", skeleton.BONE_PARENTS), device)
     window = Ypos.shape[1]
     # local root velocities in the body frame (:142-143)
-    Yrvel = tq.inv_mul_vec(Yrot[:, :, 0], Yvel[:, :, 0])
-    Yrang = tq.inv_mul_vec(Yrot[:, :, 0], Yang[:, :, 0])
-    # world space (:146), then every frame's root replaced by the window's last root (:148-151)
+    nwin, J = Ypos.shape[0], Ypos.shape[2]
+    r0 = Yrot[:, :, 0].reshape(-1, 4).contiguous()
+    Yrvel = kin.quat_op("inv_mul_vec", r0, Yvel[:, :, 0].reshape(-1, 3).contiguous()).reshape(nwin, window, 3)
+    Yrang = kin.quat_op("inv_mul_vec", r0, Yang[:, :, 0].reshape(-1, 3).contiguous()).reshape(nwin, window, 3)
+    # world space (:146), then every window relative to its last frame's root, encoded and normalised (:148-158,:180-186)
     Grot, Gpos, Gvel, Gang = kin.fk_vel(Yrot, Ypos, Yvel, Yang, par)
-    for G in (Gpos, Grot, Gvel, Gang):
-        G[:, :, 0:1] = G[:, -1:, 0:1].expand(-1, window, -1, -1).clone()
-    R0 = Grot[:, :, 0:1]
-    Xpos = tq.inv_mul_vec(R0, Gpos - Gpos[:, :, 0:1])                 # (:154-158)
-    Xrot = tq.inv_mul(R0, Grot)
-    Xtxy = kin.quat_to_xy(Xrot.contiguous())
-    Xvel = tq.inv_mul_vec(R0, Gvel)
-    Xang = tq.inv_mul_vec(R0, Gang)
-    Yrot2, Ypos2 = kin.ik(Xrot.contiguous(), Xpos.contiguous(), par)   # (:160)
+    xm = torch.as_tensor(np.ascontiguousarray(np.asarray(X_mean, dtype=np.float32)), **f32).contiguous()
+    xs = torch.as_tensor(np.ascontiguousarray(np.asarray(X_std, dtype=np.float32)), **f32).contiguous()
+    X = torch.empty((nwin, window, J - 1, 15), **f32)
+    Xrot = torch.empty_like(Grot)
+    Xpos = torch.empty_like(Gpos)
+    _lib.check(_lib.load().mocha_window_features(_lib.ptr(Grot), _lib.ptr(Gpos), _lib.ptr(Gvel), _lib.ptr(Gang), nwin, window, J,
+                                                 _lib.ptr(xm), _lib.ptr(xs), _lib.ptr(X), _lib.ptr(Xrot), _lib.ptr(Xpos),
+                                                 _lib.stream_ptr()), "mocha_window_features")
+    Yrot2, Ypos2 = kin.ik(Xrot, Xpos, par)                             # (:160)
     Yvel2 = _central_diff_time(Ypos2)                                  # (:164-169)
-    nwin, ns, nj = Xtxy.shape[:3]
-    X = torch.cat([Xpos, Xtxy.reshape(nwin, ns, nj, 6), Xvel, Xang], dim=-1)   # (:180-185)
-    xm = torch.as_tensor(np.asarray(X_mean, dtype=np.float32)[1:], **f32)
-    xs = torch.as_tensor(np.asarray(X_std, dtype=np.float32)[1:], **f32)
-    X = ((X[:, :, 1:] - xm) / xs).contiguous()                         # (:186)
     return {"X": X, "Yrvel": Yrvel.contiguous(), "Yrang": Yrang.contiguous(), "Ypos": Ypos2, "Yrot": Yrot2,
             "Yvel": Yvel2, "contacts": torch.as_tensor(windows["contacts"], dtype=torch.uint8, device=device)}
