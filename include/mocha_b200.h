@@ -204,6 +204,12 @@ int mocha_block_tail(const void* d_A0, int lda, int K0, const void* d_W0, const 
                      const void* d_W2, const float* d_b2, const float* d_g2, const float* d_be2, float eps,
                      float* d_O32, void* d_O16, int M, mocha_stream_t stream);
 
+/* Attention core in ONE launch (net/transformer.py:58-70; nn.MultiheadAttention): out[b, :, h*dh:(h+1)*dh] =
+ * softmax(Q_h K_h^T / sqrt(dh)) V_h. d_q / d_k / d_v: bf16 views [B*nq | B*nkv, ld] with head h at columns h*dh
+ * (16 B-aligned, ld % 8 == 0); d_out bf16 [B, nq, H*dh] with ldo == H*dh. dh in {64,128,256}, nkv <= 256. */
+int mocha_attention_core(const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, int B, int H,
+                         int nq, int nkv, int dh, void* d_out, int ldo, mocha_stream_t stream);
+
 /* ---- (a8) Generator.decoder = Transformer(adain=True)  transformer.py:79-113 ---------------- */
 size_t mocha_decoder_workspace_bytes(const mocha_dims* dims, int B);
 int mocha_decoder_fwd(const mocha_generator_weights* w, const float* d_src_encoded,

@@ -123,6 +123,7 @@ SIGNATURES = {
     "mocha_encoder_workspace_bytes": (_S, [C.POINTER(Dims), _I]),
     "mocha_encoder_fwd": (_I, [C.POINTER(GeneratorWeights), _P, _I, _P, _I, _P, _S, _P]),
     "mocha_cnt_features": (_I, [_P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
+    "mocha_attention_core": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P]),
     "mocha_block_tail": (_I, [_P, _I, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _F, _P, _P, _I, _P]),
     "mocha_decoder_workspace_bytes": (_S, [C.POINTER(Dims), _I]),
     "mocha_decoder_fwd": (_I, [C.POINTER(GeneratorWeights), _P, _P, _I, _P, _I, _P, _S, _P]),

@@ -1,2 +1,315 @@
-// placeholder until the fused attention kernel lands
+// Fused attention core on tcgen05 (sm_100a): softmax(Q K^T / sqrt(dh)) V for B x H (clip, head) problems in ONE launch
+// (net/transformer.py:37-76; nn.MultiheadAttention inside model_CVAE.py's encoder / decoder layers).
+//
+// One persistent CTA per SM walks units (clip b, head h, 128-row query tile). Per unit:
+//   S = Q_h K_h^T            tcgen05.mma, fp32 scores in TMEM columns [0, npad)              (npad = keys rounded up to 64)
+//   P = exp2((S - max) c)    softmax in the epilogue warps straight from TMEM; the unnormalised bf16 probabilities go to
+//                            shared memory as the K-major, 128 B-swizzled A operand of the second GEMM (they used to
+//                            round-trip through HBM between two launches)
+//   O = P V_h                V read in place as an MN-major B operand, fp32 accumulators in TMEM columns [256, 256 + dh)
+//   out = O / sum(P)         bf16, TMA store into the [B, nq, H*dh] tensor the out-projection reads
+// Q, K, V, P each have ONE shared-memory buffer with its own full / empty barrier, so the TMA producer refills Q and K
+// for the next unit as soon as the score GEMM has read them (under the softmax, the second GEMM and the output
+// epilogue of the current unit) and V as soon as the second GEMM has; the score GEMM of unit u+1 is issued before the
+// P V GEMM of unit u. Warp roles as in gemm_tc.cu: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..9
+// epilogue (two warps per TMEM lane quarter split the key columns / the head dimension and exchange row maxima and sums).
 #include "fused.cuh"
+
+#include "gemm_tc.cuh"
+#include "tc_ptx.cuh"
+
+namespace mocha {
+
+using namespace tcx;
+
+namespace {
+
+constexpr int FA_THREADS = 320;
+enum { A_QKFULL = 0, A_QKEMPTY, A_VFULL, A_VEMPTY, A_SFULL, A_SEMPTY, A_PREADY, A_OFULL, A_OEMPTY, A_COUNT };
+
+struct AttnParams {
+  int B, H, nq, nkv, dh, npad;   // npad = nkv rounded up to a multiple of 64 (<= 256)
+  int nqt;                       // query tiles per (clip, head)
+  int units;
+  float scale_log2e;             // log2(e) / sqrt(dh)
+  uint32_t off_k, off_v, off_p, off_bar, off_xch;   // shared-memory plan (Q at 0)
+};
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t smem_addr, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tm), "r"(smem_addr),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(FA_THREADS, 1)
+attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+            const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_trigger();
+  const uint32_t sbase = smem_u32(smem);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + A_COUNT);
+  float* xch = reinterpret_cast<float*>(smem + p.off_xch);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0 && (sbase & 1023u) != 0) {
+    printf("mocha attention kernel: dynamic shared memory base %u is not 1 KB aligned\n", sbase);
+    __trap();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmO);
+    mbar_init(&bar[A_QKFULL], 1); mbar_init(&bar[A_QKEMPTY], 1);
+    mbar_init(&bar[A_VFULL], 1); mbar_init(&bar[A_VEMPTY], 1);
+    mbar_init(&bar[A_SFULL], 1); mbar_init(&bar[A_SEMPTY], 8);
+    mbar_init(&bar[A_PREADY], 8);
+    mbar_init(&bar[A_OFULL], 1); mbar_init(&bar[A_OEMPTY], 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+
+  const int dkb = p.dh / 64;          // k-blocks of the head dimension
+  const int nkb = p.npad / 64;        // k-blocks of the key dimension
+  const uint32_t q_bytes = (uint32_t)dkb * 16384u, k_bytes = (uint32_t)dkb * (uint32_t)p.npad * 128u;
+  const uint32_t v_bytes = (uint32_t)nkb * (uint32_t)dkb * 8192u;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++it) {
+        const int qt = u % p.nqt, h = (u / p.nqt) % p.H, b = u / (p.nqt * p.H);
+        const uint32_t ph = it & 1;
+        mbar_wait(&bar[A_QKEMPTY], ph ^ 1);
+        mbar_expect_tx(&bar[A_QKFULL], q_bytes + k_bytes);
+        for (int kb = 0; kb < dkb; ++kb) {
+          tma_load_2d(sbase + (uint32_t)kb * 16384u, &tmQ, &bar[A_QKFULL], h * p.dh + kb * 64, b * p.nq + qt * 128);
+          tma_load_2d(sbase + p.off_k + (uint32_t)kb * (uint32_t)p.npad * 128u, &tmK, &bar[A_QKFULL], h * p.dh + kb * 64, b * p.nkv);
+        }
+        mbar_wait(&bar[A_VEMPTY], ph ^ 1);
+        mbar_expect_tx(&bar[A_VFULL], v_bytes);
+        for (int kb = 0; kb < nkb; ++kb)
+          for (int a = 0; a < dkb; ++a)
+            tma_load_2d(sbase + p.off_v + (uint32_t)(kb * dkb + a) * 8192u, &tmV, &bar[A_VFULL], h * p.dh + a * 64, b * p.nkv + kb * 64);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc(128, p.npad), idesc_o = make_idesc(128, p.dh, true);
+      const uint32_t accS = tmem, accO = tmem + 256u;
+      auto issue_s = [&](uint32_t it) {
+        const uint32_t ph = it & 1;
+        mbar_wait(&bar[A_QKFULL], ph);
+        mbar_wait(&bar[A_SEMPTY], ph ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < dkb; ++kb) {
+          const uint64_t adesc = make_smem_desc(sbase + (uint32_t)kb * 16384u);
+          const uint64_t bdesc = make_smem_desc(sbase + p.off_k + (uint32_t)kb * (uint32_t)p.npad * 128u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(accS, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s, (kb | k) != 0);
+        }
+        umma_commit(&bar[A_QKEMPTY]);
+        umma_commit(&bar[A_SFULL]);
+      };
+      auto issue_o = [&](uint32_t it) {
+        const uint32_t ph = it & 1;
+        mbar_wait(&bar[A_PREADY], ph);
+        mbar_wait(&bar[A_VFULL], ph);
+        mbar_wait(&bar[A_OEMPTY], ph ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < nkb; ++kb) {
+          const uint64_t adesc = make_smem_desc(sbase + p.off_p + (uint32_t)kb * 16384u);
+          // MN-major V: one MMA consumes 16 key rows = 2 KB of every 64-column atom
+          const uint64_t bdesc = make_smem_desc_mn(sbase + p.off_v + (uint32_t)(kb * dkb) * 8192u, 8192u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(accO, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(128 * k), idesc_o, (kb | k) != 0);
+        }
+        umma_commit(&bar[A_VEMPTY]);
+        umma_commit(&bar[A_OFULL]);
+      };
+      uint32_t n = 0;
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x) ++n;
+      // scores of unit u+1 are issued before the P V product of unit u
+      if (n > 0) issue_s(0);
+      for (uint32_t it = 0; it < n; ++it) {
+        if (it + 1 < n) issue_s(it + 1);
+        issue_o(it);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9) =====================
+    const int ew = warp - 2, q = warp & 3, half = ew >> 2;
+    const int row_l = q * 32 + lane, sw7 = lane & 7;
+    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
+    const int scols = p.npad / 2;                               // score columns of this warp
+    const int sc0 = half * scols;
+    const bool o_active = p.dh >= 128 || half == 0;
+    const int ocols = p.dh >= 128 ? p.dh / 2 : p.dh;            // head-dimension columns of this warp
+    const int oc0 = p.dh >= 128 ? half * ocols : 0;
+    const uint32_t stage = sbase + p.off_p + (uint32_t)ew * 4096u;   // output staging inside the (then idle) P buffer
+    uint32_t it = 0;
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++it) {
+      const int qt = u % p.nqt, h = (u / p.nqt) % p.H, b = u / (p.nqt * p.H);
+      const uint32_t ph = it & 1;
+      // ---- softmax ----
+      mbar_wait(&bar[A_SFULL], ph);
+      tc_fence_after();
+      float m = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < scols; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)(sc0 + c), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (sc0 + c + j < p.nkv) m = fmaxf(m, __uint_as_float(v[j]));
+      }
+      {
+        xch[(half * 4 + q) * 32 + lane] = m;
+        named_bar_sync(2 + q, 64);
+        m = fmaxf(m, xch[((half ^ 1) * 4 + q) * 32 + lane]);
+      }
+      // the previous unit's output stores read their staging boxes out of the P buffer: they must have left it, in every
+      // warp, before new probabilities are written
+      if (it > 0) {
+        if (lane == 0) bulk_wait_read0();
+        named_bar_sync(1, 256);
+      }
+      const float ms = m * p.scale_log2e;
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < scols; c += 32) {
+        const int col = sc0 + c;
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)col, v);
+        float e[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) e[j] = col + j < p.nkv ? ex2(fmaf(__uint_as_float(v[j]), p.scale_log2e, -ms)) : 0.f;
+        const uint32_t prow = sbase + p.off_p + (uint32_t)(col >> 6) * 16384u + (uint32_t)row_l * 128u;
+        const int c16 = (col & 63) >> 3;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int w2 = 0; w2 < 4; ++w2) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(e[8 * t + 2 * w2], e[8 * t + 2 * w2 + 1]);
+            sum += __low2float(h2) + __high2float(h2);       // the denominator sums what the second GEMM multiplies
+            pk[w2] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          sts128(prow + (uint32_t)(((c16 + t) ^ sw7) << 4), pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&bar[A_SEMPTY]); mbar_arrive(&bar[A_PREADY]); }
+      {
+        xch[256 + (half * 4 + q) * 32 + lane] = sum;
+        named_bar_sync(2 + q, 64);
+        sum += xch[256 + ((half ^ 1) * 4 + q) * 32 + lane];
+      }
+      const float inv = 1.f / sum;
+      // ---- output ----
+      mbar_wait(&bar[A_OFULL], ph);
+      tc_fence_after();
+      if (o_active) {
+#pragma unroll 1
+        for (int c = 0; c < ocols; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + 256u + (uint32_t)(oc0 + c), v);
+          const int hc = (c >> 5) & 1;                        // half of the 64-column staging box
+          if (hc == 0 && c > 0) {                             // second box of this unit: the first one's store must be done
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            sts128(stage + (uint32_t)(lane * 128 + (((t + 4 * hc) ^ sw7) << 4)),
+                   pack_bf16(__uint_as_float(v[8 * t]) * inv, __uint_as_float(v[8 * t + 1]) * inv),
+                   pack_bf16(__uint_as_float(v[8 * t + 2]) * inv, __uint_as_float(v[8 * t + 3]) * inv),
+                   pack_bf16(__uint_as_float(v[8 * t + 4]) * inv, __uint_as_float(v[8 * t + 5]) * inv),
+                   pack_bf16(__uint_as_float(v[8 * t + 6]) * inv, __uint_as_float(v[8 * t + 7]) * inv));
+          if (hc == 1 || c + 32 >= ocols) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&tmO, stage, h * p.dh + oc0 + (c & ~63), qt * 128 + q * 32, b);
+              bulk_commit();
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar[A_OEMPTY]);
+    }
+    if (lane == 0) bulk_wait_read0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace
+
+bool tc_attn_fused_supported(int nq, int nkv, int dh) {
+  if (!(nq >= 1 && nkv >= 1 && nkv <= 256 && (dh == 64 || dh == 128 || dh == 256))) return false;
+  const int npad = (nkv + 63) / 64 * 64, dkb = dh / 64, nkb = npad / 64;
+  const size_t bytes = (size_t)dkb * 16384 + (size_t)dkb * npad * 128 + (size_t)nkb * dkb * 8192 + (size_t)nkb * 16384 + 256 + 2048;
+  return bytes <= 227 * 1024 && (size_t)nkb * 16384 >= 8 * 4096;   // the P buffer also hosts the output staging boxes
+}
+
+// q/k/v: bf16 views [B*nq | B*nkv, ld*] with head h at columns h*dh; out bf16 [B, nq, H*dh]
+int tc_attn_fused(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v, int ldv, int B, int H,
+                  int nq, int nkv, int dh, __nv_bfloat16* out, int ldo, cudaStream_t s) {
+  MOCHA_CHECK_ARG(tc_attn_fused_supported(nq, nkv, dh), "tc_attn_fused: unsupported geometry nq=%d nkv=%d dh=%d", nq, nkv, dh);
+  MOCHA_CHECK_ARG(q && k && v && out && B > 0 && H > 0, "tc_attn_fused: null operand");
+  MOCHA_CHECK_ARG(ldo == H * dh && (ldq % 8) == 0 && (ldk % 8) == 0 && (ldv % 8) == 0, "tc_attn_fused: bad leading dimensions");
+  AttnParams p{};
+  p.B = B; p.H = H; p.nq = nq; p.nkv = nkv; p.dh = dh;
+  p.npad = (nkv + 63) / 64 * 64;
+  p.nqt = ceil_div(nq, 128);
+  p.units = B * H * p.nqt;
+  p.scale_log2e = 1.4426950408889634f / sqrtf((float)dh);
+  const int dkb = dh / 64, nkb = p.npad / 64;
+  p.off_k = (uint32_t)dkb * 16384u;
+  p.off_v = p.off_k + (uint32_t)dkb * (uint32_t)p.npad * 128u;
+  p.off_v = (p.off_v + 1023u) & ~1023u;
+  p.off_p = p.off_v + (uint32_t)nkb * (uint32_t)dkb * 8192u;
+  p.off_bar = p.off_p + (uint32_t)nkb * 16384u;
+  p.off_xch = p.off_bar + 256u;
+  const size_t smem = (size_t)p.off_xch + 2048;
+  MOCHA_CHECK_ARG(smem <= 227 * 1024, "tc_attn_fused: shared-memory plan of %zu B exceeds 227 KB", smem);
+  const int inner = H * dh;
+  CUtensorMap tmQ, tmK, tmV, tmO;
+  MOCHA_TRY(tc_make_tmap(&tmQ, q, (unsigned long long)B * nq, (unsigned long long)inner, 128, (unsigned long long)ldq));
+  MOCHA_TRY(tc_make_tmap(&tmK, k, (unsigned long long)B * nkv, (unsigned long long)inner, p.npad, (unsigned long long)ldk));
+  MOCHA_TRY(tc_make_tmap(&tmV, v, (unsigned long long)B * nkv, (unsigned long long)inner, 64, (unsigned long long)ldv));
+  MOCHA_TRY(tc_make_out_tmap(&tmO, out, (unsigned long long)ldo, (unsigned long long)nq, (unsigned long long)B,
+                             (unsigned long long)ldo, false, 0, true));
+  static size_t configured = 0;
+  if (smem > configured) {
+    MOCHA_CUDA(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = 227 * 1024;
+  }
+  const int grid = p.units < tc_num_sms() ? p.units : tc_num_sms();
+  launch_k(attn_kernel, dim3((unsigned)grid), dim3(FA_THREADS), smem, s, tmQ, tmK, tmV, tmO, p);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("attn_kernel");
+  return MOCHA_OK;
+}
+
+}  // namespace mocha

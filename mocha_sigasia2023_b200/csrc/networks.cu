@@ -626,3 +626,10 @@ extern "C" int mocha_block_tail(const void* A0, int lda, int K0, const void* W0,
                  (const __nv_bfloat16*)W1, b1, (const __nv_bfloat16*)W2, b2, g2, be2, eps, O32, (__nv_bfloat16*)O16, M,
                  (cudaStream_t)stream);
 }
+
+// Stand-alone entry of the fused attention core (unit tests, bench.py): bf16 q / k / v views, bf16 output.
+extern "C" int mocha_attention_core(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int B, int H, int nq,
+                                    int nkv, int dh, void* out, int ldo, mocha_stream_t stream) {
+  return tc_attn_fused((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk, (const __nv_bfloat16*)v, ldv, B, H, nq, nkv, dh,
+                       (__nv_bfloat16*)out, ldo, (cudaStream_t)stream);
+}

@@ -49,6 +49,16 @@ inline bool use_fused_tail(int D) {
   return !off && D == 256;
 }
 
+// Attention of the bf16 path: one fused launch (fused_attn.cu) when the geometry fits, else the two-launch sequence
+// (scores + softmax epilogue, P V) of gemm_tc.cu. MOCHA_NO_FUSED_ATTN=1 forces the latter (A/B runs).
+int attn(cudaStream_t s, Workspace& ws, const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv, int B, int H, int nq,
+         int nkv, int dh, bf16* out, int ldo) {
+  static const bool off = getenv("MOCHA_NO_FUSED_ATTN") != nullptr;
+  if (!off && tc_attn_fused_supported(nq, nkv, dh) && ldo == H * dh)
+    return tc_attn_fused(q, ldq, k, ldk, v, ldv, B, H, nq, nkv, dh, out, ldo, s);
+  return tc_attention_ex(nullptr, q, ldq, nullptr, k, ldk, nullptr, v, ldv, B, H, nq, nkv, dh, nullptr, h16(out), ldo, ws, s);
+}
+
 // fused block tail (fused_tail.cu) on fp32 weight pointers: looks up the registered bf16 mirrors
 int tail(cudaStream_t s, const bf16* A0, int K0, const float* W0, const float* b0, const float* R0, const float* g1,
          const float* be1, int Hd, int act, const float* W1, const float* b1, const float* W2, const float* b2,
@@ -134,8 +144,7 @@ int encoder_bf16(const mocha_generator_weights* w, const float* tokens, int B, f
     MOCHA_CHECK_ARG(L.wqkv && L.wo && L.bo && L.w1 && L.b1 && L.w2 && L.b2, "mocha_encoder_fwd: layer %d weights missing", l);
     const bool last = l == d.enc_depth - 1;
     MOCHA_TRY(tc.lin(x16, d.D, L.wqkv, nullptr, 0, nullptr, h16(qkv), R, 3 * inner, d.D, ACT_NONE));
-    MOCHA_TRY(tc_attention_ex(nullptr, qkv, 3 * inner, nullptr, qkv + inner, 3 * inner, nullptr, qkv + 2 * inner,
-                              3 * inner, B, d.heads, n, n, d.enc_dh, S, h16(att), inner, ws, s));
+    MOCHA_TRY(attn(s, ws, qkv, 3 * inner, qkv + inner, 3 * inner, qkv + 2 * inner, 3 * inner, B, d.heads, n, n, d.enc_dh, att, inner));
     float* dst = last ? encoded : xb;
     if (use_fused_tail(d.D) && tc_tail_supported(R, inner, d.mlp)) {
       // out-projection + residual + GELU FFN + residual in one launch (x and dst may alias: tiles are row-local)
@@ -197,8 +206,7 @@ int decoder_bf16(const mocha_generator_weights* w, const float* src, const float
     MOCHA_TRY(tc.lin(qin, d.D, L.wq, nullptr, 0, nullptr, h16(q), R, inner, d.D, ACT_NONE));
     MOCHA_TRY(tc.lin(sty_in, d.D, L.wk, nullptr, 0, nullptr, h16(k), R, inner, d.D, ACT_NONE));
     MOCHA_TRY(tc.lin(cha16, d.D, L.wv, nullptr, 0, nullptr, h16(v), R, inner, d.D, ACT_NONE));
-    MOCHA_TRY(tc_attention_ex(nullptr, q, inner, nullptr, k, inner, nullptr, v, inner, B, d.heads, n, n, d.dec_dh, S,
-                              h16(att), inner, ws, s));
+    MOCHA_TRY(attn(s, ws, q, inner, k, inner, v, inner, B, d.heads, n, n, d.dec_dh, att, inner));
     float* dst = (l == d.dec_depth - 1) ? decoded : xb;
     if (use_fused_tail(d.D) && tc_tail_supported(R, inner, d.mlp)) {
       MOCHA_TRY(tail(s, att, inner, L.wo, L.bo, x1, nullptr, nullptr, d.mlp, ACT_GELU, L.w1, L.b1, L.w2, L.b2, nullptr, nullptr,
@@ -286,8 +294,7 @@ int cvae_bf16(const mocha_cvae_weights* w, const float* cond, int B, int ncond, 
       bf16* att2 = hid;       // [2B, D]
       MOCHA_TRY(tc.lin(x16, D, L.in_w + (size_t)D * D, L.in_b + D, 0, nullptr, h16(kv), Rp, 2 * D, D, ACT_NONE));
       MOCHA_TRY(tc.lin(xq16, D, L.in_w, L.in_b, 0, nullptr, h16(q2), R2, D, D, ACT_NONE));
-      MOCHA_TRY(tc_attention_ex(nullptr, q2, D, nullptr, kv, 2 * D, nullptr, kv + D, 2 * D, B, H, 2, np, dh, S, h16(att2), D,
-                                ws, s));
+      MOCHA_TRY(attn(s, ws, q2, D, kv, 2 * D, kv + D, 2 * D, B, H, 2, np, dh, att2, D));
       if (use_fused_tail(D) && tc_tail_supported(R2, D, w->dff)) {
         MOCHA_TRY(tail(s, att2, D, L.out_w, L.out_b, xq, L.n1_g, L.n1_b, w->dff, ACT_RELU, L.l1_w, L.l1_b, L.l2_w, L.l2_b,
                        L.n2_g, L.n2_b, w->ln_eps, xq, nullptr, R2));
@@ -306,8 +313,7 @@ int cvae_bf16(const mocha_cvae_weights* w, const float* cond, int B, int ncond, 
       break;
     }
     MOCHA_TRY(tc.lin(x16, D, L.in_w, L.in_b, 0, nullptr, h16(qkv), Rp, 3 * D, D, ACT_NONE));
-    MOCHA_TRY(tc_attention_ex(nullptr, qkv, 3 * D, nullptr, qkv + D, 3 * D, nullptr, qkv + 2 * D, 3 * D, B, H, np, np, dh,
-                              S, h16(att), D, ws, s));
+    MOCHA_TRY(attn(s, ws, qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, B, H, np, np, dh, att, D));
     if (use_fused_tail(D) && tc_tail_supported(Rp, D, w->dff)) {
       // x <- LN2(y + FF(y)), y = LN1(x + SA(x)): one launch, in place (tiles are row-local)
       MOCHA_TRY(tail(s, att, D, L.out_w, L.out_b, x, L.n1_g, L.n1_b, w->dff, ACT_RELU, L.l1_w, L.l1_b, L.l2_w, L.l2_b, L.n2_g,
@@ -335,8 +341,7 @@ int cvae_bf16(const mocha_cvae_weights* w, const float* cond, int B, int ncond, 
       MOCHA_TRY(broadcast_rows(w->dec0_sa, dy, B, (long long)nq * D, s, dy16));
     } else {
       MOCHA_TRY(tc.lin(dx16, D, L.sa_in_w, L.sa_in_b, 0, nullptr, h16(qkv), Rq, 3 * D, D, ACT_NONE));
-      MOCHA_TRY(tc_attention_ex(nullptr, qkv, 3 * D, nullptr, qkv + D, 3 * D, nullptr, qkv + 2 * D, 3 * D, B, H, nq, nq, dh,
-                                S, h16(att), D, ws, s));
+      MOCHA_TRY(attn(s, ws, qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, B, H, nq, nq, dh, att, D));
       if (use_fused_tail(D) && tc_tail_supported(Rq, D, 0)) {
         MOCHA_TRY(tail(s, att, D, L.sa_out_w, L.sa_out_b, dx, L.n1_g, L.n1_b, 0, ACT_NONE, nullptr, nullptr, nullptr, nullptr,
                        nullptr, nullptr, w->ln_eps, dy, dy16, Rq));
@@ -347,8 +352,7 @@ int cvae_bf16(const mocha_cvae_weights* w, const float* cond, int B, int ncond, 
     }
     MOCHA_TRY(tc.lin(dy16, D, L.ca_in_w, L.ca_in_b, 0, nullptr, h16(dq), Rq, D, D, ACT_NONE));
     MOCHA_TRY(tc.lin(mem, D, L.ca_in_w + (size_t)D * D, L.ca_in_b + D, 0, nullptr, h16(memkv), Rm, 2 * D, D, ACT_NONE));
-    MOCHA_TRY(tc_attention_ex(nullptr, dq, D, nullptr, memkv, 2 * D, nullptr, memkv + D, 2 * D, B, H, nq, nm, dh, S,
-                              h16(att), D, ws, s));
+    MOCHA_TRY(attn(s, ws, dq, D, memkv, 2 * D, memkv + D, 2 * D, B, H, nq, nm, dh, att, D));
     const bool fused = use_fused_tail(D) && tc_tail_supported(Rq, D, w->dff);
     const bool last = l == w->depth - 1;
     if (fused) {

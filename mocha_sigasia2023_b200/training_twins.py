@@ -36,14 +36,18 @@ def _character_space(pos, txy, vel, ang, parents):
 def convert_YtilToX(Ytil: torch.Tensor, Ygrd: torch.Tensor, parents) -> torch.Tensor:
     """trainer.py:337-374. Ytil [B,T,V,15] decoded window, Ygrd [B,T,1,15] root stream -> X [B,T,V+1,15]."""
     for t in (Ytil, Ygrd):
-        _lib.require_cuda(t)
+        if not t.is_cuda:
+            raise _lib.MochaError("convert_YtilToX needs CUDA tensors (no CPU fallback)")
     pos, txy, vel, ang = (torch.cat([g, y], dim=2) for g, y in zip(_split(Ygrd.float()), _split(Ytil.float())))
     X, _ = _character_space(pos, txy, vel, ang, parents)
     return X
 
 
 def recon_criterion(Ytil: torch.Tensor, Ygt: torch.Tensor, parents) -> torch.Tensor:
-    """Forward value of trainer.py:249-335 (no gradient). Ytil [B,T,V,15], Ygt [B,T,V+1,15]."""
+    """Forward value of trainer.py:249-335 (no gradient). Ytil [B,T,V,15], Ygt [B,T,V+1,15].
+    The FK runs on quaternions (mocha_xy_to_quat orthonormalises the 6-D columns); the reference's matrix FK keeps the
+    first column un-normalised (txform.py:22-33), so the two agree when the 6-D columns are orthonormal - exactly for
+    ground-truth windows, up to the network's rotation noise for decoded ones."""
     dt = 1.0 / 60.0
     g_pos, g_txy, g_vel, g_ang = _split(Ygt.float())
     t_pos, t_txy, t_vel, t_ang = _split(Ytil.float())

@@ -19,6 +19,15 @@ def inputs(seed=3, B=2, T=8, V=24):
     def win(J):
         y = rng.standard_normal((B, T, J, 15)).astype(np.float32)
         y[..., :3] *= 0.3
+        # 6-D rotation channels: the first two columns of proper rotation matrices (what a trained network emits up to
+        # noise). The reference's matrix FK keeps the first column un-normalised (txform.py:22-33) while the quaternion
+        # kernels normalise, so the two only agree on orthonormal columns.
+        q = rng.standard_normal((B, T, J, 4))
+        q /= np.linalg.norm(q, axis=-1, keepdims=True)
+        w, x, yq, z = q[..., 0], q[..., 1], q[..., 2], q[..., 3]
+        c0 = np.stack([1 - 2 * (yq * yq + z * z), 2 * (x * yq + w * z), 2 * (x * z - w * yq)], -1)
+        c1 = np.stack([2 * (x * yq - w * z), 1 - 2 * (x * x + z * z), 2 * (yq * z + w * x)], -1)
+        y[..., 3:9] = np.stack([c0, c1], -1).reshape(B, T, J, 6).astype(np.float32)
         return y
     return win(V), win(V + 1)
 

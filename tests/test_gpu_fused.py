@@ -1,5 +1,7 @@
 """Fused tcgen05 kernels of the transformer layers vs a plain PyTorch fp32 reference of the same op (operands rounded to
 bf16 exactly where the kernel rounds them: the GEMM inputs, the bf16 copy of Y and the hidden activations)."""
+import ctypes as C
+
 import numpy as np
 import pytest
 import torch
@@ -77,3 +79,42 @@ def test_block_tail_vs_torch(M, K0, Hd, act, ln1, ln2):
 def test_block_tail_no_bias_no_residual():
     err32, err16 = _run_tail(640, 512, 512, 1, False, False, res=False, bias=False, seed=3)
     assert err32 < 2e-3 and err16 < 8e-3
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused attention core
+# ---------------------------------------------------------------------------------------------------
+def _attn_ref(q, k, v, B, H, nq, nkv, dh):
+    qf = q.float().view(B, nq, H, dh).permute(0, 2, 1, 3)
+    kf = k.float().view(B, nkv, H, dh).permute(0, 2, 1, 3)
+    vf = v.float().view(B, nkv, H, dh).permute(0, 2, 1, 3)
+    s = (qf @ kf.transpose(-1, -2)) / dh ** 0.5
+    p = torch.exp(s - s.amax(-1, keepdim=True)).to(torch.bfloat16).float()     # the kernel rounds P to bf16 ...
+    o = (p @ vf) / p.sum(-1, keepdim=True)                                     # ... and normalises by the rounded sum
+    return o.permute(0, 2, 1, 3).reshape(B, nq, H * dh)
+
+
+@pytest.mark.parametrize("B,H,nq,nkv,dh", [
+    (5, 4, 90, 90, 128),       # Generator encoder self-attention
+    (3, 4, 90, 90, 256),       # Generator decoder cross-attention
+    (3, 4, 182, 182, 64),      # CVAE prior: two query tiles per (clip, head), keys padded to 192
+    (4, 4, 90, 181, 64),       # CVAE decoder cross-attention
+    (6, 4, 2, 182, 64),        # CVAE prior last layer: only the mu / logvar rows query
+    (128, 4, 90, 90, 128),     # the benchmarked batch: 512 units over 148 persistent CTAs
+    (2, 2, 33, 100, 64),
+])
+def test_attention_core_vs_torch(B, H, nq, nkv, dh):
+    g = torch.Generator(device="cuda").manual_seed(B * 7 + nq)
+    inner = H * dh
+    # q / k / v live side by side in one projection buffer, like the QKV GEMM leaves them
+    qkv_q = torch.randn((B * nq, inner), generator=g, device="cuda").to(torch.bfloat16)
+    kv = torch.randn((B * nkv, 2 * inner), generator=g, device="cuda").to(torch.bfloat16)
+    k, v = kv[:, :inner], kv[:, inner:]
+    out = torch.full((B, nq, inner), float("nan"), device="cuda", dtype=torch.bfloat16)
+    lib = _lib.load()
+    _lib.check(lib.mocha_attention_core(_lib.ptr(qkv_q), inner, C.c_void_p(k.data_ptr()), 2 * inner, C.c_void_p(v.data_ptr()),
+                                        2 * inner, B, H, nq, nkv, dh, _lib.ptr(out), inner, _lib.stream_ptr()), "attention_core")
+    torch.cuda.synchronize()
+    want = _attn_ref(qkv_q, k.contiguous(), v.contiguous(), B, H, nq, nkv, dh)
+    err = (out.float() - want).abs().max().item() / want.abs().max().item()
+    assert err < 1e-2, f"attention core error {err:.3e} of range"
