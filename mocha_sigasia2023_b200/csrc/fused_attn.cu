@@ -27,6 +27,17 @@ namespace {
 constexpr int FA_THREADS = 320;
 enum { A_QKFULL = 0, A_QKEMPTY, A_VFULL, A_VEMPTY, A_SFULL, A_SEMPTY, A_PREADY, A_OFULL, A_OEMPTY, A_COUNT };
 
+#ifdef MOCHA_TRACE
+// trace build: per-CTA clock64 time line (tools/attn_trace.py), 64 slots per CTA: 16 per unit for the first 4 units
+__device__ unsigned long long* g_fa_trace = nullptr;
+#define FA_TRACE(it, slot)                                                                                          \
+  do {                                                                                                              \
+    if (g_fa_trace && (it) < 4) g_fa_trace[(size_t)blockIdx.x * 64 + (it) * 16 + (slot)] = (unsigned long long)clock64(); \
+  } while (0)
+#else
+#define FA_TRACE(it, slot) do { } while (0)
+#endif
+
 struct AttnParams {
   int B, H, nq, nkv, dh, npad;   // npad = nkv rounded up to a multiple of 64 (<= 256)
   int nqt;                       // query tiles per (clip, head)
@@ -51,6 +62,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
             const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   pdl_trigger();
+  if (threadIdx.x == 0) FA_TRACE(0, 14);   // CTA start
   const uint32_t sbase = smem_u32(smem);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + A_COUNT);
@@ -75,6 +87,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   pdl_wait();
+  if (threadIdx.x == 0) FA_TRACE(0, 15);   // prologue done
 
   const int dkb = p.dh / 64;          // k-blocks of the head dimension
   const int nkb = p.npad / 64;        // k-blocks of the key dimension
@@ -89,12 +102,14 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         const int qt = u % p.nqt, h = (u / p.nqt) % p.H, b = u / (p.nqt * p.H);
         const uint32_t ph = it & 1;
         mbar_wait(&bar[A_QKEMPTY], ph ^ 1);
+        FA_TRACE(it, 0);   // producer: Q / K buffers free
         mbar_expect_tx(&bar[A_QKFULL], q_bytes + k_bytes);
         for (int kb = 0; kb < dkb; ++kb) {
           tma_load_2d(sbase + (uint32_t)kb * 16384u, &tmQ, &bar[A_QKFULL], h * p.dh + kb * 64, b * p.nq + qt * 128);
           tma_load_2d(sbase + p.off_k + (uint32_t)kb * (uint32_t)p.npad * 128u, &tmK, &bar[A_QKFULL], h * p.dh + kb * 64, b * p.nkv);
         }
         mbar_wait(&bar[A_VEMPTY], ph ^ 1);
+        FA_TRACE(it, 1);   // producer: V buffer free
         mbar_expect_tx(&bar[A_VFULL], v_bytes);
         for (int kb = 0; kb < nkb; ++kb)
           for (int a = 0; a < dkb; ++a)
@@ -109,8 +124,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       auto issue_s = [&](uint32_t it) {
         const uint32_t ph = it & 1;
         mbar_wait(&bar[A_QKFULL], ph);
+        FA_TRACE(it, 2);   // MMA: Q / K landed
         mbar_wait(&bar[A_SEMPTY], ph ^ 1);
         tc_fence_after();
+        FA_TRACE(it, 3);   // MMA: score accumulator free, issuing S
         for (int kb = 0; kb < dkb; ++kb) {
           const uint64_t adesc = make_smem_desc(sbase + (uint32_t)kb * 16384u);
           const uint64_t bdesc = make_smem_desc(sbase + p.off_k + (uint32_t)kb * (uint32_t)p.npad * 128u);
@@ -123,9 +140,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       auto issue_o = [&](uint32_t it) {
         const uint32_t ph = it & 1;
         mbar_wait(&bar[A_PREADY], ph);
+        FA_TRACE(it, 4);   // MMA: P ready
         mbar_wait(&bar[A_VFULL], ph);
         mbar_wait(&bar[A_OEMPTY], ph ^ 1);
         tc_fence_after();
+        FA_TRACE(it, 5);   // MMA: V landed + output accumulator free, issuing P V
         for (int kb = 0; kb < nkb; ++kb) {
           const uint64_t adesc = make_smem_desc(sbase + p.off_p + (uint32_t)kb * 16384u);
           // MN-major V: one MMA consumes 16 key rows = 2 KB of every 64-column atom
@@ -163,6 +182,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       // ---- softmax ----
       mbar_wait(&bar[A_SFULL], ph);
       tc_fence_after();
+      if (warp == 2 && lane == 0) FA_TRACE(it, 8);    // epilogue: scores ready
       float m = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < scols; c += 32) {
@@ -183,6 +203,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         if (lane == 0) bulk_wait_read0();
         named_bar_sync(1, 256);
       }
+      if (warp == 2 && lane == 0) FA_TRACE(it, 9);    // epilogue: row max known, P buffer free
       const float ms = m * p.scale_log2e;
       float sum = 0.f;
 #pragma unroll 1
@@ -211,6 +232,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { mbar_arrive(&bar[A_SEMPTY]); mbar_arrive(&bar[A_PREADY]); }
+      if (warp == 2 && lane == 0) FA_TRACE(it, 10);   // epilogue: P written
       {
         xch[256 + (half * 4 + q) * 32 + lane] = sum;
         named_bar_sync(2 + q, 64);
@@ -220,6 +242,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       // ---- output ----
       mbar_wait(&bar[A_OFULL], ph);
       tc_fence_after();
+      if (warp == 2 && lane == 0) FA_TRACE(it, 11);   // epilogue: output accumulator ready
       if (o_active) {
 #pragma unroll 1
         for (int c = 0; c < ocols; c += 32) {
@@ -250,6 +273,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar[A_OEMPTY]);
+      if (warp == 2 && lane == 0) FA_TRACE(it, 12);   // epilogue: output handed to TMA
     }
     if (lane == 0) bulk_wait_read0();
   }
@@ -313,3 +337,9 @@ int tc_attn_fused(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int l
 }
 
 }  // namespace mocha
+
+#ifdef MOCHA_TRACE
+extern "C" int mocha_debug_set_attn_trace(unsigned long long* buf) {
+  return cudaMemcpyToSymbol(mocha::g_fa_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : 1;
+}
+#endif

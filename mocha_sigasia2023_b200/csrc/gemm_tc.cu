@@ -1972,6 +1972,32 @@ int tc_linear_bf16_img(const __nv_bfloat16* A16, int lda, const __nv_bfloat16* W
                      ceil_div(K, BLOCK_K), epi, s);
 }
 
+// nb independent linear layers of one shape in ONE launch: out[g] = A[g] W[g]^T with A16 [nb, R, K], W16 [nb, N, K] and
+// out16 [nb, R, N] stacked densely (the decoder's q / k / v projections: three inputs, three weights). Runs as the images
+// of the batched-head mode (H = 1): image g selects its A rows, its weight rows and its output image, so the persistent
+// CTAs walk nb x tiles without a launch ramp / tail per layer.
+int tc_linear_bf16_grouped(const __nv_bfloat16* A16, const __nv_bfloat16* W16, __nv_bfloat16* out16, int nb, int R, int N,
+                           int K, cudaStream_t s) {
+  MOCHA_CHECK_ARG(A16 && W16 && out16 && nb >= 1, "tc_linear_grouped: bad operands");
+  MOCHA_CHECK_ARG(tc_linear_supported(R, N, K) && N % 64 == 0, "tc_linear_grouped: unsupported shape R=%d N=%d K=%d", R, N, K);
+  CUtensorMap tmA;
+  MOCHA_TRY(make_tmap(&tmA, A16, (unsigned long long)nb * R, (unsigned long long)K, BLOCK_M));
+  TcShape sh{};
+  sh.nb = nb; sh.H = 1;
+  sh.rows_out_per_b = R;
+  sh.tiles_m_per_b = ceil_div(R, BLOCK_M);
+  sh.tiles_m_total = sh.tiles_m_per_b * nb;
+  sh.src_rows_per_b = R; sh.a_rows_h = 0; sh.a_cols_h = 0;
+  sh.b_rows_b = N; sh.b_rows_h = 0; sh.b_cols_h = 0;
+  sh.c_img_b = (long long)R * N; sh.c_img_h = 0;
+  sh.taps = 1; sh.kb_per_tap = ceil_div(K, BLOCK_K); sh.tap_row_stride = 0;
+  LinearEpi epi{nullptr, N, N, nullptr, 0, nullptr, ACT_NONE, out16, 0};
+  MOCHA_TRY(setup_out_tma(epi, (unsigned long long)R, (unsigned long long)nb));
+  if (epi.tma != 1) return set_error(MOCHA_ERR_ARG, "tc_linear_grouped: output is not TMA-storable");
+  return dispatch_bn(pick_bn(sh.tiles_m_total, N, ceil_div(K, BLOCK_K)), tmA, W16, (unsigned long long)nb * N, (unsigned long long)K, sh,
+                     N, ceil_div(K, BLOCK_K), epi, s);
+}
+
 int tc_linear(const float* A, const float* W, const float* bias, int bias_period, const float* res, float* C, int M,
               int N, int K, int act, int a_lrelu, Workspace& ws, cudaStream_t s) {
   const __nv_bfloat16* W16 = tc_lookup_bf16(W);

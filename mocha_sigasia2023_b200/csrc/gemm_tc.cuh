@@ -46,6 +46,9 @@ struct TcOut {
 // Same with operands already in bf16 (A16 [M,K] with row pitch lda, W16 [N,K], K-major, 16B-aligned rows).
 int tc_linear_bf16(const __nv_bfloat16* A16, int lda, const __nv_bfloat16* W16, const float* bias, int bias_period,
                    const float* res, TcOut out, int M, int N, int K, int act, cudaStream_t s);
+// nb stacked linear layers of one shape in one launch: out16[g] = A16[g] W16[g]^T, A16 [nb,R,K], W16 [nb,N,K], out16 [nb,R,N]
+int tc_linear_bf16_grouped(const __nv_bfloat16* A16, const __nv_bfloat16* W16, __nv_bfloat16* out16, int nb, int R, int N,
+                           int K, cudaStream_t s);
 // fp32 -> bf16 (optionally through LeakyReLU(0.2))
 int tc_cast(const float* x, __nv_bfloat16* y, long long n, int lrelu, cudaStream_t s);
 

@@ -171,16 +171,19 @@ int decoder_bf16(const mocha_generator_weights* w, const float* src, const float
   bf16* smean16 = ws.take<bf16>((size_t)B * d.D);
   bf16* shid = ws.take<bf16>((size_t)B * 2 * d.D);
   float* gb = ws.take<float>((size_t)B * 2 * d.D);
-  bf16* sty_in = ws.take<bf16>((size_t)R * d.D);
-  bf16* cha16 = ws.take<bf16>((size_t)R * d.D);
+  // the three projection inputs and outputs are stacked so that q / k / v run as ONE grouped GEMM launch
+  bf16* in3 = ws.take<bf16>((size_t)3 * R * d.D);          // [IN(x1) | IN(style) | style]
+  bf16* qin = in3;
+  bf16* sty_in = in3 + (size_t)R * d.D;
+  bf16* cha16 = in3 + (size_t)2 * R * d.D;
   float* x1 = ws.take<float>((size_t)R * d.D);
-  bf16* qin = ws.take<bf16>((size_t)R * d.D);
   float* x2 = ws.take<float>((size_t)R * d.D);
   bf16* x2h = ws.take<bf16>((size_t)R * d.D);
   float* xb = ws.take<float>((size_t)R * d.D);
-  bf16* q = ws.take<bf16>((size_t)R * inner);
-  bf16* k = ws.take<bf16>((size_t)R * inner);
-  bf16* v = ws.take<bf16>((size_t)R * inner);
+  bf16* qkv3 = ws.take<bf16>((size_t)3 * R * inner);
+  bf16* q = qkv3;
+  bf16* k = qkv3 + (size_t)R * inner;
+  bf16* v = qkv3 + (size_t)2 * R * inner;
   bf16* att = ws.take<bf16>((size_t)R * inner);
   float* S = nullptr;   // scores stay in TMEM (softmax fused into the Q K^T epilogue)
   bf16* hid = ws.take<bf16>((size_t)R * d.mlp);
@@ -203,9 +206,16 @@ int decoder_bf16(const mocha_generator_weights* w, const float* src, const float
       MOCHA_TRY(instance_norm_tokens(x, B, n, d.D, eps, gb, x1, nullptr, nullptr, nullptr, s));
       MOCHA_TRY(instance_norm_tokens(x1, B, n, d.D, eps, nullptr, nullptr, nullptr, nullptr, nullptr, s, qin));
     }
-    MOCHA_TRY(tc.lin(qin, d.D, L.wq, nullptr, 0, nullptr, h16(q), R, inner, d.D, ACT_NONE));
-    MOCHA_TRY(tc.lin(sty_in, d.D, L.wk, nullptr, 0, nullptr, h16(k), R, inner, d.D, ACT_NONE));
-    MOCHA_TRY(tc.lin(cha16, d.D, L.wv, nullptr, 0, nullptr, h16(v), R, inner, d.D, ACT_NONE));
+    static const bool no_group = getenv("MOCHA_NO_GROUPED_QKV") != nullptr;
+    const bf16* wq16 = tc_lookup_bf16(L.wq);
+    if (!no_group && wq16 && L.wk == L.wq + (size_t)inner * d.D && L.wv == L.wk + (size_t)inner * d.D && inner % 64 == 0) {
+      // to_q / to_k / to_v sit back to back in the packed blob: three inputs x three weights in one launch
+      MOCHA_TRY(tc_linear_bf16_grouped(in3, wq16, qkv3, 3, R, inner, d.D, s));
+    } else {
+      MOCHA_TRY(tc.lin(qin, d.D, L.wq, nullptr, 0, nullptr, h16(q), R, inner, d.D, ACT_NONE));
+      MOCHA_TRY(tc.lin(sty_in, d.D, L.wk, nullptr, 0, nullptr, h16(k), R, inner, d.D, ACT_NONE));
+      MOCHA_TRY(tc.lin(cha16, d.D, L.wv, nullptr, 0, nullptr, h16(v), R, inner, d.D, ACT_NONE));
+    }
     MOCHA_TRY(attn(s, ws, q, inner, k, inner, v, inner, B, d.heads, n, n, d.dec_dh, att, inner));
     float* dst = (l == d.dec_depth - 1) ? decoded : xb;
     if (use_fused_tail(d.D) && tc_tail_supported(R, inner, d.mlp)) {
