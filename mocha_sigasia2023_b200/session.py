@@ -9,6 +9,7 @@ whole step can be captured once into a CUDA graph (`capture()`) and replayed per
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -115,6 +116,15 @@ class CharacterizationSession:
         self.parts = [(cuts[i], cuts[i + 1]) for i in range(lanes) if cuts[i + 1] > cuts[i]]
         self.lane_ws = [self.ws] + [torch.empty_like(self.ws) for _ in self.parts[1:]]
         self.lane_streams = [torch.cuda.Stream(device=dev) for _ in self.parts[1:]]
+        # The matcher's result is only read at the init frame (it seeds the autoregression) and by the optional cm_trans
+        # decode; in the steady state it is a side branch of the frame, so it runs on its own stream (own workspace)
+        # concurrently with the CVAE / decoder chain and is joined at the end of the frame. Its kernels are small
+        # (split-K coarse pass, re-rank) and fit next to the 90-CTA block tails.
+        self.match_async = os.environ.get("MOCHA_MATCH_ASYNC", "1") != "0"
+        mbytes = max(self.lib.mocha_match_exact_workspace_bytes(B, self.tree.N, 1),
+                     self.lib.mocha_match_tc_workspace_bytes(B, self.tree.N, self.tree.D, self.tree.kc))
+        self.match_ws = [torch.empty(mbytes + 4096, dtype=torch.uint8, device=dev) for _ in self.parts]
+        self.match_streams = [torch.cuda.Stream(device=dev) for _ in self.parts]
         self.frame = 0
         self.graph = None
         self.deterministic = False
@@ -178,7 +188,15 @@ class CharacterizationSession:
         sl = slice(lo, hi)
         Bp = hi - lo
         self.encode(self.X[sl], self.tokens[sl], self.encoded[sl], self.cnt[sl], self.cnt_nm[sl], self.cnt_nm16[sl], ws)
-        self._match(lo, hi, ws)
+        side = None
+        if self.match_async and not init and not self.with_cm_path:
+            k = next(i for i, pr in enumerate(self.parts) if pr[0] == lo)
+            side = self.match_streams[k]
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._match(lo, hi, self.match_ws[k])
+        else:
+            self._match(lo, hi, ws)
         if init or self.with_cm_path:
             torch.index_select(self.cha_encoded, 0, self.match_idx[sl, 0], out=self.cm_cha[sl])
         if init:
@@ -196,6 +214,8 @@ class CharacterizationSession:
         self._decode(self.encoded[sl], self.prev_cha[sl], self.decoded[sl], self.Y[sl], ws)
         # the kernel reads the packed `side` rows in place (no slicing copies inside the captured frame)
         self.post.step_packed(self.Y[sl], self.side[sl], self.contacts[sl], lo=lo, init=init)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)       # join: match_idx / match_dist are frame outputs
         if self.with_cm_path:
             self._decode(self.encoded[sl], self.cm_cha[sl], self.decoded[sl], self.cm_Y[sl], ws)
             self.cm_post.step_packed(self.cm_Y[sl], self.side[sl], self.contacts[sl], lo=lo, init=init)
