@@ -125,14 +125,15 @@ def test_tf32_fp32_storage_matcher(shape):
     np.testing.assert_allclose(dist[:, 0], wd[:, 0], rtol=1e-9)
 
 
-def test_peer_exchange_two_logical_ranks_on_one_gpu():
+@pytest.mark.parametrize("nq,k", [(300, 3), (301, 3), (3, 1), (77, 1)])     # odd nq*k: slots stay 16 B aligned (round-1 advisor finding)
+def test_peer_exchange_two_logical_ranks_on_one_gpu(nq, k):
     """mocha_topk_exchange_merge (fused P2P store / signal / merge kernel of the DB-sharded matcher): two
     logical ranks on ONE GPU, their kernels on two streams so that both are resident and signal each other
     through their exchange buffers, three consecutive epochs; result = merge of the two shards' lists."""
     import ctypes as C
     from mocha_sigasia2023_b200 import _lib
     lib = _lib.load()
-    world, nq, k = 2, 300, 3
+    world = 2
     nbytes = lib.mocha_topk_exchange_bytes(world, nq, k)
     bufs, handles = [], []
     for r in range(world):
@@ -148,7 +149,8 @@ def test_peer_exchange_two_logical_ranks_on_one_gpu():
             i_np = rng.integers(0, 10_000, size=(world, nq, k)).astype(np.int64)
             i_np[1, ::7, -1] = -1                      # a shard with fewer than k rows for some queries
             d_np[1, ::7, -1] = np.inf
-            d = torch.from_numpy(d_np).cuda(); i = torch.from_numpy(i_np).cuda()
+            d = [torch.from_numpy(d_np[r].copy()).cuda() for r in range(world)]     # own allocations: 16 B aligned lists
+            i = [torch.from_numpy(i_np[r].copy()).cuda() for r in range(world)]
             outs = []
             torch.cuda.synchronize()
             for r in range(world):
