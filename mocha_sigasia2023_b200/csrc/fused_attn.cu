@@ -15,6 +15,8 @@
 // epilogue (two warps per TMEM lane quarter split the key columns / the head dimension and exchange row maxima and sums).
 #include "fused.cuh"
 
+#include <cstdlib>
+
 #include "gemm_tc.cuh"
 #include "tc_ptx.cuh"
 
@@ -25,7 +27,9 @@ using namespace tcx;
 namespace {
 
 constexpr int FA_THREADS = 320;
-enum { A_QKFULL = 0, A_QKEMPTY, A_VFULL, A_VEMPTY, A_SFULL, A_SEMPTY, A_PREADY, A_OFULL, A_OEMPTY, A_COUNT };
+// per-buffer barriers come in pairs ([0], [1]) for the two-group mode
+enum { A_QKFULL = 0, A_QKEMPTY, A_VFULL, A_VEMPTY, A_SFULL, A_SEMPTY = A_SFULL + 2, A_PREADY = A_SEMPTY + 2, A_OFULL = A_PREADY + 2,
+       A_OEMPTY = A_OFULL + 2, A_COUNT = A_OEMPTY + 2 };
 
 #ifdef MOCHA_TRACE
 // trace build: per-CTA clock64 time line (tools/attn_trace.py), 64 slots per CTA: 16 per unit for the first 4 units
@@ -44,6 +48,8 @@ struct AttnParams {
   int units;
   float scale_log2e;             // log2(e) / sqrt(dh)
   uint32_t off_k, off_v, off_p, off_bar, off_xch;   // shared-memory plan (Q at 0)
+  uint32_t p_bytes;              // one P buffer
+  int groups;                    // 2: the two warps of a TMEM lane quarter alternate units (double-buffered S / O / P)
 };
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t smem_addr, int c0, int c1, int c2) {
@@ -76,9 +82,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmO);
     mbar_init(&bar[A_QKFULL], 1); mbar_init(&bar[A_QKEMPTY], 1);
     mbar_init(&bar[A_VFULL], 1); mbar_init(&bar[A_VEMPTY], 1);
-    mbar_init(&bar[A_SFULL], 1); mbar_init(&bar[A_SEMPTY], 8);
-    mbar_init(&bar[A_PREADY], 8);
-    mbar_init(&bar[A_OFULL], 1); mbar_init(&bar[A_OEMPTY], 8);
+    const uint32_t narr = p.groups == 2 ? 4 : 8;      // epilogue warps per unit
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar[A_SFULL + i], 1); mbar_init(&bar[A_SEMPTY + i], narr);
+      mbar_init(&bar[A_PREADY + i], narr);
+      mbar_init(&bar[A_OFULL + i], 1); mbar_init(&bar[A_OEMPTY + i], narr);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -120,88 +129,107 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc(128, p.npad), idesc_o = make_idesc(128, p.dh, true);
-      const uint32_t accS = tmem, accO = tmem + 256u;
+      const int G = p.groups;
+      // TMEM plan: one group: S at [0, npad), O at [256, 256 + dh); two groups: S[b] at b*npad, O[b] at 2*npad + b*dh
+      auto acc_s = [&](int b) { return tmem + (uint32_t)(b * p.npad); };
+      auto acc_o = [&](int b) { return tmem + (G == 2 ? (uint32_t)(2 * p.npad + b * p.dh) : 256u); };
       auto issue_s = [&](uint32_t it) {
-        const uint32_t ph = it & 1;
-        mbar_wait(&bar[A_QKFULL], ph);
+        const int b = G == 2 ? (int)(it & 1) : 0;
+        const uint32_t ub = G == 2 ? it >> 1 : it;     // use count of buffer b
+        mbar_wait(&bar[A_QKFULL], it & 1);
         FA_TRACE(it, 2);   // MMA: Q / K landed
-        mbar_wait(&bar[A_SEMPTY], ph ^ 1);
+        mbar_wait(&bar[A_SEMPTY + b], (ub & 1) ^ 1);
         tc_fence_after();
         FA_TRACE(it, 3);   // MMA: score accumulator free, issuing S
         for (int kb = 0; kb < dkb; ++kb) {
           const uint64_t adesc = make_smem_desc(sbase + (uint32_t)kb * 16384u);
           const uint64_t bdesc = make_smem_desc(sbase + p.off_k + (uint32_t)kb * (uint32_t)p.npad * 128u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(accS, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) umma_bf16(acc_s(b), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s, (kb | k) != 0);
         }
         umma_commit(&bar[A_QKEMPTY]);
-        umma_commit(&bar[A_SFULL]);
+        umma_commit(&bar[A_SFULL + b]);
       };
       auto issue_o = [&](uint32_t it) {
-        const uint32_t ph = it & 1;
-        mbar_wait(&bar[A_PREADY], ph);
+        const int b = G == 2 ? (int)(it & 1) : 0;
+        const uint32_t ub = G == 2 ? it >> 1 : it;
+        mbar_wait(&bar[A_PREADY + b], ub & 1);
         FA_TRACE(it, 4);   // MMA: P ready
-        mbar_wait(&bar[A_VFULL], ph);
-        mbar_wait(&bar[A_OEMPTY], ph ^ 1);
+        mbar_wait(&bar[A_VFULL], it & 1);
+        mbar_wait(&bar[A_OEMPTY + b], (ub & 1) ^ 1);
         tc_fence_after();
         FA_TRACE(it, 5);   // MMA: V landed + output accumulator free, issuing P V
         for (int kb = 0; kb < nkb; ++kb) {
-          const uint64_t adesc = make_smem_desc(sbase + p.off_p + (uint32_t)kb * 16384u);
+          const uint64_t adesc = make_smem_desc(sbase + p.off_p + (uint32_t)b * p.p_bytes + (uint32_t)kb * 16384u);
           // MN-major V: one MMA consumes 16 key rows = 2 KB of every 64-column atom
           const uint64_t bdesc = make_smem_desc_mn(sbase + p.off_v + (uint32_t)(kb * dkb) * 8192u, 8192u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(accO, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(128 * k), idesc_o, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) umma_bf16(acc_o(b), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(128 * k), idesc_o, (kb | k) != 0);
         }
         umma_commit(&bar[A_VEMPTY]);
-        umma_commit(&bar[A_OFULL]);
+        umma_commit(&bar[A_OFULL + b]);
       };
       uint32_t n = 0;
       for (int u = blockIdx.x; u < p.units; u += gridDim.x) ++n;
-      // scores of unit u+1 are issued before the P V product of unit u
-      if (n > 0) issue_s(0);
+      // the score GEMMs run G units ahead of the P V products
+      for (uint32_t it = 0; it < (uint32_t)G && it < n; ++it) issue_s(it);
       for (uint32_t it = 0; it < n; ++it) {
-        if (it + 1 < n) issue_s(it + 1);
+        if (G == 1 && it + 1 < n) issue_s(it + 1);
         issue_o(it);
+        if (G == 2 && it + 2 < n) issue_s(it + 2);
       }
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
+    // One group: the two warps of a TMEM lane quarter split the key columns / the head dimension of EVERY unit and
+    // exchange row maxima and sums. Two groups (when 2 x (npad + dh) TMEM columns and two P buffers fit): warp `half`
+    // of each quarter owns whole rows of the units with (it & 1) == half, so one group's softmax runs while the other
+    // group waits for its P V product - the kernel is epilogue-bound, and this hides the waits.
     const int ew = warp - 2, q = warp & 3, half = ew >> 2;
+    const int G = p.groups;
     const int row_l = q * 32 + lane, sw7 = lane & 7;
     const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
-    const int scols = p.npad / 2;                               // score columns of this warp
-    const int sc0 = half * scols;
-    const bool o_active = p.dh >= 128 || half == 0;
-    const int ocols = p.dh >= 128 ? p.dh / 2 : p.dh;            // head-dimension columns of this warp
-    const int oc0 = p.dh >= 128 ? half * ocols : 0;
-    const uint32_t stage = sbase + p.off_p + (uint32_t)ew * 4096u;   // output staging inside the (then idle) P buffer
+    const int scols = G == 2 ? p.npad : p.npad / 2;             // score columns of this warp
+    const int sc0 = G == 2 ? 0 : half * scols;
+    const bool o_active = G == 2 || p.dh >= 128 || half == 0;
+    const int ocols = G == 2 ? p.dh : (p.dh >= 128 ? p.dh / 2 : p.dh);   // head-dimension columns of this warp
+    const int oc0 = G == 2 ? 0 : (p.dh >= 128 ? half * ocols : 0);
     uint32_t it = 0;
     for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++it) {
+      if (G == 2 && (int)(it & 1) != half) continue;
+      const int bsel = G == 2 ? half : 0;                        // S / O / P buffer of this unit
+      const uint32_t ub = G == 2 ? it >> 1 : it;
+      const uint32_t ph = ub & 1;
       const int qt = u % p.nqt, h = (u / p.nqt) % p.H, b = u / (p.nqt * p.H);
-      const uint32_t ph = it & 1;
+      const uint32_t t_s = taddr + (uint32_t)(bsel * p.npad);
+      const uint32_t t_o = taddr + (G == 2 ? (uint32_t)(2 * p.npad + bsel * p.dh) : 256u);
+      const uint32_t pbuf = sbase + p.off_p + (uint32_t)bsel * p.p_bytes;
+      // output staging inside this unit's (then idle) P buffer: one group: 4 KB per warp; two groups: 2 x 4 KB per warp
+      const uint32_t stage = pbuf + (G == 2 ? (uint32_t)q * 8192u : (uint32_t)ew * 4096u);
       // ---- softmax ----
-      mbar_wait(&bar[A_SFULL], ph);
+      mbar_wait(&bar[A_SFULL + bsel], ph);
       tc_fence_after();
       if (warp == 2 && lane == 0) FA_TRACE(it, 8);    // epilogue: scores ready
       float m = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < scols; c += 32) {
         uint32_t v[32];
-        tmem_ld32(taddr + (uint32_t)(sc0 + c), v);
+        tmem_ld32(t_s + (uint32_t)(sc0 + c), v);
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (sc0 + c + j < p.nkv) m = fmaxf(m, __uint_as_float(v[j]));
       }
-      {
+      if (G == 1) {
         xch[(half * 4 + q) * 32 + lane] = m;
         named_bar_sync(2 + q, 64);
         m = fmaxf(m, xch[((half ^ 1) * 4 + q) * 32 + lane]);
       }
-      // the previous unit's output stores read their staging boxes out of the P buffer: they must have left it, in every
-      // warp, before new probabilities are written
-      if (it > 0) {
+      // the previous output stores of this buffer read their staging boxes out of the P buffer: they must have left it,
+      // in every warp that shares it, before new probabilities are written
+      if (ub > 0) {
         if (lane == 0) bulk_wait_read0();
-        named_bar_sync(1, 256);
+        if (G == 2) named_bar_sync(6 + half, 128);
+        else named_bar_sync(1, 256);
       }
       if (warp == 2 && lane == 0) FA_TRACE(it, 9);    // epilogue: row max known, P buffer free
       const float ms = m * p.scale_log2e;
@@ -210,11 +238,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       for (int c = 0; c < scols; c += 32) {
         const int col = sc0 + c;
         uint32_t v[32];
-        tmem_ld32(taddr + (uint32_t)col, v);
+        tmem_ld32(t_s + (uint32_t)col, v);
         float e[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) e[j] = col + j < p.nkv ? ex2(fmaf(__uint_as_float(v[j]), p.scale_log2e, -ms)) : 0.f;
-        const uint32_t prow = sbase + p.off_p + (uint32_t)(col >> 6) * 16384u + (uint32_t)row_l * 128u;
+        const uint32_t prow = pbuf + (uint32_t)(col >> 6) * 16384u + (uint32_t)row_l * 128u;
         const int c16 = (col & 63) >> 3;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -231,31 +259,33 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&bar[A_SEMPTY]); mbar_arrive(&bar[A_PREADY]); }
+      if (lane == 0) { mbar_arrive(&bar[A_SEMPTY + bsel]); mbar_arrive(&bar[A_PREADY + bsel]); }
       if (warp == 2 && lane == 0) FA_TRACE(it, 10);   // epilogue: P written
-      {
+      if (G == 1) {
         xch[256 + (half * 4 + q) * 32 + lane] = sum;
         named_bar_sync(2 + q, 64);
         sum += xch[256 + ((half ^ 1) * 4 + q) * 32 + lane];
       }
       const float inv = 1.f / sum;
       // ---- output ----
-      mbar_wait(&bar[A_OFULL], ph);
+      mbar_wait(&bar[A_OFULL + bsel], ph);
       tc_fence_after();
       if (warp == 2 && lane == 0) FA_TRACE(it, 11);   // epilogue: output accumulator ready
       if (o_active) {
 #pragma unroll 1
         for (int c = 0; c < ocols; c += 32) {
           uint32_t v[32];
-          tmem_ld32(taddr + 256u + (uint32_t)(oc0 + c), v);
+          tmem_ld32(t_o + (uint32_t)(oc0 + c), v);
           const int hc = (c >> 5) & 1;                        // half of the 64-column staging box
-          if (hc == 0 && c > 0) {                             // second box of this unit: the first one's store must be done
+          const int box = G == 2 ? (c >> 6) & 1 : 0;          // two groups: two boxes per warp, alternating
+          if (hc == 0 && c > 0 && (G == 1 || c >= 128)) {     // reusing a box: its previous store must have read it
             if (lane == 0) bulk_wait_read0();
             __syncwarp();
           }
+          const uint32_t sbox = stage + (uint32_t)box * 4096u;
 #pragma unroll
           for (int t = 0; t < 4; ++t)
-            sts128(stage + (uint32_t)(lane * 128 + (((t + 4 * hc) ^ sw7) << 4)),
+            sts128(sbox + (uint32_t)(lane * 128 + (((t + 4 * hc) ^ sw7) << 4)),
                    pack_bf16(__uint_as_float(v[8 * t]) * inv, __uint_as_float(v[8 * t + 1]) * inv),
                    pack_bf16(__uint_as_float(v[8 * t + 2]) * inv, __uint_as_float(v[8 * t + 3]) * inv),
                    pack_bf16(__uint_as_float(v[8 * t + 4]) * inv, __uint_as_float(v[8 * t + 5]) * inv),
@@ -264,7 +294,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_3d(&tmO, stage, h * p.dh + oc0 + (c & ~63), qt * 128 + q * 32, b);
+              tma_store_3d(&tmO, sbox, h * p.dh + oc0 + (c & ~63), qt * 128 + q * 32, b);
               bulk_commit();
             }
           }
@@ -272,7 +302,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar[A_OEMPTY]);
+      if (lane == 0) mbar_arrive(&bar[A_OEMPTY + bsel]);
       if (warp == 2 && lane == 0) FA_TRACE(it, 12);   // epilogue: output handed to TMA
     }
     if (lane == 0) bulk_wait_read0();
@@ -313,7 +343,12 @@ int tc_attn_fused(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int l
   p.off_v = p.off_k + (uint32_t)dkb * (uint32_t)p.npad * 128u;
   p.off_v = (p.off_v + 1023u) & ~1023u;
   p.off_p = p.off_v + (uint32_t)nkb * (uint32_t)dkb * 8192u;
-  p.off_bar = p.off_p + (uint32_t)nkb * 16384u;
+  p.p_bytes = (uint32_t)nkb * 16384u;
+  // two-group mode: double-buffered scores / outputs in TMEM, two P buffers (each also hosts 4 warps x 2 staging boxes)
+  static const bool one_group = getenv("MOCHA_ATTN_ONE_GROUP") != nullptr;
+  p.groups = (!one_group && 2 * (p.npad + dh) <= 512 && p.p_bytes >= 32768u &&
+              (size_t)p.off_p + 2 * (size_t)p.p_bytes + 256 + 2048 <= 227 * 1024) ? 2 : 1;
+  p.off_bar = p.off_p + (uint32_t)p.groups * p.p_bytes;
   p.off_xch = p.off_bar + 256u;
   const size_t smem = (size_t)p.off_xch + 2048;
   MOCHA_CHECK_ARG(smem <= 227 * 1024, "tc_attn_fused: shared-memory plan of %zu B exceeds 227 KB", smem);
