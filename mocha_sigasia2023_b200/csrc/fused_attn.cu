@@ -28,7 +28,7 @@ namespace {
 
 constexpr int FA_THREADS = 320;
 // per-buffer barriers come in pairs ([0], [1]) for the two-group mode
-enum { A_QKFULL = 0, A_QKEMPTY, A_VFULL, A_VEMPTY, A_SFULL, A_SEMPTY = A_SFULL + 2, A_PREADY = A_SEMPTY + 2, A_OFULL = A_PREADY + 2,
+enum { A_QKFULL = 0, A_QKEMPTY = 2, A_VFULL = 4, A_VEMPTY, A_SFULL, A_SEMPTY = A_SFULL + 2, A_PREADY = A_SEMPTY + 2, A_OFULL = A_PREADY + 2,
        A_OEMPTY = A_OFULL + 2, A_COUNT = A_OEMPTY + 2 };
 
 #ifdef MOCHA_TRACE
@@ -49,6 +49,8 @@ struct AttnParams {
   float scale_log2e;             // log2(e) / sqrt(dh)
   uint32_t off_k, off_v, off_p, off_bar, off_xch;   // shared-memory plan (Q at 0)
   uint32_t p_bytes;              // one P buffer
+  int qk_stages;                 // 1 or 2 Q / K buffers (stride qk_stride bytes; K at off_k inside a stage)
+  uint32_t qk_stride;
   int groups;                    // 2: the two warps of a TMEM lane quarter alternate units (double-buffered S / O / P)
 };
 
@@ -80,7 +82,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmO);
-    mbar_init(&bar[A_QKFULL], 1); mbar_init(&bar[A_QKEMPTY], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar[A_QKFULL + i], 1); mbar_init(&bar[A_QKEMPTY + i], 1); }
     mbar_init(&bar[A_VFULL], 1); mbar_init(&bar[A_VEMPTY], 1);
     const uint32_t narr = p.groups == 2 ? 4 : 8;      // epilogue warps per unit
     for (int i = 0; i < 2; ++i) {
@@ -106,23 +108,38 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++it) {
+      uint32_t n = 0;
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x) ++n;
+      const uint32_t QS = (uint32_t)p.qk_stages;
+      auto load_qk = [&](uint32_t it) {
+        const int u = blockIdx.x + (int)it * gridDim.x;
         const int qt = u % p.nqt, h = (u / p.nqt) % p.H, b = u / (p.nqt * p.H);
-        const uint32_t ph = it & 1;
-        mbar_wait(&bar[A_QKEMPTY], ph ^ 1);
-        FA_TRACE(it, 0);   // producer: Q / K buffers free
-        mbar_expect_tx(&bar[A_QKFULL], q_bytes + k_bytes);
+        const uint32_t st = it % QS, ph = (it / QS) & 1;
+        mbar_wait(&bar[A_QKEMPTY + st], ph ^ 1);
+        FA_TRACE(it, 0);   // producer: Q / K buffer free
+        mbar_expect_tx(&bar[A_QKFULL + st], q_bytes + k_bytes);
+        const uint32_t base = sbase + st * p.qk_stride;
         for (int kb = 0; kb < dkb; ++kb) {
-          tma_load_2d(sbase + (uint32_t)kb * 16384u, &tmQ, &bar[A_QKFULL], h * p.dh + kb * 64, b * p.nq + qt * 128);
-          tma_load_2d(sbase + p.off_k + (uint32_t)kb * (uint32_t)p.npad * 128u, &tmK, &bar[A_QKFULL], h * p.dh + kb * 64, b * p.nkv);
+          tma_load_2d(base + (uint32_t)kb * 16384u, &tmQ, &bar[A_QKFULL + st], h * p.dh + kb * 64, b * p.nq + qt * 128);
+          tma_load_2d(base + p.off_k + (uint32_t)kb * (uint32_t)p.npad * 128u, &tmK, &bar[A_QKFULL + st], h * p.dh + kb * 64, b * p.nkv);
         }
-        mbar_wait(&bar[A_VEMPTY], ph ^ 1);
+      };
+      auto load_v = [&](uint32_t it) {
+        const int u = blockIdx.x + (int)it * gridDim.x;
+        const int h = (u / p.nqt) % p.H, b = u / (p.nqt * p.H);
+        mbar_wait(&bar[A_VEMPTY], (it & 1) ^ 1);
         FA_TRACE(it, 1);   // producer: V buffer free
         mbar_expect_tx(&bar[A_VFULL], v_bytes);
         for (int kb = 0; kb < nkb; ++kb)
           for (int a = 0; a < dkb; ++a)
             tma_load_2d(sbase + p.off_v + (uint32_t)(kb * dkb + a) * 8192u, &tmV, &bar[A_VFULL], h * p.dh + a * 64, b * p.nkv + kb * 64);
+      };
+      // Q / K run QS units ahead of V: the score GEMM of a later unit never waits behind the V refill, which has to wait
+      // for the previous unit's second GEMM
+      for (uint32_t it = 0; it < QS && it < n; ++it) load_qk(it);
+      for (uint32_t it = 0; it < n; ++it) {
+        load_v(it);
+        if (it + QS < n) load_qk(it + QS);
       }
     }
   } else if (warp == 1) {
@@ -136,18 +153,19 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       auto issue_s = [&](uint32_t it) {
         const int b = G == 2 ? (int)(it & 1) : 0;
         const uint32_t ub = G == 2 ? it >> 1 : it;     // use count of buffer b
-        mbar_wait(&bar[A_QKFULL], it & 1);
+        const uint32_t QS = (uint32_t)p.qk_stages, st = it % QS;
+        mbar_wait(&bar[A_QKFULL + st], (it / QS) & 1);
         FA_TRACE(it, 2);   // MMA: Q / K landed
         mbar_wait(&bar[A_SEMPTY + b], (ub & 1) ^ 1);
         tc_fence_after();
         FA_TRACE(it, 3);   // MMA: score accumulator free, issuing S
         for (int kb = 0; kb < dkb; ++kb) {
-          const uint64_t adesc = make_smem_desc(sbase + (uint32_t)kb * 16384u);
-          const uint64_t bdesc = make_smem_desc(sbase + p.off_k + (uint32_t)kb * (uint32_t)p.npad * 128u);
+          const uint64_t adesc = make_smem_desc(sbase + st * p.qk_stride + (uint32_t)kb * 16384u);
+          const uint64_t bdesc = make_smem_desc(sbase + st * p.qk_stride + p.off_k + (uint32_t)kb * (uint32_t)p.npad * 128u);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(acc_s(b), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s, (kb | k) != 0);
         }
-        umma_commit(&bar[A_QKEMPTY]);
+        umma_commit(&bar[A_QKEMPTY + st]);
         umma_commit(&bar[A_SFULL + b]);
       };
       auto issue_o = [&](uint32_t it) {
@@ -339,15 +357,19 @@ int tc_attn_fused(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int l
   p.units = B * H * p.nqt;
   p.scale_log2e = 1.4426950408889634f / sqrtf((float)dh);
   const int dkb = dh / 64, nkb = p.npad / 64;
-  p.off_k = (uint32_t)dkb * 16384u;
-  p.off_v = p.off_k + (uint32_t)dkb * (uint32_t)p.npad * 128u;
-  p.off_v = (p.off_v + 1023u) & ~1023u;
-  p.off_p = p.off_v + (uint32_t)nkb * (uint32_t)dkb * 8192u;
+  p.off_k = (uint32_t)dkb * 16384u;                                 // K inside a Q / K stage
+  p.qk_stride = (p.off_k + (uint32_t)dkb * (uint32_t)p.npad * 128u + 1023u) & ~1023u;
   p.p_bytes = (uint32_t)nkb * 16384u;
-  // two-group mode: double-buffered scores / outputs in TMEM, two P buffers (each also hosts 4 warps x 2 staging boxes)
+  const uint32_t v_bytes = (uint32_t)nkb * (uint32_t)dkb * 8192u;
+  // two-group mode: double-buffered scores / outputs in TMEM, two P buffers (each also hosts 4 warps x 2 staging boxes);
+  // a second Q / K stage when it still fits
   static const bool one_group = getenv("MOCHA_ATTN_ONE_GROUP") != nullptr;
+  const size_t fixed = 256 + 2048;
   p.groups = (!one_group && 2 * (p.npad + dh) <= 512 && p.p_bytes >= 32768u &&
-              (size_t)p.off_p + 2 * (size_t)p.p_bytes + 256 + 2048 <= 227 * 1024) ? 2 : 1;
+              (size_t)p.qk_stride + v_bytes + 2 * (size_t)p.p_bytes + fixed <= 227 * 1024) ? 2 : 1;
+  p.qk_stages = (p.groups == 2 && 2 * (size_t)p.qk_stride + v_bytes + 2 * (size_t)p.p_bytes + fixed <= 227 * 1024) ? 2 : 1;
+  p.off_v = (uint32_t)p.qk_stages * p.qk_stride;
+  p.off_p = p.off_v + v_bytes;
   p.off_bar = p.off_p + (uint32_t)p.groups * p.p_bytes;
   p.off_xch = p.off_bar + 256u;
   const size_t smem = (size_t)p.off_xch + 2048;
