@@ -156,6 +156,10 @@ typedef struct {
    * the constant positional table (model_CVAE.py:161-162), so this block is input-independent; fill it
    * once with mocha_cvae_precompute_dec0(). NULL = recompute it on every call. */
   const float* dec0_sa;
+  /* Optional bf16 [out_seq, D] table = the layer-0 cross-attention QUERY projection of dec0_sa (rows of
+   * ca_in_w[0:D], ca_in_b[0:D]): with it the tensor-core path neither materialises the broadcast query tensor nor
+   * projects it per clip (every clip shares the table). Requires dec0_sa. NULL = project per call. */
+  const void* dec0_q16;
 } mocha_cvae_weights;
 
 /* ---- (a1) Generator.mot_embedding  model.py:42-50, call site test_fullframework.py:190 ------ */

@@ -70,6 +70,7 @@ class CvaeWeights(C.Structure):
         ("mu_token", C.c_void_p), ("logvar_token", C.c_void_p), ("pe", C.c_void_p),
         ("prior", CvaeEncLayer * MAX_DEPTH), ("dec", CvaeDecLayer * MAX_DEPTH),
         ("dec0_sa", C.c_void_p),
+        ("dec0_q16", C.c_void_p),
     ]
 
 

@@ -44,6 +44,7 @@ __device__ unsigned long long* g_fa_trace = nullptr;
 
 struct AttnParams {
   int B, H, nq, nkv, dh, npad;   // npad = nkv rounded up to a multiple of 64 (<= 256)
+  int q_rows_b;                  // Q rows per clip: nq, or 0 when every clip shares one [nq, H*dh] query table
   int nqt;                       // query tiles per (clip, head)
   int units;
   float scale_log2e;             // log2(e) / sqrt(dh)
@@ -120,7 +121,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         mbar_expect_tx(&bar[A_QKFULL + st], q_bytes + k_bytes);
         const uint32_t base = sbase + st * p.qk_stride;
         for (int kb = 0; kb < dkb; ++kb) {
-          tma_load_2d(base + (uint32_t)kb * 16384u, &tmQ, &bar[A_QKFULL + st], h * p.dh + kb * 64, b * p.nq + qt * 128);
+          tma_load_2d(base + (uint32_t)kb * 16384u, &tmQ, &bar[A_QKFULL + st], h * p.dh + kb * 64, b * p.q_rows_b + qt * 128);
           tma_load_2d(base + p.off_k + (uint32_t)kb * (uint32_t)p.npad * 128u, &tmK, &bar[A_QKFULL + st], h * p.dh + kb * 64, b * p.nkv);
         }
       };
@@ -346,12 +347,13 @@ bool tc_attn_fused_supported(int nq, int nkv, int dh) {
 
 // q/k/v: bf16 views [B*nq | B*nkv, ld*] with head h at columns h*dh; out bf16 [B, nq, H*dh]
 int tc_attn_fused(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v, int ldv, int B, int H,
-                  int nq, int nkv, int dh, __nv_bfloat16* out, int ldo, cudaStream_t s) {
+                  int nq, int nkv, int dh, __nv_bfloat16* out, int ldo, cudaStream_t s, bool q_shared) {
   MOCHA_CHECK_ARG(tc_attn_fused_supported(nq, nkv, dh), "tc_attn_fused: unsupported geometry nq=%d nkv=%d dh=%d", nq, nkv, dh);
   MOCHA_CHECK_ARG(q && k && v && out && B > 0 && H > 0, "tc_attn_fused: null operand");
   MOCHA_CHECK_ARG(ldo == H * dh && (ldq % 8) == 0 && (ldk % 8) == 0 && (ldv % 8) == 0, "tc_attn_fused: bad leading dimensions");
   AttnParams p{};
   p.B = B; p.H = H; p.nq = nq; p.nkv = nkv; p.dh = dh;
+  p.q_rows_b = q_shared ? 0 : nq;
   p.npad = (nkv + 63) / 64 * 64;
   p.nqt = ceil_div(nq, 128);
   p.units = B * H * p.nqt;
@@ -376,7 +378,7 @@ int tc_attn_fused(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int l
   MOCHA_CHECK_ARG(smem <= 227 * 1024, "tc_attn_fused: shared-memory plan of %zu B exceeds 227 KB", smem);
   const int inner = H * dh;
   CUtensorMap tmQ, tmK, tmV, tmO;
-  MOCHA_TRY(tc_make_tmap(&tmQ, q, (unsigned long long)B * nq, (unsigned long long)inner, 128, (unsigned long long)ldq));
+  MOCHA_TRY(tc_make_tmap(&tmQ, q, (unsigned long long)(q_shared ? 1 : B) * nq, (unsigned long long)inner, 128, (unsigned long long)ldq));
   MOCHA_TRY(tc_make_tmap(&tmK, k, (unsigned long long)B * nkv, (unsigned long long)inner, p.npad, (unsigned long long)ldk));
   MOCHA_TRY(tc_make_tmap(&tmV, v, (unsigned long long)B * nkv, (unsigned long long)inner, 64, (unsigned long long)ldv));
   MOCHA_TRY(tc_make_out_tmap(&tmO, out, (unsigned long long)ldo, (unsigned long long)nq, (unsigned long long)B,

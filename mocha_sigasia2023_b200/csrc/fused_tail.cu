@@ -72,6 +72,7 @@ struct TailParams {
   const float* be2;
   float eps;
   int out32, out16;
+  int r0_period;     // > 0: the residual is a [period, 256] table shared by every group of `period` rows
 };
 
 __device__ __forceinline__ float gelu_fast_f(float x) {
@@ -201,12 +202,13 @@ __device__ __forceinline__ void emit_chunk(const float (&f)[32], int col, int c,
 // made every LDG.128 touch 32 different lines - 256 line requests per warp and chunk, ~1900 cycles per chunk on the
 // L1 tag stage, the longest stall of this stage.
 struct Res32 { float4 r[8]; };
-__device__ __forceinline__ void load_res(Res32& x, const float* R0, long long slab_row0, int M, int col, int lane) {
+__device__ __forceinline__ void load_res(Res32& x, const float* R0, long long slab_row0, int M, int col, int lane, int period) {
   const int rr = lane >> 3, c4 = (lane & 7) * 4;
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const long long row = slab_row0 + rr + 4 * it;
-    x.r[it] = (R0 && row < M) ? __ldg(reinterpret_cast<const float4*>(R0 + row * FT_D + col + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const long long src = period > 0 ? row % period : row;
+    x.r[it] = (R0 && row < M) ? __ldg(reinterpret_cast<const float4*>(R0 + src * FT_D + col + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 // coalesced registers -> lane = row registers (warp-collective)
@@ -440,7 +442,7 @@ tail_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     const long long slab_row0 = (long long)m0 + e.q * 32;
     // transposition tile: the A stages are free once the out-projection has completed; without an FFN the ring is
     const uint32_t tb = sbase + (nch > 0 ? FT_OFF_HB : FT_OFF_RING + FT_SLOT) + (uint32_t)e.ew * 4096u;
-    load_res(res, p.R0, slab_row0, p.M, colbase, lane);
+    load_res(res, p.R0, slab_row0, p.M, colbase, lane, p.r0_period);
     mbar_wait(&bar[B_ACCP], 0);
     tc_fence_after();
     if (warp == 2 && lane == 0) FT_TRACE(24);   // epilogue: out-projection accumulator ready
@@ -457,7 +459,7 @@ tail_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
         if (p.R0) { transpose_res(res, tb, lane); add_res(f, res); }
-        if (c < 3) load_res(res, p.R0, slab_row0, p.M, col + 32, lane);
+        if (c < 3) load_res(res, p.R0, slab_row0, p.M, col + 32, lane, p.r0_period);
         if (p.b0) add_bias32(f, par + PV_B0 * 4u, col);
         if (c == 0) k = f[0];
 #pragma unroll
@@ -479,7 +481,7 @@ tail_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
         ln_apply(f, par + PV_G1 * 4u, par + PV_BE1 * 4u, col, mean, rstd);
       } else {
         if (p.R0) { transpose_res(res, tb, lane); add_res(f, res); }
-        if (c < 3) load_res(res, p.R0, slab_row0, p.M, col + 32, lane);
+        if (c < 3) load_res(res, p.R0, slab_row0, p.M, col + 32, lane, p.r0_period);
         if (p.b0) add_bias32(f, par + PV_B0 * 4u, col);
       }
       if (nch > 0) {
@@ -618,7 +620,7 @@ bool tc_tail_supported(int M, int K0, int Hd) {
 int tc_tail(const __nv_bfloat16* A0, int lda, int K0, const __nv_bfloat16* W0, const float* b0, const float* R0,
             const float* g1, const float* be1, int Hd, int act, const __nv_bfloat16* W1, const float* b1,
             const __nv_bfloat16* W2, const float* b2, const float* g2, const float* be2, float eps, float* O32,
-            __nv_bfloat16* O16, int M, cudaStream_t s) {
+            __nv_bfloat16* O16, int M, cudaStream_t s, int r0_period) {
   MOCHA_CHECK_ARG(tc_tail_supported(M, K0, Hd), "tc_tail: unsupported shape M=%d K0=%d hidden=%d", M, K0, Hd);
   MOCHA_CHECK_ARG(A0 && W0 && (O32 || O16), "tc_tail: null operand");
   MOCHA_CHECK_ARG(Hd == 0 || (W1 && W2), "tc_tail: FFN weights missing");
@@ -645,6 +647,7 @@ int tc_tail(const __nv_bfloat16* A0, int lda, int K0, const __nv_bfloat16* W0, c
   p.M = M; p.K0 = K0; p.Hd = Hd; p.act = act;
   p.b0 = b0; p.R0 = R0; p.g1 = g1; p.be1 = be1; p.b1 = b1; p.b2 = b2; p.g2 = g2; p.be2 = be2;
   p.eps = eps; p.out32 = O32 != nullptr; p.out16 = O16 != nullptr;
+  p.r0_period = r0_period;
   static bool configured = false;
   if (!configured) {
     MOCHA_CUDA(cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));

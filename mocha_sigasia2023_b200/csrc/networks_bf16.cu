@@ -51,9 +51,13 @@ inline bool use_fused_tail(int D) {
 
 // Attention of the bf16 path: one fused launch (fused_attn.cu) when the geometry fits, else the two-launch sequence
 // (scores + softmax epilogue, P V) of gemm_tc.cu. MOCHA_NO_FUSED_ATTN=1 forces the latter (A/B runs).
+inline bool fused_attn_on() {
+  static const bool off = getenv("MOCHA_NO_FUSED_ATTN") != nullptr;
+  return !off;
+}
 int attn(cudaStream_t s, Workspace& ws, const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv, int B, int H, int nq,
          int nkv, int dh, bf16* out, int ldo) {
-  static const bool off = getenv("MOCHA_NO_FUSED_ATTN") != nullptr;
+  const bool off = !fused_attn_on();
   if (!off && tc_attn_fused_supported(nq, nkv, dh) && ldo == H * dh)
     return tc_attn_fused(q, ldq, k, ldk, v, ldv, B, H, nq, nkv, dh, out, ldo, s);
   return tc_attention_ex(nullptr, q, ldq, nullptr, k, ldk, nullptr, v, ldv, B, H, nq, nkv, dh, nullptr, h16(out), ldo, ws, s);
@@ -62,13 +66,13 @@ int attn(cudaStream_t s, Workspace& ws, const bf16* q, int ldq, const bf16* k, i
 // fused block tail (fused_tail.cu) on fp32 weight pointers: looks up the registered bf16 mirrors
 int tail(cudaStream_t s, const bf16* A0, int K0, const float* W0, const float* b0, const float* R0, const float* g1,
          const float* be1, int Hd, int act, const float* W1, const float* b1, const float* W2, const float* b2,
-         const float* g2, const float* be2, float eps, float* O32, bf16* O16, int M) {
+         const float* g2, const float* be2, float eps, float* O32, bf16* O16, int M, int r0_period = 0) {
   const bf16* W016 = tc_lookup_bf16(W0);
   const bf16* W116 = Hd > 0 ? tc_lookup_bf16(W1) : nullptr;
   const bf16* W216 = Hd > 0 ? tc_lookup_bf16(W2) : nullptr;
   if (!W016 || (Hd > 0 && (!W116 || !W216)))
     return set_error(MOCHA_ERR_ARG, "bf16 path: a block-tail weight has no registered bf16 mirror");
-  return tc_tail(A0, K0, K0, W016, b0, R0, g1, be1, Hd, act, W116, b1, W216, b2, g2, be2, eps, O32, O16, M, s);
+  return tc_tail(A0, K0, K0, W016, b0, R0, g1, be1, Hd, act, W116, b1, W216, b2, g2, be2, eps, O32, O16, M, s, r0_period);
 }
 
 }  // namespace
@@ -346,6 +350,22 @@ int cvae_bf16(const mocha_cvae_weights* w, const float* cond, int B, int ncond, 
     const mocha_cvae_dec_layer& L = w->dec[l];
     MOCHA_CHECK_ARG(L.sa_in_w && L.sa_out_w && L.ca_in_w && L.ca_out_w && L.l1_w && L.l2_w && L.n1_g && L.n2_g && L.n3_g,
                     "mocha_cvae_sample: decoder layer %d weights missing", l);
+    const bool fused = use_fused_tail(D) && tc_tail_supported(Rq, D, w->dff);
+    const bool last = l == w->depth - 1;
+    // Layer 0 with both cached tables: the query rows are the same for every clip, so neither the broadcast [B, nq, D]
+    // tensor nor its per-clip projection is materialised - the attention kernel reads the shared bf16 query table and the
+    // block tail reads the fp32 table as a periodic residual.
+    static const bool no_shared_q = getenv("MOCHA_NO_SHARED_Q") != nullptr;
+    const bool shared_q = !no_shared_q && l == 0 && w->dec0_sa && w->dec0_q16 && fused && fused_attn_on() &&
+                          tc_attn_fused_supported(nq, nm, dh);
+    const float* res_cross = dy;
+    int res_period = 0;
+    if (shared_q) {
+      MOCHA_TRY(tc.lin(mem, D, L.ca_in_w + (size_t)D * D, L.ca_in_b + D, 0, nullptr, h16(memkv), Rm, 2 * D, D, ACT_NONE));
+      MOCHA_TRY(tc_attn_fused((const bf16*)w->dec0_q16, D, memkv, 2 * D, memkv + D, 2 * D, B, H, nq, nm, dh, att, D, s, true));
+      res_cross = w->dec0_sa;
+      res_period = nq;
+    } else {
     if (l == 0 && w->dec0_sa) {
       // layer 0's self-attention block acts on the constant query: cached table (mocha_cvae_precompute_dec0)
       MOCHA_TRY(broadcast_rows(w->dec0_sa, dy, B, (long long)nq * D, s, dy16));
@@ -363,12 +383,12 @@ int cvae_bf16(const mocha_cvae_weights* w, const float* cond, int B, int ncond, 
     MOCHA_TRY(tc.lin(dy16, D, L.ca_in_w, L.ca_in_b, 0, nullptr, h16(dq), Rq, D, D, ACT_NONE));
     MOCHA_TRY(tc.lin(mem, D, L.ca_in_w + (size_t)D * D, L.ca_in_b + D, 0, nullptr, h16(memkv), Rm, 2 * D, D, ACT_NONE));
     MOCHA_TRY(attn(s, ws, dq, D, memkv, 2 * D, memkv + D, 2 * D, B, H, nq, nm, dh, att, D));
-    const bool fused = use_fused_tail(D) && tc_tail_supported(Rq, D, w->dff);
-    const bool last = l == w->depth - 1;
+    }
     if (fused) {
       // cross-attention out-projection + LN2 + ReLU FFN (+ LN3 unless the de-normalising last LayerNorm follows)
-      MOCHA_TRY(tail(s, att, D, L.ca_out_w, L.ca_out_b, dy, L.n2_g, L.n2_b, w->dff, ACT_RELU, L.l1_w, L.l1_b, L.l2_w, L.l2_b,
-                     last ? nullptr : L.n3_g, last ? nullptr : L.n3_b, w->ln_eps, last ? proj : dy, last ? nullptr : dy16, Rq));
+      MOCHA_TRY(tail(s, att, D, L.ca_out_w, L.ca_out_b, res_cross, L.n2_g, L.n2_b, w->dff, ACT_RELU, L.l1_w, L.l1_b, L.l2_w, L.l2_b,
+                     last ? nullptr : L.n3_g, last ? nullptr : L.n3_b, w->ln_eps, last ? proj : dy, last ? nullptr : dy16, Rq,
+                     res_period));
       if (!last) {
         float* t = dx; dx = dy; dy = t;
         bf16* t16 = dx16; dx16 = dy16; dy16 = t16;

@@ -68,6 +68,7 @@ embed_graph_agg_kernel(const float* __restrict__ X, const float* __restrict__ We
                        const float* __restrict__ A, __nv_bfloat16* __restrict__ out16, int BT, int V, int Cin, int C,
                        int Kk, int ldo) {
   pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   float* xs = sm;                                     // [G*V][C]   activated h0
   float* xin = xs + G * V * C;                        // [G*V][16]  raw inputs, rows padded to 16 floats
@@ -75,9 +76,26 @@ embed_graph_agg_kernel(const float* __restrict__ X, const float* __restrict__ We
   int* src = reinterpret_cast<int*>(val + Kk * V * V);  // [Kk*V][V] source nodes of the non-zeros
   int* cnt = src + Kk * V * V;                        // [Kk*V]
   __nv_bfloat16* tails = reinterpret_cast<__nv_bfloat16*>(cnt + Kk * V);  // [V][ldo - Kk*C] row tails
+  const int bt0 = blockIdx.x * G;
+  const int rows = min(G, BT - bt0) * V;
   const int KC = Kk * C, tail = ldo - KC;
-  // Persistent blocks: the adjacency lists, the row tails and the 1x1 weights (registers) are set up ONCE per block and
-  // reused for every group of G frames the block walks (they used to be rebuilt per 4 frames: ~1/3 of the instructions)
+  {
+    // all of this thread's input elements are requested before the first one is stored (the loop form paid one global
+    // round trip per iteration: 19 % of the kernel's stall samples sat on its STS)
+    constexpr int NIT = (G * 32 * EMB_MAXCIN + 255) / 256;   // V <= 32
+    float vals[NIT];
+#pragma unroll
+    for (int j = 0; j < NIT; ++j) {
+      const int i = threadIdx.x + 256 * j;
+      const int r = i / EMB_MAXCIN, k = i - r * EMB_MAXCIN;
+      vals[j] = (i < rows * EMB_MAXCIN && k < Cin) ? __ldg(X + ((long long)bt0 * V + r) * Cin + k) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < NIT; ++j) {
+      const int i = threadIdx.x + 256 * j;
+      if (i < rows * EMB_MAXCIN) xin[i] = vals[j];
+    }
+  }
   for (int i = threadIdx.x; i < Kk * V * V; i += blockDim.x) {   // coalesced read, transposed to [k][w][u]
     const int k = i / (V * V), rem = i - k * V * V, u = rem / V, w = rem - u * V;
     val[(k * V + w) * V + u] = A[i];
@@ -98,30 +116,17 @@ embed_graph_agg_kernel(const float* __restrict__ X, const float* __restrict__ We
   }
   for (int i = threadIdx.x; i < V * tail; i += blockDim.x)
     if (i % tail >= Kk) tails[i] = __float2bfloat16_rn(0.f);
-  const int C2 = C / 2;
-  const int cp = threadIdx.x % C2, stripe = threadIdx.x / C2, nstripes = blockDim.x / C2;
-  float w0[EMB_MAXCIN], w1[EMB_MAXCIN];
-#pragma unroll
-  for (int k = 0; k < EMB_MAXCIN; ++k) {
-    w0[k] = k < Cin ? Wemb[(2 * cp) * Cin + k] : 0.f;
-    w1[k] = k < Cin ? Wemb[(2 * cp + 1) * Cin + k] : 0.f;
-  }
-  const float b0 = bemb ? bemb[2 * cp] : 0.f, b1 = bemb ? bemb[2 * cp + 1] : 0.f;
-  const int C4 = C / 4, gpw = 32 / C4;                 // lanes per row, rows per warp pass
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int grp = lane / C4, l4 = (lane - grp * C4) * 4;
-  const int ngroups = (blockDim.x >> 5) * gpw;
-  pdl_wait();   // everything above reads constants only (adjacency, 1x1 weights): it ran under the previous kernel's tail
-  for (int bt0 = blockIdx.x * G; bt0 < BT; bt0 += gridDim.x * G) {
-  const int rows = min(G, BT - bt0) * V;
-  __syncthreads();   // the previous group's aggregation has read xs / xin (and, first time, the lists are complete)
-  for (int i = threadIdx.x; i < rows * EMB_MAXCIN; i += blockDim.x) {
-    const int r = i / EMB_MAXCIN, k = i - r * EMB_MAXCIN;
-    xin[i] = k < Cin ? X[((long long)bt0 * V + r) * Cin + k] : 0.f;
-  }
-  __syncthreads();
   // h0 = lrelu(x W^T + b): thread = channel pair (weights in registers), rows striped over the block
   {
+    const int C2 = C / 2;
+    const int cp = threadIdx.x % C2, stripe = threadIdx.x / C2, nstripes = blockDim.x / C2;
+    float w0[EMB_MAXCIN], w1[EMB_MAXCIN];
+#pragma unroll
+    for (int k = 0; k < EMB_MAXCIN; ++k) {
+      w0[k] = k < Cin ? Wemb[(2 * cp) * Cin + k] : 0.f;
+      w1[k] = k < Cin ? Wemb[(2 * cp + 1) * Cin + k] : 0.f;
+    }
+    const float b0 = bemb ? bemb[2 * cp] : 0.f, b1 = bemb ? bemb[2 * cp + 1] : 0.f;
     if (stripe < nstripes)
       for (int r = stripe; r < rows; r += nstripes) {
         const float4* xr = reinterpret_cast<const float4*>(xin + r * EMB_MAXCIN);
@@ -139,6 +144,10 @@ embed_graph_agg_kernel(const float* __restrict__ X, const float* __restrict__ We
   }
   __syncthreads();
   // aggregation: a group of C/4 lanes owns one output row, 4 channels per lane
+  const int C4 = C / 4, gpw = 32 / C4;                 // lanes per row, rows per warp pass
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane / C4, l4 = (lane - grp * C4) * 4;
+  const int ngroups = (blockDim.x >> 5) * gpw;
   for (int r = warp * gpw + grp; r < rows; r += ngroups) {
     const int g = r / V, w = r - g * V;
     const float* xg = xs + g * V * C + l4;
@@ -161,7 +170,6 @@ embed_graph_agg_kernel(const float* __restrict__ X, const float* __restrict__ We
     for (int t = l4; t < tail; t += C)   // tail <= C in practice: one 8 B copy per lane
       *reinterpret_cast<uint2*>(dst + KC - l4 + t) = *reinterpret_cast<const uint2*>(tails + w * tail + t);
   }
-  }   // frame groups
 }
 
 __global__ void graph_agg_kv_kernel(const float* __restrict__ in, const float* __restrict__ A2,
@@ -442,7 +450,10 @@ instance_norm_tokens_reg_kernel(const float* __restrict__ x, int n, int C, float
 // 1.4 TB/s); same two-pass statistics.
 __global__ void __launch_bounds__(256)
 instance_norm_tokens_v4_kernel(const float* __restrict__ x, int n, int C, float eps, const float* __restrict__ gb,
-                               float* __restrict__ y, __nv_bfloat16* __restrict__ y16, __nv_bfloat16* __restrict__ q16) {
+                               float* __restrict__ y, __nv_bfloat16* __restrict__ y16, __nv_bfloat16* __restrict__ q16,
+                               const float* __restrict__ tab_mean = nullptr, const float* __restrict__ tab_std = nullptr,
+                               float* __restrict__ y2 = nullptr, __nv_bfloat16* __restrict__ y2h = nullptr,
+                               const float* __restrict__ y2h_center = nullptr) {
   pdl_trigger();
   pdl_wait();
   __shared__ float4 part[16][16];
@@ -523,6 +534,25 @@ instance_norm_tokens_v4_kernel(const float* __restrict__ x, int n, int C, float 
         pk.x = *reinterpret_cast<uint32_t*>(&lo);
         pk.y = *reinterpret_cast<uint32_t*>(&hi);
         *reinterpret_cast<uint2*>(y16 + o) = pk;
+      }
+      if (y2 || y2h) {
+        // matcher query (test_fullframework.py:442): (cnt - cnt_mean) / cnt_std with [n, C] tables; the bf16 copy is taken
+        // relative to the origin the bf16 DB rows were packed around
+        const long long ot = (long long)i * C + c;
+        const float4 tm = *reinterpret_cast<const float4*>(tab_mean + ot), ts = *reinterpret_cast<const float4*>(tab_std + ot);
+        float4 w = make_float4((u.x - tm.x) / ts.x, (u.y - tm.y) / ts.y, (u.z - tm.z) / ts.z, (u.w - tm.w) / ts.w);
+        if (y2) *reinterpret_cast<float4*>(y2 + o) = w;
+        if (y2h) {
+          if (y2h_center) {
+            const float4 cc = *reinterpret_cast<const float4*>(y2h_center + ot);
+            w = make_float4(w.x - cc.x, w.y - cc.y, w.z - cc.z, w.w - cc.w);
+          }
+          __nv_bfloat162 lo = __floats2bfloat162_rn(w.x, w.y), hi = __floats2bfloat162_rn(w.z, w.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(y2h + o) = pk;
+        }
       }
     }
   }
@@ -885,7 +915,7 @@ int embed_graph_agg(const float* X, const float* Wemb, const float* bemb, const 
   MOCHA_CHECK_ARG(X && Wemb && A && out16 && BT > 0 && V > 0 && Cin > 0 && Kk > 0, "embed_graph_agg: bad args");
   MOCHA_CHECK_ARG(C >= 8 && C <= 128 && (C & 3) == 0 && 128 % C == 0, "embed_graph_agg: C=%d unsupported", C);
   MOCHA_CHECK_ARG(Cin <= EMB_MAXCIN, "embed_graph_agg: Cin=%d > %d unsupported", Cin, EMB_MAXCIN);
-  MOCHA_CHECK_ARG(V % 4 == 0, "embed_graph_agg: V=%d must be a multiple of 4", V);
+  MOCHA_CHECK_ARG(V % 4 == 0 && V <= 32, "embed_graph_agg: V=%d must be a multiple of 4, at most 32", V);
   constexpr int G = 4;
   const size_t smem = (size_t)(G * V * C + G * V * EMB_MAXCIN + 2 * Kk * V * V + Kk * V) * sizeof(float) +
                       (size_t)V * (ldo - Kk * C) * 2 + 16;
@@ -896,12 +926,7 @@ int embed_graph_agg(const float* X, const float* Wemb, const float* bemb, const 
       MOCHA_CUDA(cudaFuncSetAttribute(embed_graph_agg_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  // persistent: as many blocks as fit on the chip at once (shared memory bound), each walking frame groups
-  const int groups = (BT + G - 1) / G;
-  int per_sm = (int)((220 * 1024) / (smem + 1024));
-  per_sm = per_sm < 1 ? 1 : per_sm > 6 ? 6 : per_sm;
-  const int grid = groups < 148 * per_sm ? groups : 148 * per_sm;
-  launch_k(embed_graph_agg_kernel<G>, grid, 256, smem, s, X, Wemb, bemb, A, out16, BT, V, Cin, C, Kk, ldo);
+  launch_k(embed_graph_agg_kernel<G>, (BT + G - 1) / G, 256, smem, s, X, Wemb, bemb, A, out16, BT, V, Cin, C, Kk, ldo);
   count_launch();
   MOCHA_LAUNCH_CHECK("embed_graph_agg");
   return MOCHA_OK;
@@ -1054,8 +1079,11 @@ int instance_norm_tokens(const float* x, int B, int n, int C, float eps, const f
   MOCHA_CHECK_ARG(!(y2 || y2h) || (tab_mean && tab_std), "instance_norm_tokens: y2 needs its table");
   const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gb)) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(y16) & 7) == 0;
-  if (n <= 128 && y16 && !y2 && !y2h && (C % 64) == 0 && al)   // tensor-core path (bf16 twin requested): float4 kernel
-    launch_k(instance_norm_tokens_v4_kernel, dim3(B, C / 64), 256, 0, s, x, n, C, eps, gb, y, y16, nullptr);
+  const bool al2 = ((reinterpret_cast<uintptr_t>(tab_mean) | reinterpret_cast<uintptr_t>(tab_std) | reinterpret_cast<uintptr_t>(y2) |
+                     reinterpret_cast<uintptr_t>(y2h_center)) & 15) == 0 && (reinterpret_cast<uintptr_t>(y2h) & 7) == 0;
+  if (n <= 128 && (y16 || y2 || y2h) && (C % 64) == 0 && al && al2)   // float4 kernel (bf16 twin and / or matcher query)
+    launch_k(instance_norm_tokens_v4_kernel, dim3(B, C / 64), 256, 0, s, x, n, C, eps, gb, y, y16, (__nv_bfloat16*)nullptr, tab_mean,
+             tab_std, y2, y2h, y2h_center);
   else if (n <= 128)
     launch_k(instance_norm_tokens_reg_kernel, dim3(B, (C + 31) / 32), 256, 0, s, x, n, C, eps, gb, y, tab_mean, tab_std, y2, y16, y2h, y2h_center);
   else
@@ -1070,7 +1098,8 @@ int adain_norm_tokens(const float* x, int B, int n, int C, float eps, const floa
   MOCHA_CHECK_ARG(x && gb && y && q16 && B > 0 && n > 1 && n <= 128 && (C % 64) == 0, "adain_norm_tokens: bad args");
   MOCHA_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gb)) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(q16) & 7) == 0, "adain_norm_tokens: operands must be 16 B aligned");
-  launch_k(instance_norm_tokens_v4_kernel, dim3(B, C / 64), 256, 0, s, x, n, C, eps, gb, y, nullptr, q16);
+  launch_k(instance_norm_tokens_v4_kernel, dim3(B, C / 64), 256, 0, s, x, n, C, eps, gb, y, (__nv_bfloat16*)nullptr, q16,
+           (const float*)nullptr, (const float*)nullptr, (float*)nullptr, (__nv_bfloat16*)nullptr, (const float*)nullptr);
   count_launch();
   MOCHA_LAUNCH_CHECK("adain_norm_tokens");
   return MOCHA_OK;

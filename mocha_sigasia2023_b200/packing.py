@@ -257,6 +257,7 @@ class PackedCVAE:
                       "l1_w", "l1_b", "l2_w", "l2_b", "n1_g", "n1_b", "n2_g", "n2_b", "n3_g", "n3_b"):
                 setattr(w.dec[l], f, b.ptr(f"de{l}.{f}"))
         w.dec0_sa = None
+        w.dec0_q16 = None
         self.struct = w
         # decoder layer 0's self-attention block acts on the constant positional query: compute it once
         lib = _lib.load()
@@ -268,3 +269,16 @@ class PackedCVAE:
                    "mocha_cvae_precompute_dec0")
         torch.cuda.current_stream(device).synchronize()
         w.dec0_sa = self.dec0_sa.data_ptr()
+        # ... and so does the layer-0 cross-attention query projection of that table (bf16 operands, like the per-clip
+        # projection it replaces): mocha_linear in bf16 mode on the registered weight blob
+        D = latent_dim
+        q32 = torch.empty((output_seq, D), dtype=torch.float32, device=device)
+        wsb = lib.mocha_linear_workspace_bytes(output_seq, D, D, _lib.MOCHA_BF16)
+        ws2 = torch.empty(max(int(wsb), 256), dtype=torch.uint8, device=device)
+        _lib.check(lib.mocha_linear(C.c_void_p(self.dec0_sa.data_ptr()), C.c_void_p(b.ptr("de0.ca_in_w")),
+                                    C.c_void_p(b.ptr("de0.ca_in_b")), None, C.c_void_p(q32.data_ptr()), output_seq, D, D, 0,
+                                    _lib.MOCHA_BF16, C.c_void_p(ws2.data_ptr()), ws2.numel(),
+                                    C.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "mocha_linear(dec0 query)")
+        torch.cuda.current_stream(device).synchronize()
+        self.dec0_q16 = q32.to(torch.bfloat16).contiguous()
+        w.dec0_q16 = self.dec0_q16.data_ptr()
