@@ -288,8 +288,10 @@ tail_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     }
   }
   if (warp >= 2) {
-    // bias / LayerNorm vectors -> shared memory (constants too: loaded before the grid dependency is waited for)
-    float* par = reinterpret_cast<float*>(smem + FT_OFF_PAR);
+    // bias / LayerNorm vectors -> shared memory with cp.async (constants: requested before the grid dependency is waited
+    // for and NOT awaited here - the epilogue warps wait for them right before their first use, several microseconds
+    // later; a blocking load here cost 4400 cycles of prologue on the critical path)
+    const uint32_t par_s = sbase + FT_OFF_PAR;
     const int t = (int)threadIdx.x - 64;
 #pragma unroll
     for (int it = 0; it < PV_COUNT / 4 / 256; ++it) {
@@ -297,10 +299,13 @@ tail_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
       const float* src = i < PV_G1 ? p.b0 : i < PV_BE1 ? p.g1 : i < PV_B1 ? p.be1 : i < PV_B2 ? p.b1 : i < PV_G2 ? p.b2 : i < PV_BE2 ? p.g2 : p.be2;
       const int base = i < PV_G1 ? PV_B0 : i < PV_BE1 ? PV_G1 : i < PV_B1 ? PV_BE1 : i < PV_B2 ? PV_B1 : i < PV_G2 ? PV_B2 : i < PV_BE2 ? PV_G2 : PV_BE2;
       const int len = base == PV_B1 ? p.Hd : FT_D;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (src && i - base < len) v = __ldg(reinterpret_cast<const float4*>(src + (i - base)));
-      *reinterpret_cast<float4*>(par + i) = v;
+      if (src && i - base < len) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(par_s + (uint32_t)i * 4u), "l"(src + (i - base)) : "memory");
+      } else {
+        asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(par_s + (uint32_t)i * 4u), "f"(0.f) : "memory");
+      }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -443,6 +448,9 @@ tail_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     // transposition tile: the A stages are free once the out-projection has completed; without an FFN the ring is
     const uint32_t tb = sbase + (nch > 0 ? FT_OFF_HB : FT_OFF_RING + FT_SLOT) + (uint32_t)e.ew * 4096u;
     load_res(res, p.R0, slab_row0, p.M, colbase, lane, p.r0_period);
+    // the staged vectors: every epilogue thread's own cp.async requests have landed, then all of them have
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    named_bar_sync(1, 256);
     mbar_wait(&bar[B_ACCP], 0);
     tc_fence_after();
     if (warp == 2 && lane == 0) FT_TRACE(24);   // epilogue: out-projection accumulator ready
