@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — characterised frames/s of MOCHA's per-frame hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--clips C | --total-clips T] [--precision bf16|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--clips C | --total-clips T] [--precision bf16|fp32|tf32x3]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...      # the UNMODIFIED reference's per-frame loop on the host cores
     python bench.py --workload match_sweep    # BASELINE config 3 alone (4096 queries x --sweep-rows rows x 23040)
@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--no-extras", action="store_true", help="headline only (skip sweep / hbm / latency / fp32 legs)")
     ap.add_argument("--no-match-sharded", action="store_true")
     ap.add_argument("--db-rows", type=int, default=385, help="character DB rows (400-frame character clip)")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "tf32x3"])
     ap.add_argument("--lanes", type=int, default=1, help="sub-batch lanes: the clips of a GPU are cut into this many groups "
                     "whose frames run concurrently on separate streams inside the captured graph (measured on B200 at 128 "
                     "clips: 1.37 / 1.49 / 1.63 / 1.83 ms per step for 1 / 2 / 3 / 4 lanes - one lane is fastest)")
@@ -576,6 +576,7 @@ def run_b200(args):
     if rank == 0 and not args.no_extras:
         if args.precision == "bf16":
             line["fp32_mode"] = fp32_mode_pass(args, dev, torch, workload, lib)
+            line["tf32x3_mode"] = fp32_mode_pass(args, dev, torch, workload, lib, precision="tf32x3")
         if not args.no_latency:
             line["latency_batch1"] = latency_pass(args, dev, torch, workload)
             line["latency_batch1_bf16"] = latency_pass(args, dev, torch, workload, precision="bf16")
@@ -739,17 +740,21 @@ def hbm_kernels(sess, torch, lib, _lib):
     return out
 
 
-def fp32_mode_pass(args, dev, torch, workload, lib):
-    """The same step in the fp32 parity mode (every contraction in fp32 FFMA, exact fp64 matcher): throughput for the
-    record, so that the bf16 headline has its reference-precision counterpart next to it."""
+def fp32_mode_pass(args, dev, torch, workload, lib, precision="fp32"):
+    """The same step in a parity mode, for the record, so that the bf16 headline has its reference-precision counterpart
+    next to it: "fp32" = every contraction in fp32 FFMA, "tf32x3" = linear layers and temporal convolutions as split-fp32
+    (3xTF32) tcgen05 GEMMs; exact fp64 matcher in both."""
     B = args.clips
-    sess, *_ = workload.build_session(B, n_db=args.db_rows, precision="fp32", device=dev, seed=5)
+    sess, *_ = workload.build_session(B, n_db=args.db_rows, precision=precision, device=dev, seed=5)
     inp = workload.step_inputs(B, seed=11)
     sess.step_host(inp["X"], inp["src_hips_vel"], inp["src_rvel"], inp["src_rang"], inp["contacts"], inp["eps"])
     sess.step_host(inp["X"], inp["src_hips_vel"], inp["src_rvel"], inp["src_rang"], inp["contacts"], inp["eps"])
     sess.capture()
     ms = timed(torch, sess.step_device, 10, warm=2)
-    return {"precision": "fp32 (FFMA GEMMs, fp64 brute-force matcher)", "clips": B, "ms_per_step": ms, "value": B / ms * 1e3, "unit": UNIT,
+    label = ("fp32 (FFMA GEMMs, fp64 brute-force matcher)" if precision == "fp32" else
+             "tf32x3 (3xTF32 tcgen05 GEMMs for linear layers / temporal convolutions, FFMA attention products, fp64 "
+             "brute-force matcher)")
+    return {"precision": label, "clips": B, "ms_per_step": ms, "value": B / ms * 1e3, "unit": UNIT,
             "tolerance": "1e-4 relative vs the reference (tests/test_gpu_session.py, test_gpu_e2e.py)"}
 
 

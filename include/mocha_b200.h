@@ -20,7 +20,12 @@
  *    Generator.mot_embedding ('b t v c', model.py:43), token tensors [B,n,C], quaternions [w,x,y,z].
  *  - precision: MOCHA_FP32 computes every contraction in fp32 FFMA (parity mode, 1e-4 rel);
  *    MOCHA_BF16 runs the dense contractions on tcgen05 tensor cores with bf16 operands and fp32
- *    accumulation in TMEM (throughput mode, 2e-2 rel).
+ *    accumulation in TMEM (throughput mode, 2e-2 rel); MOCHA_TF32X3 is the parity mode on the tensor
+ *    cores: every linear layer and temporal convolution splits its fp32 operands into tf32 hi / lo parts
+ *    and runs a . w = a_hi w_hi + a_lo w_hi + a_hi w_lo as one tcgen05 kind::tf32 GEMM over a 3x longer K
+ *    (fp32 accumulation in TMEM, same 1e-4 tolerance as MOCHA_FP32; attention products and the matcher
+ *    stay on the fp32 / fp64 kernels). Its split operands live in whatever workspace is left after the
+ *    stage's own buffers; long layers run as row chunks when that is short.
  */
 #ifndef MOCHA_B200_H_
 #define MOCHA_B200_H_
@@ -41,6 +46,7 @@ extern "C" {
 
 #define MOCHA_FP32 0
 #define MOCHA_BF16 1
+#define MOCHA_TF32X3 2
 
 #define MOCHA_MAX_DEPTH 4
 
@@ -63,6 +69,12 @@ int mocha_struct_sizes(size_t* out, int n);
 /* MOCHA_BF16 layers look up the bf16 copy of a weight by address: register the bf16 mirror
  * (same element order) of each contiguous fp32 weight blob once after packing. */
 int mocha_register_bf16_blob(const float* d_blob32, const void* d_blob16, size_t elems);
+
+/* The mocha_*_workspace_bytes queries below answer for this precision mode from now on (process-wide).
+ * The default covers MOCHA_FP32 and MOCHA_BF16; set MOCHA_TF32X3 before sizing the workspace of a
+ * stage that will run in that mode (its split fp32 operands are three times the layer's A operand);
+ * with less room the layers still run, as row chunks. */
+int mocha_workspace_precision(int precision);
 
 /* ---- model geometry (configs/config.yaml:13-43) -------------------------------------------- */
 typedef struct {

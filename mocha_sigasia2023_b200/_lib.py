@@ -5,6 +5,7 @@ raises — there is no CPU or PyTorch fallback anywhere in this package.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 
@@ -14,6 +15,27 @@ LIB_PATH = os.environ.get("MOCHA_LIB") or os.path.join(_HERE, "libmocha_b200.so"
 
 MOCHA_FP32 = 0
 MOCHA_BF16 = 1
+MOCHA_TF32X3 = 2
+
+
+@contextlib.contextmanager
+def workspace_precision(prec: int):
+    """The mocha_*_workspace_bytes queries inside the block answer for precision mode `prec` (MOCHA_TF32X3 needs room for
+    its split operands); the library default is restored afterwards."""
+    lib = load()
+    check(lib.mocha_workspace_precision(int(prec)), "mocha_workspace_precision")
+    try:
+        yield
+    finally:
+        lib.mocha_workspace_precision(MOCHA_BF16)
+
+
+def precision_code(precision: str) -> int:
+    """"fp32" (FFMA parity mode), "bf16" (tcgen05 throughput mode) or "tf32x3" (parity mode on tcgen05: split-fp32 GEMMs)."""
+    try:
+        return {"fp32": MOCHA_FP32, "bf16": MOCHA_BF16, "tf32x3": MOCHA_TF32X3}[precision]
+    except KeyError:
+        raise ValueError(f"unknown precision {precision!r} (fp32 | bf16 | tf32x3)") from None
 MAX_DEPTH = 4
 
 c_float_p = C.c_void_p  # device pointers travel as integers
@@ -117,6 +139,7 @@ SIGNATURES = {
     "mocha_reset_launch_count": (None, []),
     "mocha_struct_sizes": (_I, [C.POINTER(C.c_size_t), _I]),
     "mocha_register_bf16_blob": (_I, [_P, _P, _S]),
+    "mocha_workspace_precision": (_I, [_I]),
     "mocha_embed_workspace_bytes": (_S, [C.POINTER(Dims), _I]),
     "mocha_embed_fwd": (_I, [C.POINTER(GeneratorWeights), _P, _I, _P, _I, _I, _P, _S, _P]),
     "mocha_bench_tconv": (_I, [C.POINTER(GeneratorWeights), _P, _I, _P, _I, _I, _P, _S, _P]),

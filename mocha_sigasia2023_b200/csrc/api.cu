@@ -58,6 +58,15 @@ extern "C" int mocha_register_bf16_blob(const float* blob32, const void* blob16,
   return MOCHA_OK;
 }
 
+// Workspace size queries (mocha_*_workspace_bytes) answer for this precision mode from now on (process-wide; the
+// default covers MOCHA_FP32 and MOCHA_BF16; MOCHA_TF32X3 adds room for its split operands).
+extern "C" int mocha_workspace_precision(int precision) {
+  if (precision != MOCHA_FP32 && precision != MOCHA_BF16 && precision != MOCHA_TF32X3)
+    return mocha::set_error(MOCHA_ERR_ARG, "mocha_workspace_precision: unknown precision %d", precision);
+  mocha::tc_set_workspace_precision(precision);
+  return MOCHA_OK;
+}
+
 // sizeof() of every ABI struct, so a binding can verify its mirror definitions at load time.
 // order: dims, enc_layer, dec_layer, generator_weights, cvae_enc_layer, cvae_dec_layer, cvae_weights,
 //        clip_state, post_params, frame_out

@@ -1850,7 +1850,7 @@ template <class Epi>
 int dispatch_bn_impl(int bn, const CUtensorMap& tmA, const void* Wptr, unsigned long long wrows, unsigned long long K,
                 TcShape sh, int N, int num_kb, const Epi& epi, cudaStream_t s, unsigned long long wpitch = 0) {
   CUtensorMap tmB;
-  MOCHA_TRY(make_tmap(&tmB, Wptr, wrows, K, sh.b_mn ? 64 : bn, wpitch));
+  MOCHA_TRY(make_tmap(&tmB, Wptr, wrows, K, sh.b_mn ? 64 : bn, wpitch, Epi::kTf32));
   sh.tiles_n = ceil_div(N, bn);
   sh.tiles_per_unit = 1;
   sh.units = sh.tiles_m_total * sh.tiles_n;
@@ -1880,6 +1880,19 @@ int dispatch_bn(int bn, const CUtensorMap& tmA, const void* Wptr, unsigned long 
   return dispatch_bn_impl(bn, tmA, Wptr, wrows, K, sh, N, num_kb, LinearEpiT<0>{epi}, s, wpitch);
 }
 
+// fp32 operands consumed as TF32 (kind::tf32, 32 elements per 128-byte k-block row): the 3xTF32 parity mode's GEMMs.
+// Same epilogues; fp32 output only (modes 0 / 3 / 4).
+template <int MODE>
+struct LinearEpiTf : LinearEpiT<MODE> {
+  static constexpr bool kTf32 = true;
+};
+int dispatch_bn_tf32(int bn, const CUtensorMap& tmA, const void* Wptr, unsigned long long wrows, unsigned long long K,
+                     TcShape sh, int N, int num_kb, const LinearEpi& epi, cudaStream_t s) {
+  if (epi.tma == 2) return dispatch_bn_impl(bn, tmA, Wptr, wrows, K, sh, N, num_kb, LinearEpiTf<3>{LinearEpiT<3>{epi}}, s);
+  if (epi.tma == 1) return dispatch_bn_impl(bn, tmA, Wptr, wrows, K, sh, N, num_kb, LinearEpiTf<4>{LinearEpiT<4>{epi}}, s);
+  return dispatch_bn_impl(bn, tmA, Wptr, wrows, K, sh, N, num_kb, LinearEpiTf<0>{LinearEpiT<0>{epi}}, s);
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -1899,7 +1912,14 @@ int tc_num_sms() { return num_sms(); }
 
 bool tc_linear_supported(int M, int N, int K) { return M >= 1 && N >= 8 && K >= 64 && (K % 8) == 0; }
 
-size_t tc_scratch_bytes(size_t rows, size_t K) { return align_up(rows * K * 2, 256) + 256; }
+// Workspace queries answer for the precision mode set by mocha_workspace_precision() (default: bf16, which also covers
+// fp32): the 3xTF32 mode stages [rows, 3K] fp32 split operands plus the split weights (allowance: 2048 output rows).
+int g_ws_precision = MOCHA_BF16;
+void tc_set_workspace_precision(int precision) { g_ws_precision = precision; }
+size_t tc_scratch_bytes(size_t rows, size_t K) {
+  if (g_ws_precision == MOCHA_TF32X3) return align_up((rows + 2048) * K * 12, 256) + 1024;
+  return align_up(rows * K * 2, 256) + 256;
+}
 
 void tc_register_blob(const float* blob32, const void* blob16, size_t elems) {
   // drop every entry that overlaps the new range (stale mirrors of freed / re-used allocations)
@@ -2019,10 +2039,196 @@ int tc_cast(const float* x, __nv_bfloat16* y, long long n, int lrelu, cudaStream
   return MOCHA_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// 3xTF32: fp32-grade GEMMs on the tensor cores (MOCHA_TF32X3 precision mode).
+//   x = hi + lo with hi = tf32(x), lo = tf32(x - hi) (both exactly representable, so the MMA's operand truncation is a
+//   no-op);  a . w ~= a_hi w_hi + a_lo w_hi + a_hi w_lo  (the dropped lo x lo term is ~2^-22 relative), accumulated in
+//   fp32 in TMEM. The three products run as ONE GEMM over a three times longer K: the A operand is written as
+//   [hi | lo | hi] and the weights as [hi | hi | lo] per row (per tap for the temporal convolutions), so the main loop,
+//   the implicit-convolution tap windows and every epilogue are the bf16 path's.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void split4(const float4& v, float4& hi, float4& lo) {
+  hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
+  lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
+}
+
+// two jobs in one launch: blocks [0, nblkA) split A [rowsA, K] -> [rowsA, 3K] as [hi | lo | hi], the rest split
+// W [rowsW, K] -> [rowsW, 3K] as [hi | hi | lo]
+__global__ void split3_kernel(const float* __restrict__ A, float* __restrict__ A3, long long rowsA, int a_lrelu,
+                              const float* __restrict__ W, float* __restrict__ W3, long long rowsW, int K, int nblkA) {
+  pdl_trigger();
+  pdl_wait();
+  const bool isw = (int)blockIdx.x >= nblkA;
+  const float* x = isw ? W : A;
+  float* y = isw ? W3 : A3;
+  const long long rows = isw ? rowsW : rowsA;
+  const int k4 = K / 4;
+  const long long i4 = (long long)(isw ? blockIdx.x - nblkA : blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i4 >= rows * k4) return;
+  const long long r = i4 / k4;
+  const int c = (int)(i4 - r * k4) * 4;
+  float4 v = *reinterpret_cast<const float4*>(x + r * K + c);
+  if (!isw && a_lrelu) { v.x = lrelu02(v.x); v.y = lrelu02(v.y); v.z = lrelu02(v.z); v.w = lrelu02(v.w); }
+  float4 hi, lo;
+  split4(v, hi, lo);
+  float* o = y + r * 3 * K + c;
+  *reinterpret_cast<float4*>(o) = hi;
+  *reinterpret_cast<float4*>(o + K) = isw ? hi : lo;
+  *reinterpret_cast<float4*>(o + 2 * K) = isw ? lo : hi;
+}
+
+// X fp32 [nb, T/tdiv, V, C] -> [nb, T + 2*pad, V, 3C] reflect-padded along T, rows as [hi | lo | hi]
+__global__ void reflect_pad_split3_kernel(const float* __restrict__ x, float* __restrict__ y, int T, int V, int C, int pad,
+                                          int tdiv, long long total4) {
+  pdl_trigger();
+  pdl_wait();
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= total4) return;
+  const long long i = i4 * 4;
+  const int c = (int)(i % C);
+  const long long r = i / C;
+  const int v = (int)(r % V);
+  const long long bt = r / V;
+  const int Tp = T + 2 * pad;
+  const int tp = (int)(bt % Tp);
+  const long long b = bt / Tp;
+  int t = tp - pad;
+  if (t < 0) t = -t;
+  if (t >= T) t = 2 * (T - 1) - t;
+  t /= tdiv;
+  const float4 val = *reinterpret_cast<const float4*>(x + (((b * (T / tdiv) + t) * V + v) * (long long)C + c));
+  float4 hi, lo;
+  split4(val, hi, lo);
+  float* o = y + r * 3 * C + c;
+  *reinterpret_cast<float4*>(o) = hi;
+  *reinterpret_cast<float4*>(o + C) = lo;
+  *reinterpret_cast<float4*>(o + 2 * C) = hi;
+}
+
+constexpr int TF_K = 32;  // fp32 elements per 128-byte k-block row
+
+}  // namespace
+
+bool tc_linear_tf32x3_supported(int M, int N, int K) { return M >= 1 && N >= 8 && K >= 16 && (K % 4) == 0; }
+
+int tc_linear_tf32x3(const float* A, const float* W, const float* bias, int bias_period, const float* res, float* C, int M,
+                     int N, int K, int act, int a_lrelu, Workspace& ws, cudaStream_t s) {
+  MOCHA_CHECK_ARG(A && W && C, "tc_linear_tf32x3: null operand");
+  MOCHA_CHECK_ARG(tc_linear_tf32x3_supported(M, N, K), "tc_linear_tf32x3: unsupported shape M=%d N=%d K=%d", M, N, K);
+  MOCHA_CHECK_ARG(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W)) & 15) == 0, "tc_linear_tf32x3: operands not 16 B aligned");
+  const size_t mark = ws.off;
+  const int K3 = 3 * K;
+  float* W3 = ws.take<float>((size_t)N * K3);
+  if (!W3) return set_error(MOCHA_ERR_WORKSPACE, "tc_linear_tf32x3: workspace too small for the split weights");
+  // the split A operand takes whatever workspace is left; long problems run as row chunks (a multiple of 128 rows and of
+  // the bias period, so tiles and the periodic bias keep their phase)
+  const long long quantum = bias_period > 0 ? 128LL * bias_period : 128LL;
+  const size_t avail = ws.cap > ws.off + 512 ? ws.cap - ws.off - 512 : 0;
+  long long rows_fit = (long long)(avail / ((size_t)K3 * 4));
+  if (rows_fit < M) rows_fit = rows_fit / quantum * quantum;
+  if (rows_fit <= 0) return set_error(MOCHA_ERR_WORKSPACE, "tc_linear_tf32x3: workspace too small for the split A operand");
+  if (rows_fit > M) rows_fit = M;
+  float* A3 = ws.take<float>((size_t)rows_fit * K3);
+  if (!A3) return set_error(MOCHA_ERR_WORKSPACE, "tc_linear_tf32x3: workspace too small for the split A operand");
+  int rc = MOCHA_OK;
+  bool w_done = false;
+  for (long long m0 = 0; m0 < M && rc == MOCHA_OK; m0 += rows_fit) {
+    const int mc = (int)((long long)M - m0 < rows_fit ? (long long)M - m0 : rows_fit);
+    const int nblkA = (int)(((long long)mc * (K / 4) + 255) / 256);
+    const int nblkW = w_done ? 0 : (int)(((long long)N * (K / 4) + 255) / 256);
+    launch_k(split3_kernel, (unsigned)(nblkA + nblkW), 256, 0, s, A + m0 * K, A3, (long long)mc, a_lrelu, W, W3, (long long)N, K, nblkA);
+    count_launch();
+    MOCHA_LAUNCH_CHECK("split3_kernel");
+    w_done = true;
+    CUtensorMap tmA;
+    MOCHA_TRY(make_tmap(&tmA, A3, (unsigned long long)mc, (unsigned long long)K3, BLOCK_M, 0, true));
+    TcShape sh{};
+    sh.nb = 1;
+    sh.rows_out_per_b = mc;
+    sh.tiles_m_per_b = ceil_div(mc, BLOCK_M);
+    sh.tiles_m_total = sh.tiles_m_per_b;
+    sh.src_rows_per_b = mc;
+    sh.taps = 1;
+    sh.kb_per_tap = ceil_div(K3, TF_K);
+    sh.tap_row_stride = 0;
+    LinearEpi epi{C + m0 * N, N, N, bias, bias_period, res ? res + m0 * N : nullptr, act, nullptr, 0};
+    MOCHA_TRY(setup_out_tma(epi, (unsigned long long)mc, 1));
+    rc = dispatch_bn_tf32(pick_bn(sh.tiles_m_total, N, sh.kb_per_tap), tmA, W3, (unsigned long long)N, (unsigned long long)K3, sh, N,
+                          sh.kb_per_tap, epi, s);
+  }
+  ws.off = mark;
+  return rc;
+}
+
+bool tc_tconv_tf32x3_supported(int B, int T, int V, int Cin, int Cout, int taps) {
+  return B >= 1 && (Cin % TF_K) == 0 && Cout >= 8 && (taps & 1) && taps / 2 < T && (long long)T * V >= 1;
+}
+
+int tc_tconv_tf32x3(const float* X, const float* W, const float* bias, int bias_period, float* C, int B, int T, int V, int Cin,
+                    int Cout, int taps, int tdiv, Workspace& ws, cudaStream_t s) {
+  MOCHA_CHECK_ARG(X && W && C, "tc_tconv_tf32x3: null operand");
+  MOCHA_CHECK_ARG(tdiv >= 1 && T % tdiv == 0, "tc_tconv_tf32x3: T=%d not a multiple of tdiv=%d", T, tdiv);
+  MOCHA_CHECK_ARG(tc_tconv_tf32x3_supported(B, T, V, Cin, Cout, taps), "tc_tconv_tf32x3: unsupported geometry");
+  MOCHA_CHECK_ARG(bias_period == 0 || (T * V) % bias_period == 0, "tc_tconv_tf32x3: bias period does not divide an image");
+  const int pad = taps / 2, Tp = T + 2 * pad, C3 = 3 * Cin;
+  const size_t mark = ws.off;
+  // weights [Cout, taps * Cin] (tap-major K) -> [Cout, taps * 3 Cin], [hi | hi | lo] per tap
+  float* W3 = ws.take<float>((size_t)Cout * taps * C3);
+  if (!W3) return set_error(MOCHA_ERR_WORKSPACE, "tc_tconv_tf32x3: workspace too small for the split weights");
+  const size_t img_bytes = (size_t)Tp * V * C3 * 4;
+  const size_t avail = ws.cap > ws.off + 512 ? ws.cap - ws.off - 512 : 0;
+  int imgs_fit = (int)(avail / img_bytes < (size_t)B ? avail / img_bytes : (size_t)B);
+  if (imgs_fit <= 0) return set_error(MOCHA_ERR_WORKSPACE, "tc_tconv_tf32x3: workspace too small for the padded split operand");
+  float* X3 = ws.take<float>((size_t)imgs_fit * Tp * V * C3);
+  if (!X3) return set_error(MOCHA_ERR_WORKSPACE, "tc_tconv_tf32x3: workspace too small for the padded split operand");
+  {
+    const long long rowsW = (long long)Cout * taps;
+    const int nblkW = (int)((rowsW * (Cin / 4) + 255) / 256);
+    launch_k(split3_kernel, (unsigned)nblkW, 256, 0, s, (const float*)nullptr, (float*)nullptr, 0LL, 0, W, W3, rowsW, Cin, 0);
+    count_launch();
+    MOCHA_LAUNCH_CHECK("split3_kernel");
+  }
+  int rc = MOCHA_OK;
+  for (int b0 = 0; b0 < B && rc == MOCHA_OK; b0 += imgs_fit) {
+    const int nb = B - b0 < imgs_fit ? B - b0 : imgs_fit;
+    const long long total4 = (long long)nb * Tp * V * Cin / 4;
+    launch_k(reflect_pad_split3_kernel, (unsigned)((total4 + 255) / 256), 256, 0, s,
+             X + (long long)b0 * (T / tdiv) * V * Cin, X3, T, V, Cin, pad, tdiv, total4);
+    count_launch();
+    MOCHA_LAUNCH_CHECK("reflect_pad_split3_kernel");
+    CUtensorMap tmA;
+    MOCHA_TRY(make_tmap(&tmA, X3, (unsigned long long)nb * Tp * V, (unsigned long long)C3, BLOCK_M, 0, true));
+    TcShape sh{};
+    sh.nb = nb;
+    sh.rows_out_per_b = T * V;
+    sh.tiles_m_per_b = ceil_div(T * V, BLOCK_M);
+    sh.tiles_m_total = sh.tiles_m_per_b * nb;
+    sh.src_rows_per_b = (long long)Tp * V;
+    sh.taps = taps;
+    sh.kb_per_tap = C3 / TF_K;
+    sh.tap_row_stride = V;
+    LinearEpi epi{C + (long long)b0 * T * V * Cout, Cout, Cout, bias, bias_period, nullptr, ACT_NONE, nullptr, 0};
+    MOCHA_TRY(setup_out_tma(epi, (unsigned long long)T * V, (unsigned long long)nb));
+    rc = dispatch_bn_tf32(pick_bn(sh.tiles_m_total, Cout, taps * sh.kb_per_tap), tmA, W3, (unsigned long long)Cout,
+                          (unsigned long long)taps * C3, sh, Cout, taps * sh.kb_per_tap, epi, s);
+  }
+  ws.off = mark;
+  return rc;
+}
+
 bool tc_tconv_supported(int B, int T, int V, int Cin, int Cout, int taps) {
   return B >= 1 && (Cin % BLOCK_K) == 0 && Cout >= 8 && (taps & 1) && taps / 2 < T && (long long)T * V >= 1;
 }
 size_t tc_tconv_scratch_bytes(int B, int T, int V, int Cin, int taps) {
+  if (g_ws_precision == MOCHA_TF32X3)
+    return align_up(((size_t)B * (T + 2 * (taps / 2)) * V + (size_t)2048 * taps) * Cin * 12, 256) + 1024;
   return align_up((size_t)B * (T + 2 * (taps / 2)) * V * Cin * 2, 256) + 256;
 }
 

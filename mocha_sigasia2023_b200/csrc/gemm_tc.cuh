@@ -27,6 +27,7 @@ int tc_num_sms();
 bool tc_linear_supported(int M, int N, int K);
 // bytes of bf16 scratch needed to stage an [rows, K] A operand
 size_t tc_scratch_bytes(size_t rows, size_t K);
+void tc_set_workspace_precision(int precision);
 
 // Registered bf16 mirror of an fp32 weight blob: W16 = blob16 + (W - blob32).
 void tc_register_blob(const float* blob32, const void* blob16, size_t elems);
@@ -65,6 +66,16 @@ int tc_tconv_ex(const float* X, const __nv_bfloat16* Xh, const float* W, const f
 // GEMM over nb images whose outputs land at out + b * out_img_pitch_rows * N (TMA-store epilogue, column bias)
 int tc_linear_bf16_img(const __nv_bfloat16* A16, int lda, const __nv_bfloat16* W16, const float* bias, TcOut out, int nb,
                        int rows_per_img, long long out_img_pitch_rows, int N, int K, int act, cudaStream_t s);
+
+// ---- 3xTF32: fp32-grade GEMMs on the tensor cores (MOCHA_TF32X3) -------------------------------------
+// fp32 operands split into tf32 hi / lo parts ([hi | lo | hi] x [hi | hi | lo] over a 3x longer K), fp32 accumulation in
+// TMEM, the bf16 path's main loop and epilogues. Long problems run as row / image chunks sized by the free workspace.
+bool tc_linear_tf32x3_supported(int M, int N, int K);
+int tc_linear_tf32x3(const float* A, const float* W, const float* bias, int bias_period, const float* res, float* C, int M,
+                     int N, int K, int act, int a_lrelu, Workspace& ws, cudaStream_t s);
+bool tc_tconv_tf32x3_supported(int B, int T, int V, int Cin, int Cout, int taps);
+int tc_tconv_tf32x3(const float* X, const float* W, const float* bias, int bias_period, float* C, int B, int T, int V, int Cin,
+                    int Cout, int taps, int tdiv, Workspace& ws, cudaStream_t s);
 
 // ---- attention: softmax(Q K^T / sqrt(dh)) V for B*H (batch, head) problems on tensor cores ------------
 // q/k/v are fp32 strided views [B*n, ld] with head h at columns h*dh; S is a [B,H,nq,nkv] fp32 scratch.

@@ -19,13 +19,15 @@ struct Ctx {
   Workspace* ws;
 };
 
-// C[M,N] = act(prologue(A) W^T + bias) (+res); fp32 FFMA or tcgen05 bf16 depending on ctx.precision.
+// C[M,N] = act(prologue(A) W^T + bias) (+res); fp32 FFMA, tcgen05 bf16 or tcgen05 3xTF32 depending on ctx.precision.
 // Shapes the tensor-core kernel does not take (tiny N/K, gathers) stay on the fp32 kernel.
 int dense(const Ctx& c, const float* A, int lda, const float* W, const float* bias, int bias_period,
           const float* res, float* C, int M, int N, int K, int act, int a_lrelu = 0) {
   if (c.precision == MOCHA_BF16 && tc_linear_supported(M, N, K) && lda == K) {
     return tc_linear(A, W, bias, bias_period, res, C, M, N, K, act, a_lrelu, *c.ws, c.s);
   }
+  if (c.precision == MOCHA_TF32X3 && tc_linear_tf32x3_supported(M, N, K) && lda == K)
+    return tc_linear_tf32x3(A, W, bias, bias_period, res, C, M, N, K, act, a_lrelu, *c.ws, c.s);
   GemmParams p;
   p.A = A; p.W = W; p.C = C;
   p.M = M; p.N = N; p.K = K;
@@ -40,6 +42,8 @@ int tconv(const Ctx& c, const float* A, const float* W, const float* bias, int b
           int T, int V, int Cin, int Cout, int taps, int tdiv) {
   if (c.precision == MOCHA_BF16 && tc_tconv_supported(B, T, V, Cin, Cout, taps))
     return tc_tconv(A, W, bias, bias_period, C, B, T, V, Cin, Cout, taps, tdiv, *c.ws, c.s);
+  if (c.precision == MOCHA_TF32X3 && tc_tconv_tf32x3_supported(B, T, V, Cin, Cout, taps))
+    return tc_tconv_tf32x3(A, W, bias, bias_period, C, B, T, V, Cin, Cout, taps, tdiv, *c.ws, c.s);
   GemmParams p;
   p.A = A; p.W = W; p.C = C;
   p.M = B * T * V; p.N = Cout; p.K = taps * Cin;
@@ -498,7 +502,7 @@ extern "C" int mocha_cvae_condition(const float* src_cnt, const float* prev, con
 // exposed dense primitive
 // ------------------------------------------------------------------------------------------------
 extern "C" size_t mocha_linear_workspace_bytes(int M, int N, int K, int precision) {
-  (void)N;
+  if (precision == MOCHA_TF32X3) return ((size_t)M + (size_t)N) * 3 * (size_t)K * 4 + 8192;
   return precision == MOCHA_BF16 ? tc_scratch_bytes((size_t)M, (size_t)K) + 4096 : 0;
 }
 

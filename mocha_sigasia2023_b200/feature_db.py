@@ -62,7 +62,7 @@ class FeatureEncoder:
         _lib.check(self.lib.mocha_check_device(), "mocha_check_device")
         self.dev = torch.device(device)
         self.B = batch
-        self.prec = _lib.MOCHA_BF16 if precision == "bf16" else _lib.MOCHA_FP32
+        self.prec = _lib.precision_code(precision)
         self.gen = packing.PackedGenerator(gen_sd, cfg, self.dev)
         d = self.gen.dims
         self.n, self.D = self.gen.ntok, d.D
@@ -72,7 +72,8 @@ class FeatureEncoder:
         self.X = torch.zeros((batch, d.T, d.V, d.Cin), **f32)
         self.tokens = torch.empty((batch, self.n, self.D), **f32)
         dims = C.byref(self.gen.struct.dims)
-        nbytes = max(self.lib.mocha_embed_workspace_bytes(dims, batch), self.lib.mocha_encoder_workspace_bytes(dims, batch))
+        with _lib.workspace_precision(self.prec):
+            nbytes = max(self.lib.mocha_embed_workspace_bytes(dims, batch), self.lib.mocha_encoder_workspace_bytes(dims, batch))
         self.ws = torch.empty(nbytes + 4096, dtype=torch.uint8, device=self.dev)
 
     def encode_into(self, X: torch.Tensor, encoded: torch.Tensor, cnt, rows32, rows16):

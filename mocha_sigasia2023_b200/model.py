@@ -98,7 +98,7 @@ class Generator(nn.Module):
         return self._packed
 
     def _prec(self) -> int:
-        return _lib.MOCHA_BF16 if self.precision == "bf16" else _lib.MOCHA_FP32
+        return _lib.precision_code(self.precision)
 
     def _check_in(self, x, shape_tail):
         _lib.require_cuda(x)
@@ -116,7 +116,8 @@ class Generator(nn.Module):
         B = X.shape[0]
         lib = _lib.load()
         out = torch.empty((B, pk.ntok, d.D), dtype=torch.float32, device=X.device)
-        nbytes = lib.mocha_embed_workspace_bytes(C.byref(pk.struct.dims), B)
+        with _lib.workspace_precision(self._prec()):
+            nbytes = lib.mocha_embed_workspace_bytes(C.byref(pk.struct.dims), B)
         ws = self._ws.get(nbytes, X.device)
         _lib.check(lib.mocha_embed_fwd(C.byref(pk.struct), _lib.ptr(X), B, _lib.ptr(out), int(add_pos_emb),
                                        self._prec(), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "mocha_embed_fwd")
@@ -130,7 +131,8 @@ class Generator(nn.Module):
         B = tokens.shape[0]
         lib = _lib.load()
         out = torch.empty_like(tokens)
-        nbytes = lib.mocha_encoder_workspace_bytes(C.byref(pk.struct.dims), B)
+        with _lib.workspace_precision(self._prec()):
+            nbytes = lib.mocha_encoder_workspace_bytes(C.byref(pk.struct.dims), B)
         ws = self._ws.get(nbytes, tokens.device)
         _lib.check(lib.mocha_encoder_fwd(C.byref(pk.struct), _lib.ptr(tokens), B, _lib.ptr(out), self._prec(),
                                          _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "mocha_encoder_fwd")
@@ -147,7 +149,8 @@ class Generator(nn.Module):
         B = src.shape[0]
         lib = _lib.load()
         out = torch.empty_like(src)
-        nbytes = lib.mocha_decoder_workspace_bytes(C.byref(pk.struct.dims), B)
+        with _lib.workspace_precision(self._prec()):
+            nbytes = lib.mocha_decoder_workspace_bytes(C.byref(pk.struct.dims), B)
         ws = self._ws.get(nbytes, src.device)
         _lib.check(lib.mocha_decoder_fwd(C.byref(pk.struct), _lib.ptr(src), _lib.ptr(sty), B, _lib.ptr(out),
                                          self._prec(), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
@@ -162,7 +165,8 @@ class Generator(nn.Module):
         B = tokens.shape[0]
         lib = _lib.load()
         out = torch.empty((B, d.T, d.V, d.Cin), dtype=torch.float32, device=tokens.device)
-        nbytes = lib.mocha_to_mot_workspace_bytes(C.byref(pk.struct.dims), B)
+        with _lib.workspace_precision(self._prec()):
+            nbytes = lib.mocha_to_mot_workspace_bytes(C.byref(pk.struct.dims), B)
         ws = self._ws.get(nbytes, tokens.device)
         _lib.check(lib.mocha_to_mot_fwd(C.byref(pk.struct), _lib.ptr(tokens), B, _lib.ptr(out), None, None, None,
                                         self._prec(), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),

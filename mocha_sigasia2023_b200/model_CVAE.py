@@ -50,7 +50,7 @@ class CVAE(nn.Module):
         return self._packed
 
     def _prec(self):
-        return _lib.MOCHA_BF16 if self.precision == "bf16" else _lib.MOCHA_FP32
+        return _lib.precision_code(self.precision)
 
     def _run(self, c, eps):
         pk = self._pack()
@@ -63,7 +63,8 @@ class CVAE(nn.Module):
         out = torch.empty((B, self.output_seq, self.latent_dim), dtype=torch.float32, device=c.device)
         mu = torch.empty((B, self.latent_dim), dtype=torch.float32, device=c.device)
         logvar = torch.empty_like(mu)
-        nbytes = lib.mocha_cvae_workspace_bytes(C.byref(pk.struct), B, ncond)
+        with _lib.workspace_precision(self._prec()):
+            nbytes = lib.mocha_cvae_workspace_bytes(C.byref(pk.struct), B, ncond)
         ws = self._ws.get(nbytes, c.device)
         _lib.check(lib.mocha_cvae_sample(C.byref(pk.struct), _lib.ptr(c), B, ncond, _lib.ptr(eps), _lib.ptr(out),
                                          _lib.ptr(mu), _lib.ptr(logvar), None, None, None, self._prec(),

@@ -43,7 +43,7 @@ class CharacterizationSession:
         _lib.check(self.lib.mocha_check_device(), "mocha_check_device")
         dev = torch.device(device)
         self.dev, self.B = dev, batch
-        self.prec = _lib.MOCHA_BF16 if precision == "bf16" else _lib.MOCHA_FP32
+        self.prec = _lib.precision_code(precision)
         self.gen = packing.PackedGenerator(gen_sd, cfg, dev)
         self.cvae = packing.PackedCVAE(cvae_sd, 90, 256, 2, 4, 512, dev)
         d = self.gen.dims
@@ -102,11 +102,12 @@ class CharacterizationSession:
         self.post = kinematics.PostProcessor(B, dev, post_params)
         self.cm_post = kinematics.PostProcessor(B, dev, post_params) if with_cm_path else None
         dims = C.byref(self.gen.struct.dims)
-        nbytes = max(self.lib.mocha_embed_workspace_bytes(dims, B), self.lib.mocha_encoder_workspace_bytes(dims, B),
-                     self.lib.mocha_decoder_workspace_bytes(dims, B), self.lib.mocha_to_mot_workspace_bytes(dims, B),
-                     self.lib.mocha_cvae_workspace_bytes(C.byref(self.cvae.struct), B, 2 * n),
-                     self.lib.mocha_match_exact_workspace_bytes(B, self.tree.N, 1),
-                     self.lib.mocha_match_tc_workspace_bytes(B, self.tree.N, self.tree.D, self.tree.kc))
+        with _lib.workspace_precision(self.prec):
+            nbytes = max(self.lib.mocha_embed_workspace_bytes(dims, B), self.lib.mocha_encoder_workspace_bytes(dims, B),
+                         self.lib.mocha_decoder_workspace_bytes(dims, B), self.lib.mocha_to_mot_workspace_bytes(dims, B),
+                         self.lib.mocha_cvae_workspace_bytes(C.byref(self.cvae.struct), B, 2 * n),
+                         self.lib.mocha_match_exact_workspace_bytes(B, self.tree.N, 1),
+                         self.lib.mocha_match_tc_workspace_bytes(B, self.tree.N, self.tree.D, self.tree.kc))
         self.ws = torch.empty(nbytes + 4096, dtype=torch.uint8, device=dev)
         # Sub-batch lanes: clips are independent, so the batch can be cut into `lanes` contiguous groups whose frames
         # run concurrently on separate streams (forked / joined inside the captured graph). Most kernels of the frame

@@ -146,3 +146,50 @@ def test_bf16_mode_at_bench_batch_sizes():
     for name, a, b in zip(("tokens", "encoded", "decoded", "Ytil"), outs["bf16"], outs["fp32"]):
         assert np.isfinite(a).all(), name
         assert rel_err(a, b) < RTOL_BF16, (name, rel_err(a, b))
+
+
+def test_tf32x3_tensor_core_parity_mode(gold):
+    """MOCHA_TF32X3: every linear layer / temporal convolution as a split-fp32 (3xTF32) tcgen05 GEMM must meet the fp32
+    tolerance (1e-4 relative, north_star) against the reference goldens - the parity mode on the tensor cores."""
+    g = Generator(weights.DEFAULT_MODEL_CFG, precision="tf32x3")
+    g.load_state_dict(weights.generator_state_dict(1777), strict=True)
+    g = g.to("cuda").eval()
+    src, cha = gi.pose_windows()
+    tok = g.mot_embedding(cu(src)).cpu().numpy()
+    assert rel_err(tok, gold["tokens"]) < RTOL_FP32
+    enc = g.encoder(cu(gold["tokens"]) + g.pos_emb[:, :90]).cpu().numpy()
+    assert rel_err(enc, gold["src_encoded"]) < RTOL_FP32
+    dec = g.decoder(cu(gold["src_encoded"]), cu(gold["cha_encoded"])).cpu().numpy()
+    assert rel_err(dec, gold["decoded"]) < RTOL_FP32
+    y = g.to_mot(cu(gold["decoded"])).cpu().numpy()
+    assert rel_err(y, gold["Ytil"]) < RTOL_FP32
+    c = CVAE(output_seq=90, precision="tf32x3")
+    c.load_state_dict(weights.cvae_state_dict(1778), strict=True)
+    c = c.to("cuda").eval()
+    cond, _ = gi.cvae_inputs()
+    out = c.sample(cu(cond), deterministic=True).cpu().numpy()
+    assert rel_err(out, gold["cvae_det"]) < RTOL_FP32
+
+
+def test_tf32x3_linear_chunked_and_periodic_bias():
+    """mocha_linear in MOCHA_TF32X3 mode vs float64: a workspace that only fits a fraction of the split A operand forces the
+    row-chunked path; error must stay at fp32 level (far below bf16's 4e-3)."""
+    import ctypes as C
+    from mocha_sigasia2023_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    M, N, K = 1000, 264, 192
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    R = rng.standard_normal((M, N)).astype(np.float32)
+    want = np.maximum(A.astype(np.float64) @ W.astype(np.float64).T + b, 0) + R
+    dA, dW, db, dR = cu(A), cu(W), cu(b), cu(R)
+    for ws_rows in (M + 8, 300):     # whole operand / 256-row chunks
+        nbytes = (N + ws_rows) * 3 * K * 4 + 8192
+        ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        out = torch.empty((M, N), dtype=torch.float32, device="cuda")
+        _lib.check(lib.mocha_linear(_lib.ptr(dA), _lib.ptr(dW), _lib.ptr(db), _lib.ptr(dR), _lib.ptr(out), M, N, K, 1,
+                                    _lib.MOCHA_TF32X3, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "mocha_linear")
+        got = out.cpu().numpy()
+        assert np.abs(got - want).max() < 2e-5, (ws_rows, np.abs(got - want).max())

@@ -25,7 +25,7 @@ def _run(precision, frames, B, use_graph, tol):
             sess.capture()
         got = sess.step_host(inp["X"], inp["src_hips_vel"], inp["src_rvel"], inp["src_rang"], inp["contacts"], inp["eps"])
         want = ora.step(inp["X"], inp["src_hips_vel"], inp["src_rvel"], inp["src_rang"], inp["contacts"], inp["eps"])
-        if precision == "fp32":
+        if precision in ("fp32", "tf32x3"):
             np.testing.assert_array_equal(sess.match_idx[:, 0].cpu().numpy(), ora.last["match_idx"])
         Y = sess.Y.cpu().numpy()
         err = np.abs(Y - ora.last["Y"]).max() / np.abs(ora.last["Y"]).max()
@@ -42,6 +42,11 @@ def test_session_fp32_eager():
 
 def test_session_fp32_cuda_graph():
     _run("fp32", frames=5, B=2, use_graph=True, tol=2e-4)
+
+
+def test_session_tf32x3_cuda_graph():
+    """the parity mode on the tensor cores (3xTF32 GEMMs): same tolerance and exact match indices as fp32"""
+    _run("tf32x3", frames=4, B=3, use_graph=True, tol=2e-4)
 
 
 def test_session_bf16():
