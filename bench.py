@@ -205,6 +205,48 @@ def cpu_port_rate(args, clips, steps, warmup, db_rows=None):
     return clips * len(times) / sum(times), sum(times) / len(times)
 
 
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return None
+
+
+def torch_eager_gpu_baseline(args, timeout_s=600):
+    """the reference's own Generator / CVAE modules, unmodified, on the same B200 with stock PyTorch
+    eager (library kernels), batched like the bench step, network portion of the frame only (oracle/ref_eager_gpu.py, run
+    in a subprocess). A reported baseline: "hand-written kernels vs library kernels" with the GPU held fixed."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import stage_reference
+    if stage_reference.reference_root() is None:
+        return {"unavailable": "reference tree not staged (oracle/stage_reference.py)"}
+    out = tempfile.NamedTemporaryFile("w+", suffix=".json", delete=False)
+    out.close()
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_eager_gpu.py"), "--clips", str(args.clips),
+                            "--steps", "20", "--warmup", "5", "--db-rows", str(args.db_rows), "--out", out.name],
+                           env=env, capture_output=True, text=True, timeout=timeout_s, cwd=tempfile.gettempdir())
+        if r.returncode != 0:
+            return {"unavailable": "ref_eager_gpu.py failed: " + r.stderr[-300:]}
+        modes = json.load(open(out.name))
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+    finally:
+        if os.path.exists(out.name):
+            os.unlink(out.name)
+    return {"what": "the reference's Generator + CVAE modules (unmodified) on this GPU with stock PyTorch eager kernels, "
+                    f"{args.clips} clips per step: encode + cdist/argmin match + CVAE.sample + decoder + to_mot + D2H of Y; the "
+                    "reference's NumPy FK / IK / inertialization and its second decode are NOT included (so this is an upper "
+                    "bound for an eager-GPU run of the reference), CUDA-event timed",
+            "modes": modes}
+
+
 def host_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -222,7 +264,11 @@ def cpu_baseline_record(args):
                          f"one 240-frame clip vs a 385-row character DB on CPU (torch threads = {ref['threads']} of "
                          f"{os.cpu_count()} host cpus), timed between its first and last in-loop BallTree.query call; "
                          f"the reference decodes twice per frame (trans + cm_trans) and runs batch 1",
-               "ms_per_frame": ref["ms_per_frame"], "main_s": ref["main_s"]}
+               "ms_per_frame": ref["ms_per_frame"], "main_s": ref["main_s"],
+               "p50_ms_per_frame": ref.get("p50_ms_per_frame"), "p99_ms_per_frame": ref.get("p99_ms_per_frame"),
+               "cpu_model": cpu_model(),
+               # per-stage perf_counter wrappers around the reference's own calls, whole main()
+               "stages": ref.get("stages")}
         return rec, ref["frames_per_s"], ref["ms_per_frame"]
     import numpy  # noqa: F401
     rate, sec = cpu_port_rate(args, 2, 3, 1)
@@ -590,6 +636,8 @@ def run_b200(args):
         ms = match_sharded(args, torch, dist, lib, _lib, dev, rank, world)
         if rank == 0:
             line["match_sharded"] = ms
+    if rank == 0 and world == 1 and not args.no_extras:
+        line["torch_eager_gpu"] = torch_eager_gpu_baseline(args)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"], _, _ = cpu_baseline_record(args)
     finish(line)

@@ -84,6 +84,23 @@ def run_reference_main(patched: bool = False, eps_replay=None, timing: dict | No
 
     rec = {"eps": [], "match": [], "cvae_cond": [], "cvae_out": [], "Ytil": [], "saves": []}
 
+    # per-stage perf_counter wrappers, active in timing mode only: call-through, nothing edited
+    stages = timing.setdefault("stages", {}) if timing is not None else None
+
+    def staged(name, fn):
+        if stages is None:
+            return fn
+
+        def wrapped(*a, **k):
+            t0 = time.perf_counter()
+            try:
+                return fn(*a, **k)
+            finally:
+                acc = stages.setdefault(name, [0.0, 0])
+                acc[0] += time.perf_counter() - t0
+                acc[1] += 1
+        return wrapped
+
     real_randn_like = torch.randn_like
 
     def spy_randn_like(t, *a, **k):
@@ -150,7 +167,7 @@ def run_reference_main(patched: bool = False, eps_replay=None, timing: dict | No
         def query(self, q, *a, **k):
             if timing is not None:
                 timing.setdefault("query_t", []).append(time.perf_counter())
-            r = self._t.query(q, *a, **k)
+            r = staged("BallTree.query", self._t.query)(q, *a, **k)
             rec["match"].append(np.array(r).reshape(-1)[0])
             return r
 
@@ -159,7 +176,7 @@ def run_reference_main(patched: bool = False, eps_replay=None, timing: dict | No
     real_sample = tf.CVAE.sample
 
     def spy_sample(self, c, deterministic=False):
-        out = real_sample(self, c, deterministic)
+        out = staged("CVAE.sample", real_sample)(self, c, deterministic)
         if len(rec["cvae_out"]) < 6:
             rec["cvae_cond"].append(c.detach().cpu().clone().numpy())
             rec["cvae_out"].append(out.detach().cpu().clone().numpy())
@@ -174,13 +191,22 @@ def run_reference_main(patched: bool = False, eps_replay=None, timing: dict | No
         real_to_mot = self.gen_ema.to_mot.forward
 
         def spy_to_mot(x):
-            y = real_to_mot(x)
+            y = staged("Generator.to_mot", real_to_mot)(x)
             rec["Ytil"].append(y.detach().cpu().clone().numpy()[0, -1])     # last frame row only (24,15)
             return y
 
         self.gen_ema.to_mot.forward = spy_to_mot
+        self.gen_ema.decoder.forward = staged("Generator.decoder (Transformer.forward)", self.gen_ema.decoder.forward)
+        self.gen_ema.encoder.forward = staged("Generator.encoder (Transformer.forward)", self.gen_ema.encoder.forward)
+        self.gen_ema.mot_embedding.forward = staged("Generator.mot_embedding", self.gen_ema.mot_embedding.forward)
 
     tf.Trainer.__init__ = spy_trainer_init
+    if stages is not None and not patched:
+        for name in ("fk_partial", "ik_two_bone", "from_xform_xy", "fk", "fk_vel"):
+            if hasattr(tf.quat, name):
+                setattr(tf.quat, name, staged("quat." + name, getattr(tf.quat, name)))
+        if hasattr(tf.inert, "contact_update"):
+            tf.inert.contact_update = staged("inert.contact_update", tf.inert.contact_update)
     torch.set_num_threads(threads)
     if timing is not None:
         timing["t_main0"] = time.perf_counter()
@@ -220,8 +246,11 @@ def time_reference_loop(threads: int) -> dict:
     q = timing["query_t"]            # q[0]: frame-0 initialisation (:296); q[1:]: one per loop iteration
     frames = len(q) - 2
     loop_s = q[-1] - q[1]
+    per_frame = np.diff(np.asarray(q[1:]))
+    stages = {k: {"calls": c, "total_ms": 1e3 * t, "ms_per_call": 1e3 * t / max(c, 1)} for k, (t, c) in timing["stages"].items()}
     return {"frames": frames, "loop_s": loop_s, "frames_per_s": frames / loop_s, "ms_per_frame": 1e3 * loop_s / frames,
-            "main_s": timing["t_main1"] - timing["t_main0"], "threads": timing["threads"]}
+            "p50_ms_per_frame": float(np.median(per_frame) * 1e3), "p99_ms_per_frame": float(np.percentile(per_frame, 99) * 1e3),
+            "main_s": timing["t_main1"] - timing["t_main0"], "threads": timing["threads"], "stages": stages}
 
 
 if __name__ == "__main__":
