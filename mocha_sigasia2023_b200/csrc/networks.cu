@@ -221,7 +221,7 @@ extern "C" size_t mocha_decoder_workspace_bytes(const mocha_dims* d, int B) {
   const size_t n = ntok(*d), R = (size_t)B * n, inner = (size_t)d->heads * d->dec_dh;
   size_t bytes = 0;
   bytes += pad256((size_t)B * d->D * 4);           // style mean
-  bytes += pad256((size_t)B * 2 * d->D * 4) * 2;   // style hidden, gamma|beta
+  bytes += pad256((size_t)B * 2 * d->D * 4) * (1 + MOCHA_MAX_DEPTH);   // style hidden, gamma|beta of every layer
   bytes += pad256(R * d->D * 4) * 5;               // sty_in, x1, qin, x2, xb
   bytes += pad256(R * inner * 4) * 4;              // q, k, v, att
   bytes += pad256((size_t)B * d->heads * n * n * 4);

@@ -174,7 +174,7 @@ int decoder_bf16(const mocha_generator_weights* w, const float* src, const float
   float* smean = ws.take<float>((size_t)B * d.D);
   bf16* smean16 = ws.take<bf16>((size_t)B * d.D);
   bf16* shid = ws.take<bf16>((size_t)B * 2 * d.D);
-  float* gb = ws.take<float>((size_t)B * 2 * d.D);
+  float* gb_all = ws.take<float>((size_t)d.dec_depth * B * 2 * d.D);
   // the three projection inputs and outputs are stacked so that q / k / v run as ONE grouped GEMM launch
   bf16* in3 = ws.take<bf16>((size_t)3 * R * d.D);          // [IN(x1) | IN(style) | style]
   bf16* qin = in3;
@@ -193,16 +193,35 @@ int decoder_bf16(const mocha_generator_weights* w, const float* src, const float
   bf16* hid = ws.take<bf16>((size_t)R * d.mlp);
   WS_OK(ws, "mocha_decoder_fwd(bf16)");
   // layer-independent functions of the style tokens
-  MOCHA_TRY(token_mean(cha, B, n, d.D, smean, s));
-  MOCHA_TRY(tc_cast(smean, smean16, (long long)B * d.D, 0, s));
+  // AdaIN parameters of every layer depend on the style only: one launch for the token mean and all MLPs
+  static const bool no_style_mlp = getenv("MOCHA_NO_STYLE_MLP") != nullptr;
+  bool fused_style = !no_style_mlp && style_mlp_supported(d.D, d.dec_depth);
+  if (fused_style) {
+    const bf16 *w1[MOCHA_MAX_DEPTH], *w2[MOCHA_MAX_DEPTH];
+    const float *b1[MOCHA_MAX_DEPTH], *b2[MOCHA_MAX_DEPTH];
+    for (int l = 0; l < d.dec_depth && fused_style; ++l) {
+      MOCHA_CHECK_ARG(w->dec[l].sw1 && w->dec[l].sw2, "mocha_decoder_fwd: layer %d weights missing", l);
+      w1[l] = tc_lookup_bf16(w->dec[l].sw1); w2[l] = tc_lookup_bf16(w->dec[l].sw2);
+      b1[l] = w->dec[l].sb1; b2[l] = w->dec[l].sb2;
+      fused_style = w1[l] && w2[l];
+    }
+    if (fused_style) MOCHA_TRY(style_mlp(cha, B, n, d.D, d.dec_depth, w1, b1, w2, b2, gb_all, s));
+  }
+  if (!fused_style) {
+    MOCHA_TRY(token_mean(cha, B, n, d.D, smean, s));
+    MOCHA_TRY(tc_cast(smean, smean16, (long long)B * d.D, 0, s));
+  }
   MOCHA_TRY(instance_norm_tokens(cha, B, n, d.D, eps, nullptr, nullptr, nullptr, nullptr, nullptr, s, sty_in));
   MOCHA_TRY(tc_cast(cha, cha16, (long long)R * d.D, 0, s));
   const float* x = src;
   for (int l = 0; l < d.dec_depth; ++l) {
     const mocha_dec_layer& L = w->dec[l];
     MOCHA_CHECK_ARG(L.sw1 && L.sw2 && L.wq && L.wk && L.wv && L.wo && L.w1 && L.w2, "mocha_decoder_fwd: layer %d weights missing", l);
-    MOCHA_TRY(tc.lin(smean16, d.D, L.sw1, L.sb1, 0, nullptr, h16(shid), B, 2 * d.D, d.D, ACT_LRELU));
-    MOCHA_TRY(tc.lin(shid, 2 * d.D, L.sw2, L.sb2, 0, nullptr, f32(gb), B, 2 * d.D, 2 * d.D, ACT_NONE));
+    float* gb = gb_all + (size_t)l * B * 2 * d.D;
+    if (!fused_style) {
+      MOCHA_TRY(tc.lin(smean16, d.D, L.sw1, L.sb1, 0, nullptr, h16(shid), B, 2 * d.D, d.D, ACT_LRELU));
+      MOCHA_TRY(tc.lin(shid, 2 * d.D, L.sw2, L.sb2, 0, nullptr, f32(gb), B, 2 * d.D, 2 * d.D, ACT_NONE));
+    }
     if (n <= 128 && d.D % 64 == 0) {
       // x1 = AdaIN(x) and qin = IN(x1) from one pass (closed form for the second normalisation)
       MOCHA_TRY(adain_norm_tokens(x, B, n, d.D, eps, gb, x1, qin, s));

@@ -172,6 +172,169 @@ embed_graph_agg_kernel(const float* __restrict__ X, const float* __restrict__ We
   }
 }
 
+// ---- tensor-core variant (mma.sync m16n8k8, TF32 operands, fp32 accumulation) ----------------------------------------
+// The sparse walk above is issue-bound (~30 K warp instructions per 96-row block, 0.2 of the HBM roof). Both steps are
+// tiny dense products per frame: h0[V, C] = X[V, Cin] Wemb^T and out[(k, w), c] = sum_u A[k][u][w] h0[u, c], i.e.
+// [Kk*V x V] x [V x C]. With the adjacency (transposed, zero rows up to a multiple of 16) and the 1x1 weights held as
+// constant mma fragments in registers, a frame costs 8 + 15 mma per warp instead of ~900 FFMA / LDS instructions, and
+// the kernel becomes what it should be: a stream of 512-byte output rows. Warp w owns channels 8w..8w+7 in both
+// products; h0 goes through shared memory once (fp32, rounded to TF32, row stride 72 = conflict-free B fragments);
+// finished rows are staged as bf16 (row stride ldo + 8) and leave with one 1-D bulk copy (cp.async.bulk) per row, so
+// no thread waits for a store. Persistent over groups of G frames; the next group's inputs are in flight in registers
+// while the current group is aggregated. TF32 rounding (2^-11) sits below the bf16 rounding of the output (2^-9).
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+constexpr int EMB_XLD = 20;   // floats per staged input row: A-fragment loads (rows g, cols t / t+4) hit 32 distinct banks
+constexpr int EMB_HLD = 72;   // floats per h0 row (C = 64): B-fragment loads (rows t, cols g) hit 32 distinct banks
+
+template <int V, int KK, int G>
+__global__ void __launch_bounds__(256, 2)
+embed_graph_agg_mma_kernel(const float* __restrict__ X, const float* __restrict__ Wemb, const float* __restrict__ bemb,
+                           const float* __restrict__ A, __nv_bfloat16* __restrict__ out16, int BT, int Cin, int ldo) {
+  constexpr int C = 64, KC = KK * C, M = KK * V, MT = (M + 15) / 16, KS = V / 8, ROWS = G * V, XT = (ROWS + 15) / 16;
+  constexpr int NLD = (ROWS * EMB_MAXCIN + 255) / 256;
+  static_assert(V % 8 == 0 && ROWS <= 256 && ROWS % 8 == 0, "geometry");
+  pdl_trigger();
+  extern __shared__ __align__(16) unsigned char smraw[];
+  float* xin = reinterpret_cast<float*>(smraw);                      // [XT*16][EMB_XLD]
+  float* hs = xin + XT * 16 * EMB_XLD;                               // [ROWS][EMB_HLD]
+  __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(hs + ROWS * EMB_HLD);   // [ROWS][ldo + 8]
+  const int sld = ldo + 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int c0 = warp * 8;
+
+  // ---- constants (weights: may be read before the grid dependency resolves) ----
+  uint32_t wb[2][2];                      // 1x1 conv, B fragments: B[k = cin][n = c] = Wemb[c][cin]
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    const int k0 = ks * 8 + t, k1 = k0 + 4;
+    wb[ks][0] = f2tf32(k0 < Cin ? __ldg(Wemb + (c0 + g) * Cin + k0) : 0.f);
+    wb[ks][1] = f2tf32(k1 < Cin ? __ldg(Wemb + (c0 + g) * Cin + k1) : 0.f);
+  }
+  const float bias0 = bemb ? __ldg(bemb + c0 + 2 * t) : 0.f, bias1 = bemb ? __ldg(bemb + c0 + 2 * t + 1) : 0.f;
+  uint32_t adj[MT][KS][4];                // aggregation, A fragments: At[(k, w)][u] = A[k][u][w]
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = mt * 16 + g + (j & 1) * 8, u = ks * 8 + t + (j >> 1) * 4;
+        const int k = r / V, w = r - k * V;
+        adj[mt][ks][j] = f2tf32(r < M ? __ldg(A + (k * V + u) * V + w) : 0.f);
+      }
+  // staging offsets of this thread's output rows (row r = (k, w) -> staged row w, columns k*C + c0 + 2t)
+  // (M is a multiple of 8, so whether a half tile of 8 rows exists is known at compile time)
+  static_assert(M % 8 == 0, "half tiles are all-valid or all-padding");
+  int soff[MT][2];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = mt * 16 + g + h * 8, k = r / V, w = r - k * V;
+      soff[mt][h] = w * sld + k * C + c0 + 2 * t;
+    }
+  // zero the padded input columns / rows once; row tails (adjacency column sums = bias columns of the GEMM, then zeros)
+  for (int i = threadIdx.x; i < XT * 16 * EMB_XLD; i += 256) xin[i] = 0.f;
+  for (int i = threadIdx.x; i < ROWS * (ldo - KC); i += 256) {
+    const int r = i / (ldo - KC), j = i - r * (ldo - KC), w = r % V;
+    float sum = 0.f;
+    if (j < KK)
+      for (int u = 0; u < V; ++u) sum += __ldg(A + (j * V + u) * V + w);
+    stg[r * sld + KC + j] = __float2bfloat16_rn(sum);
+  }
+  pdl_wait();
+
+  const int ngroups = (BT + G - 1) / G;
+  float xv[NLD];
+  int xoff[NLD];   // shared-memory slot of this thread's j-th input element (row r, column k -> r * EMB_XLD + k); -1 = none
+#pragma unroll
+  for (int j = 0; j < NLD; ++j) {
+    const int i = threadIdx.x + 256 * j, r = i / Cin;
+    xoff[j] = i < ROWS * Cin ? r * EMB_XLD + (i - r * Cin) : -1;
+  }
+  auto load_x = [&](int grp) {
+    const long long base = (long long)grp * ROWS * Cin;
+    const int n = min(G, BT - grp * G) * V * Cin;
+#pragma unroll
+    for (int j = 0; j < NLD; ++j) {
+      const int i = threadIdx.x + 256 * j;
+      xv[j] = i < n ? __ldg(X + base + i) : 0.f;
+    }
+  };
+  if ((int)blockIdx.x < ngroups) load_x(blockIdx.x);
+  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const int rows = min(G, BT - grp * G) * V;
+    __syncthreads();                                  // previous group's fragment reads of xin / hs are done
+#pragma unroll
+    for (int j = 0; j < NLD; ++j)
+      if (xoff[j] >= 0) xin[xoff[j]] = xv[j];
+    __syncthreads();
+    if (grp + (int)gridDim.x < ngroups) load_x(grp + gridDim.x);   // in flight during both products
+    // ---- h0 = lrelu(x Wemb^T + b) for this warp's 8 channels, all rows ----
+#pragma unroll
+    for (int mt = 0; mt < XT; ++mt) {
+      float d[4] = {bias0, bias1, bias0, bias1};
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const float* xr = xin + (mt * 16 + g) * EMB_XLD + ks * 8 + t;
+        // raw fp32 bits: the MMA reads the top 19 bits (truncation, 2^-10 relative: below the bf16 rounding of the output)
+        uint32_t a[4] = {__float_as_uint(xr[0]), __float_as_uint(xr[8 * EMB_XLD]), __float_as_uint(xr[4]),
+                         __float_as_uint(xr[8 * EMB_XLD + 4])};
+        mma_tf32(d, a, wb[ks][0], wb[ks][1]);
+      }
+      const int r0 = mt * 16 + g;
+      if (mt * 16 < ROWS)
+        *reinterpret_cast<float2*>(hs + r0 * EMB_HLD + c0 + 2 * t) =
+            make_float2(__uint_as_float(f2tf32(lrelu02(d[0]))), __uint_as_float(f2tf32(lrelu02(d[1]))));
+      if (mt * 16 + 8 < ROWS)
+        *reinterpret_cast<float2*>(hs + (r0 + 8) * EMB_HLD + c0 + 2 * t) =
+            make_float2(__uint_as_float(f2tf32(lrelu02(d[2]))), __uint_as_float(f2tf32(lrelu02(d[3]))));
+    }
+    // the previous group's bulk stores must have finished reading the staging rows before they are overwritten
+    if (threadIdx.x < ROWS) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncthreads();
+    // ---- aggregation: out[(k, w), c] = sum_u At[(k, w), u] h0[u, c] per frame ----
+#pragma unroll 1
+    for (int f = 0; f < G; ++f) {
+      uint32_t hb[KS][2];
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const float* hr = hs + (f * V + ks * 8 + t) * EMB_HLD + c0 + g;
+        hb[ks][0] = __float_as_uint(hr[0]);
+        hb[ks][1] = __float_as_uint(hr[4 * EMB_HLD]);
+      }
+      __nv_bfloat16* sf = stg + f * V * sld;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) mma_tf32(d, adj[mt][ks], hb[ks][0], hb[ks][1]);
+        if (mt * 16 < M) *reinterpret_cast<__nv_bfloat162*>(sf + soff[mt][0]) = __floats2bfloat162_rn(d[0], d[1]);
+        if (mt * 16 + 8 < M) *reinterpret_cast<__nv_bfloat162*>(sf + soff[mt][1]) = __floats2bfloat162_rn(d[2], d[3]);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if ((int)threadIdx.x < rows) {
+      const uint32_t src = (uint32_t)__cvta_generic_to_shared(stg + threadIdx.x * sld);
+      __nv_bfloat16* dst = out16 + ((long long)grp * ROWS + threadIdx.x) * ldo;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"((uint32_t)ldo * 2u)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (threadIdx.x < ROWS) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 __global__ void graph_agg_kv_kernel(const float* __restrict__ in, const float* __restrict__ A2,
                                     float* __restrict__ out, int U, int Wn, int C, int Kk) {
   pdl_trigger();
@@ -570,6 +733,122 @@ __global__ void token_mean_kernel(const float* __restrict__ x, int n, int C, flo
   }
 }
 
+// AdaIN parameter MLP of every decoder layer in one launch (transformer.py:98-103 with the style token mean):
+//   smean = mean over tokens of the style; per layer gb = W2 lrelu(W1 smean + b1) + b2   ([2D] = gamma | beta)
+// Four 128-row GEMM launches + a token mean + a cast were ~54 us of pure launch / pipeline latency per step for
+// 0.1 GFLOP. One block per clip: the mean with one column per thread, then a warp per output feature with the lanes
+// across K (one coalesced 512-byte weight row segment per LDG.128, bf16 weights from the registered mirror, fp32
+// activations), eight outputs reduced at a time with a transposing butterfly (9 shuffles per 8 outputs).
+struct StyleMlpLayers {
+  const __nv_bfloat16* w1[MOCHA_MAX_DEPTH];
+  const float* b1[MOCHA_MAX_DEPTH];
+  const __nv_bfloat16* w2[MOCHA_MAX_DEPTH];
+  const float* b2[MOCHA_MAX_DEPTH];
+};
+
+// sums of NV (8 or 4) per-lane values across the warp with a transposing butterfly: lane L with L % 4 == 0 ends up with the
+// total of value index 4*bit4(L) + 2*bit3(L) + bit2(L) (NV = 8) or 2*bit4(L) + bit3(L) (NV = 4, lanes with L % 8 == 0)
+template <int NV>
+__device__ __forceinline__ float warp_reduce_t(float (&v)[NV], int lane) {
+  static_assert(NV == 8 || NV == 4, "NV");
+  int bit = 16;
+#pragma unroll
+  for (int h = NV / 2; h >= 1; h /= 2) {
+    const bool up = lane & bit;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float send = up ? v[i] : v[i + h], keep = up ? v[i + h] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+    bit >>= 1;
+  }
+#pragma unroll
+  for (; bit >= 1; bit >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], bit);
+  return v[0];
+}
+
+// y[o] = act(W[o, :] . x + b[o]) for o in [0, N): W bf16 [N, K] row-major, x fp32 in shared memory, K = KCH * 256. A warp
+// owns NV outputs per pass with its lanes across K: one coalesced 16-byte load per lane, row and 256-column chunk, all
+// NV * KCH of them in flight before the first is used.
+template <int KCH, int NV>
+__device__ __forceinline__ void warp_matvec(const __nv_bfloat16* __restrict__ W, const float* __restrict__ b, const float* xs,
+                                            float* ys, float* yg, int N, int lrelu, int warp, int nwarps, int lane) {
+  constexpr int K = KCH * 256;
+  float x[KCH * 8];
+#pragma unroll
+  for (int c = 0; c < KCH; ++c) {
+    const float4 lo = *reinterpret_cast<const float4*>(xs + c * 256 + lane * 8);
+    const float4 hi = *reinterpret_cast<const float4*>(xs + c * 256 + lane * 8 + 4);
+    x[c * 8 + 0] = lo.x; x[c * 8 + 1] = lo.y; x[c * 8 + 2] = lo.z; x[c * 8 + 3] = lo.w;
+    x[c * 8 + 4] = hi.x; x[c * 8 + 5] = hi.y; x[c * 8 + 6] = hi.z; x[c * 8 + 7] = hi.w;
+  }
+  for (int o0 = warp * NV; o0 < N; o0 += nwarps * NV) {
+    uint4 wv[NV * KCH];
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int c = 0; c < KCH; ++c)
+        wv[i * KCH + c] = __ldg(reinterpret_cast<const uint4*>(W + (size_t)(o0 + i) * K + c * 256 + lane * 8));
+    float v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < KCH; ++c) {
+        const uint32_t u[4] = {wv[i * KCH + c].x, wv[i * KCH + c].y, wv[i * KCH + c].z, wv[i * KCH + c].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {   // bf16 -> fp32 is a shift / mask of the packed pair
+          acc = fmaf(__uint_as_float(u[j] << 16), x[c * 8 + 2 * j], acc);
+          acc = fmaf(__uint_as_float(u[j] & 0xffff0000u), x[c * 8 + 2 * j + 1], acc);
+        }
+      }
+      v[i] = acc;
+    }
+    const float tot = warp_reduce_t<NV>(v, lane);
+    constexpr int STEP = 32 / NV;   // lanes per reduced value
+    if ((lane & (STEP - 1)) == 0) {
+      const int o = o0 + (NV == 8 ? ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)
+                                  : ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1));
+      float r = tot + (b ? __ldg(b + o) : 0.f);
+      if (lrelu) r = lrelu02(r);
+      if (ys) ys[o] = r;
+      if (yg) yg[o] = r;
+    }
+  }
+}
+
+constexpr int STYLE_THREADS = 1024;
+__global__ void __launch_bounds__(STYLE_THREADS, 1)
+style_mlp_kernel(const float* __restrict__ cha, int n, const StyleMlpLayers L, int nlayers, float* __restrict__ gb, int B) {
+  constexpr int D = 256, NW = STYLE_THREADS / 32;
+  pdl_trigger();
+  pdl_wait();
+  __shared__ __align__(16) float part[4][D];
+  __shared__ __align__(16) float smean[D];
+  __shared__ __align__(16) float hid[2 * D];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  {
+    // token mean: four threads per column, each over a quarter of the tokens
+    const int c = threadIdx.x & (D - 1), q = threadIdx.x >> 8;
+    const float* xb = cha + (long long)b * n * D + c;
+    float s0 = 0.f, s1 = 0.f;
+    int i = q;
+    for (; i + 4 < n; i += 8) { s0 += xb[(long long)i * D]; s1 += xb[(long long)(i + 4) * D]; }
+    for (; i < n; i += 4) s0 += xb[(long long)i * D];
+    part[q][c] = s0 + s1;
+  }
+  __syncthreads();
+  if (threadIdx.x < D)
+    smean[threadIdx.x] = ((part[0][threadIdx.x] + part[1][threadIdx.x]) + (part[2][threadIdx.x] + part[3][threadIdx.x])) / (float)n;
+  __syncthreads();
+  for (int l = 0; l < nlayers; ++l) {
+    warp_matvec<1, 8>(L.w1[l], L.b1[l], smean, hid, nullptr, 2 * D, 1, warp, NW, lane);
+    __syncthreads();
+    warp_matvec<2, 4>(L.w2[l], L.b2[l], hid, nullptr, gb + ((long long)l * B + b) * 2 * D, 2 * D, 0, warp, NW, lane);
+    __syncthreads();
+  }
+}
+
 constexpr int SM_MAXPL = 8;  // up to 256 columns per row
 __global__ void softmax_rows_kernel(float* __restrict__ S, long long rows, int ncols, float scale) {
   pdl_trigger();
@@ -917,6 +1196,25 @@ int embed_graph_agg(const float* X, const float* Wemb, const float* bemb, const 
   MOCHA_CHECK_ARG(Cin <= EMB_MAXCIN, "embed_graph_agg: Cin=%d > %d unsupported", Cin, EMB_MAXCIN);
   MOCHA_CHECK_ARG(V % 4 == 0 && V <= 32, "embed_graph_agg: V=%d must be a multiple of 4, at most 32", V);
   constexpr int G = 4;
+  static const bool no_mma = getenv("MOCHA_NO_MMA_EMBED") != nullptr;   // A/B switch: the sparse SIMT kernel below
+  if (!no_mma && V == 24 && Kk == 3 && C == 64 && ldo % 8 == 0 && ldo <= 512 &&
+      ((reinterpret_cast<uintptr_t>(out16) | reinterpret_cast<uintptr_t>(X)) & 15) == 0) {
+    constexpr int XT = (G * 24 + 15) / 16;
+    const size_t smem_mma = (size_t)(XT * 16 * EMB_XLD + G * 24 * EMB_HLD) * sizeof(float) + (size_t)G * 24 * (ldo + 8) * 2;
+    static size_t configured_mma = 0;
+    if (smem_mma > configured_mma) {
+      MOCHA_CUDA(cudaFuncSetAttribute(embed_graph_agg_mma_kernel<24, 3, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma));
+      configured_mma = smem_mma;
+    }
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    const int ngroups = (BT + G - 1) / G;
+    const int grid = ngroups < 2 * sms ? ngroups : 2 * sms;
+    launch_k(embed_graph_agg_mma_kernel<24, 3, G>, grid, 256, smem_mma, s, X, Wemb, bemb, A, out16, BT, Cin, ldo);
+    count_launch();
+    MOCHA_LAUNCH_CHECK("embed_graph_agg_mma");
+    return MOCHA_OK;
+  }
   const size_t smem = (size_t)(G * V * C + G * V * EMB_MAXCIN + 2 * Kk * V * V + Kk * V) * sizeof(float) +
                       (size_t)V * (ldo - Kk * C) * 2 + 16;
   static size_t configured = 0;
@@ -1110,6 +1408,22 @@ int token_mean(const float* x, int B, int n, int C, float* out, cudaStream_t s) 
   launch_k(token_mean_kernel, B, 256, 0, s, x, n, C, out);
   count_launch();
   MOCHA_LAUNCH_CHECK("token_mean");
+  return MOCHA_OK;
+}
+
+bool style_mlp_supported(int D, int nlayers) { return D == 256 && nlayers >= 1 && nlayers <= MOCHA_MAX_DEPTH; }
+
+int style_mlp(const float* cha, int B, int n, int D, int nlayers, const __nv_bfloat16* const* w1, const float* const* b1,
+              const __nv_bfloat16* const* w2, const float* const* b2, float* gb, cudaStream_t s) {
+  MOCHA_CHECK_ARG(cha && gb && B > 0 && n > 0 && style_mlp_supported(D, nlayers), "style_mlp: bad args");
+  StyleMlpLayers L{};
+  for (int l = 0; l < nlayers; ++l) {
+    MOCHA_CHECK_ARG(w1[l] && w2[l] && aligned16(w1[l]) && aligned16(w2[l]), "style_mlp: layer %d weights missing / unaligned", l);
+    L.w1[l] = w1[l]; L.b1[l] = b1[l]; L.w2[l] = w2[l]; L.b2[l] = b2[l];
+  }
+  launch_k(style_mlp_kernel, B, STYLE_THREADS, 0, s, cha, n, L, nlayers, gb, B);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("style_mlp");
   return MOCHA_OK;
 }
 

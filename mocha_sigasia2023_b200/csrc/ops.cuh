@@ -59,6 +59,11 @@ int adain_norm_tokens(const float* x, int B, int n, int C, float eps, const floa
 
 // mean over tokens: out[b,c] = mean_n x[b,n,c]  (AdaptiveAvgPool1d(1), transformer.py:102)
 int token_mean(const float* x, int B, int n, int C, float* out, cudaStream_t s);
+// AdaIN parameter MLPs of all decoder layers in one launch: gb [nlayers, B, 2D] = W2 lrelu(W1 mean_tokens(cha) + b1) + b2
+// (bf16 weights, fp32 activations)
+bool style_mlp_supported(int D, int nlayers);
+int style_mlp(const float* cha, int B, int n, int D, int nlayers, const __nv_bfloat16* const* w1, const float* const* b1,
+              const __nv_bfloat16* const* w2, const float* const* b2, float* gb, cudaStream_t s);
 
 // in-place softmax over the last dim of S[rows, ncols] after multiplying by scale
 int softmax_rows(float* S, long long rows, int ncols, float scale, cudaStream_t s);
