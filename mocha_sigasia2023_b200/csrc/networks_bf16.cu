@@ -321,8 +321,20 @@ int cvae_bf16(const mocha_cvae_weights* w, const float* cond, int B, int ncond, 
       const int R2 = 2 * B;
       float* xq = y;          // [2B, D] gathered rows of x (residual)
       bf16* xq16 = y16;
-      MOCHA_TRY(gather_token_rows(x, x16, np, 2, D, B, xq, xq16, s));
       bf16* kv = qkv;         // [Rp, 2D]
+      static const bool no_rows_kernel = getenv("MOCHA_NO_PRIOR_LAST_KERNEL") != nullptr;
+      const bf16 *wq16 = tc_lookup_bf16(L.in_w), *wo16 = tc_lookup_bf16(L.out_w), *w116 = tc_lookup_bf16(L.l1_w),
+                 *w216 = tc_lookup_bf16(L.l2_w);
+      if (!no_rows_kernel && cvae_prior_last_supported(D, H, w->dff, np) && wq16 && wo16 && w116 && w216 && L.n1_b && L.n2_b) {
+        // everything after the K / V projection acts on 2 rows per clip: one SIMT launch (ops.cu)
+        MOCHA_TRY(tc.lin(x16, D, L.in_w + (size_t)D * D, L.in_b + D, 0, nullptr, h16(kv), Rp, 2 * D, D, ACT_NONE));
+        MOCHA_TRY(cvae_prior_last(x, B, np, kv, wq16, L.in_b, wo16, L.out_b, L.n1_g, L.n1_b, w116, L.l1_b, w216, L.l2_b, L.n2_g,
+                                  L.n2_b, H, w->dff, w->ln_eps, xq, s));
+        x = xq;
+        prior_rows = 2;
+        break;
+      }
+      MOCHA_TRY(gather_token_rows(x, x16, np, 2, D, B, xq, xq16, s));
       bf16* q2 = att;         // [2B, D]
       bf16* att2 = hid;       // [2B, D]
       MOCHA_TRY(tc.lin(x16, D, L.in_w + (size_t)D * D, L.in_b + D, 0, nullptr, h16(kv), Rp, 2 * D, D, ACT_NONE));

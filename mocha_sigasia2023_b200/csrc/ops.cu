@@ -849,6 +849,199 @@ style_mlp_kernel(const float* __restrict__ cha, int n, const StyleMlpLayers L, i
   }
 }
 
+// ---- last CVAE prior layer on its two read rows, one launch ---------------------------------------------------------
+// Only the mu / logvar token rows (tokens 0 and 1) of the last prior layer are read (model_CVAE.py:78). Keys / values
+// still come from every token (one tensor-core GEMM), but everything that follows acts on 2 rows per clip: as tcgen05
+// launches (gather, 256-row q projection, attention with 2 valid query rows per 128-row tile, a 2-CTA block tail) that
+// was four launches and ~56 us of pure pipeline latency. Here one block per clip does all of it with the lanes of a warp
+// across K (bf16 weights / keys / values, fp32 activations and statistics):
+//   q = Wq x + bq;  p = softmax(q k^T / sqrt(dh)) per head;  a = p v;  y = LN1(x + Wo a + bo);  out = LN2(y + W2 relu(W1 y + b1) + b2)
+// (nn.TransformerEncoderLayer, post-LN, ReLU: model_CVAE.py:60-79).
+struct PriorLastW {
+  const __nv_bfloat16 *wq, *wo, *w1, *w2;
+  const float *bq, *bo, *b1, *b2, *g1, *be1, *g2, *be2;
+};
+
+// two-vector version of warp_matvec: ys[v * ldy + o] = act(W[o, :] . xs[v * ldx ...] + b[o]) (* scale) (+ res[v * ldy + o])
+template <int KCH, int NV>
+__device__ __forceinline__ void warp_matvec2(const __nv_bfloat16* __restrict__ W, const float* __restrict__ b, const float* xs,
+                                             int ldx, float* ys, int ldy, const float* res, int N, int relu, float scale,
+                                             int warp, int nwarps, int lane) {
+  constexpr int K = KCH * 256;
+  float x[2][KCH * 8];
+#pragma unroll
+  for (int v = 0; v < 2; ++v)
+#pragma unroll
+    for (int c = 0; c < KCH; ++c) {
+      const float4 lo = *reinterpret_cast<const float4*>(xs + v * ldx + c * 256 + lane * 8);
+      const float4 hi = *reinterpret_cast<const float4*>(xs + v * ldx + c * 256 + lane * 8 + 4);
+      x[v][c * 8 + 0] = lo.x; x[v][c * 8 + 1] = lo.y; x[v][c * 8 + 2] = lo.z; x[v][c * 8 + 3] = lo.w;
+      x[v][c * 8 + 4] = hi.x; x[v][c * 8 + 5] = hi.y; x[v][c * 8 + 6] = hi.z; x[v][c * 8 + 7] = hi.w;
+    }
+  for (int o0 = warp * NV; o0 < N; o0 += nwarps * NV) {
+    uint4 wv[NV * KCH];
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int c = 0; c < KCH; ++c)
+        wv[i * KCH + c] = __ldg(reinterpret_cast<const uint4*>(W + (size_t)(o0 + i) * K + c * 256 + lane * 8));
+    float v0[NV], v1[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < KCH; ++c) {
+        const uint32_t u[4] = {wv[i * KCH + c].x, wv[i * KCH + c].y, wv[i * KCH + c].z, wv[i * KCH + c].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float wl = __uint_as_float(u[j] << 16), wh = __uint_as_float(u[j] & 0xffff0000u);
+          a0 = fmaf(wl, x[0][c * 8 + 2 * j], a0); a0 = fmaf(wh, x[0][c * 8 + 2 * j + 1], a0);
+          a1 = fmaf(wl, x[1][c * 8 + 2 * j], a1); a1 = fmaf(wh, x[1][c * 8 + 2 * j + 1], a1);
+        }
+      }
+      v0[i] = a0; v1[i] = a1;
+    }
+    const float t0 = warp_reduce_t<NV>(v0, lane), t1 = warp_reduce_t<NV>(v1, lane);
+    constexpr int STEP = 32 / NV;
+    if ((lane & (STEP - 1)) == 0) {
+      const int o = o0 + (NV == 8 ? ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)
+                                  : ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1));
+      const float bo = b ? __ldg(b + o) : 0.f;
+      float r0 = (t0 + bo) * scale, r1 = (t1 + bo) * scale;
+      if (relu) { r0 = fmaxf(r0, 0.f); r1 = fmaxf(r1, 0.f); }
+      if (res) { r0 += res[o]; r1 += res[ldy + o]; }
+      ys[o] = r0; ys[ldy + o] = r1;
+    }
+  }
+}
+
+// LayerNorm of two 256-wide rows held in shared memory (warps 0 and 1), two-pass statistics; out may be shared or global
+__device__ __forceinline__ void ln2_rows256(const float* in, int ldi, const float* __restrict__ g, const float* __restrict__ be,
+                                            float eps, float* out, int ldo_, int warp, int lane) {
+  if (warp < 2) {
+    const float* r = in + warp * ldi;
+    float v[8];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v[j] = r[lane + 32 * j]; s += v[j]; }
+    const float mean = warp_sum(s) * (1.f / 256.f);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float d = v[j] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / 256.f) + eps);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = lane + 32 * j;
+      out[warp * ldo_ + c] = (v[j] - mean) * rstd * __ldg(g + c) + __ldg(be + c);
+    }
+  }
+}
+
+constexpr int PL_THREADS = 512;
+constexpr int PL_MAXKEYS = 256;
+template <int KCH2>   // dff / 256
+__global__ void __launch_bounds__(PL_THREADS, 1)
+cvae_prior_last_kernel(const float* __restrict__ x, int np, const __nv_bfloat16* __restrict__ kv, const PriorLastW W, int H,
+                       float eps, float* __restrict__ out) {
+  constexpr int D = 256, NW = PL_THREADS / 32, DFF = KCH2 * 256;
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) float psm[];
+  float* xs = psm;                       // [2][D] the two query rows (residual)
+  float* qs = xs + 2 * D;                // [2][D] q * 1/sqrt(dh); later the attention output
+  float* y1 = qs + 2 * D;                // [2][D]
+  float* t1 = y1 + 2 * D;                // [2][D] pre-LayerNorm rows
+  float* hid = t1 + 2 * D;               // [2][DFF]
+  float* part = hid + 2 * DFF;           // [4][2][D] partial P V sums
+  float* sc = part + 8 * D;              // [2][H][PL_MAXKEYS] scores / probabilities
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int dh = D / H, lph = dh / 8;    // lanes per head when a lane owns 8 consecutive columns
+  for (int i = threadIdx.x; i < 2 * D; i += PL_THREADS) xs[i] = x[(long long)b * np * D + i];   // tokens 0 and 1 are adjacent
+  __syncthreads();
+  warp_matvec2<1, 8>(W.wq, W.bq, xs, D, qs, D, nullptr, D, 0, rsqrtf((float)dh), warp, NW, lane);
+  __syncthreads();
+  {
+    // scores: a warp per key, lane = 8 consecutive columns of the key row (one 512-byte coalesced load)
+    float q0[8], q1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { q0[j] = qs[lane * 8 + j]; q1[j] = qs[D + lane * 8 + j]; }
+    const __nv_bfloat16* kb = kv + (long long)b * np * 2 * D;
+    for (int j0 = warp; j0 < np; j0 += 2 * NW) {
+      const int j1 = j0 + NW;
+      const uint4 k0 = __ldg(reinterpret_cast<const uint4*>(kb + (long long)j0 * 2 * D + lane * 8));
+      uint4 k1 = make_uint4(0, 0, 0, 0);
+      if (j1 < np) k1 = __ldg(reinterpret_cast<const uint4*>(kb + (long long)j1 * 2 * D + lane * 8));
+      const uint32_t u0[4] = {k0.x, k0.y, k0.z, k0.w}, u1[4] = {k1.x, k1.y, k1.z, k1.w};
+      float s00 = 0.f, s01 = 0.f, s10 = 0.f, s11 = 0.f;   // s[key][row]
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = __uint_as_float(u0[e] << 16), c = __uint_as_float(u0[e] & 0xffff0000u);
+        const float a1 = __uint_as_float(u1[e] << 16), c1 = __uint_as_float(u1[e] & 0xffff0000u);
+        s00 = fmaf(a, q0[2 * e], s00); s00 = fmaf(c, q0[2 * e + 1], s00);
+        s01 = fmaf(a, q1[2 * e], s01); s01 = fmaf(c, q1[2 * e + 1], s01);
+        s10 = fmaf(a1, q0[2 * e], s10); s10 = fmaf(c1, q0[2 * e + 1], s10);
+        s11 = fmaf(a1, q1[2 * e], s11); s11 = fmaf(c1, q1[2 * e + 1], s11);
+      }
+      for (int o = 1; o < lph; o <<= 1) {
+        s00 += __shfl_xor_sync(0xffffffffu, s00, o); s01 += __shfl_xor_sync(0xffffffffu, s01, o);
+        s10 += __shfl_xor_sync(0xffffffffu, s10, o); s11 += __shfl_xor_sync(0xffffffffu, s11, o);
+      }
+      if ((lane & (lph - 1)) == 0) {
+        const int h = lane / lph;
+        sc[(0 * H + h) * PL_MAXKEYS + j0] = s00; sc[(1 * H + h) * PL_MAXKEYS + j0] = s01;
+        if (j1 < np) { sc[(0 * H + h) * PL_MAXKEYS + j1] = s10; sc[(1 * H + h) * PL_MAXKEYS + j1] = s11; }
+      }
+    }
+  }
+  __syncthreads();
+  for (int r = warp; r < 2 * H; r += NW) {   // softmax of one (row, head) list per warp
+    float* row = sc + r * PL_MAXKEYS;
+    float v[PL_MAXKEYS / 32];
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < PL_MAXKEYS / 32; ++j) { const int i = lane + 32 * j; v[j] = i < np ? row[i] : -INFINITY; m = fmaxf(m, v[j]); }
+    m = warp_max(m);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < PL_MAXKEYS / 32; ++j) { v[j] = __expf(v[j] - m); sum += v[j]; }
+    const float inv = 1.f / warp_sum(sum);
+#pragma unroll
+    for (int j = 0; j < PL_MAXKEYS / 32; ++j) { const int i = lane + 32 * j; if (i < np) row[i] = v[j] * inv; }
+  }
+  __syncthreads();
+  {
+    // a = p v: thread = 2 columns x one of 4 key groups
+    const int c2 = (threadIdx.x & 127) * 2, kg = threadIdx.x >> 7, h = c2 / dh;
+    const __nv_bfloat16* vb = kv + (long long)b * np * 2 * D + D + c2;
+    const float* p0 = sc + (0 * H + h) * PL_MAXKEYS;
+    const float* p1 = sc + (1 * H + h) * PL_MAXKEYS;
+    float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;   // a[row][column]
+#pragma unroll 4
+    for (int j = kg; j < np; j += 4) {
+      const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(vb + (long long)j * 2 * D));
+      const float vl = __uint_as_float(u << 16), vh = __uint_as_float(u & 0xffff0000u);
+      const float w0 = p0[j], w1 = p1[j];
+      a00 = fmaf(w0, vl, a00); a01 = fmaf(w0, vh, a01);
+      a10 = fmaf(w1, vl, a10); a11 = fmaf(w1, vh, a11);
+    }
+    *reinterpret_cast<float2*>(part + (kg * 2 + 0) * D + c2) = make_float2(a00, a01);
+    *reinterpret_cast<float2*>(part + (kg * 2 + 1) * D + c2) = make_float2(a10, a11);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * D; i += PL_THREADS)
+    qs[i] = (part[i] + part[2 * D + i]) + (part[4 * D + i] + part[6 * D + i]);
+  __syncthreads();
+  warp_matvec2<1, 8>(W.wo, W.bo, qs, D, t1, D, xs, D, 0, 1.f, warp, NW, lane);        // x + Wo a + bo
+  __syncthreads();
+  ln2_rows256(t1, D, W.g1, W.be1, eps, y1, D, warp, lane);
+  __syncthreads();
+  warp_matvec2<1, 8>(W.w1, W.b1, y1, D, hid, DFF, nullptr, DFF, 1, 1.f, warp, NW, lane);
+  __syncthreads();
+  warp_matvec2<KCH2, 4>(W.w2, W.b2, hid, DFF, t1, D, y1, D, 0, 1.f, warp, NW, lane);  // y + W2 relu(.) + b2
+  __syncthreads();
+  ln2_rows256(t1, D, W.g2, W.be2, eps, out + (long long)b * 2 * D, D, warp, lane);
+}
+
 constexpr int SM_MAXPL = 8;  // up to 256 columns per row
 __global__ void softmax_rows_kernel(float* __restrict__ S, long long rows, int ncols, float scale) {
   pdl_trigger();
@@ -1424,6 +1617,40 @@ int style_mlp(const float* cha, int B, int n, int D, int nlayers, const __nv_bfl
   launch_k(style_mlp_kernel, B, STYLE_THREADS, 0, s, cha, n, L, nlayers, gb, B);
   count_launch();
   MOCHA_LAUNCH_CHECK("style_mlp");
+  return MOCHA_OK;
+}
+
+bool cvae_prior_last_supported(int D, int H, int dff, int np) {
+  if (D != 256 || H < 1 || D % H != 0 || np < 2 || np > PL_MAXKEYS) return false;
+  const int dh = D / H;
+  if (dh % 8 != 0 || (dh / 8 & (dh / 8 - 1)) != 0) return false;   // a head = a power-of-two group of 8-column lanes
+  return dff == 256 || dff == 512 || dff == 1024;
+}
+
+int cvae_prior_last(const float* x, int B, int np, const __nv_bfloat16* kv, const __nv_bfloat16* wq, const float* bq,
+                    const __nv_bfloat16* wo, const float* bo, const float* g1, const float* be1, const __nv_bfloat16* w1,
+                    const float* b1, const __nv_bfloat16* w2, const float* b2, const float* g2, const float* be2, int H, int dff,
+                    float eps, float* out, cudaStream_t s) {
+  MOCHA_CHECK_ARG(x && kv && wq && wo && w1 && w2 && g1 && be1 && g2 && be2 && out && B > 0, "cvae_prior_last: null argument");
+  MOCHA_CHECK_ARG(cvae_prior_last_supported(256, H, dff, np), "cvae_prior_last: unsupported geometry");
+  MOCHA_CHECK_ARG(aligned16(kv) && aligned16(wq) && aligned16(wo) && aligned16(w1) && aligned16(w2), "cvae_prior_last: unaligned operand");
+  PriorLastW W{wq, wo, w1, w2, bq, bo, b1, b2, g1, be1, g2, be2};
+  const size_t smem = (size_t)(8 * 256 + 2 * dff + 8 * 256 + 2 * H * PL_MAXKEYS) * sizeof(float);
+  MOCHA_CHECK_ARG(smem <= 200 * 1024, "cvae_prior_last: too many heads");
+  auto go = [&](auto kern) -> int {
+    static size_t configured = 0;
+    if (smem > configured && smem > 48 * 1024) {
+      MOCHA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    launch_k(kern, B, PL_THREADS, smem, s, x, np, kv, W, H, eps, out);
+    return MOCHA_OK;
+  };
+  if (dff == 256) MOCHA_TRY(go(cvae_prior_last_kernel<1>));
+  else if (dff == 512) MOCHA_TRY(go(cvae_prior_last_kernel<2>));
+  else MOCHA_TRY(go(cvae_prior_last_kernel<4>));
+  count_launch();
+  MOCHA_LAUNCH_CHECK("cvae_prior_last");
   return MOCHA_OK;
 }
 

@@ -59,6 +59,13 @@ int adain_norm_tokens(const float* x, int B, int n, int C, float eps, const floa
 
 // mean over tokens: out[b,c] = mean_n x[b,n,c]  (AdaptiveAvgPool1d(1), transformer.py:102)
 int token_mean(const float* x, int B, int n, int C, float* out, cudaStream_t s);
+// last CVAE prior layer on its two read rows (tokens 0 / 1 of x [B, np, D]; kv bf16 [B*np, 2D] from the K/V projection):
+// q projection, attention, out-projection + LayerNorm, FFN + LayerNorm in one launch -> out [2B, D] fp32
+bool cvae_prior_last_supported(int D, int H, int dff, int np);
+int cvae_prior_last(const float* x, int B, int np, const __nv_bfloat16* kv, const __nv_bfloat16* wq, const float* bq,
+                    const __nv_bfloat16* wo, const float* bo, const float* g1, const float* be1, const __nv_bfloat16* w1,
+                    const float* b1, const __nv_bfloat16* w2, const float* b2, const float* g2, const float* be2, int H, int dff,
+                    float eps, float* out, cudaStream_t s);
 // AdaIN parameter MLPs of all decoder layers in one launch: gb [nlayers, B, 2D] = W2 lrelu(W1 mean_tokens(cha) + b1) + b2
 // (bf16 weights, fp32 activations)
 bool style_mlp_supported(int D, int nlayers);

@@ -122,6 +122,10 @@ def test_bf16_tensor_core_mode(gold):
     cond, _ = gi.cvae_inputs()
     out = c.sample(cu(cond), deterministic=True).cpu().numpy()
     assert rel_err(out, gold["cvae_det"]) < RTOL_BF16
+    # the last prior layer runs on its two read rows in one SIMT kernel (cvae_prior_last): mu / logvar directly
+    mu, logvar = c.prior(cu(cond))
+    assert rel_err(mu.cpu().numpy(), gold["cvae_mu"]) < RTOL_BF16
+    assert rel_err(logvar.cpu().numpy(), gold["cvae_logvar"]) < RTOL_BF16
 
 
 def test_bf16_mode_at_bench_batch_sizes():
