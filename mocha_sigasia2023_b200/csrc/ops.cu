@@ -52,6 +52,47 @@ __global__ void graph_agg_first_kernel(const float* __restrict__ in, const float
   }
 }
 
+// Small graphs (V <= 8: the 6-node body-part graph of to_mot) with a bf16 output: one thread per (frame, 4 channels) keeps
+// the V source vectors in registers and writes all Kk * V outputs (the adjacency is dense at this size); no per-block list
+// building, loads and stores fully coalesced across channels. The list kernel above needed 19 us for 24 MB at 128 clips.
+constexpr int GAS_VMAX = 8;
+__global__ void __launch_bounds__(256)
+graph_agg_small_kernel(const float* __restrict__ in, const float* __restrict__ A, __nv_bfloat16* __restrict__ out16,
+                       long long total, int V, int C4, int Kk, int lrelu) {
+  pdl_trigger();
+  __shared__ float As[4 * GAS_VMAX * GAS_VMAX];
+  for (int i = threadIdx.x; i < Kk * V * V; i += blockDim.x) As[i] = A[i];   // constant: before the grid dependency
+  pdl_wait();
+  __syncthreads();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long bt = idx / C4;
+  const int c = (int)(idx - bt * C4) * 4, C = C4 * 4, KC = Kk * C;
+  float4 x[GAS_VMAX];
+#pragma unroll
+  for (int u = 0; u < GAS_VMAX; ++u)
+    if (u < V) {
+      float4 v = *reinterpret_cast<const float4*>(in + (bt * V + u) * C + c);
+      if (lrelu) { v.x = lrelu02(v.x); v.y = lrelu02(v.y); v.z = lrelu02(v.z); v.w = lrelu02(v.w); }
+      x[u] = v;
+    }
+  for (int k = 0; k < Kk; ++k)
+    for (int w = 0; w < V; ++w) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < GAS_VMAX; ++u)
+        if (u < V) {
+          const float av = As[(k * V + u) * V + w];
+          a.x = fmaf(x[u].x, av, a.x); a.y = fmaf(x[u].y, av, a.y); a.z = fmaf(x[u].z, av, a.z); a.w = fmaf(x[u].w, av, a.w);
+        }
+      __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(out16 + (bt * V + w) * KC + k * C + c) = pk;
+    }
+}
+
 // Fused front of mot_embedding's JointBlock for the tensor-core path (model.py:42-44, blocks.py:125-129):
 //   h0 = Conv2d 1x1 (Cin -> C0) of the pose window, LeakyReLU(0.2), graph aggregation with the sparse
 //   adjacency -> bf16 operand [BT*V, Kk*C0] of the 1x1 graph convolution GEMM.
@@ -1372,6 +1413,13 @@ int graph_agg_first(const float* in, const float* A, float* out, int BT, int V, 
                     cudaStream_t s, __nv_bfloat16* out16) {
   MOCHA_CHECK_ARG(in && A && (out || out16) && BT > 0 && V > 0 && C > 0 && Kk > 0, "graph_agg_first: bad args");
   MOCHA_CHECK_ARG(C <= 256, "graph_agg_first: C=%d > 256 unsupported", C);
+  if (!out && out16 && V <= GAS_VMAX && Kk <= 4 && (C & 3) == 0 && aligned16(in) && (reinterpret_cast<uintptr_t>(out16) & 7) == 0) {
+    const long long total = (long long)BT * (C / 4);
+    launch_k(graph_agg_small_kernel, blocks_for(total, 256), 256, 0, s, in, A, out16, total, V, C / 4, Kk, lrelu);
+    count_launch();
+    MOCHA_LAUNCH_CHECK("graph_agg_small");
+    return MOCHA_OK;
+  }
   size_t smem = (size_t)(V * C + 2 * Kk * V * V + Kk * V) * sizeof(float);
   MOCHA_CHECK_ARG(smem <= 48 * 1024, "graph_agg_first: tile too large (%zu B)", smem);
   launch_k(graph_agg_first_kernel, BT, 256, smem, s, in, A, out, out16, V, C, Kk, lrelu);
@@ -1487,6 +1535,68 @@ graph_agg_kv_pad16_kernel(const float* __restrict__ in, const float* __restrict_
   }
 }
 
+// Streaming variant: one thread per (source frame, group of 4 output nodes, 4 channels). The Kk * U source vectors of a
+// frame are re-read by its 6 node groups through L1 (they are 4.6 KB), nothing is staged or built per block, and every
+// store is an 8-byte piece of a coalesced 128-byte row segment. Geometry limits: Kk * U <= 24 adjacency terms per node.
+constexpr int GKP_TERMS = 24;
+__global__ void __launch_bounds__(256)
+graph_agg_kv_pad16_stream_kernel(const float* __restrict__ in, const float* __restrict__ A2, __nv_bfloat16* __restrict__ out16,
+                                 long long total, int Ts, int tdiv, int pad, int U, int Wn, int C4, int Kk) {
+  pdl_trigger();
+  __shared__ __align__(16) float As[GKP_TERMS * 32];     // [Kk*U][Wn] (Wn <= 32)
+  const int KU = Kk * U;
+  for (int i = threadIdx.x; i < KU * Wn; i += blockDim.x) As[i] = A2[i];   // constant: before the grid dependency
+  pdl_wait();
+  __syncthreads();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int WG = Wn / 4, C = C4 * 4, KC = Kk * C;
+  const int c = (int)(idx % C4) * 4;
+  const long long r = idx / C4;
+  const int wg = (int)(r % WG);
+  const long long bt = r / WG;
+  const int b = (int)(bt / Ts), t2 = (int)(bt - (long long)b * Ts);
+  const float* src = in + bt * U * KC + c;
+  float4 acc[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 6
+  for (int ku = 0; ku < KU; ++ku) {            // ascending (k, u): the list kernel's summation order
+    const int k = ku / U, u = ku - k * U;
+    const float4 x = *reinterpret_cast<const float4*>(src + u * KC + k * C);
+    const float4 a = *reinterpret_cast<const float4*>(As + ku * Wn + wg * 4);
+    acc[0].x = fmaf(x.x, a.x, acc[0].x); acc[0].y = fmaf(x.y, a.x, acc[0].y); acc[0].z = fmaf(x.z, a.x, acc[0].z); acc[0].w = fmaf(x.w, a.x, acc[0].w);
+    acc[1].x = fmaf(x.x, a.y, acc[1].x); acc[1].y = fmaf(x.y, a.y, acc[1].y); acc[1].z = fmaf(x.z, a.y, acc[1].z); acc[1].w = fmaf(x.w, a.y, acc[1].w);
+    acc[2].x = fmaf(x.x, a.z, acc[2].x); acc[2].y = fmaf(x.y, a.z, acc[2].y); acc[2].z = fmaf(x.z, a.z, acc[2].z); acc[2].w = fmaf(x.w, a.z, acc[2].w);
+    acc[3].x = fmaf(x.x, a.w, acc[3].x); acc[3].y = fmaf(x.y, a.w, acc[3].y); acc[3].z = fmaf(x.z, a.w, acc[3].z); acc[3].w = fmaf(x.w, a.w, acc[3].w);
+  }
+  uint2 pk[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(acc[j].x, acc[j].y), hi = __floats2bfloat162_rn(acc[j].z, acc[j].w);
+    pk[j].x = *reinterpret_cast<uint32_t*>(&lo);
+    pk[j].y = *reinterpret_cast<uint32_t*>(&hi);
+  }
+  // padded frames whose (reflected, down-sampled) source frame is t2: the tdiv interior ones plus reflected borders
+  const int T = Ts * tdiv, Tp = T + 2 * pad;
+  __nv_bfloat16* ob = out16 + (long long)b * Tp * Wn * C + (long long)(wg * 4) * C + c;
+  for (int i = 0; i < tdiv; ++i) {
+    __nv_bfloat16* o = ob + (long long)(pad + t2 * tdiv + i) * Wn * C;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) *reinterpret_cast<uint2*>(o + j * C) = pk[j];
+  }
+  for (int e = 0; e < 2 * pad; ++e) {
+    const int tp = e < pad ? e : T + e;          // border frame (front: 0..pad-1, back: T+pad..T+2pad-1)
+    int t = tp - pad;
+    t = t < 0 ? -t : 2 * (T - 1) - t;
+    if (t / tdiv == t2) {
+      __nv_bfloat16* o = ob + (long long)tp * Wn * C;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<uint2*>(o + j * C) = pk[j];
+    }
+  }
+}
+
 // reflect-pad borders of a [B, T + 2*pad, V*C] bf16 tensor whose interior rows are already written
 __global__ void reflect_border_kernel(__nv_bfloat16* __restrict__ xp, int T, int pad, long long row8, long long total8) {
   pdl_trigger();
@@ -1531,6 +1641,14 @@ int graph_agg_kv_pad16(const float* in, const float* A2, __nv_bfloat16* out16, i
                       (C & 3) == 0 && Kk > 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0,
                   "graph_agg_kv_pad16: bad args");
   MOCHA_CHECK_ARG(tdiv + 2 * pad <= 16 && pad < Ts * tdiv, "graph_agg_kv_pad16: tdiv / pad too large");
+  static const bool no_stream = getenv("MOCHA_NO_STREAM_AGG") != nullptr;   // A/B switch: the list kernel below
+  if (!no_stream && Kk * U <= GKP_TERMS && Wn % 4 == 0 && Wn <= 32 && (reinterpret_cast<uintptr_t>(out16) & 7) == 0) {
+    const long long total = (long long)B * Ts * (Wn / 4) * (C / 4);
+    launch_k(graph_agg_kv_pad16_stream_kernel, blocks_for(total, 256), 256, 0, s, in, A2, out16, total, Ts, tdiv, pad, U, Wn, C / 4, Kk);
+    count_launch();
+    MOCHA_LAUNCH_CHECK("graph_agg_kv_pad16_stream");
+    return MOCHA_OK;
+  }
   const size_t smem = (size_t)(U * Kk * C + 2 * Kk * U * Wn + Wn) * sizeof(float);
   MOCHA_CHECK_ARG(smem <= 48 * 1024, "graph_agg_kv_pad16: tile too large (%zu B)", smem);
   launch_k(graph_agg_kv_pad16_kernel, B * Ts, 256, smem, s, in, A2, out16, Ts, tdiv, pad, U, Wn, C, Kk);
