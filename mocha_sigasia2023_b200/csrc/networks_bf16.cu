@@ -280,6 +280,9 @@ int to_mot_bf16(const mocha_generator_weights* w, const float* tokens, int B, fl
   MOCHA_TRY(graph_agg_kv_pad16(y3, w->tm_A2, gp16, B, Tp, d.tp, padj, d.P, d.V, d.C0, d.Kj, s));
   MOCHA_TRY(tc_tconv_ex(nullptr, gp16, w->tm_jb_tcn_w, w->tm_jb_tcn_b, 0, h16(y4, 1), B, d.T, d.V, d.C0, d.C0, d.taps_j, 1, ws, s, 1,
                         true));
+  static const bool no_out_conv = getenv("MOCHA_NO_OUT_CONV_KERNEL") != nullptr;
+  if (!no_out_conv && out_conv_affine_supported(d.C0, d.Cin) && (Y || Ytil))
+    return out_conv_affine(y4, w->tm_out_w, w->tm_out_b, Y_mean, Y_std, Ytil, Y, R, d.C0, d.Cin, d.V, s);
   MOCHA_TRY(tc.lin(y4, d.C0, w->tm_out_w, w->tm_out_b, 0, nullptr, f32(ytp), R, Cp, d.C0, ACT_NONE));
   if (Y || Ytil) MOCHA_TRY(affine_rows(ytp, Y_mean, Y_std, Y, R, d.Cin, d.V, s, Cp, Ytil));
   return MOCHA_OK;

@@ -1057,7 +1057,7 @@ cvae_prior_last_kernel(const float* __restrict__ x, int np, const __nv_bfloat16*
     const float* p0 = sc + (0 * H + h) * PL_MAXKEYS;
     const float* p1 = sc + (1 * H + h) * PL_MAXKEYS;
     float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;   // a[row][column]
-#pragma unroll 4
+#pragma unroll 16
     for (int j = kg; j < np; j += 4) {
       const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(vb + (long long)j * 2 * D));
       const float vl = __uint_as_float(u << 16), vh = __uint_as_float(u & 0xffff0000u);
@@ -1351,6 +1351,105 @@ __global__ void affine_rows_kernel(const float* __restrict__ x, const float* __r
   const float v = x[r * ld_in + (i - r * C)];
   if (out) out[i] = v * sd[o] + mu[o];
   if (copy) copy[i] = v;
+}
+
+// to_mot's output layer in one pass (model.py:77-78 + the driver's de-normalisation, test_fullframework.py:457):
+//   Ytil = x W^T + b (x: bf16 rows that already went through LeakyReLU, K = 16 KS -> N <= 16 channels), Y = Ytil * std + mean
+// on mma.sync m16n8k16 (bf16 operands, fp32 accumulation): the N x K weights are constant B fragments in registers, a
+// warp takes 16 rows per pass with its A fragments loaded straight from global memory (4-byte pieces that L1 merges
+// into whole sectors), results go through a staging tile so that the stores - and the table look-ups of the
+// de-normalisation - are coalesced. Replaces a 15-wide tensor-core GEMM (16 us: all epilogue) and a scalar affine pass
+// (14 us); a first SIMT version (thread per row, broadcast LDS.128 weights) was shared-memory-issue-bound at 27 us.
+constexpr int OC_ROWS = 256;
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <int KS>
+__global__ void __launch_bounds__(OC_ROWS)
+out_conv_affine_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
+                       const float* __restrict__ mu, const float* __restrict__ sd, float* __restrict__ ytil,
+                       float* __restrict__ y, int R, int N, int period) {
+  constexpr int K = KS * 16, PASSES = OC_ROWS / 128;
+  pdl_trigger();
+  extern __shared__ __align__(16) float osm[];
+  float* stage = osm;                         // [OC_ROWS][N]
+  float* tab = osm + OC_ROWS * N;             // [2][period * N] de-normalisation tables (std, mean)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int pn = period * N;
+  // constants (weights, tables): loaded before the grid dependency resolves
+  if (y)
+    for (int i = threadIdx.x; i < pn; i += OC_ROWS) { tab[i] = sd[i]; tab[pn + i] = mu[i]; }
+  uint32_t wb[KS][2][2];                      // B fragments: B[k][n] = W[n][k], two n-tiles of 8 (columns >= N are zero)
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int n = nt * 8 + g, k = ks * 16 + 2 * t + 8 * h;
+        float2 wv = make_float2(0.f, 0.f);
+        if (n < N) wv = __ldg(reinterpret_cast<const float2*>(W + n * K + k));
+        const __nv_bfloat162 p = __floats2bfloat162_rn(wv.x, wv.y);
+        wb[ks][nt][h] = *reinterpret_cast<const uint32_t*>(&p);
+      }
+  float bz[2][2];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int n = nt * 8 + 2 * t + e;
+      bz[nt][e] = (bias && n < N) ? __ldg(bias + n) : 0.f;
+    }
+  pdl_wait();
+  const int ntiles = (R + OC_ROWS - 1) / OC_ROWS;
+  uint32_t a[PASSES][KS][4];
+  auto load_a = [&](int tile) {               // all of a tile's fragment loads in flight at once
+    const int row0 = tile * OC_ROWS;
+#pragma unroll
+    for (int ps = 0; ps < PASSES; ++ps) {
+      const int r0 = row0 + ps * 128 + warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const uint32_t* p0 = reinterpret_cast<const uint32_t*>(x + (long long)r0 * K + ks * 16 + 2 * t);
+        const uint32_t* p1 = reinterpret_cast<const uint32_t*>(x + (long long)r1 * K + ks * 16 + 2 * t);
+        a[ps][ks][0] = r0 < R ? __ldg(p0) : 0u;
+        a[ps][ks][1] = r1 < R ? __ldg(p1) : 0u;
+        a[ps][ks][2] = r0 < R ? __ldg(p0 + 4) : 0u;
+        a[ps][ks][3] = r1 < R ? __ldg(p1 + 4) : 0u;
+      }
+    }
+  };
+  if ((int)blockIdx.x < ntiles) load_a(blockIdx.x);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int row0 = tile * OC_ROWS;
+#pragma unroll
+    for (int ps = 0; ps < PASSES; ++ps) {
+      const int lr = ps * 128 + warp * 16 + g;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        float d[4] = {bz[nt][0], bz[nt][1], bz[nt][0], bz[nt][1]};
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) mma_bf16_16816(d, a[ps][ks], wb[ks][nt][0], wb[ks][nt][1]);
+        const int n = nt * 8 + 2 * t;
+        if (n < N) { stage[lr * N + n] = d[0]; stage[(lr + 8) * N + n] = d[2]; }
+        if (n + 1 < N) { stage[lr * N + n + 1] = d[1]; stage[(lr + 8) * N + n + 1] = d[3]; }
+      }
+    }
+    __syncthreads();
+    if (tile + (int)gridDim.x < ntiles) load_a(tile + gridDim.x);   // next tile's rows arrive while this one is stored
+    const int nvalid = min(OC_ROWS, R - row0) * N;
+    const long long g0 = (long long)row0 * N;
+    int o = (int)(g0 % pn) + (int)threadIdx.x;       // table index of this thread's first element
+    for (int i = threadIdx.x; i < nvalid; i += OC_ROWS, o += OC_ROWS) {
+      while (o >= pn) o -= pn;
+      const float v = stage[i];
+      if (ytil) ytil[g0 + i] = v;
+      if (y) y[g0 + i] = fmaf(v, tab[o], tab[pn + o]);
+    }
+    __syncthreads();
+  }
 }
 
 __global__ void broadcast_rows_kernel(const float* __restrict__ x, float* __restrict__ out,
@@ -1875,6 +1974,30 @@ int affine_rows(const float* x, const float* mu, const float* sd, float* out, lo
   launch_k(affine_rows_kernel, blocks_for(total, 256), 256, 0, s, x, mu, sd, out, total, C, period, ld_in > 0 ? ld_in : C, copy);
   count_launch();
   MOCHA_LAUNCH_CHECK("affine_rows");
+  return MOCHA_OK;
+}
+
+bool out_conv_affine_supported(int K, int N) { return (K == 64 || K == 128) && N >= 1 && N <= 16; }
+
+int out_conv_affine(const __nv_bfloat16* x, const float* W, const float* bias, const float* mu, const float* sd, float* ytil,
+                    float* y, int R, int K, int N, int period, cudaStream_t s) {
+  MOCHA_CHECK_ARG(x && W && (ytil || y) && R > 0 && out_conv_affine_supported(K, N) && aligned16(x), "out_conv_affine: bad args");
+  MOCHA_CHECK_ARG(!y || (mu && sd && period > 0), "out_conv_affine: Y needs its tables");
+  if (period <= 0) period = 1;
+  const size_t smem = (size_t)(OC_ROWS * N + 2 * period * N) * sizeof(float);
+  MOCHA_CHECK_ARG(smem <= 48 * 1024, "out_conv_affine: tables too large");
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  const int ntiles = (int)blocks_for(R, OC_ROWS);
+  // persistent: at most 3 co-resident blocks per SM, every block the same number of tiles (no ragged last round)
+  const int per = (ntiles + 3 * sms - 1) / (3 * sms);
+  const int grid = (ntiles + per - 1) / per;
+  if (K == 64)
+    launch_k(out_conv_affine_kernel<4>, grid, OC_ROWS, smem, s, x, W, bias, mu, sd, ytil, y, R, N, period);
+  else
+    launch_k(out_conv_affine_kernel<8>, grid, OC_ROWS, smem, s, x, W, bias, mu, sd, ytil, y, R, N, period);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("out_conv_affine");
   return MOCHA_OK;
 }
 

@@ -59,6 +59,11 @@ int adain_norm_tokens(const float* x, int B, int n, int C, float eps, const floa
 
 // mean over tokens: out[b,c] = mean_n x[b,n,c]  (AdaptiveAvgPool1d(1), transformer.py:102)
 int token_mean(const float* x, int B, int n, int C, float* out, cudaStream_t s);
+// to_mot's output layer + de-normalisation in one pass: ytil [R, N] = x [R, K] (bf16) W^T [N, K] + b, y = ytil * sd + mu
+// with [period, N] tables indexed by row % period
+bool out_conv_affine_supported(int K, int N);
+int out_conv_affine(const __nv_bfloat16* x, const float* W, const float* bias, const float* mu, const float* sd, float* ytil,
+                    float* y, int R, int K, int N, int period, cudaStream_t s);
 // last CVAE prior layer on its two read rows (tokens 0 / 1 of x [B, np, D]; kv bf16 [B*np, 2D] from the K/V projection):
 // q projection, attention, out-projection + LayerNorm, FFN + LayerNorm in one launch -> out [2B, D] fp32
 bool cvae_prior_last_supported(int D, int H, int dff, int np);
