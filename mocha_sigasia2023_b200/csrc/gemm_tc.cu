@@ -13,7 +13,11 @@
 #include <cstdlib>
 
 #include "gemm_tc.cuh"
+
+#include <mutex>
+#include <vector>
 #include "gemm_f32.cuh"
+#include "ops.cuh"
 
 namespace mocha {
 
@@ -1826,9 +1830,10 @@ struct Blob {
   const __nv_bfloat16* b16;
   size_t elems;
 };
-constexpr int MAX_BLOBS = 16;
-Blob g_blobs[MAX_BLOBS];
-int g_nblobs = 0;
+// registry of bf16 weight mirrors: any number of live blobs, guarded for concurrent host threads (sessions / models are
+// built and destroyed from Python threads; look-ups happen on every tensor-core layer call)
+std::vector<Blob> g_blobs;
+std::mutex g_blob_mutex;
 
 // k_blocks > 0 lets long-K problems keep 256-wide tiles below one wave: a 128-wide tile needs twice the
 // shared-memory fill per MMA (fill-bound at ~64 B/clk/SM), measured 16.3 -> 12.0 us on 11520 x 256 x 1024
@@ -1922,24 +1927,22 @@ size_t tc_scratch_bytes(size_t rows, size_t K) {
 }
 
 void tc_register_blob(const float* blob32, const void* blob16, size_t elems) {
+  std::lock_guard<std::mutex> lock(g_blob_mutex);
   // drop every entry that overlaps the new range (stale mirrors of freed / re-used allocations)
-  int n = 0;
-  for (int i = 0; i < g_nblobs; ++i) {
+  size_t n = 0;
+  for (size_t i = 0; i < g_blobs.size(); ++i) {
     const Blob& b = g_blobs[i];
     const bool overlap = blob32 < b.b32 + b.elems && b.b32 < blob32 + elems;
     if (!overlap) g_blobs[n++] = b;
   }
-  g_nblobs = n;
+  g_blobs.resize(n);
   if (!blob16) return;  // unregister only
-  if (g_nblobs == MAX_BLOBS) {  // evict the oldest
-    for (int i = 1; i < MAX_BLOBS; ++i) g_blobs[i - 1] = g_blobs[i];
-    --g_nblobs;
-  }
-  g_blobs[g_nblobs++] = Blob{blob32, (const __nv_bfloat16*)blob16, elems};
+  g_blobs.push_back(Blob{blob32, (const __nv_bfloat16*)blob16, elems});
 }
 
 const __nv_bfloat16* tc_lookup_bf16(const float* W) {
-  for (int i = 0; i < g_nblobs; ++i) {
+  std::lock_guard<std::mutex> lock(g_blob_mutex);
+  for (size_t i = g_blobs.size(); i-- > 0;) {   // newest first
     const Blob& b = g_blobs[i];
     if (b.b16 && W >= b.b32 && W < b.b32 + b.elems) return b.b16 + (W - b.b32);
   }
@@ -2359,7 +2362,9 @@ bool tc_attention_supported(int nq, int nkv, int dh) {
 
 static int attn_ldp(int nkv) { return (nkv + 7) / 8 * 8; }
 
+size_t tc_attention_tf32x3_scratch_bytes(int B, int H, int nq, int nkv, int dh);
 size_t tc_attention_scratch_bytes(int B, int H, int nq, int nkv, int dh) {
+  if (g_ws_precision == MOCHA_TF32X3) return tc_attention_tf32x3_scratch_bytes(B, H, nq, nkv, dh);
   const size_t Z = (size_t)B * H, ldp = attn_ldp(nkv);
   return align_up((size_t)B * nq * H * dh * 2, 256) + align_up((size_t)B * nkv * H * dh * 2, 256) +
          align_up(Z * dh * ldp * 2, 256) + align_up(Z * nq * ldp * 2, 256) + align_up(Z * nq * 4, 256) + 1024;
@@ -2471,6 +2476,155 @@ int tc_attention_ex(const float* q, const __nv_bfloat16* qh, int ldq, const floa
       MOCHA_TRY(dispatch_bn(pick_bn(sh.tiles_m_total, dh), tmA, VT16, (unsigned long long)Z * dh,
                             (unsigned long long)ldp, sh, dh, ceil_div(ldp, BLOCK_K), epi, s));
     }
+  }
+  ws.off = mark;
+  return MOCHA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention in the 3xTF32 parity mode: Q K^T and P V as split-fp32 batched-head GEMMs (same [hi | lo | hi] x [hi | hi | lo]
+// K-concatenation as tc_linear_tf32x3, per head), softmax in fp32 between them (softmax_rows_kernel via the caller's S)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// x [rows, ld] with head h at columns h*dh -> y [rows, H*3dh], per head [hi | lo | hi] (w_order = 0) or [hi | hi | lo] (1)
+__global__ void split3_heads_kernel(const float* __restrict__ x, int ld, int H, int dh, long long total4, int w_order,
+                                    float* __restrict__ y) {
+  pdl_trigger();
+  pdl_wait();
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= total4) return;
+  const int d4 = dh / 4, inner4 = H * d4;
+  const long long r = i4 / inner4;
+  const int rem = (int)(i4 - r * inner4), h = rem / d4, c = (rem - h * d4) * 4;
+  const float4 v = *reinterpret_cast<const float4*>(x + r * ld + h * dh + c);
+  float4 hi, lo;
+  split4(v, hi, lo);
+  float* o = y + (r * H + h) * 3 * dh + c;
+  *reinterpret_cast<float4*>(o) = hi;
+  *reinterpret_cast<float4*>(o + dh) = w_order ? hi : lo;
+  *reinterpret_cast<float4*>(o + 2 * dh) = w_order ? lo : hi;
+}
+
+// P [rows, n] -> [rows, 3 kp] as [hi | lo | hi], each part zero-padded from n to kp columns
+__global__ void split3_pad_rows_kernel(const float* __restrict__ x, int n, int kp, long long total, float* __restrict__ y) {
+  pdl_trigger();
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long r = i / kp;
+  const int j = (int)(i - r * kp);
+  const float v = j < n ? x[r * n + j] : 0.f;
+  const float hi = tf32_rna(v), lo = tf32_rna(v - hi);
+  float* o = y + r * 3 * kp + j;
+  o[0] = hi; o[kp] = lo; o[2 * kp] = hi;
+}
+
+// v view [B*nkv, ldv] (head h at columns h*dh) -> Vt3 [Z*dh, 3 kp]: row (z, d) = [hi | hi | lo] of v[b, :, h*dh + d], padded to kp
+__global__ void transpose_split3_v_kernel(const float* __restrict__ v, int ldv, int H, int nkv, int dh, int kp,
+                                          float* __restrict__ vt) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float tile[32][33];
+  const int z = blockIdx.z, b = z / H, h = z - b * H;
+  const int j0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int j = j0 + i, d = d0 + tx;
+    tile[i][tx] = (j < nkv && d < dh) ? v[((long long)b * nkv + j) * ldv + h * dh + d] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int d = d0 + i, j = j0 + tx;
+    if (d < dh && j < kp) {
+      const float x = tile[tx][i];
+      const float hi = tf32_rna(x), lo = tf32_rna(x - hi);
+      float* o = vt + ((long long)z * dh + d) * 3 * kp + j;
+      o[0] = hi; o[kp] = hi; o[2 * kp] = lo;
+    }
+  }
+}
+
+inline int attn_kp(int nkv) { return (nkv + 3) / 4 * 4; }
+
+}  // namespace
+
+bool tc_attention_tf32x3_supported(int nq, int nkv, int dh) {
+  return nq >= 1 && nkv >= 1 && nkv <= 256 && dh >= 32 && (dh % 32) == 0;
+}
+
+size_t tc_attention_tf32x3_scratch_bytes(int B, int H, int nq, int nkv, int dh) {
+  const size_t Z = (size_t)B * H, kp = attn_kp(nkv), inner3 = (size_t)H * 3 * dh;
+  return align_up((size_t)B * nq * inner3 * 4, 256) + align_up((size_t)B * nkv * inner3 * 4, 256) +
+         align_up(Z * nq * 3 * kp * 4, 256) + align_up(Z * dh * 3 * kp * 4, 256) + 1024;
+}
+
+int tc_attention_tf32x3(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int B, int H, int nq, int nkv,
+                        int dh, float* S, float* out, int ldo, Workspace& ws, cudaStream_t s) {
+  MOCHA_CHECK_ARG(tc_attention_tf32x3_supported(nq, nkv, dh), "tc_attention_tf32x3: unsupported geometry nq=%d nkv=%d dh=%d", nq, nkv, dh);
+  MOCHA_CHECK_ARG(q && k && v && S && out, "tc_attention_tf32x3: null operand");
+  MOCHA_CHECK_ARG(((ldq | ldk) & 3) == 0 && ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k)) & 15) == 0,
+                  "tc_attention_tf32x3: q / k views must be 16 B aligned");
+  const int inner = H * dh, inner3 = 3 * inner, Z = B * H, kp = attn_kp(nkv);
+  const size_t mark = ws.off;
+  float* Q3 = ws.take<float>((size_t)B * nq * inner3);
+  float* K3 = ws.take<float>((size_t)B * nkv * inner3);
+  float* P3 = ws.take<float>((size_t)Z * nq * 3 * kp);
+  float* V3 = ws.take<float>((size_t)Z * dh * 3 * kp);
+  if (ws.overflow) { ws.off = mark; ws.overflow = false; return set_error(MOCHA_ERR_WORKSPACE, "tc_attention_tf32x3: workspace too small"); }
+  {
+    const long long tq = (long long)B * nq * inner / 4, tk = (long long)B * nkv * inner / 4;
+    launch_k(split3_heads_kernel, (unsigned)((tq + 255) / 256), 256, 0, s, q, ldq, H, dh, tq, 0, Q3);
+    launch_k(split3_heads_kernel, (unsigned)((tk + 255) / 256), 256, 0, s, k, ldk, H, dh, tk, 1, K3);
+    dim3 g((kp + 31) / 32, (dh + 31) / 32, Z);
+    launch_k(transpose_split3_v_kernel, g, 256, 0, s, v, ldv, H, nkv, dh, kp, V3);
+    count_launch(3);
+    MOCHA_LAUNCH_CHECK("attention tf32x3 staging");
+  }
+  // scores S[z] = Q[z] K[z]^T (fp32, [Z, nq, nkv])
+  {
+    CUtensorMap tmA;
+    MOCHA_TRY(make_tmap(&tmA, Q3, (unsigned long long)B * nq, (unsigned long long)inner3, BLOCK_M, 0, true));
+    TcShape sh{};
+    sh.nb = Z; sh.H = H;
+    sh.rows_out_per_b = nq;
+    sh.tiles_m_per_b = ceil_div(nq, BLOCK_M);
+    sh.tiles_m_total = sh.tiles_m_per_b * Z;
+    sh.src_rows_per_b = nq; sh.a_rows_h = 0; sh.a_cols_h = 3 * dh;
+    sh.b_rows_b = nkv; sh.b_rows_h = 0; sh.b_cols_h = 3 * dh;
+    sh.c_img_b = (long long)H * nq * nkv; sh.c_img_h = (long long)nq * nkv;
+    sh.taps = 1; sh.kb_per_tap = 3 * dh / TF_K; sh.tap_row_stride = 0;
+    LinearEpi epi{S, nkv, nkv, nullptr, 0, nullptr, ACT_NONE, nullptr, 0};
+    epi.tma = 0;   // batched-head score blocks: LSU epilogue
+    const int bn = nkv <= 32 ? 32 : nkv <= 64 ? 64 : nkv <= 128 ? 128 : 256;
+    MOCHA_TRY(dispatch_bn_tf32(bn, tmA, K3, (unsigned long long)B * nkv, (unsigned long long)inner3, sh, nkv, sh.kb_per_tap, epi, s));
+  }
+  {
+    // softmax over the keys, in place (fp32), then the split / padded A operand of the second GEMM
+    MOCHA_TRY(softmax_rows(S, (long long)Z * nq, nkv, 1.0f / sqrtf((float)dh), s));
+    const long long tp = (long long)Z * nq * kp;
+    launch_k(split3_pad_rows_kernel, (unsigned)((tp + 255) / 256), 256, 0, s, (const float*)S, nkv, kp, tp, P3);
+    count_launch();
+    MOCHA_LAUNCH_CHECK("split3_pad_rows");
+  }
+  // out[b, :, h*dh:(h+1)*dh] = P[z] V[z]
+  {
+    CUtensorMap tmA;
+    MOCHA_TRY(make_tmap(&tmA, P3, (unsigned long long)Z * nq, (unsigned long long)3 * kp, BLOCK_M, 0, true));
+    TcShape sh{};
+    sh.nb = Z; sh.H = H;
+    sh.rows_out_per_b = nq;
+    sh.tiles_m_per_b = ceil_div(nq, BLOCK_M);
+    sh.tiles_m_total = sh.tiles_m_per_b * Z;
+    sh.src_rows_per_b = (long long)H * nq; sh.a_rows_h = nq; sh.a_cols_h = 0;
+    sh.b_rows_b = (long long)H * dh; sh.b_rows_h = dh; sh.b_cols_h = 0;
+    sh.c_img_b = (long long)nq * ldo; sh.c_img_h = dh;
+    sh.taps = 1; sh.kb_per_tap = ceil_div(3 * kp, TF_K); sh.tap_row_stride = 0;
+    LinearEpi epi{out, ldo, dh, nullptr, 0, nullptr, ACT_NONE, nullptr, 0};
+    if (ldo == H * dh) MOCHA_TRY(setup_out_tma(epi, (unsigned long long)nq, (unsigned long long)B, (unsigned long long)ldo));
+    else epi.tma = 0;
+    MOCHA_TRY(dispatch_bn_tf32(pick_bn(sh.tiles_m_total, dh), tmA, V3, (unsigned long long)Z * dh, (unsigned long long)3 * kp, sh, dh,
+                               sh.kb_per_tap, epi, s));
   }
   ws.off = mark;
   return MOCHA_OK;

@@ -77,6 +77,11 @@ bool tc_tconv_tf32x3_supported(int B, int T, int V, int Cin, int Cout, int taps)
 int tc_tconv_tf32x3(const float* X, const float* W, const float* bias, int bias_period, float* C, int B, int T, int V, int Cin,
                     int Cout, int taps, int tdiv, Workspace& ws, cudaStream_t s);
 
+bool tc_attention_tf32x3_supported(int nq, int nkv, int dh);
+// softmax(Q K^T / sqrt(dh)) V with both products as split-fp32 batched-head GEMMs; S is the caller's [B, H, nq, nkv] scratch
+int tc_attention_tf32x3(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int B, int H, int nq, int nkv,
+                        int dh, float* S, float* out, int ldo, Workspace& ws, cudaStream_t s);
+
 // ---- attention: softmax(Q K^T / sqrt(dh)) V for B*H (batch, head) problems on tensor cores ------------
 // q/k/v are fp32 strided views [B*n, ld] with head h at columns h*dh; S is a [B,H,nq,nkv] fp32 scratch.
 bool tc_attention_supported(int nq, int nkv, int dh);

@@ -59,6 +59,11 @@ int attention(const Ctx& c, const float* q, int ldq, const float* k, int ldk, co
               int H, int nq, int nkv, int dh, float* S, float* out, int ldo) {
   if (c.precision == MOCHA_BF16 && tc_attention_supported(nq, nkv, dh))
     return tc_attention(q, ldq, k, ldk, v, ldv, B, H, nq, nkv, dh, S, out, ldo, *c.ws, c.s);
+  if (c.precision == MOCHA_TF32X3 && tc_attention_tf32x3_supported(nq, nkv, dh) && nq >= 16) {
+    // (tiny query counts - the cached decoder-0 table - stay on the fp32 kernel)
+    const int rc = tc_attention_tf32x3(q, ldq, k, ldk, v, ldv, B, H, nq, nkv, dh, S, out, ldo, *c.ws, c.s);
+    if (rc != MOCHA_ERR_WORKSPACE) return rc;   // without room for the split operands the FFMA products below still apply
+  }
   GemmParams p;
   p.A = q; p.lda = ldq; p.sA1 = (long long)nq * ldq; p.sA2 = dh;
   p.W = k; p.ldw = ldk; p.sW1 = (long long)nkv * ldk; p.sW2 = dh;
