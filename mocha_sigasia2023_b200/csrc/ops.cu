@@ -904,7 +904,9 @@ struct PriorLastW {
 };
 
 // two-vector version of warp_matvec: ys[v * ldy + o] = act(W[o, :] . xs[v * ldx ...] + b[o]) (* scale) (+ res[v * ldy + o])
-template <int KCH, int NV>
+// ITER groups of NV outputs are loaded together (ITER * NV * KCH 16-byte loads in flight per lane): the phases are L2-latency
+// chains, one round trip per pass of the loop.
+template <int KCH, int NV, int ITER>
 __device__ __forceinline__ void warp_matvec2(const __nv_bfloat16* __restrict__ W, const float* __restrict__ b, const float* xs,
                                              int ldx, float* ys, int ldy, const float* res, int N, int relu, float scale,
                                              int warp, int nwarps, int lane) {
@@ -919,39 +921,50 @@ __device__ __forceinline__ void warp_matvec2(const __nv_bfloat16* __restrict__ W
       x[v][c * 8 + 0] = lo.x; x[v][c * 8 + 1] = lo.y; x[v][c * 8 + 2] = lo.z; x[v][c * 8 + 3] = lo.w;
       x[v][c * 8 + 4] = hi.x; x[v][c * 8 + 5] = hi.y; x[v][c * 8 + 6] = hi.z; x[v][c * 8 + 7] = hi.w;
     }
-  for (int o0 = warp * NV; o0 < N; o0 += nwarps * NV) {
-    uint4 wv[NV * KCH];
+  for (int ob = warp * NV; ob < N; ob += nwarps * NV * ITER) {
+    uint4 wv[ITER][NV * KCH];
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
+    for (int it = 0; it < ITER; ++it) {
+      const int o0 = ob + it * nwarps * NV;
+      if (o0 < N) {
 #pragma unroll
-      for (int c = 0; c < KCH; ++c)
-        wv[i * KCH + c] = __ldg(reinterpret_cast<const uint4*>(W + (size_t)(o0 + i) * K + c * 256 + lane * 8));
-    float v0[NV], v1[NV];
+        for (int i = 0; i < NV; ++i)
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-      for (int c = 0; c < KCH; ++c) {
-        const uint32_t u[4] = {wv[i * KCH + c].x, wv[i * KCH + c].y, wv[i * KCH + c].z, wv[i * KCH + c].w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float wl = __uint_as_float(u[j] << 16), wh = __uint_as_float(u[j] & 0xffff0000u);
-          a0 = fmaf(wl, x[0][c * 8 + 2 * j], a0); a0 = fmaf(wh, x[0][c * 8 + 2 * j + 1], a0);
-          a1 = fmaf(wl, x[1][c * 8 + 2 * j], a1); a1 = fmaf(wh, x[1][c * 8 + 2 * j + 1], a1);
-        }
+          for (int c = 0; c < KCH; ++c)
+            wv[it][i * KCH + c] = __ldg(reinterpret_cast<const uint4*>(W + (size_t)(o0 + i) * K + c * 256 + lane * 8));
       }
-      v0[i] = a0; v1[i] = a1;
     }
-    const float t0 = warp_reduce_t<NV>(v0, lane), t1 = warp_reduce_t<NV>(v1, lane);
-    constexpr int STEP = 32 / NV;
-    if ((lane & (STEP - 1)) == 0) {
-      const int o = o0 + (NV == 8 ? ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)
-                                  : ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1));
-      const float bo = b ? __ldg(b + o) : 0.f;
-      float r0 = (t0 + bo) * scale, r1 = (t1 + bo) * scale;
-      if (relu) { r0 = fmaxf(r0, 0.f); r1 = fmaxf(r1, 0.f); }
-      if (res) { r0 += res[o]; r1 += res[ldy + o]; }
-      ys[o] = r0; ys[ldy + o] = r1;
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+      const int o0 = ob + it * nwarps * NV;
+      if (o0 >= N) break;
+      float v0[NV], v1[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < KCH; ++c) {
+          const uint32_t u[4] = {wv[it][i * KCH + c].x, wv[it][i * KCH + c].y, wv[it][i * KCH + c].z, wv[it][i * KCH + c].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float wl = __uint_as_float(u[j] << 16), wh = __uint_as_float(u[j] & 0xffff0000u);
+            a0 = fmaf(wl, x[0][c * 8 + 2 * j], a0); a0 = fmaf(wh, x[0][c * 8 + 2 * j + 1], a0);
+            a1 = fmaf(wl, x[1][c * 8 + 2 * j], a1); a1 = fmaf(wh, x[1][c * 8 + 2 * j + 1], a1);
+          }
+        }
+        v0[i] = a0; v1[i] = a1;
+      }
+      const float t0 = warp_reduce_t<NV>(v0, lane), t1 = warp_reduce_t<NV>(v1, lane);
+      constexpr int STEP = 32 / NV;
+      if ((lane & (STEP - 1)) == 0) {
+        const int o = o0 + (NV == 8 ? ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)
+                                    : ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1));
+        const float bo = b ? __ldg(b + o) : 0.f;
+        float r0 = (t0 + bo) * scale, r1 = (t1 + bo) * scale;
+        if (relu) { r0 = fmaxf(r0, 0.f); r1 = fmaxf(r1, 0.f); }
+        if (res) { r0 += res[o]; r1 += res[ldy + o]; }
+        ys[o] = r0; ys[ldy + o] = r1;
+      }
     }
   }
 }
@@ -980,14 +993,14 @@ __device__ __forceinline__ void ln2_rows256(const float* in, int ldi, const floa
 
 constexpr int PL_THREADS = 512;
 constexpr int PL_MAXKEYS = 256;
-template <int KCH2>   // dff / 256
+constexpr int PL_SMEM_KEYS = 192;   // a clip's K | V rows (1 KB per key) are staged in shared memory up to this many keys
+template <int KCH2, bool KVS>   // dff / 256; K / V staged in shared memory
 __global__ void __launch_bounds__(PL_THREADS, 1)
 cvae_prior_last_kernel(const float* __restrict__ x, int np, const __nv_bfloat16* __restrict__ kv, const PriorLastW W, int H,
                        float eps, float* __restrict__ out) {
   constexpr int D = 256, NW = PL_THREADS / 32, DFF = KCH2 * 256;
   pdl_trigger();
-  pdl_wait();
-  extern __shared__ __align__(16) float psm[];
+  extern __shared__ __align__(128) float psm[];
   float* xs = psm;                       // [2][D] the two query rows (residual)
   float* qs = xs + 2 * D;                // [2][D] q * 1/sqrt(dh); later the attention output
   float* y1 = qs + 2 * D;                // [2][D]
@@ -995,23 +1008,47 @@ cvae_prior_last_kernel(const float* __restrict__ x, int np, const __nv_bfloat16*
   float* hid = t1 + 2 * D;               // [2][DFF]
   float* part = hid + 2 * DFF;           // [4][2][D] partial P V sums
   float* sc = part + 8 * D;              // [2][H][PL_MAXKEYS] scores / probabilities
+  __nv_bfloat16* kvs = reinterpret_cast<__nv_bfloat16*>(sc + 2 * H * PL_MAXKEYS);   // [np][2D] (KVS only; 16 B aligned)
+  __shared__ __align__(8) unsigned long long kv_bar;
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int dh = D / H, lph = dh / 8;    // lanes per head when a lane owns 8 consecutive columns
+  const __nv_bfloat16* kb = kv + (long long)b * np * 2 * D;
+  const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(&kv_bar);
+  if (KVS && threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pdl_wait();
+  if (KVS && threadIdx.x == 0) {
+    // the clip's keys and values are one contiguous block: a single bulk copy, in flight during the q projection
+    const uint32_t bytes = (uint32_t)np * 2u * D * 2u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(kvs)),
+                 "l"(kb), "r"(bytes), "r"(bar_s)
+                 : "memory");
+  }
   for (int i = threadIdx.x; i < 2 * D; i += PL_THREADS) xs[i] = x[(long long)b * np * D + i];   // tokens 0 and 1 are adjacent
   __syncthreads();
-  warp_matvec2<1, 8>(W.wq, W.bq, xs, D, qs, D, nullptr, D, 0, rsqrtf((float)dh), warp, NW, lane);
+  warp_matvec2<1, 8, 2>(W.wq, W.bq, xs, D, qs, D, nullptr, D, 0, rsqrtf((float)dh), warp, NW, lane);
   __syncthreads();
+  if (KVS) {
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}"
+                   : "=r"(done) : "r"(bar_s) : "memory");
+  }
+  const __nv_bfloat16* ksrc = KVS ? kvs : kb;
   {
-    // scores: a warp per key, lane = 8 consecutive columns of the key row (one 512-byte coalesced load)
+    // scores: a warp per key, lane = 8 consecutive columns of the key row (one 512-byte row per load)
     float q0[8], q1[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { q0[j] = qs[lane * 8 + j]; q1[j] = qs[D + lane * 8 + j]; }
-    const __nv_bfloat16* kb = kv + (long long)b * np * 2 * D;
     for (int j0 = warp; j0 < np; j0 += 2 * NW) {
       const int j1 = j0 + NW;
-      const uint4 k0 = __ldg(reinterpret_cast<const uint4*>(kb + (long long)j0 * 2 * D + lane * 8));
+      const uint4 k0 = *reinterpret_cast<const uint4*>(ksrc + (long long)j0 * 2 * D + lane * 8);
       uint4 k1 = make_uint4(0, 0, 0, 0);
-      if (j1 < np) k1 = __ldg(reinterpret_cast<const uint4*>(kb + (long long)j1 * 2 * D + lane * 8));
+      if (j1 < np) k1 = *reinterpret_cast<const uint4*>(ksrc + (long long)j1 * 2 * D + lane * 8);
       const uint32_t u0[4] = {k0.x, k0.y, k0.z, k0.w}, u1[4] = {k1.x, k1.y, k1.z, k1.w};
       float s00 = 0.f, s01 = 0.f, s10 = 0.f, s11 = 0.f;   // s[key][row]
 #pragma unroll
@@ -1053,13 +1090,13 @@ cvae_prior_last_kernel(const float* __restrict__ x, int np, const __nv_bfloat16*
   {
     // a = p v: thread = 2 columns x one of 4 key groups
     const int c2 = (threadIdx.x & 127) * 2, kg = threadIdx.x >> 7, h = c2 / dh;
-    const __nv_bfloat16* vb = kv + (long long)b * np * 2 * D + D + c2;
+    const __nv_bfloat16* vb = ksrc + D + c2;
     const float* p0 = sc + (0 * H + h) * PL_MAXKEYS;
     const float* p1 = sc + (1 * H + h) * PL_MAXKEYS;
     float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;   // a[row][column]
 #pragma unroll 16
     for (int j = kg; j < np; j += 4) {
-      const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(vb + (long long)j * 2 * D));
+      const uint32_t u = *reinterpret_cast<const uint32_t*>(vb + (long long)j * 2 * D);
       const float vl = __uint_as_float(u << 16), vh = __uint_as_float(u & 0xffff0000u);
       const float w0 = p0[j], w1 = p1[j];
       a00 = fmaf(w0, vl, a00); a01 = fmaf(w0, vh, a01);
@@ -1072,13 +1109,13 @@ cvae_prior_last_kernel(const float* __restrict__ x, int np, const __nv_bfloat16*
   for (int i = threadIdx.x; i < 2 * D; i += PL_THREADS)
     qs[i] = (part[i] + part[2 * D + i]) + (part[4 * D + i] + part[6 * D + i]);
   __syncthreads();
-  warp_matvec2<1, 8>(W.wo, W.bo, qs, D, t1, D, xs, D, 0, 1.f, warp, NW, lane);        // x + Wo a + bo
+  warp_matvec2<1, 8, 2>(W.wo, W.bo, qs, D, t1, D, xs, D, 0, 1.f, warp, NW, lane);        // x + Wo a + bo
   __syncthreads();
   ln2_rows256(t1, D, W.g1, W.be1, eps, y1, D, warp, lane);
   __syncthreads();
-  warp_matvec2<1, 8>(W.w1, W.b1, y1, D, hid, DFF, nullptr, DFF, 1, 1.f, warp, NW, lane);
+  warp_matvec2<1, 8, 2>(W.w1, W.b1, y1, D, hid, DFF, nullptr, DFF, 1, 1.f, warp, NW, lane);
   __syncthreads();
-  warp_matvec2<KCH2, 4>(W.w2, W.b2, hid, DFF, t1, D, y1, D, 0, 1.f, warp, NW, lane);  // y + W2 relu(.) + b2
+  warp_matvec2<KCH2, 4, (KCH2 <= 2 ? 2 : 1)>(W.w2, W.b2, hid, DFF, t1, D, y1, D, 0, 1.f, warp, NW, lane);  // y + W2 relu(.) + b2
   __syncthreads();
   ln2_rows256(t1, D, W.g2, W.be2, eps, out + (long long)b * 2 * D, D, warp, lane);
 }
@@ -1852,8 +1889,14 @@ int cvae_prior_last(const float* x, int B, int np, const __nv_bfloat16* kv, cons
   MOCHA_CHECK_ARG(cvae_prior_last_supported(256, H, dff, np), "cvae_prior_last: unsupported geometry");
   MOCHA_CHECK_ARG(aligned16(kv) && aligned16(wq) && aligned16(wo) && aligned16(w1) && aligned16(w2), "cvae_prior_last: unaligned operand");
   PriorLastW W{wq, wo, w1, w2, bq, bo, b1, b2, g1, be1, g2, be2};
-  const size_t smem = (size_t)(8 * 256 + 2 * dff + 8 * 256 + 2 * H * PL_MAXKEYS) * sizeof(float);
-  MOCHA_CHECK_ARG(smem <= 200 * 1024, "cvae_prior_last: too many heads");
+  const size_t base = (size_t)(8 * 256 + 2 * dff + 8 * 256 + 2 * H * PL_MAXKEYS) * sizeof(float);
+  // staging the clip's K | V block in shared memory (one bulk copy) makes the kernel itself faster but costs more than it
+  // gains inside the frame: with ~215 KB of shared memory the block cannot become resident next to the previous GEMM's
+  // CTAs, so the programmatic-launch overlap of its prologue (and of the next kernel's) is lost. Opt-in for A/B runs.
+  static const bool want_kvs = getenv("MOCHA_PRIOR_LAST_KVS") != nullptr;
+  const bool kvs = want_kvs && np <= PL_SMEM_KEYS && base + (size_t)np * 1024 + 256 <= 220 * 1024;
+  const size_t smem = base + (kvs ? (size_t)np * 1024 : 0) + 128;
+  MOCHA_CHECK_ARG(smem <= 227 * 1024, "cvae_prior_last: too many heads");
   auto go = [&](auto kern) -> int {
     static size_t configured = 0;
     if (smem > configured && smem > 48 * 1024) {
@@ -1863,9 +1906,15 @@ int cvae_prior_last(const float* x, int B, int np, const __nv_bfloat16* kv, cons
     launch_k(kern, B, PL_THREADS, smem, s, x, np, kv, W, H, eps, out);
     return MOCHA_OK;
   };
-  if (dff == 256) MOCHA_TRY(go(cvae_prior_last_kernel<1>));
-  else if (dff == 512) MOCHA_TRY(go(cvae_prior_last_kernel<2>));
-  else MOCHA_TRY(go(cvae_prior_last_kernel<4>));
+  if (kvs) {
+    if (dff == 256) MOCHA_TRY(go(cvae_prior_last_kernel<1, true>));
+    else if (dff == 512) MOCHA_TRY(go(cvae_prior_last_kernel<2, true>));
+    else MOCHA_TRY(go(cvae_prior_last_kernel<4, true>));
+  } else {
+    if (dff == 256) MOCHA_TRY(go(cvae_prior_last_kernel<1, false>));
+    else if (dff == 512) MOCHA_TRY(go(cvae_prior_last_kernel<2, false>));
+    else MOCHA_TRY(go(cvae_prior_last_kernel<4, false>));
+  }
   count_launch();
   MOCHA_LAUNCH_CHECK("cvae_prior_last");
   return MOCHA_OK;
