@@ -13,8 +13,9 @@ AdaIN decode -> to_mot -> root integration / blending / foot-lock IK). Clips are
 N GPUs run N x C clips with no data-path collective (weak scaling; --total-clips T fixes the total instead: strong).
 Besides the headline the line carries: `roofline` (largest launch), `roofline_step` (whole step vs the tensor roof),
 `roofline_kernels` (the GEMM family and the fused block tail), `hbm_kernels` (achieved GB/s of the bandwidth-bound
-kernels), `match_sweep` (config 3), `latency_batch1*` (config 2 at 385 / 10 k / 100 k DB rows), `fp32_mode` (parity-mode
-throughput), `cpu_baseline` (the reference itself, N = 1) and, for N > 1, `match_sharded` (config 5).
+kernels), `match_sweep` (config 3), `latency_batch1*` (config 2 at 385 / 10 k / 100 k DB rows), `fp32_mode` / `tf32x3_mode`
+(parity-mode throughput on FFMA / on 3xTF32 tcgen05 GEMMs), `torch_eager_gpu` (the reference's own modules with stock PyTorch eager
+kernels on the same GPU), `cpu_baseline` (the reference itself with per-stage timings, N = 1) and, for N > 1, `match_sharded` (config 5).
 Prints ONE JSON line on rank 0, as the LAST line of stdout.
 """
 from __future__ import annotations
@@ -754,8 +755,11 @@ def hbm_kernels(sess, torch, lib, _lib):
     peak = peaks["hbm_gbs"]
     dev, B = sess.dev, sess.B
     out = []
-    names = {0: "embed_graph_agg_kernel (1x1 embed conv + LeakyReLU + joint-graph aggregation)", 1: "pool_graph_agg_kernel",
-             2: "add_layernorm_reg_kernel (CVAE prior rows, fp32 + bf16 out)", 3: "graph_agg_kv_pad16_kernel (to_mot)",
+    names = {0: "embed_graph_agg_mma_kernel (1x1 embed conv + LeakyReLU + joint-graph aggregation on mma.sync TF32 fragments, "
+                "bulk-copy row stores)", 1: "pool_graph_agg_kernel",
+             2: "add_layernorm_reg_kernel (CVAE prior rows, fp32 + bf16 out)", 3: "graph_agg_kv_pad16_stream_kernel (to_mot)",
+             6: "out_conv_affine_kernel (to_mot output layer on mma.sync bf16 + de-normalisation)",
+             7: "graph_agg_small_kernel (to_mot body-part graph aggregation)",
              4: "adain_norm_tokens (AdaIN + instance norm, fp32 + bf16 out)", 5: "instance_norm_tokens_v4_kernel (bf16 out)"}
     wp, wn = _lib.ptr(sess.ws), sess.ws.numel()
     for which, name in names.items():
@@ -790,8 +794,8 @@ def hbm_kernels(sess, torch, lib, _lib):
 
 def fp32_mode_pass(args, dev, torch, workload, lib, precision="fp32"):
     """The same step in a parity mode, for the record, so that the bf16 headline has its reference-precision counterpart
-    next to it: "fp32" = every contraction in fp32 FFMA, "tf32x3" = linear layers and temporal convolutions as split-fp32
-    (3xTF32) tcgen05 GEMMs; exact fp64 matcher in both."""
+    next to it: "fp32" = every contraction in fp32 FFMA, "tf32x3" = linear layers, temporal convolutions and the attention
+    products as split-fp32 (3xTF32) tcgen05 GEMMs; exact fp64 matcher in both."""
     B = args.clips
     sess, *_ = workload.build_session(B, n_db=args.db_rows, precision=precision, device=dev, seed=5)
     inp = workload.step_inputs(B, seed=11)
@@ -800,8 +804,8 @@ def fp32_mode_pass(args, dev, torch, workload, lib, precision="fp32"):
     sess.capture()
     ms = timed(torch, sess.step_device, 10, warm=2)
     label = ("fp32 (FFMA GEMMs, fp64 brute-force matcher)" if precision == "fp32" else
-             "tf32x3 (3xTF32 tcgen05 GEMMs for linear layers / temporal convolutions, FFMA attention products, fp64 "
-             "brute-force matcher)")
+             "tf32x3 (3xTF32 tcgen05 GEMMs for linear layers, temporal convolutions and both attention products; fp32 softmax / "
+             "norms, fp64 brute-force matcher)")
     return {"precision": label, "clips": B, "ms_per_step": ms, "value": B / ms * 1e3, "unit": UNIT,
             "tolerance": "1e-4 relative vs the reference (tests/test_gpu_session.py, test_gpu_e2e.py)"}
 

@@ -546,7 +546,8 @@ extern "C" int mocha_bench_tconv(const mocha_generator_weights* w, const float* 
 // of one launch (every input element read once + every output element written once).
 // which: 0 embed_graph_agg (1x1 embed conv + LeakyReLU + joint-graph aggregation), 1 pool_graph_agg,
 // 2 add_layernorm (CVAE prior rows, fp32 + bf16 outputs), 3 graph_agg_kv_pad16 (to_mot), 4 adain_norm_tokens,
-// 5 instance_norm_tokens -> bf16 (decoder style tokens)
+// 5 instance_norm_tokens -> bf16 (decoder style tokens), 6 out_conv_affine (to_mot output layer + de-normalisation),
+// 7 graph_agg_small (to_mot body-part aggregation)
 extern "C" int mocha_bench_hbm_kernel(const mocha_generator_weights* w, int which, int B, int repeats, void* workspace,
                                       size_t workspace_bytes, double* algo_bytes, mocha_stream_t stream) {
   MOCHA_CHECK_ARG(w && B > 0 && repeats >= 1 && algo_bytes, "mocha_bench_hbm_kernel: bad argument");
@@ -618,6 +619,31 @@ extern "C" int mocha_bench_hbm_kernel(const mocha_generator_weights* w, int whic
         rc = which == 4 ? adain_norm_tokens(x, B, n, d.D, 1e-5f, gb, y, q16, s)
                         : instance_norm_tokens(x, B, n, d.D, 1e-5f, nullptr, nullptr, nullptr, nullptr, nullptr, s, q16);
       *algo_bytes = which == 4 ? (double)B * n * d.D * (4 + 4 + 2) : (double)B * n * d.D * (4 + 2);
+      break;
+    }
+    case 6: {
+      // to_mot output layer + de-normalisation (out_conv_affine): bf16 rows in, de-normalised fp32 Y out
+      bf16* y4 = ws.take<bf16>((size_t)R * d.C0);
+      float* Y = ws.take<float>((size_t)R * d.Cin);
+      float* tab = ws.take<float>((size_t)2 * d.V * d.Cin);
+      WS_GUARD(ws, "mocha_bench_hbm_kernel");
+      MOCHA_CHECK_ARG(out_conv_affine_supported(d.C0, d.Cin), "mocha_bench_hbm_kernel: out_conv_affine does not take this geometry");
+      MOCHA_CUDA(cudaMemsetAsync(y4, 0, (size_t)R * d.C0 * 2, s));
+      MOCHA_CUDA(cudaMemsetAsync(tab, 0, (size_t)2 * d.V * d.Cin * 4, s));
+      for (int i = 0; i < repeats && rc == MOCHA_OK; ++i)
+        rc = out_conv_affine(y4, w->tm_out_w, w->tm_out_b, tab, tab + d.V * d.Cin, nullptr, Y, R, d.C0, d.Cin, d.V, s);
+      *algo_bytes = (double)R * d.C0 * 2 + (double)R * d.Cin * 4;
+      break;
+    }
+    case 7: {
+      // to_mot's body-part graph aggregation (graph_agg_small): fp32 tokens in, bf16 [R2, Kb*D] out
+      float* x = ws.take<float>((size_t)R2 * d.D);
+      bf16* out = ws.take<bf16>((size_t)R2 * d.Kb * d.D);
+      WS_GUARD(ws, "mocha_bench_hbm_kernel");
+      MOCHA_CUDA(cudaMemsetAsync(x, 0, (size_t)R2 * d.D * 4, s));
+      for (int i = 0; i < repeats && rc == MOCHA_OK; ++i)
+        rc = graph_agg_first(x, w->tm_A_b, nullptr, B * Tp, d.P, d.D, d.Kb, 1, s, out);
+      *algo_bytes = (double)R2 * d.D * 4 + (double)R2 * d.Kb * d.D * 2;
       break;
     }
     default:
