@@ -66,7 +66,8 @@ def build(force: bool = False, verbose: bool = False, trace: bool = False) -> st
         log = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".ptxas.log")
         with open(log, "w") as f:
             f.write(r.stderr)
-        if r.returncode != 0:
+        # (nvcc can return 0 after a host-preprocessor error such as a macro arity mismatch: treat any "error:" line as fatal)
+        if r.returncode != 0 or ": error:" in r.stderr or " error: " in r.stderr:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
         if verbose:
             sys.stderr.write(r.stderr)

@@ -1898,11 +1898,8 @@ int cvae_prior_last(const float* x, int B, int np, const __nv_bfloat16* kv, cons
   const size_t smem = base + (kvs ? (size_t)np * 1024 : 0) + 128;
   MOCHA_CHECK_ARG(smem <= 227 * 1024, "cvae_prior_last: too many heads");
   auto go = [&](auto kern) -> int {
-    static size_t configured = 0;
-    if (smem > configured && smem > 48 * 1024) {
-      MOCHA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
+    // (no cached flag: the variants share one function-pointer type, so a static here would be shared between them)
+    if (smem > 48 * 1024) MOCHA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     launch_k(kern, B, PL_THREADS, smem, s, x, np, kv, W, H, eps, out);
     return MOCHA_OK;
   };
