@@ -243,7 +243,10 @@ int mocha_to_mot_fwd(const mocha_generator_weights* w, const float* d_tokens, in
 /* ---- (a6,a7) CVAE.sample  model_CVAE.py:44-46 (PriorNet :70-92, Decoder :159-165) ----------- */
 /* cond [B,ncond,D]; d_eps [B,D] standard-normal draw or NULL for deterministic=True;
  * out [B,out_seq,D]; d_mu/d_logvar [B,D] optional. If d_out_mean/d_out_std ([out_seq,D]) are given,
- * d_out_denorm = out*std+mean (test_fullframework.py:449) is also written. */
+ * d_out_denorm = out*std+mean (test_fullframework.py:449) is also written.
+ * With d_out == d_out_denorm == NULL and d_mu / d_logvar given only the token network runs: this is CVAE.prior
+ * (model_CVAE.py:29-31) and, with the posterior Encoder's weights in the `prior` slots and cond = [c ; x]
+ * (model_CVAE.py:116-126, up to 510 tokens), CVAE.encode (:33-35). */
 size_t mocha_cvae_workspace_bytes(const mocha_cvae_weights* w, int B, int ncond);
 int mocha_cvae_sample(const mocha_cvae_weights* w, const float* d_cond, int B, int ncond,
                       const float* d_eps, float* d_out, float* d_mu, float* d_logvar,

@@ -383,16 +383,17 @@ extern "C" int mocha_cvae_sample(const mocha_cvae_weights* w, const float* cond,
                                  const float* eps, float* out, float* mu, float* logvar,
                                  const float* out_mean, const float* out_std, float* out_denorm, int precision,
                                  void* workspace, size_t workspace_bytes, mocha_stream_t stream) {
-  MOCHA_CHECK_ARG(w && cond && B > 0 && ncond > 0 && (out || out_denorm), "mocha_cvae_sample: null/empty argument");
+  // out == out_denorm == NULL with mu / logvar given: only the token network runs (CVAE.prior / CVAE.encode)
+  MOCHA_CHECK_ARG(w && cond && B > 0 && ncond > 0 && (out || out_denorm || (mu && logvar)), "mocha_cvae_sample: null/empty argument");
   MOCHA_CHECK_ARG(w->D > 0 && w->heads > 0 && w->D % w->heads == 0 && w->dff > 0 && w->out_seq > 0,
                   "mocha_cvae_sample: bad geometry");
   MOCHA_CHECK_ARG(w->depth >= 1 && w->depth <= MOCHA_MAX_DEPTH, "mocha_cvae_sample: depth out of range");
-  MOCHA_CHECK_ARG(ncond + 2 <= 256, "mocha_cvae_sample: ncond=%d too long", ncond);
+  MOCHA_CHECK_ARG(ncond + 2 <= 512, "mocha_cvae_sample: ncond=%d too long", ncond);
   MOCHA_CHECK_ARG(!out_denorm || (out_mean && out_std), "mocha_cvae_sample: denorm needs its tables");
   Workspace ws(workspace, workspace_bytes);
   {
     const int dh_ = w->D / w->heads;
-    if (precision == MOCHA_BF16 && w->D % 64 == 0 && w->dff % 64 == 0 && w->out_seq <= ncond + 2 &&
+    if (precision == MOCHA_BF16 && (out || out_denorm) && ncond + 2 <= 256 && w->D % 64 == 0 && w->dff % 64 == 0 && w->out_seq <= ncond + 2 &&
         tc_attention_supported(ncond + 2, ncond + 2, dh_) && tc_attention_supported(w->out_seq, ncond + 1, dh_))
       return cvae_bf16(w, cond, B, ncond, eps, out, mu, logvar, out_mean, out_std, out_denorm, ws, (cudaStream_t)stream);
   }
@@ -439,6 +440,7 @@ extern "C" int mocha_cvae_sample(const mocha_cvae_weights* w, const float* cond,
   }
   // ---- reparameterise, assemble decoder memory [z ; cond] ----
   MOCHA_TRY(cvae_memory(x, np, eps, cond, mem, mu, logvar, B, ncond, D, c.s));
+  if (!out && !out_denorm) return MOCHA_OK;   // mu / logvar only
 
   // ---- decoder ----
   if (!w->dec0_sa) MOCHA_TRY(broadcast_rows(w->pe, da, B, (long long)nq * D, c.s));  // tgt = zeros + pe[:out_seq]

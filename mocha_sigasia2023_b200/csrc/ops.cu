@@ -1120,7 +1120,7 @@ cvae_prior_last_kernel(const float* __restrict__ x, int np, const __nv_bfloat16*
   ln2_rows256(t1, D, W.g2, W.be2, eps, out + (long long)b * 2 * D, D, warp, lane);
 }
 
-constexpr int SM_MAXPL = 8;  // up to 256 columns per row
+constexpr int SM_MAXPL = 16;  // up to 512 columns per row (the CVAE posterior attends over 272 tokens)
 __global__ void softmax_rows_kernel(float* __restrict__ S, long long rows, int ncols, float scale) {
   pdl_trigger();
   pdl_wait();

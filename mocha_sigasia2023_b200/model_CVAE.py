@@ -32,6 +32,8 @@ class CVAE(nn.Module):
             _attach(self, k, v, _is_buffer(k))
         self._packed = None
         self._packed_key = None
+        self._packed_post = None
+        self._packed_post_key = None
         self._ws = _Workspace()
         # Source of the reparameterisation noise. Default mirrors the reference
         # (torch.randn_like on the tensor's device, model_CVAE.py:83); parity runs inject host draws.
@@ -51,6 +53,38 @@ class CVAE(nn.Module):
 
     def _prec(self):
         return _lib.precision_code(self.precision)
+
+    def _pack_posterior(self):
+        """The posterior Encoder's weights in the token-network slots of a second ABI struct (training-side surface:
+        built on first use of encode / forward)."""
+        sd = self.state_dict()
+        key = tuple((p.data_ptr(), p._version) for p in sd.values())
+        dev = next(iter(sd.values())).device
+        if self._packed_post is None or key != self._packed_post_key:
+            if dev.type != "cuda":
+                raise _lib.MochaError("CVAE must live on a CUDA device: call .to('cuda') (no CPU fallback)")
+            self._packed_post = packing.PackedCVAE(sd, self.output_seq, self.latent_dim, self.depth, self.nheads,
+                                                   self.feedforward_dim, dev, token_net="encoder")
+            self._packed_post_key = key
+        return self._packed_post
+
+    def _run_tokens(self, pk, tokens):
+        """mu, logvar of a token network (prior or posterior) over `tokens` [B, n, D]: mocha_cvae_sample without outputs."""
+        tokens = tokens.contiguous()
+        _lib.require_cuda(tokens)
+        if tokens.dtype != torch.float32 or tokens.dim() != 3 or tokens.shape[2] != self.latent_dim:
+            raise _lib.MochaError(f"tokens must be float32 [B, n, {self.latent_dim}]")
+        B, n = tokens.shape[0], tokens.shape[1]
+        lib = _lib.load()
+        mu = torch.empty((B, self.latent_dim), dtype=torch.float32, device=tokens.device)
+        logvar = torch.empty_like(mu)
+        with _lib.workspace_precision(self._prec()):
+            nbytes = lib.mocha_cvae_workspace_bytes(C.byref(pk.struct), B, n)
+        ws = self._ws.get(nbytes, tokens.device)
+        _lib.check(lib.mocha_cvae_sample(C.byref(pk.struct), _lib.ptr(tokens), B, n, None, None, _lib.ptr(mu),
+                                         _lib.ptr(logvar), None, None, None, self._prec(), _lib.ptr(ws), ws.numel(),
+                                         _lib.stream_ptr()), "mocha_cvae_sample(tokens)")
+        return mu, logvar
 
     def _run(self, c, eps):
         pk = self._pack()
@@ -89,7 +123,21 @@ class CVAE(nn.Module):
         return out
 
     def encode(self, x, c):
-        raise _lib.MochaError("CVAE.encode (posterior) is training-only and not part of the B200 hot path")
+        """(model_CVAE.py:33-35) posterior mu, logvar: the Encoder is the prior's network over [mu, logvar, c, x] (:116-126).
+        Forward values only - no autograd (training stays out of scope)."""
+        if x.dim() != 3 or c.dim() != 3 or x.shape[0] != c.shape[0]:
+            raise _lib.MochaError("encode(x, c): expected [B, n_x, D] and [B, n_c, D]")
+        return self._run_tokens(self._pack_posterior(), torch.cat((c, x), dim=1))
 
     def forward(self, x, c):
-        raise _lib.MochaError("CVAE.forward (posterior path) is training-only and not part of the B200 hot path")
+        """(model_CVAE.py:37-42) out, (mu_po, logvar_po), (mu_pr, logvar_pr) with z_po = mu_po + eps * exp(logvar_po / 2).
+        The decoder kernel path takes its latent as `mu_pr + eps' * std_pr`, so z_po is handed over as the equivalent eps'.
+        Like the reference, two noise tensors are drawn (posterior, then prior: :128, :83); only the first is used."""
+        mu_po, logvar_po = self.encode(x, c)
+        eps_po = self._draw_eps(c)
+        self._draw_eps(c)                       # the prior's draw (PriorNet.forward), unused by the output
+        z_po = mu_po + eps_po * torch.exp(0.5 * logvar_po)
+        mu_pr, logvar_pr = self.prior(c)
+        eps_equiv = ((z_po - mu_pr) * torch.exp(-0.5 * logvar_pr)).contiguous()
+        out, _, _ = self._run(c, eps_equiv)
+        return out, (mu_po, logvar_po), (mu_pr, logvar_pr)

@@ -202,15 +202,17 @@ class PackedGenerator:
         self.ntok = (w.dims.T // w.dims.tp) * w.dims.P
 
 
-def cvae_tensors(sd, depth: int) -> "dict[str, torch.Tensor]":
+def cvae_tensors(sd, depth: int, token_net: str = "prior_net") -> "dict[str, torch.Tensor]":
+    """token_net = "prior_net" (PriorNet, model_CVAE.py:49-93) or "encoder" (the posterior Encoder, :95-135: the same
+    network over [mu, logvar, c, x] with its own weights) fills the `prior` slots of the ABI struct."""
     sd = {k: v.detach().to(torch.float32).cpu() for k, v in sd.items()}
     out = {
-        "mu_token": sd["prior_net.mu_token"].reshape(-1),
-        "logvar_token": sd["prior_net.logvar_token"].reshape(-1),
-        "pe": sd["prior_net.pos_encoder.pe"][0, :512].contiguous(),
+        "mu_token": sd[f"{token_net}.mu_token"].reshape(-1),
+        "logvar_token": sd[f"{token_net}.logvar_token"].reshape(-1),
+        "pe": sd[f"{token_net}.pos_encoder.pe"][0, :512].contiguous(),
     }
     for l in range(depth):
-        p = f"prior_net.encoder.layers.{l}"
+        p = f"{token_net}.encoder.layers.{l}"
         out[f"pr{l}.in_w"] = sd[p + ".self_attn.in_proj_weight"]
         out[f"pr{l}.in_b"] = sd[p + ".self_attn.in_proj_bias"]
         out[f"pr{l}.out_w"] = sd[p + ".self_attn.out_proj.weight"]
@@ -243,8 +245,9 @@ def cvae_tensors(sd, depth: int) -> "dict[str, torch.Tensor]":
 
 
 class PackedCVAE:
-    def __init__(self, sd, output_seq: int, latent_dim: int, depth: int, nheads: int, dff: int, device):
-        self.blob = PackedBlob(cvae_tensors(sd, depth), device)
+    def __init__(self, sd, output_seq: int, latent_dim: int, depth: int, nheads: int, dff: int, device,
+                 token_net: str = "prior_net"):
+        self.blob = PackedBlob(cvae_tensors(sd, depth, token_net), device)
         w = _lib.CvaeWeights()
         w.D, w.heads, w.dff, w.depth, w.out_seq = latent_dim, nheads, dff, depth, output_seq
         w.ln_eps = 1e-5

@@ -19,6 +19,11 @@ def cvae_inputs(B=2, seed=1):
     return cond, eps
 
 
+def cvae_posterior_inputs(B=2, seed=2):
+    """x [B, 90, 256] for CVAE.encode / CVAE.forward (the condition and eps are cvae_inputs()'s)."""
+    return np.random.default_rng(seed).standard_normal((B, 90, 256)).astype(np.float32)
+
+
 def _rand_quat(rng, shape, dtype):
     q = rng.standard_normal(tuple(shape) + (4,))
     q /= np.linalg.norm(q, axis=-1, keepdims=True)

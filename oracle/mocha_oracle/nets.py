@@ -217,6 +217,25 @@ def cvae_prior(sd, c, depth=2, heads=4):
     return x[:, 0], x[:, 1]
 
 
+def cvae_encode(sd, x, c, depth=2, heads=4):
+    """Encoder.encode, the posterior (model_CVAE.py:116-126): the prior's network over [mu, logvar, c, x], own weights."""
+    B = c.shape[0]
+    mu_t = np.repeat(sd["encoder.mu_token"], B, axis=0)
+    lv_t = np.repeat(sd["encoder.logvar_token"], B, axis=0)
+    t = np.concatenate([mu_t, lv_t, c, x], axis=1).astype(F32)
+    t = t + sd["encoder.pos_encoder.pe"][:, :t.shape[1]]
+    for l in range(depth):
+        t = encoder_layer(sd, f"encoder.encoder.layers.{l}", t, heads)
+    return t[:, 0], t[:, 1]
+
+
+def cvae_forward(sd, x, c, eps, out_seq=90, depth=2, heads=4):
+    """CVAE.forward (model_CVAE.py:37-42) with the posterior's noise given: out, (mu_po, logvar_po), (mu_pr, logvar_pr)."""
+    mu_po, lv_po = cvae_encode(sd, x, c, depth, heads)
+    z = (mu_po + eps * np.exp(F32(0.5) * lv_po)).astype(F32)
+    return cvae_decode(sd, z, c, out_seq, depth, heads), (mu_po, lv_po), cvae_prior(sd, c, depth, heads)
+
+
 def cvae_decode(sd, z, c, out_seq=90, depth=2, heads=4):
     """Decoder.forward (model_CVAE.py:159-165)."""
     B = c.shape[0]

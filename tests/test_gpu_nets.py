@@ -197,3 +197,24 @@ def test_tf32x3_linear_chunked_and_periodic_bias():
                                     _lib.MOCHA_TF32X3, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "mocha_linear")
         got = out.cpu().numpy()
         assert np.abs(got - want).max() < 2e-5, (ws_rows, np.abs(got - want).max())
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", RTOL_FP32), ("tf32x3", RTOL_FP32), ("bf16", RTOL_BF16)])
+def test_cvae_posterior_surface(gold, precision, tol):
+    """CVAE.encode / CVAE.forward (model_CVAE.py:33-42): the posterior Encoder is the prior's network over 272 tokens
+    [mu, logvar, c, x]; forward decodes z_po. Noise replayed from the golden run (posterior draw first, prior draw second)."""
+    c = CVAE(output_seq=90, precision=precision)
+    c.load_state_dict(weights.cvae_state_dict(1778), strict=True)
+    c = c.to("cuda").eval()
+    cond, eps = gi.cvae_inputs()
+    x = gi.cvae_posterior_inputs()
+    mu, logvar = c.encode(cu(x), cu(cond))
+    assert rel_err(mu.cpu().numpy(), gold["cvae_enc_mu"]) < tol
+    assert rel_err(logvar.cpu().numpy(), gold["cvae_enc_logvar"]) < tol
+    draws = iter([torch.from_numpy(eps), torch.zeros(eps.shape)])
+    c.eps_fn = lambda shape: next(draws)
+    out, (mu_po, lv_po), (mu_pr, lv_pr) = c(cu(x), cu(cond))
+    assert rel_err(out.cpu().numpy(), gold["cvae_fwd"]) < 2 * tol
+    assert rel_err(mu_po.cpu().numpy(), gold["cvae_enc_mu"]) < tol
+    assert rel_err(mu_pr.cpu().numpy(), gold["cvae_mu"]) < tol
+    assert rel_err(lv_pr.cpu().numpy(), gold["cvae_logvar"]) < tol

@@ -84,6 +84,18 @@ def test_cvae(gnets, cvae_sd):
     _close(out_e, gnets["cvae_eps"], 1e-4, 2e-5)
 
 
+def test_cvae_posterior(gnets, cvae_sd):
+    """CVAE.encode / CVAE.forward (training-side surface, model_CVAE.py:33-42) with the posterior noise replayed."""
+    cond, eps = gi.cvae_inputs()
+    x = gi.cvae_posterior_inputs()
+    mu, logvar = nets.cvae_encode(cvae_sd, x, cond)
+    _close(mu, gnets["cvae_enc_mu"], 1e-4, 2e-5)
+    _close(logvar, gnets["cvae_enc_logvar"], 1e-4, 2e-5)
+    out, _, (mu_pr, _) = nets.cvae_forward(cvae_sd, x, cond, eps)
+    _close(out, gnets["cvae_fwd"], 1e-4, 2e-5)
+    _close(mu_pr, gnets["cvae_mu"], 1e-4, 2e-5)
+
+
 def test_rotation_helpers(gkin):
     d = gi.kin_inputs()
     par = skeleton.BONE_PARENTS
