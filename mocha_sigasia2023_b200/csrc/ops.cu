@@ -652,7 +652,8 @@ instance_norm_tokens_reg_kernel(const float* __restrict__ x, int n, int C, float
 // float4 cover the channels, the 16 row slots of the block (2 per warp) stride over the tokens. Four times
 // fewer load / store instructions than the scalar kernels for the same bytes (which were request-bound at
 // 1.4 TB/s); same two-pass statistics.
-__global__ void __launch_bounds__(256)
+// (4 blocks per SM: at 80 registers only 3 fitted, and the 128-clip grid of 512 blocks ran as 1.15 waves)
+__global__ void __launch_bounds__(256, 4)
 instance_norm_tokens_v4_kernel(const float* __restrict__ x, int n, int C, float eps, const float* __restrict__ gb,
                                float* __restrict__ y, __nv_bfloat16* __restrict__ y16, __nv_bfloat16* __restrict__ q16,
                                const float* __restrict__ tab_mean = nullptr, const float* __restrict__ tab_std = nullptr,

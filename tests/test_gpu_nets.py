@@ -218,3 +218,28 @@ def test_cvae_posterior_surface(gold, precision, tol):
     assert rel_err(mu_po.cpu().numpy(), gold["cvae_enc_mu"]) < tol
     assert rel_err(mu_pr.cpu().numpy(), gold["cvae_mu"]) < tol
     assert rel_err(lv_pr.cpu().numpy(), gold["cvae_logvar"]) < tol
+
+
+def test_tf32x3_chunked_when_workspace_is_short(gold):
+    """MOCHA_TF32X3 with a workspace sized for the OTHER modes (no room for whole split operands): the linear layers run
+    as row chunks and the temporal convolutions as image chunks; results must not change."""
+    import ctypes as C
+    from mocha_sigasia2023_b200 import _lib
+    lib = _lib.load()
+    g = Generator(weights.DEFAULT_MODEL_CFG, precision="tf32x3")
+    g.load_state_dict(weights.generator_state_dict(1777), strict=True)
+    g = g.to("cuda").eval()
+    pk = g._pack()
+    src, cha = gi.pose_windows()
+    X = cu(np.concatenate([src, cha, src, cha], axis=0))           # 8 clips: several image chunks
+    B = X.shape[0]
+    nbytes = lib.mocha_embed_workspace_bytes(C.byref(pk.struct.dims), B)      # default (fp32 / bf16) sizing
+    with _lib.workspace_precision(_lib.MOCHA_TF32X3):
+        assert lib.mocha_embed_workspace_bytes(C.byref(pk.struct.dims), B) > 2 * nbytes
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    out = torch.empty((B, pk.ntok, pk.dims.D), dtype=torch.float32, device="cuda")
+    _lib.check(lib.mocha_embed_fwd(C.byref(pk.struct), _lib.ptr(X), B, _lib.ptr(out), 0, _lib.MOCHA_TF32X3, _lib.ptr(ws),
+                                   ws.numel(), _lib.stream_ptr()), "mocha_embed_fwd")
+    tok = out.cpu().numpy()
+    assert rel_err(tok[:2], gold["tokens"]) < RTOL_FP32
+    assert rel_err(tok[4:6], gold["tokens"]) < RTOL_FP32
