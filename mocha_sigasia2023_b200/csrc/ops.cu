@@ -1676,7 +1676,7 @@ graph_agg_kv_pad16_kernel(const float* __restrict__ in, const float* __restrict_
 // frame are re-read by its 6 node groups through L1 (they are 4.6 KB), nothing is staged or built per block, and every
 // store is an 8-byte piece of a coalesced 128-byte row segment. Geometry limits: Kk * U <= 24 adjacency terms per node.
 constexpr int GKP_TERMS = 24;
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)   // 5 blocks per SM: the 720-block grid of the 128-clip step runs as one wave
 graph_agg_kv_pad16_stream_kernel(const float* __restrict__ in, const float* __restrict__ A2, __nv_bfloat16* __restrict__ out16,
                                  long long total, int Ts, int tdiv, int pad, int U, int Wn, int C4, int Kk) {
   pdl_trigger();
