@@ -511,6 +511,89 @@ pool_graph_agg_kernel(const __nv_bfloat16* __restrict__ in, const float* __restr
   }
 }
 
+// Four channels per thread (8-byte loads): half the load / convert / FMA instructions of the bf162 kernel above for the same
+// bytes (that one was issue- and latency-bound at 0.5 of the HBM roof: 16.7 M warp instructions for 94 MB). A (b, t2) group
+// takes C / 4 threads; a block holds 128 / (C / 4) groups, so every warp still reads whole 256-byte row segments.
+__global__ void __launch_bounds__(128)
+pool_graph_agg_v4_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ Wp, const float* __restrict__ A,
+                         __nv_bfloat16* __restrict__ out16, int groups, int T, int V, int P, int C, int tp, int Kk) {
+  pdl_trigger();
+  extern __shared__ float ws[];
+  float* As = ws;                                   // [Kk][P][P] adjacency
+  float* mw = As + Kk * P * P;                      // [P][V] member weights of each body part (compact)
+  int* mv = reinterpret_cast<int*>(mw + P * V);     // [P][V] member joints
+  int* mc = mv + P * V;                             // [P]
+  for (int i = threadIdx.x; i < Kk * P * P; i += blockDim.x) As[i] = A[i];       // constants: before the grid dependency
+  if (threadIdx.x < P) {
+    const int p = threadIdx.x;
+    int n = 0;
+    for (int v = 0; v < V; ++v) {
+      const float wv = Wp[v * P + p];
+      if (wv != 0.f) { mw[p * V + n] = wv; mv[p * V + n] = v; ++n; }
+    }
+    mc[p] = n;
+  }
+  pdl_wait();
+  __syncthreads();
+  const int C4 = C / 4, gpb = blockDim.x / C4;
+  const int grp = blockIdx.x * gpb + threadIdx.x / C4, c4 = threadIdx.x % C4;
+  if (grp >= groups || threadIdx.x >= gpb * C4) return;
+  const int Tp = T / tp, b = grp / Tp, t2 = grp - b * Tp;
+  const float inv = 1.f / (float)tp;
+  const int KC = Kk * C;
+  const uint2* src = reinterpret_cast<const uint2*>(in + ((long long)(b * T + t2 * tp) * V) * C) + c4;   // row r at src[r * C4]
+  float a[POOL_MAXP][4];
+#pragma unroll
+  for (int p = 0; p < POOL_MAXP; ++p) {
+    a[p][0] = a[p][1] = a[p][2] = a[p][3] = 0.f;
+    if (p < P) {
+      const int n = mc[p];
+      for (int i = 0; i < n; ++i) {
+        const uint2* sj = src + (long long)mv[p * V + i] * C4;
+        const float wv = mw[p * V + i];
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        if (tp == 4) {
+          // four frames of one member joint = four independent 8-byte loads in flight
+          const long long fs = (long long)V * C4;
+          const uint2 x0 = __ldg(sj), x1 = __ldg(sj + fs), x2 = __ldg(sj + 2 * fs), x3 = __ldg(sj + 3 * fs);
+          s0 = (__uint_as_float(x0.x << 16) + __uint_as_float(x1.x << 16)) + (__uint_as_float(x2.x << 16) + __uint_as_float(x3.x << 16));
+          s1 = (__uint_as_float(x0.x & 0xffff0000u) + __uint_as_float(x1.x & 0xffff0000u)) +
+               (__uint_as_float(x2.x & 0xffff0000u) + __uint_as_float(x3.x & 0xffff0000u));
+          s2 = (__uint_as_float(x0.y << 16) + __uint_as_float(x1.y << 16)) + (__uint_as_float(x2.y << 16) + __uint_as_float(x3.y << 16));
+          s3 = (__uint_as_float(x0.y & 0xffff0000u) + __uint_as_float(x1.y & 0xffff0000u)) +
+               (__uint_as_float(x2.y & 0xffff0000u) + __uint_as_float(x3.y & 0xffff0000u));
+        } else {
+          for (int dt = 0; dt < tp; ++dt) {
+            const uint2 x = __ldg(sj + (long long)dt * V * C4);
+            s0 += __uint_as_float(x.x << 16); s1 += __uint_as_float(x.x & 0xffff0000u);
+            s2 += __uint_as_float(x.y << 16); s3 += __uint_as_float(x.y & 0xffff0000u);
+          }
+        }
+        a[p][0] = fmaf(s0, wv, a[p][0]); a[p][1] = fmaf(s1, wv, a[p][1]);
+        a[p][2] = fmaf(s2, wv, a[p][2]); a[p][3] = fmaf(s3, wv, a[p][3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a[p][j] = lrelu02(a[p][j] * inv);
+    }
+  }
+  __nv_bfloat16* dst = out16 + ((long long)grp * P) * KC + 4 * c4;
+  for (int k = 0; k < Kk; ++k)
+    for (int w = 0; w < P; ++w) {
+      float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+#pragma unroll
+      for (int u = 0; u < POOL_MAXP; ++u)
+        if (u < P) {
+          const float av = As[(k * P + u) * P + w];
+          o0 = fmaf(a[u][0], av, o0); o1 = fmaf(a[u][1], av, o1); o2 = fmaf(a[u][2], av, o2); o3 = fmaf(a[u][3], av, o3);
+        }
+      __nv_bfloat162 lo = __floats2bfloat162_rn(o0, o1), hi = __floats2bfloat162_rn(o2, o3);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(dst + (long long)w * KC + k * C) = pk;
+    }
+}
+
 // block = (batch b, group of 32 channels); lane = channel (coalesced 128 B rows), the 8 warps split the
 // tokens; two-pass mean / unbiased variance like torch.std, partials combined through shared memory.
 __global__ void __launch_bounds__(256)
@@ -1811,6 +1894,15 @@ int pool_graph_agg(const __nv_bfloat16* in, const float* Wp, const float* A, __n
   MOCHA_CHECK_ARG(P > 0 && P <= POOL_MAXP, "pool_graph_agg: P=%d unsupported (max %d)", P, POOL_MAXP);
   MOCHA_CHECK_ARG(tp > 0 && T % tp == 0, "pool_graph_agg: T=%d not a multiple of tp=%d", T, tp);
   const size_t smem = (size_t)(Kk * P * P + 2 * P * V + P) * sizeof(float);
+  static const bool no_v4 = getenv("MOCHA_NO_POOL_V4") != nullptr;   // A/B switch: the bf162 kernel below
+  if (!no_v4 && C % 4 == 0 && C / 4 <= 128 && 128 % (C / 4) == 0 && (reinterpret_cast<uintptr_t>(in) & 7) == 0 &&
+      (reinterpret_cast<uintptr_t>(out16) & 7) == 0) {
+    const int groups = B * (T / tp), gpb = 128 / (C / 4);
+    launch_k(pool_graph_agg_v4_kernel, (groups + gpb - 1) / gpb, 128, smem, s, in, Wp, A, out16, groups, T, V, P, C, tp, Kk);
+    count_launch();
+    MOCHA_LAUNCH_CHECK("pool_graph_agg_v4");
+    return MOCHA_OK;
+  }
   launch_k(pool_graph_agg_kernel, B * (T / tp), 128, smem, s, in, Wp, A, out16, T, V, P, C, tp, Kk);
   count_launch();
   MOCHA_LAUNCH_CHECK("pool_graph_agg");
