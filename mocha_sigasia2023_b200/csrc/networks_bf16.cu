@@ -30,6 +30,26 @@ struct Tc {
   }
 };
 
+// One side stream + fork / join events per host thread (created on first use; creating them is not a stream operation, so it
+// is legal while the caller's stream is being captured).
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+SideStream* side_stream() {
+  static thread_local SideStream ss;
+  static thread_local bool failed = false;
+  if (!ss.stream && !failed) {
+    if (cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess) {
+      failed = true;
+      (void)cudaGetLastError();
+    }
+  }
+  return failed ? nullptr : &ss;
+}
+
 inline TcOut f32(float* p) { return TcOut{p, nullptr, 0}; }
 inline TcOut h16(bf16* p, int lrelu = 0) { return TcOut{nullptr, p, lrelu}; }
 inline TcOut both(float* p, bf16* q) { return TcOut{p, q, 0}; }
@@ -196,23 +216,37 @@ int decoder_bf16(const mocha_generator_weights* w, const float* src, const float
   // AdaIN parameters of every layer depend on the style only: one launch for the token mean and all MLPs
   static const bool no_style_mlp = getenv("MOCHA_NO_STYLE_MLP") != nullptr;
   bool fused_style = !no_style_mlp && style_mlp_supported(d.D, d.dec_depth);
-  if (fused_style) {
-    const bf16 *w1[MOCHA_MAX_DEPTH], *w2[MOCHA_MAX_DEPTH];
-    const float *b1[MOCHA_MAX_DEPTH], *b2[MOCHA_MAX_DEPTH];
-    for (int l = 0; l < d.dec_depth && fused_style; ++l) {
-      MOCHA_CHECK_ARG(w->dec[l].sw1 && w->dec[l].sw2, "mocha_decoder_fwd: layer %d weights missing", l);
-      w1[l] = tc_lookup_bf16(w->dec[l].sw1); w2[l] = tc_lookup_bf16(w->dec[l].sw2);
-      b1[l] = w->dec[l].sb1; b2[l] = w->dec[l].sb2;
-      fused_style = w1[l] && w2[l];
-    }
-    if (fused_style) MOCHA_TRY(style_mlp(cha, B, n, d.D, d.dec_depth, w1, b1, w2, b2, gb_all, s));
+  const bf16 *w1[MOCHA_MAX_DEPTH], *w2[MOCHA_MAX_DEPTH];
+  const float *b1[MOCHA_MAX_DEPTH], *b2[MOCHA_MAX_DEPTH];
+  for (int l = 0; l < d.dec_depth && fused_style; ++l) {
+    MOCHA_CHECK_ARG(w->dec[l].sw1 && w->dec[l].sw2, "mocha_decoder_fwd: layer %d weights missing", l);
+    w1[l] = tc_lookup_bf16(w->dec[l].sw1); w2[l] = tc_lookup_bf16(w->dec[l].sw2);
+    b1[l] = w->dec[l].sb1; b2[l] = w->dec[l].sb2;
+    fused_style = w1[l] && w2[l];
   }
-  if (!fused_style) {
+  // The style MLP (128 blocks, L2-latency-bound) and the two token-wise passes over the style (instance norm, bf16 copy)
+  // are independent: the latter run on a side stream that forks from and joins the caller's stream through events, so the
+  // fork is captured into a CUDA graph like any other dependency. MOCHA_NO_DECODER_FORK=1 keeps one stream.
+  static const bool no_fork = getenv("MOCHA_NO_DECODER_FORK") != nullptr;
+  SideStream* side = (!no_fork && fused_style) ? side_stream() : nullptr;
+  cudaStream_t s2 = s;
+  if (side) {
+    MOCHA_CUDA(cudaEventRecord(side->fork, s));
+    MOCHA_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    s2 = side->stream;
+  }
+  if (fused_style) {
+    MOCHA_TRY(style_mlp(cha, B, n, d.D, d.dec_depth, w1, b1, w2, b2, gb_all, s));
+  } else {
     MOCHA_TRY(token_mean(cha, B, n, d.D, smean, s));
     MOCHA_TRY(tc_cast(smean, smean16, (long long)B * d.D, 0, s));
   }
-  MOCHA_TRY(instance_norm_tokens(cha, B, n, d.D, eps, nullptr, nullptr, nullptr, nullptr, nullptr, s, sty_in));
-  MOCHA_TRY(tc_cast(cha, cha16, (long long)R * d.D, 0, s));
+  MOCHA_TRY(instance_norm_tokens(cha, B, n, d.D, eps, nullptr, nullptr, nullptr, nullptr, nullptr, s2, sty_in));
+  MOCHA_TRY(tc_cast(cha, cha16, (long long)R * d.D, 0, s2));
+  if (side) {
+    MOCHA_CUDA(cudaEventRecord(side->join, side->stream));
+    MOCHA_CUDA(cudaStreamWaitEvent(s, side->join, 0));
+  }
   const float* x = src;
   for (int l = 0; l < d.dec_depth; ++l) {
     const mocha_dec_layer& L = w->dec[l];
