@@ -373,6 +373,7 @@ extern "C" size_t mocha_cvae_workspace_bytes(const mocha_cvae_weights* w, int B,
   bytes += pad256(Rx * w->dff * 4);        // hidden
   bytes += pad256(Rm * D * 4);             // memory
   bytes += pad256(Rm * 2 * D * 4);         // memory K|V
+  bytes += pad256(Rm * 2 * D * 2) * (MOCHA_MAX_DEPTH - 1);   // ... of the later decoder layers, projected ahead (bf16 path)
   bytes += pad256(Rq * D * 4) * 3;         // decoder x ping-pong + q
   bytes += tc_scratch_bytes(Rx, w->dff);
   bytes += tc_attention_scratch_bytes(B, w->heads, (int)np, (int)np, (int)(D / w->heads));

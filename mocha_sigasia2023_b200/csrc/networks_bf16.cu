@@ -340,6 +340,12 @@ int cvae_bf16(const mocha_cvae_weights* w, const float* cond, int B, int ncond, 
   bf16* hid = ws.take<bf16>((size_t)Rp * w->dff);
   bf16* mem = ws.take<bf16>((size_t)Rm * D);
   bf16* memkv = ws.take<bf16>((size_t)Rm * 2 * D);
+  // memory K | V of the decoder layers after the first depend on `mem` only: they are projected on a side stream while
+  // layer 0 runs (its 90-CTA block tails leave 58 SMs idle) - MOCHA_NO_CVAE_FORK=1 keeps them in line
+  static const bool no_cvae_fork = getenv("MOCHA_NO_CVAE_FORK") != nullptr;
+  bf16* memkv_ahead[MOCHA_MAX_DEPTH] = {nullptr, nullptr, nullptr, nullptr};
+  if (!no_cvae_fork)
+    for (int l = 1; l < w->depth; ++l) memkv_ahead[l] = ws.take<bf16>((size_t)Rm * 2 * D);
   bf16* dq = ws.take<bf16>((size_t)Rq * D);
   WS_OK(ws, "mocha_cvae_sample(bf16)");
 
@@ -409,6 +415,20 @@ int cvae_bf16(const mocha_cvae_weights* w, const float* cond, int B, int ncond, 
     }
   }
   MOCHA_TRY(cvae_memory(x, prior_rows, eps, cond, nullptr, mu, logvar, B, ncond, D, s, mem));
+  SideStream* side = (!no_cvae_fork && w->depth > 1) ? side_stream() : nullptr;
+  bool ahead_pending = false;
+  if (side) {
+    MOCHA_CUDA(cudaEventRecord(side->fork, s));
+    MOCHA_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    Tc tc2{side->stream, ws};
+    for (int l = 1; l < w->depth; ++l) {
+      const mocha_cvae_dec_layer& L = w->dec[l];
+      MOCHA_CHECK_ARG(L.ca_in_w && L.ca_in_b, "mocha_cvae_sample: decoder layer %d weights missing", l);
+      MOCHA_TRY(tc2.lin(mem, D, L.ca_in_w + (size_t)D * D, L.ca_in_b + D, 0, nullptr, h16(memkv_ahead[l]), Rm, 2 * D, D, ACT_NONE));
+    }
+    MOCHA_CUDA(cudaEventRecord(side->join, side->stream));
+    ahead_pending = true;
+  }
 
   // ---- decoder (query rows reuse the prior's buffers: Rq <= Rp) ----
   float* dx = xa; bf16* dx16 = xa16;
@@ -449,8 +469,14 @@ int cvae_bf16(const mocha_cvae_weights* w, const float* cond, int B, int ncond, 
       }
     }
     MOCHA_TRY(tc.lin(dy16, D, L.ca_in_w, L.ca_in_b, 0, nullptr, h16(dq), Rq, D, D, ACT_NONE));
-    MOCHA_TRY(tc.lin(mem, D, L.ca_in_w + (size_t)D * D, L.ca_in_b + D, 0, nullptr, h16(memkv), Rm, 2 * D, D, ACT_NONE));
-    MOCHA_TRY(attn(s, ws, dq, D, memkv, 2 * D, memkv + D, 2 * D, B, H, nq, nm, dh, att, D));
+    const bf16* mkv = memkv;
+    if (side && l >= 1) {
+      if (ahead_pending) { MOCHA_CUDA(cudaStreamWaitEvent(s, side->join, 0)); ahead_pending = false; }
+      mkv = memkv_ahead[l];
+    } else {
+      MOCHA_TRY(tc.lin(mem, D, L.ca_in_w + (size_t)D * D, L.ca_in_b + D, 0, nullptr, h16(memkv), Rm, 2 * D, D, ACT_NONE));
+    }
+    MOCHA_TRY(attn(s, ws, dq, D, mkv, 2 * D, mkv + D, 2 * D, B, H, nq, nm, dh, att, D));
     }
     if (fused) {
       // cross-attention out-projection + LN2 + ReLU FFN (+ LN3 unless the de-normalising last LayerNorm follows)
@@ -476,6 +502,7 @@ int cvae_bf16(const mocha_cvae_weights* w, const float* cond, int B, int ncond, 
       bf16* t16 = dx16; dx16 = dy16; dy16 = t16;
     }
   }
+  if (side && ahead_pending) MOCHA_CUDA(cudaStreamWaitEvent(s, side->join, 0));
   return MOCHA_OK;
 }
 
