@@ -229,6 +229,7 @@ extern "C" size_t mocha_decoder_workspace_bytes(const mocha_dims* d, int B) {
   bytes += pad256((size_t)B * 2 * d->D * 4) * (1 + MOCHA_MAX_DEPTH);   // style hidden, gamma|beta of every layer
   bytes += pad256(R * d->D * 4) * 5;               // sty_in, x1, qin, x2, xb
   bytes += pad256(R * inner * 4) * 4;              // q, k, v, att
+  bytes += pad256(R * inner * 2) * 2 * (MOCHA_MAX_DEPTH - 1);   // k | v of the later layers, projected ahead (bf16 path)
   bytes += pad256((size_t)B * d->heads * n * n * 4);
   bytes += pad256(R * d->mlp * 4);
   bytes += tc_scratch_bytes(R, inner > (size_t)d->mlp ? inner : d->mlp);

@@ -35,6 +35,7 @@ struct Tc {
 struct SideStream {
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t ev[MOCHA_MAX_DEPTH] = {nullptr, nullptr, nullptr, nullptr};   // per-layer "ready" marks of side work
 };
 SideStream* side_stream() {
   static thread_local SideStream ss;
@@ -46,6 +47,8 @@ SideStream* side_stream() {
       failed = true;
       (void)cudaGetLastError();
     }
+    for (int i = 0; i < MOCHA_MAX_DEPTH && !failed; ++i)
+      if (cudaEventCreateWithFlags(&ss.ev[i], cudaEventDisableTiming) != cudaSuccess) { failed = true; (void)cudaGetLastError(); }
   }
   return failed ? nullptr : &ss;
 }
@@ -243,7 +246,37 @@ int decoder_bf16(const mocha_generator_weights* w, const float* src, const float
   }
   MOCHA_TRY(instance_norm_tokens(cha, B, n, d.D, eps, nullptr, nullptr, nullptr, nullptr, nullptr, s2, sty_in));
   MOCHA_TRY(tc_cast(cha, cha16, (long long)R * d.D, 0, s2));
-  if (side) {
+  // Keys and values of every layer are functions of the style only (k = to_k(IN(style)), v = to_v(style)), so the later
+  // layers' projections CAN run on the side stream while layer 0 is busy. Measured negative (same-box A/B at 128 clips:
+  // +4.5 us with layer 1 ahead, +6 us with both layers ahead): a second 148-CTA persistent GEMM competes with the
+  // critical path's GEMMs for whole SMs instead of filling the block tails' idle ones. Opt-in: MOCHA_DECODER_KV_AHEAD=1.
+  static const bool want_kv_ahead = getenv("MOCHA_DECODER_KV_AHEAD") != nullptr;
+  bool kv_ahead = side != nullptr && want_kv_ahead && inner % 64 == 0;
+  for (int l = 0; l < d.dec_depth && kv_ahead; ++l) {
+    const mocha_dec_layer& L = w->dec[l];
+    kv_ahead = L.wq && L.wk && L.wv && L.wk == L.wq + (size_t)inner * d.D && L.wv == L.wk + (size_t)inner * d.D &&
+               tc_lookup_bf16(L.wk) != nullptr;
+  }
+  bf16* kv_l[MOCHA_MAX_DEPTH] = {nullptr, nullptr, nullptr, nullptr};
+  if (kv_ahead) {
+    const size_t mark = ws.off;
+    for (int l = 0; l < d.dec_depth; ++l) {
+      kv_l[l] = l == 0 ? k : ws.take<bf16>((size_t)2 * R * inner);     // layer 0 uses the k | v part of qkv3
+      if (!kv_l[l]) { kv_ahead = false; break; }
+    }
+    if (!kv_ahead) { ws.off = mark; ws.overflow = false; }   // no room: fall back to the in-line grouped projection
+  }
+  if (kv_ahead) {
+    // layer 0 keeps its grouped q / k / v launch on the main stream (projecting its k / v on the side stream as well put two
+    // 148-CTA GEMMs in competition right on the critical path: +6 us); ev[0] marks the style operands as ready
+    MOCHA_CUDA(cudaEventRecord(side->ev[0], side->stream));
+    for (int l = 1; l < d.dec_depth; ++l) {
+      MOCHA_TRY(tc_linear_bf16_grouped(sty_in, tc_lookup_bf16(w->dec[l].wk), kv_l[l], 2, R, inner, d.D, s2));
+      MOCHA_CUDA(cudaEventRecord(side->ev[l], side->stream));
+    }
+    if (d.dec_depth == 1) kv_ahead = false;   // nothing to project ahead: plain fork / join
+    MOCHA_CUDA(cudaStreamWaitEvent(s, side->ev[0], 0));
+  } else if (side) {
     MOCHA_CUDA(cudaEventRecord(side->join, side->stream));
     MOCHA_CUDA(cudaStreamWaitEvent(s, side->join, 0));
   }
@@ -265,7 +298,13 @@ int decoder_bf16(const mocha_generator_weights* w, const float* src, const float
     }
     static const bool no_group = getenv("MOCHA_NO_GROUPED_QKV") != nullptr;
     const bf16* wq16 = tc_lookup_bf16(L.wq);
-    if (!no_group && wq16 && L.wk == L.wq + (size_t)inner * d.D && L.wv == L.wk + (size_t)inner * d.D && inner % 64 == 0) {
+    const bf16 *kk = k, *vv = v;
+    if (kv_ahead && l >= 1) {
+      MOCHA_TRY(tc.lin(qin, d.D, L.wq, nullptr, 0, nullptr, h16(q), R, inner, d.D, ACT_NONE));
+      MOCHA_CUDA(cudaStreamWaitEvent(s, side->ev[l], 0));
+      kk = kv_l[l];
+      vv = kv_l[l] + (size_t)R * inner;
+    } else if (!no_group && wq16 && L.wk == L.wq + (size_t)inner * d.D && L.wv == L.wk + (size_t)inner * d.D && inner % 64 == 0) {
       // to_q / to_k / to_v sit back to back in the packed blob: three inputs x three weights in one launch
       MOCHA_TRY(tc_linear_bf16_grouped(in3, wq16, qkv3, 3, R, inner, d.D, s));
     } else {
@@ -273,7 +312,7 @@ int decoder_bf16(const mocha_generator_weights* w, const float* src, const float
       MOCHA_TRY(tc.lin(sty_in, d.D, L.wk, nullptr, 0, nullptr, h16(k), R, inner, d.D, ACT_NONE));
       MOCHA_TRY(tc.lin(cha16, d.D, L.wv, nullptr, 0, nullptr, h16(v), R, inner, d.D, ACT_NONE));
     }
-    MOCHA_TRY(attn(s, ws, q, inner, k, inner, v, inner, B, d.heads, n, n, d.dec_dh, att, inner));
+    MOCHA_TRY(attn(s, ws, q, inner, kk, inner, vv, inner, B, d.heads, n, n, d.dec_dh, att, inner));
     float* dst = (l == d.dec_depth - 1) ? decoded : xb;
     if (use_fused_tail(d.D) && tc_tail_supported(R, inner, d.mlp)) {
       MOCHA_TRY(tail(s, att, inner, L.wo, L.bo, x1, nullptr, nullptr, d.mlp, ACT_GELU, L.w1, L.b1, L.w2, L.b2, nullptr, nullptr,
