@@ -38,19 +38,24 @@ struct SideStream {
   cudaEvent_t ev[MOCHA_MAX_DEPTH] = {nullptr, nullptr, nullptr, nullptr};   // per-layer "ready" marks of side work
 };
 SideStream* side_stream() {
-  static thread_local SideStream ss;
-  static thread_local bool failed = false;
-  if (!ss.stream && !failed) {
-    if (cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess) {
-      failed = true;
+  // one set per (host thread, device): a stream belongs to the device that was current when it was created
+  constexpr int MAXDEV = 16;
+  static thread_local SideStream per_dev[MAXDEV];
+  static thread_local bool failed[MAXDEV] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAXDEV) return nullptr;
+  SideStream& ss = per_dev[dev];
+  if (!ss.stream && !failed[dev]) {
+    bool ok = cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < MOCHA_MAX_DEPTH && ok; ++i) ok = cudaEventCreateWithFlags(&ss.ev[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      failed[dev] = true;
       (void)cudaGetLastError();
     }
-    for (int i = 0; i < MOCHA_MAX_DEPTH && !failed; ++i)
-      if (cudaEventCreateWithFlags(&ss.ev[i], cudaEventDisableTiming) != cudaSuccess) { failed = true; (void)cudaGetLastError(); }
   }
-  return failed ? nullptr : &ss;
+  return failed[dev] ? nullptr : &ss;
 }
 
 inline TcOut f32(float* p) { return TcOut{p, nullptr, 0}; }
