@@ -1,11 +1,13 @@
 // tcgen05 / TMEM / TMA GEMM family for sm_100a (see gemm_tc.cuh).
 //
-// Kernel anatomy (one persistent CTA per SM, 320 threads):
+// Kernel anatomy (one persistent CTA per SM, 384 threads in three warpgroups; setmaxnreg moves registers from the
+// producer group, 88 per thread, to the epilogue groups, 208 per thread, so the epilogue does not spill):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2D tiles (128B swizzle) into a STAGES-deep ring
 //   warp 1      MMA issuer:   one elected thread issues tcgen05.mma.cta_group::1.kind::f16
 //               (M=128, N=BN, K=16) x4 per 64-wide k-block; tcgen05.commit frees ring slots and
 //               publishes finished accumulators; also owns tcgen05.alloc / dealloc
-//   warps 2..9  epilogue: tcgen05.ld 32x32b (lane = output row) from one of two TMEM accumulator
+//   warps 2, 3  idle (they complete the producer warpgroup)
+//   warps 4..11 epilogue: tcgen05.ld 32x32b (lane = output row) from one of two TMEM accumulator
 //               buffers, so the epilogue of tile i overlaps the main loop of tile i+1
 // Operands are K-major bf16: A tile 128 x 64, B tile BN x 64, both landing in the canonical
 // SWIZZLE_128B layout the UMMA shared-memory descriptors describe (8-row groups 1024 B apart).
@@ -26,7 +28,17 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle atom row
 constexpr int UMMA_K = 16;
-constexpr int TC_THREADS = 64 + 8 * 32;  // TMA warp, MMA warp, 8 epilogue warps
+// Warp roles. Ten warps put three warps on one scheduler partition (16 K registers each), which caps every thread at
+// 168 registers and made the epilogue spill. Default: twelve warps in three warpgroups - warps 0-3 are the producer
+// group (TMA warp, MMA warp, two idle warps) and shrink to TC_REGS_PRODUCER with setmaxnreg, warps 4-11 (the epilogue)
+// grow to TC_REGS_EPI. -DMOCHA_TC_TEN_WARPS restores the ten-warp layout.
+#ifdef MOCHA_TC_TEN_WARPS
+constexpr int TC_EPI_WARP0 = 2;
+#else
+constexpr int TC_EPI_WARP0 = 4;
+#endif
+constexpr int TC_THREADS = TC_EPI_WARP0 * 32 + 8 * 32;
+constexpr int TC_REGS_PRODUCER = 88, TC_REGS_EPI = 208;   // 4 x 88 + 8 x 208 = 2016 = the 12 x 168 registers per lane slot the launch allocates
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 
 // ------------------------------------------------------------------------------------------------
@@ -449,7 +461,7 @@ struct LinearEpiT : LinearEpiData {
     const uint32_t sbase0 = e.stage + (uint32_t)((rr * EPI_LD + cc) * 4);
     float4 bc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (bias && bias_period == 0) bc = __ldg(reinterpret_cast<const float4*>(bias + c));
-    // two half-chunks of 4 passes (16 rows) keep the live set under the 168-register cap of a 320-thread CTA
+    // two half-chunks of 4 passes (16 rows): written for the 168-register cap of the ten-warp layout, kept as is
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const long long base = e.c_off + (e.slab_row0 + rr + 16 * h) * (long long)ldc + c;
@@ -1059,6 +1071,20 @@ struct TcSmem {
   static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
 };
 
+
+// Register re-partition between the producer warpgroup and the two epilogue warpgroups (see TC_EPI_WARP0): warpgroup-
+// uniform, executed by every warp of the CTA once the prologue is done.
+__device__ __forceinline__ void tc_regs_producer() {
+#ifndef MOCHA_TC_TEN_WARPS
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_PRODUCER));
+#endif
+}
+__device__ __forceinline__ void tc_regs_epilogue() {
+#ifndef MOCHA_TC_TEN_WARPS
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_EPI));
+#endif
+}
+
 template <int BN, class Epi>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -1107,6 +1133,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   int trace_tile = 0;
 #endif
 
+  if (warp < TC_EPI_WARP0) {
+  tc_regs_producer();
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -1221,16 +1249,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+  }
   } else {
-    // ===================== epilogue (warps 2..9) =====================
+    tc_regs_epilogue();
+    // ===================== epilogue (the last eight warps) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     int as = 0; uint32_t aphase = 0;
     typename Epi::State st;
     EpiCtx ectx;
-    ectx.stage = smem_u32(epi_stage + (warp - 2) * Epi::kWarpStageBytes);
-    ectx.res_bar = smem_u32(&res_bar[warp - 2]);
+    ectx.stage = smem_u32(epi_stage + (warp - TC_EPI_WARP0) * Epi::kWarpStageBytes);
+    ectx.res_bar = smem_u32(&res_bar[warp - TC_EPI_WARP0]);
     ectx.bias_smem = smem_u32(epi_stage + EPI_WARPS * Epi::kWarpStageBytes);
-    ectx.etid = (int)threadIdx.x - 64;
+    ectx.etid = (int)threadIdx.x - TC_EPI_WARP0 * 32;
     ectx.lane = lane;
     epi.kernel_begin(st, ectx);
     // Tile bookkeeping off the critical path: the unit -> (m tile, split, image) decode is ~200 dependent
@@ -1268,7 +1298,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ectx.img = b;
       ectx.row0_in_img = mtb * BLOCK_M + q * 32;
       ectx.lane = lane;
-      ectx.half = (warp - 2) >> 2;
+      ectx.half = (warp - TC_EPI_WARP0) >> 2;
       ectx.slab_row0 = (long long)b * sh.rows_out_per_b + mtb * BLOCK_M + q * 32;
       ectx.slab_rows = max(0, min(32, sh.rows_out_per_b - (mtb * BLOCK_M + q * 32)));
       ectx.c_off = 0;
@@ -1286,16 +1316,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr int kSplitCol = ((BN / 32 + 1) / 2) * 32;
         const int c_begin = ectx.half == 0 ? 0 : kSplitCol, c_end = ectx.half == 0 ? kSplitCol : BN;
 #ifdef MOCHA_TRACE
-        if (warp == 2 && lane == 0 && trace_tile == 1) TC_TRACE(29, (unsigned long long)clock64());
+        if (warp == TC_EPI_WARP0 && lane == 0 && trace_tile == 1) TC_TRACE(29, (unsigned long long)clock64());
 #endif
         if (c_begin < c_end) epi.tile_begin(st, ectx, nt * BN + c_begin, c_end - c_begin);  // overlaps the main loop
 #ifdef MOCHA_TRACE
-        if (warp == 2 && lane == 0 && trace_tile == 1) TC_TRACE(30, (unsigned long long)clock64());
+        if (warp == TC_EPI_WARP0 && lane == 0 && trace_tile == 1) TC_TRACE(30, (unsigned long long)clock64());
 #endif
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
 #ifdef MOCHA_TRACE
-        if (warp == 2 && lane == 0) TC_TRACE(16 + trace_tile, (unsigned long long)clock64());  // accumulator ready
+        if (warp == TC_EPI_WARP0 && lane == 0) TC_TRACE(16 + trace_tile, (unsigned long long)clock64());  // accumulator ready
 #endif
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
         if constexpr (Epi::kWholeTile) epi.tile(st, ectx, taddr, as);
@@ -1309,12 +1339,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint32_t v[32];
           tmem_ld32(taddr + (uint32_t)c0, v);
 #ifdef MOCHA_TRACE
-          if (warp == 2 && lane == 0 && trace_tile == 0 && c0 == c_begin) TC_TRACE(26, (unsigned long long)clock64());
+          if (warp == TC_EPI_WARP0 && lane == 0 && trace_tile == 0 && c0 == c_begin) TC_TRACE(26, (unsigned long long)clock64());
 #endif
           epi.chunk(st, ectx, row, row_ok, nt * BN + c0, v, c0 + 32 < c_end ? nt * BN + c0 + 32 : -1);
 #ifdef MOCHA_TRACE
-          if (warp == 2 && lane == 0 && trace_tile == 0 && c0 == c_begin) TC_TRACE(27, (unsigned long long)clock64());
-          if (warp == 2 && lane == 0 && trace_tile == 0 && c0 == c_begin + 32) TC_TRACE(28, (unsigned long long)clock64());
+          if (warp == TC_EPI_WARP0 && lane == 0 && trace_tile == 0 && c0 == c_begin) TC_TRACE(27, (unsigned long long)clock64());
+          if (warp == TC_EPI_WARP0 && lane == 0 && trace_tile == 0 && c0 == c_begin + 32) TC_TRACE(28, (unsigned long long)clock64());
 #endif
         }
         tc_fence_before();
@@ -1322,7 +1352,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) mbar_arrive(&tempty_bar[as]);
         if (++as == 2) { as = 0; aphase ^= 1; }
 #ifdef MOCHA_TRACE
-        if (warp == 2 && lane == 0) TC_TRACE(20 + trace_tile, (unsigned long long)clock64());  // tile drained
+        if (warp == TC_EPI_WARP0 && lane == 0) TC_TRACE(20 + trace_tile, (unsigned long long)clock64());  // tile drained
         if (trace_tile < 3) ++trace_tile;
 #endif
       }
@@ -1464,6 +1494,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (threadIdx.x == 0) TC_TRACE(2, (unsigned long long)clock64());
 #endif
 
+  if (warp < TC_EPI_WARP0) {
+  tc_regs_producer();
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
@@ -1532,17 +1564,19 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     }
+  }
   } else {
-    // ===================== epilogue (warps 2..9 of both CTAs) =====================
+    tc_regs_epilogue();
+    // ===================== epilogue (the last eight warps of both CTAs) =====================
     const int q = warp & 3;
     int as = 0; uint32_t aphase = 0;
     typename Epi::State st;
     EpiCtx ectx;
-    ectx.stage = smem_u32(epi_stage + (warp - 2) * Epi::kWarpStageBytes);
-    ectx.res_bar = smem_u32(&res_bar[warp - 2]);
+    ectx.stage = smem_u32(epi_stage + (warp - TC_EPI_WARP0) * Epi::kWarpStageBytes);
+    ectx.res_bar = smem_u32(&res_bar[warp - TC_EPI_WARP0]);
     ectx.bias_smem = smem_u32(epi_stage + EPI_WARPS * Epi::kWarpStageBytes);
-    ectx.etid = (int)threadIdx.x - 64;
-    ectx.lane = lane; ectx.half = (warp - 2) >> 2; ectx.c_off = 0; ectx.col_off = 0;
+    ectx.etid = (int)threadIdx.x - TC_EPI_WARP0 * 32;
+    ectx.lane = lane; ectx.half = (warp - TC_EPI_WARP0) >> 2; ectx.c_off = 0; ectx.col_off = 0;
     epi.kernel_begin(st, ectx);
     // lane i decodes the cluster's i-th unit up front (see tc_gemm_kernel); tiles fetch it with shuffles
     int pre_mt = 0, pre_split = 0, pre_b = 0;
@@ -1579,7 +1613,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
 #ifdef MOCHA_TRACE
-        if (warp == 2 && lane == 0) TC_TRACE(16 + trace_tile, (unsigned long long)clock64());
+        if (warp == TC_EPI_WARP0 && lane == 0) TC_TRACE(16 + trace_tile, (unsigned long long)clock64());
 #endif
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
@@ -1593,7 +1627,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (lane == 0) mbar_arrive_remote(&tempty_bar[as], 0);
         if (++as == 2) { as = 0; aphase ^= 1; }
 #ifdef MOCHA_TRACE
-        if (warp == 2 && lane == 0) TC_TRACE(20 + trace_tile, (unsigned long long)clock64());
+        if (warp == TC_EPI_WARP0 && lane == 0) TC_TRACE(20 + trace_tile, (unsigned long long)clock64());
         if (trace_tile < 3) ++trace_tile;
 #endif
       }
