@@ -545,6 +545,213 @@ post_frame_kernel(const mocha_post_params P, const float* __restrict__ Y,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Steady-state frame (init == 0) of the same post-process, shaped for latency: the kernel above walks its phases through
+// the clip's structs in GLOBAL memory (every phase boundary is an L2 round trip, the chain walk indexes local arrays), which
+// made it a 20 us tail on a step whose last kernel it is. Here one single-warp block per clip (clips spread over the SMs)
+// fetches everything the frame reads - state struct, last pose row, hips velocities, source root motion, contacts - in ONE
+// round of independent loads, runs the phases on shared-memory copies of the two structs (same expressions, same order:
+// fp64 results as above), and writes both structs back with 16-byte stores. The ancestor chains of the two contact bones
+// depend only on the parameters and are built before the grid dependency resolves.
+// ------------------------------------------------------------------------------------------------
+static_assert(sizeof(mocha_clip_state) % 16 == 0 && sizeof(mocha_frame_out) % 16 == 0, "struct copies use 16-byte vectors");
+constexpr int PF_S16 = (int)(sizeof(mocha_clip_state) / 16), PF_O16 = (int)(sizeof(mocha_frame_out) / 16);
+constexpr int PF_YMAX = 24 * 15;   // last pose row: V <= 24 joints x 15 features
+
+__global__ void __launch_bounds__(32)
+post_frame_step_kernel(const __grid_constant__ mocha_post_params P, const float* __restrict__ Y,
+                       const float* __restrict__ src_hips_vel, const float* __restrict__ src_rvel,
+                       const float* __restrict__ src_rang, const uint8_t* __restrict__ contacts, int T, int V, int Cin,
+                       mocha_clip_state* __restrict__ states, mocha_frame_out* __restrict__ outs, int hv_stride,
+                       int rv_stride) {
+  pdl_trigger();
+  __shared__ __align__(16) mocha_frame_out Osh;
+  __shared__ __align__(16) mocha_clip_state Ssh;
+  __shared__ float ylast[PF_YMAX];
+  __shared__ int chain_s[2][MAXJ];
+  __shared__ int chain_n[2];
+  const int b = blockIdx.x, lane = threadIdx.x;
+  mocha_clip_state& S = Ssh;
+  mocha_frame_out& O = Osh;
+  const int J = P.J;
+  const double dt = P.dt;
+  // ---- before the grid dependency: parameters only ----
+  for (int i = lane; i < PF_O16; i += 32) reinterpret_cast<double2*>(&Osh)[i] = make_double2(0.0, 0.0);
+  if (lane < 2) {
+    int n = 0;
+    for (int j = P.contact_bones[lane]; j >= 0; j = P.parents[j]) chain_s[lane][n++] = j;
+    chain_n[lane] = n;
+  }
+  pdl_wait();
+
+  // ---- every global read of the frame, issued back to back ----
+  const float* Yb = Y + (long long)b * T * V * Cin;
+  const float* last = Yb + (long long)(T - 1) * V * Cin;
+  const int nlast = V * Cin;
+  const double2* Sg = reinterpret_cast<const double2*>(states + b);
+  double2 sreg[(PF_S16 + 31) / 32];
+#pragma unroll
+  for (int k = 0; k < (PF_S16 + 31) / 32; ++k) {
+    const int i = lane + 32 * k;
+    sreg[k] = i < PF_S16 ? Sg[i] : make_double2(0.0, 0.0);
+  }
+  float yreg[(PF_YMAX + 31) / 32];
+#pragma unroll
+  for (int k = 0; k < (PF_YMAX + 31) / 32; ++k) {
+    const int i = lane + 32 * k;
+    yreg[k] = i < nlast ? last[i] : 0.f;
+  }
+  float yv[2][3], sv[2][3];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int t = lane + 32 * k;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      yv[k][c] = t < T ? Yb[((long long)t * V + 0) * Cin + 9 + c] : 0.f;
+      sv[k][c] = t < T ? src_hips_vel[(long long)b * hv_stride + t * 3 + c] : 0.f;
+    }
+  }
+  float rvf[3], raf[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { rvf[c] = src_rvel[(long long)b * rv_stride + c]; raf[c] = src_rang[(long long)b * rv_stride + c]; }
+  const bool contact_in = lane < 2 ? contacts[b * 2 + lane] != 0 : false;
+
+#pragma unroll
+  for (int k = 0; k < (PF_S16 + 31) / 32; ++k) {
+    const int i = lane + 32 * k;
+    if (i < PF_S16) reinterpret_cast<double2*>(&Ssh)[i] = sreg[k];
+  }
+#pragma unroll
+  for (int k = 0; k < (PF_YMAX + 31) / 32; ++k) {
+    const int i = lane + 32 * k;
+    if (i < nlast) ylast[i] = yreg[k];
+  }
+
+  // speed ratio (test_fullframework.py:492-496): mean |hips vel| over the window, fp32 like NumPy
+  float num = 0.f, den = 0.f;
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+    if (lane + 32 * k < T) {
+      num += sqrtf(yv[k][0] * yv[k][0] + yv[k][1] * yv[k][1] + yv[k][2] * yv[k][2]);
+      den += sqrtf(sv[k][0] * sv[k][0] + sv[k][1] * sv[k][1] + sv[k][2] * sv[k][2]);
+    }
+  for (int t = lane + 64; t < T; t += 32) {   // windows longer than 64 frames
+    const float* y3 = Yb + ((long long)t * V + 0) * Cin + 9;
+    num += sqrtf(y3[0] * y3[0] + y3[1] * y3[1] + y3[2] * y3[2]);
+    const float* s3 = src_hips_vel + (long long)b * hv_stride + t * 3;
+    den += sqrtf(s3[0] * s3[0] + s3[1] * s3[1] + s3[2] * s3[2]);
+  }
+  num = warp_sum(num);
+  den = warp_sum(den);
+  float ratio = (num / (float)T) / (den / (float)T);
+  if (ratio > 3.0f || ratio < 0.33f) ratio = 1.0f;
+  __syncwarp();   // state struct and pose row are in shared memory
+
+  DQ rootrot = q4<double>(1.0, 0.0, 0.0, 0.0);
+  if (lane == 0) {
+    // root integration (:500-503)
+    const D3 yrvel = v3<double>((double)(rvf[0] * ratio), (double)(rvf[1] * ratio), (double)(rvf[2] * ratio));
+    const D3 yrang = v3<double>((double)raf[0], (double)raf[1], (double)raf[2]);
+    const DQ prev_rot = ld4(S.root_rot);
+    const D3 prev_pos = ld3(S.root_pos);
+    const D3 rootvel = qrot(prev_rot, yrvel);
+    const D3 rootang = qrot(prev_rot, yrang);
+    const D3 rootpos = prev_pos + dt * rootvel;
+    rootrot = qmul(prev_rot, q_from_scaled_angle_axis(dt * rootang));
+    st3(O.pos[0], rootpos); st3(O.vel[0], rootvel); st4(O.rot[0], rootrot); st3(O.ang[0], rootang);
+  } else if (lane == 1) {
+    // source root (:476-483): float32 arrays in the reference, so fp32 integration
+    const V3<float> rv = v3<float>(rvf[0], rvf[1], rvf[2]);
+    const V3<float> ra = v3<float>(raf[0], raf[1], raf[2]);
+    const Q4<float> pr = q4<float>((float)S.src_root_rot[0], (float)S.src_root_rot[1], (float)S.src_root_rot[2],
+                                   (float)S.src_root_rot[3]);
+    const V3<float> pp = v3<float>((float)S.src_root_pos[0], (float)S.src_root_pos[1], (float)S.src_root_pos[2]);
+    const float dtf = (float)dt;
+    const V3<float> wv = qrot(pr, rv), wa = qrot(pr, ra);
+    const V3<float> np_ = pp + dtf * wv;
+    const Q4<float> nr = qmul(pr, q_from_scaled_angle_axis(dtf * wa));
+    st3(O.src_root_vel, v3<double>((double)wv.x, (double)wv.y, (double)wv.z));
+    st3(O.src_root_ang, v3<double>((double)wa.x, (double)wa.y, (double)wa.z));
+    st3(O.src_root_pos, v3<double>((double)np_.x, (double)np_.y, (double)np_.z));
+    st4(O.src_root_rot, q4<double>((double)nr.w, (double)nr.x, (double)nr.y, (double)nr.z));
+    for (int c = 0; c < 3; ++c) S.src_root_pos[c] = O.src_root_pos[c];
+    for (int c = 0; c < 4; ++c) S.src_root_rot[c] = O.src_root_rot[c];
+  }
+  // assemble the pose (:505-508); lane = joint
+  for (int j = lane; j < V; j += 32) {
+    const float* y = ylast + j * Cin;
+    O.pos[j + 1][0] = (double)y[0]; O.pos[j + 1][1] = (double)y[1]; O.pos[j + 1][2] = (double)y[2];
+    const Q4<float> q = q_from_xy(v3<float>(y[3], y[5], y[7]), v3<float>(y[4], y[6], y[8]));
+    O.rot[j + 1][0] = (double)q.w; O.rot[j + 1][1] = (double)q.x; O.rot[j + 1][2] = (double)q.y; O.rot[j + 1][3] = (double)q.z;
+    O.vel[j + 1][0] = (double)y[9]; O.vel[j + 1][1] = (double)y[10]; O.vel[j + 1][2] = (double)y[11];
+    O.ang[j + 1][0] = (double)y[12]; O.ang[j + 1][1] = (double)y[13]; O.ang[j + 1][2] = (double)y[14];
+  }
+  __syncwarp();
+
+  // position blending (:532-536, :626); lane = bone
+  for (int j = lane; j < J; j += 32) {
+    for (int c = 0; c < 3; ++c) {
+      O.ik_pos[j][c] = (S.prev_ik_pos[j][c] + O.vel[j][c] * dt) * 0.5 + O.pos[j][c] * 0.5;
+      O.blend_pos[j][c] = (S.prev_pos[j][c] + O.vel[j][c] * dt) * 0.5 + O.pos[j][c] * 0.5;
+    }
+    for (int c = 0; c < 4; ++c) O.ik_rot[j][c] = O.rot[j][c];
+  }
+  __syncwarp();
+
+  if (P.ik_enabled && lane < 2) {
+    const int f = lane;
+    const int* ch = chain_s[f];
+    const int n = chain_n[f];
+    const int toe = ch[0], heel = ch[1], knee = ch[2], hip = ch[3];
+    // quat.fk_partial (motion/quat.py:241-272) down the toe's ancestor chain on the blended pose: a running transform
+    // from the top of the chain to the hip's parent, then the four bones the IK step needs by name
+    D3 gp = ld3(O.ik_pos[ch[n - 1]]);
+    DQ gr = ld4(O.rot[ch[n - 1]]);
+    for (int k = n - 2; k >= 4; --k) {
+      const int j = ch[k];
+      gp = qrot(gr, ld3(O.ik_pos[j])) + gp;
+      gr = qmul(gr, ld4(O.rot[j]));
+    }
+    const DQ r_rootb = gr;
+    const D3 p_hip = qrot(gr, ld3(O.ik_pos[hip])) + gp;
+    const DQ r_hip = qmul(gr, ld4(O.rot[hip]));
+    const D3 p_knee = qrot(r_hip, ld3(O.ik_pos[knee])) + p_hip;
+    const DQ r_knee = qmul(r_hip, ld4(O.rot[knee]));
+    const D3 p_heel = qrot(r_knee, ld3(O.ik_pos[heel])) + p_knee;
+    const DQ r_heel = qmul(r_knee, ld4(O.rot[heel]));
+    const D3 p_toe = qrot(r_heel, ld3(O.ik_pos[toe])) + p_heel;
+    ContactState c;
+    c.state = S.contact_state[f] != 0; c.lock = S.contact_lock[f] != 0;
+    c.position = ld3(S.contact_position[f]); c.velocity = ld3(S.contact_velocity[f]);
+    c.point = ld3(S.contact_point[f]); c.target = ld3(S.contact_target[f]);
+    c.off_pos = ld3(S.contact_offset_position[f]); c.off_vel = ld3(S.contact_offset_velocity[f]);
+    contact_update_dev(c, p_toe, contact_in, P.ik_unlock_radius, P.ik_foot_height, P.ik_blending_halflife, dt);
+    c.position.y = fmax(c.position.y, P.ik_foot_height);   // aliases contact_positions[bs] in the reference (:581-582)
+    S.contact_state[f] = c.state; S.contact_lock[f] = c.lock;
+    st3(S.contact_position[f], c.position); st3(S.contact_velocity[f], c.velocity);
+    st3(S.contact_point[f], c.point); st3(S.contact_target[f], c.target);
+    st3(S.contact_offset_position[f], c.off_pos); st3(S.contact_offset_velocity[f], c.off_vel);
+
+    const D3 target = c.position + (p_heel - p_toe);
+    const D3 fwd = qrot(r_knee, v3<double>(0.0, 1.0, 0.0));
+    DQ new_hip, new_knee;
+    ik_two_bone_dev(p_hip, p_knee, p_heel, target, fwd, r_hip, r_knee, r_rootb, P.ik_max_length_buffer, new_hip, new_knee);
+    st4(O.ik_rot[hip], new_hip);
+    st4(O.ik_rot[knee], new_knee);
+  }
+  __syncwarp();
+
+  // carry state
+  if (lane == 0) { st3(S.root_pos, ld3(O.blend_pos[0])); st4(S.root_rot, rootrot); }
+  for (int j = lane; j < J; j += 32)
+    for (int c = 0; c < 3; ++c) { S.prev_pos[j][c] = O.blend_pos[j][c]; S.prev_ik_pos[j][c] = O.ik_pos[j][c]; }
+  __syncwarp();
+  double2* Og = reinterpret_cast<double2*>(outs + b);
+  for (int i = lane; i < PF_O16; i += 32) Og[i] = reinterpret_cast<const double2*>(&Osh)[i];
+  double2* Sw = reinterpret_cast<double2*>(states + b);
+  for (int i = lane; i < PF_S16; i += 32) Sw[i] = reinterpret_cast<const double2*>(&Ssh)[i];
+}
+
+// ------------------------------------------------------------------------------------------------
 // batched stand-alone versions (API completeness + unit parity tests)
 // ------------------------------------------------------------------------------------------------
 __global__ void contact_update_kernel(int32_t* state, int32_t* lock, double* position, double* velocity,
@@ -734,8 +941,16 @@ int post_frame_launch(const mocha_post_params* params, const float* Y, const flo
     MOCHA_CHECK_ARG(params->contact_bones[f] > 0 && params->contact_bones[f] < params->J && depth >= 4,
                     "mocha_post_frame: contact bone %d needs 4 ancestors", params->contact_bones[f]);
   }
-  launch_k(post_frame_kernel, nblk((long long)B * 32, 128), 128, 0, (cudaStream_t)stream, *params, Y, src_hips_vel, src_rvel, src_rang,
-                                                                 contacts, B, T, V, Cin, init, state, out, hv_stride, rv_stride);
+  // steady state: the latency-shaped kernel (shared-memory structs, one load round); frame 0 and unaligned struct arrays
+  // take the general kernel
+  static const bool no_step_kernel = getenv("MOCHA_NO_POST_STEP_KERNEL") != nullptr;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(state) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  if (!init && aligned && !no_step_kernel && V * Cin <= PF_YMAX)
+    launch_k(post_frame_step_kernel, B, 32, 0, (cudaStream_t)stream, *params, Y, src_hips_vel, src_rvel, src_rang, contacts, T, V,
+             Cin, state, out, hv_stride, rv_stride);
+  else
+    launch_k(post_frame_kernel, nblk((long long)B * 32, 128), 128, 0, (cudaStream_t)stream, *params, Y, src_hips_vel, src_rvel, src_rang,
+                                                                   contacts, B, T, V, Cin, init, state, out, hv_stride, rv_stride);
   count_launch();
   MOCHA_LAUNCH_CHECK("post_frame_kernel");
   return MOCHA_OK;
