@@ -136,7 +136,7 @@ typedef struct {
   const float* tm_jb_tcn_w; const float* tm_jb_tcn_b; /* [C0, taps_j*C0], [C0] */
   const float* tm_out_w; const float* tm_out_b;       /* .6 [Cin, C0], [Cin] */
   /* optional (tensor-core path): jb_gcn_w with the per-partition biases folded in as Kj extra K columns that
-     multiply the adjacency column sums, K padded to a multiple of 64: [D, jb_gcn_kaug]; NULL = not provided */
+     multiply the adjacency column sums, K padded to a multiple of 16: [D, jb_gcn_kaug]; NULL = not provided */
   const float* jb_gcn_w_aug;
   int jb_gcn_kaug;
 } mocha_generator_weights;

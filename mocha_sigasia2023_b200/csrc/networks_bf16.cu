@@ -123,7 +123,7 @@ int embed_bf16(const mocha_generator_weights* w, const float* X, int B, float* t
   bf16* g2 = ws.take<bf16>((size_t)R2 * d.D);
   WS_OK(ws, "mocha_embed_fwd(bf16)");
   const int KC = d.Kj * d.C0;
-  if (w->jb_gcn_w_aug && w->jb_gcn_kaug >= KC + d.Kj && w->jb_gcn_kaug % 64 == 0 && (d.taps_j & 1)) {
+  if (w->jb_gcn_w_aug && w->jb_gcn_kaug >= KC + d.Kj && w->jb_gcn_kaug % 16 == 0 && (d.taps_j & 1)) {
     // bias folded into the GEMM (Kj extra K columns x adjacency column sums) -> plain single-pass epilogue,
     // and the GEMM's TMA stores land directly in the interior of the temporal conv's reflect-padded input
     const int Ka = w->jb_gcn_kaug, pad = d.taps_j / 2, Tpad = d.T + 2 * pad;
