@@ -779,8 +779,8 @@ def hbm_kernels(sess, torch, lib, _lib):
     par = kin.parents_tensor(skeleton.BONE_PARENTS, dev)
     lrot = torch.randn((F, 25, 4), device=dev); lpos = torch.randn((F, 25, 3), device=dev)
     lvel = torch.randn((F, 25, 3), device=dev); lang = torch.randn((F, 25, 3), device=dev)
-    for name, fn, per in (("fk_kernel (16 clips x 225 windows x 60 frames)", lambda: kin.fk(lrot, lpos, par), 25 * 7 * 4 * 2),
-                          ("fk_kernel<WITH_VEL> (fk_vel)", lambda: kin.fk_vel(lrot, lpos, lvel, lang, par), 25 * 13 * 4 * 2)):
+    for name, fn, per in (("fk_rows_kernel (thread per skeleton, bulk-copy slabs; 16 clips x 225 windows x 60 frames)", lambda: kin.fk(lrot, lpos, par), 25 * 7 * 4 * 2),
+                          ("fk_rows_kernel<WITH_VEL> (fk_vel)", lambda: kin.fk_vel(lrot, lpos, lvel, lang, par), 25 * 13 * 4 * 2)):
         ms = timed(torch, fn, 10)
         out.append({"kernel": name, "ms_per_launch": ms, "bytes_per_launch": F * per, "achieved": F * per / ms / 1e6, "peak": peak,
                     "unit": "GB/s", "frac": F * per / ms / 1e6 / peak})

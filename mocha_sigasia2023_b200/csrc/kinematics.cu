@@ -230,6 +230,140 @@ fk_kernel(const T* __restrict__ lrot, const T* __restrict__ lpos, const T* __res
   }
 }
 
+// Streaming fp32 FK for large batches (window feature extraction runs it over clips x windows x frames skeletons): one
+// THREAD per skeleton instead of one warp. The level-synchronous walk above keeps 25 lanes busy for one joint level at a
+// time, round-trips through shared memory per level and stages with 4-byte loops (0.18 of the HBM roof; ncu: issue-bound).
+// Here a warp owns 32 consecutive skeletons, whose inputs are contiguous slabs of the global arrays: each slab arrives with
+// ONE bulk copy (cp.async.bulk, completion on the warp's mbarrier) in its global layout, every lane walks its skeleton's
+// joints in index order in place (parents precede children, so joint j's parent is already global; same expressions as
+// above; quaternions move as 16-byte vectors - conflict-free at any row stride - and the 3-vectors as scalars, whose row
+// stride 3 J is odd for the 25-bone skeleton), and each slab leaves with one bulk store. No staging loops at all: the
+// instruction stream is the quaternion algebra. Warps of an SM sit in different phases, which overlaps one warp's
+// copies with another's walk. A last, partly filled group (slab sizes not multiples of 16 bytes) uses element loops.
+__device__ __forceinline__ void fk_bulk_in(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fk_bulk_out(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
+template <bool WITH_VEL, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+fk_rows_kernel(const float* __restrict__ lrot, const float* __restrict__ lpos, const float* __restrict__ lvel,
+               const float* __restrict__ lang, const int32_t* __restrict__ parents, long long F, int J,
+               float* __restrict__ grot, float* __restrict__ gpos, float* __restrict__ gvel, float* __restrict__ gang) {
+  pdl_trigger();
+  extern __shared__ __align__(16) float fk_sm[];
+  __shared__ int32_t par[MAXJ];
+  __shared__ __align__(8) unsigned long long bars[WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n4 = J * 4, n3 = J * 3;
+  const int per_warp = 32 * (n4 + n3 * (WITH_VEL ? 3 : 1));
+  float* rot = fk_sm + warp * per_warp;
+  float* pos = rot + 32 * n4;
+  float* vel = pos + 32 * n3;
+  float* ang = vel + 32 * n3;
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&bars[warp]);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pdl_wait();
+  if (threadIdx.x < J) par[threadIdx.x] = parents[threadIdx.x];
+  __syncthreads();
+  uint32_t parity = 0;
+  const long long groups = (F + 31) / 32;
+  for (long long grp = (long long)blockIdx.x * WARPS + warp; grp < groups; grp += (long long)gridDim.x * WARPS) {
+    const long long f0 = grp * 32;
+    const int cnt = (int)min(32LL, F - f0);
+    const bool full = cnt == 32;     // warp-uniform
+    if (full) {
+      if (lane == 0) {
+        // the previous group's bulk stores have finished reading this warp's buffers
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        const uint32_t b4 = 32u * n4 * 4u, b3 = 32u * n3 * 4u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(b4 + b3 * (WITH_VEL ? 3u : 1u)) : "memory");
+        fk_bulk_in((uint32_t)__cvta_generic_to_shared(rot), lrot + f0 * n4, b4, bar);
+        fk_bulk_in((uint32_t)__cvta_generic_to_shared(pos), lpos + f0 * n3, b3, bar);
+        if (WITH_VEL) {
+          fk_bulk_in((uint32_t)__cvta_generic_to_shared(vel), lvel + f0 * n3, b3, bar);
+          fk_bulk_in((uint32_t)__cvta_generic_to_shared(ang), lang + f0 * n3, b3, bar);
+        }
+      }
+      uint32_t done = 0;
+      while (!done)
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+      parity ^= 1u;
+    } else {
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+      for (int i = lane; i < cnt * n4; i += 32) rot[i] = lrot[f0 * n4 + i];
+      for (int i = lane; i < cnt * n3; i += 32) pos[i] = lpos[f0 * n3 + i];
+      if (WITH_VEL) {
+        for (int i = lane; i < cnt * n3; i += 32) { vel[i] = lvel[f0 * n3 + i]; ang[i] = lang[f0 * n3 + i]; }
+      }
+      __syncwarp();
+    }
+    if (lane < cnt) {
+      float4* r = reinterpret_cast<float4*>(rot + lane * n4);
+      float* x = pos + lane * n3;
+      float* v = vel + lane * n3;
+      float* a = ang + lane * n3;
+      // quat.fk / quat.fk_vel (motion/quat.py:166-204)
+      for (int j = 0; j < J; ++j) {
+        const int p = par[j];
+        if (p < 0) continue;            // a root's global transform is its local one
+        const float4 lr4 = r[j], pr4 = r[p];
+        const Q4<float> lr = q4<float>(lr4.x, lr4.y, lr4.z, lr4.w);
+        const Q4<float> pr = q4<float>(pr4.x, pr4.y, pr4.z, pr4.w);
+        const V3<float> lp = v3<float>(x[3 * j], x[3 * j + 1], x[3 * j + 2]);
+        const V3<float> pp = v3<float>(x[3 * p], x[3 * p + 1], x[3 * p + 2]);
+        const V3<float> rp = qrot(pr, lp);
+        const V3<float> gp = rp + pp;
+        const Q4<float> gr = qmul(pr, lr);
+        x[3 * j] = gp.x; x[3 * j + 1] = gp.y; x[3 * j + 2] = gp.z;
+        r[j] = make_float4(gr.w, gr.x, gr.y, gr.z);
+        if (WITH_VEL) {
+          const V3<float> lv = v3<float>(v[3 * j], v[3 * j + 1], v[3 * j + 2]);
+          const V3<float> la = v3<float>(a[3 * j], a[3 * j + 1], a[3 * j + 2]);
+          const V3<float> pv = v3<float>(v[3 * p], v[3 * p + 1], v[3 * p + 2]);
+          const V3<float> pa = v3<float>(a[3 * p], a[3 * p + 1], a[3 * p + 2]);
+          const V3<float> gv = qrot(pr, lv) + cross(pa, rp) + pv;
+          const V3<float> ga = qrot(pr, la) + pa;
+          v[3 * j] = gv.x; v[3 * j + 1] = gv.y; v[3 * j + 2] = gv.z;
+          a[3 * j] = ga.x; a[3 * j + 1] = ga.y; a[3 * j + 2] = ga.z;
+        }
+      }
+    }
+    if (full) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t b4 = 32u * n4 * 4u, b3 = 32u * n3 * 4u;
+        fk_bulk_out(grot + f0 * n4, (uint32_t)__cvta_generic_to_shared(rot), b4);
+        fk_bulk_out(gpos + f0 * n3, (uint32_t)__cvta_generic_to_shared(pos), b3);
+        if (WITH_VEL) {
+          fk_bulk_out(gvel + f0 * n3, (uint32_t)__cvta_generic_to_shared(vel), b3);
+          fk_bulk_out(gang + f0 * n3, (uint32_t)__cvta_generic_to_shared(ang), b3);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    } else {
+      __syncwarp();
+      for (int i = lane; i < cnt * n4; i += 32) grot[f0 * n4 + i] = rot[i];
+      for (int i = lane; i < cnt * n3; i += 32) gpos[f0 * n3 + i] = pos[i];
+      if (WITH_VEL) {
+        for (int i = lane; i < cnt * n3; i += 32) { gvel[f0 * n3 + i] = vel[i]; gang[f0 * n3 + i] = ang[i]; }
+      }
+      __syncwarp();
+    }
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // quat.ik (motion/quat.py:175-187)
 template <typename T>
 __global__ void __launch_bounds__(FK_WARPS * 32)
@@ -890,12 +1024,45 @@ static unsigned fk_grid(long long F) {
   return (unsigned)(g < cap ? g : cap);
 }
 
+// thread-per-skeleton streaming kernel for batches that fill the GPU (>= 4096 skeletons); the warp-per-skeleton kernel keeps
+// the small calls (a frame's clips), where parallelism inside the skeleton is all there is. MOCHA_NO_FK_ROWS=1 disables it.
+static bool fk_rows_wanted(long long F, int J, const void* a = nullptr, const void* b = nullptr, const void* c = nullptr,
+                           const void* d = nullptr, const void* e = nullptr, const void* f = nullptr, const void* g = nullptr,
+                           const void* h = nullptr) {
+  static const bool off = getenv("MOCHA_NO_FK_ROWS") != nullptr;
+  const uintptr_t all = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+                        reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(e) | reinterpret_cast<uintptr_t>(f) |
+                        reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(h);
+  return !off && F >= 4096 && J >= 1 && J <= MAXJ && (all & 15) == 0;   // bulk copies move 16-byte aligned slabs
+}
+template <bool WITH_VEL, int WARPS>
+static int fk_rows_launch(const float* lrot, const float* lpos, const float* lvel, const float* lang, const int32_t* parents,
+                          long long F, int J, float* grot, float* gpos, float* gvel, float* gang, cudaStream_t s) {
+  const size_t smem = (size_t)WARPS * 32 * (J * 4 + J * 3 * (WITH_VEL ? 3 : 1)) * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    MOCHA_CUDA(cudaFuncSetAttribute(fk_rows_kernel<WITH_VEL, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  const long long blocks = ((F + 31) / 32 + WARPS - 1) / WARPS;
+  const long long resident = (long long)sms * (long long)max(1, (int)((220 * 1024) / (smem + 1024)));
+  launch_k(fk_rows_kernel<WITH_VEL, WARPS>, (unsigned)min(blocks, resident), WARPS * 32, smem, s, lrot, lpos, lvel, lang, parents, F, J,
+           grot, gpos, gvel, gang);
+  return MOCHA_OK;
+}
+
 extern "C" int mocha_fk(const float* lrot, const float* lpos, const int32_t* parents, long long F, int J, float* grot,
                         float* gpos, mocha_stream_t stream) {
   MOCHA_CHECK_ARG(lrot && lpos && grot && gpos && F > 0, "mocha_fk: bad argument");
   MOCHA_TRY(check_parents_arg(parents, J));
-  launch_k(fk_kernel<false, float>, fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream, lrot, lpos, nullptr, nullptr, parents, F, J,
-                                                                          grot, gpos, nullptr, nullptr);
+  if (fk_rows_wanted(F, J, lrot, lpos, grot, gpos)) {
+    MOCHA_TRY((fk_rows_launch<false, 8>(lrot, lpos, nullptr, nullptr, parents, F, J, grot, gpos, nullptr, nullptr, (cudaStream_t)stream)));
+  } else {
+    launch_k(fk_kernel<false, float>, fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream, lrot, lpos, nullptr, nullptr, parents, F, J,
+                                                                            grot, gpos, nullptr, nullptr);
+  }
   count_launch();
   MOCHA_LAUNCH_CHECK("fk_kernel");
   return MOCHA_OK;
@@ -906,8 +1073,12 @@ extern "C" int mocha_fk_vel(const float* lrot, const float* lpos, const float* l
                             float* gang, mocha_stream_t stream) {
   MOCHA_CHECK_ARG(lrot && lpos && lvel && lang && grot && gpos && gvel && gang && F > 0, "mocha_fk_vel: bad argument");
   MOCHA_TRY(check_parents_arg(parents, J));
-  launch_k(fk_kernel<true, float>, fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream, lrot, lpos, lvel, lang, parents, F, J, grot,
-                                                                         gpos, gvel, gang);
+  if (fk_rows_wanted(F, J, lrot, lpos, lvel, lang, grot, gpos, gvel, gang)) {
+    MOCHA_TRY((fk_rows_launch<true, 5>(lrot, lpos, lvel, lang, parents, F, J, grot, gpos, gvel, gang, (cudaStream_t)stream)));
+  } else {
+    launch_k(fk_kernel<true, float>, fk_grid(F), FK_WARPS * 32, 0, (cudaStream_t)stream, lrot, lpos, lvel, lang, parents, F, J, grot,
+                                                                           gpos, gvel, gang);
+  }
   count_launch();
   MOCHA_LAUNCH_CHECK("fk_vel_kernel");
   return MOCHA_OK;

@@ -56,6 +56,29 @@ def test_fk_family(gkin):
     close(gr2[0, -37:], gkin["fk_grot"]); close(gp2[0, :37], gkin["fk_gpos"])
 
 
+def test_fk_streaming_kernel_large_ragged_batch():
+    """Batches of >= 4096 skeletons take the thread-per-skeleton streaming kernel (fk_rows_kernel): a ragged size (last warp
+    group partly filled) against the oracle's fk / fk_vel (motion/quat.py:166-204) in float64."""
+    from mocha_oracle import rot as orot
+    rng = np.random.default_rng(5)
+    F, J = 4096 + 32 * 7 + 21, len(skeleton.BONE_PARENTS)
+    lrot = rng.standard_normal((F, J, 4)); lrot /= np.linalg.norm(lrot, axis=-1, keepdims=True)
+    lpos = rng.standard_normal((F, J, 3)); lvel = rng.standard_normal((F, J, 3)); lang = rng.standard_normal((F, J, 3))
+    par = kin.parents_tensor(skeleton.BONE_PARENTS, "cuda")
+    f32 = lambda x: cu(x.astype(np.float32))
+    want = orot.fk_vel(lrot.astype(np.float32).astype(np.float64), lpos.astype(np.float32).astype(np.float64),
+                       lvel.astype(np.float32).astype(np.float64), lang.astype(np.float32).astype(np.float64),
+                       list(skeleton.BONE_PARENTS))
+    gr, gp = kin.fk(f32(lrot), f32(lpos), par)
+    close(gr, want[0], 1e-4, 5e-5); close(gp, want[1], 1e-4, 5e-5)
+    g4 = kin.fk_vel(f32(lrot), f32(lpos), f32(lvel), f32(lang), par)
+    for a, w in zip(g4, want):
+        close(a, w, 1e-4, 2e-4)
+    # and the two kernels agree on a prefix small enough for the warp-per-skeleton kernel
+    gr_s, gp_s = kin.fk(f32(lrot[:1000]), f32(lpos[:1000]), par)
+    close(gr[:1000], gr_s.cpu().numpy(), 1e-5, 1e-5); close(gp[:1000], gp_s.cpu().numpy(), 1e-5, 1e-5)
+
+
 def test_two_bone_ik(gkin):
     t = gi.kin_inputs()["ik2"]
     a, b = kin.ik_two_bone(*[cu(t[k]) for k in ("root", "mid", "end", "target", "fwd", "root_gr", "mid_gr", "par_gr")],
