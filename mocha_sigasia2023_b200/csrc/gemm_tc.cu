@@ -17,6 +17,7 @@
 #include "gemm_tc.cuh"
 
 #include <mutex>
+#include <type_traits>
 #include <vector>
 #include "gemm_f32.cuh"
 #include "ops.cuh"
@@ -1095,6 +1096,25 @@ struct TcSmem {
 };
 
 
+// Halo variant of the temporal convolution (HALO = true; 64 input channels, 5 taps, 24 rows per frame): the taps of one
+// output tile read the SAME rows shifted by multiples of 24, so the general kernel fetches every activation row five times
+// from L2 and the conv was bound by L2 -> SM traffic (ncu: 189 MB at 5.9 TB/s for a 24 MB tensor, tensor pipe 11 %).
+// Here one TMA box of 128 + 4 x 24 = 224 rows lands per tile and tap t's A operand is that box at byte offset
+// t x 24 x 128 = t x 3 KB - a whole number of 8-row swizzle atoms, so the UMMA descriptor just starts three atoms later -
+// and the weights (5 taps x BN rows x 128 B) are loaded once per CTA and stay resident.
+constexpr int HALO_TAPS = 5, HALO_SHIFT = 24, HALO_ROWS = BLOCK_M + (HALO_TAPS - 1) * HALO_SHIFT;
+static_assert((HALO_SHIFT * 128) % 1024 == 0, "tap shifts must be whole swizzle atoms");
+template <int BN, int EPI_BYTES>
+struct HaloSmem {
+  static constexpr int W_BYTES = HALO_TAPS * BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = HALO_ROWS * BLOCK_K * 2;
+  static constexpr int FIXED = 1024 /*alignment slack*/ + 256 /*barriers*/ + EPI_BYTES + W_BYTES;
+  static constexpr int FIT = (SMEM_LIMIT - FIXED) / STAGE_BYTES;
+  static constexpr int STAGES = FIT > 6 ? 6 : FIT;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + FIXED;
+  static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
+};
+
 // Register re-partition between the producer warpgroup and the two epilogue warpgroups (see TC_EPI_WARP0): warpgroup-
 // uniform, executed by every warp of the CTA once the prologue is done.
 __device__ __forceinline__ void tc_regs_producer() {
@@ -1108,24 +1128,28 @@ __device__ __forceinline__ void tc_regs_epilogue() {
 #endif
 }
 
-template <int BN, class Epi>
+template <int BN, class Epi, bool HALO = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcShape sh, const int num_kb, const __grid_constant__ Epi epi) {
-  using SM = TcSmem<BN, Epi::kStageBytes>;
+  using SM = typename std::conditional<HALO, HaloSmem<BN, Epi::kStageBytes>, TcSmem<BN, Epi::kStageBytes>>::type;
   constexpr int STAGES = SM::STAGES;
   constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   constexpr int KELEMS = Epi::kTf32 ? 32 : BLOCK_K;  // elements per 128-byte k-block row
+  constexpr int W_RESIDENT = HALO ? HALO_TAPS * BN * BLOCK_K * 2 : 0;
+  static_assert(!HALO || !Epi::kTf32, "the halo variant is bf16 only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  // [operand stages][epilogue staging (1 KB aligned: stage sizes are multiples of 1 KB)][barriers]
-  uint8_t* epi_stage = smem + STAGES * SM::STAGE_BYTES;
+  // [operand stages][resident weights (HALO)][epilogue staging (1 KB aligned: stage sizes are multiples of 1 KB)][barriers]
+  uint8_t* wres = smem + STAGES * SM::STAGE_BYTES;
+  uint8_t* epi_stage = wres + W_RESIDENT;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + Epi::kStageBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
   uint64_t* res_bar = tempty_bar + 2;         // [EPI_WARPS] residual-prefetch barriers (LinearEpi)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + EPI_WARPS);
+  uint64_t* w_bar = res_bar + EPI_WARPS;      // resident weights landed (HALO)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_trigger();
@@ -1141,6 +1165,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_WARPS); }
     for (int i = 0; i < EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
+    mbar_init(w_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -1160,7 +1185,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_regs_producer();
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (HALO && lane == 0) {
+      // weights: constants, but read after the grid dependency like every other global read of the kernel
+      mbar_expect_tx(w_bar, (uint32_t)W_RESIDENT);
+#pragma unroll
+      for (int tap = 0; tap < HALO_TAPS; ++tap)
+        tma_load_2d(wres + tap * BN * BLOCK_K * 2, &tmB, w_bar, tap * BLOCK_K, 0);
+      int stage = 0; uint32_t phase = 0;
+      for (int u = blockIdx.x; u < sh.units; u += gridDim.x) {
+        int mt, split;
+        decode_unit(sh, u, mt, split);
+        const int b = sh.nb == 1 ? 0 : fast_div(mt, sh.tiles_m_per_b), mtb = mt - b * sh.tiles_m_per_b;
+        const long long a_row0 = (long long)b * sh.src_rows_per_b + (long long)mtb * BLOCK_M;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
+        tma_load_2d(smem + stage * SM::STAGE_BYTES, &tmA, &full_bar[stage], 0, (int)a_row0);   // 224-row box: all five taps
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    } else if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int u = blockIdx.x; u < sh.units; u += gridDim.x) {
         int mt, split;
@@ -1218,7 +1260,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (HALO && lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_M, BN, 1u);
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      mbar_wait(w_bar, 0);
+      const uint32_t wb = smem_u32(wres);
+      for (int u = blockIdx.x; u < sh.units; u += gridDim.x) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        const uint32_t sa = smem_u32(smem + stage * SM::STAGE_BYTES);
+#pragma unroll
+        for (int tap = 0; tap < HALO_TAPS; ++tap) {
+          const uint64_t adesc = make_smem_desc(sa + (uint32_t)(tap * HALO_SHIFT * BLOCK_K * 2));
+          const uint64_t bdesc = make_smem_desc(wb + (uint32_t)(tap * BN * BLOCK_K * 2));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (tap | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        umma_commit(&tfull_bar[as]);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    } else if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BLOCK_M, BN, Epi::kTf32 ? 2u : 1u);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
@@ -1807,6 +1874,22 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcShape& sh,
   return MOCHA_OK;
 }
 
+// Halo variant (see HaloSmem): tmA boxes are HALO_ROWS x 64, tmB boxes BN x 64 over the [BN, taps * 64] weight; one n-tile.
+template <int BN, class Epi>
+int launch_tc_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcShape& sh, const Epi& epi, cudaStream_t s) {
+  using SM = HaloSmem<BN, Epi::kStageBytes>;
+  static bool configured = false;
+  if (!configured) {
+    MOCHA_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, Epi, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    configured = true;
+  }
+  const int grid = sh.units < num_sms() ? sh.units : num_sms();
+  launch_k(tc_gemm_kernel<BN, Epi, true>, grid, TC_THREADS, SM::TOTAL, s, tmA, tmB, sh, HALO_TAPS, epi);
+  count_launch();
+  MOCHA_LAUNCH_CHECK("tc_gemm_kernel(halo)");
+  return MOCHA_OK;
+}
+
 template <class Epi>
 int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcShape& sh, int num_kb, const Epi& epi,
                 cudaStream_t s) {
@@ -2374,6 +2457,23 @@ int tc_tconv_ex(const float* X, const __nv_bfloat16* Xh, const float* W, const f
     sp.group_m = 0;
     for (int it = 0; it < (repeat < 1 ? 1 : repeat) && rc == MOCHA_OK; ++it)
       rc = launch_pair(tmA, tmB, sp, taps * sh.kb_per_tap, LinearEpiT<1>{epi}, s);
+    ws.off = mark;
+    return rc;
+  }
+  // 64 -> 64 channels, 5 taps, 24 rows per frame (to_mot's JointBlock conv): one 224-row box per tile serves all taps and the
+  // weights stay resident (halo variant; MOCHA_NO_HALO_TCONV=1 keeps the general kernel)
+  static const bool no_halo = getenv("MOCHA_NO_HALO_TCONV") != nullptr;
+  if (!no_halo && epi.tma == 1 && !epi.C && epi.C16 && Cin == BLOCK_K && Cout == 64 && taps == HALO_TAPS && V == HALO_SHIFT &&
+      bias_period == 0 && sh.tiles_m_total >= num_sms()) {
+    CUtensorMap tmAh, tmB;
+    MOCHA_TRY(make_tmap(&tmAh, X16c, (unsigned long long)B * Tp * V, (unsigned long long)Cin, HALO_ROWS));
+    MOCHA_TRY(make_tmap(&tmB, W16, (unsigned long long)Cout, (unsigned long long)taps * Cin, 64));
+    TcShape sp = sh;
+    sp.tiles_n = 1; sp.tiles_per_unit = 1; sp.units = sp.tiles_m_total; sp.splits = 1; sp.group_m = 0;
+    LinearEpi e2 = epi;
+    e2.c16_wide = 0;   // a warp owns one 32-column chunk of the 64-wide tile
+    for (int it = 0; it < (repeat < 1 ? 1 : repeat) && rc == MOCHA_OK; ++it)
+      rc = launch_tc_halo<64, LinearEpiT<4>>(tmAh, tmB, sp, LinearEpiT<4>{e2}, s);
     ws.off = mark;
     return rc;
   }
