@@ -182,6 +182,26 @@ __device__ __forceinline__ void tmem_ld32_wait(uint32_t (&v)[32]) {
                :
                : "memory");
 }
+// lane = row of the accumulator, 64 consecutive fp32 columns in one instruction (the 64-column epilogue step)
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+      "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+      "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]),
+        "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]),
+        "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]),
+        "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]),
+        "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 
 // UMMA shared-memory descriptor, K-major operand in SWIZZLE_128B canonical layout:
 //   start address >> 4 | LBO (ignored for swizzled K-major, 1) | SBO = 1024 B (8 rows x 128 B)
@@ -423,6 +443,7 @@ struct LinearEpiT : LinearEpiData {
     uint32_t par;     // MODE 4: which of the two staging boxes the next chunk fills
   };
   static constexpr bool kM1 = MODE == 1 || MODE == 4;   // single-output TMA-store epilogue
+  static constexpr bool kWide64 = MODE == 4;            // has the 64-column step (chunk64) for bf16-only wide boxes
   static constexpr bool kDouble = MODE == 4;
   // per warp: 4 KB fp32 box [32][128 B] (128 B-swizzled, 1 KB aligned) + 2 KB bf16 box [32][64 B]
   // (64 B-swizzled) + 4 KB residual box (128 B-swizzled); the LSU path uses a [32][EPI_LD] float
@@ -768,6 +789,67 @@ struct LinearEpiT : LinearEpiData {
     EPI_DBG(13);
   }
 
+  // -DMOCHA_TC_WIDE64 (opt-in, measured NEGATIVE: 1.127 -> 1.138 ms/step at 128 clips, same-box A/B): 64-column step of the
+  // bf16-only wide-box path (MODE 4, c16_wide): ONE tcgen05.ld.x64 and one dependent chain - bias, activation, eight 16-byte
+  // staging stores, fence, one TMA store of the 128-byte-row box - per 64 columns instead of two chains of 32. Coarser steps
+  // lose more overlap between the warps of a scheduler than the saved load / fence latency gains.
+  __device__ __forceinline__ bool wide64() const { return kWide64 && c16_wide && !C && (bias_period == 0 || !bias); }
+  template <int ACT>
+  __device__ __forceinline__ void drain_tma64(State& st, const EpiCtx& e, int col0, const uint32_t (&v)[64]) const {
+    float f[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) f[j] = __uint_as_float(v[j]);
+    if (row_scale) {
+      const float rs = st.rs;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) f[j] *= rs;
+    }
+    if (bias) {
+      const uint32_t bs = e.bias_smem + (uint32_t)(col0 * 4);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float4 b4 = lds128(bs + 16u * j);   // same address in every lane: broadcast
+        f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
+      }
+    }
+    if (ACT != ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) f[j] = act_fn<ACT>(f[j]);
+    }
+    const uint32_t sbuf = e.stage + (kDouble ? st.par * 4096u : 0u);
+    if (e.lane == 0) { if (kDouble) bulk_wait_read1(); else bulk_wait_read0(); }
+    __syncwarp();
+    const int sw = e.lane & 7;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float a = f[8 * j + 2 * t], b = f[8 * j + 2 * t + 1];
+        if (c16_lrelu) { a = lrelu02(a); b = lrelu02(b); }
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+        pk[t] = *reinterpret_cast<uint32_t*>(&h2);
+      }
+      sts128(sbuf + (uint32_t)(e.lane * 128 + ((j ^ sw) << 4)), pk[0], pk[1], pk[2], pk[3]);
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (e.lane == 0) {
+      tma_store_3d(&tmC16w, sbuf, col0 + e.col_off, e.row0_in_img, e.img);
+      bulk_commit();
+    }
+    if (kDouble) st.par ^= 1u;
+  }
+  __device__ __forceinline__ void chunk64(State& st, const EpiCtx& e, int col0, const uint32_t (&v)[64]) const {
+    if (col0 >= N || e.slab_rows <= 0) return;
+    switch (act) {
+      case ACT_RELU: drain_tma64<ACT_RELU>(st, e, col0, v); break;
+      case ACT_GELU: drain_tma64<ACT_GELU>(st, e, col0, v); break;
+      case ACT_LRELU: drain_tma64<ACT_LRELU>(st, e, col0, v); break;
+      default: drain_tma64<ACT_NONE>(st, e, col0, v); break;
+    }
+  }
+
   // Residual GEMMs (x + f(x) feeding both an fp32 stream and a bf16 operand): the residual box is
   // TMA-prefetched one chunk ahead into a 128 B-swizzled buffer, so everything stays in the lane = row
   // layout of tcgen05.ld: v = act(v + bias) + res, fp32 box and 64 B-swizzled bf16 box, TMA stores.
@@ -949,6 +1031,7 @@ struct SoftmaxEpi {
   static constexpr uint64_t kHintA = 0, kHintB = 0;
   static constexpr bool kTf32 = false;
   static constexpr bool kWholeTile = true;
+  static constexpr bool kWide64 = false;
   __device__ __forceinline__ void unit_begin(State&) const {}
   __device__ __forceinline__ void kernel_begin(State&, const EpiCtx&) const {}
   __device__ __forceinline__ void tile_begin(State&, const EpiCtx&, int, int) const {}
@@ -1031,6 +1114,7 @@ struct MatchEpi {
   static constexpr int kWarpStageBytes = 0;
   static constexpr int kStageBytes = 0;
   static constexpr bool kWholeTile = false;
+  static constexpr bool kWide64 = false;
   // query tiles are re-read for every DB tile: keep them in L2; DB rows stream through once per group
   static constexpr uint64_t kHintA = L2_EVICT_LAST, kHintB = L2_EVICT_FIRST;
   struct State {
@@ -1423,6 +1507,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int c_stop = dbg_mode == 3 ? c_begin : c_end;
 #else
         const int c_stop = c_end;
+#endif
+#if defined(MOCHA_TC_WIDE64) && !defined(MOCHA_TC_TEN_WARPS) && !defined(MOCHA_TRACE)
+        bool done64 = false;
+        if constexpr (Epi::kWide64 && !HALO && BN >= 128) {
+          if (epi.wide64()) {   // bf16-only wide boxes: the warp's share (BN / 2 columns) goes out in 64-column steps
+#pragma unroll 1
+            for (int c0 = c_begin; c0 < c_stop; c0 += 64) {
+              uint32_t v64[64];
+              tmem_ld64(taddr + (uint32_t)c0, v64);
+              epi.chunk64(st, ectx, nt * BN + c0, v64);
+            }
+            done64 = true;
+          }
+        }
+        if (!done64)
 #endif
 #if !defined(MOCHA_TC_LD_PIPELINE) || defined(MOCHA_TC_TEN_WARPS) || defined(MOCHA_TRACE)
 #pragma unroll 1

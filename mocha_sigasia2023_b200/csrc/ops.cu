@@ -1045,11 +1045,50 @@ __device__ __forceinline__ void warp_matvec2(const __nv_bfloat16* __restrict__ W
                                     : ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1));
         const float bo = b ? __ldg(b + o) : 0.f;
         float r0 = (t0 + bo) * scale, r1 = (t1 + bo) * scale;
-        if (relu) { r0 = fmaxf(r0, 0.f); r1 = fmaxf(r1, 0.f); }
+        if (relu == 1) { r0 = fmaxf(r0, 0.f); r1 = fmaxf(r1, 0.f); }
+        else if (relu == 2) { r0 = lrelu02(r0); r1 = lrelu02(r1); }   // LeakyReLU(0.2)
         if (res) { r0 += res[o]; r1 += res[ldy + o]; }
         ys[o] = r0; ys[ldy + o] = r1;
       }
     }
+  }
+}
+
+// Two clips per block (opt-in: MOCHA_STYLE_MLP_TWO_CLIPS=1). With one clip per block the 128 blocks pull the same 1.5 MB of
+// weights from L2 each (197 MB in 26 us = 7.5 TB/s), so a weight row loaded once here serves two clips and the traffic halves.
+// Measured NEGATIVE in the frame (+2.8 us at 128 clips, same-box A/B): 64 blocks pull 1.5 MB each at the per-SM rate, which
+// takes as long as 128 blocks sharing the aggregate rate, and the launch overlaps the side stream's work either way.
+constexpr int STYLE2_THREADS = 512;
+__global__ void __launch_bounds__(STYLE2_THREADS, 1)
+style_mlp2_kernel(const float* __restrict__ cha, int n, const StyleMlpLayers L, int nlayers, float* __restrict__ gb, int B) {
+  constexpr int D = 256, NW = STYLE2_THREADS / 32;
+  pdl_trigger();
+  pdl_wait();
+  __shared__ __align__(16) float smean[2][D];
+  __shared__ __align__(16) float hid[2][2 * D];
+  const int b0 = 2 * blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  {
+    // token means: one thread per (clip, column), four independent partial sums (same pairing as style_mlp_kernel)
+    const int c = threadIdx.x & (D - 1), v = threadIdx.x >> 8;
+    const float* xb = cha + (long long)(b0 + v) * n * D + c;
+    float part[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float s0 = 0.f, s1 = 0.f;
+      int i = q;
+      for (; i + 4 < n; i += 8) { s0 += xb[(long long)i * D]; s1 += xb[(long long)(i + 4) * D]; }
+      for (; i < n; i += 4) s0 += xb[(long long)i * D];
+      part[q] = s0 + s1;
+    }
+    smean[v][c] = ((part[0] + part[1]) + (part[2] + part[3])) / (float)n;
+  }
+  __syncthreads();
+  for (int l = 0; l < nlayers; ++l) {
+    warp_matvec2<1, 8, 2>(L.w1[l], L.b1[l], &smean[0][0], D, &hid[0][0], 2 * D, nullptr, 2 * D, 2, 1.f, warp, NW, lane);
+    __syncthreads();
+    warp_matvec2<2, 4, 2>(L.w2[l], L.b2[l], &hid[0][0], 2 * D, gb + ((long long)l * B + b0) * 2 * D, 2 * D, nullptr, 2 * D, 0, 1.f,
+                          warp, NW, lane);
+    __syncthreads();
   }
 }
 
@@ -1961,7 +2000,11 @@ int style_mlp(const float* cha, int B, int n, int D, int nlayers, const __nv_bfl
     MOCHA_CHECK_ARG(w1[l] && w2[l] && aligned16(w1[l]) && aligned16(w2[l]), "style_mlp: layer %d weights missing / unaligned", l);
     L.w1[l] = w1[l]; L.b1[l] = b1[l]; L.w2[l] = w2[l]; L.b2[l] = b2[l];
   }
-  launch_k(style_mlp_kernel, B, STYLE_THREADS, 0, s, cha, n, L, nlayers, gb, B);
+  static const bool two_clips = getenv("MOCHA_STYLE_MLP_TWO_CLIPS") != nullptr;   // opt-in (measured negative, see the kernel)
+  if (two_clips && (B & 1) == 0 && B >= 64)
+    launch_k(style_mlp2_kernel, B / 2, STYLE2_THREADS, 0, s, cha, n, L, nlayers, gb, B);
+  else
+    launch_k(style_mlp_kernel, B, STYLE_THREADS, 0, s, cha, n, L, nlayers, gb, B);
   count_launch();
   MOCHA_LAUNCH_CHECK("style_mlp");
   return MOCHA_OK;
