@@ -1715,7 +1715,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const long long a_row0 = (long long)b * sh.src_rows_per_b + (long long)mtb * 256 + (int)rank * 128;
         const int nt_end = min(sh.tiles_n, (split + 1) * sh.tiles_per_unit);
         for (int nt = split * sh.tiles_per_unit; nt < nt_end; ++nt) {
-          const int b_row0 = nt * BN + (int)rank * 128;
+          const int b_row0 = nt * BN + (int)rank * 128 + (sh.H > 0 ? b * (int)sh.b_rows_b : 0);   // H > 0: one weight per image
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * M2_STAGE_BYTES;
@@ -2207,6 +2207,26 @@ const __nv_bfloat16* tc_lookup_bf16(const float* W) {
   return nullptr;
 }
 
+namespace {
+// plain / image-batched linear layers on the CTA-pair kernel: single TMA-stored output, column bias or none, whole 256-wide n-tiles
+bool pair_linear_wanted(const LinearEpi& epi, int rows_per_img, int nb, int N, int bias_period) {
+  static const bool off = getenv("MOCHA_NO_PAIR_LINEAR") != nullptr;
+  return !off && epi.tma == 1 && N % 256 == 0 && bias_period == 0 &&
+         (long long)ceil_div(rows_per_img, 256) * nb * (N / 256) >= num_sms() / 4;
+}
+TcShape pair_shape(const TcShape& sh, int rows_per_img, int nb, int N) {
+  TcShape sp = sh;
+  sp.tiles_m_per_b = ceil_div(rows_per_img, 256);
+  sp.tiles_m_total = sp.tiles_m_per_b * nb;
+  sp.tiles_n = N / 256;
+  sp.tiles_per_unit = 1;
+  sp.units = sp.tiles_m_total * sp.tiles_n;
+  sp.splits = sp.tiles_n;
+  sp.group_m = 0;
+  return sp;
+}
+}  // namespace
+
 int tc_linear_bf16(const __nv_bfloat16* A16, int lda, const __nv_bfloat16* W16, const float* bias, int bias_period,
                    const float* res, TcOut out, int M, int N, int K, int act, cudaStream_t s) {
   MOCHA_CHECK_ARG(A16 && W16 && (out.f32 || out.bf16), "tc_linear: null operand");
@@ -2224,6 +2244,15 @@ int tc_linear_bf16(const __nv_bfloat16* A16, int lda, const __nv_bfloat16* W16, 
   sh.tap_row_stride = 0;
   LinearEpi epi{out.f32, N, N, bias, bias_period, res, act, out.bf16, out.lrelu};
   MOCHA_TRY(setup_out_tma(epi, (unsigned long long)M, 1));
+  // CTA pairs (256 x 256 pair tiles, each CTA stages half of the weight rows) for the plain projections too: a 128 x 256 tile
+  // of a K = 256 layer pulls 192 KB of operands per CTA from L2, a pair tile 128 KB, and these short-K launches turned out to
+  // be sensitive to exactly that (same-box A/B: -15 us per step; 128-wide tiles, which re-read A twice as often: +28 us).
+  // MOCHA_NO_PAIR_LINEAR=1 keeps the 1-CTA kernel.
+  if (pair_linear_wanted(epi, M, 1, N, bias_period)) {
+    CUtensorMap tmB;
+    MOCHA_TRY(make_tmap(&tmB, W16, (unsigned long long)N, (unsigned long long)K, 128));
+    return launch_pair(tmA, tmB, pair_shape(sh, M, 1, N), ceil_div(K, BLOCK_K), LinearEpiT<1>{epi}, s);
+  }
   return dispatch_bn(pick_bn(sh.tiles_m_total, N, ceil_div(K, BLOCK_K)), tmA, W16, (unsigned long long)N, (unsigned long long)K, sh, N,
                      ceil_div(K, BLOCK_K), epi, s);
 }
@@ -2249,6 +2278,12 @@ int tc_linear_bf16_img(const __nv_bfloat16* A16, int lda, const __nv_bfloat16* W
   LinearEpi epi{out.f32, N, N, bias, 0, nullptr, act, out.bf16, out.lrelu};
   MOCHA_TRY(setup_out_tma(epi, (unsigned long long)rows_per_img, (unsigned long long)nb, 0, (unsigned long long)out_img_pitch_rows));
   if (epi.tma != 1) return set_error(MOCHA_ERR_ARG, "tc_linear_img: output is not TMA-storable");
+  static const bool no_pair_img = getenv("MOCHA_NO_PAIR_IMG") != nullptr;   // A/B switch (-9.5 us per step with the pair kernel)
+  if (!no_pair_img && pair_linear_wanted(epi, rows_per_img, nb, N, 0)) {
+    CUtensorMap tmB;
+    MOCHA_TRY(make_tmap(&tmB, W16, (unsigned long long)N, (unsigned long long)K, 128));
+    return launch_pair(tmA, tmB, pair_shape(sh, rows_per_img, nb, N), ceil_div(K, BLOCK_K), LinearEpiT<1>{epi}, s);
+  }
   return dispatch_bn(pick_bn(sh.tiles_m_total, N, ceil_div(K, BLOCK_K)), tmA, W16, (unsigned long long)N, (unsigned long long)K, sh, N,
                      ceil_div(K, BLOCK_K), epi, s);
 }
@@ -2275,6 +2310,12 @@ int tc_linear_bf16_grouped(const __nv_bfloat16* A16, const __nv_bfloat16* W16, _
   LinearEpi epi{nullptr, N, N, nullptr, 0, nullptr, ACT_NONE, out16, 0};
   MOCHA_TRY(setup_out_tma(epi, (unsigned long long)R, (unsigned long long)nb));
   if (epi.tma != 1) return set_error(MOCHA_ERR_ARG, "tc_linear_grouped: output is not TMA-storable");
+  static const bool no_pair_grp = getenv("MOCHA_NO_PAIR_GROUPED") != nullptr;   // A/B switch (-6.7 us per step with the pair kernel)
+  if (!no_pair_grp && pair_linear_wanted(epi, R, nb, N, 0)) {
+    CUtensorMap tmB;
+    MOCHA_TRY(make_tmap(&tmB, W16, (unsigned long long)nb * N, (unsigned long long)K, 128));
+    return launch_pair(tmA, tmB, pair_shape(sh, R, nb, N), ceil_div(K, BLOCK_K), LinearEpiT<1>{epi}, s);   // sh.H = 1: per-image weights
+  }
   return dispatch_bn(pick_bn(sh.tiles_m_total, N, ceil_div(K, BLOCK_K)), tmA, W16, (unsigned long long)nb * N, (unsigned long long)K, sh,
                      N, ceil_div(K, BLOCK_K), epi, s);
 }
