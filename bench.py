@@ -720,7 +720,7 @@ def kernel_rooflines(sess, torch, lib, _lib):
     ms = timed(torch, lambda: _lib.check(lib.mocha_linear(P(A), P(Wt), None, None, P(C32), R, 1536, 256, 0, _lib.MOCHA_BF16, P(ws),
                                                           ws.numel(), _lib.stream_ptr()), "mocha_linear"), 20)
     fl = 2.0 * R * 1536 * 256
-    out.append({"kernel": "cast + tc_gemm_kernel<256, LinearEpiT<4>> (QKV projection shape 11520 x 1536 x 256, fp32 in/out "
+    out.append({"kernel": "cast + tc_gemm2_kernel<LinearEpiT<1>> (CTA pairs; QKV projection shape 11520 x 1536 x 256, fp32 in/out "
                           "through mocha_linear: includes the bf16 cast of A)", "bound": "tensor", "ms_per_launch": ms,
                 "achieved": fl / ms / 1e9, "peak": peak, "unit": "TFLOP/s", "frac": fl / ms / 1e9 / peak, "flops_per_launch": fl})
     lib.mocha_register_bf16_blob(P(Wt), None, Wt.numel())
