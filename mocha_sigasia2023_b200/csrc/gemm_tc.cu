@@ -2208,10 +2208,11 @@ const __nv_bfloat16* tc_lookup_bf16(const float* W) {
 }
 
 namespace {
-// plain / image-batched linear layers on the CTA-pair kernel: single TMA-stored output, column bias or none, whole 256-wide n-tiles
+// plain / image-batched linear layers on the CTA-pair kernel: single TMA-stored output, whole 256-wide n-tiles
 bool pair_linear_wanted(const LinearEpi& epi, int rows_per_img, int nb, int N, int bias_period) {
   static const bool off = getenv("MOCHA_NO_PAIR_LINEAR") != nullptr;
-  return !off && epi.tma == 1 && N % 256 == 0 && bias_period == 0 &&
+  static const bool no_periodic = getenv("MOCHA_NO_PAIR_PERIODIC_BIAS") != nullptr;   // A/B switch: bias tables [period, N] (-7 us)
+  return !off && epi.tma == 1 && N % 256 == 0 && (bias_period == 0 || !no_periodic) &&
          (long long)ceil_div(rows_per_img, 256) * nb * (N / 256) >= num_sms() / 4;
 }
 TcShape pair_shape(const TcShape& sh, int rows_per_img, int nb, int N) {
