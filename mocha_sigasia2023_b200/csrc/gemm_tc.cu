@@ -2585,7 +2585,11 @@ int tc_tconv_ex(const float* X, const __nv_bfloat16* Xh, const float* W, const f
   // tiles: a CTA pair (cta_group::2) stages half of the weight rows each and runs 256 x 256 tiles
   static const bool no_pair = getenv("MOCHA_NO_PAIR_GEMM") != nullptr;
   const int pair_tiles = ceil_div(T * V, 256) * B;
-  if (!no_pair && epi.tma == 1 && Cout % 256 == 0 && taps * sh.kb_per_tap >= 8 && pair_tiles >= num_sms() / 2) {
+  // images shorter than a pair tile (BodyBlock convs: 90 rows per clip) would run 256-row tiles that are mostly padding:
+  // those keep the 1-CTA kernel's 128-row tiles (MOCHA_PAIR_SHORT_IMAGES=1 restores the pair kernel for them)
+  static const bool pair_short = getenv("MOCHA_PAIR_SHORT_IMAGES") != nullptr;
+  const bool pair_fill_ok = pair_short || ceil_div(T * V, 256) * 256 <= ceil_div(T * V, BLOCK_M) * BLOCK_M;
+  if (!no_pair && pair_fill_ok && epi.tma == 1 && Cout % 256 == 0 && taps * sh.kb_per_tap >= 8 && pair_tiles >= num_sms() / 2) {
     CUtensorMap tmB;
     MOCHA_TRY(make_tmap(&tmB, W16, (unsigned long long)Cout, (unsigned long long)taps * Cin, 128));
     TcShape sp = sh;
