@@ -1,6 +1,8 @@
 // Bandwidth/latency-bound building blocks (see ops.cuh for the reference citations).
 #include "ops.cuh"
 
+#include <cooperative_groups.h>
+
 namespace mocha {
 
 namespace {
@@ -993,7 +995,7 @@ struct PriorLastW {
 template <int KCH, int NV, int ITER>
 __device__ __forceinline__ void warp_matvec2(const __nv_bfloat16* __restrict__ W, const float* __restrict__ b, const float* xs,
                                              int ldx, float* ys, int ldy, const float* res, int N, int relu, float scale,
-                                             int warp, int nwarps, int lane) {
+                                             int warp, int nwarps, int lane, float* ys_mirror = nullptr) {
   constexpr int K = KCH * 256;
   float x[2][KCH * 8];
 #pragma unroll
@@ -1049,6 +1051,7 @@ __device__ __forceinline__ void warp_matvec2(const __nv_bfloat16* __restrict__ W
         else if (relu == 2) { r0 = lrelu02(r0); r1 = lrelu02(r1); }   // LeakyReLU(0.2)
         if (res) { r0 += res[o]; r1 += res[ldy + o]; }
         ys[o] = r0; ys[ldy + o] = r1;
+        if (ys_mirror) { ys_mirror[o] = r0; ys_mirror[ldy + o] = r1; }   // second copy (peer CTA's shared memory)
       }
     }
   }
@@ -1089,6 +1092,52 @@ style_mlp2_kernel(const float* __restrict__ cha, int n, const StyleMlpLayers L, 
     warp_matvec2<2, 4, 2>(L.w2[l], L.b2[l], &hid[0][0], 2 * D, gb + ((long long)l * B + b0) * 2 * D, 2 * D, nullptr, 2 * D, 0, 1.f,
                           warp, NW, lane);
     __syncthreads();
+  }
+}
+
+// Two clips per CLUSTER of two CTAs (default for even batches >= 64): the launch above is bound by the aggregate L2 -> SM
+// bandwidth (128 blocks x 1.5 MB of the same weights), and two clips per block only moved the bound to the per-SM load rate.
+// Here CTA r of the pair owns HALF of every layer's output features for both clips: it reads half of each weight matrix
+// (768 KB per CTA, 98 MB per launch), writes its half of the hidden vector into both CTAs' shared memory (DSMEM stores) and,
+// after a cluster barrier, produces its half of gamma | beta. Same summation order per output as style_mlp_kernel.
+constexpr int STYLEC_THREADS = 512;
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(STYLEC_THREADS, 1)
+style_mlp_cluster_kernel(const float* __restrict__ cha, int n, const StyleMlpLayers L, int nlayers, float* __restrict__ gb, int B) {
+  constexpr int D = 256, NW = STYLEC_THREADS / 32;
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  pdl_trigger();
+  pdl_wait();
+  __shared__ __align__(16) float smean[2][D];
+  __shared__ __align__(16) float hid[2][2 * D];
+  const int rank = (int)cluster.block_rank();
+  const int b0 = 2 * (int)(blockIdx.x >> 1), lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* peer_hid = cluster.map_shared_rank(&hid[0][0], rank ^ 1);
+  {
+    // token means of both clips in both CTAs (same pairing as style_mlp_kernel)
+    const int c = threadIdx.x & (D - 1), v = threadIdx.x >> 8;
+    const float* xb = cha + (long long)(b0 + v) * n * D + c;
+    float part[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float s0 = 0.f, s1 = 0.f;
+      int i = q;
+      for (; i + 4 < n; i += 8) { s0 += xb[(long long)i * D]; s1 += xb[(long long)(i + 4) * D]; }
+      for (; i < n; i += 4) s0 += xb[(long long)i * D];
+      part[q] = s0 + s1;
+    }
+    smean[v][c] = ((part[0] + part[1]) + (part[2] + part[3])) / (float)n;
+  }
+  __syncthreads();
+  for (int l = 0; l < nlayers; ++l) {
+    // hidden features [rank * D, (rank + 1) * D) of both clips -> both CTAs
+    warp_matvec2<1, 8, 2>(L.w1[l] + (size_t)rank * D * D, L.b1[l] + rank * D, &smean[0][0], D, &hid[0][0] + rank * D, 2 * D, nullptr,
+                          D, 2, 1.f, warp, NW, lane, peer_hid + rank * D);
+    cluster.sync();
+    // outputs [rank * D, (rank + 1) * D) of gamma | beta for both clips
+    warp_matvec2<2, 4, 2>(L.w2[l] + (size_t)rank * D * 2 * D, L.b2[l] + rank * D, &hid[0][0], 2 * D,
+                          gb + ((long long)l * B + b0) * 2 * D + rank * D, 2 * D, nullptr, D, 0, 1.f, warp, NW, lane);
+    cluster.sync();   // the peer has read this layer's hidden vector before the next layer overwrites it
   }
 }
 
@@ -2001,7 +2050,10 @@ int style_mlp(const float* cha, int B, int n, int D, int nlayers, const __nv_bfl
     L.w1[l] = w1[l]; L.b1[l] = b1[l]; L.w2[l] = w2[l]; L.b2[l] = b2[l];
   }
   static const bool two_clips = getenv("MOCHA_STYLE_MLP_TWO_CLIPS") != nullptr;   // opt-in (measured negative, see the kernel)
-  if (two_clips && (B & 1) == 0 && B >= 64)
+  static const bool no_cluster = getenv("MOCHA_NO_STYLE_MLP_CLUSTER") != nullptr;  // A/B switch
+  if (!two_clips && !no_cluster && (B & 1) == 0 && B >= 64)
+    launch_k(style_mlp_cluster_kernel, B, STYLEC_THREADS, 0, s, cha, n, L, nlayers, gb, B);
+  else if (two_clips && (B & 1) == 0 && B >= 64)
     launch_k(style_mlp2_kernel, B / 2, STYLE2_THREADS, 0, s, cha, n, L, nlayers, gb, B);
   else
     launch_k(style_mlp_kernel, B, STYLE_THREADS, 0, s, cha, n, L, nlayers, gb, B);
