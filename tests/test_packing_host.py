@@ -16,6 +16,19 @@ def _spatial_conv_ref(x, w, b, A):
     return np.einsum("nkctv,kvw->nctw", y, A)
 
 
+def test_augmented_weight_padding_switch(monkeypatch):
+    """MOCHA_GCN_KAUG_PAD picks the K padding of the augmented gcn weight: 16 by default (the GEMM's TMA boxes zero-fill
+    the rest of the last 64-column k-block), 64 = the dense layout; the payload columns are the same either way."""
+    sd = {k: v.detach().to(torch.float32) for k, v in weights.generator_state_dict(1777).items()}
+    w4, b, A = sd["mot_embedding.2.blk.gcn.conv.weight"], sd["mot_embedding.2.blk.gcn.conv.bias"], sd["mot_embedding.2.A_j"]
+    monkeypatch.delenv("MOCHA_GCN_KAUG_PAD", raising=False)
+    w16 = packing._gcn_first_aug(w4, b, A)
+    monkeypatch.setenv("MOCHA_GCN_KAUG_PAD", "64")
+    w64 = packing._gcn_first_aug(w4, b, A)
+    assert w16.shape[1] % 16 == 0 and w64.shape[1] % 64 == 0 and w16.shape[1] <= w64.shape[1]
+    assert torch.equal(w64[:, :w16.shape[1]], w16) and not w64[:, w16.shape[1]:].any()
+
+
 def test_gcn_first_and_augmented_weights_reproduce_spatial_conv():
     """_gcn_first (aggregate first, bias table) and _gcn_first_aug (biases as extra K columns multiplying
     the adjacency column sums, K padded to one tcgen05 K step of 16) are both the reference SpatialConv."""
